@@ -1,0 +1,583 @@
+/*
+ * sba_oracle.c -- CPU restatement of the reference hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This file is the parity checker for the CUDA product path.  It may be imported /
+ * linked / executed only by tests/, __graft_entry__.smoke() and the cpu_baseline /
+ * --impl reference legs of bench.py.  Nothing under spherical_bundle_adjuster_b200/
+ * links or calls it.
+ *
+ * Every function cites the reference file:line it restates (paths relative to the
+ * upstream repo whdlgp/spherical_bundle_adjuster).
+ *
+ * Pinning status (see DESIGN.md "Oracle"):
+ *   - remap / cube2equi : pinned against the REAL reference sources compiled into
+ *                         oracle/_ref (oracle/Makefile, cv shim headers) + golden files.
+ *   - matcher           : pinned bit-for-bit (indices AND fp32 distances) against
+ *                         cv2.BFMatcher(NORM_L2).knnMatch run in the build container;
+ *                         golden vectors under tests/golden/.
+ *   - BA functor / LM   : PARITY UNPINNED at the Ceres boundary (Ceres is not installed
+ *                         and the reference holds no BA test or golden number).  The
+ *                         restatement is validated against scipy (Rotation.from_rotvec,
+ *                         finite differences, least_squares(loss='huber')) instead.
+ *
+ * Plain C11, double precision wherever the reference is double.  OpenMP pragmas are only
+ * used so the same code can serve as the multi-threaded CPU baseline in bench.py.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <float.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+int orc_max_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+void orc_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Remap.  equi2cube.cpp:12-280 (six get_* functions) and :282-302 (get_all).
+ *
+ * Face ids follow the strip order of get_all (equi2cube.cpp:293-298):
+ *   0 left, 1 front, 2 right, 3 back, 4 top, 5 bottom.
+ * ---------------------------------------------------------------------------------------- */
+
+/* Cartesian direction of face pixel (row i, col j).  equi2cube.cpp:28-30 (back),
+ * :73-75 (front), :118-120 (left), :163-165 (right), :208-210 (top), :253-255 (bottom).
+ * i and j are doubles so cube2equi_pixel (equi2cube_surf.cpp:22-57) can share it. */
+static void face_cart(int face, double i, double j, double cs, double v[3])
+{
+    switch (face) {
+    case 0: /* left   */ v[0] = (cs - 2.0 * j) / cs; v[1] = 1.0;  v[2] = (cs - 2.0 * i) / cs; break;
+    case 1: /* front  */ v[0] = -1.0; v[1] = (cs - 2.0 * j) / cs; v[2] = (cs - 2.0 * i) / cs; break;
+    case 2: /* right  */ v[0] = (2.0 * j - cs) / cs; v[1] = -1.0; v[2] = (cs - 2.0 * i) / cs; break;
+    case 3: /* back   */ v[0] = 1.0;  v[1] = (2.0 * j - cs) / cs; v[2] = (cs - 2.0 * i) / cs; break;
+    case 4: /* top    */ v[0] = (cs - 2.0 * i) / cs; v[1] = (cs - 2.0 * j) / cs; v[2] = 1.0;  break;
+    default:/* bottom */ v[0] = (2.0 * i - cs) / cs; v[1] = (cs - 2.0 * j) / cs; v[2] = -1.0; break;
+    }
+}
+
+/* Direction -> (theta, phi).  equi2cube.cpp:32-44. */
+static void cart_to_rad(const double v[3], double *theta, double *phi)
+{
+    double n = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    double ux = v[0] / n, uy = v[1] / n, uz = v[2] / n;
+    *theta = acos(uz);
+    *phi = atan2(uy, ux);
+    if (*phi < 0) *phi += M_PI * 2;
+}
+
+/* Source index of one face pixel.  equi2cube.cpp:46-50.  The reference indexes
+ * im_data[row*w + col] with no bounds check; row can equal h at the bottom-face centre
+ * (theta == pi).  `clamped` (may be NULL) reports whether the clamp fired; the returned index
+ * is always in range so the oracle itself never reads out of bounds. */
+int32_t orc_equi2cube_src_index(int face, int i, int j, int cs, int w, int h, int *clamped)
+{
+    double v[3], theta, phi;
+    face_cart(face, (double)i, (double)j, (double)cs, v);
+    cart_to_rad(v, &theta, &phi);
+    int row = (int)(h * theta / M_PI);          /* Vec2i assignment truncates */
+    int col = (int)(w * phi / (2 * M_PI));
+    int c = 0;
+    if (row >= h) { row = h - 1; c = 1; }
+    if (col >= w) { col = w - 1; c = 1; }
+    if (row < 0) { row = 0; c = 1; }
+    if (col < 0) { col = 0; c = 1; }
+    if (clamped) *clamped = c;
+    return (int32_t)row * w + col;
+}
+
+/* Full index table in strip layout: lut[i*(6*cs) + face*cs + j].  Returns #clamped pixels. */
+int orc_equi2cube_lut(int cs, int w, int h, int32_t *lut)
+{
+    int nclamp = 0;
+#pragma omp parallel for reduction(+ : nclamp) schedule(static)
+    for (int i = 0; i < cs; i++)
+        for (int f = 0; f < 6; f++)
+            for (int j = 0; j < cs; j++) {
+                int c;
+                lut[(size_t)i * 6 * cs + (size_t)f * cs + j] = orc_equi2cube_src_index(f, i, j, cs, w, h, &c);
+                nclamp += c;
+            }
+    return nclamp;
+}
+
+/* One face, cs x cs x 3 bytes.  equi2cube.cpp:12-55 etc. */
+void orc_equi2cube_face(const uint8_t *im, int w, int h, int cs, int face, uint8_t *out)
+{
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < cs; i++)
+        for (int j = 0; j < cs; j++) {
+            int32_t s = orc_equi2cube_src_index(face, i, j, cs, w, h, NULL);
+            uint8_t *o = out + ((size_t)i * cs + j) * 3;
+            const uint8_t *p = im + (size_t)s * 3;
+            o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+        }
+}
+
+/* get_all: cs rows x 6cs cols x 3 bytes, faces left,front,right,back,top,bottom.
+ * equi2cube.cpp:282-302. */
+void orc_equi2cube_all(const uint8_t *im, int w, int h, int cs, uint8_t *strip)
+{
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < cs; i++)
+        for (int f = 0; f < 6; f++)
+            for (int j = 0; j < cs; j++) {
+                int32_t s = orc_equi2cube_src_index(f, i, j, cs, w, h, NULL);
+                uint8_t *o = strip + ((size_t)i * 6 * cs + (size_t)f * cs + j) * 3;
+                const uint8_t *p = im + (size_t)s * 3;
+                o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+            }
+}
+
+/* Strip keypoint -> ERP pixel (float in, double math, float out).
+ * equi2cube_surf.cpp:19-76.  xy_in / xy_out are n interleaved (x, y) float pairs. */
+void orc_cube2equi_points(const float *xy_in, int n, int cs, int w, int h, float *xy_out)
+{
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < n; k++) {
+        float px = xy_in[2 * k], py = xy_in[2 * k + 1];
+        double v[3];
+        /* Face selection by float comparison against integer multiples of cs
+         * (equi2cube_surf.cpp:22,28,34,40,46,52).  x<0 falls in the first branch (left),
+         * x>=5cs (including >=6cs) in the last (bottom), exactly as the if/else chain. */
+        int face;
+        if (px < cs) face = 0;
+        else if (px < 2 * cs) face = 1;
+        else if (px < 3 * cs) face = 2;
+        else if (px < 4 * cs) face = 3;
+        else if (px < 5 * cs) face = 4;
+        else face = 5;
+        /* (cube_pixel.x - k*cube_size) is float - int -> float, then 2.0* promotes. */
+        float fx = (face == 0) ? px : (px - (float)(face * cs));
+        face_cart(face, (double)py, (double)fx, (double)cs, v);
+        double theta, phi;
+        cart_to_rad(v, &theta, &phi);
+        xy_out[2 * k] = (float)(w * phi / (2 * M_PI));
+        xy_out[2 * k + 1] = (float)(h * theta / M_PI);
+    }
+}
+
+/* ERP pixel -> unit bearing, double.  spherical_bundle_adjuster.cpp:271-298.
+ * im_width / im_height are doubles there (:271-272) and pt.x is float: pt.x / im_width
+ * promotes to double before the divide. */
+void orc_pixels_to_bearings(const float *xy, int n, int w, int h, double *xyz)
+{
+    double dw = (double)w, dh = (double)h;
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < n; k++) {
+        double lon = 2 * M_PI * ((double)xy[2 * k] / dw);
+        double lat = M_PI * ((double)xy[2 * k + 1] / dh);
+        xyz[3 * k] = sin(lat) * cos(lon);
+        xyz[3 * k + 1] = sin(lat) * sin(lon);
+        xyz[3 * k + 2] = cos(lat);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Matcher.  feature_matcher.cpp:42-59 with the matcher north_star fixes (BFMatcher, NORM_L2).
+ *
+ * Third-party arithmetic: OpenCV BFMatcher::knnMatchImpl -> batchDistance -> batchDistL2_ ->
+ * normL2Sqr_ (modules/core/src/norm.cpp; reference pins 3.4.2, the container has 4.13 whose
+ * arithmetic was probed and reproduced bit-for-bit):
+ *   t = a[k]-b[k] in fp32; sixteen fp32 accumulators (4 vectors x 4 lanes), element k of each
+ *   16-chunk goes to accumulator k%16 with a SEPARATE multiply and add (SSE baseline, no FMA);
+ *   lane-wise ((d0+d1)+d2)+d3; horizontal (s0+s2)+(s1+s3); a scalar tail for dim%16;
+ *   distance = sqrtf(sum).
+ * kNN keeps the k smallest with ties resolved to the lower train index.
+ * ---------------------------------------------------------------------------------------- */
+#if defined(__GNUC__)
+#define ORC_NOFMA __attribute__((optimize("fp-contract=off")))
+#else
+#define ORC_NOFMA
+#endif
+
+ORC_NOFMA float orc_l2sqr_opencv(const float *a, const float *b, int n)
+{
+    float acc[16];
+    for (int m = 0; m < 16; m++) acc[m] = 0.f;
+    int j = 0;
+    float d = 0.f;
+    if (n >= 16) {
+        for (; j <= n - 16; j += 16)
+            for (int m = 0; m < 16; m++) {
+                float t = a[j + m] - b[j + m];
+                float p = t * t;
+                acc[m] = acc[m] + p;
+            }
+        float s[4];
+        for (int l = 0; l < 4; l++) s[l] = ((acc[l] + acc[4 + l]) + acc[8 + l]) + acc[12 + l];
+        d = (s[0] + s[2]) + (s[1] + s[3]);
+    }
+    for (; j < n; j++) {
+        float t = a[j] - b[j];
+        float p = t * t;
+        d = d + p;
+    }
+    return d;
+}
+
+/* kNN k=2 over all train rows.  idx/dist are nq x 2; missing neighbours (nt < 2) are written
+ * as idx=-1, dist=+inf.  `dist` holds sqrtf(l2sqr) like DMatch::distance. */
+void orc_knn2_l2(const float *q, int nq, const float *t, int nt, int dim, int32_t *idx, float *dist)
+{
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int i = 0; i < nq; i++) {
+        float d0 = INFINITY, d1 = INFINITY;
+        int32_t i0 = -1, i1 = -1;
+        const float *a = q + (size_t)i * dim;
+        for (int j = 0; j < nt; j++) {
+            float d = sqrtf(orc_l2sqr_opencv(a, t + (size_t)j * dim, dim));
+            /* strict '<' keeps the earlier (lower) train index on ties */
+            if (d < d0) { d1 = d0; i1 = i0; d0 = d; i0 = j; }
+            else if (d < d1) { d1 = d; i1 = j; }
+        }
+        idx[2 * i] = i0; idx[2 * i + 1] = i1;
+        dist[2 * i] = d0; dist[2 * i + 1] = d1;
+    }
+}
+
+/* Lowe ratio filter, feature_matcher.cpp:47-56: keep m[0] iff m0.distance < ratio*m1.distance
+ * (fp32 product).  Rows with fewer than two neighbours are skipped (the reference would read
+ * knn[i][1] out of bounds there; documented guard).  Returns the number of survivors, written
+ * in ascending query order. */
+ORC_NOFMA int orc_ratio_filter(const int32_t *idx, const float *dist, int nq, float ratio,
+                               int32_t *query_idx, int32_t *train_idx, float *out_dist)
+{
+    int n = 0;
+    for (int i = 0; i < nq; i++) {
+        if (idx[2 * i] < 0 || idx[2 * i + 1] < 0) continue;
+        float thr = ratio * dist[2 * i + 1];
+        if (dist[2 * i] < thr) {
+            query_idx[n] = i; train_idx[n] = idx[2 * i]; out_dist[n] = dist[2 * i];
+            n++;
+        }
+    }
+    return n;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Bundle adjustment, rotation-only.  spherical_bundle_adjuster.cpp:892-919 (functor),
+ * :921-945 (per-residual constants), :183-217 + :334-338 (solve, options).
+ *
+ * Third-party arithmetic (Ceres Solver, version unpinned by the reference's CMakeLists.txt:12,
+ * absent here -> restated from its published algorithm; PARITY UNPINNED):
+ *   - ceres::AngleAxisRotatePoint (rotation.h): theta2 = r.r; if theta2 > DBL_EPSILON:
+ *       theta = sqrt(theta2), w = r/theta, out = p cos + (w x p) sin + w (w.p)(1-cos)
+ *     else out = p + r x p.
+ *   - AutoDiff Jacobian == analytic derivative of the above (checked by finite differences).
+ *   - HuberLoss(a): s=|res|^2, b=a^2; s<=b: rho=s,rho'=1 ; else rho=2a sqrt(s)-b, rho'=a/sqrt(s),
+ *     rho''<0 -> Corrector with alpha=0: residual and Jacobian scaled by sqrt(rho').
+ *   - cost = 1/2 sum rho(s).
+ * ---------------------------------------------------------------------------------------- */
+
+static void cross3(const double a[3], const double b[3], double o[3])
+{
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+/* ceres::AngleAxisRotatePoint restated. */
+void orc_angle_axis_rotate_point(const double r[3], const double p[3], double out[3])
+{
+    double theta2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    if (theta2 > DBL_EPSILON) {
+        double theta = sqrt(theta2), c = cos(theta), s = sin(theta), ith = 1.0 / theta;
+        double w[3] = {r[0] * ith, r[1] * ith, r[2] * ith};
+        double wxp[3];
+        cross3(w, p, wxp);
+        double tmp = (w[0] * p[0] + w[1] * p[1] + w[2] * p[2]) * (1.0 - c);
+        for (int k = 0; k < 3; k++) out[k] = p[k] * c + wxp[k] * s + w[k] * tmp;
+    } else {
+        double rxp[3];
+        cross3(r, p, rxp);
+        for (int k = 0; k < 3; k++) out[k] = p[k] + rxp[k];
+    }
+}
+
+/* Rotation matrix R(r) and its three partial derivatives dR/dr_k, both branches consistent
+ * with what differentiating AngleAxisRotatePoint (Jets) gives.  R row-major 3x3, dR[k] 3x3. */
+void orc_rot_and_derivs(const double r[3], double R[9], double dR[3][9])
+{
+    double theta2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    if (theta2 > DBL_EPSILON) {
+        double th = sqrt(theta2), c = cos(th), s = sin(th);
+        double w[3] = {r[0] / th, r[1] / th, r[2] / th};
+        double K[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+        /* R = c I + s K + (1-c) w w^T */
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 3; b++)
+                R[3 * a + b] = (a == b ? c : 0.0) + s * K[3 * a + b] + (1.0 - c) * w[a] * w[b];
+        for (int k = 0; k < 3; k++) {
+            /* dtheta/dr_k = w_k ; dw_a/dr_k = (delta_ak - w_a w_k)/theta */
+            double dw[3];
+            for (int a = 0; a < 3; a++) dw[a] = ((a == k ? 1.0 : 0.0) - w[a] * w[k]) / th;
+            double dK[9] = {0, -dw[2], dw[1], dw[2], 0, -dw[0], -dw[1], dw[0], 0};
+            for (int a = 0; a < 3; a++)
+                for (int b = 0; b < 3; b++)
+                    dR[k][3 * a + b] = (a == b ? -s * w[k] : 0.0) + c * w[k] * K[3 * a + b] + s * dK[3 * a + b] +
+                                       s * w[k] * w[a] * w[b] + (1.0 - c) * (dw[a] * w[b] + w[a] * dw[b]);
+        }
+    } else {
+        /* out = p + r x p  ->  R = I + [r]x, dR/dr_k = [e_k]x */
+        double K[9] = {0, -r[2], r[1], r[2], 0, -r[0], -r[1], r[0], 0};
+        for (int a = 0; a < 9; a++) R[a] = K[a];
+        R[0] += 1.0; R[4] += 1.0; R[8] += 1.0;
+        for (int k = 0; k < 3; k++) {
+            double e[3] = {k == 0, k == 1, k == 2};
+            double G[9] = {0, -e[2], e[1], e[2], 0, -e[0], -e[1], e[0], 0};
+            for (int a = 0; a < 9; a++) dR[k][a] = G[a];
+        }
+    }
+}
+
+/* One residual + Jacobian, raw (no loss).  spherical_bundle_adjuster.cpp:892-919.
+ * res[3]; J[9] row-major: J[3*a+k] = d res_a / d r_k. */
+void orc_ba_rot_functor(const double b1[3], const double b2[3], const double r[3], const double t[3],
+                        double d1, double d2, double res[3], double J[9])
+{
+    double X1[3] = {b1[0] * d1, b1[1] * d1, b1[2] * d1};
+    double X2[3] = {b2[0] * d2, b2[1] * d2, b2[2] * d2};
+    double X1r[3];
+    orc_angle_axis_rotate_point(r, X1, X1r);
+    for (int a = 0; a < 3; a++) res[a] = X2[a] - (X1r[a] - t[a]);
+    if (J) {
+        double R[9], dR[3][9];
+        orc_rot_and_derivs(r, R, dR);
+        for (int k = 0; k < 3; k++)
+            for (int a = 0; a < 3; a++)
+                J[3 * a + k] = -(dR[k][3 * a] * X1[0] + dR[k][3 * a + 1] * X1[1] + dR[k][3 * a + 2] * X1[2]);
+    }
+}
+
+/* Huber rho(s) and rho'(s) with scale a (ceres::HuberLoss). */
+static void huber(double a, double s, double *rho, double *rho1)
+{
+    double b = a * a;
+    if (a <= 0.0) { *rho = s; *rho1 = 1.0; return; }       /* a<=0: no loss (NULL loss function) */
+    if (s > b) { double r = sqrt(s); *rho = 2.0 * a * r - b; *rho1 = fmax(DBL_MIN, a / r); }
+    else { *rho = s; *rho1 = 1.0; }
+}
+
+/* Evaluate all observations.  b1,b2: n x 3 double.  cam: n camera ids (NULL -> all 0).
+ * r: n_cam x 3.  Outputs (any may be NULL): res n x 3 and jac n x 9 are the RAW functor values
+ * (what CostFunction::Evaluate returns); H n_cam x 6 (xx,xy,xz,yy,yz,zz), g n_cam x 3 and
+ * cost n_cam are the Huber-corrected normal-equation blocks sum J~^T J~, sum J~^T r~, 1/2 sum rho.
+ * d1/d2 are the uniform depths of spherical_bundle_adjuster.cpp:941-942. */
+void orc_ba_rot_eval(const double *b1, const double *b2, const int32_t *cam, int n, const double *r, int n_cam,
+                     const double t[3], double d1, double d2, double huber_a,
+                     double *res, double *jac, double *H, double *g, double *cost)
+{
+    if (H) memset(H, 0, sizeof(double) * 6 * n_cam);
+    if (g) memset(g, 0, sizeof(double) * 3 * n_cam);
+    if (cost) memset(cost, 0, sizeof(double) * n_cam);
+    int want_J = (jac || H || g);
+#ifdef _OPENMP
+    int nth = omp_get_max_threads();
+#else
+    int nth = 1;
+#endif
+    /* per-thread private blocks, combined in thread order (deterministic for a fixed nth) */
+    double *priv = (double *)calloc((size_t)nth * n_cam * 10, sizeof(double));
+#pragma omp parallel num_threads(nth)
+    {
+#ifdef _OPENMP
+        int tid = omp_get_thread_num();
+#else
+        int tid = 0;
+#endif
+        double *P = priv + (size_t)tid * n_cam * 10;
+#pragma omp for schedule(static)
+        for (int i = 0; i < n; i++) {
+            int c = cam ? cam[i] : 0;
+            double rr[3], J[9];
+            orc_ba_rot_functor(b1 + 3 * i, b2 + 3 * i, r + 3 * c, t, d1, d2, rr, want_J ? J : NULL);
+            if (res) memcpy(res + 3 * i, rr, 3 * sizeof(double));
+            if (jac) memcpy(jac + 9 * i, J, 9 * sizeof(double));
+            double s = rr[0] * rr[0] + rr[1] * rr[1] + rr[2] * rr[2], rho, rho1;
+            huber(huber_a, s, &rho, &rho1);
+            double *B = P + (size_t)c * 10;
+            B[9] += 0.5 * rho;
+            if (want_J) {
+                /* J~ = sqrt(rho') J, r~ = sqrt(rho') r  ->  J~^T J~ = rho' J^T J */
+                double jx[3] = {J[0], J[3], J[6]}, jy[3] = {J[1], J[4], J[7]}, jz[3] = {J[2], J[5], J[8]};
+                double xx = 0, xy = 0, xz = 0, yy = 0, yz = 0, zz = 0, gx = 0, gy = 0, gz = 0;
+                for (int a = 0; a < 3; a++) {
+                    xx += jx[a] * jx[a]; xy += jx[a] * jy[a]; xz += jx[a] * jz[a];
+                    yy += jy[a] * jy[a]; yz += jy[a] * jz[a]; zz += jz[a] * jz[a];
+                    gx += jx[a] * rr[a]; gy += jy[a] * rr[a]; gz += jz[a] * rr[a];
+                }
+                B[0] += rho1 * xx; B[1] += rho1 * xy; B[2] += rho1 * xz;
+                B[3] += rho1 * yy; B[4] += rho1 * yz; B[5] += rho1 * zz;
+                B[6] += rho1 * gx; B[7] += rho1 * gy; B[8] += rho1 * gz;
+            }
+        }
+    }
+    for (int tix = 0; tix < nth; tix++)
+        for (int c = 0; c < n_cam; c++) {
+            const double *B = priv + ((size_t)tix * n_cam + c) * 10;
+            if (H) for (int k = 0; k < 6; k++) H[6 * c + k] += B[k];
+            if (g) for (int k = 0; k < 3; k++) g[3 * c + k] += B[6 + k];
+            if (cost) cost[c] += B[9];
+        }
+    free(priv);
+}
+
+/* Solve the symmetric 3x3 system (H + diag(dd)) x = rhs by Cholesky.  Returns 0 on success. */
+static int solve3_spd(const double H[6], const double dd[3], const double rhs[3], double x[3])
+{
+    double a00 = H[0] + dd[0], a01 = H[1], a02 = H[2], a11 = H[3] + dd[1], a12 = H[4], a22 = H[5] + dd[2];
+    if (!(a00 > 0.0)) return 1;
+    double l00 = sqrt(a00), l10 = a01 / l00, l20 = a02 / l00;
+    double t11 = a11 - l10 * l10;
+    if (!(t11 > 0.0)) return 1;
+    double l11 = sqrt(t11), l21 = (a12 - l20 * l10) / l11;
+    double t22 = a22 - l20 * l20 - l21 * l21;
+    if (!(t22 > 0.0)) return 1;
+    double l22 = sqrt(t22);
+    double y0 = rhs[0] / l00, y1 = (rhs[1] - l10 * y0) / l11, y2 = (rhs[2] - l20 * y0 - l21 * y1) / l22;
+    x[2] = y2 / l22;
+    x[1] = (y1 - l21 * x[2]) / l11;
+    x[0] = (y0 - l10 * x[1] - l20 * x[2]) / l00;
+    return 0;
+}
+
+typedef struct {
+    int iterations;            /* LM iterations executed (successful + unsuccessful) */
+    int num_successful;
+    int termination;           /* 0 max-iter, 1 function tol, 2 gradient tol, 3 parameter tol, 4 failure */
+    double initial_cost;
+    double final_cost;
+    double final_radius;
+} orc_lm_summary;
+
+/* Levenberg-Marquardt over all camera blocks as ONE problem (one trust-region radius, one
+ * accept/reject), following Ceres' TrustRegionMinimizer + LevenbergMarquardtStrategy defaults
+ * named at spherical_bundle_adjuster.cpp:334-338 (max 50 iterations; everything else default):
+ *   initial_trust_region_radius 1e4, max 1e16, min 1e-32; min_lm_diagonal 1e-6, max 1e32;
+ *   jacobi_scaling on: column scale 1/(1+sqrt(diag(J^T J)));  min_relative_decrease 1e-3;
+ *   function_tolerance 1e-6, gradient_tolerance 1e-10, parameter_tolerance 1e-8;
+ *   radius update: accepted -> radius /= max(1/3, 1-(2 rho-1)^3), decrease_factor=2;
+ *                  rejected -> radius /= decrease_factor, decrease_factor *= 2.
+ * The linear solve is exact (dense 3x3 Cholesky per block) where the reference asks for
+ * ITERATIVE_SCHUR (:335); with one 3-parameter block per camera the reduced system IS this
+ * 3x3 block, so the exact solve is the converged limit of that iteration. */
+void orc_ba_rot_solve(const double *b1, const double *b2, const int32_t *cam, int n, double *r, int n_cam,
+                      const double t[3], double d1, double d2, double huber_a, int max_iter,
+                      orc_lm_summary *sum)
+{
+    const double min_diag = 1e-6, max_diag = 1e32, min_rel_dec = 1e-3;
+    const double ftol = 1e-6, gtol = 1e-10, ptol = 1e-8, max_radius = 1e16, min_radius = 1e-32;
+    double radius = 1e4, dec_factor = 2.0;
+    int consecutive_invalid = 0;
+    int np = 3 * n_cam;
+    double *H = malloc(sizeof(double) * 6 * n_cam), *g = malloc(sizeof(double) * np), *c = malloc(sizeof(double) * n_cam);
+    double *Hn = malloc(sizeof(double) * 6 * n_cam), *gn = malloc(sizeof(double) * np), *cn = malloc(sizeof(double) * n_cam);
+    double *scale = malloc(sizeof(double) * np), *step = malloc(sizeof(double) * np), *xn = malloc(sizeof(double) * np);
+
+    orc_ba_rot_eval(b1, b2, cam, n, r, n_cam, t, d1, d2, huber_a, NULL, NULL, H, g, c);
+    double cost = 0;
+    for (int k = 0; k < n_cam; k++) cost += c[k];
+    /* Jacobi scaling is computed once from the initial Jacobian (Ceres does the same). */
+    for (int k = 0; k < n_cam; k++) {
+        scale[3 * k] = 1.0 / (1.0 + sqrt(H[6 * k]));
+        scale[3 * k + 1] = 1.0 / (1.0 + sqrt(H[6 * k + 3]));
+        scale[3 * k + 2] = 1.0 / (1.0 + sqrt(H[6 * k + 5]));
+    }
+    sum->initial_cost = cost; sum->iterations = 0; sum->num_successful = 0; sum->termination = 0;
+
+    double gmax = 0;
+    for (int k = 0; k < np; k++) gmax = fmax(gmax, fabs(g[k]));
+    if (gmax <= gtol) { sum->termination = 2; goto done; }
+
+    for (int it = 0; it < max_iter; it++) {
+        sum->iterations = it + 1;
+        /* scaled system: Hs = S H S, gs = S g; D^2 = clamp(diag(Hs))/radius */
+        double model_dec = 0, step_norm2 = 0, x_norm2 = 0;
+        int bad = 0;
+        for (int k = 0; k < n_cam; k++) {
+            const double *s = scale + 3 * k;
+            double Hs[6] = {H[6 * k] * s[0] * s[0], H[6 * k + 1] * s[0] * s[1], H[6 * k + 2] * s[0] * s[2],
+                            H[6 * k + 3] * s[1] * s[1], H[6 * k + 4] * s[1] * s[2], H[6 * k + 5] * s[2] * s[2]};
+            double gs[3] = {g[3 * k] * s[0], g[3 * k + 1] * s[1], g[3 * k + 2] * s[2]};
+            double dd[3] = {fmin(fmax(Hs[0], min_diag), max_diag) / radius,
+                            fmin(fmax(Hs[3], min_diag), max_diag) / radius,
+                            fmin(fmax(Hs[5], min_diag), max_diag) / radius};
+            double rhs[3] = {-gs[0], -gs[1], -gs[2]}, ds[3];
+            if (solve3_spd(Hs, dd, rhs, ds)) { bad = 1; break; }
+            /* model decrease = -(gs.ds + 1/2 ds^T Hs ds)  (Ceres: -model_residuals.(f + model_residuals/2)) */
+            double Hd[3] = {Hs[0] * ds[0] + Hs[1] * ds[1] + Hs[2] * ds[2], Hs[1] * ds[0] + Hs[3] * ds[1] + Hs[4] * ds[2],
+                            Hs[2] * ds[0] + Hs[4] * ds[1] + Hs[5] * ds[2]};
+            model_dec -= (gs[0] * ds[0] + gs[1] * ds[1] + gs[2] * ds[2]) + 0.5 * (ds[0] * Hd[0] + ds[1] * Hd[1] + ds[2] * Hd[2]);
+            for (int a = 0; a < 3; a++) {
+                step[3 * k + a] = ds[a] * s[a];
+                xn[3 * k + a] = r[3 * k + a] + step[3 * k + a];
+                step_norm2 += step[3 * k + a] * step[3 * k + a];
+                x_norm2 += r[3 * k + a] * r[3 * k + a];
+            }
+        }
+        if (bad || !(model_dec > 0.0)) {
+            /* invalid step (TrustRegionMinimizer::HandleInvalidStep ->
+             * LevenbergMarquardtStrategy::StepIsInvalid): radius *= 0.5, at most 5 in a row */
+            if (++consecutive_invalid >= 5) { sum->termination = 4; break; }
+            radius *= 0.5;
+            if (radius <= min_radius) { sum->termination = 4; break; }
+            continue;
+        }
+        consecutive_invalid = 0;
+
+        orc_ba_rot_eval(b1, b2, cam, n, xn, n_cam, t, d1, d2, huber_a, NULL, NULL, Hn, gn, cn);
+        double new_cost = 0;
+        for (int k = 0; k < n_cam; k++) new_cost += cn[k];
+
+        /* ParameterToleranceReached / FunctionToleranceReached are tested on the CANDIDATE,
+         * before it is accepted; on termination the candidate is NOT applied. */
+        if (sqrt(step_norm2) <= ptol * (sqrt(x_norm2) + ptol)) { sum->termination = 3; break; }
+        double cost_change = cost - new_cost;
+        if (fabs(cost_change) <= ftol * cost) { sum->termination = 1; break; }
+
+        double rel_dec = cost_change / model_dec;
+        if (rel_dec > min_rel_dec) {
+            memcpy(r, xn, sizeof(double) * np);
+            memcpy(H, Hn, sizeof(double) * 6 * n_cam);
+            memcpy(g, gn, sizeof(double) * np);
+            cost = new_cost;
+            sum->num_successful++;
+            double q = 2.0 * rel_dec - 1.0;
+            radius = radius / fmax(1.0 / 3.0, 1.0 - q * q * q);
+            radius = fmin(max_radius, radius);
+            dec_factor = 2.0;
+            gmax = 0;
+            for (int k = 0; k < np; k++) gmax = fmax(gmax, fabs(g[k]));
+            if (gmax <= gtol) { sum->termination = 2; break; }
+        } else {
+            radius = radius / dec_factor; dec_factor *= 2.0;
+        }
+        /* MinTrustRegionRadiusReached (checked between iterations) */
+        if (radius <= min_radius) { sum->termination = 4; break; }
+    }
+done:
+    sum->final_cost = cost; sum->final_radius = radius;
+    free(H); free(g); free(c); free(Hn); free(gn); free(cn); free(scale); free(step); free(xn);
+}
