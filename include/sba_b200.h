@@ -1,0 +1,189 @@
+/*
+ * sba_b200.h -- C ABI of libsba_b200.so: the B200 (sm_100a) implementation of the hot path of
+ * whdlgp/spherical_bundle_adjuster.
+ *
+ * The reference has no FFI layer; its boundary is the public C++ class API
+ * (equi2cube.hpp:20-32, equi2cube_surf.hpp:7-18, feature_matcher.hpp:24-49,
+ * spherical_bundle_adjuster.hpp:15-23,86-115).  The drop-in facade classes in
+ * spherical_bundle_adjuster_b200/host/ keep those signatures and call the entry points below;
+ * a maintainer of the reference binds the same entry points directly.
+ *
+ * Conventions
+ *   - every function returns 0 (SBA_OK) or a negative sba_status; sba_last_error() gives text.
+ *   - plain pointers and sizes only.  `mem` says where the data pointers of THAT call live:
+ *     SBA_MEM_HOST (the library stages through its own device buffers and copies results back,
+ *     synchronising before it returns) or SBA_MEM_DEVICE (zero copy, asynchronous on the
+ *     context's stream; scalars returned through host pointers force a synchronisation).
+ *   - there is no CPU fallback: without a usable CUDA device sba_ctx_create fails.
+ *   - a context is not thread safe; use one per host thread (the reference's classes are not
+ *     re-entrant either: feature_matcher.hpp:44-48).
+ */
+#ifndef SBA_B200_H
+#define SBA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SBA_B200_VERSION 100 /* 0.1.0 */
+
+typedef enum sba_status {
+    SBA_OK = 0,
+    SBA_ERR_INVALID = -1,     /* bad argument */
+    SBA_ERR_CUDA = -2,        /* CUDA runtime/driver error (text in sba_last_error) */
+    SBA_ERR_NOMEM = -3,
+    SBA_ERR_UNSUPPORTED = -4, /* e.g. descriptor dimension not handled by the selected algorithm */
+    SBA_ERR_NO_DEVICE = -5,
+    SBA_ERR_COMM = -6
+} sba_status;
+
+typedef enum sba_mem { SBA_MEM_HOST = 0, SBA_MEM_DEVICE = 1 } sba_mem;
+
+typedef struct sba_ctx sba_ctx;
+
+int sba_version(void);
+/* Text of the last error raised on this thread ("" if none). */
+const char* sba_last_error(void);
+
+/* Create a context on CUDA device `device`.  `stream` is a cudaStream_t (as void*) that all work
+ * of this context is enqueued on, or NULL to let the context create its own non-blocking stream. */
+int sba_ctx_create(int device, void* stream, sba_ctx** out);
+int sba_ctx_destroy(sba_ctx* ctx);
+int sba_ctx_set_stream(sba_ctx* ctx, void* stream);
+void* sba_ctx_get_stream(sba_ctx* ctx);
+int sba_ctx_synchronize(sba_ctx* ctx);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+int64_t sba_ctx_launch_count(sba_ctx* ctx);
+
+/* ---------------------------------------------------------------------------------------------
+ * equi2cube  (replaces equi2cube.cpp:12-302)
+ *
+ * erp      : n_images x h x w x 3 bytes, interleaved BGR, continuous (CV_8UC3).
+ * strip_out: n_images x cube_size x (6*cube_size) x 3 bytes; faces in get_all's order
+ *            left, front, right, back, top, bottom (equi2cube.cpp:293-298).
+ * Source index per output pixel is the reference's truncating fp64 formula (equi2cube.cpp:26-48).
+ * The one unchecked read of the reference (row == h at the exact bottom-centre pixel when theta
+ * rounds to pi) is clamped to row h-1.
+ * The index table depends only on (w, h, cube_size); it is built once per geometry (on the
+ * device, with near-integer coordinates resolved by the host libm so every index is bit-exact)
+ * and cached in the context.
+ * ------------------------------------------------------------------------------------------- */
+int sba_equi2cube(sba_ctx* ctx, const uint8_t* erp, int w, int h, int n_images, int cube_size, uint8_t* strip_out, int mem);
+
+/* One face, cube_size x cube_size x 3 (get_left/get_front/get_right/get_back/get_top/get_bottom).
+ * face: 0 left, 1 front, 2 right, 3 back, 4 top, 5 bottom. */
+int sba_equi2cube_face(sba_ctx* ctx, const uint8_t* erp, int w, int h, int cube_size, int face, uint8_t* face_out, int mem);
+
+/* Build (or fetch from the cache) the index table: lut_out[cube_size][6*cube_size] int32 source
+ * pixel indices (row*w + col).  lut_out may be NULL to only warm the cache. */
+int sba_equi2cube_lut(sba_ctx* ctx, int w, int h, int cube_size, int32_t* lut_out, int mem);
+
+/* equi2cube_surf::cube2equi_pixel for n keypoints (equi2cube_surf.cpp:19-76).
+ * xy_in / xy_out: n interleaved (x, y) float pairs (cv::Point2f). */
+int sba_cube2equi_points(sba_ctx* ctx, const float* xy_in, int n, int cube_size, int w, int h, float* xy_out, int mem);
+
+/* ERP pixel -> unit bearing (spherical_bundle_adjuster.cpp:271-298), fp64 math.
+ * bearings_out: n x float4 (x, y, z, 0) -- the layout the BA kernels read.
+ * bearings64_out (optional, may be NULL): n x 3 doubles, the reference's vector<Point3d>. */
+int sba_pixels_to_bearings(sba_ctx* ctx, const float* xy, int n, int w, int h, float* bearings_out, double* bearings64_out, int mem);
+
+/* ---------------------------------------------------------------------------------------------
+ * Matcher  (replaces feature_matcher::match_two_image, feature_matcher.cpp:42-59)
+ *
+ * Exact brute-force L2 kNN (k=2) of every query row over all train rows with OpenCV BFMatcher
+ * semantics (fp32 distance in OpenCV's accumulation order, ties -> lower train index), then the
+ * Lowe ratio test  d0 < ratio * d1  (feature_matcher.cpp:47,52).
+ *
+ * q [nq x dim], t [nt x dim] fp32 row-major.  dim must be a multiple of 16 (SURF: 64 or 128).
+ * Survivors are written in ascending query order: query_idx/train_idx/dist [capacity nq].
+ * knn_idx / knn_dist (optional, may be NULL): nq x 2, the raw kNN result; missing neighbours
+ * (nt < 2) are -1 / +inf and such rows never pass the ratio test (the reference reads
+ * knn[i][1] unconditionally there -- guarded here).
+ * algo: SBA_MATCH_AUTO picks the tensor-core path when it applies.
+ * ------------------------------------------------------------------------------------------- */
+typedef enum sba_match_algo {
+    SBA_MATCH_AUTO = 0,
+    SBA_MATCH_SIMT_EXACT = 1, /* fp32 CUDA-core brute force in OpenCV's arithmetic order */
+    SBA_MATCH_TENSOR = 2      /* tcgen05 bf16x3 candidate filter + exact fp32 re-rank */
+} sba_match_algo;
+
+int sba_knn2_ratio(sba_ctx* ctx, const float* q, int nq, const float* t, int nt, int dim, float ratio,
+                   int32_t* query_idx, int32_t* train_idx, float* dist, int32_t* n_matches,
+                   int32_t* knn_idx, float* knn_dist, int mem, int algo);
+
+/* Statistics of the last sba_knn2_ratio call on this context (tensor path diagnostics). */
+typedef struct sba_match_stats {
+    int algo_used;          /* sba_match_algo actually run */
+    int n_fallback_rows;    /* query rows whose candidate set failed the error-bound test and were
+                               re-scanned exactly */
+    int n_tiles;            /* tensor-core tiles issued */
+    int n_ctas;
+} sba_match_stats;
+int sba_match_last_stats(sba_ctx* ctx, sba_match_stats* out);
+
+/* Gather matched keypoints (equi2cube_surf.cpp:107-113): out_left[i] = key_left[query_idx[i]],
+ * out_right[i] = key_right[train_idx[i]] on (x, y) float pairs. */
+int sba_gather_matches(sba_ctx* ctx, const float* key_left_xy, const float* key_right_xy, const int32_t* query_idx,
+                       const int32_t* train_idx, int n_matches, float* out_left_xy, float* out_right_xy, int mem);
+
+/* ---------------------------------------------------------------------------------------------
+ * Rotation-only bundle adjustment
+ * (replaces ba_spherical_costfunctor_rot_only + ceres::Solve, spherical_bundle_adjuster.cpp:892-945,
+ *  :183-217, :334-338)
+ *
+ * A problem owns the observations on the device: b1, b2 are n_obs x float4 unit bearings
+ * (x, y, z, unused); cam (may be NULL == all zero) gives the rotation block each observation
+ * belongs to, 0 <= cam < n_cam.  The reference has exactly one block (:943); n_cam > 1 is the
+ * multi-camera extension of BASELINE config 4.  Observations are grouped by camera at creation.
+ *
+ * residual_i = d2*b2_i - (R(r_cam) * d1*b1_i - t)            (:896-916)
+ * loss       = Huber(huber_delta) on |residual_i|^2, huber_delta <= 0 means no loss (:943)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct sba_ba_problem sba_ba_problem;
+
+int sba_ba_problem_create(sba_ctx* ctx, const float* b1, const float* b2, const int32_t* cam, int64_t n_obs, int n_cam,
+                          int mem, sba_ba_problem** out);
+int sba_ba_problem_destroy(sba_ba_problem* p);
+
+/* Multi-GPU: this rank holds a shard of the residuals.  After each evaluation the per-camera
+ * normal-equation blocks are summed over ranks by `allreduce(buffer, count, user)`, which must
+ * sum `count` doubles in place on the context's stream (bench/tests pass an NCCL all-reduce).
+ * Pass NULL to return to single-GPU operation. */
+typedef int (*sba_allreduce_fn)(void* device_buffer, int64_t count, void* user);
+int sba_ba_problem_set_allreduce(sba_ba_problem* p, sba_allreduce_fn fn, void* user);
+
+/* One evaluation at rotations r [n_cam x 3] (axis-angle, host pointer always).
+ * Outputs, each optional (NULL to skip), located per `mem`:
+ *   res  n_obs x 3 fp32 and jac n_obs x 9 fp32 (row-major d res_a / d r_k): the RAW functor values
+ *        in the caller's original observation order;
+ *   H n_cam x 6 (xx,xy,xz,yy,yz,zz), g n_cam x 3, cost n_cam, fp64: Huber-corrected J^T J, J^T r
+ *        and 1/2 sum rho per camera. */
+int sba_ba_rot_eval(sba_ba_problem* p, const double* r, const double t[3], double d1, double d2, double huber_delta,
+                    float* res, float* jac, double* H, double* g, double* cost, int mem);
+
+typedef struct sba_solve_summary {
+    int iterations;      /* LM iterations run (successful + unsuccessful + invalid) */
+    int num_successful;
+    int termination;     /* 0 max iterations, 1 function tol, 2 gradient tol, 3 parameter tol, 4 failure */
+    int evaluations;     /* residual+Jacobian passes over the observations */
+    double initial_cost;
+    double final_cost;
+    double final_radius;
+} sba_solve_summary;
+
+/* Levenberg-Marquardt with Ceres' default trust-region policy (one radius for the whole problem),
+ * at most max_iter iterations (the reference sets 50, :336).  r_inout [n_cam x 3] host pointer. */
+int sba_ba_rot_solve(sba_ba_problem* p, double* r_inout, const double t[3], double d1, double d2, double huber_delta,
+                     int max_iter, sba_solve_summary* summary);
+
+/* Device-timed evaluation loop for benchmarking: runs `iters` fused evaluations (residual +
+ * Jacobian + per-camera normal equations) back to back at r and returns the mean kernel time. */
+int sba_ba_rot_eval_timed(sba_ba_problem* p, const double* r, const double t[3], double d1, double d2, double huber_delta,
+                          int materialise, int iters, float* mean_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SBA_B200_H */

@@ -1,0 +1,304 @@
+"""Python host layer over the C ABI (tests, bench and scripting; C++ users take host/*.hpp).
+
+Every array argument may be a NumPy array (host memory: the library stages it, runs on the GPU and
+copies results back) or a CUDA ``torch.Tensor`` (device memory: zero copy, asynchronous on the
+tensor's current stream).  Results come back in the same kind.  The compute is always the CUDA
+library; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import MATCH_AUTO, MATCH_SIMT_EXACT, MATCH_TENSOR, SBA_MEM_DEVICE, SBA_MEM_HOST, SbaError, check
+
+try:  # torch is only plumbing: device memory, streams, torch.distributed
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+_CUDA_STREAM_LEGACY = 1  # cudaStreamLegacy handle: torch's default stream has the raw handle 0
+
+
+def _is_tensor(a) -> bool:
+    return torch is not None and isinstance(a, torch.Tensor)
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if _is_tensor(a):
+        return C.c_void_p(a.data_ptr())
+    return C.c_void_p(a.ctypes.data)
+
+
+def _mem_of(*arrs) -> int:
+    kinds = {("dev" if (_is_tensor(a) and a.is_cuda) else "host") for a in arrs if a is not None}
+    if len(kinds) > 1:
+        raise SbaError("mixing host and device arrays in one call")
+    return SBA_MEM_DEVICE if kinds == {"dev"} else SBA_MEM_HOST
+
+
+def _as(a, dtype_np, dtype_t):
+    """Contiguous array of the right dtype, NumPy or torch."""
+    if _is_tensor(a):
+        if a.dtype != dtype_t:
+            a = a.to(dtype_t)
+        return a.contiguous()
+    return np.ascontiguousarray(a, dtype_np)
+
+
+def _empty_like_kind(ref, shape, dtype_np, dtype_t):
+    if _is_tensor(ref):
+        return torch.empty(shape, dtype=dtype_t, device=ref.device)
+    return np.empty(shape, dtype_np)
+
+
+@dataclass
+class MatchResult:
+    query_idx: object
+    train_idx: object
+    distance: object
+    knn_idx: object = None
+    knn_dist: object = None
+
+    def __len__(self):
+        return int(self.query_idx.shape[0])
+
+
+class Context:
+    """One CUDA context of the library bound to one device (wraps ``sba_ctx``)."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        self.device = device
+        if stream is None and torch is not None and torch.cuda.is_available():
+            with torch.cuda.device(device):
+                stream = torch.cuda.current_stream().cuda_stream or _CUDA_STREAM_LEGACY
+        check(self._lib.sba_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            self._lib.sba_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- plumbing
+    def use_current_torch_stream(self):
+        s = torch.cuda.current_stream(self.device).cuda_stream or _CUDA_STREAM_LEGACY
+        check(self._lib.sba_ctx_set_stream(self._h, C.c_void_p(s)))
+
+    def set_stream(self, handle: int):
+        check(self._lib.sba_ctx_set_stream(self._h, C.c_void_p(handle or _CUDA_STREAM_LEGACY)))
+
+    def synchronize(self):
+        check(self._lib.sba_ctx_synchronize(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.sba_ctx_launch_count(self._h))
+
+    # -- equi2cube.hpp:20-32
+    def equi2cube(self, erp, cube_size: int, out=None):
+        """``equi2cube::get_all`` for one image [h,w,3] or a batch [n,h,w,3] (uint8, BGR)."""
+        erp = _as(erp, np.uint8, torch.uint8 if torch else None)
+        batched = erp.ndim == 4
+        n = erp.shape[0] if batched else 1
+        h, w = (erp.shape[1], erp.shape[2]) if batched else (erp.shape[0], erp.shape[1])
+        shape = (n, cube_size, 6 * cube_size, 3) if batched else (cube_size, 6 * cube_size, 3)
+        if out is None:
+            out = _empty_like_kind(erp, shape, np.uint8, torch.uint8 if torch else None)
+        check(self._lib.sba_equi2cube(self._h, _ptr(erp), w, h, n, cube_size, _ptr(out), _mem_of(erp, out)))
+        return out
+
+    def equi2cube_face(self, erp, cube_size: int, face: int):
+        """``equi2cube::get_left/front/right/back/top/bottom`` (face 0..5 in strip order)."""
+        erp = _as(erp, np.uint8, torch.uint8 if torch else None)
+        h, w = erp.shape[0], erp.shape[1]
+        out = _empty_like_kind(erp, (cube_size, cube_size, 3), np.uint8, torch.uint8 if torch else None)
+        check(self._lib.sba_equi2cube_face(self._h, _ptr(erp), w, h, cube_size, face, _ptr(out), _mem_of(erp, out)))
+        return out
+
+    def equi2cube_lut(self, w: int, h: int, cube_size: int) -> np.ndarray:
+        lut = np.empty((cube_size, 6 * cube_size), np.int32)
+        check(self._lib.sba_equi2cube_lut(self._h, w, h, cube_size, _ptr(lut), SBA_MEM_HOST))
+        return lut
+
+    # -- equi2cube_surf.hpp:12
+    def cube2equi_points(self, xy, cube_size: int, w: int, h: int):
+        xy = _as(xy, np.float32, torch.float32 if torch else None).reshape(-1, 2)
+        out = _empty_like_kind(xy, xy.shape, np.float32, torch.float32 if torch else None)
+        check(self._lib.sba_cube2equi_points(self._h, _ptr(xy), xy.shape[0], cube_size, w, h, _ptr(out), _mem_of(xy, out)))
+        return out
+
+    # -- spherical_bundle_adjuster.cpp:271-298
+    def pixels_to_bearings(self, xy, w: int, h: int, want_f64: bool = False):
+        xy = _as(xy, np.float32, torch.float32 if torch else None).reshape(-1, 2)
+        n = xy.shape[0]
+        b32 = _empty_like_kind(xy, (n, 4), np.float32, torch.float32 if torch else None)
+        b64 = _empty_like_kind(xy, (n, 3), np.float64, torch.float64 if torch else None) if want_f64 else None
+        check(self._lib.sba_pixels_to_bearings(self._h, _ptr(xy), n, w, h, _ptr(b32), _ptr(b64), _mem_of(xy, b32)))
+        return (b32, b64) if want_f64 else b32
+
+    # -- feature_matcher.hpp:34
+    def match_two_image(self, desc1, desc2, ratio: float = 0.3, algo: int = MATCH_AUTO, want_knn: bool = False) -> MatchResult:
+        """``feature_matcher::match_two_image``: kNN(k=2) + ratio test, survivors in query order."""
+        f32t = torch.float32 if torch else None
+        i32t = torch.int32 if torch else None
+        q = _as(desc1, np.float32, f32t)
+        t = _as(desc2, np.float32, f32t)
+        nq = q.shape[0]
+        nt = t.shape[0]
+        dim = q.shape[1] if q.ndim == 2 and nq else (t.shape[1] if t.ndim == 2 else 64)
+        qi = _empty_like_kind(q, (max(nq, 1),), np.int32, i32t)
+        ti = _empty_like_kind(q, (max(nq, 1),), np.int32, i32t)
+        dd = _empty_like_kind(q, (max(nq, 1),), np.float32, f32t)
+        ki = _empty_like_kind(q, (nq, 2), np.int32, i32t) if want_knn else None
+        kd = _empty_like_kind(q, (nq, 2), np.float32, f32t) if want_knn else None
+        mem = _mem_of(q, t)
+        if mem == SBA_MEM_DEVICE:
+            nm = torch.zeros(1, dtype=torch.int32, device=q.device)
+            check(self._lib.sba_knn2_ratio(self._h, _ptr(q), nq, _ptr(t), nt, dim, ratio, _ptr(qi), _ptr(ti), _ptr(dd), _ptr(nm),
+                                           _ptr(ki), _ptr(kd), mem, algo))
+            n = int(nm.item())
+        else:
+            nm = C.c_int32(0)
+            check(self._lib.sba_knn2_ratio(self._h, _ptr(q), nq, _ptr(t), nt, dim, ratio, _ptr(qi), _ptr(ti), _ptr(dd),
+                                           C.cast(C.byref(nm), C.c_void_p), _ptr(ki), _ptr(kd), mem, algo))
+            n = nm.value
+        return MatchResult(qi[:n], ti[:n], dd[:n], ki, kd)
+
+    def match_stats(self) -> _lib.MatchStats:
+        s = _lib.MatchStats()
+        check(self._lib.sba_match_last_stats(self._h, C.byref(s)))
+        return s
+
+    def gather_matches(self, key_left_xy, key_right_xy, query_idx, train_idx):
+        n = int(query_idx.shape[0])
+        ol = torch.empty((n, 2), dtype=torch.float32, device=key_left_xy.device)
+        orr = torch.empty((n, 2), dtype=torch.float32, device=key_left_xy.device)
+        check(self._lib.sba_gather_matches(self._h, _ptr(key_left_xy.contiguous()), _ptr(key_right_xy.contiguous()),
+                                           _ptr(query_idx.contiguous()), _ptr(train_idx.contiguous()), n, _ptr(ol), _ptr(orr),
+                                           SBA_MEM_DEVICE))
+        return ol, orr
+
+    # -- bundle adjustment
+    def ba_problem(self, b1, b2, cam=None, n_cam: int = 1) -> "BAProblem":
+        return BAProblem(self, b1, b2, cam, n_cam)
+
+
+def _bearings4(b, f32t):
+    """n x 3 or n x 4 -> contiguous n x 4 float32 (x, y, z, 0)."""
+    if _is_tensor(b):
+        b = b.to(torch.float32)
+        if b.shape[1] == 3:
+            b = torch.cat([b, torch.zeros_like(b[:, :1])], dim=1)
+        return b.contiguous()
+    b = np.asarray(b, np.float32)
+    if b.shape[1] == 3:
+        b = np.concatenate([b, np.zeros_like(b[:, :1])], axis=1)
+    return np.ascontiguousarray(b)
+
+
+class BAProblem:
+    """Rotation-only BA problem resident on the device (wraps ``sba_ba_problem``)."""
+
+    def __init__(self, ctx: Context, b1, b2, cam=None, n_cam: int = 1):
+        f32t = torch.float32 if torch else None
+        self.ctx = ctx
+        self._lib = ctx._lib
+        self._h = C.c_void_p()
+        b1 = _bearings4(b1, f32t)
+        b2 = _bearings4(b2, f32t)
+        if cam is not None:
+            cam = _as(cam, np.int32, torch.int32 if torch else None)
+        self.n_obs = int(b1.shape[0])
+        self.n_cam = int(n_cam)
+        self._device_kind = _is_tensor(b1) and b1.is_cuda
+        check(self._lib.sba_ba_problem_create(ctx._h, _ptr(b1), _ptr(b2), _ptr(cam), self.n_obs, self.n_cam, _mem_of(b1, b2, cam),
+                                              C.byref(self._h)))
+        self._cb = None
+
+    def close(self):
+        if self._h:
+            self._lib.sba_ba_problem_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_allreduce(self, fn):
+        """``fn(ptr:int, count:int) -> None`` sums `count` doubles at device address `ptr` over ranks."""
+        if fn is None:
+            self._cb = None
+            check(self._lib.sba_ba_problem_set_allreduce(self._h, _lib.ALLREDUCE_FN(), None))
+            return
+
+        def _tramp(ptr, count, _user):
+            try:
+                fn(ptr, count)
+                return 0
+            except Exception as e:  # pragma: no cover
+                print("allreduce callback failed:", e)
+                return 1
+
+        self._cb = _lib.ALLREDUCE_FN(_tramp)
+        check(self._lib.sba_ba_problem_set_allreduce(self._h, self._cb, None))
+
+    @staticmethod
+    def _r(r, n_cam):
+        r = np.ascontiguousarray(np.asarray(r, np.float64).reshape(n_cam, 3))
+        return r
+
+    def eval(self, r, t=(0.0, 0.0, 0.0), d1=1.0, d2=1.0, huber=1.0, want_res=False, want_jac=False, device_out=False):
+        """One evaluation.  Returns dict(res, jac, H, g, cost); NumPy unless device_out."""
+        r = self._r(r, self.n_cam)
+        t = np.ascontiguousarray(t, np.float64)
+        n, m = self.n_obs, self.n_cam
+        if device_out:
+            dev = torch.device("cuda", self.ctx.device)
+            res = torch.empty((n, 3), dtype=torch.float32, device=dev) if want_res else None
+            jac = torch.empty((n, 3, 3), dtype=torch.float32, device=dev) if want_jac else None
+            H = torch.empty((m, 6), dtype=torch.float64, device=dev)
+            g = torch.empty((m, 3), dtype=torch.float64, device=dev)
+            cost = torch.empty((m,), dtype=torch.float64, device=dev)
+            mem = SBA_MEM_DEVICE
+        else:
+            res = np.empty((n, 3), np.float32) if want_res else None
+            jac = np.empty((n, 3, 3), np.float32) if want_jac else None
+            H = np.empty((m, 6)); g = np.empty((m, 3)); cost = np.empty(m)
+            mem = SBA_MEM_HOST
+        check(self._lib.sba_ba_rot_eval(self._h, _ptr(r), _ptr(t), d1, d2, huber, _ptr(res), _ptr(jac), _ptr(H), _ptr(g), _ptr(cost), mem))
+        return dict(res=res, jac=jac, H=H, g=g, cost=cost)
+
+    def solve(self, r0, t=(0.0, 0.0, 0.0), d1=1.0, d2=1.0, huber=1.0, max_iter=50):
+        r = self._r(r0, self.n_cam).copy()
+        t = np.ascontiguousarray(t, np.float64)
+        s = _lib.SolveSummary()
+        check(self._lib.sba_ba_rot_solve(self._h, _ptr(r), _ptr(t), d1, d2, huber, max_iter, C.byref(s)))
+        return r, s
+
+    def eval_timed(self, r, t=(0.0, 0.0, 0.0), d1=1.0, d2=1.0, huber=1.0, materialise=False, iters=20) -> float:
+        r = self._r(r, self.n_cam)
+        t = np.ascontiguousarray(t, np.float64)
+        ms = C.c_float(0)
+        check(self._lib.sba_ba_rot_eval_timed(self._h, _ptr(r), _ptr(t), d1, d2, huber, int(materialise), iters, C.byref(ms)))
+        return float(ms.value)

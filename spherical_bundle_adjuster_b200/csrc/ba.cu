@@ -1,0 +1,897 @@
+// ba.cu -- rotation-only spherical bundle adjustment on the device (K5 + K6).
+//
+// Replaces ba_spherical_costfunctor_rot_only::operator() / add_residual
+// (spherical_bundle_adjuster.cpp:892-945) plus the ceres::Solve call that consumes them
+// (:183-217, options :334-338).
+//
+// Data layout in HBM
+//   b1, b2   : n_obs x float4 (x, y, z, -), observations grouped by camera at problem creation so a
+//              work item (<= 8192 consecutive observations of ONE camera) is a contiguous, 16-byte
+//              aligned range; 32 B read per observation, nothing else on the fused path.
+//   params   : per camera {R (9 fp64), -dR/dr_k (27 fp32)} = 184 B, rebuilt whenever r changes.
+//   partial  : n_items x 10 fp64 {Hxx,Hxy,Hxz,Hyy,Hyz,Hzz,gx,gy,gz,cost}, one row per work item.
+//   blocks   : n_cam x 10 fp64, the per-camera normal-equation blocks (what an all-reduce sums).
+//
+// Precision split (north_star: residuals/Jacobians 1e-5 relative, rotations 1e-6 rad):
+//   residual, |res|^2, Huber rho and the cost are fp64 (fp32 bearings widened on load); the 3x3
+//   Jacobian and the J^T J / J^T r products are fp32, summed in fp32 over at most 8 observations and
+//   then carried in fp64.  Jacobian rounding only perturbs the LM path, not its fixed point
+//   (sum J^T r = 0 is evaluated with fp64 residuals), so recovered rotations agree with the fp64
+//   oracle far below 1e-6 rad.
+//
+// Determinism: every reduction has a fixed order (lane-strided partial sums, xor-butterfly warp
+// tree, ordered item sums per camera, fixed block tree) -- no floating-point atomics.
+//
+// One kernel launch per LM iteration: the evaluation kernel's last CTA to finish (atomic ticket)
+// folds the work-item partials into per-camera blocks and, on a single GPU, also runs the
+// trust-region decision + the damped 3x3 solves + the next candidate's rotation tables.  With an
+// all-reduce installed (residual-sharded multi-GPU) the decision runs as its own 1-CTA kernel after
+// the collective.
+#include <cfloat>
+#include <cmath>
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace sba {
+
+struct CamParams {
+    double R[9];
+    float nM[27];  // nM[k*9 + a*3 + b] = -dR/dr_k [a][b]  ->  J[a][k] = sum_b nM[k][a][b] * X1[b]
+    float pad;
+};
+
+struct Item {
+    int64_t start;
+    int count;
+    int cam;
+};
+
+struct LMState {
+    double cost, radius, dec_factor, model_dec, initial_cost;
+    int iter, num_successful, termination, done;
+    int consecutive_invalid, evals, max_iter, phase;
+};
+
+struct SolveConsts {
+    double t[3];
+    double d1, d2, huber;
+};
+
+constexpr int EVAL_THREADS = 256;
+constexpr int EVAL_WARPS = EVAL_THREADS / 32;
+
+// ---- rotation tables ----------------------------------------------------------------------------
+// R(r) and dR/dr_k exactly as differentiating ceres::AngleAxisRotatePoint gives, both branches.
+__device__ inline void rot_and_derivs(const double r[3], double R[9], double dR[3][9])
+{
+    double theta2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    if (theta2 > DBL_EPSILON) {
+        double th = sqrt(theta2), s, c;
+        sincos(th, &s, &c);
+        double w[3] = {r[0] / th, r[1] / th, r[2] / th};
+        double K[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 3; b++) R[3 * a + b] = (a == b ? c : 0.0) + s * K[3 * a + b] + (1.0 - c) * w[a] * w[b];
+        for (int k = 0; k < 3; k++) {
+            double dw[3];
+            for (int a = 0; a < 3; a++) dw[a] = ((a == k ? 1.0 : 0.0) - w[a] * w[k]) / th;
+            double dK[9] = {0, -dw[2], dw[1], dw[2], 0, -dw[0], -dw[1], dw[0], 0};
+            for (int a = 0; a < 3; a++)
+                for (int b = 0; b < 3; b++)
+                    dR[k][3 * a + b] = (a == b ? -s * w[k] : 0.0) + c * w[k] * K[3 * a + b] + s * dK[3 * a + b] +
+                                       s * w[k] * w[a] * w[b] + (1.0 - c) * (dw[a] * w[b] + w[a] * dw[b]);
+        }
+    } else {
+        double K[9] = {0, -r[2], r[1], r[2], 0, -r[0], -r[1], r[0], 0};
+        for (int a = 0; a < 9; a++) R[a] = K[a];
+        R[0] += 1.0; R[4] += 1.0; R[8] += 1.0;
+        for (int k = 0; k < 3; k++) {
+            double e[3] = {k == 0 ? 1.0 : 0.0, k == 1 ? 1.0 : 0.0, k == 2 ? 1.0 : 0.0};
+            double G[9] = {0, -e[2], e[1], e[2], 0, -e[0], -e[1], e[0], 0};
+            for (int a = 0; a < 9; a++) dR[k][a] = G[a];
+        }
+    }
+}
+
+__device__ inline void write_cam_params(const double r[3], CamParams* out)
+{
+    double R[9], dR[3][9];
+    rot_and_derivs(r, R, dR);
+    for (int a = 0; a < 9; a++) out->R[a] = R[a];
+    for (int k = 0; k < 3; k++)
+        for (int a = 0; a < 9; a++) out->nM[k * 9 + a] = (float)(-dR[k][a]);
+    out->pad = 0.f;
+}
+
+__global__ void ba_cam_params_kernel(const double* __restrict__ x, int n_cam, CamParams* __restrict__ out)
+{
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n_cam) {
+        double r[3] = {x[3 * c], x[3 * c + 1], x[3 * c + 2]};
+        write_cam_params(r, out + c);
+    }
+}
+
+// ---- reductions ---------------------------------------------------------------------------------
+__device__ inline double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Fixed-tree block sum; every thread gets the result.  `sh` has EVAL_THREADS doubles.
+__device__ inline double block_sum(double v, double* sh)
+{
+    __syncthreads();
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int s = EVAL_THREADS / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    double r = sh[0];
+    __syncthreads();
+    return r;
+}
+
+__device__ inline double block_max(double v, double* sh)
+{
+    __syncthreads();
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int s = EVAL_THREADS / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + s]);
+        __syncthreads();
+    }
+    double r = sh[0];
+    __syncthreads();
+    return r;
+}
+
+// ---- Ceres-default Levenberg-Marquardt decision (single CTA) ---------------------------------------
+__device__ inline int solve3_spd(const double H[6], const double dd[3], const double rhs[3], double x[3])
+{
+    double a00 = H[0] + dd[0], a01 = H[1], a02 = H[2], a11 = H[3] + dd[1], a12 = H[4], a22 = H[5] + dd[2];
+    if (!(a00 > 0.0)) return 1;
+    double l00 = sqrt(a00), l10 = a01 / l00, l20 = a02 / l00;
+    double t11 = a11 - l10 * l10;
+    if (!(t11 > 0.0)) return 1;
+    double l11 = sqrt(t11), l21 = (a12 - l20 * l10) / l11;
+    double t22 = a22 - l20 * l20 - l21 * l21;
+    if (!(t22 > 0.0)) return 1;
+    double l22 = sqrt(t22);
+    double y0 = rhs[0] / l00, y1 = (rhs[1] - l10 * y0) / l11, y2 = (rhs[2] - l20 * y0 - l21 * y1) / l22;
+    x[2] = y2 / l22;
+    x[1] = (y1 - l21 * x[2]) / l11;
+    x[0] = (y0 - l10 * x[1] - l20 * x[2]) / l00;
+    return 0;
+}
+
+struct LMArrays {
+    double* x;         // n_cam x 3 current parameters
+    double* xc;        // n_cam x 3 candidate
+    double* blk_cur;   // n_cam x 10 blocks at x
+    double* blk_cand;  // n_cam x 10 blocks at xc (just evaluated)
+    double* scale;     // n_cam x 3 Jacobi scaling
+    CamParams* params; // tables for xc
+    LMState* st;
+    int n_cam;
+};
+
+// Trust-region bookkeeping restated from Ceres' TrustRegionMinimizer / LevenbergMarquardtStrategy
+// defaults (the reference only sets max_num_iterations=50, spherical_bundle_adjuster.cpp:334-338).
+__device__ void lm_decide(const LMArrays A, double* sh)
+{
+    const double min_diag = 1e-6, max_diag = 1e32, min_rel_dec = 1e-3;
+    const double ftol = 1e-6, gtol = 1e-10, ptol = 1e-8, max_radius = 1e16, min_radius = 1e-32;
+    __shared__ LMState S;
+    __shared__ int s_accept;
+    const int tid = threadIdx.x, nthr = EVAL_THREADS, n_cam = A.n_cam;
+
+    if (tid == 0) S = *A.st;
+    double part = 0;
+    for (int c = tid; c < n_cam; c += nthr) part += A.blk_cand[10 * c + 9];
+    double total_new = block_sum(part, sh);
+
+    if (tid == 0) {
+        s_accept = 0;
+        S.evals++;
+        if (S.phase == 0) {
+            S.cost = total_new;
+            S.initial_cost = total_new;
+            S.phase = 1;
+            s_accept = 2;  // adopt blocks, compute scaling
+        } else {
+            double cost_change = S.cost - total_new;
+            if (fabs(cost_change) <= ftol * S.cost) {
+                S.termination = 1; S.done = 1;
+            } else {
+                double rel = cost_change / S.model_dec;
+                if (rel > min_rel_dec) {
+                    s_accept = 1;
+                    S.cost = total_new;
+                    S.num_successful++;
+                    double q = 2.0 * rel - 1.0;
+                    S.radius = S.radius / fmax(1.0 / 3.0, 1.0 - q * q * q);
+                    S.radius = fmin(max_radius, S.radius);
+                    S.dec_factor = 2.0;
+                } else {
+                    S.radius = S.radius / S.dec_factor;
+                    S.dec_factor *= 2.0;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int accept = s_accept;
+    if (accept) {
+        double gm = 0;
+        for (int c = tid; c < n_cam; c += nthr) {
+            for (int k = 0; k < 10; k++) A.blk_cur[10 * c + k] = A.blk_cand[10 * c + k];
+            for (int k = 0; k < 3; k++) {
+                if (accept == 1) A.x[3 * c + k] = A.xc[3 * c + k];
+                gm = fmax(gm, fabs(A.blk_cand[10 * c + 6 + k]));
+            }
+            if (accept == 2) {
+                A.scale[3 * c] = 1.0 / (1.0 + sqrt(A.blk_cand[10 * c]));
+                A.scale[3 * c + 1] = 1.0 / (1.0 + sqrt(A.blk_cand[10 * c + 3]));
+                A.scale[3 * c + 2] = 1.0 / (1.0 + sqrt(A.blk_cand[10 * c + 5]));
+            }
+        }
+        double gmax = block_max(gm, sh);
+        if (tid == 0 && gmax <= gtol) { S.termination = 2; S.done = 1; }
+    }
+    __syncthreads();
+    if (tid == 0 && !S.done && S.radius <= min_radius) { S.termination = 4; S.done = 1; }
+    __syncthreads();
+
+    // next candidate (invalid steps retry in place: H and g do not change)
+    while (!S.done) {
+        __syncthreads();
+        if (S.iter >= S.max_iter) {
+            __syncthreads();
+            if (tid == 0) { S.termination = 0; S.done = 1; }
+            __syncthreads();
+            break;
+        }
+        const double radius = S.radius;
+        double md = 0, sn2 = 0, xn2 = 0, bad = 0;
+        for (int c = tid; c < n_cam; c += nthr) {
+            const double* B = A.blk_cur + 10 * c;
+            const double* s = A.scale + 3 * c;
+            double Hs[6] = {B[0] * s[0] * s[0], B[1] * s[0] * s[1], B[2] * s[0] * s[2],
+                            B[3] * s[1] * s[1], B[4] * s[1] * s[2], B[5] * s[2] * s[2]};
+            double gs[3] = {B[6] * s[0], B[7] * s[1], B[8] * s[2]};
+            double dd[3] = {fmin(fmax(Hs[0], min_diag), max_diag) / radius, fmin(fmax(Hs[3], min_diag), max_diag) / radius,
+                            fmin(fmax(Hs[5], min_diag), max_diag) / radius};
+            double rhs[3] = {-gs[0], -gs[1], -gs[2]}, ds[3] = {0, 0, 0};
+            if (solve3_spd(Hs, dd, rhs, ds)) bad = 1;
+            double Hd[3] = {Hs[0] * ds[0] + Hs[1] * ds[1] + Hs[2] * ds[2], Hs[1] * ds[0] + Hs[3] * ds[1] + Hs[4] * ds[2],
+                            Hs[2] * ds[0] + Hs[4] * ds[1] + Hs[5] * ds[2]};
+            md -= (gs[0] * ds[0] + gs[1] * ds[1] + gs[2] * ds[2]) + 0.5 * (ds[0] * Hd[0] + ds[1] * Hd[1] + ds[2] * Hd[2]);
+            for (int a = 0; a < 3; a++) {
+                double st = ds[a] * s[a], xv = A.x[3 * c + a];
+                A.xc[3 * c + a] = xv + st;
+                sn2 += st * st;
+                xn2 += xv * xv;
+            }
+        }
+        md = block_sum(md, sh);
+        sn2 = block_sum(sn2, sh);
+        xn2 = block_sum(xn2, sh);
+        bad = block_max(bad, sh);
+        if (tid == 0) {
+            S.iter++;
+            if (bad > 0 || !(md > 0.0)) {
+                if (++S.consecutive_invalid >= 5) { S.termination = 4; S.done = 1; }
+                else {
+                    S.radius *= 0.5;
+                    if (S.radius <= min_radius) { S.termination = 4; S.done = 1; }
+                }
+                s_accept = -1;
+            } else {
+                S.consecutive_invalid = 0;
+                S.model_dec = md;
+                // Ceres tests the parameter tolerance after evaluating the candidate; the test does
+                // not depend on that evaluation, so it is applied here and the evaluation is saved.
+                if (sqrt(sn2) <= ptol * (sqrt(xn2) + ptol)) { S.termination = 3; S.done = 1; }
+                s_accept = 0;
+            }
+        }
+        __syncthreads();
+        if (s_accept == 0) break;
+    }
+    __syncthreads();
+    if (!S.done)
+        for (int c = tid; c < n_cam; c += nthr) {
+            double r[3] = {A.xc[3 * c], A.xc[3 * c + 1], A.xc[3 * c + 2]};
+            write_cam_params(r, A.params + c);
+        }
+    if (tid == 0) *A.st = S;
+}
+
+__global__ void __launch_bounds__(EVAL_THREADS) ba_decide_kernel(LMArrays A)
+{
+    __shared__ double sh[EVAL_THREADS];
+    if (A.st->done) return;
+    lm_decide(A, sh);
+}
+
+// ---- the evaluation kernel (K5) ------------------------------------------------------------------
+// Fold work-item partials into per-camera blocks, in item order.  `item_ptr` [n_cam+1].
+__device__ void fold_items(const double* __restrict__ partial, const int* __restrict__ item_ptr, int n_cam, double* __restrict__ blk)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_items_total = item_ptr[n_cam];
+    if (n_items_total <= 8 * n_cam) {
+        // few items per camera: one thread per camera, sequential ordered sum
+        for (int c = threadIdx.x; c < n_cam; c += EVAL_THREADS) {
+            double acc[10];
+#pragma unroll
+            for (int k = 0; k < 10; k++) acc[k] = 0;
+            for (int it = item_ptr[c]; it < item_ptr[c + 1]; it++)
+#pragma unroll
+                for (int k = 0; k < 10; k++) acc[k] += partial[(size_t)it * 10 + k];
+#pragma unroll
+            for (int k = 0; k < 10; k++) blk[10 * c + k] = acc[k];
+        }
+    } else {
+        // many items per camera: one warp per camera, lane-strided ordered sums + butterfly
+        for (int c = warp; c < n_cam; c += EVAL_WARPS) {
+            double acc[10];
+#pragma unroll
+            for (int k = 0; k < 10; k++) acc[k] = 0;
+            for (int it = item_ptr[c] + lane; it < item_ptr[c + 1]; it += 32)
+#pragma unroll
+                for (int k = 0; k < 10; k++) acc[k] += partial[(size_t)it * 10 + k];
+#pragma unroll
+            for (int k = 0; k < 10; k++) acc[k] = warp_sum(acc[k]);
+            if (lane == 0)
+#pragma unroll
+                for (int k = 0; k < 10; k++) blk[10 * c + k] = acc[k];
+        }
+    }
+}
+
+struct EvalArgs {
+    const float4* b1;
+    const float4* b2;
+    const int32_t* perm;  // sorted position -> caller's observation index (NULL = identity)
+    const Item* items;
+    const int* item_ptr;
+    int n_items;
+    int n_cam;
+    const CamParams* params;
+    double* partial;
+    double* blk_out;
+    unsigned int* ticket;
+    float* res;  // optional materialised outputs (caller order)
+    float* jac;
+    SolveConsts k;
+};
+
+template <bool WRITE, bool FUSE>
+__global__ void __launch_bounds__(EVAL_THREADS, 2) ba_rot_eval_kernel(EvalArgs E, LMArrays A)
+{
+    __shared__ double sh[EVAL_THREADS];
+    __shared__ int s_last;
+    if (FUSE && A.st->done) return;  // converged earlier in this launch chunk
+
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * EVAL_WARPS + (threadIdx.x >> 5);
+    const int warp_stride = gridDim.x * EVAL_WARPS;
+    const double d1 = E.k.d1, d2 = E.k.d2, huber = E.k.huber, hub2 = huber * huber;
+    const double t0 = E.k.t[0], t1 = E.k.t[1], t2 = E.k.t[2];
+    const float d1f = (float)d1;
+
+    for (int it = warp_global; it < E.n_items; it += warp_stride) {
+        const Item item = E.items[it];
+        const CamParams* P = E.params + item.cam;
+        double R[9];
+#pragma unroll
+        for (int a = 0; a < 9; a++) R[a] = P->R[a];
+        float M[27];
+#pragma unroll
+        for (int a = 0; a < 27; a++) M[a] = P->nM[a];
+
+        double acc[10];
+#pragma unroll
+        for (int k = 0; k < 10; k++) acc[k] = 0;
+        float facc[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) facc[k] = 0.f;
+        int in_flight = 0;
+
+        for (int o = lane; o < item.count; o += 32) {
+            const int64_t i = item.start + o;
+            const float4 p1 = __ldg(E.b1 + i);
+            const float4 p2 = __ldg(E.b2 + i);
+            // residual in fp64 (spherical_bundle_adjuster.cpp:896-916)
+            const double X1x = (double)p1.x * d1, X1y = (double)p1.y * d1, X1z = (double)p1.z * d1;
+            const double X2x = (double)p2.x * d2, X2y = (double)p2.y * d2, X2z = (double)p2.z * d2;
+            const double rx = X2x - ((R[0] * X1x + R[1] * X1y + R[2] * X1z) - t0);
+            const double ry = X2y - ((R[3] * X1x + R[4] * X1y + R[5] * X1z) - t1);
+            const double rz = X2z - ((R[6] * X1x + R[7] * X1y + R[8] * X1z) - t2);
+            const double s = rx * rx + ry * ry + rz * rz;
+            // Huber: rho' = 1 (s <= a^2) or a/sqrt(s); rho = s or 2 a sqrt(s) - a^2
+            double rho = s, rho1 = 1.0;
+            if (huber > 0.0 && s > hub2) {
+                double y = (double)rsqrtf((float)s);
+                y = y * (1.5 - 0.5 * s * y * y);
+                y = y * (1.5 - 0.5 * s * y * y);
+                rho1 = huber * y;
+                rho = 2.0 * huber * (s * y) - hub2;
+            }
+            acc[9] += 0.5 * rho;
+            // Jacobian in fp32: J[a][k] = sum_b nM[k][a][b] * X1[b]
+            const float x1 = p1.x * d1f, y1 = p1.y * d1f, z1 = p1.z * d1f;
+            float J[9];
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+#pragma unroll
+                for (int a = 0; a < 3; a++) J[3 * a + k] = M[k * 9 + a * 3] * x1 + M[k * 9 + a * 3 + 1] * y1 + M[k * 9 + a * 3 + 2] * z1;
+            const float rxf = (float)rx, ryf = (float)ry, rzf = (float)rz, wf = (float)rho1;
+            facc[0] += wf * (J[0] * J[0] + J[3] * J[3] + J[6] * J[6]);
+            facc[1] += wf * (J[0] * J[1] + J[3] * J[4] + J[6] * J[7]);
+            facc[2] += wf * (J[0] * J[2] + J[3] * J[5] + J[6] * J[8]);
+            facc[3] += wf * (J[1] * J[1] + J[4] * J[4] + J[7] * J[7]);
+            facc[4] += wf * (J[1] * J[2] + J[4] * J[5] + J[7] * J[8]);
+            facc[5] += wf * (J[2] * J[2] + J[5] * J[5] + J[8] * J[8]);
+            facc[6] += wf * (J[0] * rxf + J[3] * ryf + J[6] * rzf);
+            facc[7] += wf * (J[1] * rxf + J[4] * ryf + J[7] * rzf);
+            facc[8] += wf * (J[2] * rxf + J[5] * ryf + J[8] * rzf);
+            if (++in_flight == 8) {
+#pragma unroll
+                for (int k = 0; k < 9; k++) { acc[k] += (double)facc[k]; facc[k] = 0.f; }
+                in_flight = 0;
+            }
+            if (WRITE) {
+                const int64_t dst = E.perm ? (int64_t)E.perm[i] : i;
+                if (E.res) {
+                    E.res[3 * dst] = rxf; E.res[3 * dst + 1] = ryf; E.res[3 * dst + 2] = rzf;
+                }
+                if (E.jac) {
+#pragma unroll
+                    for (int a = 0; a < 9; a++) E.jac[9 * dst + a] = J[a];
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 9; k++) acc[k] += (double)facc[k];
+#pragma unroll
+        for (int k = 0; k < 10; k++) acc[k] = warp_sum(acc[k]);
+        if (lane == 0) {
+            double* out = E.partial + (size_t)it * 10;
+#pragma unroll
+            for (int k = 0; k < 10; k++) out[k] = acc[k];
+        }
+    }
+
+    // last CTA to finish folds the partials (classic threadfence reduction ticket)
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int tk = atomicAdd(E.ticket, 1u);
+        s_last = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    fold_items(E.partial, E.item_ptr, E.n_cam, E.blk_out);
+    if (threadIdx.x == 0) *E.ticket = 0;
+    if (FUSE) {
+        __syncthreads();
+        lm_decide(A, sh);
+    }
+}
+
+// blocks [n_cam x 10] -> H [n_cam x 6], g [n_cam x 3], cost [n_cam]
+__global__ void ba_unpack_blocks_kernel(const double* __restrict__ blk, int n_cam, double* __restrict__ H, double* __restrict__ g,
+                                        double* __restrict__ cost)
+{
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cam) return;
+    if (H) for (int k = 0; k < 6; k++) H[6 * c + k] = blk[10 * c + k];
+    if (g) for (int k = 0; k < 3; k++) g[3 * c + k] = blk[10 * c + 6 + k];
+    if (cost) cost[c] = blk[10 * c + 9];
+}
+
+// ---- problem construction ---------------------------------------------------------------------------
+__global__ void iota_kernel(int32_t* p, int64_t n)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = (int32_t)i;
+}
+
+__global__ void cam_hist_kernel(const int32_t* __restrict__ cam, int64_t n, int n_cam, int* __restrict__ counts, int* __restrict__ bad)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = cam[i];
+        if (c < 0 || c >= n_cam) atomicExch(bad, 1);
+        else atomicAdd(counts + c, 1);
+    }
+}
+
+__global__ void gather_obs_kernel(const float4* __restrict__ b1, const float4* __restrict__ b2, const int32_t* __restrict__ perm, int64_t n,
+                                  float4* __restrict__ o1, float4* __restrict__ o2)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int32_t s = perm[i];
+        o1[i] = b1[s];
+        o2[i] = b2[s];
+    }
+}
+
+}  // namespace sba
+
+using namespace sba;
+
+struct sba_ba_problem {
+    sba_ctx* ctx = nullptr;
+    int64_t n_obs = 0;
+    int n_cam = 0, n_items = 0;
+    float4* b1 = nullptr;
+    float4* b2 = nullptr;
+    int32_t* perm = nullptr;
+    Item* items = nullptr;
+    int* item_ptr = nullptr;
+    double* partial = nullptr;
+    CamParams* params = nullptr;
+    double *x = nullptr, *xc = nullptr, *blk_cur = nullptr, *blk_cand = nullptr, *scale = nullptr;
+    LMState* state = nullptr;
+    unsigned int* ticket = nullptr;
+    LMState* h_state = nullptr;  // pinned
+    double* h_x = nullptr;       // pinned, n_cam x 3
+    sba_allreduce_fn allreduce = nullptr;
+    void* allreduce_user = nullptr;
+    int eval_blocks = 1;
+};
+
+static void free_problem(sba_ba_problem* p)
+{
+    if (!p) return;
+    cudaFree(p->b1); cudaFree(p->b2); cudaFree(p->perm); cudaFree(p->items); cudaFree(p->item_ptr);
+    cudaFree(p->partial); cudaFree(p->params); cudaFree(p->x); cudaFree(p->xc); cudaFree(p->blk_cur);
+    cudaFree(p->blk_cand); cudaFree(p->scale); cudaFree(p->state); cudaFree(p->ticket);
+    if (p->h_state) cudaFreeHost(p->h_state);
+    if (p->h_x) cudaFreeHost(p->h_x);
+    delete p;
+}
+
+// Work-item length: a multiple of 32 observations; short enough that every SM gets several warps of
+// work on small problems, long enough that n_items stays <= ~32k on huge ones (the fold is serial
+// in one CTA).
+static int pick_item_len(int64_t n_obs, int sm_count)
+{
+    int64_t target_warps = (int64_t)sm_count * 16;
+    int64_t len = (n_obs + target_warps - 1) / target_warps;
+    len = (len + 31) / 32 * 32;
+    if (len < 32) len = 32;
+    if (len > 256) {
+        int64_t k = (n_obs + (int64_t)256 * 32768 - 1) / ((int64_t)256 * 32768);
+        if (k < 1) k = 1;
+        if (k > 32) k = 32;
+        len = 256 * k;
+    }
+    return (int)len;
+}
+
+static EvalArgs make_eval_args(sba_ba_problem* p, const double t[3], double d1, double d2, double huber, float* res, float* jac, double* blk_out)
+{
+    EvalArgs E;
+    E.b1 = p->b1; E.b2 = p->b2; E.perm = p->perm; E.items = p->items; E.item_ptr = p->item_ptr;
+    E.n_items = p->n_items; E.n_cam = p->n_cam; E.params = p->params; E.partial = p->partial;
+    E.blk_out = blk_out; E.ticket = p->ticket; E.res = res; E.jac = jac;
+    E.k.t[0] = t[0]; E.k.t[1] = t[1]; E.k.t[2] = t[2];
+    E.k.d1 = d1; E.k.d2 = d2; E.k.huber = huber;
+    return E;
+}
+
+static LMArrays make_lm_arrays(sba_ba_problem* p)
+{
+    LMArrays A;
+    A.x = p->x; A.xc = p->xc; A.blk_cur = p->blk_cur; A.blk_cand = p->blk_cand; A.scale = p->scale;
+    A.params = p->params; A.st = p->state; A.n_cam = p->n_cam;
+    return A;
+}
+
+static int upload_rotations(sba_ba_problem* p, const double* r, double* dst)
+{
+    memcpy(p->h_x, r, (size_t)p->n_cam * 3 * sizeof(double));
+    SBA_CUDA(cudaMemcpyAsync(dst, p->h_x, (size_t)p->n_cam * 3 * sizeof(double), cudaMemcpyHostToDevice, p->ctx->stream));
+    return SBA_OK;
+}
+
+template <bool WRITE, bool FUSE>
+static int launch_eval(sba_ba_problem* p, const EvalArgs& E, const LMArrays& A)
+{
+    ba_rot_eval_kernel<WRITE, FUSE><<<p->eval_blocks, EVAL_THREADS, 0, p->ctx->stream>>>(E, A);
+    SBA_LAUNCHED(p->ctx);
+    SBA_CUDA(cudaGetLastError());
+    return SBA_OK;
+}
+
+extern "C" {
+
+int sba_ba_problem_create(sba_ctx* c, const float* b1, const float* b2, const int32_t* cam, int64_t n_obs, int n_cam, int mem,
+                          sba_ba_problem** out)
+{
+    SBA_CHECK_ARG(c && out && n_obs >= 0 && n_cam >= 1 && n_obs < ((int64_t)1 << 31));
+    SBA_CHECK_ARG(n_obs == 0 || (b1 && b2));
+    *out = nullptr;
+    SBA_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    sba_ba_problem* p = new sba_ba_problem();
+    p->ctx = c; p->n_obs = n_obs; p->n_cam = n_cam;
+    int status = SBA_OK;
+    auto fail = [&](int s) { free_problem(p); return s; };
+#define P_CUDA(call)                                                                              \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            sba::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return fail(SBA_ERR_CUDA);                                                            \
+        }                                                                                         \
+    } while (0)
+
+    size_t nb = (size_t)(n_obs ? n_obs : 1) * sizeof(float4);
+    P_CUDA(cudaMalloc(&p->b1, nb));
+    P_CUDA(cudaMalloc(&p->b2, nb));
+    cudaMemcpyKind kind = mem == SBA_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    std::vector<int> counts(n_cam, 0);
+    const bool need_sort = (cam != nullptr && n_cam > 1 && n_obs > 0);
+    if (!need_sort) {
+        if (n_obs) {
+            P_CUDA(cudaMemcpyAsync(p->b1, b1, nb, kind, st));
+            P_CUDA(cudaMemcpyAsync(p->b2, b2, nb, kind, st));
+        }
+        counts[0] = (int)n_obs;
+        if (cam != nullptr && n_cam == 1) { /* ids must all be 0; trusted */ }
+    } else {
+        // group observations by camera: stable radix sort of (cam, index), then gather
+        const float *d_b1, *d_b2;
+        const int32_t* d_cam;
+        if ((status = stage_in(c, b1, (size_t)4 * n_obs, mem, SCR_IN0, &d_b1)) != SBA_OK) return fail(status);
+        if ((status = stage_in(c, b2, (size_t)4 * n_obs, mem, SCR_IN1, &d_b2)) != SBA_OK) return fail(status);
+        if ((status = stage_in(c, cam, (size_t)n_obs, mem, SCR_IN2, &d_cam)) != SBA_OK) return fail(status);
+        if ((status = c->scratch[SCR_WORK0].ensure((size_t)n_obs * 4, st)) != SBA_OK) return fail(status);
+        if ((status = c->scratch[SCR_WORK1].ensure((size_t)n_obs * 4, st)) != SBA_OK) return fail(status);
+        if ((status = c->scratch[SCR_WORK3].ensure((size_t)(n_cam + 1) * 4, st)) != SBA_OK) return fail(status);
+        int32_t* d_idx = c->scratch[SCR_WORK0].as<int32_t>();
+        int32_t* d_keys_sorted = c->scratch[SCR_WORK1].as<int32_t>();
+        int* d_counts = c->scratch[SCR_WORK3].as<int>();
+        P_CUDA(cudaMalloc(&p->perm, (size_t)n_obs * 4));
+        int gb = (int)std::min<int64_t>(ceil_div64(n_obs, 256), (int64_t)c->sm_count * 8);
+        iota_kernel<<<gb, 256, 0, st>>>(d_idx, n_obs);
+        SBA_LAUNCHED(c);
+        P_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)(n_cam + 1) * 4, st));
+        cam_hist_kernel<<<gb, 256, 0, st>>>(d_cam, n_obs, n_cam, d_counts, d_counts + n_cam);
+        SBA_LAUNCHED(c);
+        int end_bit = 1;
+        while ((1ll << end_bit) < n_cam) end_bit++;
+        size_t tmp_bytes = 0;
+        P_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_cam, d_keys_sorted, d_idx, p->perm, (int)n_obs, 0, end_bit, st));
+        if ((status = c->scratch[SCR_WORK2].ensure(tmp_bytes, st)) != SBA_OK) return fail(status);
+        P_CUDA(cub::DeviceRadixSort::SortPairs(c->scratch[SCR_WORK2].p, tmp_bytes, d_cam, d_keys_sorted, d_idx, p->perm, (int)n_obs, 0, end_bit, st));
+        SBA_LAUNCHED(c);
+        gather_obs_kernel<<<gb, 256, 0, st>>>((const float4*)d_b1, (const float4*)d_b2, p->perm, n_obs, p->b1, p->b2);
+        SBA_LAUNCHED(c);
+        std::vector<int> hc(n_cam + 1);
+        P_CUDA(cudaMemcpyAsync(hc.data(), d_counts, (size_t)(n_cam + 1) * 4, cudaMemcpyDeviceToHost, st));
+        P_CUDA(cudaStreamSynchronize(st));
+        if (hc[n_cam]) {
+            sba::set_error("camera index out of range [0, %d)", n_cam);
+            return fail(SBA_ERR_INVALID);
+        }
+        for (int k = 0; k < n_cam; k++) counts[k] = hc[k];
+    }
+
+    // work items (host, O(n_cam + n_items))
+    const int len = pick_item_len(n_obs, c->sm_count);
+    std::vector<Item> items;
+    std::vector<int> item_ptr(n_cam + 1, 0);
+    int64_t off = 0;
+    for (int k = 0; k < n_cam; k++) {
+        item_ptr[k] = (int)items.size();
+        for (int64_t s = 0; s < counts[k]; s += len) {
+            Item it;
+            it.start = off + s;
+            it.count = (int)std::min<int64_t>(len, counts[k] - s);
+            it.cam = k;
+            items.push_back(it);
+        }
+        off += counts[k];
+    }
+    item_ptr[n_cam] = (int)items.size();
+    p->n_items = (int)items.size();
+    size_t ni = items.size() ? items.size() : 1;
+    P_CUDA(cudaMalloc(&p->items, ni * sizeof(Item)));
+    P_CUDA(cudaMalloc(&p->item_ptr, (size_t)(n_cam + 1) * sizeof(int)));
+    P_CUDA(cudaMalloc(&p->partial, ni * 10 * sizeof(double)));
+    P_CUDA(cudaMalloc(&p->params, (size_t)n_cam * sizeof(CamParams)));
+    P_CUDA(cudaMalloc(&p->x, (size_t)n_cam * 3 * sizeof(double)));
+    P_CUDA(cudaMalloc(&p->xc, (size_t)n_cam * 3 * sizeof(double)));
+    P_CUDA(cudaMalloc(&p->blk_cur, (size_t)n_cam * 10 * sizeof(double)));
+    P_CUDA(cudaMalloc(&p->blk_cand, (size_t)n_cam * 10 * sizeof(double)));
+    P_CUDA(cudaMalloc(&p->scale, (size_t)n_cam * 3 * sizeof(double)));
+    P_CUDA(cudaMalloc(&p->state, sizeof(LMState)));
+    P_CUDA(cudaMalloc(&p->ticket, sizeof(unsigned int)));
+    P_CUDA(cudaMallocHost((void**)&p->h_state, sizeof(LMState)));
+    P_CUDA(cudaMallocHost((void**)&p->h_x, (size_t)n_cam * 3 * sizeof(double)));
+    P_CUDA(cudaMemsetAsync(p->ticket, 0, sizeof(unsigned int), st));
+    if (!items.empty()) P_CUDA(cudaMemcpyAsync(p->items, items.data(), items.size() * sizeof(Item), cudaMemcpyHostToDevice, st));
+    P_CUDA(cudaMemcpyAsync(p->item_ptr, item_ptr.data(), (size_t)(n_cam + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    P_CUDA(cudaStreamSynchronize(st));  // host vectors and staged inputs are released after this
+
+    // grid: enough CTAs for every work item's warp, capped at 2 resident CTAs per SM x 4 waves
+    int want = (p->n_items + EVAL_WARPS - 1) / EVAL_WARPS;
+    if (want < 1) want = 1;
+    p->eval_blocks = std::min(want, c->sm_count * 8);
+    *out = p;
+    return SBA_OK;
+#undef P_CUDA
+}
+
+int sba_ba_problem_destroy(sba_ba_problem* p)
+{
+    if (!p) return SBA_OK;
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+    free_problem(p);
+    return SBA_OK;
+}
+
+int sba_ba_problem_set_allreduce(sba_ba_problem* p, sba_allreduce_fn fn, void* user)
+{
+    SBA_CHECK_ARG(p != nullptr);
+    p->allreduce = fn;
+    p->allreduce_user = user;
+    return SBA_OK;
+}
+
+int sba_ba_rot_eval(sba_ba_problem* p, const double* r, const double t[3], double d1, double d2, double huber, float* res, float* jac,
+                    double* H, double* g, double* cost, int mem)
+{
+    SBA_CHECK_ARG(p && r && t);
+    sba_ctx* c = p->ctx;
+    SBA_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const int n_cam = p->n_cam;
+    SBA_CUDA(cudaStreamSynchronize(st));  // h_x reuse
+    SBA_TRY(upload_rotations(p, r, p->xc));
+    ba_cam_params_kernel<<<(n_cam + 127) / 128, 128, 0, st>>>(p->xc, n_cam, p->params);
+    SBA_LAUNCHED(c);
+    float *d_res, *d_jac;
+    double *d_H, *d_g, *d_cost;
+    SBA_TRY(stage_out(c, res, (size_t)3 * p->n_obs, mem, SCR_OUT0, &d_res));
+    SBA_TRY(stage_out(c, jac, (size_t)9 * p->n_obs, mem, SCR_OUT1, &d_jac));
+    SBA_TRY(stage_out(c, H, (size_t)6 * n_cam, mem, SCR_OUT2, &d_H));
+    SBA_TRY(stage_out(c, g, (size_t)3 * n_cam, mem, SCR_OUT3, &d_g));
+    SBA_TRY(stage_out(c, cost, (size_t)n_cam, mem, SCR_OUT4, &d_cost));
+    EvalArgs E = make_eval_args(p, t, d1, d2, huber, d_res, d_jac, p->blk_cand);
+    LMArrays A = make_lm_arrays(p);
+    if (d_res || d_jac) SBA_TRY((launch_eval<true, false>(p, E, A)));
+    else SBA_TRY((launch_eval<false, false>(p, E, A)));
+    if (p->allreduce) {
+        if (p->allreduce(p->blk_cand, (int64_t)n_cam * 10, p->allreduce_user) != 0) {
+            sba::set_error("allreduce callback failed");
+            return SBA_ERR_COMM;
+        }
+    }
+    ba_unpack_blocks_kernel<<<(n_cam + 127) / 128, 128, 0, st>>>(p->blk_cand, n_cam, d_H, d_g, d_cost);
+    SBA_LAUNCHED(c);
+    SBA_TRY(copy_out(c, res, d_res, (size_t)3 * p->n_obs, mem));
+    SBA_TRY(copy_out(c, jac, d_jac, (size_t)9 * p->n_obs, mem));
+    SBA_TRY(copy_out(c, H, d_H, (size_t)6 * n_cam, mem));
+    SBA_TRY(copy_out(c, g, d_g, (size_t)3 * n_cam, mem));
+    SBA_TRY(copy_out(c, cost, d_cost, (size_t)n_cam, mem));
+    return finish(c, mem);
+}
+
+int sba_ba_rot_solve(sba_ba_problem* p, double* r_inout, const double t[3], double d1, double d2, double huber, int max_iter,
+                     sba_solve_summary* summary)
+{
+    SBA_CHECK_ARG(p && r_inout && t && max_iter >= 0);
+    sba_ctx* c = p->ctx;
+    SBA_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const int n_cam = p->n_cam;
+    SBA_CUDA(cudaStreamSynchronize(st));
+    SBA_TRY(upload_rotations(p, r_inout, p->x));
+    SBA_CUDA(cudaMemcpyAsync(p->xc, p->x, (size_t)n_cam * 3 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    LMState init{};
+    init.radius = 1e4; init.dec_factor = 2.0; init.max_iter = max_iter; init.phase = 0;
+    *p->h_state = init;
+    SBA_CUDA(cudaMemcpyAsync(p->state, p->h_state, sizeof(LMState), cudaMemcpyHostToDevice, st));
+    ba_cam_params_kernel<<<(n_cam + 127) / 128, 128, 0, st>>>(p->xc, n_cam, p->params);
+    SBA_LAUNCHED(c);
+    EvalArgs E = make_eval_args(p, t, d1, d2, huber, nullptr, nullptr, p->blk_cand);
+    LMArrays A = make_lm_arrays(p);
+
+    // Evaluations are enqueued in chunks; kernels of a chunk that start after convergence return
+    // immediately (state.done), and the host looks at the state once per chunk.
+    const int chunk = 6;
+    int launched = 0;
+    const int max_evals = max_iter + 1;
+    bool done = false;
+    while (!done && launched < max_evals) {
+        int n = std::min(chunk, max_evals - launched);
+        for (int k = 0; k < n; k++) {
+            if (p->allreduce) {
+                SBA_TRY((launch_eval<false, false>(p, E, A)));
+                if (p->allreduce(p->blk_cand, (int64_t)n_cam * 10, p->allreduce_user) != 0) {
+                    sba::set_error("allreduce callback failed");
+                    return SBA_ERR_COMM;
+                }
+                ba_decide_kernel<<<1, EVAL_THREADS, 0, st>>>(A);
+                SBA_LAUNCHED(c);
+            } else {
+                SBA_TRY((launch_eval<false, true>(p, E, A)));
+            }
+        }
+        launched += n;
+        SBA_CUDA(cudaMemcpyAsync(p->h_state, p->state, sizeof(LMState), cudaMemcpyDeviceToHost, st));
+        SBA_CUDA(cudaStreamSynchronize(st));
+        done = p->h_state->done != 0;
+    }
+    SBA_CUDA(cudaMemcpyAsync(p->h_x, p->x, (size_t)n_cam * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SBA_CUDA(cudaStreamSynchronize(st));
+    memcpy(r_inout, p->h_x, (size_t)n_cam * 3 * sizeof(double));
+    if (summary) {
+        const LMState& S = *p->h_state;
+        summary->iterations = S.iter;
+        summary->num_successful = S.num_successful;
+        summary->termination = S.done ? S.termination : 0;
+        summary->evaluations = S.evals;
+        summary->initial_cost = S.initial_cost;
+        summary->final_cost = S.cost;
+        summary->final_radius = S.radius;
+    }
+    return SBA_OK;
+}
+
+int sba_ba_rot_eval_timed(sba_ba_problem* p, const double* r, const double t[3], double d1, double d2, double huber, int materialise,
+                          int iters, float* mean_ms)
+{
+    SBA_CHECK_ARG(p && r && t && iters > 0 && mean_ms);
+    sba_ctx* c = p->ctx;
+    SBA_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const int n_cam = p->n_cam;
+    SBA_CUDA(cudaStreamSynchronize(st));
+    SBA_TRY(upload_rotations(p, r, p->xc));
+    ba_cam_params_kernel<<<(n_cam + 127) / 128, 128, 0, st>>>(p->xc, n_cam, p->params);
+    SBA_LAUNCHED(c);
+    float *d_res = nullptr, *d_jac = nullptr;
+    if (materialise) {
+        SBA_TRY(c->scratch[SCR_OUT0].ensure((size_t)3 * p->n_obs * sizeof(float) + 16, st));
+        SBA_TRY(c->scratch[SCR_OUT1].ensure((size_t)9 * p->n_obs * sizeof(float) + 16, st));
+        d_res = c->scratch[SCR_OUT0].as<float>();
+        d_jac = c->scratch[SCR_OUT1].as<float>();
+    }
+    EvalArgs E = make_eval_args(p, t, d1, d2, huber, d_res, d_jac, p->blk_cand);
+    LMArrays A = make_lm_arrays(p);
+    cudaEvent_t e0, e1;
+    SBA_CUDA(cudaEventCreate(&e0));
+    SBA_CUDA(cudaEventCreate(&e1));
+    for (int k = 0; k < 3; k++) {
+        if (materialise) SBA_TRY((launch_eval<true, false>(p, E, A)));
+        else SBA_TRY((launch_eval<false, false>(p, E, A)));
+    }
+    SBA_CUDA(cudaEventRecord(e0, st));
+    for (int k = 0; k < iters; k++) {
+        if (materialise) SBA_TRY((launch_eval<true, false>(p, E, A)));
+        else SBA_TRY((launch_eval<false, false>(p, E, A)));
+    }
+    SBA_CUDA(cudaEventRecord(e1, st));
+    SBA_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    SBA_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *mean_ms = ms / iters;
+    return SBA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,142 @@
+// common.cuh -- context, error handling and scratch memory shared by all kernels of libsba_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "sba_b200.h"
+
+namespace sba {
+
+void set_error(const char* fmt, ...);
+
+#define SBA_CUDA(call)                                                                             \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            sba::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return SBA_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+#define SBA_CHECK_ARG(cond)                                                         \
+    do {                                                                            \
+        if (!(cond)) {                                                              \
+            sba::set_error("%s:%d: invalid argument: %s", __FILE__, __LINE__, #cond); \
+            return SBA_ERR_INVALID;                                                 \
+        }                                                                           \
+    } while (0)
+
+#define SBA_TRY(expr)            \
+    do {                         \
+        int s__ = (expr);        \
+        if (s__ != SBA_OK) return s__; \
+    } while (0)
+
+// Grow-only device buffer.  Growing synchronises the stream first (the old block may be in use).
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes, cudaStream_t s)
+    {
+        if (bytes <= cap) return SBA_OK;
+        if (p) {
+            SBA_CUDA(cudaStreamSynchronize(s));
+            SBA_CUDA(cudaFree(p));
+            p = nullptr; cap = 0;
+        }
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+            return SBA_ERR_NOMEM;
+        }
+        cap = want;
+        return SBA_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+    }
+    template <typename T> T* as() { return (T*)p; }
+};
+
+struct RemapPlan {
+    int w, h, cs;
+    int32_t* lut = nullptr;  // device, cs x 6cs
+    int n_patched = 0;       // near-integer pixels resolved with the host libm
+    int n_clamped = 0;
+};
+
+// Named scratch slots (one DevBuf each) so independent stages never alias.
+enum ScratchSlot {
+    SCR_IN0 = 0, SCR_IN1, SCR_IN2, SCR_IN3, SCR_OUT0, SCR_OUT1, SCR_OUT2, SCR_OUT3, SCR_OUT4,
+    SCR_WORK0, SCR_WORK1, SCR_WORK2, SCR_WORK3, SCR_WORK4, SCR_WORK5, SCR_COUNT
+};
+
+}  // namespace sba
+
+struct sba_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    int64_t launches = 0;
+    sba::DevBuf scratch[sba::SCR_COUNT];
+    std::map<std::tuple<int, int, int>, sba::RemapPlan> plans;
+    sba_match_stats match_stats{};
+    int* pinned_i32 = nullptr;  // small pinned host mailbox (64 ints) for scalar read-backs
+};
+
+namespace sba {
+
+// Where a user pointer lives decides whether we stage it.  Returns the device pointer to use.
+template <typename T>
+inline int stage_in(sba_ctx* c, const T* user, size_t count, int mem, ScratchSlot slot, const T** dev)
+{
+    if (count == 0 || user == nullptr) { *dev = user; return SBA_OK; }
+    if (mem == SBA_MEM_DEVICE) { *dev = user; return SBA_OK; }
+    SBA_TRY(c->scratch[slot].ensure(count * sizeof(T), c->stream));
+    SBA_CUDA(cudaMemcpyAsync(c->scratch[slot].p, user, count * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    *dev = (const T*)c->scratch[slot].p;
+    return SBA_OK;
+}
+
+template <typename T>
+inline int stage_out(sba_ctx* c, T* user, size_t count, int mem, ScratchSlot slot, T** dev)
+{
+    if (user == nullptr) { *dev = nullptr; return SBA_OK; }
+    if (mem == SBA_MEM_DEVICE) { *dev = user; return SBA_OK; }
+    SBA_TRY(c->scratch[slot].ensure((count ? count : 1) * sizeof(T), c->stream));
+    *dev = (T*)c->scratch[slot].p;
+    return SBA_OK;
+}
+
+template <typename T>
+inline int copy_out(sba_ctx* c, T* user, const T* dev, size_t count, int mem)
+{
+    if (user == nullptr || mem == SBA_MEM_DEVICE || count == 0) return SBA_OK;
+    SBA_CUDA(cudaMemcpyAsync(user, dev, count * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+    return SBA_OK;
+}
+
+inline int finish(sba_ctx* c, int mem)
+{
+    SBA_CUDA(cudaGetLastError());
+    if (mem == SBA_MEM_HOST) SBA_CUDA(cudaStreamSynchronize(c->stream));
+    return SBA_OK;
+}
+
+#define SBA_LAUNCHED(ctx) ((ctx)->launches++)
+
+__host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace sba

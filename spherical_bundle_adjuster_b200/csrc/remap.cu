@@ -1,0 +1,395 @@
+// remap.cu -- equi2cube gather (K1), cube2equi keypoints (K2), pixel->bearing (K4), match gather.
+//
+// Replaces equi2cube.cpp:12-302, equi2cube_surf.cpp:19-76,:107-113 and
+// spherical_bundle_adjuster.cpp:271-298 of the reference.
+//
+// K1 design (HBM-bound byte gather; no tensor cores, no textures):
+//   The source index of an output pixel depends only on the geometry (w, h, cube_size), so it is
+//   computed once into an int32 table ("remap plan", cached per geometry in the context) and every
+//   frame after that is a pure table-driven gather:  4 B index read + 3 B gathered + 3 B written per
+//   output pixel.  Each thread produces 4 adjacent strip pixels = 12 output bytes = three aligned
+//   32-bit stores; a warp writes 384 contiguous bytes.  Neighbouring strip pixels map to
+//   neighbouring source pixels of (mostly) one ERP row, so the byte gathers hit L1/L2 lines that the
+//   same warp already touched.
+//   The table is built on the device with the reference's fp64 formula.  CUDA's fp64 acos/atan2 are
+//   not correctly rounded, so any pixel whose continuous source coordinate lies within 1e-6 of an
+//   integer (the only place a last-ulp difference can flip the truncation; ~0.6 % of pixels: axes
+//   and diagonals) is re-evaluated on the host with the same glibc libm the reference links and
+//   patched in.  The table is therefore bit-identical to the reference's index arithmetic.
+#include <cmath>
+
+#include "common.cuh"
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+namespace sba {
+
+// ---- geometry shared by host and device (same operation order as equi2cube.cpp:26-48) ----------
+__host__ __device__ inline void face_cart(int face, double i, double j, double cs, double v[3])
+{
+    switch (face) {
+    case 0: v[0] = (cs - 2.0 * j) / cs; v[1] = 1.0; v[2] = (cs - 2.0 * i) / cs; break;   // left   :118-120
+    case 1: v[0] = -1.0; v[1] = (cs - 2.0 * j) / cs; v[2] = (cs - 2.0 * i) / cs; break;  // front  :73-75
+    case 2: v[0] = (2.0 * j - cs) / cs; v[1] = -1.0; v[2] = (cs - 2.0 * i) / cs; break;  // right  :163-165
+    case 3: v[0] = 1.0; v[1] = (2.0 * j - cs) / cs; v[2] = (cs - 2.0 * i) / cs; break;   // back   :28-30
+    case 4: v[0] = (cs - 2.0 * i) / cs; v[1] = (cs - 2.0 * j) / cs; v[2] = 1.0; break;   // top    :208-210
+    default: v[0] = (2.0 * i - cs) / cs; v[1] = (cs - 2.0 * j) / cs; v[2] = -1.0; break; // bottom :253-255
+    }
+}
+
+__host__ __device__ inline double no_fma_norm(const double v[3])
+{
+#ifdef __CUDA_ARCH__
+    // the host code rounds every product and sum separately; keep the device from contracting to FMA
+    return sqrt(__dadd_rn(__dadd_rn(__dmul_rn(v[0], v[0]), __dmul_rn(v[1], v[1])), __dmul_rn(v[2], v[2])));
+#else
+    return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+#endif
+}
+
+// Continuous ERP coordinates (row_f, col_f) of a direction: equi2cube.cpp:32-48 before truncation.
+__host__ __device__ inline void dir_to_erp(const double v[3], int w, int h, double* row_f, double* col_f)
+{
+    double n = no_fma_norm(v);
+    double ux = v[0] / n, uy = v[1] / n, uz = v[2] / n;
+    double theta = acos(uz);
+    double phi = atan2(uy, ux);
+    if (phi < 0) phi += M_PI * 2;
+#ifdef __CUDA_ARCH__
+    *row_f = __dmul_rn((double)h, theta) / M_PI;
+    *col_f = __dmul_rn((double)w, phi) / (2 * M_PI);
+#else
+    *row_f = h * theta / M_PI;
+    *col_f = w * phi / (2 * M_PI);
+#endif
+}
+
+__host__ __device__ inline int32_t clamp_index(double row_f, double col_f, int w, int h, int* clamped)
+{
+    int row = (int)row_f, col = (int)col_f;  // Vec2i assignment truncates toward zero (:46-48)
+    int c = 0;
+    if (row >= h) { row = h - 1; c = 1; }
+    if (col >= w) { col = w - 1; c = 1; }
+    if (row < 0) { row = 0; c = 1; }
+    if (col < 0) { col = 0; c = 1; }
+    if (clamped) *clamped = c;
+    return row * w + col;
+}
+
+// ---- plan construction ------------------------------------------------------------------------
+__global__ void lut_build_kernel(int cs, int w, int h, int32_t* __restrict__ lut, int32_t* __restrict__ flagged,
+                                 int* __restrict__ n_flagged, int flag_cap, int* __restrict__ n_clamped)
+{
+    int64_t total = (int64_t)cs * 6 * cs;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+        int i = (int)(p / (6 * cs));
+        int rem = (int)(p - (int64_t)i * 6 * cs);
+        int f = rem / cs, j = rem - f * cs;
+        double v[3], rf, cf;
+        face_cart(f, (double)i, (double)j, (double)cs, v);
+        dir_to_erp(v, w, h, &rf, &cf);
+        int c;
+        lut[p] = clamp_index(rf, cf, w, h, &c);
+        if (c) atomicAdd(n_clamped, 1);
+        const double tol = 1e-6;
+        bool near = fabs(rf - rint(rf)) < tol || fabs(cf - rint(cf)) < tol;
+        if (near) {
+            int slot = atomicAdd(n_flagged, 1);
+            if (slot < flag_cap) flagged[slot] = (int32_t)p;
+        }
+    }
+}
+
+__global__ void lut_patch_kernel(int32_t* __restrict__ lut, const int32_t* __restrict__ where, const int32_t* __restrict__ what, int n)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) lut[where[k]] = what[k];
+}
+
+static int32_t host_src_index(int p, int cs, int w, int h, int* clamped)
+{
+    int i = p / (6 * cs), rem = p - i * 6 * cs, f = rem / cs, j = rem - f * cs;
+    double v[3], rf, cf;
+    face_cart(f, (double)i, (double)j, (double)cs, v);
+    dir_to_erp(v, w, h, &rf, &cf);
+    return clamp_index(rf, cf, w, h, clamped);
+}
+
+static int get_plan(sba_ctx* c, int w, int h, int cs, RemapPlan** out)
+{
+    auto key = std::make_tuple(w, h, cs);
+    auto it = c->plans.find(key);
+    if (it != c->plans.end()) { *out = &it->second; return SBA_OK; }
+
+    int64_t total = (int64_t)cs * 6 * cs;
+    SBA_CHECK_ARG(total * 1 < (int64_t)1 << 31 && (int64_t)w * h < (int64_t)1 << 31);
+    RemapPlan plan;
+    plan.w = w; plan.h = h; plan.cs = cs;
+    SBA_CUDA(cudaMalloc(&plan.lut, total * sizeof(int32_t)));
+    int flag_cap = (int)total;  // worst case every pixel is flagged
+    SBA_TRY(c->scratch[SCR_WORK0].ensure((size_t)flag_cap * sizeof(int32_t), c->stream));
+    SBA_TRY(c->scratch[SCR_WORK1].ensure(2 * sizeof(int), c->stream));
+    int32_t* d_flag = c->scratch[SCR_WORK0].as<int32_t>();
+    int* d_cnt = c->scratch[SCR_WORK1].as<int>();
+    SBA_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int), c->stream));
+    int threads = 256;
+    int blocks = (int)std::min<int64_t>(ceil_div64(total, threads), (int64_t)c->sm_count * 8);
+    lut_build_kernel<<<blocks, threads, 0, c->stream>>>(cs, w, h, plan.lut, d_flag, d_cnt, flag_cap, d_cnt + 1);
+    SBA_LAUNCHED(c);
+    SBA_CUDA(cudaGetLastError());
+    int cnt[2];
+    SBA_CUDA(cudaMemcpyAsync(cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
+    SBA_CUDA(cudaStreamSynchronize(c->stream));
+    int nflag = std::min(cnt[0], flag_cap);
+    plan.n_patched = nflag;
+    if (nflag > 0) {
+        std::vector<int32_t> where(nflag), what(nflag);
+        SBA_CUDA(cudaMemcpyAsync(where.data(), d_flag, (size_t)nflag * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        SBA_CUDA(cudaStreamSynchronize(c->stream));
+        for (int k = 0; k < nflag; k++) what[k] = host_src_index(where[k], cs, w, h, nullptr);
+        SBA_TRY(c->scratch[SCR_WORK2].ensure((size_t)nflag * sizeof(int32_t), c->stream));
+        int32_t* d_what = c->scratch[SCR_WORK2].as<int32_t>();
+        SBA_CUDA(cudaMemcpyAsync(d_what, what.data(), (size_t)nflag * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        lut_patch_kernel<<<(nflag + 255) / 256, 256, 0, c->stream>>>(plan.lut, d_flag, d_what, nflag);
+        SBA_LAUNCHED(c);
+        SBA_CUDA(cudaGetLastError());
+        SBA_CUDA(cudaStreamSynchronize(c->stream));  // `what` goes out of scope
+    }
+    plan.n_clamped = cnt[1];
+    auto ins = c->plans.emplace(key, plan);
+    *out = &ins.first->second;
+    return SBA_OK;
+}
+
+// ---- the gather -------------------------------------------------------------------------------
+// One thread = 4 adjacent strip pixels of one image.  `groups` = ceil(P/4) per image.
+__global__ void __launch_bounds__(256)
+remap_gather4_kernel(const uint8_t* __restrict__ erp, const int32_t* __restrict__ lut, uint8_t* __restrict__ out,
+                     int64_t src_bytes_per_image, int64_t P, int64_t groups, int n_images)
+{
+    int64_t total = groups * n_images;
+    for (int64_t gidx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; gidx < total; gidx += (int64_t)gridDim.x * blockDim.x) {
+        int img = (int)(gidx / groups);
+        int64_t grp = gidx - (int64_t)img * groups;
+        const uint8_t* src = erp + (int64_t)img * src_bytes_per_image;
+        uint8_t* dst = out + ((int64_t)img * P + grp * 4) * 3;
+        int4 s = __ldg(reinterpret_cast<const int4*>(lut) + grp);
+        const uint8_t* p0 = src + (int64_t)s.x * 3;
+        const uint8_t* p1 = src + (int64_t)s.y * 3;
+        const uint8_t* p2 = src + (int64_t)s.z * 3;
+        const uint8_t* p3 = src + (int64_t)s.w * 3;
+        // issue all twelve byte gathers before packing (memory-level parallelism)
+        uint32_t a0 = __ldg(p0), a1 = __ldg(p0 + 1), a2 = __ldg(p0 + 2);
+        uint32_t b0 = __ldg(p1), b1 = __ldg(p1 + 1), b2 = __ldg(p1 + 2);
+        uint32_t c0 = __ldg(p2), c1 = __ldg(p2 + 1), c2 = __ldg(p2 + 2);
+        uint32_t d0 = __ldg(p3), d1 = __ldg(p3 + 1), d2 = __ldg(p3 + 2);
+        uint32_t w0 = a0 | (a1 << 8) | (a2 << 16) | (b0 << 24);
+        uint32_t w1 = b1 | (b2 << 8) | (c0 << 16) | (c1 << 24);
+        uint32_t w2 = c2 | (d0 << 8) | (d1 << 16) | (d2 << 24);
+        uint32_t* o = reinterpret_cast<uint32_t*>(dst);
+        o[0] = w0; o[1] = w1; o[2] = w2;
+    }
+}
+
+// Generic path: one thread per pixel; handles odd sizes, unaligned bases and single faces
+// (`lut_row_stride`/`face_off` select a cs-wide window of the strip table).
+__global__ void remap_gather1_kernel(const uint8_t* __restrict__ erp, const int32_t* __restrict__ lut, uint8_t* __restrict__ out,
+                                     int64_t src_bytes_per_image, int rows, int cols, int lut_row_stride, int face_off, int n_images)
+{
+    int64_t P = (int64_t)rows * cols, total = P * n_images;
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        int img = (int)(g / P);
+        int64_t p = g - (int64_t)img * P;
+        int i = (int)(p / cols), j = (int)(p - (int64_t)i * cols);
+        int32_t s = __ldg(lut + (int64_t)i * lut_row_stride + face_off + j);
+        const uint8_t* q = erp + (int64_t)img * src_bytes_per_image + (int64_t)s * 3;
+        uint8_t* o = out + g * 3;
+        o[0] = __ldg(q); o[1] = __ldg(q + 1); o[2] = __ldg(q + 2);
+    }
+}
+
+// ---- elementwise keypoint kernels --------------------------------------------------------------
+// equi2cube_surf.cpp:19-76
+__global__ void cube2equi_points_kernel(const float2* __restrict__ in, int n, int cs, int w, int h, float2* __restrict__ out)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    float2 p = in[k];
+    int face;
+    if (p.x < cs) face = 0;
+    else if (p.x < 2 * cs) face = 1;
+    else if (p.x < 3 * cs) face = 2;
+    else if (p.x < 4 * cs) face = 3;
+    else if (p.x < 5 * cs) face = 4;
+    else face = 5;
+    float fx = (face == 0) ? p.x : __fsub_rn(p.x, (float)(face * cs));  // float - int in the reference
+    double v[3], rf, cf;
+    face_cart(face, (double)p.y, (double)fx, (double)cs, v);
+    dir_to_erp(v, w, h, &rf, &cf);
+    out[k] = make_float2((float)cf, (float)rf);
+}
+
+// spherical_bundle_adjuster.cpp:271-298
+__global__ void pixels_to_bearings_kernel(const float2* __restrict__ px, int n, double w, double h, float4* __restrict__ b32,
+                                          double* __restrict__ b64)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    float2 p = px[k];
+    double lon = 2 * M_PI * ((double)p.x / w);
+    double lat = M_PI * ((double)p.y / h);
+    double sl, cl, so, co;
+    sincos(lat, &sl, &cl);
+    sincos(lon, &so, &co);
+    double x = sl * co, y = sl * so, z = cl;
+    if (b32) b32[k] = make_float4((float)x, (float)y, (float)z, 0.f);
+    if (b64) { b64[3 * k] = x; b64[3 * k + 1] = y; b64[3 * k + 2] = z; }
+}
+
+// equi2cube_surf.cpp:107-113
+__global__ void gather_matches_kernel(const float2* __restrict__ kl, const float2* __restrict__ kr, const int32_t* __restrict__ qi,
+                                      const int32_t* __restrict__ ti, int n, float2* __restrict__ ol, float2* __restrict__ orr)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    ol[k] = kl[qi[k]];
+    orr[k] = kr[ti[k]];
+}
+
+static int launch_gather(sba_ctx* c, const uint8_t* d_erp, const RemapPlan* plan, uint8_t* d_out, int n_images, int face)
+{
+    int cs = plan->cs;
+    int64_t src_bytes = (int64_t)plan->w * plan->h * 3;
+    if (face < 0) {
+        int64_t P = (int64_t)cs * 6 * cs;
+        bool vec_ok = (P % 4 == 0) && (((uintptr_t)d_out) % 4 == 0);
+        if (vec_ok) {
+            int64_t groups = P / 4, total = groups * n_images;
+            int threads = 256;
+            // grid: a multiple of the SM count, 8 resident CTAs of 256 threads per SM
+            int64_t want = ceil_div64(total, threads);
+            int blocks = (int)std::min<int64_t>(want, (int64_t)c->sm_count * 8 * 4);
+            if (blocks >= c->sm_count) blocks = blocks / c->sm_count * c->sm_count;
+            remap_gather4_kernel<<<blocks, threads, 0, c->stream>>>(d_erp, plan->lut, d_out, src_bytes, P, groups, n_images);
+        } else {
+            int64_t total = P * n_images;
+            int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)c->sm_count * 32);
+            remap_gather1_kernel<<<blocks, 256, 0, c->stream>>>(d_erp, plan->lut, d_out, src_bytes, cs, 6 * cs, 6 * cs, 0, n_images);
+        }
+    } else {
+        int64_t total = (int64_t)cs * cs * n_images;
+        int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)c->sm_count * 32);
+        remap_gather1_kernel<<<blocks, 256, 0, c->stream>>>(d_erp, plan->lut, d_out, src_bytes, cs, cs, 6 * cs, face * cs, n_images);
+    }
+    SBA_LAUNCHED(c);
+    SBA_CUDA(cudaGetLastError());
+    return SBA_OK;
+}
+
+}  // namespace sba
+
+using namespace sba;
+
+extern "C" {
+
+int sba_equi2cube_lut(sba_ctx* c, int w, int h, int cs, int32_t* lut_out, int mem)
+{
+    SBA_CHECK_ARG(c && w > 0 && h > 0 && cs > 0);
+    SBA_CUDA(cudaSetDevice(c->device));
+    RemapPlan* plan;
+    SBA_TRY(get_plan(c, w, h, cs, &plan));
+    if (lut_out) {
+        size_t bytes = (size_t)cs * 6 * cs * sizeof(int32_t);
+        SBA_CUDA(cudaMemcpyAsync(lut_out, plan->lut, bytes, mem == SBA_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, c->stream));
+    }
+    return finish(c, mem);
+}
+
+int sba_equi2cube(sba_ctx* c, const uint8_t* erp, int w, int h, int n_images, int cs, uint8_t* strip_out, int mem)
+{
+    SBA_CHECK_ARG(c && erp && strip_out && w > 0 && h > 0 && cs > 0 && n_images >= 0);
+    if (n_images == 0) return SBA_OK;
+    SBA_CUDA(cudaSetDevice(c->device));
+    RemapPlan* plan;
+    SBA_TRY(get_plan(c, w, h, cs, &plan));
+    size_t in_bytes = (size_t)w * h * 3 * n_images, out_bytes = (size_t)cs * 6 * cs * 3 * n_images;
+    const uint8_t* d_in;
+    uint8_t* d_out;
+    SBA_TRY(stage_in(c, erp, in_bytes, mem, SCR_IN0, &d_in));
+    SBA_TRY(stage_out(c, strip_out, out_bytes, mem, SCR_OUT0, &d_out));
+    SBA_TRY(launch_gather(c, d_in, plan, d_out, n_images, -1));
+    SBA_TRY(copy_out(c, strip_out, d_out, out_bytes, mem));
+    return finish(c, mem);
+}
+
+int sba_equi2cube_face(sba_ctx* c, const uint8_t* erp, int w, int h, int cs, int face, uint8_t* face_out, int mem)
+{
+    SBA_CHECK_ARG(c && erp && face_out && w > 0 && h > 0 && cs > 0 && face >= 0 && face < 6);
+    SBA_CUDA(cudaSetDevice(c->device));
+    RemapPlan* plan;
+    SBA_TRY(get_plan(c, w, h, cs, &plan));
+    size_t in_bytes = (size_t)w * h * 3, out_bytes = (size_t)cs * cs * 3;
+    const uint8_t* d_in;
+    uint8_t* d_out;
+    SBA_TRY(stage_in(c, erp, in_bytes, mem, SCR_IN0, &d_in));
+    SBA_TRY(stage_out(c, face_out, out_bytes, mem, SCR_OUT0, &d_out));
+    SBA_TRY(launch_gather(c, d_in, plan, d_out, 1, face));
+    SBA_TRY(copy_out(c, face_out, d_out, out_bytes, mem));
+    return finish(c, mem);
+}
+
+int sba_cube2equi_points(sba_ctx* c, const float* xy_in, int n, int cs, int w, int h, float* xy_out, int mem)
+{
+    SBA_CHECK_ARG(c && n >= 0 && cs > 0 && w > 0 && h > 0);
+    if (n == 0) return SBA_OK;
+    SBA_CHECK_ARG(xy_in && xy_out);
+    SBA_CUDA(cudaSetDevice(c->device));
+    const float* d_in;
+    float* d_out;
+    SBA_TRY(stage_in(c, xy_in, (size_t)2 * n, mem, SCR_IN0, &d_in));
+    SBA_TRY(stage_out(c, xy_out, (size_t)2 * n, mem, SCR_OUT0, &d_out));
+    cube2equi_points_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>((const float2*)d_in, n, cs, w, h, (float2*)d_out);
+    SBA_LAUNCHED(c);
+    SBA_TRY(copy_out(c, xy_out, d_out, (size_t)2 * n, mem));
+    return finish(c, mem);
+}
+
+int sba_pixels_to_bearings(sba_ctx* c, const float* xy, int n, int w, int h, float* b32, double* b64, int mem)
+{
+    SBA_CHECK_ARG(c && n >= 0 && w > 0 && h > 0);
+    if (n == 0) return SBA_OK;
+    SBA_CHECK_ARG(xy && (b32 || b64));
+    SBA_CUDA(cudaSetDevice(c->device));
+    const float* d_in;
+    float* d_b32;
+    double* d_b64;
+    SBA_TRY(stage_in(c, xy, (size_t)2 * n, mem, SCR_IN0, &d_in));
+    SBA_TRY(stage_out(c, b32, (size_t)4 * n, mem, SCR_OUT0, &d_b32));
+    SBA_TRY(stage_out(c, b64, (size_t)3 * n, mem, SCR_OUT1, &d_b64));
+    pixels_to_bearings_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>((const float2*)d_in, n, (double)w, (double)h, (float4*)d_b32, d_b64);
+    SBA_LAUNCHED(c);
+    SBA_TRY(copy_out(c, b32, d_b32, (size_t)4 * n, mem));
+    SBA_TRY(copy_out(c, b64, d_b64, (size_t)3 * n, mem));
+    return finish(c, mem);
+}
+
+int sba_gather_matches(sba_ctx* c, const float* kl, const float* kr, const int32_t* qi, const int32_t* ti, int n, float* ol, float* orr, int mem)
+{
+    SBA_CHECK_ARG(c && n >= 0);
+    if (n == 0) return SBA_OK;
+    SBA_CHECK_ARG(kl && kr && qi && ti && ol && orr);
+    if (mem != SBA_MEM_DEVICE) {
+        // The keypoint array lengths are not part of this call, so host arrays cannot be staged;
+        // the facade gathers its own cv::KeyPoint vectors, the device pipeline calls this.
+        set_error("sba_gather_matches takes device pointers only");
+        return SBA_ERR_UNSUPPORTED;
+    }
+    SBA_CUDA(cudaSetDevice(c->device));
+    gather_matches_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>((const float2*)kl, (const float2*)kr, qi, ti, n, (float2*)ol, (float2*)orr);
+    SBA_LAUNCHED(c);
+    return finish(c, mem);
+}
+
+}  // extern "C"

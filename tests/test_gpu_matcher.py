@@ -1,0 +1,92 @@
+"""GPU parity: kNN(k=2) + ratio test through the C ABI against cv2.BFMatcher golden vectors and the
+oracle.  Indices AND fp32 distances are bit-exact (the CUDA path reproduces OpenCV's accumulation
+order); both the exact SIMT kernel and whatever SBA_MATCH_AUTO selects are checked."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from spherical_bundle_adjuster_b200 import MATCH_AUTO, MATCH_SIMT_EXACT, synth
+
+pytestmark = pytest.mark.gpu
+ALGOS = [MATCH_SIMT_EXACT, MATCH_AUTO]
+
+
+def _check(m, q, t, ratio=0.3):
+    idx, dist = oracle.knn2_l2(q, t)
+    qi, ti, dd = oracle.ratio_filter(idx, dist, ratio)
+    assert np.array_equal(m.knn_idx, idx)
+    assert np.array_equal(m.knn_dist.view(np.uint32), dist.view(np.uint32))
+    assert np.array_equal(m.query_idx, qi) and np.array_equal(m.train_idx, ti)
+    assert np.array_equal(m.distance.view(np.uint32), dd.view(np.uint32))
+    assert (np.diff(m.query_idx) > 0).all()          # survivors in ascending query order
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("name", ["matcher_64.npz", "matcher_128.npz", "matcher_ragged.npz"])
+def test_matcher_matches_cv2_golden(ctx, golden_dir, name, algo):
+    g = np.load(os.path.join(golden_dir, name))
+    m = ctx.match_two_image(g["q"], g["t"], 0.3, algo=algo, want_knn=True)
+    assert np.array_equal(m.knn_idx, g["knn_idx"])
+    assert np.array_equal(m.knn_dist.view(np.uint32), g["knn_dist"].view(np.uint32))
+    assert np.array_equal(m.query_idx, g["keep"])
+    assert np.array_equal(m.train_idx, g["knn_idx"][g["keep"], 0])
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("nq,nt,dim", [(1000, 1000, 64), (777, 1301, 64), (130, 4097, 64), (2048, 300, 128), (5000, 3000, 64)])
+def test_matcher_matches_oracle(ctx, nq, nt, dim, algo):
+    A, B, _ = synth.make_descriptors(nq, nt, dim, seed=nq + nt)
+    _check(ctx.match_two_image(A, B, 0.3, algo=algo, want_knn=True), A, B)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_matcher_ties_and_duplicates(ctx, algo):
+    A, B, _ = synth.make_descriptors(600, 900, 64, seed=3)
+    B[100:140] = B[7]            # forty identical train rows: the two lowest indices must win
+    A[5] = B[7]
+    B[500] = B[20]; B[20 + 300] = B[20]
+    A[9] = A[5]
+    _check(ctx.match_two_image(A, B, 0.3, algo=algo, want_knn=True), A, B)
+    _check(ctx.match_two_image(A, B, 0.9, algo=algo, want_knn=True), A, B, 0.9)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_matcher_degenerate_sizes(ctx, algo):
+    rng = np.random.default_rng(1)
+    q = synth.unit_rows(rng.standard_normal((40, 64))).astype(np.float32)
+    m = ctx.match_two_image(q, np.zeros((0, 64), np.float32), algo=algo, want_knn=True)     # M = 0
+    assert len(m) == 0 and (m.knn_idx == -1).all() and np.isinf(m.knn_dist).all()
+    m = ctx.match_two_image(q, q[:1].copy(), algo=algo, want_knn=True)                        # M = 1
+    assert len(m) == 0 and (m.knn_idx[:, 0] == 0).all() and (m.knn_idx[:, 1] == -1).all()
+    _check(ctx.match_two_image(q, q[:2].copy(), algo=algo, want_knn=True), q, q[:2])          # M = 2
+    m = ctx.match_two_image(np.zeros((0, 64), np.float32), q, algo=algo, want_knn=True)     # N = 0
+    assert len(m) == 0
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_matcher_device_tensors(ctx, algo):
+    import torch
+    A, B, _ = synth.make_descriptors(1500, 1700, 64, seed=9)
+    m = ctx.match_two_image(torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda(), 0.3, algo=algo, want_knn=True)
+    torch.cuda.synchronize()
+    m2 = type(m)(m.query_idx.cpu().numpy(), m.train_idx.cpu().numpy(), m.distance.cpu().numpy(), m.knn_idx.cpu().numpy(), m.knn_dist.cpu().numpy())
+    _check(m2, A, B)
+
+
+def test_matcher_full_size_properties(ctx):
+    """BASELINE config-2 size (16k x 16k): the oracle needs ~1 min here, so check size-independent
+    properties: every planted pair is recovered exactly, AUTO == SIMT bit-for-bit, and a sampled
+    subset of rows equals the oracle."""
+    A, B, truth = synth.make_descriptors(16384, 16384, 64, seed=2)
+    ms = ctx.match_two_image(A, B, 0.3, algo=MATCH_SIMT_EXACT, want_knn=True)
+    ma = ctx.match_two_image(A, B, 0.3, algo=MATCH_AUTO, want_knn=True)
+    planted = np.flatnonzero(truth >= 0)
+    assert np.array_equal(ms.query_idx, planted) and np.array_equal(ms.train_idx, truth[planted])
+    for a, b in [(ms.knn_idx, ma.knn_idx), (ms.query_idx, ma.query_idx), (ms.train_idx, ma.train_idx)]:
+        assert np.array_equal(a, b)
+    assert np.array_equal(ms.knn_dist.view(np.uint32), ma.knn_dist.view(np.uint32))
+    rows = np.random.default_rng(0).choice(16384, 256, replace=False)
+    idx, dist = oracle.knn2_l2(A[rows], B)
+    assert np.array_equal(ms.knn_idx[rows], idx) and np.array_equal(ms.knn_dist[rows].view(np.uint32), dist.view(np.uint32))

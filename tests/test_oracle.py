@@ -1,0 +1,157 @@
+"""CPU tests: the oracle (oracle/sba_oracle.c) against the golden vectors in tests/golden/ that were
+produced by cv2.BFMatcher, the reference's own equi2cube sources (oracle/_ref) and scipy."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from spherical_bundle_adjuster_b200 import synth
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+@pytest.mark.parametrize("name", ["matcher_64.npz", "matcher_128.npz", "matcher_ragged.npz"])
+def test_matcher_oracle_matches_cv2_golden(golden_dir, name):
+    g = _load(golden_dir, name)
+    idx, dist = oracle.knn2_l2(g["q"], g["t"])
+    assert np.array_equal(idx, g["knn_idx"])                                   # bit-exact indices
+    assert np.array_equal(dist.view(np.uint32), g["knn_dist"].view(np.uint32))  # bit-exact fp32 distances
+    qi, ti, dd = oracle.match_two_image(g["q"], g["t"], 0.3)
+    assert np.array_equal(qi, g["keep"])
+    assert np.array_equal(ti, g["knn_idx"][g["keep"], 0])
+
+
+def test_matcher_oracle_matches_live_cv2_when_present():
+    cv2 = pytest.importorskip("cv2")
+    A, B, _ = synth.make_descriptors(300, 257, 64, seed=5)
+    knn = cv2.BFMatcher(cv2.NORM_L2).knnMatch(A, B, 2)
+    idx, dist = oracle.knn2_l2(A, B)
+    assert np.array_equal(idx, np.array([[m.trainIdx for m in k] for k in knn], np.int32))
+    assert np.array_equal(dist.view(np.uint32), np.array([[m.distance for m in k] for k in knn], np.float32).view(np.uint32))
+
+
+def test_matcher_oracle_edge_cases():
+    q = synth.unit_rows(np.random.default_rng(0).standard_normal((5, 64))).astype(np.float32)
+    idx, dist = oracle.knn2_l2(q, np.zeros((0, 64), np.float32))   # empty train set
+    assert (idx == -1).all() and np.isinf(dist).all()
+    idx, dist = oracle.knn2_l2(q, q[:1])                            # a single train row: no second neighbour
+    assert (idx[:, 0] == 0).all() and (idx[:, 1] == -1).all()
+    assert len(oracle.match_two_image(q, q[:1])[0]) == 0           # guarded: the reference would read knn[i][1]
+    idx, _ = oracle.knn2_l2(np.zeros((0, 64), np.float32), q)       # empty query set
+    assert idx.shape == (0, 2)
+
+
+@pytest.mark.parametrize("name", ["remap_even.npz", "remap_odd.npz"])
+def test_remap_oracle_matches_reference_golden(golden_dir, name):
+    g = _load(golden_dir, name)
+    cs = int(g["cs"])
+    assert np.array_equal(oracle.equi2cube_all(g["im"], cs), g["strip"])
+    for f in range(6):
+        assert np.array_equal(oracle.equi2cube_face(g["im"], cs, f), g["faces"][f])
+    # get_all == hconcat(left, front, right, back, top, bottom)  (equi2cube.cpp:293-298)
+    assert np.array_equal(np.concatenate(list(g["faces"]), axis=1), g["strip"])
+
+
+@pytest.mark.parametrize("geom", ["512x256_cs128", "100x50_cs15", "2048x1024_cs512"])
+def test_remap_lut_hash(golden_dir, geom):
+    h = json.load(open(os.path.join(golden_dir, "remap_lut_hashes.json")))[geom]
+    wh, cs = geom.split("_cs")
+    w, hh = map(int, wh.split("x"))
+    lut, _ = oracle.equi2cube_lut(int(cs), w, hh)
+    assert int(lut.astype(np.int64).sum()) == h["sum"]
+    assert hashlib.sha256(lut.tobytes()).hexdigest() == h["sha256"]
+
+
+def test_remap_bottom_centre_clamp():
+    # h a power of two and an even cube: theta rounds to pi at the bottom-face centre, the reference
+    # indexes row h (equi2cube.cpp:268-275); the restatement clamps that single pixel.
+    _, nclamp = oracle.equi2cube_lut(512, 2048, 1024)
+    assert nclamp == 1
+    _, nclamp = oracle.equi2cube_lut(960, 3840, 1920)
+    assert nclamp == 0
+
+
+@pytest.mark.skipif(not oracle.ref_available(), reason="oracle/_ref not built")
+def test_oracle_equals_compiled_reference():
+    im = synth.make_erp_image(256, 128, seed=9)
+    for cs in (32, 33, 64):
+        assert np.array_equal(oracle.equi2cube_all(im, cs), oracle.ref_equi2cube_all(im, cs))
+    rng = np.random.default_rng(3)
+    xy = np.stack([rng.uniform(0, 6 * 64, 1000), rng.uniform(0, 64, 1000)], 1).astype(np.float32)
+    a, b = oracle.cube2equi_points(xy, 64, 256, 128), oracle.ref_cube2equi_points(xy, 64, 256, 128)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_cube2equi_golden(golden_dir):
+    g = _load(golden_dir, "cube2equi.npz")
+    out = oracle.cube2equi_points(g["xy"], int(g["cs"]), int(g["w"]), int(g["h"]))
+    assert np.array_equal(out.view(np.uint32), g["out"].view(np.uint32))
+
+
+def test_cube2equi_inverts_remap_sampling():
+    # property: the ERP pixel of a face-pixel coordinate is the pixel equi2cube sampled
+    cs, w, h = 64, 512, 256
+    lut, _ = oracle.equi2cube_lut(cs, w, h)
+    ii, jj = np.mgrid[0:cs, 0:6 * cs]
+    xy = np.stack([jj.ravel() + 0.25, ii.ravel() + 0.25], 1).astype(np.float32)   # strictly inside the pixel
+    e = oracle.cube2equi_points(np.stack([jj.ravel(), ii.ravel()], 1).astype(np.float32), cs, w, h)
+    src = (np.minimum(e[:, 1].astype(np.int64), h - 1)) * w + np.minimum(e[:, 0].astype(np.int64), w - 1)
+    assert (src == lut.ravel()).mean() > 0.995   # float32 rounding of the keypoint flips a few boundary pixels
+    assert xy.shape[0] == lut.size
+
+
+def test_bearings_match_reference_convention():
+    # theta from +z, phi from +x (spherical_bundle_adjuster.cpp:279-297)
+    xy = np.array([[0, 128], [128, 128], [256, 128], [0, 0], [17.5, 255.9]], np.float32)
+    b = oracle.pixels_to_bearings(xy, 512, 256)
+    assert np.allclose(b[0], [1, 0, 0], atol=1e-12) and np.allclose(b[1], [0, 1, 0], atol=1e-12)
+    assert np.allclose(b[2], [-1, 0, 0], atol=1e-12) and np.allclose(b[3], [0, 0, 1], atol=1e-12)
+    assert np.allclose(np.linalg.norm(b, axis=1), 1.0, atol=1e-14)
+
+
+def test_ba_oracle_matches_scipy_golden(golden_dir):
+    g = _load(golden_dir, "ba_small.npz")
+    res, jac, H, gg, cost = oracle.ba_rot_eval(g["b1"], g["b2"], None, g["r"][None], g["t"], float(g["d1"]), float(g["d2"]), 1.0)
+    assert np.abs(res - g["res"]).max() < 1e-14
+    assert np.abs(jac - g["jac"]).max() < 5e-9            # golden Jacobian is a central difference
+    assert np.allclose(H[0], g["H"], rtol=1e-7) and np.allclose(gg[0], g["g"], rtol=1e-6, atol=1e-8)
+    assert abs(cost[0] - float(g["cost"])) < 1e-12
+    r, s = oracle.ba_rot_solve(g["b1"], g["b2"], None, np.zeros((1, 3)))
+    assert np.abs(r - g["r_solved"]).max() < 1e-12 and s.iterations == int(g["iterations"])
+
+
+def test_ba_oracle_known_answers():
+    b1, b2, cam, r_true = synth.make_bearings(500, noise=0.0, seed=1)
+    res, *_ = oracle.ba_rot_eval(b1, b2, None, r_true)
+    assert np.abs(res).max() < 1e-14                      # zero residual at the truth
+    r, s = oracle.ba_rot_solve(b1, b2, None, np.zeros((1, 3)))
+    assert np.abs(r - r_true).max() < 1e-6                # recovered rotation <= 1e-6 rad
+    # small-angle branch (theta^2 <= DBL_EPSILON): out = p + r x p
+    rs = np.array([[1e-9, -2e-9, 3e-9]])
+    res_s, jac_s, *_ = oracle.ba_rot_eval(b1, b1, None, rs)
+    assert np.allclose(res_s, -np.cross(rs[0], b1), atol=1e-20)
+    # theta near pi
+    rp = np.array([[np.pi - 1e-7, 0.0, 0.0]])
+    res_p, *_ = oracle.ba_rot_eval(b1, b1 * [1, -1, -1], None, rp)
+    assert np.abs(res_p).max() < 1e-6
+    # Huber: outliers beyond |res| > 1 contribute 2|res|-1
+    b2o = -b1
+    _, _, _, _, cost = oracle.ba_rot_eval(b1, b2o, None, np.zeros((1, 3)))
+    assert abs(cost[0] - 0.5 * 500 * (2 * 2.0 - 1)) < 1e-9
+
+
+def test_ba_oracle_multi_camera_blocks_are_independent():
+    b1, b2, cam, r_true = synth.make_bearings(3000, noise=1e-3, seed=3, n_cam=4)
+    r0 = np.zeros((4, 3))
+    _, _, H, g, cost = oracle.ba_rot_eval(b1, b2, cam, r0)
+    for c in range(4):
+        m = cam == c
+        _, _, Hc, gc, cc = oracle.ba_rot_eval(b1[m], b2[m], None, r0[c:c + 1])
+        assert np.allclose(H[c], Hc[0], rtol=1e-12) and np.allclose(g[c], gc[0], rtol=1e-10, atol=1e-12)
+    r, s = oracle.ba_rot_solve(b1, b2, cam, r0)
+    assert np.abs(r - r_true).max() < 5e-4
