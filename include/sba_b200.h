@@ -57,6 +57,17 @@ int sba_ctx_synchronize(sba_ctx* ctx);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 int64_t sba_ctx_launch_count(sba_ctx* ctx);
 
+/* Kernel timing for roofline reports.  When enabled, the dominant kernel of each stage is bracketed
+ * by CUDA events on the context's stream; sba_ctx_kernel_ms returns the device time of the most
+ * recent launch of that kernel (synchronising on its end event). */
+typedef enum sba_kernel_id {
+    SBA_KERNEL_MATCH = 0, /* the kNN distance kernel (SIMT or tensor-core) */
+    SBA_KERNEL_REMAP = 1, /* the equi2cube gather */
+    SBA_KERNEL_BA_EVAL = 2 /* the BA residual+Jacobian evaluation kernel */
+} sba_kernel_id;
+int sba_ctx_set_profiling(sba_ctx* ctx, int enable);
+int sba_ctx_kernel_ms(sba_ctx* ctx, int kernel_id, float* ms);
+
 /* ---------------------------------------------------------------------------------------------
  * equi2cube  (replaces equi2cube.cpp:12-302)
  *

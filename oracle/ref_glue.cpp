@@ -35,7 +35,7 @@ void ref_equi2cube_all(const unsigned char* im_padded, int w, int h, int cs, int
 {
     cv::Mat im(h, w, CV_8UC3, (void*)im_padded);
     equi2cube e;
-    e.set_omp(nthreads);
+    omp_set_num_threads(nthreads);  // what equi2cube::set_omp does (equi2cube.cpp:8) minus its stdout print
     cv::Mat out = e.get_all(im, cs);
     std::memcpy(strip, out.data, (size_t)cs * 6 * cs * 3);
 }

@@ -17,7 +17,7 @@ MATCH_AUTO, MATCH_SIMT_EXACT, MATCH_TENSOR = 0, 1, 2
 # every symbol include/sba_b200.h declares (tests check the .so exports all of them)
 EXPORTED = [
     "sba_version", "sba_last_error", "sba_ctx_create", "sba_ctx_destroy", "sba_ctx_set_stream", "sba_ctx_get_stream",
-    "sba_ctx_synchronize", "sba_ctx_launch_count", "sba_equi2cube", "sba_equi2cube_face", "sba_equi2cube_lut",
+    "sba_ctx_synchronize", "sba_ctx_launch_count", "sba_ctx_set_profiling", "sba_ctx_kernel_ms", "sba_equi2cube", "sba_equi2cube_face", "sba_equi2cube_lut",
     "sba_cube2equi_points", "sba_pixels_to_bearings", "sba_knn2_ratio", "sba_match_last_stats", "sba_gather_matches",
     "sba_ba_problem_create", "sba_ba_problem_destroy", "sba_ba_problem_set_allreduce", "sba_ba_rot_eval",
     "sba_ba_rot_solve", "sba_ba_rot_eval_timed",
@@ -62,6 +62,8 @@ def load():
     lib.sba_ctx_synchronize.argtypes = [vp]
     lib.sba_ctx_launch_count.argtypes = [vp]
     lib.sba_ctx_launch_count.restype = i64
+    lib.sba_ctx_set_profiling.argtypes = [vp, i32]
+    lib.sba_ctx_kernel_ms.argtypes = [vp, i32, C.POINTER(f32)]
     lib.sba_equi2cube.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32]
     lib.sba_equi2cube_face.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32]
     lib.sba_equi2cube_lut.argtypes = [vp, i32, i32, i32, vp, i32]

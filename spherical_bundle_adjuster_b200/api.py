@@ -117,6 +117,15 @@ class Context:
     def launch_count(self) -> int:
         return int(self._lib.sba_ctx_launch_count(self._h))
 
+    def set_profiling(self, enable: bool):
+        check(self._lib.sba_ctx_set_profiling(self._h, int(enable)))
+
+    def kernel_ms(self, kernel_id: int) -> float:
+        """Device time of the last profiled launch: 0 matcher, 1 remap gather, 2 BA evaluation."""
+        ms = C.c_float(0)
+        check(self._lib.sba_ctx_kernel_ms(self._h, kernel_id, C.byref(ms)))
+        return float(ms.value)
+
     # -- equi2cube.hpp:20-32
     def equi2cube(self, erp, cube_size: int, out=None):
         """``equi2cube::get_all`` for one image [h,w,3] or a batch [n,h,w,3] (uint8, BGR)."""

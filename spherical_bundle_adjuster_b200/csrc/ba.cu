@@ -606,7 +606,9 @@ static int upload_rotations(sba_ba_problem* p, const double* r, double* dst)
 template <bool WRITE, bool FUSE>
 static int launch_eval(sba_ba_problem* p, const EvalArgs& E, const LMArrays& A)
 {
+    prof_begin(p->ctx, SBA_KERNEL_BA_EVAL);
     ba_rot_eval_kernel<WRITE, FUSE><<<p->eval_blocks, EVAL_THREADS, 0, p->ctx->stream>>>(E, A);
+    prof_end(p->ctx, SBA_KERNEL_BA_EVAL);
     SBA_LAUNCHED(p->ctx);
     SBA_CUDA(cudaGetLastError());
     return SBA_OK;

@@ -94,6 +94,9 @@ struct sba_ctx {
     std::map<std::tuple<int, int, int>, sba::RemapPlan> plans;
     sba_match_stats match_stats{};
     int* pinned_i32 = nullptr;  // small pinned host mailbox (64 ints) for scalar read-backs
+    bool profiling = false;
+    cudaEvent_t prof_e0[3] = {nullptr, nullptr, nullptr}, prof_e1[3] = {nullptr, nullptr, nullptr};
+    bool prof_valid[3] = {false, false, false};
 };
 
 namespace sba {
@@ -136,6 +139,19 @@ inline int finish(sba_ctx* c, int mem)
 }
 
 #define SBA_LAUNCHED(ctx) ((ctx)->launches++)
+
+// Bracket the dominant kernel of a stage with events when profiling is on.
+inline void prof_begin(sba_ctx* c, int id)
+{
+    if (c->profiling) cudaEventRecord(c->prof_e0[id], c->stream);
+}
+inline void prof_end(sba_ctx* c, int id)
+{
+    if (c->profiling) {
+        cudaEventRecord(c->prof_e1[id], c->stream);
+        c->prof_valid[id] = true;
+    }
+}
 
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -77,6 +77,10 @@ int sba_ctx_destroy(sba_ctx* c)
     for (auto& kv : c->plans)
         if (kv.second.lut) cudaFree(kv.second.lut);
     if (c->pinned_i32) cudaFreeHost(c->pinned_i32);
+    for (int k = 0; k < 3; k++) {
+        if (c->prof_e0[k]) cudaEventDestroy(c->prof_e0[k]);
+        if (c->prof_e1[k]) cudaEventDestroy(c->prof_e1[k]);
+    }
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return SBA_OK;
@@ -110,5 +114,31 @@ int sba_ctx_synchronize(sba_ctx* c)
 }
 
 int64_t sba_ctx_launch_count(sba_ctx* c) { return c ? c->launches : 0; }
+
+int sba_ctx_set_profiling(sba_ctx* c, int enable)
+{
+    SBA_CHECK_ARG(c != nullptr);
+    SBA_CUDA(cudaSetDevice(c->device));
+    if (enable && !c->prof_e0[0]) {
+        for (int k = 0; k < 3; k++) {
+            SBA_CUDA(cudaEventCreate(&c->prof_e0[k]));
+            SBA_CUDA(cudaEventCreate(&c->prof_e1[k]));
+        }
+    }
+    c->profiling = enable != 0;
+    return SBA_OK;
+}
+
+int sba_ctx_kernel_ms(sba_ctx* c, int id, float* ms)
+{
+    SBA_CHECK_ARG(c && ms && id >= 0 && id < 3);
+    if (!c->prof_valid[id]) {
+        sba::set_error("kernel %d has not been launched with profiling enabled", id);
+        return SBA_ERR_INVALID;
+    }
+    SBA_CUDA(cudaEventSynchronize(c->prof_e1[id]));
+    SBA_CUDA(cudaEventElapsedTime(ms, c->prof_e0[id], c->prof_e1[id]));
+    return SBA_OK;
+}
 
 }  // extern "C"

@@ -239,7 +239,9 @@ static int run_simt(sba_ctx* c, const float* d_q, int nq, const float* d_t, int 
         d_parts = c->scratch[SCR_WORK1].as<Top2>();
     }
     dim3 grid(qblocks, nsplit);
+    prof_begin(c, SBA_KERNEL_MATCH);
     knn2_simt_kernel<DIM><<<grid, SIMT_THREADS, smem, c->stream>>>(d_q, nq, d_t, nt, tiles_per_split, d_parts);
+    prof_end(c, SBA_KERNEL_MATCH);
     SBA_LAUNCHED(c);
     SBA_CUDA(cudaGetLastError());
     if (nsplit > 1) {

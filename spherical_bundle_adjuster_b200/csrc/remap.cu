@@ -262,6 +262,7 @@ static int launch_gather(sba_ctx* c, const uint8_t* d_erp, const RemapPlan* plan
 {
     int cs = plan->cs;
     int64_t src_bytes = (int64_t)plan->w * plan->h * 3;
+    prof_begin(c, SBA_KERNEL_REMAP);
     if (face < 0) {
         int64_t P = (int64_t)cs * 6 * cs;
         bool vec_ok = (P % 4 == 0) && (((uintptr_t)d_out) % 4 == 0);
@@ -283,6 +284,7 @@ static int launch_gather(sba_ctx* c, const uint8_t* d_erp, const RemapPlan* plan
         int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)c->sm_count * 32);
         remap_gather1_kernel<<<blocks, 256, 0, c->stream>>>(d_erp, plan->lut, d_out, src_bytes, cs, cs, 6 * cs, face * cs, n_images);
     }
+    prof_end(c, SBA_KERNEL_REMAP);
     SBA_LAUNCHED(c);
     SBA_CUDA(cudaGetLastError());
     return SBA_OK;
