@@ -131,6 +131,8 @@ typedef struct sba_match_stats {
                                re-scanned exactly */
     int n_tiles;            /* tensor-core tiles issued */
     int n_ctas;
+    float max_rel_err;      /* largest observed |approx - exact| / (|a|^2 + max|b|^2) over the candidate
+                               chunks (must stay below the bound coefficient 4e-5 the re-rank assumes) */
 } sba_match_stats;
 int sba_match_last_stats(sba_ctx* ctx, sba_match_stats* out);
 

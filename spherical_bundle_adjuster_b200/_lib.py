@@ -29,7 +29,8 @@ class SbaError(RuntimeError):
 
 
 class MatchStats(C.Structure):
-    _fields_ = [("algo_used", C.c_int), ("n_fallback_rows", C.c_int), ("n_tiles", C.c_int), ("n_ctas", C.c_int)]
+    _fields_ = [("algo_used", C.c_int), ("n_fallback_rows", C.c_int), ("n_tiles", C.c_int), ("n_ctas", C.c_int),
+                ("max_rel_err", C.c_float)]
 
 
 class SolveSummary(C.Structure):

@@ -255,6 +255,7 @@ static int run_simt(sba_ctx* c, const float* d_q, int nq, const float* d_t, int 
 // defined in matcher_tc.cu
 int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, int dim, Top2* d_top);
 bool knn2_tensor_applicable(int nq, int nt, int dim);
+bool knn2_tensor_preferred(int nq, int nt, int dim);
 
 __global__ void fill_empty_top2_kernel(Top2* top, int nq)
 {
@@ -306,7 +307,7 @@ int sba_knn2_ratio(sba_ctx* c, const float* q, int nq, const float* t, int nt, i
     }
 
     int use = algo;
-    if (use == SBA_MATCH_AUTO) use = knn2_tensor_applicable(nq, nt, dim) ? SBA_MATCH_TENSOR : SBA_MATCH_SIMT_EXACT;
+    if (use == SBA_MATCH_AUTO) use = knn2_tensor_preferred(nq, nt, dim) ? SBA_MATCH_TENSOR : SBA_MATCH_SIMT_EXACT;
     if (nt == 0) {
         fill_empty_top2_kernel<<<(nq + 255) / 256, 256, 0, st>>>(d_top, nq);
         SBA_LAUNCHED(c);
@@ -340,6 +341,12 @@ int sba_knn2_ratio(sba_ctx* c, const float* q, int nq, const float* t, int nt, i
 int sba_match_last_stats(sba_ctx* c, sba_match_stats* out)
 {
     SBA_CHECK_ARG(c && out);
+    if (c->match_stats.n_fallback_rows < 0) {
+        // tensor path: the counters were copied to the pinned mailbox on the stream
+        SBA_CUDA(cudaStreamSynchronize(c->stream));
+        c->match_stats.n_fallback_rows = c->pinned_i32[8];
+        memcpy(&c->match_stats.max_rel_err, c->pinned_i32 + 10, sizeof(float));
+    }
     *out = c->match_stats;
     return SBA_OK;
 }

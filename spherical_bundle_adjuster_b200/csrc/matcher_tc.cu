@@ -1,14 +1,592 @@
-// matcher_tc.cu -- tensor-core (tcgen05) matcher.  Placeholder until the kernel lands.
+// matcher_tc.cu -- tensor-core matcher: tcgen05 (UMMA) bf16x3 distance contraction fed by TMA, fused with
+// a per-row candidate reduction in the TMEM epilogue, then an exact fp32 re-rank.
+//
+// Replaces the knnMatch call of feature_matcher::match_two_image (feature_matcher.cpp:45) for large
+// descriptor sets; the result is bit-identical to the exact SIMT kernel / cv::BFMatcher.
+//
+// Pipeline (all on the context's stream, no host synchronisation):
+//   1. tc_prep      fp32 rows -> [hi | lo] bf16 planes (x = hi + lo + O(2^-17 |x|)) + squared norms.
+//   2. tc_knn       persistent, warp-specialised, one CTA per SM:
+//                     warp 0   TMA producer: query block (A: 128 rows x {hi,lo}) once per query block,
+//                              train tiles (B: 256 rows x {hi,lo}) through a 2-stage mbarrier ring;
+//                     warp 1   MMA issuer: per tile 12 x tcgen05.mma.kind::f16 (M128 N256 K16) =
+//                              hi.hi + hi.lo + lo.hi accumulated in fp32 in TMEM (2 x 256 columns,
+//                              double buffered so the epilogue of tile n overlaps the MMAs of n+1);
+//                     warps 2-5 epilogue: tcgen05.ld 32 columns at a time, v = |b|^2 - 2 a.b (one FFMA),
+//                              minimum per 4-column chunk, and a sorted top-4 of (chunk minimum, chunk
+//                              id) per query row kept in registers.  The distance matrix never leaves
+//                              the SM.
+//                   Work = all (query block, train tile) pairs in query-major order, cut into one
+//                   contiguous span per CTA; a span that ends inside a query block writes its partial
+//                   top-4 to its own slot, so no inter-CTA merge or atomics are needed.
+//   3. tc_rerank    per query row: merge the slots, evaluate the 16 rows of the 4 best chunks EXACTLY
+//                   (OpenCV's fp32 order, shared with the SIMT kernel) -> top-2.  Every train row outside
+//                   those chunks has approximate value >= B (the 4th best chunk minimum); with the proven
+//                   bound |approx - exact| <= delta the row is final iff  d1^2 < B + |a|^2 - delta.
+//                   Rows that fail the test (exact ties, >4 near-duplicates) are queued ...
+//   4. tc_fallback  ... and re-scanned exactly over the whole train set, one CTA per queued row.
+//
+// Roofline: tensor pipe.  Algorithmic flops 2*D*N*M; the three bf16 products cost 3x that on the pipe.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
 #include "matcher_common.cuh"
 
 namespace sba {
 
-bool knn2_tensor_applicable(int, int, int) { return false; }
+namespace tc {
 
-int knn2_tensor(sba_ctx*, const float*, int, const float*, int, int, Top2*)
+constexpr int DIM = 64;            // descriptor length handled by this path
+constexpr int KP = 2 * DIM;        // bf16 per prepared row: [hi(64) | lo(64)]
+constexpr int BM = 128;            // query rows per block (UMMA M)
+constexpr int BN = 256;            // train rows per tile (UMMA N)
+constexpr int CHUNK = 4;           // columns per candidate chunk
+constexpr int NCAND = 4;           // candidate chunks kept per row
+constexpr int STAGES = 2;          // B smem ring
+constexpr int THREADS = 192;       // warp0 TMA, warp1 MMA, warps 2-5 epilogue
+constexpr int A_KBLOCK_BYTES = BM * 128;   // one 64-wide bf16 k-block of A: 16 KB
+constexpr int B_KBLOCK_BYTES = BN * 128;   // 32 KB
+constexpr int SMEM_A = 2 * A_KBLOCK_BYTES;                 // hi, lo
+constexpr int SMEM_B = STAGES * 2 * B_KBLOCK_BYTES;        // stages x {hi, lo}
+constexpr int SMEM_NB = 2 * BN * 4;                        // |b|^2 per accumulator stage
+constexpr int SMEM_BYTES = SMEM_A + SMEM_B + SMEM_NB + 256 /*barriers*/ + 1024 /*alignment slack*/;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr float DELTA_COEF = 4e-5f;  // |approx - exact| <= DELTA_COEF * (|a|^2 + max|b|^2), see DESIGN.md
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
 {
-    set_error("tensor-core matcher not built");
-    return SBA_ERR_UNSUPPORTED;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a protocol bug traps (CUDA error) after ~2 s instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) break;
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate, M128 x N256 x K16.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// K-major, 128-byte-swizzled operand whose rows are 128 B apart and whose 8-row groups are 1024 B apart
+// (exactly what a TMA box {64 bf16, rows} with CU_TENSOR_MAP_SWIZZLE_128B writes).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);   // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;                    // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+    return d;
+}
+
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, N=256, M=128.
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+#define TMEM_LD_X32(r, taddr)                                                                                                  \
+    asm volatile(                                                                                                              \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                              \
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];" \
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),   \
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),     \
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),     \
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                                                                    \
+        : "r"(taddr)                                                                                                           \
+        : "memory")
+
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- work partition (shared by tc_knn and tc_rerank) ------------------------------------------------
+struct Partition {
+    int nqb, ntb, n_ctas;
+    long long T;
+    __host__ __device__ long long start(int c) const { return (long long)c * T / n_ctas; }
+    // the CTA whose span contains tile t
+    __host__ __device__ int cta_of(long long t) const { return (int)(((t + 1) * n_ctas - 1) / T); }
+    __host__ __device__ int max_slots() const { return (n_ctas + nqb - 1) / nqb + 1; }
+};
+
+// ---- 1. prepare ------------------------------------------------------------------------------------------
+// 16 threads per row, 4 floats each.  Rows >= n are padding: zeros, norm = +inf (train) so they never win.
+__global__ void tc_prep_kernel(const float* __restrict__ x, int n, int n_pad, __nv_bfloat16* __restrict__ out, float* __restrict__ norm,
+                               float pad_norm)
+{
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = gid >> 4, part = gid & 15;
+    if (row >= n_pad) return;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < n) v = __ldg(reinterpret_cast<const float4*>(x + (size_t)row * DIM) + part);
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    __align__(8) __nv_bfloat16 hi[4];
+    __align__(8) __nv_bfloat16 lo[4];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        hi[k] = __float2bfloat16_rn(f[k]);
+        lo[k] = __float2bfloat16_rn(f[k] - __bfloat162float(hi[k]));
+        s = fmaf(f[k], f[k], s);
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, 16);
+    __nv_bfloat16* dst = out + (size_t)row * KP;
+    *reinterpret_cast<uint2*>(dst + part * 4) = *reinterpret_cast<const uint2*>(hi);
+    *reinterpret_cast<uint2*>(dst + DIM + part * 4) = *reinterpret_cast<const uint2*>(lo);
+    if (part == 0) norm[row] = row < n ? s : pad_norm;
+}
+
+// Largest finite train norm (for the error bound), one CTA.
+__global__ void tc_max_norm_kernel(const float* __restrict__ nb, int nt, float* __restrict__ out)
+{
+    __shared__ float sh[256];
+    float m = 0.f;
+    for (int i = threadIdx.x; i < nt; i += 256) m = fmaxf(m, nb[i]);
+    sh[threadIdx.x] = m;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sh[threadIdx.x] = fmaxf(sh[threadIdx.x], sh[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sh[0];
+}
+
+// ---- 2. the tensor-core kernel ---------------------------------------------------------------------------
+struct Cand {
+    float v[NCAND];
+    int id[NCAND];
+};
+
+__device__ __forceinline__ void cand_insert(Cand& c, float m, int id)
+{
+    if (m < c.v[3]) {
+        if (m < c.v[2]) {
+            c.v[3] = c.v[2]; c.id[3] = c.id[2];
+            if (m < c.v[1]) {
+                c.v[2] = c.v[1]; c.id[2] = c.id[1];
+                if (m < c.v[0]) { c.v[1] = c.v[0]; c.id[1] = c.id[0]; c.v[0] = m; c.id[0] = id; }
+                else { c.v[1] = m; c.id[1] = id; }
+            } else { c.v[2] = m; c.id[2] = id; }
+        } else { c.v[3] = m; c.id[3] = id; }
+    }
+}
+
+__device__ __forceinline__ void cand_reset(Cand& c)
+{
+#pragma unroll
+    for (int k = 0; k < NCAND; k++) { c.v[k] = __int_as_float(0x7f800000); c.id[k] = -1; }
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const float* __restrict__ nb,
+              Partition part, float4* __restrict__ cand_v, int4* __restrict__ cand_id, int slots)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;                       // [2 kblocks][128 rows][128 B]
+    uint8_t* sB = smem + SMEM_A;              // [STAGES][2 kblocks][256 rows][128 B]
+    float* sNB = (float*)(smem + SMEM_A + SMEM_B);  // [2][256]
+    uint64_t* bars = (uint64_t*)(smem + SMEM_A + SMEM_B + SMEM_NB);
+    uint64_t* a_full = bars + 0;
+    uint64_t* a_empty = bars + 1;
+    uint64_t* b_full = bars + 2;    // [STAGES]
+    uint64_t* b_empty = bars + 4;   // [STAGES]
+    uint64_t* acc_full = bars + 6;  // [2]
+    uint64_t* acc_empty = bars + 8; // [2]
+    uint32_t* tmem_slot = (uint32_t*)(bars + 10);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long t_begin = part.start(blockIdx.x), t_end = part.start(blockIdx.x + 1);
+
+    if (threadIdx.x == 0) {
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
+        for (int s = 0; s < STAGES; s++) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int cur_qb = -1, seg = 0;
+            long long n = 0;
+            for (long long t = t_begin; t < t_end; t++, n++) {
+                const int qb = (int)(t / part.ntb), tb = (int)(t % part.ntb);
+                if (qb != cur_qb) {
+                    mbar_wait(a_empty, (seg & 1) ^ 1);
+                    mbar_expect_tx(a_full, SMEM_A);
+                    tma_load_2d(sA, &map_a, a_full, 0, qb * BM);
+                    tma_load_2d(sA + A_KBLOCK_BYTES, &map_a, a_full, DIM, qb * BM);
+                    cur_qb = qb;
+                    seg++;
+                }
+                const int s = (int)(n % STAGES);
+                mbar_wait(b_empty + s, (uint32_t)(((n / STAGES) & 1) ^ 1));
+                mbar_expect_tx(b_full + s, 2 * B_KBLOCK_BYTES);
+                uint8_t* dst = sB + (size_t)s * 2 * B_KBLOCK_BYTES;
+                tma_load_2d(dst, &map_b, b_full + s, 0, tb * BN);
+                tma_load_2d(dst + B_KBLOCK_BYTES, &map_b, b_full + s, DIM, tb * BN);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int cur_qb = -1, seg = 0;
+            long long n = 0;
+            const uint64_t dA_hi = make_smem_desc(smem_u32(sA));
+            const uint64_t dA_lo = make_smem_desc(smem_u32(sA + A_KBLOCK_BYTES));
+            for (long long t = t_begin; t < t_end; t++, n++) {
+                const int qb = (int)(t / part.ntb);
+                if (qb != cur_qb) {
+                    mbar_wait(a_full, seg & 1);
+                    cur_qb = qb;
+                    seg++;
+                }
+                const int s = (int)(n % STAGES), acc = (int)(n & 1);
+                mbar_wait(acc_empty + acc, (uint32_t)(((n >> 1) & 1) ^ 1));
+                mbar_wait(b_full + s, (uint32_t)((n / STAGES) & 1));
+                tcgen05_fence_after();
+                const uint32_t sb = smem_u32(sB + (size_t)s * 2 * B_KBLOCK_BYTES);
+                const uint64_t dB_hi = make_smem_desc(sb), dB_lo = make_smem_desc(sb + B_KBLOCK_BYTES);
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
+                // hi.hi + hi.lo + lo.hi ; each 64-wide k-block is four K=16 steps, 32 B apart
+#pragma unroll
+                for (int k = 0; k < 4; k++) umma_bf16(d_tmem, dA_hi + 2 * k, dB_hi + 2 * k, IDESC, k > 0);
+#pragma unroll
+                for (int k = 0; k < 4; k++) umma_bf16(d_tmem, dA_hi + 2 * k, dB_lo + 2 * k, IDESC, 1);
+#pragma unroll
+                for (int k = 0; k < 4; k++) umma_bf16(d_tmem, dA_lo + 2 * k, dB_hi + 2 * k, IDESC, 1);
+                tcgen05_commit(b_empty + s);     // B stage free once these MMAs have read it
+                tcgen05_commit(acc_full + acc);  // accumulator ready for the epilogue
+                const bool last_of_seg = (t + 1 == t_end) || ((int)((t + 1) / part.ntb) != qb);
+                if (last_of_seg) tcgen05_commit(a_empty);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue warps (TMEM lane quarter = warp % 4) =====
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;          // row inside the query block
+        const int etid = (warp - 2) * 32 + lane;      // 0..127 among epilogue threads
+        Cand cand;
+        cand_reset(cand);
+        long long n = 0;
+        for (long long t = t_begin; t < t_end; t++, n++) {
+            const int qb = (int)(t / part.ntb), tb = (int)(t % part.ntb);
+            const int acc = (int)(n & 1);
+            float* nbs = sNB + acc * BN;
+            nbs[etid] = __ldg(nb + (size_t)tb * BN + etid);
+            nbs[etid + 128] = __ldg(nb + (size_t)tb * BN + etid + 128);
+            asm volatile("bar.sync 1, 128;" ::: "memory");   // the 4 epilogue warps only
+            mbar_wait(acc_full + acc, (uint32_t)((n >> 1) & 1));
+            tcgen05_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * BN;
+            uint32_t buf[2][32];
+            TMEM_LD_X32(buf[0], taddr);
+            tmem_ld_wait();
+#pragma unroll
+            for (int g = 0; g < BN / 32; g++) {
+                if (g + 1 < BN / 32) TMEM_LD_X32(buf[(g + 1) & 1], taddr + (g + 1) * 32);
+                const uint32_t* r = buf[g & 1];
+                float cm[8];
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    const float4 nv = *reinterpret_cast<const float4*>(nbs + g * 32 + c * 4);
+                    const float v0 = fmaf(-2.f, __uint_as_float(r[c * 4 + 0]), nv.x);
+                    const float v1 = fmaf(-2.f, __uint_as_float(r[c * 4 + 1]), nv.y);
+                    const float v2 = fmaf(-2.f, __uint_as_float(r[c * 4 + 2]), nv.z);
+                    const float v3 = fmaf(-2.f, __uint_as_float(r[c * 4 + 3]), nv.w);
+                    cm[c] = fminf(fminf(v0, v1), fminf(v2, v3));
+                }
+                const float gm = fminf(fminf(fminf(cm[0], cm[1]), fminf(cm[2], cm[3])), fminf(fminf(cm[4], cm[5]), fminf(cm[6], cm[7])));
+                if (gm < cand.v[3]) {
+                    const int id0 = tb * (BN / CHUNK) + g * 8;
+#pragma unroll
+                    for (int c = 0; c < 8; c++) cand_insert(cand, cm[c], id0 + c);
+                }
+                tmem_ld_wait();
+            }
+            // release the accumulator stage: one arrival per epilogue warp
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + acc);
+
+            const bool last_of_seg = (t + 1 == t_end) || ((int)((t + 1) / part.ntb) != qb);
+            if (last_of_seg) {
+                const int slot = (int)blockIdx.x - part.cta_of((long long)qb * part.ntb);
+                const size_t o = ((size_t)qb * BM + row) * slots + slot;
+                cand_v[o] = make_float4(cand.v[0], cand.v[1], cand.v[2], cand.v[3]);
+                cand_id[o] = make_int4(cand.id[0], cand.id[1], cand.id[2], cand.id[3]);
+                cand_reset(cand);
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- 3. exact re-rank ---------------------------------------------------------------------------------------
+// 16 threads per query row: thread e evaluates train row 4*chunk[e/4] + e%4 exactly.
+__global__ void __launch_bounds__(256)
+tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, int nt, const float* __restrict__ na,
+                 const float* __restrict__ nb_max, Partition part, const float4* __restrict__ cand_v, const int4* __restrict__ cand_id,
+                 int slots, Top2* __restrict__ top, int* __restrict__ fb_list, int* __restrict__ fb_count, float* __restrict__ dbg_max_err)
+{
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = gid >> 4, e = gid & 15;
+    const bool active = row < nq;
+    const int r = active ? row : nq - 1;
+    // every thread of the group merges the slots itself (<= a few entries, identical result)
+    const int qb = r / BM;
+    const int c_first = part.cta_of((long long)qb * part.ntb), c_last = part.cta_of((long long)(qb + 1) * part.ntb - 1);
+    Cand c;
+    cand_reset(c);
+    for (int s = 0; s <= c_last - c_first; s++) {
+        const float4 v = cand_v[(size_t)r * slots + s];
+        const int4 id = cand_id[(size_t)r * slots + s];
+        cand_insert(c, v.x, id.x); cand_insert(c, v.y, id.y); cand_insert(c, v.z, id.z); cand_insert(c, v.w, id.w);
+    }
+    const float B = c.v[3];
+    const int chunk = c.id[e >> 2];
+    const int j = chunk * CHUNK + (e & 3);
+    Top2 best = top2_empty();
+    float approx_gap = 0.f;
+    if (chunk >= 0 && j < nt) {
+        const float dsq = l2sqr_opencv<DIM>(q + (size_t)r * DIM, t + (size_t)j * DIM);
+        best.d0 = __fsqrt_rn(dsq);
+        best.i0 = j;
+        approx_gap = dsq - na[r];   // exact value on the scale of the approximate ones
+    }
+    // diagnostics: |chunk minimum (approx) - min over its 4 rows (exact)|, relative to the bound scale
+    float gmin = (chunk >= 0 && j < nt) ? approx_gap : __int_as_float(0x7f800000);
+    gmin = fminf(gmin, __shfl_xor_sync(0xffffffffu, gmin, 1));
+    gmin = fminf(gmin, __shfl_xor_sync(0xffffffffu, gmin, 2));
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        Top2 other;
+        other.d0 = __shfl_xor_sync(0xffffffffu, best.d0, o);
+        other.d1 = __shfl_xor_sync(0xffffffffu, best.d1, o);
+        other.i0 = __shfl_xor_sync(0xffffffffu, best.i0, o);
+        other.i1 = __shfl_xor_sync(0xffffffffu, best.i1, o);
+        best = top2_merge(best, other);
+    }
+    const float scale = na[r] + *nb_max;
+    if (active && dbg_max_err && (e & 3) == 0 && chunk >= 0 && isfinite(gmin) && scale > 0.f) {
+        const float err = fabsf(gmin - c.v[e >> 2]) / scale;
+        atomicMax((int*)dbg_max_err, __float_as_int(err));   // non-negative floats order like ints
+    }
+    if (active && e == 0) {
+        // final iff no row outside the candidate chunks can reach the second best:
+        //   d1^2 (rounded up) < B + |a|^2 - delta
+        const float delta = DELTA_COEF * scale;
+        const float d1sq_up = best.d1 * best.d1 * (1.f + 5e-7f);
+        const bool safe = !(B < __int_as_float(0x7f800000)) || (best.i1 != KNN_MISSING && d1sq_up < B + na[r] - delta);
+        if (safe) top[row] = best;
+        else {
+            const int k = atomicAdd(fb_count, 1);
+            fb_list[k] = row;
+        }
+    }
+}
+
+// ---- 4. exact fallback for queued rows --------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+tc_fallback_kernel(const float* __restrict__ q, const float* __restrict__ t, int nt, const int* __restrict__ fb_list,
+                   const int* __restrict__ fb_count, Top2* __restrict__ top)
+{
+    __shared__ Top2 sh[128];
+    __shared__ float qs[DIM];
+    const int n = *fb_count;
+    for (int k = blockIdx.x; k < n; k += gridDim.x) {
+        const int row = fb_list[k];
+        __syncthreads();
+        if (threadIdx.x < DIM) qs[threadIdx.x] = q[(size_t)row * DIM + threadIdx.x];
+        __syncthreads();
+        Top2 best = top2_empty();
+        for (int j = threadIdx.x; j < nt; j += 128) {
+            const float d = __fsqrt_rn(l2sqr_opencv<DIM>(qs, t + (size_t)j * DIM));
+            top2_push_ordered(best, d, j);
+        }
+        sh[threadIdx.x] = best;
+        __syncthreads();
+        for (int s = 64; s > 0; s >>= 1) {
+            if ((int)threadIdx.x < s) sh[threadIdx.x] = top2_merge(sh[threadIdx.x], sh[threadIdx.x + s]);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) top[row] = sh[0];
+    }
+}
+
+// ---- host ----------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// rows x KP bf16, row-major; box = 64 columns (128 B) x box_rows, 128B swizzle
+static int make_map(CUtensorMap* map, void* base, int rows, int box_rows)
+{
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return SBA_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)KP, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)KP * sizeof(__nv_bfloat16)};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return SBA_ERR_CUDA;
+    }
+    return SBA_OK;
+}
+
+}  // namespace tc
+
+bool knn2_tensor_applicable(int nq, int nt, int dim) { return dim == tc::DIM && nq >= 1 && nt >= 1; }
+
+// Heuristic used by SBA_MATCH_AUTO: below ~1M pair distances the exact SIMT kernel's latency wins.
+bool knn2_tensor_preferred(int nq, int nt, int dim) { return dim == tc::DIM && (long long)nq * nt >= (1ll << 20) && nt >= 1024; }
+
+int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, int dim, Top2* d_top)
+{
+    using namespace tc;
+    if (dim != DIM) {
+        set_error("tensor-core matcher handles dim %d only", DIM);
+        return SBA_ERR_UNSUPPORTED;
+    }
+    cudaStream_t st = c->stream;
+    const int nqb = (nq + BM - 1) / BM, ntb = (nt + BN - 1) / BN;
+    const int nq_pad = nqb * BM, nt_pad = ntb * BN;
+    Partition part;
+    part.nqb = nqb; part.ntb = ntb; part.T = (long long)nqb * ntb;
+    part.n_ctas = (int)std::min<long long>(c->sm_count, part.T);
+    const int slots = part.max_slots();
+
+    // workspace carve-up (one buffer)
+    auto align_up = [](size_t v) { return (v + 1023) & ~(size_t)1023; };
+    size_t off = 0;
+    const size_t o_a = off; off = align_up(off + (size_t)nq_pad * KP * 2);
+    const size_t o_b = off; off = align_up(off + (size_t)nt_pad * KP * 2);
+    const size_t o_na = off; off = align_up(off + (size_t)nq_pad * 4);
+    const size_t o_nb = off; off = align_up(off + (size_t)nt_pad * 4);
+    const size_t o_cv = off; off = align_up(off + (size_t)nq_pad * slots * 16);
+    const size_t o_ci = off; off = align_up(off + (size_t)nq_pad * slots * 16);
+    const size_t o_fl = off; off = align_up(off + (size_t)nq * 4);
+    const size_t o_misc = off; off = align_up(off + 64);
+    SBA_TRY(c->scratch[SCR_WORK2].ensure(off, st));
+    uint8_t* ws = c->scratch[SCR_WORK2].as<uint8_t>();
+    __nv_bfloat16* dA = (__nv_bfloat16*)(ws + o_a);
+    __nv_bfloat16* dB = (__nv_bfloat16*)(ws + o_b);
+    float* d_na = (float*)(ws + o_na);
+    float* d_nb = (float*)(ws + o_nb);
+    float4* d_cv = (float4*)(ws + o_cv);
+    int4* d_ci = (int4*)(ws + o_ci);
+    int* d_fl = (int*)(ws + o_fl);
+    int* d_fb_count = (int*)(ws + o_misc);
+    float* d_nbmax = (float*)(ws + o_misc + 4);
+    float* d_dbg = (float*)(ws + o_misc + 8);
+
+    SBA_CUDA(cudaMemsetAsync(ws + o_misc, 0, 64, st));
+    tc_prep_kernel<<<(nq_pad * 16 + 255) / 256, 256, 0, st>>>(d_q, nq, nq_pad, dA, d_na, 0.f);
+    SBA_LAUNCHED(c);
+    tc_prep_kernel<<<(nt_pad * 16 + 255) / 256, 256, 0, st>>>(d_t, nt, nt_pad, dB, d_nb, INFINITY);
+    SBA_LAUNCHED(c);
+    tc_max_norm_kernel<<<1, 256, 0, st>>>(d_nb, nt, d_nbmax);
+    SBA_LAUNCHED(c);
+
+    CUtensorMap map_a, map_b;
+    SBA_TRY(make_map(&map_a, dA, nq_pad, BM));
+    SBA_TRY(make_map(&map_b, dB, nt_pad, BN));
+    SBA_CUDA(cudaFuncSetAttribute(tc_knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    prof_begin(c, SBA_KERNEL_MATCH);
+    tc_knn_kernel<<<part.n_ctas, THREADS, SMEM_BYTES, st>>>(map_a, map_b, d_nb, part, d_cv, d_ci, slots);
+    prof_end(c, SBA_KERNEL_MATCH);
+    SBA_LAUNCHED(c);
+    SBA_CUDA(cudaGetLastError());
+
+    tc_rerank_kernel<<<(nq * 16 + 255) / 256, 256, 0, st>>>(d_q, nq, d_t, nt, d_na, d_nbmax, part, d_cv, d_ci, slots, d_top, d_fl, d_fb_count, d_dbg);
+    SBA_LAUNCHED(c);
+    tc_fallback_kernel<<<std::min(nq, 4 * c->sm_count), 128, 0, st>>>(d_q, d_t, nt, d_fl, d_fb_count, d_top);
+    SBA_LAUNCHED(c);
+    SBA_CUDA(cudaGetLastError());
+    // diagnostics land in the pinned mailbox; read by sba_match_last_stats after a synchronise
+    SBA_CUDA(cudaMemcpyAsync(c->pinned_i32 + 8, d_fb_count, 12, cudaMemcpyDeviceToHost, st));
+    c->match_stats.n_tiles = (int)part.T;
+    c->match_stats.n_ctas = part.n_ctas;
+    c->match_stats.n_fallback_rows = -1;  // resolved lazily from the mailbox
+    return SBA_OK;
 }
 
 }  // namespace sba

@@ -7,10 +7,21 @@ import numpy as np
 import pytest
 
 import oracle
-from spherical_bundle_adjuster_b200 import MATCH_AUTO, MATCH_SIMT_EXACT, synth
+from spherical_bundle_adjuster_b200 import MATCH_AUTO, MATCH_SIMT_EXACT, MATCH_TENSOR, SbaError, synth
 
 pytestmark = pytest.mark.gpu
-ALGOS = [MATCH_SIMT_EXACT, MATCH_AUTO]
+ALGOS = [MATCH_SIMT_EXACT, MATCH_TENSOR, MATCH_AUTO]
+
+
+def _match(ctx, q, t, ratio, algo, **kw):
+    """The tensor-core path covers SURF-64; asking for it explicitly with 128-d descriptors must fail
+    loudly (AUTO routes those to the exact SIMT kernel)."""
+    dim = q.shape[1] if q.ndim == 2 and q.shape[0] else t.shape[1]
+    if algo == MATCH_TENSOR and dim != 64:
+        with pytest.raises(SbaError):
+            ctx.match_two_image(q, t, ratio, algo=algo, **kw)
+        pytest.skip("tensor path: 64-d only")
+    return ctx.match_two_image(q, t, ratio, algo=algo, **kw)
 
 
 def _check(m, q, t, ratio=0.3):
@@ -27,7 +38,7 @@ def _check(m, q, t, ratio=0.3):
 @pytest.mark.parametrize("name", ["matcher_64.npz", "matcher_128.npz", "matcher_ragged.npz"])
 def test_matcher_matches_cv2_golden(ctx, golden_dir, name, algo):
     g = np.load(os.path.join(golden_dir, name))
-    m = ctx.match_two_image(g["q"], g["t"], 0.3, algo=algo, want_knn=True)
+    m = _match(ctx, g["q"], g["t"], 0.3, algo, want_knn=True)
     assert np.array_equal(m.knn_idx, g["knn_idx"])
     assert np.array_equal(m.knn_dist.view(np.uint32), g["knn_dist"].view(np.uint32))
     assert np.array_equal(m.query_idx, g["keep"])
@@ -38,7 +49,7 @@ def test_matcher_matches_cv2_golden(ctx, golden_dir, name, algo):
 @pytest.mark.parametrize("nq,nt,dim", [(1000, 1000, 64), (777, 1301, 64), (130, 4097, 64), (2048, 300, 128), (5000, 3000, 64)])
 def test_matcher_matches_oracle(ctx, nq, nt, dim, algo):
     A, B, _ = synth.make_descriptors(nq, nt, dim, seed=nq + nt)
-    _check(ctx.match_two_image(A, B, 0.3, algo=algo, want_knn=True), A, B)
+    _check(_match(ctx, A, B, 0.3, algo, want_knn=True), A, B)
 
 
 @pytest.mark.parametrize("algo", ALGOS)
@@ -75,6 +86,27 @@ def test_matcher_device_tensors(ctx, algo):
     _check(m2, A, B)
 
 
+def test_tensor_path_error_bound_and_fallback(ctx):
+    """The re-rank's safety test assumes |approx - exact| <= 4e-5 (|a|^2 + max|b|^2); the kernel reports
+    the largest value it actually saw.  Exact duplicates must route rows through the exact fallback."""
+    A, B, _ = synth.make_descriptors(4096, 4096, 64, seed=21)
+    m = ctx.match_two_image(A, B, 0.3, algo=MATCH_TENSOR, want_knn=True)
+    st = ctx.match_stats()
+    assert st.algo_used == MATCH_TENSOR and st.n_tiles == 32 * 16
+    assert 0.0 <= st.max_rel_err < 1e-5, st.max_rel_err         # observed error, 4x below the assumed bound
+    assert st.n_fallback_rows <= 8
+    _check(m, A, B)
+    B[1000:1040] = B[7]          # 40 identical rows: more ties than candidate chunks can hold
+    A[5] = B[7]
+    m = ctx.match_two_image(A, B, 0.3, algo=MATCH_TENSOR, want_knn=True)
+    assert ctx.match_stats().n_fallback_rows >= 1
+    _check(m, A, B)
+    # descriptors that are not unit norm (SIFT-like magnitudes): the bound scales with the norms
+    A2, B2 = (A * 512).astype(np.float32), (B * 512).astype(np.float32)
+    _check(ctx.match_two_image(A2, B2, 0.3, algo=MATCH_TENSOR, want_knn=True), A2, B2)
+    assert ctx.match_stats().max_rel_err < 1e-5
+
+
 def test_matcher_full_size_properties(ctx):
     """BASELINE config-2 size (16k x 16k): the oracle needs ~1 min here, so check size-independent
     properties: every planted pair is recovered exactly, AUTO == SIMT bit-for-bit, and a sampled
@@ -82,6 +114,7 @@ def test_matcher_full_size_properties(ctx):
     A, B, truth = synth.make_descriptors(16384, 16384, 64, seed=2)
     ms = ctx.match_two_image(A, B, 0.3, algo=MATCH_SIMT_EXACT, want_knn=True)
     ma = ctx.match_two_image(A, B, 0.3, algo=MATCH_AUTO, want_knn=True)
+    assert ctx.match_stats().algo_used == MATCH_TENSOR
     planted = np.flatnonzero(truth >= 0)
     assert np.array_equal(ms.query_idx, planted) and np.array_equal(ms.train_idx, truth[planted])
     for a, b in [(ms.knn_idx, ma.knn_idx), (ms.query_idx, ma.query_idx), (ms.train_idx, ma.train_idx)]:
