@@ -6,19 +6,23 @@
 //
 // Pipeline (all on the context's stream, no host synchronisation):
 //   1. tc_prep      fp32 rows -> [hi | lo] bf16 planes (x = hi + lo + O(2^-17 |x|)) + squared norms.
-//   2. tc_knn       persistent, warp-specialised, one CTA per SM:
-//                     warp 0   TMA producer: query block (A: 128 rows x {hi,lo}) once per query block,
-//                              train tiles (B: 256 rows x {hi,lo}) through a 2-stage mbarrier ring;
-//                     warp 1   MMA issuer: per tile 12 x tcgen05.mma.kind::f16 (M128 N256 K16) =
-//                              hi.hi + hi.lo + lo.hi accumulated in fp32 in TMEM (2 x 256 columns,
-//                              double buffered so the epilogue of tile n overlaps the MMAs of n+1);
-//                     warps 2-5 epilogue: tcgen05.ld 32 columns at a time, v = |b|^2 - 2 a.b (one FFMA),
-//                              minimum per 4-column chunk, and a sorted top-4 of (chunk minimum, chunk
-//                              id) per query row kept in registers.  The distance matrix never leaves
-//                              the SM.
+//   2. tc_knn       persistent, warp-specialised, one CTA per SM (640 threads):
+//                     warp 0   TMA producer: query block (A: 256 rows x {hi,lo}, 64 KB) once per query
+//                              block; train tiles (B: 128 rows x {hi,lo}, 32 KB) through a 4-stage
+//                              mbarrier ring.  One B tile feeds TWO M=128 MMA row-halves, which halves
+//                              the L2->SM operand traffic per flop (at full tensor rate a 128-row query
+//                              block would sit exactly on the L2 throughput cap).
+//                     warp 1   MMA issuer: per tile 2 x 12 tcgen05.mma.kind::f16 (M128 N128 K16) =
+//                              hi.hi + hi.lo + lo.hi accumulated in fp32 in TMEM (2 stages x 256 columns,
+//                              so the epilogue of tile n overlaps the MMAs of tile n+1);
+//                     warps 4-19 epilogue (16 warps = 4 TMEM lane quarters x 4 column slices of 64):
+//                              tcgen05.ld 32 columns at a time, v = |b|^2 - 2 a.b (one FFMA), minimum per
+//                              4-column chunk (3-input FMNMX), and a sorted top-4 of (chunk minimum, chunk
+//                              id) per thread in registers; inserts are branch-free and guarded by warp
+//                              votes.  The distance matrix never leaves the SM.
 //                   Work = all (query block, train tile) pairs in query-major order, cut into one
 //                   contiguous span per CTA; a span that ends inside a query block writes its partial
-//                   top-4 to its own slot, so no inter-CTA merge or atomics are needed.
+//                   top-4 lists to its own slots, so no inter-CTA merge or atomics are needed.
 //   3. tc_rerank    per query row: merge the slots, evaluate the 16 rows of the 4 best chunks EXACTLY
 //                   (OpenCV's fp32 order, shared with the SIMT kernel) -> top-2.  Every train row outside
 //                   those chunks has approximate value >= B (the 4th best chunk minimum); with the proven
@@ -38,18 +42,21 @@ namespace tc {
 
 constexpr int DIM = 64;            // descriptor length handled by this path
 constexpr int KP = 2 * DIM;        // bf16 per prepared row: [hi(64) | lo(64)]
-constexpr int BM = 128;            // query rows per block (UMMA M)
-constexpr int BN = 256;            // train rows per tile (UMMA N)
+constexpr int BM = 256;            // query rows per block: two UMMA M=128 row-halves share every B tile
+constexpr int BN = 128;            // train rows per tile (UMMA N)
 constexpr int CHUNK = 4;           // columns per candidate chunk
-constexpr int NCAND = 4;           // candidate chunks kept per row
-constexpr int STAGES = 2;          // B smem ring
-constexpr int THREADS = 192;       // warp0 TMA, warp1 MMA, warps 2-5 epilogue
-constexpr int A_KBLOCK_BYTES = BM * 128;   // one 64-wide bf16 k-block of A: 16 KB
-constexpr int B_KBLOCK_BYTES = BN * 128;   // 32 KB
+constexpr int NCAND = 4;           // candidate chunks kept per list
+constexpr int STAGES = 4;          // B smem ring
+constexpr int EPI_WARPS = 16;      // 4 TMEM lane quarters x 4 column slices
+constexpr int SUBSLOTS = 2;        // candidate lists per query row per CTA span (2 column slices per row-half)
+constexpr int THREADS = 128 + EPI_WARPS * 32;   // warp0 TMA, warp1 MMA, warps 2-3 idle, warps 4-19 epilogue
+constexpr int A_KBLOCK_BYTES = BM * 128;   // one 64-wide bf16 k-block of A: 32 KB
+constexpr int B_KBLOCK_BYTES = BN * 128;   // 16 KB
 constexpr int SMEM_A = 2 * A_KBLOCK_BYTES;                 // hi, lo
 constexpr int SMEM_B = STAGES * 2 * B_KBLOCK_BYTES;        // stages x {hi, lo}
 constexpr int SMEM_NB = 2 * BN * 4;                        // |b|^2 per accumulator stage
 constexpr int SMEM_BYTES = SMEM_A + SMEM_B + SMEM_NB + 256 /*barriers*/ + 1024 /*alignment slack*/;
+constexpr int ACC_COLS = 2 * BN;   // TMEM columns per accumulator stage: row-half 0 | row-half 1
 constexpr uint32_t TMEM_COLS = 512;
 constexpr float DELTA_COEF = 4e-5f;  // |approx - exact| <= DELTA_COEF * (|a|^2 + max|b|^2), see DESIGN.md
 
@@ -100,7 +107,7 @@ __device__ __forceinline__ void tcgen05_commit(uint64_t* bar)
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate, M128 x N256 x K16.
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate, M128 x N128 x K16.
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
@@ -124,8 +131,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr)
     return d;
 }
 
-// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, N=256, M=128.
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, N=128, M=128.
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 #define TMEM_LD_X32(r, taddr)                                                                                                  \
     asm volatile(                                                                                                              \
@@ -213,6 +220,25 @@ __device__ __forceinline__ void cand_insert(Cand& c, float m, int id)
     }
 }
 
+// Branch-free variant for the epilogue (same result): place at the tail if it beats the tail, then
+// bubble up with three compare-exchanges.  Strict '<' keeps the earlier chunk ahead on ties.
+__device__ __forceinline__ void cand_insert_bf(Cand& c, float m, int id)
+{
+    const bool p = m < c.v[3];
+    c.v[3] = p ? m : c.v[3];
+    c.id[3] = p ? id : c.id[3];
+#pragma unroll
+    for (int k = 3; k > 0; k--) {
+        const bool sw = c.v[k] < c.v[k - 1];
+        const float tv = c.v[k - 1];
+        const int ti = c.id[k - 1];
+        c.v[k - 1] = sw ? c.v[k] : tv;
+        c.id[k - 1] = sw ? c.id[k] : ti;
+        c.v[k] = sw ? tv : c.v[k];
+        c.id[k] = sw ? ti : c.id[k];
+    }
+}
+
 __device__ __forceinline__ void cand_reset(Cand& c)
 {
 #pragma unroll
@@ -225,17 +251,17 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* sA = smem;                       // [2 kblocks][128 rows][128 B]
-    uint8_t* sB = smem + SMEM_A;              // [STAGES][2 kblocks][256 rows][128 B]
-    float* sNB = (float*)(smem + SMEM_A + SMEM_B);  // [2][256]
+    uint8_t* sA = smem;                       // [2 kblocks][256 rows][128 B]
+    uint8_t* sB = smem + SMEM_A;              // [STAGES][2 kblocks][128 rows][128 B]
+    float* sNB = (float*)(smem + SMEM_A + SMEM_B);  // [2][BN]
     uint64_t* bars = (uint64_t*)(smem + SMEM_A + SMEM_B + SMEM_NB);
     uint64_t* a_full = bars + 0;
     uint64_t* a_empty = bars + 1;
-    uint64_t* b_full = bars + 2;    // [STAGES]
-    uint64_t* b_empty = bars + 4;   // [STAGES]
-    uint64_t* acc_full = bars + 6;  // [2]
-    uint64_t* acc_empty = bars + 8; // [2]
-    uint32_t* tmem_slot = (uint32_t*)(bars + 10);
+    uint64_t* b_full = bars + 2;               // [STAGES]
+    uint64_t* b_empty = bars + 2 + STAGES;     // [STAGES]
+    uint64_t* acc_full = bars + 2 + 2 * STAGES;   // [2]
+    uint64_t* acc_empty = bars + 4 + 2 * STAGES;  // [2]
+    uint32_t* tmem_slot = (uint32_t*)(bars + 6 + 2 * STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long t_begin = part.start(blockIdx.x), t_end = part.start(blockIdx.x + 1);
@@ -244,7 +270,7 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
         for (int s = 0; s < STAGES; s++) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4); }
+        for (int s = 0; s < 2; s++) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -285,8 +311,6 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         if (lane == 0) {
             int cur_qb = -1, seg = 0;
             long long n = 0;
-            const uint64_t dA_hi = make_smem_desc(smem_u32(sA));
-            const uint64_t dA_lo = make_smem_desc(smem_u32(sA + A_KBLOCK_BYTES));
             for (long long t = t_begin; t < t_end; t++, n++) {
                 const int qb = (int)(t / part.ntb);
                 if (qb != cur_qb) {
@@ -300,14 +324,20 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 tcgen05_fence_after();
                 const uint32_t sb = smem_u32(sB + (size_t)s * 2 * B_KBLOCK_BYTES);
                 const uint64_t dB_hi = make_smem_desc(sb), dB_lo = make_smem_desc(sb + B_KBLOCK_BYTES);
-                const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
-                // hi.hi + hi.lo + lo.hi ; each 64-wide k-block is four K=16 steps, 32 B apart
 #pragma unroll
-                for (int k = 0; k < 4; k++) umma_bf16(d_tmem, dA_hi + 2 * k, dB_hi + 2 * k, IDESC, k > 0);
+                for (int h = 0; h < 2; h++) {
+                    // row-half h of the query block: rows 128h.. of each A k-block
+                    const uint64_t dA_hi = make_smem_desc(smem_u32(sA + h * (128 * 128)));
+                    const uint64_t dA_lo = make_smem_desc(smem_u32(sA + A_KBLOCK_BYTES + h * (128 * 128)));
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS + h * BN);
+                    // hi.hi + hi.lo + lo.hi ; each 64-wide k-block is four K=16 steps, 32 B apart
 #pragma unroll
-                for (int k = 0; k < 4; k++) umma_bf16(d_tmem, dA_hi + 2 * k, dB_lo + 2 * k, IDESC, 1);
+                    for (int k = 0; k < 4; k++) umma_bf16(d_tmem, dA_hi + 2 * k, dB_hi + 2 * k, IDESC, k > 0);
 #pragma unroll
-                for (int k = 0; k < 4; k++) umma_bf16(d_tmem, dA_lo + 2 * k, dB_hi + 2 * k, IDESC, 1);
+                    for (int k = 0; k < 4; k++) umma_bf16(d_tmem, dA_hi + 2 * k, dB_lo + 2 * k, IDESC, 1);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) umma_bf16(d_tmem, dA_lo + 2 * k, dB_hi + 2 * k, IDESC, 1);
+                }
                 tcgen05_commit(b_empty + s);     // B stage free once these MMAs have read it
                 tcgen05_commit(acc_full + acc);  // accumulator ready for the epilogue
                 const bool last_of_seg = (t + 1 == t_end) || ((int)((t + 1) / part.ntb) != qb);
@@ -315,11 +345,14 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             }
         }
         __syncwarp();
-    } else {
-        // ===== epilogue warps (TMEM lane quarter = warp % 4) =====
+    } else if (warp >= 4) {
+        // ===== epilogue warps: TMEM lane quarter = warp % 4, column slice = (warp - 4) / 4 =====
         const int quarter = warp & 3;
-        const int row = quarter * 32 + lane;          // row inside the query block
-        const int etid = (warp - 2) * 32 + lane;      // 0..127 among epilogue threads
+        const int slice = (warp - 4) >> 2;            // 0..3: 64 accumulator columns each
+        const int half = slice >> 1;                  // which M=128 row-half those columns belong to
+        const int csub = slice & 1;                   // which 64 train columns of the tile
+        const int row = half * 128 + quarter * 32 + lane;   // row inside the 256-row query block
+        const int etid = threadIdx.x - 128;           // 0..511 among epilogue threads
         Cand cand;
         cand_reset(cand);
         long long n = 0;
@@ -327,23 +360,27 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             const int qb = (int)(t / part.ntb), tb = (int)(t % part.ntb);
             const int acc = (int)(n & 1);
             float* nbs = sNB + acc * BN;
-            nbs[etid] = __ldg(nb + (size_t)tb * BN + etid);
-            nbs[etid + 128] = __ldg(nb + (size_t)tb * BN + etid + 128);
-            asm volatile("bar.sync 1, 128;" ::: "memory");   // the 4 epilogue warps only
+            if (etid < BN) nbs[etid] = __ldg(nb + (size_t)tb * BN + etid);
+            asm volatile("bar.sync 1, 512;" ::: "memory");   // the 16 epilogue warps only
             mbar_wait(acc_full + acc, (uint32_t)((n >> 1) & 1));
             tcgen05_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * BN;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS + slice * 64);
+            const float* nbc = nbs + csub * 64;
             uint32_t buf[2][32];
             TMEM_LD_X32(buf[0], taddr);
+            TMEM_LD_X32(buf[1], taddr + 32);
             tmem_ld_wait();
+            // release the accumulator stage as soon as its values sit in registers
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + acc);
 #pragma unroll
-            for (int g = 0; g < BN / 32; g++) {
-                if (g + 1 < BN / 32) TMEM_LD_X32(buf[(g + 1) & 1], taddr + (g + 1) * 32);
-                const uint32_t* r = buf[g & 1];
+            for (int g = 0; g < 2; g++) {
+                const uint32_t* r = buf[g];
                 float cm[8];
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
-                    const float4 nv = *reinterpret_cast<const float4*>(nbs + g * 32 + c * 4);
+                    const float4 nv = *reinterpret_cast<const float4*>(nbc + g * 32 + c * 4);
                     const float v0 = fmaf(-2.f, __uint_as_float(r[c * 4 + 0]), nv.x);
                     const float v1 = fmaf(-2.f, __uint_as_float(r[c * 4 + 1]), nv.y);
                     const float v2 = fmaf(-2.f, __uint_as_float(r[c * 4 + 2]), nv.z);
@@ -351,21 +388,16 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                     cm[c] = fminf(fminf(v0, v1), fminf(v2, v3));
                 }
                 const float gm = fminf(fminf(fminf(cm[0], cm[1]), fminf(cm[2], cm[3])), fminf(fminf(cm[4], cm[5]), fminf(cm[6], cm[7])));
-                if (gm < cand.v[3]) {
-                    const int id0 = tb * (BN / CHUNK) + g * 8;
+                if (__any_sync(0xffffffffu, gm < cand.v[3])) {
+                    const int id0 = tb * (BN / CHUNK) + csub * 16 + g * 8;
 #pragma unroll
-                    for (int c = 0; c < 8; c++) cand_insert(cand, cm[c], id0 + c);
+                    for (int c = 0; c < 8; c++)
+                        if (__any_sync(0xffffffffu, cm[c] < cand.v[3])) cand_insert_bf(cand, cm[c], id0 + c);
                 }
-                tmem_ld_wait();
             }
-            // release the accumulator stage: one arrival per epilogue warp
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty + acc);
-
             const bool last_of_seg = (t + 1 == t_end) || ((int)((t + 1) / part.ntb) != qb);
             if (last_of_seg) {
-                const int slot = (int)blockIdx.x - part.cta_of((long long)qb * part.ntb);
+                const int slot = ((int)blockIdx.x - part.cta_of((long long)qb * part.ntb)) * SUBSLOTS + csub;
                 const size_t o = ((size_t)qb * BM + row) * slots + slot;
                 cand_v[o] = make_float4(cand.v[0], cand.v[1], cand.v[2], cand.v[3]);
                 cand_id[o] = make_int4(cand.id[0], cand.id[1], cand.id[2], cand.id[3]);
@@ -384,6 +416,7 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 
 // ---- 3. exact re-rank ---------------------------------------------------------------------------------------
 // 16 threads per query row: thread e evaluates train row 4*chunk[e/4] + e%4 exactly.
+// (BM here is the 256-row query block of tc_knn.)
 __global__ void __launch_bounds__(256)
 tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, int nt, const float* __restrict__ na,
                  const float* __restrict__ nb_max, Partition part, const float4* __restrict__ cand_v, const int4* __restrict__ cand_id,
@@ -398,7 +431,7 @@ tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ 
     const int c_first = part.cta_of((long long)qb * part.ntb), c_last = part.cta_of((long long)(qb + 1) * part.ntb - 1);
     Cand c;
     cand_reset(c);
-    for (int s = 0; s <= c_last - c_first; s++) {
+    for (int s = 0; s < (c_last - c_first + 1) * SUBSLOTS; s++) {
         const float4 v = cand_v[(size_t)r * slots + s];
         const int4 id = cand_id[(size_t)r * slots + s];
         cand_insert(c, v.x, id.x); cand_insert(c, v.y, id.y); cand_insert(c, v.z, id.z); cand_insert(c, v.w, id.w);
@@ -532,7 +565,7 @@ int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, 
     Partition part;
     part.nqb = nqb; part.ntb = ntb; part.T = (long long)nqb * ntb;
     part.n_ctas = (int)std::min<long long>(c->sm_count, part.T);
-    const int slots = part.max_slots();
+    const int slots = part.max_slots() * SUBSLOTS;
 
     // workspace carve-up (one buffer)
     auto align_up = [](size_t v) { return (v + 1023) & ~(size_t)1023; };
