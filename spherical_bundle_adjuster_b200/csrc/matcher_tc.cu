@@ -54,7 +54,7 @@ constexpr int A_KBLOCK_BYTES = BM * 128;   // one 64-wide bf16 k-block of A: 32 
 constexpr int B_KBLOCK_BYTES = BN * 128;   // 16 KB
 constexpr int SMEM_A = 2 * A_KBLOCK_BYTES;                 // hi, lo
 constexpr int SMEM_B = STAGES * 2 * B_KBLOCK_BYTES;        // stages x {hi, lo}
-constexpr int SMEM_NB = 2 * BN * 4;                        // |b|^2 per accumulator stage
+constexpr int SMEM_NB = EPI_WARPS * 64 * 4;                 // |b|^2 staging, 64 columns per epilogue warp
 constexpr int SMEM_BYTES = SMEM_A + SMEM_B + SMEM_NB + 256 /*barriers*/ + 1024 /*alignment slack*/;
 constexpr int ACC_COLS = 2 * BN;   // TMEM columns per accumulator stage: row-half 0 | row-half 1
 constexpr uint32_t TMEM_COLS = 512;
@@ -249,11 +249,12 @@ __global__ void __launch_bounds__(THREADS, 1)
 tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const float* __restrict__ nb,
               Partition part, float4* __restrict__ cand_v, int4* __restrict__ cand_id, int slots)
 {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte alignment for the 128B-swizzle atoms; offset arithmetic keeps the shared address space
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sA = smem;                       // [2 kblocks][256 rows][128 B]
     uint8_t* sB = smem + SMEM_A;              // [STAGES][2 kblocks][128 rows][128 B]
-    float* sNB = (float*)(smem + SMEM_A + SMEM_B);  // [2][BN]
+    float* sNB = (float*)(smem + SMEM_A + SMEM_B);  // [EPI_WARPS][64]: |b|^2 of each epilogue warp's columns
     uint64_t* bars = (uint64_t*)(smem + SMEM_A + SMEM_B + SMEM_NB);
     uint64_t* a_full = bars + 0;
     uint64_t* a_empty = bars + 1;
@@ -264,7 +265,10 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     uint32_t* tmem_slot = (uint32_t*)(bars + 6 + 2 * STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long t_begin = part.start(blockIdx.x), t_end = part.start(blockIdx.x + 1);
+    // this CTA's span of tiles, walked with 32-bit incremental (query block, train tile) indices
+    const int t_begin = (int)part.start(blockIdx.x), n_tiles = (int)part.start(blockIdx.x + 1) - t_begin;
+    const int ntb = part.ntb;
+    const int qb0 = t_begin / ntb, tb0 = t_begin - qb0 * ntb;
 
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
@@ -285,63 +289,72 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            int cur_qb = -1, seg = 0;
-            long long n = 0;
-            for (long long t = t_begin; t < t_end; t++, n++) {
-                const int qb = (int)(t / part.ntb), tb = (int)(t % part.ntb);
-                if (qb != cur_qb) {
+            int qb = qb0, tb = tb0, seg = 0, s = 0;
+            uint32_t ring_phase = 0;
+            bool new_seg = true;
+            for (int n = 0; n < n_tiles; n++) {
+                if (new_seg) {
                     mbar_wait(a_empty, (seg & 1) ^ 1);
                     mbar_expect_tx(a_full, SMEM_A);
                     tma_load_2d(sA, &map_a, a_full, 0, qb * BM);
                     tma_load_2d(sA + A_KBLOCK_BYTES, &map_a, a_full, DIM, qb * BM);
-                    cur_qb = qb;
                     seg++;
                 }
-                const int s = (int)(n % STAGES);
-                mbar_wait(b_empty + s, (uint32_t)(((n / STAGES) & 1) ^ 1));
+                mbar_wait(b_empty + s, ring_phase ^ 1);
                 mbar_expect_tx(b_full + s, 2 * B_KBLOCK_BYTES);
-                uint8_t* dst = sB + (size_t)s * 2 * B_KBLOCK_BYTES;
+                uint8_t* dst = sB + s * (2 * B_KBLOCK_BYTES);
                 tma_load_2d(dst, &map_b, b_full + s, 0, tb * BN);
                 tma_load_2d(dst + B_KBLOCK_BYTES, &map_b, b_full + s, DIM, tb * BN);
+                if (++s == STAGES) { s = 0; ring_phase ^= 1; }
+                new_seg = (++tb == ntb);
+                if (new_seg) { tb = 0; qb++; }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            int cur_qb = -1, seg = 0;
-            long long n = 0;
-            for (long long t = t_begin; t < t_end; t++, n++) {
-                const int qb = (int)(t / part.ntb);
-                if (qb != cur_qb) {
+            int tb = tb0, seg = 0, s = 0;
+            uint32_t ring_phase = 0;
+            bool new_seg = true;
+            const uint32_t sa = smem_u32(sA);
+            uint64_t dA_hi[2], dA_lo[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                // row-half h of the query block: rows 128h.. of each A k-block
+                dA_hi[h] = make_smem_desc(sa + h * (128 * 128));
+                dA_lo[h] = make_smem_desc(sa + A_KBLOCK_BYTES + h * (128 * 128));
+            }
+            const uint64_t dB0 = make_smem_desc(smem_u32(sB));
+            for (int n = 0; n < n_tiles; n++) {
+                if (new_seg) {
                     mbar_wait(a_full, seg & 1);
-                    cur_qb = qb;
                     seg++;
                 }
-                const int s = (int)(n % STAGES), acc = (int)(n & 1);
+                const int acc = n & 1;
                 mbar_wait(acc_empty + acc, (uint32_t)(((n >> 1) & 1) ^ 1));
-                mbar_wait(b_full + s, (uint32_t)((n / STAGES) & 1));
+                mbar_wait(b_full + s, ring_phase);
                 tcgen05_fence_after();
-                const uint32_t sb = smem_u32(sB + (size_t)s * 2 * B_KBLOCK_BYTES);
-                const uint64_t dB_hi = make_smem_desc(sb), dB_lo = make_smem_desc(sb + B_KBLOCK_BYTES);
+                // descriptors address 16-byte units: stage stride and k-block stride are plain adds
+                const uint64_t dB_hi = dB0 + (uint64_t)(s * ((2 * B_KBLOCK_BYTES) >> 4));
+                const uint64_t dB_lo = dB_hi + (B_KBLOCK_BYTES >> 4);
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
-                    // row-half h of the query block: rows 128h.. of each A k-block
-                    const uint64_t dA_hi = make_smem_desc(smem_u32(sA + h * (128 * 128)));
-                    const uint64_t dA_lo = make_smem_desc(smem_u32(sA + A_KBLOCK_BYTES + h * (128 * 128)));
                     const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS + h * BN);
                     // hi.hi + hi.lo + lo.hi ; each 64-wide k-block is four K=16 steps, 32 B apart
 #pragma unroll
-                    for (int k = 0; k < 4; k++) umma_bf16(d_tmem, dA_hi + 2 * k, dB_hi + 2 * k, IDESC, k > 0);
+                    for (int k = 0; k < 4; k++) umma_bf16(d_tmem, dA_hi[h] + 2 * k, dB_hi + 2 * k, IDESC, k > 0);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) umma_bf16(d_tmem, dA_hi + 2 * k, dB_lo + 2 * k, IDESC, 1);
+                    for (int k = 0; k < 4; k++) umma_bf16(d_tmem, dA_hi[h] + 2 * k, dB_lo + 2 * k, IDESC, 1);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) umma_bf16(d_tmem, dA_lo + 2 * k, dB_hi + 2 * k, IDESC, 1);
+                    for (int k = 0; k < 4; k++) umma_bf16(d_tmem, dA_lo[h] + 2 * k, dB_hi + 2 * k, IDESC, 1);
                 }
                 tcgen05_commit(b_empty + s);     // B stage free once these MMAs have read it
                 tcgen05_commit(acc_full + acc);  // accumulator ready for the epilogue
-                const bool last_of_seg = (t + 1 == t_end) || ((int)((t + 1) / part.ntb) != qb);
-                if (last_of_seg) tcgen05_commit(a_empty);
+                if (++s == STAGES) { s = 0; ring_phase ^= 1; }
+                new_seg = (++tb == ntb);
+                if (new_seg) tb = 0;
+                if (new_seg || n + 1 == n_tiles) tcgen05_commit(a_empty);   // last tile of this query block in the span
             }
         }
         __syncwarp();
@@ -352,20 +365,26 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         const int half = slice >> 1;                  // which M=128 row-half those columns belong to
         const int csub = slice & 1;                   // which 64 train columns of the tile
         const int row = half * 128 + quarter * 32 + lane;   // row inside the 256-row query block
-        const int etid = threadIdx.x - 128;           // 0..511 among epilogue threads
+        float* wnb = sNB + (warp - 4) * 64;           // this warp's |b|^2 staging (warp-synchronous)
+        const float* nb_col = nb + csub * 64 + lane;
         Cand cand;
         cand_reset(cand);
-        long long n = 0;
-        for (long long t = t_begin; t < t_end; t++, n++) {
-            const int qb = (int)(t / part.ntb), tb = (int)(t % part.ntb);
-            const int acc = (int)(n & 1);
-            float* nbs = sNB + acc * BN;
-            if (etid < BN) nbs[etid] = __ldg(nb + (size_t)tb * BN + etid);
-            asm volatile("bar.sync 1, 512;" ::: "memory");   // the 16 epilogue warps only
+        int qb = qb0, tb = tb0;
+        float nb0 = __ldg(nb_col + (size_t)tb * BN), nb1 = __ldg(nb_col + (size_t)tb * BN + 32);
+        for (int n = 0; n < n_tiles; n++) {
+            const int acc = n & 1;
+            __syncwarp();                             // every lane is done reading the previous tile's values
+            wnb[lane] = nb0;
+            wnb[lane + 32] = nb1;
+            __syncwarp();
+            const int tb_next = (tb + 1 == ntb) ? 0 : tb + 1;
+            if (n + 1 < n_tiles) {                    // prefetch the next tile's norms behind this tile's math
+                nb0 = __ldg(nb_col + (size_t)tb_next * BN);
+                nb1 = __ldg(nb_col + (size_t)tb_next * BN + 32);
+            }
             mbar_wait(acc_full + acc, (uint32_t)((n >> 1) & 1));
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS + slice * 64);
-            const float* nbc = nbs + csub * 64;
             uint32_t buf[2][32];
             TMEM_LD_X32(buf[0], taddr);
             TMEM_LD_X32(buf[1], taddr + 32);
@@ -380,7 +399,7 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 float cm[8];
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
-                    const float4 nv = *reinterpret_cast<const float4*>(nbc + g * 32 + c * 4);
+                    const float4 nv = *reinterpret_cast<const float4*>(wnb + g * 32 + c * 4);
                     const float v0 = fmaf(-2.f, __uint_as_float(r[c * 4 + 0]), nv.x);
                     const float v1 = fmaf(-2.f, __uint_as_float(r[c * 4 + 1]), nv.y);
                     const float v2 = fmaf(-2.f, __uint_as_float(r[c * 4 + 2]), nv.z);
@@ -395,14 +414,15 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                         if (__any_sync(0xffffffffu, cm[c] < cand.v[3])) cand_insert_bf(cand, cm[c], id0 + c);
                 }
             }
-            const bool last_of_seg = (t + 1 == t_end) || ((int)((t + 1) / part.ntb) != qb);
-            if (last_of_seg) {
-                const int slot = ((int)blockIdx.x - part.cta_of((long long)qb * part.ntb)) * SUBSLOTS + csub;
+            if (tb_next == 0 || n + 1 == n_tiles) {   // last tile of this query block in the span: publish
+                const int slot = ((int)blockIdx.x - part.cta_of((long long)qb * ntb)) * SUBSLOTS + csub;
                 const size_t o = ((size_t)qb * BM + row) * slots + slot;
                 cand_v[o] = make_float4(cand.v[0], cand.v[1], cand.v[2], cand.v[3]);
                 cand_id[o] = make_int4(cand.id[0], cand.id[1], cand.id[2], cand.id[3]);
                 cand_reset(cand);
+                qb++;
             }
+            tb = tb_next;
         }
     }
 
