@@ -148,68 +148,110 @@ __global__ void knn2_merge_splits_kernel(const Top2* __restrict__ parts, int nq,
     out[i] = r;
 }
 
-// Ratio test (feature_matcher.cpp:47-56) + ordered compaction in ONE CTA: nq <= a few 100k, so a
-// chunked block scan (1024 queries per step) costs microseconds and keeps query order without a
-// second kernel.
-__global__ void __launch_bounds__(1024) knn2_finish_kernel(const Top2* __restrict__ top, int nq, float ratio, int32_t* __restrict__ query_idx,
-                                                          int32_t* __restrict__ train_idx, float* __restrict__ dist, int32_t* __restrict__ n_matches,
-                                                          int32_t* __restrict__ knn_idx, float* __restrict__ knn_dist)
+// Ratio test (feature_matcher.cpp:47-56) + ordered compaction of the survivors, two small kernels:
+//   knn2_flags_kernel    1024 queries per CTA: raw kNN output, keep flag, per-CTA survivor count;
+//   knn2_compact_kernel  each CTA sums the counts of the CTAs before it (<= a few hundred values),
+//                        scans its own flags and scatters -- survivors stay in ascending query order.
+constexpr int FIN_THREADS = 1024;
+
+__device__ inline int keep_flag(const Top2& r, float ratio)
+{
+    return (r.i0 != KNN_MISSING && r.i1 != KNN_MISSING && r.d0 < __fmul_rn(ratio, r.d1)) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(FIN_THREADS) knn2_flags_kernel(const Top2* __restrict__ top, int nq, float ratio, int32_t* __restrict__ knn_idx,
+                                                                float* __restrict__ knn_dist, int* __restrict__ block_counts)
+{
+    __shared__ int warp_cnt[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i = blockIdx.x * FIN_THREADS + tid;
+    int keep = 0;
+    if (i < nq) {
+        const Top2 r = top[i];
+        if (knn_idx) {
+            knn_idx[2 * i] = r.i0 != KNN_MISSING ? r.i0 : -1;
+            knn_idx[2 * i + 1] = r.i1 != KNN_MISSING ? r.i1 : -1;
+        }
+        if (knn_dist) {
+            knn_dist[2 * i] = r.d0;
+            knn_dist[2 * i + 1] = r.d1;
+        }
+        keep = keep_flag(r, ratio);
+    }
+    const unsigned ball = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_cnt[warp] = __popc(ball);
+    __syncthreads();
+    if (warp == 0) {
+        int v = warp_cnt[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) block_counts[blockIdx.x] = v;
+    }
+}
+
+__global__ void __launch_bounds__(FIN_THREADS) knn2_compact_kernel(const Top2* __restrict__ top, int nq, float ratio, const int* __restrict__ block_counts,
+                                                                  int32_t* __restrict__ query_idx, int32_t* __restrict__ train_idx,
+                                                                  float* __restrict__ dist, int32_t* __restrict__ n_matches)
 {
     __shared__ int warp_off[32];
-    __shared__ int s_base, s_total;
+    __shared__ int s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_base = 0;
-    __syncthreads();
-    for (int start = 0; start < nq; start += 1024) {
-        const int i = start + tid;
-        int keep = 0;
-        Top2 r = top2_empty();
-        if (i < nq) {
-            r = top[i];
-            const bool has0 = r.i0 != KNN_MISSING, has1 = r.i1 != KNN_MISSING;
-            if (knn_idx) {
-                knn_idx[2 * i] = has0 ? r.i0 : -1;
-                knn_idx[2 * i + 1] = has1 ? r.i1 : -1;
-            }
-            if (knn_dist) {
-                knn_dist[2 * i] = r.d0;
-                knn_dist[2 * i + 1] = r.d1;
-            }
-            keep = (has0 && has1 && r.d0 < __fmul_rn(ratio, r.d1)) ? 1 : 0;
-        }
-        const unsigned ball = __ballot_sync(0xffffffffu, keep);
-        const int prefix = __popc(ball & ((1u << lane) - 1));
-        if (lane == 0) warp_off[warp] = __popc(ball);
-        __syncthreads();
-        if (warp == 0) {
-            const int v = warp_off[lane];
-            int incl = v;
+    // exclusive prefix of the CTAs before this one
+    int part = 0;
+    for (int b = tid; b < (int)blockIdx.x; b += FIN_THREADS) part += block_counts[b];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int n = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += n;
-            }
-            warp_off[lane] = incl - v;  // exclusive offset of each warp inside this chunk
-            if (lane == 31) s_total = incl;
-        }
-        __syncthreads();
-        if (keep) {
-            const int pos = s_base + warp_off[warp] + prefix;
-            query_idx[pos] = i;
-            train_idx[pos] = r.i0;
-            dist[pos] = r.d0;
-        }
-        __syncthreads();
-        if (tid == 0) s_base += s_total;
-        __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) warp_off[warp] = part;
+    __syncthreads();
+    if (warp == 0) {
+        int v = warp_off[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_base = v;
     }
-    if (tid == 0) *n_matches = s_base;
+    __syncthreads();
+    const int base = s_base;
+    const int i = blockIdx.x * FIN_THREADS + tid;
+    Top2 r = top2_empty();
+    int keep = 0;
+    if (i < nq) {
+        r = top[i];
+        keep = keep_flag(r, ratio);
+    }
+    const unsigned ball = __ballot_sync(0xffffffffu, keep);
+    const int prefix = __popc(ball & ((1u << lane) - 1));
+    __syncthreads();
+    if (lane == 0) warp_off[warp] = __popc(ball);
+    __syncthreads();
+    if (warp == 0) {
+        const int v = warp_off[lane];
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        warp_off[lane] = incl - v;
+        if (lane == 31 && blockIdx.x == gridDim.x - 1) *n_matches = base + incl;
+    }
+    __syncthreads();
+    if (keep) {
+        const int pos = base + warp_off[warp] + prefix;
+        query_idx[pos] = i;
+        train_idx[pos] = r.i0;
+        dist[pos] = r.d0;
+    }
 }
 
 int launch_knn_finish(sba_ctx* c, const Top2* d_top2, int nq, float ratio, int32_t* d_query_idx, int32_t* d_train_idx, float* d_dist,
                       int32_t* d_n_matches, int32_t* d_knn_idx, float* d_knn_dist)
 {
-    knn2_finish_kernel<<<1, 1024, 0, c->stream>>>(d_top2, nq, ratio, d_query_idx, d_train_idx, d_dist, d_n_matches, d_knn_idx, d_knn_dist);
+    const int nblocks = (nq + FIN_THREADS - 1) / FIN_THREADS;
+    SBA_TRY(c->scratch[SCR_WORK4].ensure((size_t)nblocks * sizeof(int), c->stream));
+    int* d_counts = c->scratch[SCR_WORK4].as<int>();
+    knn2_flags_kernel<<<nblocks, FIN_THREADS, 0, c->stream>>>(d_top2, nq, ratio, d_knn_idx, d_knn_dist, d_counts);
+    SBA_LAUNCHED(c);
+    knn2_compact_kernel<<<nblocks, FIN_THREADS, 0, c->stream>>>(d_top2, nq, ratio, d_counts, d_query_idx, d_train_idx, d_dist, d_n_matches);
     SBA_LAUNCHED(c);
     SBA_CUDA(cudaGetLastError());
     return SBA_OK;

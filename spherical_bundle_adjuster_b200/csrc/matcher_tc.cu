@@ -435,42 +435,106 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 }
 
 // ---- 3. exact re-rank ---------------------------------------------------------------------------------------
-// 16 threads per query row: thread e evaluates train row 4*chunk[e/4] + e%4 exactly.
-// (BM here is the 256-row query block of tc_knn.)
-__global__ void __launch_bounds__(256)
+// 16 threads per query row (8 rows per 128-thread CTA).
+//   a) the row's candidate lists (one per span slot) are merged by rank counting: thread e holds up to
+//      RR_PER_THREAD entries, every entry's rank = number of entries that sort before it (value, then
+//      position), obtained with width-16 shuffles -- no divergent branches.  Ranks 0..3 are the merged
+//      best chunks, the value of rank 3 is the bound B.
+//   b) thread e evaluates train row 4*chunk[e/4] + e%4 EXACTLY: its 256-byte row and the query row are
+//      fetched with 128-bit loads into registers and combined in OpenCV's order (l2sqr_opencv).
+//   c) top-2 by (distance, index) over the 16 threads, then the safety test against B.
+constexpr int RR_THREADS = 128;
+constexpr int RR_ROWS = RR_THREADS / 16;
+constexpr int RR_PER_THREAD = 4;   // up to 16*4 = 64 candidate entries (16 slots) merged by shuffles; more -> serial path
+
+__global__ void __launch_bounds__(RR_THREADS)
 tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, int nt, const float* __restrict__ na,
                  const float* __restrict__ nb_max, Partition part, const float4* __restrict__ cand_v, const int4* __restrict__ cand_id,
                  int slots, Top2* __restrict__ top, int* __restrict__ fb_list, int* __restrict__ fb_count, float* __restrict__ dbg_max_err)
 {
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int row = gid >> 4, e = gid & 15;
+    __shared__ __align__(16) float qs[RR_ROWS][DIM];
+    __shared__ float win_v[RR_ROWS][NCAND];
+    __shared__ int win_id[RR_ROWS][NCAND];
+    const int tid = threadIdx.x, grp = tid >> 4, e = tid & 15;
+    const int row = blockIdx.x * RR_ROWS + grp;
     const bool active = row < nq;
     const int r = active ? row : nq - 1;
-    // every thread of the group merges the slots itself (<= a few entries, identical result)
+    const float INF = __int_as_float(0x7f800000);
+
+    // query rows of this CTA -> shared (coalesced 128-bit loads: 8 rows x 16 float4)
+    reinterpret_cast<float4*>(&qs[grp][0])[e] = __ldg(reinterpret_cast<const float4*>(q + (size_t)r * DIM) + e);
+    if (e < NCAND) { win_v[grp][e] = INF; win_id[grp][e] = -1; }
+    __syncthreads();
+
+    // a) merge candidate lists
     const int qb = r / BM;
     const int c_first = part.cta_of((long long)qb * part.ntb), c_last = part.cta_of((long long)(qb + 1) * part.ntb - 1);
-    Cand c;
-    cand_reset(c);
-    for (int s = 0; s < (c_last - c_first + 1) * SUBSLOTS; s++) {
-        const float4 v = cand_v[(size_t)r * slots + s];
-        const int4 id = cand_id[(size_t)r * slots + s];
-        cand_insert(c, v.x, id.x); cand_insert(c, v.y, id.y); cand_insert(c, v.z, id.z); cand_insert(c, v.w, id.w);
+    const int n_ent = (c_last - c_first + 1) * SUBSLOTS * NCAND;   // entries are (slot, k) pairs, contiguous in memory
+    const float* ev = reinterpret_cast<const float*>(cand_v + (size_t)r * slots);
+    const int* ei = reinterpret_cast<const int*>(cand_id + (size_t)r * slots);
+    if (n_ent <= 16 * RR_PER_THREAD) {
+        float v[RR_PER_THREAD];
+        int id[RR_PER_THREAD], rank[RR_PER_THREAD];
+#pragma unroll
+        for (int k = 0; k < RR_PER_THREAD; k++) {
+            const int pos = e + 16 * k;
+            v[k] = pos < n_ent ? ev[pos] : INF;
+            id[k] = pos < n_ent ? ei[pos] : -1;
+            rank[k] = 0;
+        }
+#pragma unroll
+        for (int k2 = 0; k2 < RR_PER_THREAD; k2++) {
+            if (16 * k2 < n_ent) {   // uniform across the group
+#pragma unroll 4
+                for (int l = 0; l < 16; l++) {
+                    const float ov = __shfl_sync(0xffffffffu, v[k2], l, 16);
+                    const int opos = l + 16 * k2;
+#pragma unroll
+                    for (int k = 0; k < RR_PER_THREAD; k++) rank[k] += (ov < v[k] || (ov == v[k] && opos < e + 16 * k)) ? 1 : 0;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < RR_PER_THREAD; k++)
+            if (rank[k] < NCAND && id[k] >= 0) { win_v[grp][rank[k]] = v[k]; win_id[grp][rank[k]] = id[k]; }
+    } else if (e == 0) {
+        Cand c;
+        cand_reset(c);
+        for (int pos = 0; pos < n_ent; pos++) cand_insert(c, ev[pos], ei[pos]);
+#pragma unroll
+        for (int k = 0; k < NCAND; k++) { win_v[grp][k] = c.v[k]; win_id[grp][k] = c.id[k]; }
     }
-    const float B = c.v[3];
-    const int chunk = c.id[e >> 2];
+    __syncwarp();
+    const float B = win_v[grp][NCAND - 1];
+    const int chunk = win_id[grp][e >> 2];
+    const float chunk_v = win_v[grp][e >> 2];
+
+    // b) exact distance of this thread's train row
     const int j = chunk * CHUNK + (e & 3);
+    const bool valid = chunk >= 0 && j < nt;
     Top2 best = top2_empty();
-    float approx_gap = 0.f;
-    if (chunk >= 0 && j < nt) {
-        const float dsq = l2sqr_opencv<DIM>(q + (size_t)r * DIM, t + (size_t)j * DIM);
+    float exact_v = INF;
+    if (valid) {
+        float tv[DIM], qv[DIM];
+        const float4* tp = reinterpret_cast<const float4*>(t + (size_t)j * DIM);
+        const float4* qp = reinterpret_cast<const float4*>(&qs[grp][0]);
+#pragma unroll
+        for (int k = 0; k < DIM / 4; k++) {
+            const float4 a = __ldg(tp + k);
+            tv[4 * k] = a.x; tv[4 * k + 1] = a.y; tv[4 * k + 2] = a.z; tv[4 * k + 3] = a.w;
+            const float4 b = qp[k];
+            qv[4 * k] = b.x; qv[4 * k + 1] = b.y; qv[4 * k + 2] = b.z; qv[4 * k + 3] = b.w;
+        }
+        const float dsq = l2sqr_opencv<DIM>(qv, tv);
         best.d0 = __fsqrt_rn(dsq);
         best.i0 = j;
-        approx_gap = dsq - na[r];   // exact value on the scale of the approximate ones
+        exact_v = dsq - na[r];   // exact value on the scale of the approximate ones
     }
     // diagnostics: |chunk minimum (approx) - min over its 4 rows (exact)|, relative to the bound scale
-    float gmin = (chunk >= 0 && j < nt) ? approx_gap : __int_as_float(0x7f800000);
+    float gmin = exact_v;
     gmin = fminf(gmin, __shfl_xor_sync(0xffffffffu, gmin, 1));
     gmin = fminf(gmin, __shfl_xor_sync(0xffffffffu, gmin, 2));
+    // c) top-2 over the 16 threads of the row
 #pragma unroll
     for (int o = 1; o < 16; o <<= 1) {
         Top2 other;
@@ -481,8 +545,8 @@ tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ 
         best = top2_merge(best, other);
     }
     const float scale = na[r] + *nb_max;
-    if (active && dbg_max_err && (e & 3) == 0 && chunk >= 0 && isfinite(gmin) && scale > 0.f) {
-        const float err = fabsf(gmin - c.v[e >> 2]) / scale;
+    if (active && dbg_max_err && (e & 3) == 0 && chunk >= 0 && gmin < INF && scale > 0.f) {
+        const float err = fabsf(gmin - chunk_v) / scale;
         atomicMax((int*)dbg_max_err, __float_as_int(err));   // non-negative floats order like ints
     }
     if (active && e == 0) {
@@ -490,7 +554,7 @@ tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ 
         //   d1^2 (rounded up) < B + |a|^2 - delta
         const float delta = DELTA_COEF * scale;
         const float d1sq_up = best.d1 * best.d1 * (1.f + 5e-7f);
-        const bool safe = !(B < __int_as_float(0x7f800000)) || (best.i1 != KNN_MISSING && d1sq_up < B + na[r] - delta);
+        const bool safe = !(B < INF) || (best.i1 != KNN_MISSING && d1sq_up < B + na[r] - delta);
         if (safe) top[row] = best;
         else {
             const int k = atomicAdd(fb_count, 1);
@@ -629,7 +693,7 @@ int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, 
     SBA_LAUNCHED(c);
     SBA_CUDA(cudaGetLastError());
 
-    tc_rerank_kernel<<<(nq * 16 + 255) / 256, 256, 0, st>>>(d_q, nq, d_t, nt, d_na, d_nbmax, part, d_cv, d_ci, slots, d_top, d_fl, d_fb_count, d_dbg);
+    tc_rerank_kernel<<<(nq + RR_ROWS - 1) / RR_ROWS, RR_THREADS, 0, st>>>(d_q, nq, d_t, nt, d_na, d_nbmax, part, d_cv, d_ci, slots, d_top, d_fl, d_fb_count, d_dbg);
     SBA_LAUNCHED(c);
     tc_fallback_kernel<<<std::min(nq, 4 * c->sm_count), 128, 0, st>>>(d_q, d_t, nt, d_fl, d_fb_count, d_top);
     SBA_LAUNCHED(c);
