@@ -196,6 +196,37 @@ int sba_ba_rot_solve(sba_ba_problem* p, double* r_inout, const double t[3], doub
 int sba_ba_rot_eval_timed(sba_ba_problem* p, const double* r, const double t[3], double d1, double d2, double huber_delta,
                           int materialise, int iters, float* mean_ms);
 
+/* ---------------------------------------------------------------------------------------------
+ * The whole hot path for one ERP pair in one call
+ * (equi2cube_surf::do_all, equi2cube_surf.cpp:78-122, minus SURF; then the bearing conversion and the
+ *  rotation-only solve of spherical_bundle_adjuster::do_bundle_adjustment, :268-298 and :202-203).
+ *
+ *   erp_left/right   h x w x 3 images, or both NULL to skip the remap stage.
+ *   strip_*_out      optional cube strips (cube_size x 6*cube_size x 3); NULL keeps them on the device.
+ *   desc_*, key_*    SURF descriptors [n x dim] and keypoints [n x 2] in cube-strip coordinates
+ *                    (what detect/compute on the strips return; SURF itself stays with the caller).
+ *   query/train_idx_out, dist_out  optional match list (capacity n_left).
+ *   r0, t, d1, d2, huber_delta, max_iter  as in sba_ba_rot_solve.
+ * All data pointers live where `mem` says; `result` is a host struct.  With SBA_MEM_HOST the call
+ * copies inputs in, runs on the device and copies the requested outputs back before returning.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct sba_pair_result {
+    double rotation[3];
+    int n_matches;
+    int lm_iterations;
+    int lm_termination;
+    int reserved;
+    double initial_cost;
+    double final_cost;
+} sba_pair_result;
+
+int sba_pair_rotation(sba_ctx* ctx, const uint8_t* erp_left, const uint8_t* erp_right, int w, int h, int cube_size,
+                      uint8_t* strip_left_out, uint8_t* strip_right_out, const float* desc_left, int n_left,
+                      const float* desc_right, int n_right, int dim, const float* key_left_xy, const float* key_right_xy,
+                      float ratio, const double r0[3], const double t[3], double d1, double d2, double huber_delta,
+                      int max_iter, int32_t* query_idx_out, int32_t* train_idx_out, float* dist_out,
+                      sba_pair_result* result, int mem);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,7 +20,7 @@ EXPORTED = [
     "sba_ctx_synchronize", "sba_ctx_launch_count", "sba_ctx_set_profiling", "sba_ctx_kernel_ms", "sba_equi2cube", "sba_equi2cube_face", "sba_equi2cube_lut",
     "sba_cube2equi_points", "sba_pixels_to_bearings", "sba_knn2_ratio", "sba_match_last_stats", "sba_gather_matches",
     "sba_ba_problem_create", "sba_ba_problem_destroy", "sba_ba_problem_set_allreduce", "sba_ba_rot_eval",
-    "sba_ba_rot_solve", "sba_ba_rot_eval_timed",
+    "sba_ba_rot_solve", "sba_ba_rot_eval_timed", "sba_pair_rotation",
 ]
 
 
@@ -36,6 +36,11 @@ class MatchStats(C.Structure):
 class SolveSummary(C.Structure):
     _fields_ = [("iterations", C.c_int), ("num_successful", C.c_int), ("termination", C.c_int), ("evaluations", C.c_int),
                 ("initial_cost", C.c_double), ("final_cost", C.c_double), ("final_radius", C.c_double)]
+
+
+class PairResult(C.Structure):
+    _fields_ = [("rotation", C.c_double * 3), ("n_matches", C.c_int), ("lm_iterations", C.c_int), ("lm_termination", C.c_int),
+                ("reserved", C.c_int), ("initial_cost", C.c_double), ("final_cost", C.c_double)]
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_void_p)
@@ -79,6 +84,8 @@ def load():
     lib.sba_ba_rot_eval.argtypes = [vp, vp, vp, f64, f64, f64, vp, vp, vp, vp, vp, i32]
     lib.sba_ba_rot_solve.argtypes = [vp, vp, vp, f64, f64, f64, i32, C.POINTER(SolveSummary)]
     lib.sba_ba_rot_eval_timed.argtypes = [vp, vp, vp, f64, f64, f64, i32, i32, C.POINTER(f32)]
+    lib.sba_pair_rotation.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, vp, i32, i32, vp, vp, f32, vp, vp, f64, f64, f64, i32,
+                                      vp, vp, vp, C.POINTER(PairResult), i32]
     _lib = lib
     return lib
 

@@ -210,6 +210,40 @@ class Context:
                                            SBA_MEM_DEVICE))
         return ol, orr
 
+    # -- the whole hot path for one pair (equi2cube_surf::do_all + rotation-only BA) in one C call
+    def pair_rotation(self, im_left, im_right, desc_left, desc_right, key_left_xy, key_right_xy, cube_size: int, w: int = 0, h: int = 0,
+                      ratio: float = 0.3, r0=(0.0, 0.0, 0.0), t=(0.0, 0.0, 0.0), d1=1.0, d2=1.0, huber=1.0, max_iter=50,
+                      want_matches: bool = True, want_strips: bool = False):
+        """Returns (PairResult, matches (query_idx, train_idx, dist) or None, strips or None)."""
+        u8t = torch.uint8 if torch else None
+        f32t = torch.float32 if torch else None
+        i32t = torch.int32 if torch else None
+        dl, dr = _as(desc_left, np.float32, f32t), _as(desc_right, np.float32, f32t)
+        kl, kr = _as(key_left_xy, np.float32, f32t), _as(key_right_xy, np.float32, f32t)
+        iml = imr = None
+        if im_left is not None:
+            iml, imr = _as(im_left, np.uint8, u8t), _as(im_right, np.uint8, u8t)
+            h, w = iml.shape[0], iml.shape[1]
+        mem = _mem_of(iml, imr, dl, dr, kl, kr)
+        nl, nr = dl.shape[0], dr.shape[0]
+        dim = dl.shape[1]
+        qi = _empty_like_kind(dl, (max(nl, 1),), np.int32, i32t) if want_matches else None
+        ti = _empty_like_kind(dl, (max(nl, 1),), np.int32, i32t) if want_matches else None
+        dd = _empty_like_kind(dl, (max(nl, 1),), np.float32, f32t) if want_matches else None
+        sl = sr = None
+        if want_strips and iml is not None:
+            sl = _empty_like_kind(dl, (cube_size, 6 * cube_size, 3), np.uint8, u8t)
+            sr = _empty_like_kind(dl, (cube_size, 6 * cube_size, 3), np.uint8, u8t)
+        r0 = np.ascontiguousarray(r0, np.float64)
+        t = np.ascontiguousarray(t, np.float64)
+        res = _lib.PairResult()
+        check(self._lib.sba_pair_rotation(self._h, _ptr(iml), _ptr(imr), w, h, cube_size, _ptr(sl), _ptr(sr), _ptr(dl), nl, _ptr(dr), nr, dim,
+                                          _ptr(kl), _ptr(kr), ratio, _ptr(r0), _ptr(t), d1, d2, huber, max_iter, _ptr(qi), _ptr(ti), _ptr(dd),
+                                          C.byref(res), mem))
+        n = res.n_matches
+        matches = (qi[:n], ti[:n], dd[:n]) if want_matches else None
+        return res, matches, ((sl, sr) if sl is not None else None)
+
     # -- bundle adjustment
     def ba_problem(self, b1, b2, cam=None, n_cam: int = 1) -> "BAProblem":
         return BAProblem(self, b1, b2, cam, n_cam)

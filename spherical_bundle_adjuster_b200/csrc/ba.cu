@@ -321,9 +321,35 @@ __global__ void __launch_bounds__(EVAL_THREADS) ba_decide_kernel(LMArrays A)
 
 // ---- the evaluation kernel (K5) ------------------------------------------------------------------
 // Fold work-item partials into per-camera blocks, in item order.  `item_ptr` [n_cam+1].
-__device__ void fold_items(const double* __restrict__ partial, const int* __restrict__ item_ptr, int n_cam, double* __restrict__ blk)
+__device__ void fold_items(const double* __restrict__ partial, const int* __restrict__ item_ptr, int n_items, int n_cam,
+                           double* __restrict__ blk)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (item_ptr == nullptr) {
+        // single camera whose items are 0..n_items-1 (uniform layout): all 8 warps cooperate;
+        // thread-strided ordered sums, then a fixed tree over the CTA
+        __shared__ double red[EVAL_THREADS];
+        double acc[10];
+#pragma unroll
+        for (int k = 0; k < 10; k++) acc[k] = 0;
+        for (int it = threadIdx.x; it < n_items; it += EVAL_THREADS)
+#pragma unroll
+            for (int k = 0; k < 10; k++) acc[k] += partial[(size_t)it * 10 + k];
+#pragma unroll
+        for (int k = 0; k < 10; k++) {
+            double v = warp_sum(acc[k]);
+            __syncthreads();
+            if (lane == 0) red[warp] = v;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double t = 0;
+                for (int w = 0; w < EVAL_WARPS; w++) t += red[w];
+                blk[k] = t;
+            }
+        }
+        __syncthreads();
+        return;
+    }
     const int n_items_total = item_ptr[n_cam];
     if (n_items_total <= 8 * n_cam) {
         // few items per camera: one thread per camera, sequential ordered sum
@@ -359,8 +385,10 @@ struct EvalArgs {
     const float4* b1;
     const float4* b2;
     const int32_t* perm;  // sorted position -> caller's observation index (NULL = identity)
-    const Item* items;
-    const int* item_ptr;
+    const Item* items;     // NULL = uniform layout: one camera, item i covers [i*item_len, min(n_obs, (i+1)*item_len))
+    const int* item_ptr;   // NULL with the uniform layout
+    int item_len;
+    int n_obs;
     int n_items;
     int n_cam;
     const CamParams* params;
@@ -387,7 +415,13 @@ __global__ void __launch_bounds__(EVAL_THREADS, 2) ba_rot_eval_kernel(EvalArgs E
     const float d1f = (float)d1;
 
     for (int it = warp_global; it < E.n_items; it += warp_stride) {
-        const Item item = E.items[it];
+        Item item;
+        if (E.items) item = E.items[it];
+        else {
+            item.start = (int64_t)it * E.item_len;
+            item.count = min(E.item_len, E.n_obs - it * E.item_len);
+            item.cam = 0;
+        }
         const CamParams* P = E.params + item.cam;
         double R[9];
 #pragma unroll
@@ -479,7 +513,7 @@ __global__ void __launch_bounds__(EVAL_THREADS, 2) ba_rot_eval_kernel(EvalArgs E
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    fold_items(E.partial, E.item_ptr, E.n_cam, E.blk_out);
+    fold_items(E.partial, E.item_ptr, E.n_items, E.n_cam, E.blk_out);
     if (threadIdx.x == 0) *E.ticket = 0;
     if (FUSE) {
         __syncthreads();
@@ -546,16 +580,20 @@ struct sba_ba_problem {
     sba_allreduce_fn allreduce = nullptr;
     void* allreduce_user = nullptr;
     int eval_blocks = 1;
+    int item_len = 32;
+    bool borrowed = false;   // b1/b2 belong to the caller (fused pipeline): not returned to the cache
 };
 
 static void free_problem(sba_ba_problem* p)
 {
     if (!p) return;
-    cudaFree(p->b1); cudaFree(p->b2); cudaFree(p->perm); cudaFree(p->items); cudaFree(p->item_ptr);
-    cudaFree(p->partial); cudaFree(p->params); cudaFree(p->x); cudaFree(p->xc); cudaFree(p->blk_cur);
-    cudaFree(p->blk_cand); cudaFree(p->scale); cudaFree(p->state); cudaFree(p->ticket);
-    if (p->h_state) cudaFreeHost(p->h_state);
-    if (p->h_x) cudaFreeHost(p->h_x);
+    sba::BlockCache& C = p->ctx->cache;
+    if (p->borrowed) p->b1 = p->b2 = nullptr;
+    void* dev[] = {p->b1, p->b2, p->perm, p->items, p->item_ptr, p->partial, p->params, p->x, p->xc, p->blk_cur, p->blk_cand, p->scale,
+                   p->state, p->ticket};
+    for (void* d : dev) C.put(d, false);
+    C.put(p->h_state, true);
+    C.put(p->h_x, true);
     delete p;
 }
 
@@ -581,6 +619,7 @@ static EvalArgs make_eval_args(sba_ba_problem* p, const double t[3], double d1, 
 {
     EvalArgs E;
     E.b1 = p->b1; E.b2 = p->b2; E.perm = p->perm; E.items = p->items; E.item_ptr = p->item_ptr;
+    E.item_len = p->item_len; E.n_obs = (int)p->n_obs;
     E.n_items = p->n_items; E.n_cam = p->n_cam; E.params = p->params; E.partial = p->partial;
     E.blk_out = blk_out; E.ticket = p->ticket; E.res = res; E.jac = jac;
     E.k.t[0] = t[0]; E.k.t[1] = t[1]; E.k.t[2] = t[2];
@@ -616,8 +655,27 @@ static int launch_eval(sba_ba_problem* p, const EvalArgs& E, const LMArrays& A)
 
 extern "C" {
 
+}  // extern "C"
+
+namespace sba {
+int ba_problem_create_impl(sba_ctx* c, const float* b1, const float* b2, const int32_t* cam, int64_t n_obs, int n_cam, int mem, bool borrow,
+                           sba_ba_problem** out);
+}
+
+extern "C" {
+
 int sba_ba_problem_create(sba_ctx* c, const float* b1, const float* b2, const int32_t* cam, int64_t n_obs, int n_cam, int mem,
                           sba_ba_problem** out)
+{
+    return sba::ba_problem_create_impl(c, b1, b2, cam, n_obs, n_cam, mem, false, out);
+}
+
+}  // extern "C"
+
+// `borrow` (device pointers, no camera sort): the problem reads the caller's b1/b2 in place; they must
+// stay valid and unchanged until the problem is destroyed.
+int sba::ba_problem_create_impl(sba_ctx* c, const float* b1, const float* b2, const int32_t* cam, int64_t n_obs, int n_cam, int mem,
+                                bool borrow, sba_ba_problem** out)
 {
     SBA_CHECK_ARG(c && out && n_obs >= 0 && n_cam >= 1 && n_obs < ((int64_t)1 << 31));
     SBA_CHECK_ARG(n_obs == 0 || (b1 && b2));
@@ -638,13 +696,19 @@ int sba_ba_problem_create(sba_ctx* c, const float* b1, const float* b2, const in
     } while (0)
 
     size_t nb = (size_t)(n_obs ? n_obs : 1) * sizeof(float4);
-    P_CUDA(cudaMalloc(&p->b1, nb));
-    P_CUDA(cudaMalloc(&p->b2, nb));
+    const bool need_sort = (cam != nullptr && n_cam > 1 && n_obs > 0);
+    p->borrowed = borrow && !need_sort && mem == SBA_MEM_DEVICE && n_obs > 0;
+    if (p->borrowed) {
+        p->b1 = (float4*)b1;
+        p->b2 = (float4*)b2;
+    } else {
+        P_CUDA(c->cache.get((void**)&p->b1, nb, false));
+        P_CUDA(c->cache.get((void**)&p->b2, nb, false));
+    }
     cudaMemcpyKind kind = mem == SBA_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
     std::vector<int> counts(n_cam, 0);
-    const bool need_sort = (cam != nullptr && n_cam > 1 && n_obs > 0);
     if (!need_sort) {
-        if (n_obs) {
+        if (n_obs && !p->borrowed) {
             P_CUDA(cudaMemcpyAsync(p->b1, b1, nb, kind, st));
             P_CUDA(cudaMemcpyAsync(p->b2, b2, nb, kind, st));
         }
@@ -663,7 +727,7 @@ int sba_ba_problem_create(sba_ctx* c, const float* b1, const float* b2, const in
         int32_t* d_idx = c->scratch[SCR_WORK0].as<int32_t>();
         int32_t* d_keys_sorted = c->scratch[SCR_WORK1].as<int32_t>();
         int* d_counts = c->scratch[SCR_WORK3].as<int>();
-        P_CUDA(cudaMalloc(&p->perm, (size_t)n_obs * 4));
+        P_CUDA(c->cache.get((void**)&p->perm, (size_t)n_obs * 4, false));
         int gb = (int)std::min<int64_t>(ceil_div64(n_obs, 256), (int64_t)c->sm_count * 8);
         iota_kernel<<<gb, 256, 0, st>>>(d_idx, n_obs);
         SBA_LAUNCHED(c);
@@ -689,12 +753,14 @@ int sba_ba_problem_create(sba_ctx* c, const float* b1, const float* b2, const in
         for (int k = 0; k < n_cam; k++) counts[k] = hc[k];
     }
 
-    // work items (host, O(n_cam + n_items))
+    // work items: arithmetic (uniform) for a single camera, a host-built table otherwise
     const int len = pick_item_len(n_obs, c->sm_count);
+    p->item_len = len;
+    const bool uniform = (n_cam == 1);
     std::vector<Item> items;
     std::vector<int> item_ptr(n_cam + 1, 0);
     int64_t off = 0;
-    for (int k = 0; k < n_cam; k++) {
+    for (int k = 0; k < n_cam && !uniform; k++) {
         item_ptr[k] = (int)items.size();
         for (int64_t s = 0; s < counts[k]; s += len) {
             Item it;
@@ -706,25 +772,31 @@ int sba_ba_problem_create(sba_ctx* c, const float* b1, const float* b2, const in
         off += counts[k];
     }
     item_ptr[n_cam] = (int)items.size();
-    p->n_items = (int)items.size();
-    size_t ni = items.size() ? items.size() : 1;
-    P_CUDA(cudaMalloc(&p->items, ni * sizeof(Item)));
-    P_CUDA(cudaMalloc(&p->item_ptr, (size_t)(n_cam + 1) * sizeof(int)));
-    P_CUDA(cudaMalloc(&p->partial, ni * 10 * sizeof(double)));
-    P_CUDA(cudaMalloc(&p->params, (size_t)n_cam * sizeof(CamParams)));
-    P_CUDA(cudaMalloc(&p->x, (size_t)n_cam * 3 * sizeof(double)));
-    P_CUDA(cudaMalloc(&p->xc, (size_t)n_cam * 3 * sizeof(double)));
-    P_CUDA(cudaMalloc(&p->blk_cur, (size_t)n_cam * 10 * sizeof(double)));
-    P_CUDA(cudaMalloc(&p->blk_cand, (size_t)n_cam * 10 * sizeof(double)));
-    P_CUDA(cudaMalloc(&p->scale, (size_t)n_cam * 3 * sizeof(double)));
-    P_CUDA(cudaMalloc(&p->state, sizeof(LMState)));
-    P_CUDA(cudaMalloc(&p->ticket, sizeof(unsigned int)));
-    P_CUDA(cudaMallocHost((void**)&p->h_state, sizeof(LMState)));
-    P_CUDA(cudaMallocHost((void**)&p->h_x, (size_t)n_cam * 3 * sizeof(double)));
+    p->n_items = uniform ? (int)((n_obs + len - 1) / len) : (int)items.size();
+    size_t ni = p->n_items ? p->n_items : 1;
+    if (!uniform) {
+        P_CUDA(c->cache.get((void**)&p->items, ni * sizeof(Item), false));
+        P_CUDA(c->cache.get((void**)&p->item_ptr, (size_t)(n_cam + 1) * sizeof(int), false));
+    }
+    P_CUDA(c->cache.get((void**)&p->partial, ni * 10 * sizeof(double), false));
+    P_CUDA(c->cache.get((void**)&p->params, (size_t)n_cam * sizeof(CamParams), false));
+    P_CUDA(c->cache.get((void**)&p->x, (size_t)n_cam * 3 * sizeof(double), false));
+    P_CUDA(c->cache.get((void**)&p->xc, (size_t)n_cam * 3 * sizeof(double), false));
+    P_CUDA(c->cache.get((void**)&p->blk_cur, (size_t)n_cam * 10 * sizeof(double), false));
+    P_CUDA(c->cache.get((void**)&p->blk_cand, (size_t)n_cam * 10 * sizeof(double), false));
+    P_CUDA(c->cache.get((void**)&p->scale, (size_t)n_cam * 3 * sizeof(double), false));
+    P_CUDA(c->cache.get((void**)&p->state, sizeof(LMState), false));
+    P_CUDA(c->cache.get((void**)&p->ticket, sizeof(unsigned int), false));
+    P_CUDA(c->cache.get((void**)&p->h_state, sizeof(LMState), true));
+    P_CUDA(c->cache.get((void**)&p->h_x, (size_t)n_cam * 3 * sizeof(double), true));
     P_CUDA(cudaMemsetAsync(p->ticket, 0, sizeof(unsigned int), st));
-    if (!items.empty()) P_CUDA(cudaMemcpyAsync(p->items, items.data(), items.size() * sizeof(Item), cudaMemcpyHostToDevice, st));
-    P_CUDA(cudaMemcpyAsync(p->item_ptr, item_ptr.data(), (size_t)(n_cam + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
-    P_CUDA(cudaStreamSynchronize(st));  // host vectors and staged inputs are released after this
+    if (!uniform) {
+        if (!items.empty()) P_CUDA(cudaMemcpyAsync(p->items, items.data(), items.size() * sizeof(Item), cudaMemcpyHostToDevice, st));
+        P_CUDA(cudaMemcpyAsync(p->item_ptr, item_ptr.data(), (size_t)(n_cam + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    }
+    // host vectors / the caller's host buffers are released after this; nothing to wait for when
+    // everything already lives on the device
+    if (!uniform || mem == SBA_MEM_HOST) P_CUDA(cudaStreamSynchronize(st));
 
     // grid: enough CTAs for every work item's warp, capped at 2 resident CTAs per SM x 4 waves
     int want = (p->n_items + EVAL_WARPS - 1) / EVAL_WARPS;
@@ -735,11 +807,13 @@ int sba_ba_problem_create(sba_ctx* c, const float* b1, const float* b2, const in
 #undef P_CUDA
 }
 
+extern "C" {
+
 int sba_ba_problem_destroy(sba_ba_problem* p)
 {
     if (!p) return SBA_OK;
-    cudaSetDevice(p->ctx->device);
-    cudaStreamSynchronize(p->ctx->stream);
+    // Blocks go back to the context's cache and are only ever reused by work enqueued later on the
+    // same stream, so no synchronisation is needed here.
     free_problem(p);
     return SBA_OK;
 }
@@ -799,7 +873,7 @@ int sba_ba_rot_solve(sba_ba_problem* p, double* r_inout, const double t[3], doub
     SBA_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     const int n_cam = p->n_cam;
-    SBA_CUDA(cudaStreamSynchronize(st));
+    // h_x / h_state are pinned mailboxes of this problem; every earlier use ended with a synchronise
     SBA_TRY(upload_rotations(p, r_inout, p->x));
     SBA_CUDA(cudaMemcpyAsync(p->xc, p->x, (size_t)n_cam * 3 * sizeof(double), cudaMemcpyDeviceToDevice, st));
     LMState init{};
@@ -834,11 +908,16 @@ int sba_ba_rot_solve(sba_ba_problem* p, double* r_inout, const double t[3], doub
         }
         launched += n;
         SBA_CUDA(cudaMemcpyAsync(p->h_state, p->state, sizeof(LMState), cudaMemcpyDeviceToHost, st));
+        // small problems: fetch the parameters with the state (one round trip per chunk)
+        const bool x_with_state = n_cam <= 64;
+        if (x_with_state) SBA_CUDA(cudaMemcpyAsync(p->h_x, p->x, (size_t)n_cam * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
         SBA_CUDA(cudaStreamSynchronize(st));
-        done = p->h_state->done != 0;
+        done = p->h_state->done != 0 || launched >= max_evals;
+        if (done && !x_with_state) {
+            SBA_CUDA(cudaMemcpyAsync(p->h_x, p->x, (size_t)n_cam * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+            SBA_CUDA(cudaStreamSynchronize(st));
+        }
     }
-    SBA_CUDA(cudaMemcpyAsync(p->h_x, p->x, (size_t)n_cam * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    SBA_CUDA(cudaStreamSynchronize(st));
     memcpy(r_inout, p->h_x, (size_t)n_cam * 3 * sizeof(double));
     if (summary) {
         const LMState& S = *p->h_state;

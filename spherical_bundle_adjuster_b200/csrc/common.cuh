@@ -69,6 +69,52 @@ struct DevBuf {
     template <typename T> T* as() { return (T*)p; }
 };
 
+// Size-bucketed cache of device / pinned-host blocks.  Everything a context allocates per call (BA
+// problems are created and destroyed once per image pair) is recycled here, so steady-state calls do
+// no cudaMalloc.  All users enqueue on the context's single stream, so reuse is stream-ordered.
+struct BlockCache {
+    std::multimap<size_t, void*> free_dev, free_host;
+    std::map<void*, size_t> live_dev, live_host;
+    static size_t bucket(size_t bytes)
+    {
+        size_t b = 256;
+        while (b < bytes) b <<= 1;
+        return b;
+    }
+    cudaError_t get(void** p, size_t bytes, bool host)
+    {
+        const size_t b = bucket(bytes ? bytes : 1);
+        auto& fl = host ? free_host : free_dev;
+        auto it = fl.find(b);
+        if (it != fl.end()) {
+            *p = it->second;
+            fl.erase(it);
+        } else {
+            cudaError_t e = host ? cudaMallocHost(p, b) : cudaMalloc(p, b);
+            if (e != cudaSuccess) { *p = nullptr; return e; }
+        }
+        (host ? live_host : live_dev)[*p] = b;
+        return cudaSuccess;
+    }
+    void put(void* p, bool host)
+    {
+        if (!p) return;
+        auto& live = host ? live_host : live_dev;
+        auto it = live.find(p);
+        if (it == live.end()) return;
+        (host ? free_host : free_dev).emplace(it->second, p);
+        live.erase(it);
+    }
+    void release_all()
+    {
+        for (auto& kv : free_dev) cudaFree(kv.second);
+        for (auto& kv : live_dev) cudaFree(kv.first);
+        for (auto& kv : free_host) cudaFreeHost(kv.second);
+        for (auto& kv : live_host) cudaFreeHost(kv.first);
+        free_dev.clear(); free_host.clear(); live_dev.clear(); live_host.clear();
+    }
+};
+
 struct RemapPlan {
     int w, h, cs;
     int32_t* lut = nullptr;  // device, cs x 6cs
@@ -79,7 +125,11 @@ struct RemapPlan {
 // Named scratch slots (one DevBuf each) so independent stages never alias.
 enum ScratchSlot {
     SCR_IN0 = 0, SCR_IN1, SCR_IN2, SCR_IN3, SCR_OUT0, SCR_OUT1, SCR_OUT2, SCR_OUT3, SCR_OUT4,
-    SCR_WORK0, SCR_WORK1, SCR_WORK2, SCR_WORK3, SCR_WORK4, SCR_WORK5, SCR_COUNT
+    SCR_WORK0, SCR_WORK1, SCR_WORK2, SCR_WORK3, SCR_WORK4, SCR_WORK5,
+    // buffers owned by the fused pair pipeline (pipeline.cu); the stage entry points never touch them
+    SCR_PIPE_IM0, SCR_PIPE_IM1, SCR_PIPE_STRIP0, SCR_PIPE_STRIP1, SCR_PIPE_DESC0, SCR_PIPE_DESC1, SCR_PIPE_KEY0, SCR_PIPE_KEY1,
+    SCR_PIPE_MATCH, SCR_PIPE_PTS, SCR_PIPE_BEAR,
+    SCR_COUNT
 };
 
 }  // namespace sba
@@ -91,6 +141,7 @@ struct sba_ctx {
     int sm_count = 148;
     int64_t launches = 0;
     sba::DevBuf scratch[sba::SCR_COUNT];
+    sba::BlockCache cache;
     std::map<std::tuple<int, int, int>, sba::RemapPlan> plans;
     sba_match_stats match_stats{};
     int* pinned_i32 = nullptr;  // small pinned host mailbox (64 ints) for scalar read-backs
@@ -152,6 +203,10 @@ inline void prof_end(sba_ctx* c, int id)
         c->prof_valid[id] = true;
     }
 }
+
+// ba.cu: problem creation with the option to read the caller's device bearings in place
+int ba_problem_create_impl(sba_ctx* c, const float* b1, const float* b2, const int32_t* cam, int64_t n_obs, int n_cam, int mem, bool borrow,
+                           sba_ba_problem** out);
 
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -74,6 +74,7 @@ int sba_ctx_destroy(sba_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& b : c->scratch) b.release();
+    c->cache.release_all();
     for (auto& kv : c->plans)
         if (kv.second.lut) cudaFree(kv.second.lut);
     if (c->pinned_i32) cudaFreeHost(c->pinned_i32);

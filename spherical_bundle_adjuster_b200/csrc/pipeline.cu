@@ -1,0 +1,106 @@
+// pipeline.cu -- the whole hot path for one ERP pair behind ONE C-ABI call.
+//
+// Mirrors what a caller of the reference does per pair:
+//   equi2cube_surf::do_all            (equi2cube_surf.cpp:78-122): get_all x2, match_two_image,
+//                                     cube2equi_pixel per keypoint, gather of the matched keypoints
+//   spherical_bundle_adjuster::do_bundle_adjustment (spherical_bundle_adjuster.cpp:268-298, :202-203):
+//                                     pixel -> bearing, rotation-only solve
+// minus SURF detect/describe (non-free OpenCV, stays on the host: the caller passes keypoints and
+// descriptors).  Everything between the input copy and the result copy stays on the device; the only
+// host round trips are the match count (sizes the BA problem) and the LM state once per launch chunk.
+#include "common.cuh"
+
+using namespace sba;
+
+extern "C" {
+
+int sba_pair_rotation(sba_ctx* c, const uint8_t* erp_left, const uint8_t* erp_right, int w, int h, int cube_size, uint8_t* strip_left_out,
+                      uint8_t* strip_right_out, const float* desc_left, int n_left, const float* desc_right, int n_right, int dim,
+                      const float* key_left_xy, const float* key_right_xy, float ratio, const double r0[3], const double t[3], double d1,
+                      double d2, double huber_delta, int max_iter, int32_t* query_idx_out, int32_t* train_idx_out, float* dist_out,
+                      sba_pair_result* result, int mem)
+{
+    SBA_CHECK_ARG(c && result && w > 0 && h > 0 && cube_size > 0 && n_left >= 0 && n_right >= 0);
+    SBA_CHECK_ARG(desc_left && desc_right && key_left_xy && key_right_xy && r0 && t);
+    SBA_CHECK_ARG((erp_left == nullptr) == (erp_right == nullptr));
+    SBA_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    memset(result, 0, sizeof(*result));
+    result->rotation[0] = r0[0]; result->rotation[1] = r0[1]; result->rotation[2] = r0[2];
+    const int D = SBA_MEM_DEVICE;
+
+    // ---- inputs to the device (one async copy each when they are host buffers)
+    const size_t im_bytes = (size_t)w * h * 3, strip_bytes = (size_t)cube_size * 6 * cube_size * 3;
+    const uint8_t *d_im0 = nullptr, *d_im1 = nullptr;
+    const float *d_desc0, *d_desc1, *d_key0, *d_key1;
+    if (erp_left) {
+        SBA_TRY(stage_in(c, erp_left, im_bytes, mem, SCR_PIPE_IM0, &d_im0));
+        SBA_TRY(stage_in(c, erp_right, im_bytes, mem, SCR_PIPE_IM1, &d_im1));
+    }
+    SBA_TRY(stage_in(c, desc_left, (size_t)n_left * dim, mem, SCR_PIPE_DESC0, &d_desc0));
+    SBA_TRY(stage_in(c, desc_right, (size_t)n_right * dim, mem, SCR_PIPE_DESC1, &d_desc1));
+    SBA_TRY(stage_in(c, key_left_xy, (size_t)n_left * 2, mem, SCR_PIPE_KEY0, &d_key0));
+    SBA_TRY(stage_in(c, key_right_xy, (size_t)n_right * 2, mem, SCR_PIPE_KEY1, &d_key1));
+
+    // ---- equi2cube::get_all on both images (the strips feed the host-side detector of the reference;
+    //      they stay on the device unless the caller asks for them)
+    if (erp_left) {
+        uint8_t *d_s0, *d_s1;
+        const bool dev_out = (mem == SBA_MEM_DEVICE);
+        if (dev_out && strip_left_out) d_s0 = strip_left_out;
+        else { SBA_TRY(c->scratch[SCR_PIPE_STRIP0].ensure(strip_bytes, st)); d_s0 = c->scratch[SCR_PIPE_STRIP0].as<uint8_t>(); }
+        if (dev_out && strip_right_out) d_s1 = strip_right_out;
+        else { SBA_TRY(c->scratch[SCR_PIPE_STRIP1].ensure(strip_bytes, st)); d_s1 = c->scratch[SCR_PIPE_STRIP1].as<uint8_t>(); }
+        SBA_TRY(sba_equi2cube(c, d_im0, w, h, 1, cube_size, d_s0, D));
+        SBA_TRY(sba_equi2cube(c, d_im1, w, h, 1, cube_size, d_s1, D));
+        if (!dev_out) {
+            SBA_TRY(copy_out(c, strip_left_out, d_s0, strip_bytes, mem));
+            SBA_TRY(copy_out(c, strip_right_out, d_s1, strip_bytes, mem));
+        }
+    }
+
+    // ---- feature_matcher::match_two_image
+    const size_t nq = (size_t)(n_left > 0 ? n_left : 1);
+    SBA_TRY(c->scratch[SCR_PIPE_MATCH].ensure(nq * 12 + 64, st));
+    int32_t* d_qi = c->scratch[SCR_PIPE_MATCH].as<int32_t>();
+    int32_t* d_ti = d_qi + nq;
+    float* d_dist = (float*)(d_ti + nq);
+    int32_t* d_n = (int32_t*)(d_dist + nq);
+    SBA_TRY(sba_knn2_ratio(c, d_desc0, n_left, d_desc1, n_right, dim, ratio, d_qi, d_ti, d_dist, d_n, nullptr, nullptr, D, SBA_MATCH_AUTO));
+    SBA_CUDA(cudaMemcpyAsync(c->pinned_i32, d_n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SBA_CUDA(cudaStreamSynchronize(st));
+    const int n = c->pinned_i32[0];
+    result->n_matches = n;
+    if (query_idx_out) SBA_CUDA(cudaMemcpyAsync(query_idx_out, d_qi, (size_t)n * 4, mem == SBA_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+    if (train_idx_out) SBA_CUDA(cudaMemcpyAsync(train_idx_out, d_ti, (size_t)n * 4, mem == SBA_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+    if (dist_out) SBA_CUDA(cudaMemcpyAsync(dist_out, d_dist, (size_t)n * 4, mem == SBA_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+    if (n == 0) return finish(c, mem);
+
+    // ---- matched keypoints: gather, cube strip -> ERP pixel, pixel -> bearing (left and right in one
+    //      2n-point batch per stage)
+    SBA_TRY(c->scratch[SCR_PIPE_PTS].ensure((size_t)n * 2 * 2 * sizeof(float) * 2, st));
+    float* d_cube = c->scratch[SCR_PIPE_PTS].as<float>();      // [2n][2] strip coordinates: left block, right block
+    float* d_erp = d_cube + (size_t)4 * n;                     // [2n][2] ERP pixels
+    SBA_TRY(sba_gather_matches(c, d_key0, d_key1, d_qi, d_ti, n, d_cube, d_cube + (size_t)2 * n, D));
+    SBA_TRY(sba_cube2equi_points(c, d_cube, 2 * n, cube_size, w, h, d_erp, D));
+    SBA_TRY(c->scratch[SCR_PIPE_BEAR].ensure((size_t)2 * n * 4 * sizeof(float), st));
+    float* d_b = c->scratch[SCR_PIPE_BEAR].as<float>();        // [2n] float4: left bearings, right bearings
+    SBA_TRY(sba_pixels_to_bearings(c, d_erp, 2 * n, w, h, d_b, nullptr, D));
+
+    // ---- rotation-only bundle adjustment
+    sba_ba_problem* prob = nullptr;
+    SBA_TRY(ba_problem_create_impl(c, d_b, d_b + (size_t)4 * n, nullptr, n, 1, D, /*borrow=*/true, &prob));
+    sba_solve_summary sum;
+    double r[3] = {r0[0], r0[1], r0[2]};
+    int status = sba_ba_rot_solve(prob, r, t, d1, d2, huber_delta, max_iter, &sum);
+    sba_ba_problem_destroy(prob);
+    SBA_TRY(status);
+    result->rotation[0] = r[0]; result->rotation[1] = r[1]; result->rotation[2] = r[2];
+    result->lm_iterations = sum.iterations;
+    result->lm_termination = sum.termination;
+    result->initial_cost = sum.initial_cost;
+    result->final_cost = sum.final_cost;
+    return finish(c, mem);
+}
+
+}  // extern "C"
