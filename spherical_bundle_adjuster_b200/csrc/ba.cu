@@ -400,19 +400,32 @@ struct EvalArgs {
     SolveConsts k;
 };
 
+// 128-bit streaming load: the observations are read once per evaluation, keep them out of L1.
+__device__ __forceinline__ float4 ld_stream(const float4* p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
 template <bool WRITE, bool FUSE>
-__global__ void __launch_bounds__(EVAL_THREADS, 2) ba_rot_eval_kernel(EvalArgs E, LMArrays A)
+__global__ void __launch_bounds__(EVAL_THREADS, 3) ba_rot_eval_kernel(EvalArgs E, LMArrays A)
 {
     __shared__ double sh[EVAL_THREADS];
     __shared__ int s_last;
+    // per-warp copy of the current camera's tables: R (9 fp64) then -dR/dr_k (27 fp32).  Kept in shared
+    // memory (broadcast reads) instead of 45 registers so three CTAs fit on an SM.
+    __shared__ __align__(16) double s_tab[EVAL_WARPS][24];
     if (FUSE && A.st->done) return;  // converged earlier in this launch chunk
 
-    const int lane = threadIdx.x & 31;
-    const int warp_global = blockIdx.x * EVAL_WARPS + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int warp_global = blockIdx.x * EVAL_WARPS + wib;
     const int warp_stride = gridDim.x * EVAL_WARPS;
     const double d1 = E.k.d1, d2 = E.k.d2, huber = E.k.huber, hub2 = huber * huber;
     const double t0 = E.k.t[0], t1 = E.k.t[1], t2 = E.k.t[2];
     const float d1f = (float)d1;
+    const double* Rs = &s_tab[wib][0];
+    const float* Ms = reinterpret_cast<const float*>(&s_tab[wib][9]);   // 27 floats + pad
 
     for (int it = warp_global; it < E.n_items; it += warp_stride) {
         Item item;
@@ -422,13 +435,19 @@ __global__ void __launch_bounds__(EVAL_THREADS, 2) ba_rot_eval_kernel(EvalArgs E
             item.count = min(E.item_len, E.n_obs - it * E.item_len);
             item.cam = 0;
         }
-        const CamParams* P = E.params + item.cam;
-        double R[9];
-#pragma unroll
-        for (int a = 0; a < 9; a++) R[a] = P->R[a];
-        float M[27];
-#pragma unroll
-        for (int a = 0; a < 27; a++) M[a] = P->nM[a];
+        // first observation of every lane goes in flight before the tables are staged
+        const float4* q1 = E.b1 + item.start + lane;
+        const float4* q2 = E.b2 + item.start + lane;
+        float4 n1 = make_float4(0.f, 0.f, 0.f, 0.f), n2 = n1;
+        if (lane < item.count) { n1 = ld_stream(q1); n2 = ld_stream(q2); }
+        {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(E.params + item.cam);   // 46 words: 18 (R) + 27 (nM) + pad
+            uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab[wib][0]);
+            __syncwarp();
+            dst[lane] = src[lane];
+            if (lane < 14) dst[32 + lane] = src[32 + lane];
+            __syncwarp();
+        }
 
         double acc[10];
 #pragma unroll
@@ -439,15 +458,14 @@ __global__ void __launch_bounds__(EVAL_THREADS, 2) ba_rot_eval_kernel(EvalArgs E
         int in_flight = 0;
 
         for (int o = lane; o < item.count; o += 32) {
-            const int64_t i = item.start + o;
-            const float4 p1 = __ldg(E.b1 + i);
-            const float4 p2 = __ldg(E.b2 + i);
+            const float4 p1 = n1, p2 = n2;
+            if (o + 32 < item.count) { n1 = ld_stream(q1 + (o - lane) + 32); n2 = ld_stream(q2 + (o - lane) + 32); }   // prefetch
             // residual in fp64 (spherical_bundle_adjuster.cpp:896-916)
             const double X1x = (double)p1.x * d1, X1y = (double)p1.y * d1, X1z = (double)p1.z * d1;
             const double X2x = (double)p2.x * d2, X2y = (double)p2.y * d2, X2z = (double)p2.z * d2;
-            const double rx = X2x - ((R[0] * X1x + R[1] * X1y + R[2] * X1z) - t0);
-            const double ry = X2y - ((R[3] * X1x + R[4] * X1y + R[5] * X1z) - t1);
-            const double rz = X2z - ((R[6] * X1x + R[7] * X1y + R[8] * X1z) - t2);
+            const double rx = X2x - ((Rs[0] * X1x + Rs[1] * X1y + Rs[2] * X1z) - t0);
+            const double ry = X2y - ((Rs[3] * X1x + Rs[4] * X1y + Rs[5] * X1z) - t1);
+            const double rz = X2z - ((Rs[6] * X1x + Rs[7] * X1y + Rs[8] * X1z) - t2);
             const double s = rx * rx + ry * ry + rz * rz;
             // Huber: rho' = 1 (s <= a^2) or a/sqrt(s); rho = s or 2 a sqrt(s) - a^2
             double rho = s, rho1 = 1.0;
@@ -465,7 +483,7 @@ __global__ void __launch_bounds__(EVAL_THREADS, 2) ba_rot_eval_kernel(EvalArgs E
 #pragma unroll
             for (int k = 0; k < 3; k++)
 #pragma unroll
-                for (int a = 0; a < 3; a++) J[3 * a + k] = M[k * 9 + a * 3] * x1 + M[k * 9 + a * 3 + 1] * y1 + M[k * 9 + a * 3 + 2] * z1;
+                for (int a = 0; a < 3; a++) J[3 * a + k] = Ms[k * 9 + a * 3] * x1 + Ms[k * 9 + a * 3 + 1] * y1 + Ms[k * 9 + a * 3 + 2] * z1;
             const float rxf = (float)rx, ryf = (float)ry, rzf = (float)rz, wf = (float)rho1;
             facc[0] += wf * (J[0] * J[0] + J[3] * J[3] + J[6] * J[6]);
             facc[1] += wf * (J[0] * J[1] + J[3] * J[4] + J[6] * J[7]);
@@ -482,6 +500,7 @@ __global__ void __launch_bounds__(EVAL_THREADS, 2) ba_rot_eval_kernel(EvalArgs E
                 in_flight = 0;
             }
             if (WRITE) {
+                const int64_t i = item.start + o;
                 const int64_t dst = E.perm ? (int64_t)E.perm[i] : i;
                 if (E.res) {
                     E.res[3 * dst] = rxf; E.res[3 * dst + 1] = ryf; E.res[3 * dst + 2] = rzf;

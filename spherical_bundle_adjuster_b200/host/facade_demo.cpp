@@ -1,0 +1,68 @@
+// facade_demo.cpp -- exercises the drop-in classes end to end on files written by the Python tests:
+//   facade_demo <dir>   reads <dir>/{im.bin,desc1.bin,desc2.bin,key1.bin,key2.bin,meta.txt}
+//                       writes <dir>/{strip.bin,face3.bin,matches.bin,rot.bin}
+// (tests/test_gpu_facade.py compares those with the oracle).
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+#include <string>
+
+#include "spherical_bundle_adjuster.hpp"
+
+template <typename T> static std::vector<T> slurp(const std::string& p)
+{
+    std::ifstream f(p, std::ios::binary);
+    std::vector<char> raw((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    std::vector<T> v(raw.size() / sizeof(T));
+    memcpy(v.data(), raw.data(), v.size() * sizeof(T));
+    return v;
+}
+template <typename T> static void dump(const std::string& p, const T* d, size_t n)
+{
+    std::ofstream f(p, std::ios::binary);
+    f.write((const char*)d, n * sizeof(T));
+}
+
+int main(int argc, char** argv)
+{
+    if (argc < 2) { std::cerr << "usage: facade_demo <dir>\n"; return 2; }
+    const std::string dir = argv[1];
+    int w, h, cs, n1, n2;
+    { std::ifstream m(dir + "/meta.txt"); m >> w >> h >> cs >> n1 >> n2; }
+    try {
+        auto im = slurp<unsigned char>(dir + "/im.bin");
+        cv::Mat erp(h, w, CV_8UC3, im.data());
+        equi2cube e2c;
+        cv::Mat strip = e2c.get_all(erp, cs);
+        dump(dir + "/strip.bin", strip.data, strip.total() * 3);
+        cv::Mat back = e2c.get_back(erp, cs);
+        dump(dir + "/face3.bin", back.data, back.total() * 3);
+
+        auto d1 = slurp<float>(dir + "/desc1.bin"), d2 = slurp<float>(dir + "/desc2.bin");
+        auto k1 = slurp<float>(dir + "/key1.bin"), k2 = slurp<float>(dir + "/key2.bin");
+        cv::Mat desc1(n1, 64, CV_32FC1, d1.data()), desc2(n2, 64, CV_32FC1, d2.data());
+        std::vector<cv::KeyPoint> kp1(n1), kp2(n2);
+        for (int i = 0; i < n1; i++) { kp1[i].pt.x = k1[2 * i]; kp1[i].pt.y = k1[2 * i + 1]; }
+        for (int i = 0; i < n2; i++) { kp2[i].pt.x = k2[2 * i]; kp2[i].pt.y = k2[2 * i + 1]; }
+
+        equi2cube_surf es;
+        es.set_cube_size(cs);
+        std::vector<cv::KeyPoint> left, right;
+        std::vector<cv::DMatch> matches;
+        es.match_and_lift(kp1, kp2, desc1, desc2, w, h, left, right, matches);
+        std::vector<int> mm;
+        for (auto& m : matches) { mm.push_back(m.queryIdx); mm.push_back(m.trainIdx); }
+        dump(dir + "/matches.bin", mm.data(), mm.size());
+
+        spherical_bundle_adjuster sba;
+        double rot[3] = {0, 0, 0};
+        sba_solve_summary s = sba.adjust_rotation(left, right, w, h, rot);
+        double out[5] = {rot[0], rot[1], rot[2], (double)s.iterations, s.final_cost};
+        dump(dir + "/rot.bin", out, 5);
+        std::printf("facade_demo: %zu matches, rotation %.9f %.9f %.9f, %d LM iterations\n", matches.size(), rot[0], rot[1], rot[2], s.iterations);
+    } catch (const std::exception& ex) {
+        std::cerr << "facade_demo failed: " << ex.what() << "\n";
+        return 1;
+    }
+    return 0;
+}

@@ -1,0 +1,66 @@
+// Facade: rotation-only spherical bundle adjustment.  Replaces spherical_bundle_adjuster.cpp:268-298
+// (pixel -> bearing), :892-945 (functor + add_residual) and the ceres::Solve call at :203.
+#include "spherical_bundle_adjuster.hpp"
+
+#include "sba_host_ctx.hpp"
+
+sba_solve_summary ba_spherical_costfunctor_rot_only::solve(std::vector<cv::Point3d>& left, std::vector<cv::Point3d>& right, double* init_rot,
+                                                           double* init_tran, std::vector<std::array<double, 2>>& init_d, int match_num,
+                                                           int max_num_iterations)
+{
+    sba_solve_summary sum{};
+    if (match_num <= 0) return sum;
+    std::vector<float> b1(4 * (size_t)match_num), b2(4 * (size_t)match_num);
+    for (int i = 0; i < match_num; i++) {
+        b1[4 * i] = (float)left[i].x; b1[4 * i + 1] = (float)left[i].y; b1[4 * i + 2] = (float)left[i].z; b1[4 * i + 3] = 0.f;
+        b2[4 * i] = (float)right[i].x; b2[4 * i + 1] = (float)right[i].y; b2[4 * i + 2] = (float)right[i].z; b2[4 * i + 3] = 0.f;
+    }
+    // the reference hands init_d[0][0] and init_d[1][0] to EVERY residual (:941-942); preserved
+    const double d1 = init_d.size() > 0 ? init_d[0][0] : 1.0, d2 = init_d.size() > 1 ? init_d[1][0] : d1;
+    sba_ba_problem* prob = nullptr;
+    sba_host::check(sba_ba_problem_create(sba_host::ctx(), b1.data(), b2.data(), nullptr, match_num, 1, SBA_MEM_HOST, &prob));
+    int status = sba_ba_rot_solve(prob, init_rot, init_tran, d1, d2, 1.0 /* HuberLoss(1.0), :943 */, max_num_iterations, &sum);
+    sba_ba_problem_destroy(prob);
+    sba_host::check(status);
+    return sum;
+}
+
+void spherical_bundle_adjuster::set_omp(int num_proc) { this->num_proc = num_proc; }
+
+sba_solve_summary spherical_bundle_adjuster::adjust_rotation(const std::vector<cv::KeyPoint>& left_key, const std::vector<cv::KeyPoint>& right_key,
+                                                             int im_width, int im_height, double rot[3])
+{
+    const int n = (int)left_key.size();
+    sba_solve_summary sum{};
+    if (n == 0) return sum;
+    // pixel -> bearing for both sides in one 2n batch (spherical_bundle_adjuster.cpp:271-298)
+    std::vector<float> px(4 * (size_t)n), b(8 * (size_t)n);
+    for (int i = 0; i < n; i++) {
+        px[2 * i] = left_key[i].pt.x; px[2 * i + 1] = left_key[i].pt.y;
+        px[2 * (n + i)] = right_key[i].pt.x; px[2 * (n + i) + 1] = right_key[i].pt.y;
+    }
+    sba_host::check(sba_pixels_to_bearings(sba_host::ctx(), px.data(), 2 * n, im_width, im_height, b.data(), nullptr, SBA_MEM_HOST));
+    sba_ba_problem* prob = nullptr;
+    sba_host::check(sba_ba_problem_create(sba_host::ctx(), b.data(), b.data() + 4 * (size_t)n, nullptr, n, 1, SBA_MEM_HOST, &prob));
+    const double t[3] = {expected_tx, expected_ty, expected_tz};
+    // d = expected_d for both cameras like init_d (:325-326); 0 would zero every residual, so the usual
+    // unit sphere is used when the caller left it at the default
+    const double d = expected_d != 0.0 ? expected_d : 1.0;
+    int status = sba_ba_rot_solve(prob, rot, t, d, d, 1.0, 50, &sum);
+    sba_ba_problem_destroy(prob);
+    sba_host::check(status);
+    return sum;
+}
+
+void spherical_bundle_adjuster::do_bundle_adjustment(const cv::Mat& im_left, const cv::Mat& im_right)
+{
+    std::vector<cv::KeyPoint> left_key, right_key;
+    int match_size = 0, total_key_num = 0;
+    cv::Mat match_output;
+    equi2cube_surf fm;
+    fm.set_omp(num_proc);
+    fm.set_cube_size(600);   // test/feature_test.cpp:198
+    fm.do_all(im_left, im_right, left_key, right_key, match_size, match_output, total_key_num);
+    result_rot[0] = result_rot[1] = result_rot[2] = 0.0;
+    adjust_rotation(left_key, right_key, im_left.cols, im_left.rows, result_rot);
+}

@@ -1,0 +1,52 @@
+// Drop-in for the rotation-only path of the reference's spherical_bundle_adjuster.hpp.
+//
+// The class keeps the reference's constructor / set_omp / do_bundle_adjustment signatures
+// (spherical_bundle_adjuster.hpp:15-23).  The Ceres functor struct keeps its name and its add_residual
+// argument list minus the ceres::Problem (Ceres is not a dependency any more): `solve` does what
+// `add_residual(problem, ...)` followed by `ceres::Solve(opt, &problem, &summary)` did
+// (spherical_bundle_adjuster.cpp:202-203), on the GPU.
+#pragma once
+#include <array>
+#include <vector>
+
+#include "equi2cube_surf.hpp"
+#include "sba_b200.h"
+
+struct ba_spherical_costfunctor_rot_only
+{
+    // Residual + Jacobian evaluation and LM solve of spherical_bundle_adjuster.cpp:892-945 on the GPU.
+    // init_rot is updated in place (the single shared 3-vector parameter block, :943); t = init_tran,
+    // d1 = init_d[0][0], d2 = init_d[1][0] for every residual exactly as the reference passes them
+    // (:938-942); Huber(1.0); at most max_num_iterations LM iterations (the reference sets 50, :336).
+    static sba_solve_summary solve(std::vector<cv::Point3d>& key_point_left_rect
+                                 , std::vector<cv::Point3d>& key_point_right_rect
+                                 , double* init_rot
+                                 , double* init_tran
+                                 , std::vector<std::array<double, 2>>& init_d
+                                 , int match_num
+                                 , int max_num_iterations = 50);
+};
+
+class spherical_bundle_adjuster
+{
+    public:
+    spherical_bundle_adjuster(double roll = 0, double pitch = 0, double yaw = 0, double tx = 0, double ty = 0, double tz = 0, double d = 0)
+    : expected_roll(roll), expected_pitch(pitch), expected_yaw(yaw), expected_tx(tx), expected_ty(ty), expected_tz(tz), expected_d(d) {}
+    ~spherical_bundle_adjuster() {}
+
+    void set_omp(int num_proc);
+    // Cubemap front-end (equi2cube_surf, cube 600 like the reference's test) -> bearings -> rotation-only
+    // solve from a zero rotation.  Needs SURF (real OpenCV) for the front-end.
+    void do_bundle_adjustment(const cv::Mat &im_left, const cv::Mat &im_right);
+
+    // The post-SURF part: matched ERP keypoints -> bearings (spherical_bundle_adjuster.cpp:268-298) ->
+    // rotation-only solve.  Returns the rotation vector in rot[3].
+    sba_solve_summary adjust_rotation(const std::vector<cv::KeyPoint>& left_key, const std::vector<cv::KeyPoint>& right_key, int im_width,
+                                      int im_height, double rot[3]);
+
+    double result_rot[3] = {0, 0, 0};
+
+    private:
+    double expected_roll, expected_pitch, expected_yaw, expected_tx, expected_ty, expected_tz, expected_d;
+    int num_proc = 1;
+};

@@ -53,3 +53,23 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), f
                 assert "sba_oracle" not in src and "libsba_ref" not in src, f
+
+
+def test_cpp_facade_builds_and_fails_loudly_without_gpu(tmp_path):
+    """The drop-in C++ classes link against the C ABI; with no GPU the demo must exit non-zero with the
+    library's error text instead of computing anything on the CPU."""
+    import subprocess
+    import torch
+    facade = os.path.join(ROOT, "spherical_bundle_adjuster_b200", "libsba_facade.so")
+    demo = os.path.join(ROOT, "build", "facade_demo")
+    assert os.path.exists(facade) and os.path.exists(demo), "run __graft_entry__.build()"
+    out = subprocess.run(["nm", "-D", "--defined-only", facade], capture_output=True, text=True).stdout
+    for sym in ["equi2cube7get_all", "feature_matcher15match_two_image", "equi2cube_surf6do_all", "equi2cube_surf15cube2equi_pixel",
+                "spherical_bundle_adjuster20do_bundle_adjustment", "ba_spherical_costfunctor_rot_only5solve"]:
+        assert sym in out, sym
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    open(tmp_path / "meta.txt", "w").write("8 4 2 0 0\n")
+    (tmp_path / "im.bin").write_bytes(bytes(8 * 4 * 3))
+    r = subprocess.run([demo, str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr

@@ -1,0 +1,42 @@
+"""GPU: the C++ drop-in classes (equi2cube, equi2cube_surf, feature_matcher via match_and_lift,
+spherical_bundle_adjuster::adjust_rotation) driven from a C++ program, checked against the oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from spherical_bundle_adjuster_b200 import synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DEMO = os.path.join(ROOT, "build", "facade_demo")
+
+
+def test_cpp_facade_end_to_end(tmp_path):
+    assert os.path.exists(DEMO), "build/facade_demo missing: run __graft_entry__.build()"
+    w, h, cs, n1, n2 = 1024, 512, 200, 2500, 2300
+    pair = synth.make_pair(n1, n2, cs=cs, seed=31, rotvec=(0.05, 0.2, -0.3))
+    im = synth.make_erp_image(w, h, seed=5)
+    d = str(tmp_path)
+    im.tofile(d + "/im.bin"); pair["desc1"].tofile(d + "/desc1.bin"); pair["desc2"].tofile(d + "/desc2.bin")
+    pair["key1_xy"].tofile(d + "/key1.bin"); pair["key2_xy"].tofile(d + "/key2.bin")
+    open(d + "/meta.txt", "w").write(f"{w} {h} {cs} {n1} {n2}\n")
+    r = subprocess.run([DEMO, d], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+    strip = np.fromfile(d + "/strip.bin", np.uint8).reshape(cs, 6 * cs, 3)
+    assert np.array_equal(strip, oracle.equi2cube_all(im, cs))
+    back = np.fromfile(d + "/face3.bin", np.uint8).reshape(cs, cs, 3)
+    assert np.array_equal(back, oracle.equi2cube_face(im, cs, 3))
+    mm = np.fromfile(d + "/matches.bin", np.int32).reshape(-1, 2)
+    qi, ti, _ = oracle.match_two_image(pair["desc1"], pair["desc2"], 0.3)
+    assert np.array_equal(mm[:, 0], qi) and np.array_equal(mm[:, 1], ti)
+    rot = np.fromfile(d + "/rot.bin", np.float64)
+    e1 = oracle.cube2equi_points(pair["key1_xy"][qi], cs, w, h); e2 = oracle.cube2equi_points(pair["key2_xy"][ti], cs, w, h)
+    b1 = oracle.pixels_to_bearings(e1, w, h).astype(np.float32).astype(np.float64)
+    b2 = oracle.pixels_to_bearings(e2, w, h).astype(np.float32).astype(np.float64)
+    r_or, s_or = oracle.ba_rot_solve(b1, b2, None, np.zeros((1, 3)))
+    assert np.abs(rot[:3] - r_or[0]).max() < 1e-6 and int(rot[3]) == s_or.iterations
+    assert np.linalg.norm(rot[:3] - pair["r_true"]) < 1e-4
