@@ -8,16 +8,19 @@
 //   b1, b2   : n_obs x float4 (x, y, z, -), observations grouped by camera at problem creation so a
 //              work item (<= 8192 consecutive observations of ONE camera) is a contiguous, 16-byte
 //              aligned range; 32 B read per observation, nothing else on the fused path.
-//   params   : per camera {R (9 fp64), -dR/dr_k (27 fp32)} = 184 B, rebuilt whenever r changes.
-//   partial  : n_items x 10 fp64 {Hxx,Hxy,Hxz,Hyy,Hyz,Hzz,gx,gy,gz,cost}, one row per work item.
-//   blocks   : n_cam x 10 fp64, the per-camera normal-equation blocks (what an all-reduce sums).
+//   params   : per camera {d1*R (9 fp64), dR/dr_k (27 fp64), -dR/dr_k (27 fp32)}, rebuilt whenever r changes.
+//   partial  : n_items x 16 fp64 {S (6), C (9), cost}: the weighted moments of one work item (below).
+//   blocks   : n_cam x 10 fp64 {Hxx,Hxy,Hxz,Hyy,Hyz,Hzz,gx,gy,gz,cost}, the per-camera normal-equation
+//              blocks (what an all-reduce sums).
 //
-// Precision split (north_star: residuals/Jacobians 1e-5 relative, rotations 1e-6 rad):
-//   residual, |res|^2, Huber rho and the cost are fp64 (fp32 bearings widened on load); the 3x3
-//   Jacobian and the J^T J / J^T r products are fp32, summed in fp32 over at most 8 observations and
-//   then carried in fp64.  Jacobian rounding only perturbs the LM path, not its fixed point
-//   (sum J^T r = 0 is evaluated with fp64 residuals), so recovered rotations agree with the fp64
-//   oracle far below 1e-6 rad.
+// Moment form.  J_i = -dR(r)/dr . X1_i is LINEAR in the observation with per-camera constants, so
+//   H = sum_i w_i J_i^T J_i  and  g = sum_i w_i J_i^T res_i
+// depend on the observations only through  S = sum_i w_i b1_i b1_i^T (6 unique)  and
+// C = sum_i w_i b1_i res_i^T (9)  (w_i = Huber rho').  The evaluation kernel therefore accumulates 16
+// scalars per observation in fp64 (B200: 64 DFMA/clk/SM -- the kernel stays HBM-bound) and the
+// contraction with dR/dr (fp64, ~200 flops) happens once per camera when the partials are folded.
+// Everything on the fused path is fp64 on fp32-stored bearings widened exactly, so blocks, cost and the
+// LM trajectory agree with the fp64 oracle to ~1e-12; only the optional materialised Jacobian is fp32.
 //
 // Determinism: every reduction has a fixed order (lane-strided partial sums, xor-butterfly warp
 // tree, ordered item sums per camera, fixed block tree) -- no floating-point atomics.
@@ -36,8 +39,9 @@
 namespace sba {
 
 struct CamParams {
-    double R[9];
-    float nM[27];  // nM[k*9 + a*3 + b] = -dR/dr_k [a][b]  ->  J[a][k] = sum_b nM[k][a][b] * X1[b]
+    double Rd[9];    // d1 * R(r): X1 rotated = Rd . b1
+    double dR[27];   // dR[k*9 + a*3 + b] = dR/dr_k [a][b]
+    float nM[27];    // -d1 * dR/dr_k as fp32: the materialised Jacobian J[a][k] = sum_b nM[k][a][b] * b1[b]
     float pad;
 };
 
@@ -94,23 +98,66 @@ __device__ inline void rot_and_derivs(const double r[3], double R[9], double dR[
     }
 }
 
-__device__ inline void write_cam_params(const double r[3], CamParams* out)
+__device__ inline void write_cam_params(const double r[3], double d1, CamParams* out)
 {
     double R[9], dR[3][9];
     rot_and_derivs(r, R, dR);
-    for (int a = 0; a < 9; a++) out->R[a] = R[a];
+    for (int a = 0; a < 9; a++) out->Rd[a] = d1 * R[a];
     for (int k = 0; k < 3; k++)
-        for (int a = 0; a < 9; a++) out->nM[k * 9 + a] = (float)(-dR[k][a]);
+        for (int a = 0; a < 9; a++) {
+            out->dR[k * 9 + a] = dR[k][a];
+            out->nM[k * 9 + a] = (float)(-d1 * dR[k][a]);
+        }
     out->pad = 0.f;
 }
 
-__global__ void ba_cam_params_kernel(const double* __restrict__ x, int n_cam, CamParams* __restrict__ out)
+__global__ void ba_cam_params_kernel(const double* __restrict__ x, int n_cam, double d1, CamParams* __restrict__ out)
 {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < n_cam) {
         double r[3] = {x[3 * c], x[3 * c + 1], x[3 * c + 2]};
-        write_cam_params(r, out + c);
+        write_cam_params(r, d1, out + c);
     }
+}
+
+// Moments of one camera -> its normal-equation block.  m = {Sxx,Sxy,Sxz,Syy,Syz,Szz, C[b][a] (9), cost}
+// with S = sum w b b^T, C[b][a] = sum w b_b res_a on UNSCALED bearings b (X1 = d1 b).
+//   H_kl =  d1^2 sum_a sum_b sum_c dR_k[a][b] dR_l[a][c] S_bc        (J = -d1 dR b; the signs cancel)
+//   g_k  = -d1   sum_a sum_b dR_k[a][b] C[b][a]
+__device__ inline void moments_to_block(const double m[16], const CamParams* __restrict__ P, double d1, double blk[10])
+{
+    double dR[27];
+#pragma unroll
+    for (int i = 0; i < 27; i++) dR[i] = P->dR[i];
+    const double S[9] = {m[0], m[1], m[2], m[1], m[3], m[4], m[2], m[4], m[5]};
+    double T[27];   // T[k*9 + a*3 + c] = sum_b dR_k[a][b] S_bc
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                T[k * 9 + 3 * a + c] = dR[k * 9 + 3 * a] * S[c] + dR[k * 9 + 3 * a + 1] * S[3 + c] + dR[k * 9 + 3 * a + 2] * S[6 + c];
+    int e = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int l = k; l < 3; l++) {
+            double h = 0;
+#pragma unroll
+            for (int ac = 0; ac < 9; ac++) h += T[k * 9 + ac] * dR[l * 9 + ac];
+            blk[e++] = d1 * d1 * h;
+        }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        double gk = 0;
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++) gk += dR[k * 9 + 3 * a + b] * m[6 + 3 * b + a];
+        blk[6 + k] = -d1 * gk;
+    }
+    blk[9] = m[15];
 }
 
 // ---- reductions ---------------------------------------------------------------------------------
@@ -178,6 +225,7 @@ struct LMArrays {
     CamParams* params; // tables for xc
     LMState* st;
     int n_cam;
+    double d1;         // uniform depth of camera 1 (folded into the rotation tables)
 };
 
 // Trust-region bookkeeping restated from Ceres' TrustRegionMinimizer / LevenbergMarquardtStrategy
@@ -307,7 +355,7 @@ __device__ void lm_decide(const LMArrays A, double* sh)
     if (!S.done)
         for (int c = tid; c < n_cam; c += nthr) {
             double r[3] = {A.xc[3 * c], A.xc[3 * c + 1], A.xc[3 * c + 2]};
-            write_cam_params(r, A.params + c);
+            write_cam_params(r, A.d1, A.params + c);
         }
     if (tid == 0) *A.st = S;
 }
@@ -320,32 +368,38 @@ __global__ void __launch_bounds__(EVAL_THREADS) ba_decide_kernel(LMArrays A)
 }
 
 // ---- the evaluation kernel (K5) ------------------------------------------------------------------
-// Fold work-item partials into per-camera blocks, in item order.  `item_ptr` [n_cam+1].
+// Fold work-item moment partials into per-camera blocks, in item order.  `item_ptr` [n_cam+1] or NULL.
+constexpr int NMOM = 16;
+
 __device__ void fold_items(const double* __restrict__ partial, const int* __restrict__ item_ptr, int n_items, int n_cam,
-                           double* __restrict__ blk)
+                           const CamParams* __restrict__ params, double d1, double* __restrict__ blk)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (item_ptr == nullptr) {
         // single camera whose items are 0..n_items-1 (uniform layout): all 8 warps cooperate;
         // thread-strided ordered sums, then a fixed tree over the CTA
-        __shared__ double red[EVAL_THREADS];
-        double acc[10];
+        __shared__ double red[EVAL_WARPS][NMOM];
+        double acc[NMOM];
 #pragma unroll
-        for (int k = 0; k < 10; k++) acc[k] = 0;
+        for (int k = 0; k < NMOM; k++) acc[k] = 0;
         for (int it = threadIdx.x; it < n_items; it += EVAL_THREADS)
 #pragma unroll
-            for (int k = 0; k < 10; k++) acc[k] += partial[(size_t)it * 10 + k];
+            for (int k = 0; k < NMOM; k++) acc[k] += partial[(size_t)it * NMOM + k];
 #pragma unroll
-        for (int k = 0; k < 10; k++) {
-            double v = warp_sum(acc[k]);
-            __syncthreads();
-            if (lane == 0) red[warp] = v;
-            __syncthreads();
-            if (threadIdx.x == 0) {
+        for (int k = 0; k < NMOM; k++) acc[k] = warp_sum(acc[k]);
+        __syncthreads();
+        if (lane == 0)
+#pragma unroll
+            for (int k = 0; k < NMOM; k++) red[warp][k] = acc[k];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double m[NMOM];
+            for (int k = 0; k < NMOM; k++) {
                 double t = 0;
-                for (int w = 0; w < EVAL_WARPS; w++) t += red[w];
-                blk[k] = t;
+                for (int w = 0; w < EVAL_WARPS; w++) t += red[w][k];
+                m[k] = t;
             }
+            moments_to_block(m, params, d1, blk);
         }
         __syncthreads();
         return;
@@ -354,31 +408,47 @@ __device__ void fold_items(const double* __restrict__ partial, const int* __rest
     if (n_items_total <= 8 * n_cam) {
         // few items per camera: one thread per camera, sequential ordered sum
         for (int c = threadIdx.x; c < n_cam; c += EVAL_THREADS) {
-            double acc[10];
+            double acc[NMOM];
 #pragma unroll
-            for (int k = 0; k < 10; k++) acc[k] = 0;
+            for (int k = 0; k < NMOM; k++) acc[k] = 0;
             for (int it = item_ptr[c]; it < item_ptr[c + 1]; it++)
 #pragma unroll
-                for (int k = 0; k < 10; k++) acc[k] += partial[(size_t)it * 10 + k];
-#pragma unroll
-            for (int k = 0; k < 10; k++) blk[10 * c + k] = acc[k];
+                for (int k = 0; k < NMOM; k++) acc[k] += partial[(size_t)it * NMOM + k];
+            moments_to_block(acc, params + c, d1, blk + 10 * c);
         }
     } else {
         // many items per camera: one warp per camera, lane-strided ordered sums + butterfly
         for (int c = warp; c < n_cam; c += EVAL_WARPS) {
-            double acc[10];
+            double acc[NMOM];
 #pragma unroll
-            for (int k = 0; k < 10; k++) acc[k] = 0;
+            for (int k = 0; k < NMOM; k++) acc[k] = 0;
             for (int it = item_ptr[c] + lane; it < item_ptr[c + 1]; it += 32)
 #pragma unroll
-                for (int k = 0; k < 10; k++) acc[k] += partial[(size_t)it * 10 + k];
+                for (int k = 0; k < NMOM; k++) acc[k] += partial[(size_t)it * NMOM + k];
 #pragma unroll
-            for (int k = 0; k < 10; k++) acc[k] = warp_sum(acc[k]);
-            if (lane == 0)
-#pragma unroll
-                for (int k = 0; k < 10; k++) blk[10 * c + k] = acc[k];
+            for (int k = 0; k < NMOM; k++) acc[k] = warp_sum(acc[k]);
+            if (lane == 0) moments_to_block(acc, params + c, d1, blk + 10 * c);
         }
     }
+}
+
+// Stand-alone fold for problems with many cameras: one warp per camera over the whole grid (the
+// in-kernel fold runs in a single CTA, which is only right when there are few cameras).
+__global__ void __launch_bounds__(EVAL_THREADS) ba_fold_kernel(const double* __restrict__ partial, const int* __restrict__ item_ptr, int n_cam,
+                                                              const CamParams* __restrict__ params, double d1, double* __restrict__ blk)
+{
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * EVAL_WARPS + (threadIdx.x >> 5);
+    if (c >= n_cam) return;
+    double acc[NMOM];
+#pragma unroll
+    for (int k = 0; k < NMOM; k++) acc[k] = 0;
+    for (int it = item_ptr[c] + lane; it < item_ptr[c + 1]; it += 32)
+#pragma unroll
+        for (int k = 0; k < NMOM; k++) acc[k] += partial[(size_t)it * NMOM + k];
+#pragma unroll
+    for (int k = 0; k < NMOM; k++) acc[k] = warp_sum(acc[k]);
+    if (lane == 0) moments_to_block(acc, params + c, d1, blk + 10 * c);
 }
 
 struct EvalArgs {
@@ -408,24 +478,30 @@ __device__ __forceinline__ float4 ld_stream(const float4* p)
     return v;
 }
 
-template <bool WRITE, bool FUSE>
+// MODE 0: partials only (ba_fold_kernel follows); 1: the last CTA folds; 2: the last CTA folds and runs the LM decision.
+template <bool WRITE, int MODE>
 __global__ void __launch_bounds__(EVAL_THREADS, 3) ba_rot_eval_kernel(EvalArgs E, LMArrays A)
 {
     __shared__ double sh[EVAL_THREADS];
     __shared__ int s_last;
-    // per-warp copy of the current camera's tables: R (9 fp64) then -dR/dr_k (27 fp32).  Kept in shared
-    // memory (broadcast reads) instead of 45 registers so three CTAs fit on an SM.
-    __shared__ __align__(16) double s_tab[EVAL_WARPS][24];
-    if (FUSE && A.st->done) return;  // converged earlier in this launch chunk
+    // per-warp copy of the current camera's tables: d1*R (9 fp64) and, for the materialised variant,
+    // -d1*dR/dr_k (27 fp32).  Shared memory (broadcast reads) instead of registers: three CTAs per SM.
+    __shared__ __align__(16) double s_R[EVAL_WARPS][10];
+    __shared__ __align__(16) float s_M[WRITE ? EVAL_WARPS : 1][28];
+    if (MODE == 2 && A.st->done) return;  // converged earlier in this launch chunk
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warp_global = blockIdx.x * EVAL_WARPS + wib;
     const int warp_stride = gridDim.x * EVAL_WARPS;
-    const double d1 = E.k.d1, d2 = E.k.d2, huber = E.k.huber, hub2 = huber * huber;
+    const double d2 = E.k.d2, huber = E.k.huber, hub2 = huber * huber;
     const double t0 = E.k.t[0], t1 = E.k.t[1], t2 = E.k.t[2];
-    const float d1f = (float)d1;
-    const double* Rs = &s_tab[wib][0];
-    const float* Ms = reinterpret_cast<const float*>(&s_tab[wib][9]);   // 27 floats + pad
+    const double* Rs = &s_R[wib][0];
+    // Uniform layout (one camera): a warp keeps its moments across all of its work items and the CTA
+    // publishes ONE partial, so the final fold is over gridDim.x entries instead of n_items.
+    const bool uniform = (E.items == nullptr);
+    double acc[NMOM];
+#pragma unroll
+    for (int k = 0; k < NMOM; k++) acc[k] = 0;
 
     for (int it = warp_global; it < E.n_items; it += warp_stride) {
         Item item;
@@ -441,87 +517,96 @@ __global__ void __launch_bounds__(EVAL_THREADS, 3) ba_rot_eval_kernel(EvalArgs E
         float4 n1 = make_float4(0.f, 0.f, 0.f, 0.f), n2 = n1;
         if (lane < item.count) { n1 = ld_stream(q1); n2 = ld_stream(q2); }
         {
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(E.params + item.cam);   // 46 words: 18 (R) + 27 (nM) + pad
-            uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab[wib][0]);
+            const CamParams* P = E.params + item.cam;
             __syncwarp();
-            dst[lane] = src[lane];
-            if (lane < 14) dst[32 + lane] = src[32 + lane];
+            if (lane < 9) s_R[wib][lane] = P->Rd[lane];
+            if (WRITE && lane < 27) s_M[WRITE ? wib : 0][lane] = P->nM[lane];
             __syncwarp();
         }
 
-        double acc[10];
+        if (!uniform) {
 #pragma unroll
-        for (int k = 0; k < 10; k++) acc[k] = 0;
-        float facc[9];
-#pragma unroll
-        for (int k = 0; k < 9; k++) facc[k] = 0.f;
-        int in_flight = 0;
+            for (int k = 0; k < NMOM; k++) acc[k] = 0;
+        }
+        // two observations per lane in flight ahead of the math
+        float4 m1 = n1, m2 = n2;
+        if (lane + 32 < item.count) { m1 = ld_stream(q1 + 32); m2 = ld_stream(q2 + 32); }
 
         for (int o = lane; o < item.count; o += 32) {
             const float4 p1 = n1, p2 = n2;
-            if (o + 32 < item.count) { n1 = ld_stream(q1 + (o - lane) + 32); n2 = ld_stream(q2 + (o - lane) + 32); }   // prefetch
-            // residual in fp64 (spherical_bundle_adjuster.cpp:896-916)
-            const double X1x = (double)p1.x * d1, X1y = (double)p1.y * d1, X1z = (double)p1.z * d1;
-            const double X2x = (double)p2.x * d2, X2y = (double)p2.y * d2, X2z = (double)p2.z * d2;
-            const double rx = X2x - ((Rs[0] * X1x + Rs[1] * X1y + Rs[2] * X1z) - t0);
-            const double ry = X2y - ((Rs[3] * X1x + Rs[4] * X1y + Rs[5] * X1z) - t1);
-            const double rz = X2z - ((Rs[6] * X1x + Rs[7] * X1y + Rs[8] * X1z) - t2);
+            n1 = m1; n2 = m2;
+            if (o + 64 < item.count) { m1 = ld_stream(q1 + (o - lane) + 64); m2 = ld_stream(q2 + (o - lane) + 64); }   // prefetch
+            // residual in fp64: res = d2*b2 - (d1*R*b1 - t)   (spherical_bundle_adjuster.cpp:896-916)
+            const double bx = (double)p1.x, by = (double)p1.y, bz = (double)p1.z;
+            const double rx = fma(d2, (double)p2.x, t0) - (Rs[0] * bx + Rs[1] * by + Rs[2] * bz);
+            const double ry = fma(d2, (double)p2.y, t1) - (Rs[3] * bx + Rs[4] * by + Rs[5] * bz);
+            const double rz = fma(d2, (double)p2.z, t2) - (Rs[6] * bx + Rs[7] * by + Rs[8] * bz);
             const double s = rx * rx + ry * ry + rz * rz;
             // Huber: rho' = 1 (s <= a^2) or a/sqrt(s); rho = s or 2 a sqrt(s) - a^2
-            double rho = s, rho1 = 1.0;
+            double rho = s, w = 1.0;
             if (huber > 0.0 && s > hub2) {
-                double y = (double)rsqrtf((float)s);
+                float y0;
+                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"((float)s));   // seed, refined to fp64 below
+                double y = (double)y0;
                 y = y * (1.5 - 0.5 * s * y * y);
                 y = y * (1.5 - 0.5 * s * y * y);
-                rho1 = huber * y;
+                w = huber * y;
                 rho = 2.0 * huber * (s * y) - hub2;
             }
-            acc[9] += 0.5 * rho;
-            // Jacobian in fp32: J[a][k] = sum_b nM[k][a][b] * X1[b]
-            const float x1 = p1.x * d1f, y1 = p1.y * d1f, z1 = p1.z * d1f;
-            float J[9];
-#pragma unroll
-            for (int k = 0; k < 3; k++)
-#pragma unroll
-                for (int a = 0; a < 3; a++) J[3 * a + k] = Ms[k * 9 + a * 3] * x1 + Ms[k * 9 + a * 3 + 1] * y1 + Ms[k * 9 + a * 3 + 2] * z1;
-            const float rxf = (float)rx, ryf = (float)ry, rzf = (float)rz, wf = (float)rho1;
-            facc[0] += wf * (J[0] * J[0] + J[3] * J[3] + J[6] * J[6]);
-            facc[1] += wf * (J[0] * J[1] + J[3] * J[4] + J[6] * J[7]);
-            facc[2] += wf * (J[0] * J[2] + J[3] * J[5] + J[6] * J[8]);
-            facc[3] += wf * (J[1] * J[1] + J[4] * J[4] + J[7] * J[7]);
-            facc[4] += wf * (J[1] * J[2] + J[4] * J[5] + J[7] * J[8]);
-            facc[5] += wf * (J[2] * J[2] + J[5] * J[5] + J[8] * J[8]);
-            facc[6] += wf * (J[0] * rxf + J[3] * ryf + J[6] * rzf);
-            facc[7] += wf * (J[1] * rxf + J[4] * ryf + J[7] * rzf);
-            facc[8] += wf * (J[2] * rxf + J[5] * ryf + J[8] * rzf);
-            if (++in_flight == 8) {
-#pragma unroll
-                for (int k = 0; k < 9; k++) { acc[k] += (double)facc[k]; facc[k] = 0.f; }
-                in_flight = 0;
-            }
+            // weighted moments: S += w b b^T (6), C[b][a] += w b_b res_a (9), cost += rho/2
+            const double wx = w * bx, wy = w * by, wz = w * bz;
+            acc[0] = fma(wx, bx, acc[0]); acc[1] = fma(wx, by, acc[1]); acc[2] = fma(wx, bz, acc[2]);
+            acc[3] = fma(wy, by, acc[3]); acc[4] = fma(wy, bz, acc[4]); acc[5] = fma(wz, bz, acc[5]);
+            acc[6] = fma(wx, rx, acc[6]); acc[7] = fma(wx, ry, acc[7]); acc[8] = fma(wx, rz, acc[8]);
+            acc[9] = fma(wy, rx, acc[9]); acc[10] = fma(wy, ry, acc[10]); acc[11] = fma(wy, rz, acc[11]);
+            acc[12] = fma(wz, rx, acc[12]); acc[13] = fma(wz, ry, acc[13]); acc[14] = fma(wz, rz, acc[14]);
+            acc[15] = fma(0.5, rho, acc[15]);
             if (WRITE) {
+                // materialised RAW residual and Jacobian (fp32), in the caller's observation order
                 const int64_t i = item.start + o;
                 const int64_t dst = E.perm ? (int64_t)E.perm[i] : i;
                 if (E.res) {
-                    E.res[3 * dst] = rxf; E.res[3 * dst + 1] = ryf; E.res[3 * dst + 2] = rzf;
+                    E.res[3 * dst] = (float)rx; E.res[3 * dst + 1] = (float)ry; E.res[3 * dst + 2] = (float)rz;
                 }
                 if (E.jac) {
+                    const float* Ms = &s_M[WRITE ? wib : 0][0];
+                    float J[9];
+#pragma unroll
+                    for (int k = 0; k < 3; k++)
+#pragma unroll
+                        for (int a = 0; a < 3; a++) J[3 * a + k] = Ms[k * 9 + a * 3] * p1.x + Ms[k * 9 + a * 3 + 1] * p1.y + Ms[k * 9 + a * 3 + 2] * p1.z;
 #pragma unroll
                     for (int a = 0; a < 9; a++) E.jac[9 * dst + a] = J[a];
                 }
             }
         }
+        if (!uniform) {
 #pragma unroll
-        for (int k = 0; k < 9; k++) acc[k] += (double)facc[k];
+            for (int k = 0; k < NMOM; k++) acc[k] = warp_sum(acc[k]);
+            if (lane == 0) {
+                double* out = E.partial + (size_t)it * NMOM;
 #pragma unroll
-        for (int k = 0; k < 10; k++) acc[k] = warp_sum(acc[k]);
-        if (lane == 0) {
-            double* out = E.partial + (size_t)it * 10;
+                for (int k = 0; k < NMOM; k++) out[k] = acc[k];
+            }
+        }
+    }
+    if (uniform) {
+        // CTA partial: butterfly inside each warp, then the 8 warps in order
+        __shared__ double s_cta[EVAL_WARPS][NMOM];
 #pragma unroll
-            for (int k = 0; k < 10; k++) out[k] = acc[k];
+        for (int k = 0; k < NMOM; k++) acc[k] = warp_sum(acc[k]);
+        if (lane == 0)
+#pragma unroll
+            for (int k = 0; k < NMOM; k++) s_cta[wib][k] = acc[k];
+        __syncthreads();
+        if (threadIdx.x < NMOM) {
+            double t = 0;
+            for (int w = 0; w < EVAL_WARPS; w++) t += s_cta[w][threadIdx.x];
+            E.partial[(size_t)blockIdx.x * NMOM + threadIdx.x] = t;
         }
     }
 
+    if (MODE == 0) return;
     // last CTA to finish folds the partials (classic threadfence reduction ticket)
     __threadfence();
     __syncthreads();
@@ -532,9 +617,9 @@ __global__ void __launch_bounds__(EVAL_THREADS, 3) ba_rot_eval_kernel(EvalArgs E
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    fold_items(E.partial, E.item_ptr, E.n_items, E.n_cam, E.blk_out);
+    fold_items(E.partial, E.item_ptr, E.items ? E.n_items : (int)gridDim.x, E.n_cam, E.params, E.k.d1, E.blk_out);
     if (threadIdx.x == 0) *E.ticket = 0;
-    if (FUSE) {
+    if (MODE == 2) {
         __syncthreads();
         lm_decide(A, sh);
     }
@@ -621,16 +706,13 @@ static void free_problem(sba_ba_problem* p)
 // in one CTA).
 static int pick_item_len(int64_t n_obs, int sm_count)
 {
-    int64_t target_warps = (int64_t)sm_count * 16;
-    int64_t len = (n_obs + target_warps - 1) / target_warps;
+    // ~2 work items per resident warp (3 CTAs x 8 warps per SM) whatever the problem size: small problems
+    // still spread over the chip (32-observation items), huge ones keep the number of item partials
+    // (and the fold over them) bounded.
+    int64_t len = n_obs / ((int64_t)sm_count * 48);
     len = (len + 31) / 32 * 32;
     if (len < 32) len = 32;
-    if (len > 256) {
-        int64_t k = (n_obs + (int64_t)256 * 32768 - 1) / ((int64_t)256 * 32768);
-        if (k < 1) k = 1;
-        if (k > 32) k = 32;
-        len = 256 * k;
-    }
+    if (len > 8192) len = 8192;
     return (int)len;
 }
 
@@ -650,7 +732,7 @@ static LMArrays make_lm_arrays(sba_ba_problem* p)
 {
     LMArrays A;
     A.x = p->x; A.xc = p->xc; A.blk_cur = p->blk_cur; A.blk_cand = p->blk_cand; A.scale = p->scale;
-    A.params = p->params; A.st = p->state; A.n_cam = p->n_cam;
+    A.params = p->params; A.st = p->state; A.n_cam = p->n_cam; A.d1 = 1.0;
     return A;
 }
 
@@ -661,14 +743,28 @@ static int upload_rotations(sba_ba_problem* p, const double* r, double* dst)
     return SBA_OK;
 }
 
-template <bool WRITE, bool FUSE>
-static int launch_eval(sba_ba_problem* p, const EvalArgs& E, const LMArrays& A)
+// One evaluation: the kernel, then (many cameras) the stand-alone fold.  `decide` asks for the fused
+// in-kernel LM decision when the problem allows it; returns whether it was fused.
+constexpr int FOLD_IN_KERNEL_MAX_CAMS = 64;
+
+template <bool WRITE>
+static int launch_eval(sba_ba_problem* p, const EvalArgs& E, const LMArrays& A, bool decide, bool* fused)
 {
+    cudaStream_t st = p->ctx->stream;
+    const bool big = p->n_cam > FOLD_IN_KERNEL_MAX_CAMS;
+    const bool fuse = decide && !big && !p->allreduce;
     prof_begin(p->ctx, SBA_KERNEL_BA_EVAL);
-    ba_rot_eval_kernel<WRITE, FUSE><<<p->eval_blocks, EVAL_THREADS, 0, p->ctx->stream>>>(E, A);
+    if (big) ba_rot_eval_kernel<WRITE, 0><<<p->eval_blocks, EVAL_THREADS, 0, st>>>(E, A);
+    else if (fuse) ba_rot_eval_kernel<WRITE, 2><<<p->eval_blocks, EVAL_THREADS, 0, st>>>(E, A);
+    else ba_rot_eval_kernel<WRITE, 1><<<p->eval_blocks, EVAL_THREADS, 0, st>>>(E, A);
     prof_end(p->ctx, SBA_KERNEL_BA_EVAL);
     SBA_LAUNCHED(p->ctx);
+    if (big) {
+        ba_fold_kernel<<<(p->n_cam + EVAL_WARPS - 1) / EVAL_WARPS, EVAL_THREADS, 0, st>>>(E.partial, E.item_ptr, p->n_cam, E.params, E.k.d1, E.blk_out);
+        SBA_LAUNCHED(p->ctx);
+    }
     SBA_CUDA(cudaGetLastError());
+    if (fused) *fused = fuse;
     return SBA_OK;
 }
 
@@ -797,7 +893,6 @@ int sba::ba_problem_create_impl(sba_ctx* c, const float* b1, const float* b2, co
         P_CUDA(c->cache.get((void**)&p->items, ni * sizeof(Item), false));
         P_CUDA(c->cache.get((void**)&p->item_ptr, (size_t)(n_cam + 1) * sizeof(int), false));
     }
-    P_CUDA(c->cache.get((void**)&p->partial, ni * 10 * sizeof(double), false));
     P_CUDA(c->cache.get((void**)&p->params, (size_t)n_cam * sizeof(CamParams), false));
     P_CUDA(c->cache.get((void**)&p->x, (size_t)n_cam * 3 * sizeof(double), false));
     P_CUDA(c->cache.get((void**)&p->xc, (size_t)n_cam * 3 * sizeof(double), false));
@@ -821,6 +916,8 @@ int sba::ba_problem_create_impl(sba_ctx* c, const float* b1, const float* b2, co
     int want = (p->n_items + EVAL_WARPS - 1) / EVAL_WARPS;
     if (want < 1) want = 1;
     p->eval_blocks = std::min(want, c->sm_count * 8);
+    // uniform layout: one partial per CTA; otherwise one per work item
+    P_CUDA(c->cache.get((void**)&p->partial, (size_t)std::max<size_t>(ni, (size_t)p->eval_blocks) * NMOM * sizeof(double), false));
     *out = p;
     return SBA_OK;
 #undef P_CUDA
@@ -855,7 +952,7 @@ int sba_ba_rot_eval(sba_ba_problem* p, const double* r, const double t[3], doubl
     const int n_cam = p->n_cam;
     SBA_CUDA(cudaStreamSynchronize(st));  // h_x reuse
     SBA_TRY(upload_rotations(p, r, p->xc));
-    ba_cam_params_kernel<<<(n_cam + 127) / 128, 128, 0, st>>>(p->xc, n_cam, p->params);
+    ba_cam_params_kernel<<<(n_cam + 127) / 128, 128, 0, st>>>(p->xc, n_cam, d1, p->params);
     SBA_LAUNCHED(c);
     float *d_res, *d_jac;
     double *d_H, *d_g, *d_cost;
@@ -866,8 +963,9 @@ int sba_ba_rot_eval(sba_ba_problem* p, const double* r, const double t[3], doubl
     SBA_TRY(stage_out(c, cost, (size_t)n_cam, mem, SCR_OUT4, &d_cost));
     EvalArgs E = make_eval_args(p, t, d1, d2, huber, d_res, d_jac, p->blk_cand);
     LMArrays A = make_lm_arrays(p);
-    if (d_res || d_jac) SBA_TRY((launch_eval<true, false>(p, E, A)));
-    else SBA_TRY((launch_eval<false, false>(p, E, A)));
+    A.d1 = d1;
+    if (d_res || d_jac) SBA_TRY(launch_eval<true>(p, E, A, false, nullptr));
+    else SBA_TRY(launch_eval<false>(p, E, A, false, nullptr));
     if (p->allreduce) {
         if (p->allreduce(p->blk_cand, (int64_t)n_cam * 10, p->allreduce_user) != 0) {
             sba::set_error("allreduce callback failed");
@@ -899,10 +997,11 @@ int sba_ba_rot_solve(sba_ba_problem* p, double* r_inout, const double t[3], doub
     init.radius = 1e4; init.dec_factor = 2.0; init.max_iter = max_iter; init.phase = 0;
     *p->h_state = init;
     SBA_CUDA(cudaMemcpyAsync(p->state, p->h_state, sizeof(LMState), cudaMemcpyHostToDevice, st));
-    ba_cam_params_kernel<<<(n_cam + 127) / 128, 128, 0, st>>>(p->xc, n_cam, p->params);
+    ba_cam_params_kernel<<<(n_cam + 127) / 128, 128, 0, st>>>(p->xc, n_cam, d1, p->params);
     SBA_LAUNCHED(c);
     EvalArgs E = make_eval_args(p, t, d1, d2, huber, nullptr, nullptr, p->blk_cand);
     LMArrays A = make_lm_arrays(p);
+    A.d1 = d1;
 
     // Evaluations are enqueued in chunks; kernels of a chunk that start after convergence return
     // immediately (state.done), and the host looks at the state once per chunk.
@@ -913,16 +1012,15 @@ int sba_ba_rot_solve(sba_ba_problem* p, double* r_inout, const double t[3], doub
     while (!done && launched < max_evals) {
         int n = std::min(chunk, max_evals - launched);
         for (int k = 0; k < n; k++) {
-            if (p->allreduce) {
-                SBA_TRY((launch_eval<false, false>(p, E, A)));
-                if (p->allreduce(p->blk_cand, (int64_t)n_cam * 10, p->allreduce_user) != 0) {
+            bool fused = false;
+            SBA_TRY(launch_eval<false>(p, E, A, true, &fused));
+            if (!fused) {
+                if (p->allreduce && p->allreduce(p->blk_cand, (int64_t)n_cam * 10, p->allreduce_user) != 0) {
                     sba::set_error("allreduce callback failed");
                     return SBA_ERR_COMM;
                 }
                 ba_decide_kernel<<<1, EVAL_THREADS, 0, st>>>(A);
                 SBA_LAUNCHED(c);
-            } else {
-                SBA_TRY((launch_eval<false, true>(p, E, A)));
             }
         }
         launched += n;
@@ -961,7 +1059,7 @@ int sba_ba_rot_eval_timed(sba_ba_problem* p, const double* r, const double t[3],
     const int n_cam = p->n_cam;
     SBA_CUDA(cudaStreamSynchronize(st));
     SBA_TRY(upload_rotations(p, r, p->xc));
-    ba_cam_params_kernel<<<(n_cam + 127) / 128, 128, 0, st>>>(p->xc, n_cam, p->params);
+    ba_cam_params_kernel<<<(n_cam + 127) / 128, 128, 0, st>>>(p->xc, n_cam, d1, p->params);
     SBA_LAUNCHED(c);
     float *d_res = nullptr, *d_jac = nullptr;
     if (materialise) {
@@ -972,17 +1070,18 @@ int sba_ba_rot_eval_timed(sba_ba_problem* p, const double* r, const double t[3],
     }
     EvalArgs E = make_eval_args(p, t, d1, d2, huber, d_res, d_jac, p->blk_cand);
     LMArrays A = make_lm_arrays(p);
+    A.d1 = d1;
     cudaEvent_t e0, e1;
     SBA_CUDA(cudaEventCreate(&e0));
     SBA_CUDA(cudaEventCreate(&e1));
     for (int k = 0; k < 3; k++) {
-        if (materialise) SBA_TRY((launch_eval<true, false>(p, E, A)));
-        else SBA_TRY((launch_eval<false, false>(p, E, A)));
+        if (materialise) SBA_TRY(launch_eval<true>(p, E, A, false, nullptr));
+        else SBA_TRY(launch_eval<false>(p, E, A, false, nullptr));
     }
     SBA_CUDA(cudaEventRecord(e0, st));
     for (int k = 0; k < iters; k++) {
-        if (materialise) SBA_TRY((launch_eval<true, false>(p, E, A)));
-        else SBA_TRY((launch_eval<false, false>(p, E, A)));
+        if (materialise) SBA_TRY(launch_eval<true>(p, E, A, false, nullptr));
+        else SBA_TRY(launch_eval<false>(p, E, A, false, nullptr));
     }
     SBA_CUDA(cudaEventRecord(e1, st));
     SBA_CUDA(cudaEventSynchronize(e1));
