@@ -435,11 +435,12 @@ __device__ void fold_items(const double* __restrict__ partial, const int* __rest
 // Stand-alone fold for problems with many cameras: one warp per camera over the whole grid (the
 // in-kernel fold runs in a single CTA, which is only right when there are few cameras).
 __global__ void __launch_bounds__(EVAL_THREADS) ba_fold_kernel(const double* __restrict__ partial, const int* __restrict__ item_ptr, int n_cam,
-                                                              const CamParams* __restrict__ params, double d1, double* __restrict__ blk)
+                                                              const CamParams* __restrict__ params, double d1, double* __restrict__ blk,
+                                                              const int* __restrict__ done)
 {
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * EVAL_WARPS + (threadIdx.x >> 5);
-    if (c >= n_cam) return;
+    if (c >= n_cam || (done && *done)) return;
     double acc[NMOM];
 #pragma unroll
     for (int k = 0; k < NMOM; k++) acc[k] = 0;
@@ -465,6 +466,7 @@ struct EvalArgs {
     double* partial;
     double* blk_out;
     unsigned int* ticket;
+    const int* done;  // LM solve: skip the whole evaluation once the solver has converged (NULL = always run)
     float* res;  // optional materialised outputs (caller order)
     float* jac;
     SolveConsts k;
@@ -488,7 +490,7 @@ __global__ void __launch_bounds__(EVAL_THREADS, 3) ba_rot_eval_kernel(EvalArgs E
     // -d1*dR/dr_k (27 fp32).  Shared memory (broadcast reads) instead of registers: three CTAs per SM.
     __shared__ __align__(16) double s_R[EVAL_WARPS][10];
     __shared__ __align__(16) float s_M[WRITE ? EVAL_WARPS : 1][28];
-    if (MODE == 2 && A.st->done) return;  // converged earlier in this launch chunk
+    if (E.done && *E.done) return;  // converged earlier in this launch chunk
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warp_global = blockIdx.x * EVAL_WARPS + wib;
@@ -722,7 +724,7 @@ static EvalArgs make_eval_args(sba_ba_problem* p, const double t[3], double d1, 
     E.b1 = p->b1; E.b2 = p->b2; E.perm = p->perm; E.items = p->items; E.item_ptr = p->item_ptr;
     E.item_len = p->item_len; E.n_obs = (int)p->n_obs;
     E.n_items = p->n_items; E.n_cam = p->n_cam; E.params = p->params; E.partial = p->partial;
-    E.blk_out = blk_out; E.ticket = p->ticket; E.res = res; E.jac = jac;
+    E.blk_out = blk_out; E.ticket = p->ticket; E.res = res; E.jac = jac; E.done = nullptr;
     E.k.t[0] = t[0]; E.k.t[1] = t[1]; E.k.t[2] = t[2];
     E.k.d1 = d1; E.k.d2 = d2; E.k.huber = huber;
     return E;
@@ -760,7 +762,7 @@ static int launch_eval(sba_ba_problem* p, const EvalArgs& E, const LMArrays& A, 
     prof_end(p->ctx, SBA_KERNEL_BA_EVAL);
     SBA_LAUNCHED(p->ctx);
     if (big) {
-        ba_fold_kernel<<<(p->n_cam + EVAL_WARPS - 1) / EVAL_WARPS, EVAL_THREADS, 0, st>>>(E.partial, E.item_ptr, p->n_cam, E.params, E.k.d1, E.blk_out);
+        ba_fold_kernel<<<(p->n_cam + EVAL_WARPS - 1) / EVAL_WARPS, EVAL_THREADS, 0, st>>>(E.partial, E.item_ptr, p->n_cam, E.params, E.k.d1, E.blk_out, E.done);
         SBA_LAUNCHED(p->ctx);
     }
     SBA_CUDA(cudaGetLastError());
@@ -1000,6 +1002,7 @@ int sba_ba_rot_solve(sba_ba_problem* p, double* r_inout, const double t[3], doub
     ba_cam_params_kernel<<<(n_cam + 127) / 128, 128, 0, st>>>(p->xc, n_cam, d1, p->params);
     SBA_LAUNCHED(c);
     EvalArgs E = make_eval_args(p, t, d1, d2, huber, nullptr, nullptr, p->blk_cand);
+    E.done = &p->state->done;
     LMArrays A = make_lm_arrays(p);
     A.d1 = d1;
 

@@ -148,6 +148,10 @@ struct sba_ctx {
     bool profiling = false;
     cudaEvent_t prof_e0[3] = {nullptr, nullptr, nullptr}, prof_e1[3] = {nullptr, nullptr, nullptr};
     bool prof_valid[3] = {false, false, false};
+    // second stream + events: bulk host->device image uploads overlap compute in sba_pair_rotation
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_ev[2] = {nullptr, nullptr};
+    cudaEvent_t main_ev = nullptr;
 };
 
 namespace sba {

@@ -82,6 +82,10 @@ int sba_ctx_destroy(sba_ctx* c)
         if (c->prof_e0[k]) cudaEventDestroy(c->prof_e0[k]);
         if (c->prof_e1[k]) cudaEventDestroy(c->prof_e1[k]);
     }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (int k = 0; k < 2; k++)
+        if (c->copy_ev[k]) cudaEventDestroy(c->copy_ev[k]);
+    if (c->main_ev) cudaEventDestroy(c->main_ev);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return SBA_OK;

@@ -29,11 +29,16 @@ int sba_pair_rotation(sba_ctx* c, const uint8_t* erp_left, const uint8_t* erp_ri
     result->rotation[0] = r0[0]; result->rotation[1] = r0[1]; result->rotation[2] = r0[2];
     const int D = SBA_MEM_DEVICE;
 
-    // ---- inputs to the device (one async copy each when they are host buffers)
+    // ---- inputs to the device.  Host mode: descriptors and keypoints (8.6 MB at C2) go first on the
+    //      compute stream; the two images (44 MB) are uploaded on a second stream and only the remap,
+    //      which runs last, waits for them -- the matcher and the bundle adjustment hide the PCIe time.
     const size_t im_bytes = (size_t)w * h * 3, strip_bytes = (size_t)cube_size * 6 * cube_size * 3;
     const uint8_t *d_im0 = nullptr, *d_im1 = nullptr;
     const float *d_desc0, *d_desc1, *d_key0, *d_key1;
-    if (erp_left) {
+    const bool overlap = erp_left && mem == SBA_MEM_HOST;
+    if (overlap) {
+        // (image uploads are queued below, after the small inputs)
+    } else if (erp_left) {
         SBA_TRY(stage_in(c, erp_left, im_bytes, mem, SCR_PIPE_IM0, &d_im0));
         SBA_TRY(stage_in(c, erp_right, im_bytes, mem, SCR_PIPE_IM1, &d_im1));
     }
@@ -41,23 +46,48 @@ int sba_pair_rotation(sba_ctx* c, const uint8_t* erp_left, const uint8_t* erp_ri
     SBA_TRY(stage_in(c, desc_right, (size_t)n_right * dim, mem, SCR_PIPE_DESC1, &d_desc1));
     SBA_TRY(stage_in(c, key_left_xy, (size_t)n_left * 2, mem, SCR_PIPE_KEY0, &d_key0));
     SBA_TRY(stage_in(c, key_right_xy, (size_t)n_right * 2, mem, SCR_PIPE_KEY1, &d_key1));
+    if (overlap) {
+        if (!c->copy_stream) {
+            SBA_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+            SBA_CUDA(cudaEventCreateWithFlags(&c->copy_ev[0], cudaEventDisableTiming));
+            SBA_CUDA(cudaEventCreateWithFlags(&c->copy_ev[1], cudaEventDisableTiming));
+            SBA_CUDA(cudaEventCreateWithFlags(&c->main_ev, cudaEventDisableTiming));
+        }
+        SBA_TRY(c->scratch[SCR_PIPE_IM0].ensure(im_bytes, st));
+        SBA_TRY(c->scratch[SCR_PIPE_IM1].ensure(im_bytes, st));
+        // the staging buffers may still be read by work already queued on the compute stream
+        SBA_CUDA(cudaEventRecord(c->main_ev, st));
+        SBA_CUDA(cudaStreamWaitEvent(c->copy_stream, c->main_ev, 0));
+        SBA_CUDA(cudaMemcpyAsync(c->scratch[SCR_PIPE_IM0].p, erp_left, im_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        SBA_CUDA(cudaEventRecord(c->copy_ev[0], c->copy_stream));
+        SBA_CUDA(cudaMemcpyAsync(c->scratch[SCR_PIPE_IM1].p, erp_right, im_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        SBA_CUDA(cudaEventRecord(c->copy_ev[1], c->copy_stream));
+        d_im0 = c->scratch[SCR_PIPE_IM0].as<uint8_t>();
+        d_im1 = c->scratch[SCR_PIPE_IM1].as<uint8_t>();
+    }
 
     // ---- equi2cube::get_all on both images (the strips feed the host-side detector of the reference;
-    //      they stay on the device unless the caller asks for them)
-    if (erp_left) {
+    //      they stay on the device unless the caller asks for them).  Enqueued now when the images are
+    //      already resident, after everything else when their upload is still in flight.
+    auto remap_both = [&]() -> int {
+        if (!erp_left) return SBA_OK;
         uint8_t *d_s0, *d_s1;
         const bool dev_out = (mem == SBA_MEM_DEVICE);
         if (dev_out && strip_left_out) d_s0 = strip_left_out;
         else { SBA_TRY(c->scratch[SCR_PIPE_STRIP0].ensure(strip_bytes, st)); d_s0 = c->scratch[SCR_PIPE_STRIP0].as<uint8_t>(); }
         if (dev_out && strip_right_out) d_s1 = strip_right_out;
         else { SBA_TRY(c->scratch[SCR_PIPE_STRIP1].ensure(strip_bytes, st)); d_s1 = c->scratch[SCR_PIPE_STRIP1].as<uint8_t>(); }
-        SBA_TRY(sba_equi2cube(c, d_im0, w, h, 1, cube_size, d_s0, D));
-        SBA_TRY(sba_equi2cube(c, d_im1, w, h, 1, cube_size, d_s1, D));
+        if (overlap) SBA_CUDA(cudaStreamWaitEvent(st, c->copy_ev[0], 0));
+        SBA_TRY(sba_equi2cube(c, d_im0, w, h, 1, cube_size, d_s0, SBA_MEM_DEVICE));
+        if (overlap) SBA_CUDA(cudaStreamWaitEvent(st, c->copy_ev[1], 0));
+        SBA_TRY(sba_equi2cube(c, d_im1, w, h, 1, cube_size, d_s1, SBA_MEM_DEVICE));
         if (!dev_out) {
             SBA_TRY(copy_out(c, strip_left_out, d_s0, strip_bytes, mem));
             SBA_TRY(copy_out(c, strip_right_out, d_s1, strip_bytes, mem));
         }
-    }
+        return SBA_OK;
+    };
+    if (!overlap) SBA_TRY(remap_both());
 
     // ---- feature_matcher::match_two_image
     const size_t nq = (size_t)(n_left > 0 ? n_left : 1);
@@ -74,7 +104,10 @@ int sba_pair_rotation(sba_ctx* c, const uint8_t* erp_left, const uint8_t* erp_ri
     if (query_idx_out) SBA_CUDA(cudaMemcpyAsync(query_idx_out, d_qi, (size_t)n * 4, mem == SBA_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
     if (train_idx_out) SBA_CUDA(cudaMemcpyAsync(train_idx_out, d_ti, (size_t)n * 4, mem == SBA_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
     if (dist_out) SBA_CUDA(cudaMemcpyAsync(dist_out, d_dist, (size_t)n * 4, mem == SBA_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
-    if (n == 0) return finish(c, mem);
+    if (n == 0) {
+        if (overlap) SBA_TRY(remap_both());
+        return finish(c, mem);
+    }
 
     // ---- matched keypoints: gather, cube strip -> ERP pixel, pixel -> bearing (left and right in one
     //      2n-point batch per stage)
@@ -100,6 +133,7 @@ int sba_pair_rotation(sba_ctx* c, const uint8_t* erp_left, const uint8_t* erp_ri
     result->lm_termination = sum.termination;
     result->initial_cost = sum.initial_cost;
     result->final_cost = sum.final_cost;
+    if (overlap) SBA_TRY(remap_both());
     return finish(c, mem);
 }
 
