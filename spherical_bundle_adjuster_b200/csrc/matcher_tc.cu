@@ -313,51 +313,55 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         __syncwarp();
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
-            int tb = tb0, seg = 0, s = 0;
-            uint32_t ring_phase = 0;
-            bool new_seg = true;
-            const uint32_t sa = smem_u32(sA);
-            uint64_t dA_hi[2], dA_lo[2];
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                // row-half h of the query block: rows 128h.. of each A k-block
-                dA_hi[h] = make_smem_desc(sa + h * (128 * 128));
-                dA_lo[h] = make_smem_desc(sa + A_KBLOCK_BYTES + h * (128 * 128));
+        // The whole warp walks the tile loop in lock-step (waits included) so every descriptor is
+        // warp-uniform and lives in uniform registers; only the tcgen05 instructions themselves are
+        // issued by one elected lane.
+        uint32_t is_leader;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(is_leader));
+        int tb = tb0, seg = 0, s = 0;
+        uint32_t ring_phase = 0;
+        bool new_seg = true;
+        const uint32_t sa = smem_u32(sA);
+        // row-half h of the query block: rows 128h.. of each A k-block
+        const uint64_t dA_hi0 = make_smem_desc(sa), dA_hi1 = make_smem_desc(sa + 128 * 128);
+        const uint64_t dA_lo0 = make_smem_desc(sa + A_KBLOCK_BYTES), dA_lo1 = make_smem_desc(sa + A_KBLOCK_BYTES + 128 * 128);
+        const uint64_t dB0 = make_smem_desc(smem_u32(sB));
+        for (int n = 0; n < n_tiles; n++) {
+            if (new_seg) {
+                mbar_wait(a_full, seg & 1);
+                seg++;
             }
-            const uint64_t dB0 = make_smem_desc(smem_u32(sB));
-            for (int n = 0; n < n_tiles; n++) {
-                if (new_seg) {
-                    mbar_wait(a_full, seg & 1);
-                    seg++;
-                }
-                const int acc = n & 1;
-                mbar_wait(acc_empty + acc, (uint32_t)(((n >> 1) & 1) ^ 1));
-                mbar_wait(b_full + s, ring_phase);
-                tcgen05_fence_after();
-                // descriptors address 16-byte units: stage stride and k-block stride are plain adds
-                const uint64_t dB_hi = dB0 + (uint64_t)(s * ((2 * B_KBLOCK_BYTES) >> 4));
-                const uint64_t dB_lo = dB_hi + (B_KBLOCK_BYTES >> 4);
+            const int acc = n & 1;
+            mbar_wait(acc_empty + acc, (uint32_t)(((n >> 1) & 1) ^ 1));
+            mbar_wait(b_full + s, ring_phase);
+            tcgen05_fence_after();
+            // descriptors address 16-byte units: stage stride and k-block stride are plain adds
+            const uint64_t dB_hi = dB0 + (uint64_t)(s * ((2 * B_KBLOCK_BYTES) >> 4));
+            const uint64_t dB_lo = dB_hi + (B_KBLOCK_BYTES >> 4);
+            const uint32_t d0 = tmem_base + (uint32_t)(acc * ACC_COLS), d1 = d0 + BN;
+            if (is_leader) {
+                // hi.hi + hi.lo + lo.hi ; each 64-wide k-block is four K=16 steps, 32 B apart
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS + h * BN);
-                    // hi.hi + hi.lo + lo.hi ; each 64-wide k-block is four K=16 steps, 32 B apart
+                for (int k = 0; k < 4; k++) umma_bf16(d0, dA_hi0 + 2 * k, dB_hi + 2 * k, IDESC, k > 0);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) umma_bf16(d_tmem, dA_hi[h] + 2 * k, dB_hi + 2 * k, IDESC, k > 0);
+                for (int k = 0; k < 4; k++) umma_bf16(d0, dA_hi0 + 2 * k, dB_lo + 2 * k, IDESC, 1);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) umma_bf16(d_tmem, dA_hi[h] + 2 * k, dB_lo + 2 * k, IDESC, 1);
+                for (int k = 0; k < 4; k++) umma_bf16(d0, dA_lo0 + 2 * k, dB_hi + 2 * k, IDESC, 1);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) umma_bf16(d_tmem, dA_lo[h] + 2 * k, dB_hi + 2 * k, IDESC, 1);
-                }
+                for (int k = 0; k < 4; k++) umma_bf16(d1, dA_hi1 + 2 * k, dB_hi + 2 * k, IDESC, k > 0);
+#pragma unroll
+                for (int k = 0; k < 4; k++) umma_bf16(d1, dA_hi1 + 2 * k, dB_lo + 2 * k, IDESC, 1);
+#pragma unroll
+                for (int k = 0; k < 4; k++) umma_bf16(d1, dA_lo1 + 2 * k, dB_hi + 2 * k, IDESC, 1);
                 tcgen05_commit(b_empty + s);     // B stage free once these MMAs have read it
                 tcgen05_commit(acc_full + acc);  // accumulator ready for the epilogue
-                if (++s == STAGES) { s = 0; ring_phase ^= 1; }
-                new_seg = (++tb == ntb);
-                if (new_seg) tb = 0;
-                if (new_seg || n + 1 == n_tiles) tcgen05_commit(a_empty);   // last tile of this query block in the span
             }
+            if (++s == STAGES) { s = 0; ring_phase ^= 1; }
+            new_seg = (++tb == ntb);
+            if (new_seg) tb = 0;
+            if ((new_seg || n + 1 == n_tiles) && is_leader) tcgen05_commit(a_empty);   // last tile of this query block in the span
+            __syncwarp();
         }
-        __syncwarp();
     } else if (warp >= 4) {
         // ===== epilogue warps: TMEM lane quarter = warp % 4, column slice = (warp - 4) / 4 =====
         const int quarter = warp & 3;
