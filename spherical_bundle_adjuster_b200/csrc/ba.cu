@@ -459,7 +459,8 @@ struct EvalArgs {
     const Item* items;     // NULL = uniform layout: one camera, item i covers [i*item_len, min(n_obs, (i+1)*item_len))
     const int* item_ptr;   // NULL with the uniform layout
     int item_len;
-    int n_obs;
+    int n_obs;              // observation count, or the CAPACITY when n_obs_dev is given
+    const int* n_obs_dev;   // optional: the actual count lives on the device (fused pair pipeline)
     int n_items;
     int n_cam;
     const CamParams* params;
@@ -498,6 +499,7 @@ __global__ void __launch_bounds__(EVAL_THREADS, 3) ba_rot_eval_kernel(EvalArgs E
     const double d2 = E.k.d2, huber = E.k.huber, hub2 = huber * huber;
     const double t0 = E.k.t[0], t1 = E.k.t[1], t2 = E.k.t[2];
     const double* Rs = &s_R[wib][0];
+    const int n_obs = E.n_obs_dev ? min(E.n_obs, *E.n_obs_dev) : E.n_obs;
     // Uniform layout (one camera): a warp keeps its moments across all of its work items and the CTA
     // publishes ONE partial, so the final fold is over gridDim.x entries instead of n_items.
     const bool uniform = (E.items == nullptr);
@@ -510,7 +512,7 @@ __global__ void __launch_bounds__(EVAL_THREADS, 3) ba_rot_eval_kernel(EvalArgs E
         if (E.items) item = E.items[it];
         else {
             item.start = (int64_t)it * E.item_len;
-            item.count = min(E.item_len, E.n_obs - it * E.item_len);
+            item.count = min(E.item_len, n_obs - it * E.item_len);
             item.cam = 0;
         }
         // first observation of every lane goes in flight before the tables are staged
@@ -687,6 +689,7 @@ struct sba_ba_problem {
     void* allreduce_user = nullptr;
     int eval_blocks = 1;
     int item_len = 32;
+    const int* n_obs_dev = nullptr;   // actual observation count on the device (n_obs is then the capacity)
     bool borrowed = false;   // b1/b2 belong to the caller (fused pipeline): not returned to the cache
 };
 
@@ -722,7 +725,7 @@ static EvalArgs make_eval_args(sba_ba_problem* p, const double t[3], double d1, 
 {
     EvalArgs E;
     E.b1 = p->b1; E.b2 = p->b2; E.perm = p->perm; E.items = p->items; E.item_ptr = p->item_ptr;
-    E.item_len = p->item_len; E.n_obs = (int)p->n_obs;
+    E.item_len = p->item_len; E.n_obs = (int)p->n_obs; E.n_obs_dev = p->n_obs_dev;
     E.n_items = p->n_items; E.n_cam = p->n_cam; E.params = p->params; E.partial = p->partial;
     E.blk_out = blk_out; E.ticket = p->ticket; E.res = res; E.jac = jac; E.done = nullptr;
     E.k.t[0] = t[0]; E.k.t[1] = t[1]; E.k.t[2] = t[2];
@@ -776,7 +779,7 @@ extern "C" {
 
 namespace sba {
 int ba_problem_create_impl(sba_ctx* c, const float* b1, const float* b2, const int32_t* cam, int64_t n_obs, int n_cam, int mem, bool borrow,
-                           sba_ba_problem** out);
+                           const int* d_n_obs, sba_ba_problem** out);
 }
 
 extern "C" {
@@ -784,15 +787,18 @@ extern "C" {
 int sba_ba_problem_create(sba_ctx* c, const float* b1, const float* b2, const int32_t* cam, int64_t n_obs, int n_cam, int mem,
                           sba_ba_problem** out)
 {
-    return sba::ba_problem_create_impl(c, b1, b2, cam, n_obs, n_cam, mem, false, out);
+    return sba::ba_problem_create_impl(c, b1, b2, cam, n_obs, n_cam, mem, false, nullptr, out);
 }
 
 }  // extern "C"
 
 // `borrow` (device pointers, no camera sort): the problem reads the caller's b1/b2 in place; they must
 // stay valid and unchanged until the problem is destroyed.
+// `d_n_obs` (borrowed single-camera problems only): the real observation count is read from device
+// memory by the kernels and n_obs is just the capacity -- lets a caller enqueue the whole solve without
+// first fetching the count to the host.
 int sba::ba_problem_create_impl(sba_ctx* c, const float* b1, const float* b2, const int32_t* cam, int64_t n_obs, int n_cam, int mem,
-                                bool borrow, sba_ba_problem** out)
+                                bool borrow, const int* d_n_obs, sba_ba_problem** out)
 {
     SBA_CHECK_ARG(c && out && n_obs >= 0 && n_cam >= 1 && n_obs < ((int64_t)1 << 31));
     SBA_CHECK_ARG(n_obs == 0 || (b1 && b2));
@@ -815,6 +821,7 @@ int sba::ba_problem_create_impl(sba_ctx* c, const float* b1, const float* b2, co
     size_t nb = (size_t)(n_obs ? n_obs : 1) * sizeof(float4);
     const bool need_sort = (cam != nullptr && n_cam > 1 && n_obs > 0);
     p->borrowed = borrow && !need_sort && mem == SBA_MEM_DEVICE && n_obs > 0;
+    if (p->borrowed && n_cam == 1) p->n_obs_dev = d_n_obs;
     if (p->borrowed) {
         p->b1 = (float4*)b1;
         p->b2 = (float4*)b2;

@@ -210,7 +210,7 @@ inline void prof_end(sba_ctx* c, int id)
 
 // ba.cu: problem creation with the option to read the caller's device bearings in place
 int ba_problem_create_impl(sba_ctx* c, const float* b1, const float* b2, const int32_t* cam, int64_t n_obs, int n_cam, int mem, bool borrow,
-                           sba_ba_problem** out);
+                           const int* d_n_obs, sba_ba_problem** out);
 
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

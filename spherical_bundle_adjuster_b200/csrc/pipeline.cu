@@ -9,8 +9,34 @@
 // descriptors).  Everything between the input copy and the result copy stays on the device; the only
 // host round trips are the match count (sizes the BA problem) and the LM state once per launch chunk.
 #include "common.cuh"
+#include "geometry.cuh"
 
 using namespace sba;
+
+namespace sba {
+
+// Matched keypoints -> BA bearings in one pass (equi2cube_surf.cpp:96-113 gather + cube2equi_pixel, then
+// spherical_bundle_adjuster.cpp:271-298 pixel -> bearing).  The match count is read from device memory
+// so the host never waits for it; threads past the count write nothing.
+__global__ void pair_points_kernel(const float2* __restrict__ key_l, const float2* __restrict__ key_r, const int32_t* __restrict__ qi,
+                                   const int32_t* __restrict__ ti, const int32_t* __restrict__ d_n, int cap, int cs, int w, int h,
+                                   float4* __restrict__ b1, float4* __restrict__ b2)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = min(cap, *d_n);
+    if (i >= n) return;
+    const float2 kl = key_l[qi[i]], kr = key_r[ti[i]];
+    float ex, ey;
+    double x, y, z;
+    cube2equi_point(kl.x, kl.y, cs, w, h, &ex, &ey);
+    pixel_to_bearing(ex, ey, (double)w, (double)h, &x, &y, &z);
+    b1[i] = make_float4((float)x, (float)y, (float)z, 0.f);
+    cube2equi_point(kr.x, kr.y, cs, w, h, &ex, &ey);
+    pixel_to_bearing(ex, ey, (double)w, (double)h, &x, &y, &z);
+    b2[i] = make_float4((float)x, (float)y, (float)z, 0.f);
+}
+
+}  // namespace sba
 
 extern "C" {
 
@@ -89,50 +115,53 @@ int sba_pair_rotation(sba_ctx* c, const uint8_t* erp_left, const uint8_t* erp_ri
     };
     if (!overlap) SBA_TRY(remap_both());
 
-    // ---- feature_matcher::match_two_image
+    // ---- feature_matcher::match_two_image.  The match list goes straight into the caller's device
+    //      buffers when there are any; the count stays on the device until the very end.
     const size_t nq = (size_t)(n_left > 0 ? n_left : 1);
     SBA_TRY(c->scratch[SCR_PIPE_MATCH].ensure(nq * 12 + 64, st));
-    int32_t* d_qi = c->scratch[SCR_PIPE_MATCH].as<int32_t>();
-    int32_t* d_ti = d_qi + nq;
-    float* d_dist = (float*)(d_ti + nq);
-    int32_t* d_n = (int32_t*)(d_dist + nq);
+    int32_t* s_qi = c->scratch[SCR_PIPE_MATCH].as<int32_t>();
+    int32_t* s_ti = s_qi + nq;
+    float* s_dist = (float*)(s_ti + nq);
+    int32_t* d_n = (int32_t*)(s_dist + nq);
+    const bool dev_lists = (mem == SBA_MEM_DEVICE);
+    int32_t* d_qi = (dev_lists && query_idx_out) ? query_idx_out : s_qi;
+    int32_t* d_ti = (dev_lists && train_idx_out) ? train_idx_out : s_ti;
+    float* d_dist = (dev_lists && dist_out) ? dist_out : s_dist;
     SBA_TRY(sba_knn2_ratio(c, d_desc0, n_left, d_desc1, n_right, dim, ratio, d_qi, d_ti, d_dist, d_n, nullptr, nullptr, D, SBA_MATCH_AUTO));
-    SBA_CUDA(cudaMemcpyAsync(c->pinned_i32, d_n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    SBA_CUDA(cudaStreamSynchronize(st));
+    SBA_CUDA(cudaMemcpyAsync(c->pinned_i32, d_n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));   // read after the solve's synchronise
+
+    double r[3] = {r0[0], r0[1], r0[2]};
+    if (n_left > 0 && n_right > 0) {
+        // ---- matched keypoints -> bearings (capacity n_left; the kernel stops at the device-side count)
+        SBA_TRY(c->scratch[SCR_PIPE_BEAR].ensure((size_t)2 * n_left * 4 * sizeof(float), st));
+        float* d_b = c->scratch[SCR_PIPE_BEAR].as<float>();        // [cap] float4 left bearings, [cap] float4 right bearings
+        pair_points_kernel<<<(n_left + 255) / 256, 256, 0, st>>>((const float2*)d_key0, (const float2*)d_key1, d_qi, d_ti, d_n, n_left, cube_size,
+                                                                w, h, (float4*)d_b, (float4*)d_b + n_left);
+        SBA_LAUNCHED(c);
+
+        // ---- rotation-only bundle adjustment on the bearings in place
+        sba_ba_problem* prob = nullptr;
+        SBA_TRY(ba_problem_create_impl(c, d_b, d_b + (size_t)4 * n_left, nullptr, n_left, 1, D, /*borrow=*/true, d_n, &prob));
+        sba_solve_summary sum;
+        int status = sba_ba_rot_solve(prob, r, t, d1, d2, huber_delta, max_iter, &sum);
+        sba_ba_problem_destroy(prob);
+        SBA_TRY(status);
+        result->lm_iterations = sum.iterations;
+        result->lm_termination = sum.termination;
+        result->initial_cost = sum.initial_cost;
+        result->final_cost = sum.final_cost;
+    } else {
+        SBA_CUDA(cudaStreamSynchronize(st));
+    }
     const int n = c->pinned_i32[0];
     result->n_matches = n;
-    if (query_idx_out) SBA_CUDA(cudaMemcpyAsync(query_idx_out, d_qi, (size_t)n * 4, mem == SBA_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
-    if (train_idx_out) SBA_CUDA(cudaMemcpyAsync(train_idx_out, d_ti, (size_t)n * 4, mem == SBA_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
-    if (dist_out) SBA_CUDA(cudaMemcpyAsync(dist_out, d_dist, (size_t)n * 4, mem == SBA_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
-    if (n == 0) {
-        if (overlap) SBA_TRY(remap_both());
-        return finish(c, mem);
+    if (n > 0) { result->rotation[0] = r[0]; result->rotation[1] = r[1]; result->rotation[2] = r[2]; }
+    else { result->lm_iterations = 0; result->lm_termination = 0; result->initial_cost = result->final_cost = 0.0; }
+    if (!dev_lists) {
+        SBA_TRY(copy_out(c, query_idx_out, (const int32_t*)d_qi, (size_t)n, mem));
+        SBA_TRY(copy_out(c, train_idx_out, (const int32_t*)d_ti, (size_t)n, mem));
+        SBA_TRY(copy_out(c, dist_out, (const float*)d_dist, (size_t)n, mem));
     }
-
-    // ---- matched keypoints: gather, cube strip -> ERP pixel, pixel -> bearing (left and right in one
-    //      2n-point batch per stage)
-    SBA_TRY(c->scratch[SCR_PIPE_PTS].ensure((size_t)n * 2 * 2 * sizeof(float) * 2, st));
-    float* d_cube = c->scratch[SCR_PIPE_PTS].as<float>();      // [2n][2] strip coordinates: left block, right block
-    float* d_erp = d_cube + (size_t)4 * n;                     // [2n][2] ERP pixels
-    SBA_TRY(sba_gather_matches(c, d_key0, d_key1, d_qi, d_ti, n, d_cube, d_cube + (size_t)2 * n, D));
-    SBA_TRY(sba_cube2equi_points(c, d_cube, 2 * n, cube_size, w, h, d_erp, D));
-    SBA_TRY(c->scratch[SCR_PIPE_BEAR].ensure((size_t)2 * n * 4 * sizeof(float), st));
-    float* d_b = c->scratch[SCR_PIPE_BEAR].as<float>();        // [2n] float4: left bearings, right bearings
-    SBA_TRY(sba_pixels_to_bearings(c, d_erp, 2 * n, w, h, d_b, nullptr, D));
-
-    // ---- rotation-only bundle adjustment
-    sba_ba_problem* prob = nullptr;
-    SBA_TRY(ba_problem_create_impl(c, d_b, d_b + (size_t)4 * n, nullptr, n, 1, D, /*borrow=*/true, &prob));
-    sba_solve_summary sum;
-    double r[3] = {r0[0], r0[1], r0[2]};
-    int status = sba_ba_rot_solve(prob, r, t, d1, d2, huber_delta, max_iter, &sum);
-    sba_ba_problem_destroy(prob);
-    SBA_TRY(status);
-    result->rotation[0] = r[0]; result->rotation[1] = r[1]; result->rotation[2] = r[2];
-    result->lm_iterations = sum.iterations;
-    result->lm_termination = sum.termination;
-    result->initial_cost = sum.initial_cost;
-    result->final_cost = sum.final_cost;
     if (overlap) SBA_TRY(remap_both());
     return finish(c, mem);
 }

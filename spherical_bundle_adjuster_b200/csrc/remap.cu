@@ -19,64 +19,13 @@
 #include <cmath>
 
 #include "common.cuh"
+#include "geometry.cuh"
 
 #ifndef M_PI
 #define M_PI 3.14159265358979323846
 #endif
 
 namespace sba {
-
-// ---- geometry shared by host and device (same operation order as equi2cube.cpp:26-48) ----------
-__host__ __device__ inline void face_cart(int face, double i, double j, double cs, double v[3])
-{
-    switch (face) {
-    case 0: v[0] = (cs - 2.0 * j) / cs; v[1] = 1.0; v[2] = (cs - 2.0 * i) / cs; break;   // left   :118-120
-    case 1: v[0] = -1.0; v[1] = (cs - 2.0 * j) / cs; v[2] = (cs - 2.0 * i) / cs; break;  // front  :73-75
-    case 2: v[0] = (2.0 * j - cs) / cs; v[1] = -1.0; v[2] = (cs - 2.0 * i) / cs; break;  // right  :163-165
-    case 3: v[0] = 1.0; v[1] = (2.0 * j - cs) / cs; v[2] = (cs - 2.0 * i) / cs; break;   // back   :28-30
-    case 4: v[0] = (cs - 2.0 * i) / cs; v[1] = (cs - 2.0 * j) / cs; v[2] = 1.0; break;   // top    :208-210
-    default: v[0] = (2.0 * i - cs) / cs; v[1] = (cs - 2.0 * j) / cs; v[2] = -1.0; break; // bottom :253-255
-    }
-}
-
-__host__ __device__ inline double no_fma_norm(const double v[3])
-{
-#ifdef __CUDA_ARCH__
-    // the host code rounds every product and sum separately; keep the device from contracting to FMA
-    return sqrt(__dadd_rn(__dadd_rn(__dmul_rn(v[0], v[0]), __dmul_rn(v[1], v[1])), __dmul_rn(v[2], v[2])));
-#else
-    return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
-#endif
-}
-
-// Continuous ERP coordinates (row_f, col_f) of a direction: equi2cube.cpp:32-48 before truncation.
-__host__ __device__ inline void dir_to_erp(const double v[3], int w, int h, double* row_f, double* col_f)
-{
-    double n = no_fma_norm(v);
-    double ux = v[0] / n, uy = v[1] / n, uz = v[2] / n;
-    double theta = acos(uz);
-    double phi = atan2(uy, ux);
-    if (phi < 0) phi += M_PI * 2;
-#ifdef __CUDA_ARCH__
-    *row_f = __dmul_rn((double)h, theta) / M_PI;
-    *col_f = __dmul_rn((double)w, phi) / (2 * M_PI);
-#else
-    *row_f = h * theta / M_PI;
-    *col_f = w * phi / (2 * M_PI);
-#endif
-}
-
-__host__ __device__ inline int32_t clamp_index(double row_f, double col_f, int w, int h, int* clamped)
-{
-    int row = (int)row_f, col = (int)col_f;  // Vec2i assignment truncates toward zero (:46-48)
-    int c = 0;
-    if (row >= h) { row = h - 1; c = 1; }
-    if (col >= w) { col = w - 1; c = 1; }
-    if (row < 0) { row = 0; c = 1; }
-    if (col < 0) { col = 0; c = 1; }
-    if (clamped) *clamped = c;
-    return row * w + col;
-}
 
 // ---- plan construction ------------------------------------------------------------------------
 __global__ void lut_build_kernel(int cs, int w, int h, int32_t* __restrict__ lut, int32_t* __restrict__ flagged,
@@ -236,19 +185,10 @@ __global__ void cube2equi_points_kernel(const float2* __restrict__ in, int n, in
 {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    float2 p = in[k];
-    int face;
-    if (p.x < cs) face = 0;
-    else if (p.x < 2 * cs) face = 1;
-    else if (p.x < 3 * cs) face = 2;
-    else if (p.x < 4 * cs) face = 3;
-    else if (p.x < 5 * cs) face = 4;
-    else face = 5;
-    float fx = (face == 0) ? p.x : __fsub_rn(p.x, (float)(face * cs));  // float - int in the reference
-    double v[3], rf, cf;
-    face_cart(face, (double)p.y, (double)fx, (double)cs, v);
-    dir_to_erp(v, w, h, &rf, &cf);
-    out[k] = make_float2((float)cf, (float)rf);
+    const float2 p = in[k];
+    float2 o;
+    cube2equi_point(p.x, p.y, cs, w, h, &o.x, &o.y);
+    out[k] = o;
 }
 
 // spherical_bundle_adjuster.cpp:271-298
@@ -257,13 +197,9 @@ __global__ void pixels_to_bearings_kernel(const float2* __restrict__ px, int n, 
 {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    float2 p = px[k];
-    double lon = 2 * M_PI * ((double)p.x / w);
-    double lat = M_PI * ((double)p.y / h);
-    double sl, cl, so, co;
-    sincos(lat, &sl, &cl);
-    sincos(lon, &so, &co);
-    double x = sl * co, y = sl * so, z = cl;
+    const float2 p = px[k];
+    double x, y, z;
+    pixel_to_bearing(p.x, p.y, w, h, &x, &y, &z);
     if (b32) b32[k] = make_float4((float)x, (float)y, (float)z, 0.f);
     if (b64) { b64[3 * k] = x; b64[3 * k + 1] = y; b64[3 * k + 2] = z; }
 }
