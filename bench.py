@@ -139,10 +139,12 @@ def bench_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (also builds the remap plan and checks the answer once)
-    for k in range(max(3, args.warmup)):
+    # ---- warm-up: builds the remap plan, sizes the scratch buffers and lets the library see every pool
+    #      entry twice (first call eager, second call captured into its CUDA graph); checks the answer once
+    n_warm = max(3, args.warmup, 2 * POOL)
+    for k in range(n_warm):
         r, nm, m, s = runner.run(resident[k % POOL])
-    truth = pool_host[(max(3, args.warmup) - 1) % POOL]["r_true"]
+    truth = pool_host[(n_warm - 1) % POOL]["r_true"]
     assert np.linalg.norm(r - truth) < 1e-3, (r, truth)
 
     # ---- device-resident timed region: exactly K steps, CUDA events on the launching stream
@@ -170,7 +172,7 @@ def bench_ours(args):
 
     # ---- end-to-end timed region: pinned host -> device every step, results read back
     d2h_bytes = 0
-    for k in range(max(3, args.warmup)):                        # warm-up of the host-buffer path (staging buffers, second stream)
+    for k in range(n_warm):                                     # warm-up of the host-buffer path (staging buffers, second stream, graphs)
         runner.run(pinned[k % POOL])
     barrier()
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
@@ -202,7 +204,7 @@ def bench_ours(args):
     peak = peaks["bf16_tflops_sustained"]
     line = {
         "metric": "ERP pairs/sec end-to-end", "value": pairs / (ms_total * 1e-3), "unit": "pairs/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "steps": args.steps, "warmup": n_warm, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32 (matcher distances; bf16x3 tensor filter) / f64 (BA residual, LM)",
         "data": "synthetic",
         "config": {"workload": "C2: 3840x1920 ERP pair, cube 960, 16384x16384 SURF-64 kNN2+ratio 0.3, rotation BA",

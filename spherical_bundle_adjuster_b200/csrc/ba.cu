@@ -991,20 +991,53 @@ int sba_ba_rot_eval(sba_ba_problem* p, const double* r, const double t[3], doubl
     return finish(c, mem);
 }
 
-int sba_ba_rot_solve(sba_ba_problem* p, double* r_inout, const double t[3], double d1, double d2, double huber, int max_iter,
-                     sba_solve_summary* summary)
+}  // extern "C"
+
+namespace sba {
+
+constexpr int LM_CHUNK = 6;   // evaluations enqueued between two looks at the solver state
+
+// (1) host side only: starting point and a fresh solver state into the problem's pinned mailboxes.
+void ba_solve_prepare_host(sba_ba_problem* p, const double* r0, int max_iter)
 {
-    SBA_CHECK_ARG(p && r_inout && t && max_iter >= 0);
-    sba_ctx* c = p->ctx;
-    SBA_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = c->stream;
-    const int n_cam = p->n_cam;
-    // h_x / h_state are pinned mailboxes of this problem; every earlier use ended with a synchronise
-    SBA_TRY(upload_rotations(p, r_inout, p->x));
-    SBA_CUDA(cudaMemcpyAsync(p->xc, p->x, (size_t)n_cam * 3 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    memcpy(p->h_x, r0, (size_t)p->n_cam * 3 * sizeof(double));
     LMState init{};
     init.radius = 1e4; init.dec_factor = 2.0; init.max_iter = max_iter; init.phase = 0;
     *p->h_state = init;
+}
+
+static int enqueue_chunk(sba_ba_problem* p, const EvalArgs& E, const LMArrays& A, int n)
+{
+    sba_ctx* c = p->ctx;
+    cudaStream_t st = c->stream;
+    for (int k = 0; k < n; k++) {
+        bool fused = false;
+        SBA_TRY(launch_eval<false>(p, E, A, true, &fused));
+        if (!fused) {
+            if (p->allreduce && p->allreduce(p->blk_cand, (int64_t)p->n_cam * 10, p->allreduce_user) != 0) {
+                sba::set_error("allreduce callback failed");
+                return SBA_ERR_COMM;
+            }
+            ba_decide_kernel<<<1, EVAL_THREADS, 0, st>>>(A);
+            SBA_LAUNCHED(c);
+        }
+    }
+    SBA_CUDA(cudaMemcpyAsync(p->h_state, p->state, sizeof(LMState), cudaMemcpyDeviceToHost, st));
+    // small problems: fetch the parameters with the state (one round trip per chunk)
+    if (p->n_cam <= 64) SBA_CUDA(cudaMemcpyAsync(p->h_x, p->x, (size_t)p->n_cam * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    return SBA_OK;
+}
+
+// (2) stream side, no synchronisation (capturable in a CUDA graph): mailboxes -> device, rotation
+// tables, the first chunk of evaluations, state (+ parameters) back to the mailboxes.
+// Evaluations that start after convergence return immediately (state.done).
+int ba_solve_enqueue(sba_ba_problem* p, const double t[3], double d1, double d2, double huber, int max_iter, int* launched)
+{
+    sba_ctx* c = p->ctx;
+    cudaStream_t st = c->stream;
+    const int n_cam = p->n_cam;
+    SBA_CUDA(cudaMemcpyAsync(p->x, p->h_x, (size_t)n_cam * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    SBA_CUDA(cudaMemcpyAsync(p->xc, p->x, (size_t)n_cam * 3 * sizeof(double), cudaMemcpyDeviceToDevice, st));
     SBA_CUDA(cudaMemcpyAsync(p->state, p->h_state, sizeof(LMState), cudaMemcpyHostToDevice, st));
     ba_cam_params_kernel<<<(n_cam + 127) / 128, 128, 0, st>>>(p->xc, n_cam, d1, p->params);
     SBA_LAUNCHED(c);
@@ -1012,40 +1045,38 @@ int sba_ba_rot_solve(sba_ba_problem* p, double* r_inout, const double t[3], doub
     E.done = &p->state->done;
     LMArrays A = make_lm_arrays(p);
     A.d1 = d1;
+    const int n = std::min(LM_CHUNK, max_iter + 1);
+    SBA_TRY(enqueue_chunk(p, E, A, n));
+    *launched = n;
+    return SBA_OK;
+}
 
-    // Evaluations are enqueued in chunks; kernels of a chunk that start after convergence return
-    // immediately (state.done), and the host looks at the state once per chunk.
-    const int chunk = 6;
-    int launched = 0;
+// (3) wait for the enqueued chunk; keep going chunk by chunk until the solver reports done.
+int ba_solve_finish(sba_ba_problem* p, double* r_out, const double t[3], double d1, double d2, double huber, int max_iter, int launched,
+                    sba_solve_summary* summary)
+{
+    sba_ctx* c = p->ctx;
+    cudaStream_t st = c->stream;
+    const int n_cam = p->n_cam;
     const int max_evals = max_iter + 1;
-    bool done = false;
-    while (!done && launched < max_evals) {
-        int n = std::min(chunk, max_evals - launched);
-        for (int k = 0; k < n; k++) {
-            bool fused = false;
-            SBA_TRY(launch_eval<false>(p, E, A, true, &fused));
-            if (!fused) {
-                if (p->allreduce && p->allreduce(p->blk_cand, (int64_t)n_cam * 10, p->allreduce_user) != 0) {
-                    sba::set_error("allreduce callback failed");
-                    return SBA_ERR_COMM;
-                }
-                ba_decide_kernel<<<1, EVAL_THREADS, 0, st>>>(A);
-                SBA_LAUNCHED(c);
-            }
-        }
-        launched += n;
-        SBA_CUDA(cudaMemcpyAsync(p->h_state, p->state, sizeof(LMState), cudaMemcpyDeviceToHost, st));
-        // small problems: fetch the parameters with the state (one round trip per chunk)
-        const bool x_with_state = n_cam <= 64;
-        if (x_with_state) SBA_CUDA(cudaMemcpyAsync(p->h_x, p->x, (size_t)n_cam * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
-        SBA_CUDA(cudaStreamSynchronize(st));
-        done = p->h_state->done != 0 || launched >= max_evals;
-        if (done && !x_with_state) {
-            SBA_CUDA(cudaMemcpyAsync(p->h_x, p->x, (size_t)n_cam * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SBA_CUDA(cudaStreamSynchronize(st));
+    if (!p->h_state->done && launched < max_evals) {
+        EvalArgs E = make_eval_args(p, t, d1, d2, huber, nullptr, nullptr, p->blk_cand);
+        E.done = &p->state->done;
+        LMArrays A = make_lm_arrays(p);
+        A.d1 = d1;
+        while (!p->h_state->done && launched < max_evals) {
+            const int n = std::min(LM_CHUNK, max_evals - launched);
+            SBA_TRY(enqueue_chunk(p, E, A, n));
+            launched += n;
             SBA_CUDA(cudaStreamSynchronize(st));
         }
     }
-    memcpy(r_inout, p->h_x, (size_t)n_cam * 3 * sizeof(double));
+    if (n_cam > 64) {
+        SBA_CUDA(cudaMemcpyAsync(p->h_x, p->x, (size_t)n_cam * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        SBA_CUDA(cudaStreamSynchronize(st));
+    }
+    memcpy(r_out, p->h_x, (size_t)n_cam * 3 * sizeof(double));
     if (summary) {
         const LMState& S = *p->h_state;
         summary->iterations = S.iter;
@@ -1057,6 +1088,22 @@ int sba_ba_rot_solve(sba_ba_problem* p, double* r_inout, const double t[3], doub
         summary->final_radius = S.radius;
     }
     return SBA_OK;
+}
+
+}  // namespace sba
+
+extern "C" {
+
+int sba_ba_rot_solve(sba_ba_problem* p, double* r_inout, const double t[3], double d1, double d2, double huber, int max_iter,
+                     sba_solve_summary* summary)
+{
+    SBA_CHECK_ARG(p && r_inout && t && max_iter >= 0);
+    SBA_CUDA(cudaSetDevice(p->ctx->device));
+    // h_x / h_state are pinned mailboxes of this problem; every earlier use ended with a synchronise
+    ba_solve_prepare_host(p, r_inout, max_iter);
+    int launched = 0;
+    SBA_TRY(ba_solve_enqueue(p, t, d1, d2, huber, max_iter, &launched));
+    return ba_solve_finish(p, r_inout, t, d1, d2, huber, max_iter, launched, summary);
 }
 
 int sba_ba_rot_eval_timed(sba_ba_problem* p, const double* r, const double t[3], double d1, double d2, double huber, int materialise,

@@ -152,6 +152,11 @@ struct sba_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copy_ev[2] = {nullptr, nullptr};
     cudaEvent_t main_ev = nullptr;
+    // CUDA graphs of the fused pair pipeline (pipeline.cu), keyed by the call's buffers and parameters
+    std::vector<void*> pair_graphs;
+    int64_t pair_clock = 0;
+    cudaStream_t graph_stream = nullptr;
+    cudaEvent_t graph_ev = nullptr;
 };
 
 namespace sba {
@@ -211,6 +216,15 @@ inline void prof_end(sba_ctx* c, int id)
 // ba.cu: problem creation with the option to read the caller's device bearings in place
 int ba_problem_create_impl(sba_ctx* c, const float* b1, const float* b2, const int32_t* cam, int64_t n_obs, int n_cam, int mem, bool borrow,
                            const int* d_n_obs, sba_ba_problem** out);
+
+// pipeline.cu: drop the cached pair graphs (context teardown)
+void pipeline_release(sba_ctx* c);
+
+// ba.cu: the LM solve in three parts so that the stream part can be captured in a CUDA graph
+void ba_solve_prepare_host(sba_ba_problem* p, const double* r0, int max_iter);
+int ba_solve_enqueue(sba_ba_problem* p, const double t[3], double d1, double d2, double huber, int max_iter, int* launched);
+int ba_solve_finish(sba_ba_problem* p, double* r_out, const double t[3], double d1, double d2, double huber, int max_iter, int launched,
+                    sba_solve_summary* summary);
 
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -6,8 +6,18 @@
 //   spherical_bundle_adjuster::do_bundle_adjustment (spherical_bundle_adjuster.cpp:268-298, :202-203):
 //                                     pixel -> bearing, rotation-only solve
 // minus SURF detect/describe (non-free OpenCV, stays on the host: the caller passes keypoints and
-// descriptors).  Everything between the input copy and the result copy stays on the device; the only
-// host round trips are the match count (sizes the BA problem) and the LM state once per launch chunk.
+// descriptors).  Everything between the input copy and the result copy stays on the device, and no stage
+// waits for the host: the match count lives in device memory (the bearing kernel and the BA kernels read
+// it there), so the host's only round trip is the LM state after each chunk of evaluations.
+//
+// Optional CUDA-graph replay (SBA_PAIR_GRAPHS=1).  The second time a call arrives with the same buffers
+// and parameters its whole stream work (about 25 kernels and copies: remap x2, the matcher pipeline, the
+// bearing kernel, solver set-up and the first chunk of LM evaluations, result read-back) is captured
+// into a graph that owns its BA problem; later calls write the starting rotation into the problem's
+// pinned mailbox, launch the graph and synchronise once.  Off by default: see the measurement note at
+// the switch below.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "geometry.cuh"
 
@@ -36,24 +46,52 @@ __global__ void pair_points_kernel(const float2* __restrict__ key_l, const float
     b2[i] = make_float4((float)x, (float)y, (float)z, 0.f);
 }
 
-}  // namespace sba
+// Everything that identifies one call's stream work (a graph is only replayed for an identical key).
+struct PairKey {
+    const void *erp_l, *erp_r, *strip_l, *strip_r, *desc_l, *desc_r, *key_l, *key_r, *qi, *ti, *dist;
+    int w, h, cs, n_left, n_right, dim, mem, max_iter;
+    float ratio;
+    double t[3], d1, d2, huber;
+};
 
-extern "C" {
+struct PairGraph {
+    PairKey key;
+    int seen = 0;
+    bool disabled = false;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    sba_ba_problem* prob = nullptr;
+    int launched = 0;
+    int64_t n_launches = 0;   // kernels inside the graph (for sba_ctx_launch_count)
+    int64_t last_use = 0;
+};
 
-int sba_pair_rotation(sba_ctx* c, const uint8_t* erp_left, const uint8_t* erp_right, int w, int h, int cube_size, uint8_t* strip_left_out,
-                      uint8_t* strip_right_out, const float* desc_left, int n_left, const float* desc_right, int n_right, int dim,
-                      const float* key_left_xy, const float* key_right_xy, float ratio, const double r0[3], const double t[3], double d1,
-                      double d2, double huber_delta, int max_iter, int32_t* query_idx_out, int32_t* train_idx_out, float* dist_out,
-                      sba_pair_result* result, int mem)
+struct PairState {   // what enqueue hands to finish
+    int32_t *d_qi, *d_ti;
+    float* d_dist;
+    bool dev_lists;
+    bool have_solve;
+};
+
+static bool host_ptr_is_pinned(const void* p)
 {
-    SBA_CHECK_ARG(c && result && w > 0 && h > 0 && cube_size > 0 && n_left >= 0 && n_right >= 0);
-    SBA_CHECK_ARG(desc_left && desc_right && key_left_xy && key_right_xy && r0 && t);
-    SBA_CHECK_ARG((erp_left == nullptr) == (erp_right == nullptr));
-    SBA_CUDA(cudaSetDevice(c->device));
+    if (!p) return true;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// All stream work of one pair on c->stream, no synchronisation.  *prob: in = an existing problem to
+// reuse (graph replay capture) or NULL; out = the problem the solve was enqueued on (NULL if none).
+static int enqueue_pair(sba_ctx* c, const PairKey& a, const double r0[3], sba_ba_problem** prob, int* launched, PairState* ps)
+{
     cudaStream_t st = c->stream;
-    memset(result, 0, sizeof(*result));
-    result->rotation[0] = r0[0]; result->rotation[1] = r0[1]; result->rotation[2] = r0[2];
     const int D = SBA_MEM_DEVICE;
+    const int mem = a.mem, w = a.w, h = a.h, cube_size = a.cs, n_left = a.n_left, n_right = a.n_right, dim = a.dim;
+    const uint8_t* erp_left = (const uint8_t*)a.erp_l;
+    const uint8_t* erp_right = (const uint8_t*)a.erp_r;
+    uint8_t* strip_left_out = (uint8_t*)a.strip_l;
+    uint8_t* strip_right_out = (uint8_t*)a.strip_r;
 
     // ---- inputs to the device.  Host mode: descriptors and keypoints (8.6 MB at C2) go first on the
     //      compute stream; the two images (44 MB) are uploaded on a second stream and only the remap,
@@ -62,16 +100,14 @@ int sba_pair_rotation(sba_ctx* c, const uint8_t* erp_left, const uint8_t* erp_ri
     const uint8_t *d_im0 = nullptr, *d_im1 = nullptr;
     const float *d_desc0, *d_desc1, *d_key0, *d_key1;
     const bool overlap = erp_left && mem == SBA_MEM_HOST;
-    if (overlap) {
-        // (image uploads are queued below, after the small inputs)
-    } else if (erp_left) {
+    if (erp_left && !overlap) {
         SBA_TRY(stage_in(c, erp_left, im_bytes, mem, SCR_PIPE_IM0, &d_im0));
         SBA_TRY(stage_in(c, erp_right, im_bytes, mem, SCR_PIPE_IM1, &d_im1));
     }
-    SBA_TRY(stage_in(c, desc_left, (size_t)n_left * dim, mem, SCR_PIPE_DESC0, &d_desc0));
-    SBA_TRY(stage_in(c, desc_right, (size_t)n_right * dim, mem, SCR_PIPE_DESC1, &d_desc1));
-    SBA_TRY(stage_in(c, key_left_xy, (size_t)n_left * 2, mem, SCR_PIPE_KEY0, &d_key0));
-    SBA_TRY(stage_in(c, key_right_xy, (size_t)n_right * 2, mem, SCR_PIPE_KEY1, &d_key1));
+    SBA_TRY(stage_in(c, (const float*)a.desc_l, (size_t)n_left * dim, mem, SCR_PIPE_DESC0, &d_desc0));
+    SBA_TRY(stage_in(c, (const float*)a.desc_r, (size_t)n_right * dim, mem, SCR_PIPE_DESC1, &d_desc1));
+    SBA_TRY(stage_in(c, (const float*)a.key_l, (size_t)n_left * 2, mem, SCR_PIPE_KEY0, &d_key0));
+    SBA_TRY(stage_in(c, (const float*)a.key_r, (size_t)n_right * 2, mem, SCR_PIPE_KEY1, &d_key1));
     if (overlap) {
         if (!c->copy_stream) {
             SBA_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -123,47 +159,208 @@ int sba_pair_rotation(sba_ctx* c, const uint8_t* erp_left, const uint8_t* erp_ri
     int32_t* s_ti = s_qi + nq;
     float* s_dist = (float*)(s_ti + nq);
     int32_t* d_n = (int32_t*)(s_dist + nq);
-    const bool dev_lists = (mem == SBA_MEM_DEVICE);
-    int32_t* d_qi = (dev_lists && query_idx_out) ? query_idx_out : s_qi;
-    int32_t* d_ti = (dev_lists && train_idx_out) ? train_idx_out : s_ti;
-    float* d_dist = (dev_lists && dist_out) ? dist_out : s_dist;
-    SBA_TRY(sba_knn2_ratio(c, d_desc0, n_left, d_desc1, n_right, dim, ratio, d_qi, d_ti, d_dist, d_n, nullptr, nullptr, D, SBA_MATCH_AUTO));
-    SBA_CUDA(cudaMemcpyAsync(c->pinned_i32, d_n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));   // read after the solve's synchronise
+    ps->dev_lists = (mem == SBA_MEM_DEVICE);
+    ps->d_qi = (ps->dev_lists && a.qi) ? (int32_t*)a.qi : s_qi;
+    ps->d_ti = (ps->dev_lists && a.ti) ? (int32_t*)a.ti : s_ti;
+    ps->d_dist = (ps->dev_lists && a.dist) ? (float*)a.dist : s_dist;
+    SBA_TRY(sba_knn2_ratio(c, d_desc0, n_left, d_desc1, n_right, dim, a.ratio, ps->d_qi, ps->d_ti, ps->d_dist, d_n, nullptr, nullptr, D,
+                           SBA_MATCH_AUTO));
+    SBA_CUDA(cudaMemcpyAsync(c->pinned_i32, d_n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));   // read after the final synchronise
 
-    double r[3] = {r0[0], r0[1], r0[2]};
-    if (n_left > 0 && n_right > 0) {
+    ps->have_solve = (n_left > 0 && n_right > 0);
+    *launched = 0;
+    if (ps->have_solve) {
         // ---- matched keypoints -> bearings (capacity n_left; the kernel stops at the device-side count)
         SBA_TRY(c->scratch[SCR_PIPE_BEAR].ensure((size_t)2 * n_left * 4 * sizeof(float), st));
-        float* d_b = c->scratch[SCR_PIPE_BEAR].as<float>();        // [cap] float4 left bearings, [cap] float4 right bearings
-        pair_points_kernel<<<(n_left + 255) / 256, 256, 0, st>>>((const float2*)d_key0, (const float2*)d_key1, d_qi, d_ti, d_n, n_left, cube_size,
-                                                                w, h, (float4*)d_b, (float4*)d_b + n_left);
+        float* d_b = c->scratch[SCR_PIPE_BEAR].as<float>();   // [cap] float4 left bearings, [cap] float4 right bearings
+        pair_points_kernel<<<(n_left + 255) / 256, 256, 0, st>>>((const float2*)d_key0, (const float2*)d_key1, ps->d_qi, ps->d_ti, d_n, n_left,
+                                                                cube_size, w, h, (float4*)d_b, (float4*)d_b + n_left);
         SBA_LAUNCHED(c);
+        // ---- rotation-only bundle adjustment on the bearings in place: set-up + first chunk of evaluations
+        if (!*prob) SBA_TRY(ba_problem_create_impl(c, d_b, d_b + (size_t)4 * n_left, nullptr, n_left, 1, D, /*borrow=*/true, d_n, prob));
+        ba_solve_prepare_host(*prob, r0, a.max_iter);   // pinned mailboxes; a graph replay rewrites them before each launch
+        SBA_TRY(ba_solve_enqueue(*prob, a.t, a.d1, a.d2, a.huber, a.max_iter, launched));
+    }
+    if (overlap) SBA_TRY(remap_both());
+    SBA_CUDA(cudaGetLastError());
+    return SBA_OK;
+}
 
-        // ---- rotation-only bundle adjustment on the bearings in place
-        sba_ba_problem* prob = nullptr;
-        SBA_TRY(ba_problem_create_impl(c, d_b, d_b + (size_t)4 * n_left, nullptr, n_left, 1, D, /*borrow=*/true, d_n, &prob));
-        sba_solve_summary sum;
-        int status = sba_ba_rot_solve(prob, r, t, d1, d2, huber_delta, max_iter, &sum);
-        sba_ba_problem_destroy(prob);
-        SBA_TRY(status);
+// Wait for the enqueued work, finish the solve if its first chunk was not enough, hand results back.
+static int finish_pair(sba_ctx* c, const PairKey& a, sba_ba_problem* prob, int launched, const PairState& ps, const double r0[3],
+                       sba_pair_result* result)
+{
+    cudaStream_t st = c->stream;
+    double r[3] = {r0[0], r0[1], r0[2]};
+    sba_solve_summary sum{};
+    if (ps.have_solve) SBA_TRY(ba_solve_finish(prob, r, a.t, a.d1, a.d2, a.huber, a.max_iter, launched, &sum));
+    else SBA_CUDA(cudaStreamSynchronize(st));
+    const int n = c->pinned_i32[0];
+    result->n_matches = n;
+    if (n > 0 && ps.have_solve) {
+        result->rotation[0] = r[0]; result->rotation[1] = r[1]; result->rotation[2] = r[2];
         result->lm_iterations = sum.iterations;
         result->lm_termination = sum.termination;
         result->initial_cost = sum.initial_cost;
         result->final_cost = sum.final_cost;
-    } else {
-        SBA_CUDA(cudaStreamSynchronize(st));
     }
-    const int n = c->pinned_i32[0];
-    result->n_matches = n;
-    if (n > 0) { result->rotation[0] = r[0]; result->rotation[1] = r[1]; result->rotation[2] = r[2]; }
-    else { result->lm_iterations = 0; result->lm_termination = 0; result->initial_cost = result->final_cost = 0.0; }
-    if (!dev_lists) {
-        SBA_TRY(copy_out(c, query_idx_out, (const int32_t*)d_qi, (size_t)n, mem));
-        SBA_TRY(copy_out(c, train_idx_out, (const int32_t*)d_ti, (size_t)n, mem));
-        SBA_TRY(copy_out(c, dist_out, (const float*)d_dist, (size_t)n, mem));
+    if (!ps.dev_lists) {
+        SBA_TRY(copy_out(c, (int32_t*)a.qi, (const int32_t*)ps.d_qi, (size_t)n, a.mem));
+        SBA_TRY(copy_out(c, (int32_t*)a.ti, (const int32_t*)ps.d_ti, (size_t)n, a.mem));
+        SBA_TRY(copy_out(c, (float*)a.dist, (const float*)ps.d_dist, (size_t)n, a.mem));
     }
-    if (overlap) SBA_TRY(remap_both());
-    return finish(c, mem);
+    return finish(c, a.mem);
+}
+
+static void destroy_graph(PairGraph* g)
+{
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    if (g->prob) sba_ba_problem_destroy(g->prob);
+    delete g;
+}
+
+void pipeline_release(sba_ctx* c)
+{
+    for (void* v : c->pair_graphs) destroy_graph((PairGraph*)v);
+    c->pair_graphs.clear();
+    if (c->graph_stream) cudaStreamDestroy(c->graph_stream);
+    if (c->graph_ev) cudaEventDestroy(c->graph_ev);
+    c->graph_stream = nullptr;
+    c->graph_ev = nullptr;
+}
+
+}  // namespace sba
+
+extern "C" {
+
+int sba_pair_rotation(sba_ctx* c, const uint8_t* erp_left, const uint8_t* erp_right, int w, int h, int cube_size, uint8_t* strip_left_out,
+                      uint8_t* strip_right_out, const float* desc_left, int n_left, const float* desc_right, int n_right, int dim,
+                      const float* key_left_xy, const float* key_right_xy, float ratio, const double r0[3], const double t[3], double d1,
+                      double d2, double huber_delta, int max_iter, int32_t* query_idx_out, int32_t* train_idx_out, float* dist_out,
+                      sba_pair_result* result, int mem)
+{
+    SBA_CHECK_ARG(c && result && w > 0 && h > 0 && cube_size > 0 && n_left >= 0 && n_right >= 0 && max_iter >= 0);
+    SBA_CHECK_ARG(desc_left && desc_right && key_left_xy && key_right_xy && r0 && t);
+    SBA_CHECK_ARG((erp_left == nullptr) == (erp_right == nullptr));
+    SBA_CUDA(cudaSetDevice(c->device));
+    memset(result, 0, sizeof(*result));
+    result->rotation[0] = r0[0]; result->rotation[1] = r0[1]; result->rotation[2] = r0[2];
+
+    PairKey key;
+    memset(&key, 0, sizeof(key));
+    key.erp_l = erp_left; key.erp_r = erp_right; key.strip_l = strip_left_out; key.strip_r = strip_right_out;
+    key.desc_l = desc_left; key.desc_r = desc_right; key.key_l = key_left_xy; key.key_r = key_right_xy;
+    key.qi = query_idx_out; key.ti = train_idx_out; key.dist = dist_out;
+    key.w = w; key.h = h; key.cs = cube_size; key.n_left = n_left; key.n_right = n_right; key.dim = dim; key.mem = mem; key.max_iter = max_iter;
+    key.ratio = ratio; key.t[0] = t[0]; key.t[1] = t[1]; key.t[2] = t[2]; key.d1 = d1; key.d2 = d2; key.huber = huber_delta;
+
+    // Opt-in (SBA_PAIR_GRAPHS=1): measured on B200 at C2 with six alternating buffer sets the replay path
+    // (450-500 us per pair) loses to the plain stream path (373 us) -- after the device-side match count
+    // removed the mid-pipeline host wait the pipeline is bounded by kernel time and dependencies, not by
+    // launch overhead.  Kept for callers that reuse ONE buffer set (345 us vs 368 us there).
+    static const bool graphs_on = std::getenv("SBA_PAIR_GRAPHS") != nullptr;
+    const bool graphable = graphs_on && !c->profiling && n_left > 0 && n_right > 0;
+    PairGraph* g = nullptr;
+    if (graphable) {
+        for (void* v : c->pair_graphs)
+            if (memcmp(&((PairGraph*)v)->key, &key, sizeof(key)) == 0) { g = (PairGraph*)v; break; }
+        if (!g) {
+            if (c->pair_graphs.size() >= 16) {   // evict the least recently used entry
+                size_t lru = 0;
+                for (size_t k = 1; k < c->pair_graphs.size(); k++)
+                    if (((PairGraph*)c->pair_graphs[k])->last_use < ((PairGraph*)c->pair_graphs[lru])->last_use) lru = k;
+                cudaStreamSynchronize(c->stream);
+                if (c->graph_stream) cudaStreamSynchronize(c->graph_stream);
+                destroy_graph((PairGraph*)c->pair_graphs[lru]);
+                c->pair_graphs.erase(c->pair_graphs.begin() + lru);
+            }
+            g = new PairGraph();
+            g->key = key;
+            c->pair_graphs.push_back(g);
+        }
+        g->last_use = ++c->pair_clock;
+    }
+
+    PairState ps{};
+    cudaStream_t user_stream = c->stream;
+
+    // ---- capture on the second sighting of a key
+    if (g && !g->exec && !g->disabled && g->seen >= 1) {
+        bool ok = true;
+        if (mem == SBA_MEM_HOST) {
+            const void* hp[] = {erp_left, erp_right, strip_left_out, strip_right_out, desc_left, desc_right, key_left_xy, key_right_xy};
+            for (const void* p : hp) ok = ok && host_ptr_is_pinned(p);   // graph memcpy nodes need page-locked host memory
+        }
+        if (ok && !c->graph_stream) {
+            ok = cudaStreamCreate(&c->graph_stream) == cudaSuccess &&   // blocking stream: ordered with the legacy default stream
+                 cudaEventCreateWithFlags(&c->graph_ev, cudaEventDisableTiming) == cudaSuccess;
+        }
+        if (ok) {
+            cudaStreamSynchronize(user_stream);
+            c->stream = c->graph_stream;
+            sba_ba_problem* prob = nullptr;
+            int launched = 0;
+            int status = SBA_ERR_CUDA;
+            const int64_t launches_before = c->launches;
+            if (cudaStreamBeginCapture(c->graph_stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+                status = enqueue_pair(c, key, r0, &prob, &launched, &ps);
+                cudaGraph_t graph = nullptr;
+                cudaError_t e = cudaStreamEndCapture(c->graph_stream, &graph);
+                if (status == SBA_OK && e == cudaSuccess && graph && cudaGraphInstantiate(&g->exec, graph, 0) == cudaSuccess) {
+                    g->graph = graph;
+                    g->prob = prob;
+                    g->launched = launched;
+                    g->n_launches = c->launches - launches_before;
+                } else {
+                    if (graph) cudaGraphDestroy(graph);
+                    g->exec = nullptr;
+                    status = SBA_ERR_CUDA;
+                }
+            }
+            c->stream = user_stream;
+            c->launches = launches_before;   // nothing ran yet: captured launches are counted per replay
+            if (!g->exec) {
+                cudaGetLastError();
+                g->disabled = true;   // fall back to the eager path for this key from now on
+                if (prob) sba_ba_problem_destroy(prob);
+            }
+        } else {
+            g->disabled = true;
+        }
+    }
+
+    // ---- replay
+    if (g && g->exec) {
+        if (g->prob) ba_solve_prepare_host(g->prob, r0, max_iter);
+        // order the graph after whatever the caller already queued on its stream
+        SBA_CUDA(cudaEventRecord(c->graph_ev, user_stream));
+        SBA_CUDA(cudaStreamWaitEvent(c->graph_stream, c->graph_ev, 0));
+        SBA_CUDA(cudaGraphLaunch(g->exec, c->graph_stream));
+        c->launches += g->n_launches;
+        c->stream = c->graph_stream;
+        // the pointers enqueue_pair chose are a pure function of the key: recompute them for finish
+        ps.dev_lists = (mem == SBA_MEM_DEVICE);
+        const size_t nq = (size_t)n_left;
+        int32_t* s_qi = c->scratch[SCR_PIPE_MATCH].as<int32_t>();
+        ps.d_qi = (ps.dev_lists && query_idx_out) ? query_idx_out : s_qi;
+        ps.d_ti = (ps.dev_lists && train_idx_out) ? train_idx_out : s_qi + nq;
+        ps.d_dist = (ps.dev_lists && dist_out) ? dist_out : (float*)(s_qi + 2 * nq);
+        ps.have_solve = true;
+        int status = finish_pair(c, key, g->prob, g->launched, ps, r0, result);
+        if (status == SBA_OK) cudaStreamSynchronize(c->graph_stream);
+        c->stream = user_stream;
+        return status;
+    }
+
+    // ---- eager path (first sighting of a key, graphs disabled, or capture not possible)
+    if (g) g->seen++;
+    sba_ba_problem* prob = nullptr;
+    int launched = 0;
+    int status = enqueue_pair(c, key, r0, &prob, &launched, &ps);
+    if (status == SBA_OK) status = finish_pair(c, key, prob, launched, ps, r0, result);
+    if (prob) sba_ba_problem_destroy(prob);
+    return status;
 }
 
 }  // extern "C"
