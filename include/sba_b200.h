@@ -191,6 +191,15 @@ typedef struct sba_solve_summary {
 int sba_ba_rot_solve(sba_ba_problem* p, double* r_inout, const double t[3], double d1, double d2, double huber_delta,
                      int max_iter, sba_solve_summary* summary);
 
+/* Translation-only variant (ba_spherical_costfunctor_tran_only, spherical_bundle_adjuster.cpp:948-1002,
+ * solved at :208-209): same residual, the rotations r_fixed [n_cam x 3] are constants and the free block
+ * is the translation t [n_cam x 3] (the reference has one camera: a single 3-vector); d res / d t = +I.
+ * Outputs of the evaluation as in sba_ba_rot_eval (the Jacobian is the identity and is not materialised). */
+int sba_ba_tran_eval(sba_ba_problem* p, const double* r_fixed, const double* t, double d1, double d2, double huber_delta,
+                     float* res, double* H, double* g, double* cost, int mem);
+int sba_ba_tran_solve(sba_ba_problem* p, const double* r_fixed, double* t_inout, double d1, double d2, double huber_delta,
+                      int max_iter, sba_solve_summary* summary);
+
 /* Device-timed evaluation loop for benchmarking: runs `iters` fused evaluations (residual +
  * Jacobian + per-camera normal equations) back to back at r and returns the mean kernel time. */
 int sba_ba_rot_eval_timed(sba_ba_problem* p, const double* r, const double t[3], double d1, double d2, double huber_delta,

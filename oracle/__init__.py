@@ -58,6 +58,8 @@ def _load():
                                     f64p, f64p, f64p, f64p, f64p]
     lib.orc_ba_rot_solve.argtypes = [f64p, f64p, i32p, C.c_int, f64p, C.c_int, f64p, C.c_double, C.c_double, C.c_double,
                                      C.c_int, C.c_void_p]
+    lib.orc_ba_tran_eval.argtypes = [f64p, f64p, i32p, C.c_int, f64p, f64p, C.c_int, C.c_double, C.c_double, C.c_double, f64p, f64p, f64p, f64p]
+    lib.orc_ba_tran_solve.argtypes = [f64p, f64p, i32p, C.c_int, f64p, f64p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p]
     return lib
 
 
@@ -192,6 +194,26 @@ def ba_rot_solve(b1, b2, cam, r0, t=(0, 0, 0), d1=1.0, d2=1.0, huber=1.0, max_it
     lib().orc_ba_rot_solve(_p(b1, C.c_double), _p(b2, C.c_double), _p(cam, C.c_int32), len(b1), _p(r, C.c_double), len(r),
                            _p(t, C.c_double), d1, d2, huber, max_iter, C.byref(s))
     return r, LMSummary(s.iterations, s.num_successful, s.termination, s.initial_cost, s.final_cost, s.final_radius)
+
+
+def ba_tran_eval(b1, b2, cam, r, tv, d1=1.0, d2=1.0, huber=1.0):
+    """Translation-only functor (spherical_bundle_adjuster.cpp:948-1002): r fixed, tv [n_cam x 3] free."""
+    b1, b2, cam, r, _ = _ba_args(b1, b2, cam, r, (0, 0, 0))
+    tv = np.ascontiguousarray(tv, np.float64).reshape(-1, 3)
+    n, n_cam = len(b1), len(r)
+    res = np.empty((n, 3)); H = np.empty((n_cam, 6)); g = np.empty((n_cam, 3)); cost = np.empty(n_cam)
+    lib().orc_ba_tran_eval(_p(b1, C.c_double), _p(b2, C.c_double), _p(cam, C.c_int32), n, _p(r, C.c_double), _p(tv, C.c_double), n_cam,
+                           d1, d2, huber, _p(res, C.c_double), _p(H, C.c_double), _p(g, C.c_double), _p(cost, C.c_double))
+    return res, H, g, cost
+
+
+def ba_tran_solve(b1, b2, cam, r, t0, d1=1.0, d2=1.0, huber=1.0, max_iter=50):
+    b1, b2, cam, r, _ = _ba_args(b1, b2, cam, r, (0, 0, 0))
+    tv = np.ascontiguousarray(t0, np.float64).reshape(-1, 3).copy()
+    s = _CSummary()
+    lib().orc_ba_tran_solve(_p(b1, C.c_double), _p(b2, C.c_double), _p(cam, C.c_int32), len(b1), _p(r, C.c_double), _p(tv, C.c_double), len(r),
+                            d1, d2, huber, max_iter, C.byref(s))
+    return tv, LMSummary(s.iterations, s.num_successful, s.termination, s.initial_cost, s.final_cost, s.final_radius)
 
 
 # ------------------------------------------------------------------ the real reference (oracle/_ref)

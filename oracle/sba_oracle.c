@@ -444,6 +444,30 @@ void orc_ba_rot_eval(const double *b1, const double *b2, const int32_t *cam, int
     free(priv);
 }
 
+/* Translation-only functor.  spherical_bundle_adjuster.cpp:948-976 (residual identical to the rot-only
+ * one, the free block is t: d res / d t = +I) and :978-1002 (constants per residual: r = init_rot,
+ * d1 = init_d[0][0], d2 = init_d[1][0], HuberLoss(1.0), one shared 3-vector block).
+ * r: n_cam x 3 fixed rotations, tv: n_cam x 3 translations (the parameters).
+ * Outputs as in orc_ba_rot_eval; the Jacobian is the identity and is not materialised. */
+void orc_ba_tran_eval(const double *b1, const double *b2, const int32_t *cam, int n, const double *r, const double *tv, int n_cam,
+                      double d1, double d2, double huber_a, double *res, double *H, double *g, double *cost)
+{
+    if (H) memset(H, 0, sizeof(double) * 6 * n_cam);
+    if (g) memset(g, 0, sizeof(double) * 3 * n_cam);
+    if (cost) memset(cost, 0, sizeof(double) * n_cam);
+    for (int i = 0; i < n; i++) {
+        int c = cam ? cam[i] : 0;
+        double rr[3];
+        orc_ba_rot_functor(b1 + 3 * i, b2 + 3 * i, r + 3 * c, tv + 3 * c, d1, d2, rr, NULL);
+        if (res) memcpy(res + 3 * i, rr, 3 * sizeof(double));
+        double s = rr[0] * rr[0] + rr[1] * rr[1] + rr[2] * rr[2], rho, rho1;
+        huber(huber_a, s, &rho, &rho1);
+        if (cost) cost[c] += 0.5 * rho;
+        if (H) { H[6 * c] += rho1; H[6 * c + 3] += rho1; H[6 * c + 5] += rho1; }   /* rho' I^T I */
+        if (g) for (int a = 0; a < 3; a++) g[3 * c + a] += rho1 * rr[a];            /* rho' I^T res */
+    }
+}
+
 /* Solve the symmetric 3x3 system (H + diag(dd)) x = rhs by Cholesky.  Returns 0 on success. */
 static int solve3_spd(const double H[6], const double dd[3], const double rhs[3], double x[3])
 {
@@ -483,9 +507,34 @@ typedef struct {
  * The linear solve is exact (dense 3x3 Cholesky per block) where the reference asks for
  * ITERATIVE_SCHUR (:335); with one 3-parameter block per camera the reduced system IS this
  * 3x3 block, so the exact solve is the converged limit of that iteration. */
+/* which block is free: 0 = rotation (t fixed), 1 = translation (rotation `fixed` fixed) */
+static void lm_eval(int mode, const double *b1, const double *b2, const int32_t *cam, int n, const double *x, int n_cam,
+                    const double *fixed, double d1, double d2, double huber_a, double *H, double *g, double *c)
+{
+    if (mode == 0) orc_ba_rot_eval(b1, b2, cam, n, x, n_cam, fixed, d1, d2, huber_a, NULL, NULL, H, g, c);
+    else orc_ba_tran_eval(b1, b2, cam, n, fixed, x, n_cam, d1, d2, huber_a, NULL, H, g, c);
+}
+
+static void lm_solve(int mode, const double *b1, const double *b2, const int32_t *cam, int n, double *r, int n_cam,
+                     const double *t, double d1, double d2, double huber_a, int max_iter, orc_lm_summary *sum);
+
 void orc_ba_rot_solve(const double *b1, const double *b2, const int32_t *cam, int n, double *r, int n_cam,
                       const double t[3], double d1, double d2, double huber_a, int max_iter,
                       orc_lm_summary *sum)
+{
+    lm_solve(0, b1, b2, cam, n, r, n_cam, t, d1, d2, huber_a, max_iter, sum);
+}
+
+/* spherical_bundle_adjuster.cpp:208-209: the same ceres::Solve on the translation block.
+ * r: n_cam x 3 fixed rotations; tv: n_cam x 3 translations, updated in place. */
+void orc_ba_tran_solve(const double *b1, const double *b2, const int32_t *cam, int n, const double *r, double *tv, int n_cam,
+                       double d1, double d2, double huber_a, int max_iter, orc_lm_summary *sum)
+{
+    lm_solve(1, b1, b2, cam, n, tv, n_cam, r, d1, d2, huber_a, max_iter, sum);
+}
+
+static void lm_solve(int mode, const double *b1, const double *b2, const int32_t *cam, int n, double *r, int n_cam,
+                     const double *t, double d1, double d2, double huber_a, int max_iter, orc_lm_summary *sum)
 {
     const double min_diag = 1e-6, max_diag = 1e32, min_rel_dec = 1e-3;
     const double ftol = 1e-6, gtol = 1e-10, ptol = 1e-8, max_radius = 1e16, min_radius = 1e-32;
@@ -496,7 +545,7 @@ void orc_ba_rot_solve(const double *b1, const double *b2, const int32_t *cam, in
     double *Hn = malloc(sizeof(double) * 6 * n_cam), *gn = malloc(sizeof(double) * np), *cn = malloc(sizeof(double) * n_cam);
     double *scale = malloc(sizeof(double) * np), *step = malloc(sizeof(double) * np), *xn = malloc(sizeof(double) * np);
 
-    orc_ba_rot_eval(b1, b2, cam, n, r, n_cam, t, d1, d2, huber_a, NULL, NULL, H, g, c);
+    lm_eval(mode, b1, b2, cam, n, r, n_cam, t, d1, d2, huber_a, H, g, c);
     double cost = 0;
     for (int k = 0; k < n_cam; k++) cost += c[k];
     /* Jacobi scaling is computed once from the initial Jacobian (Ceres does the same). */
@@ -547,7 +596,7 @@ void orc_ba_rot_solve(const double *b1, const double *b2, const int32_t *cam, in
         }
         consecutive_invalid = 0;
 
-        orc_ba_rot_eval(b1, b2, cam, n, xn, n_cam, t, d1, d2, huber_a, NULL, NULL, Hn, gn, cn);
+        lm_eval(mode, b1, b2, cam, n, xn, n_cam, t, d1, d2, huber_a, Hn, gn, cn);
         double new_cost = 0;
         for (int k = 0; k < n_cam; k++) new_cost += cn[k];
 

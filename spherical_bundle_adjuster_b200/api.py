@@ -344,6 +344,23 @@ class BAProblem:
         check(self._lib.sba_ba_rot_solve(self._h, _ptr(r), _ptr(t), d1, d2, huber, max_iter, C.byref(s)))
         return r, s
 
+    # -- translation-only block (ba_spherical_costfunctor_tran_only, spherical_bundle_adjuster.cpp:948-1002)
+    def tran_eval(self, r_fixed, t, d1=1.0, d2=1.0, huber=1.0, want_res=False):
+        r = self._r(r_fixed, self.n_cam)
+        tv = self._r(t, self.n_cam)
+        n, m = self.n_obs, self.n_cam
+        res = np.empty((n, 3), np.float32) if want_res else None
+        H = np.empty((m, 6)); g = np.empty((m, 3)); cost = np.empty(m)
+        check(self._lib.sba_ba_tran_eval(self._h, _ptr(r), _ptr(tv), d1, d2, huber, _ptr(res), _ptr(H), _ptr(g), _ptr(cost), SBA_MEM_HOST))
+        return dict(res=res, H=H, g=g, cost=cost)
+
+    def tran_solve(self, r_fixed, t0, d1=1.0, d2=1.0, huber=1.0, max_iter=50):
+        r = self._r(r_fixed, self.n_cam)
+        tv = self._r(t0, self.n_cam).copy()
+        s = _lib.SolveSummary()
+        check(self._lib.sba_ba_tran_solve(self._h, _ptr(r), _ptr(tv), d1, d2, huber, max_iter, C.byref(s)))
+        return tv, s
+
     def eval_timed(self, r, t=(0.0, 0.0, 0.0), d1=1.0, d2=1.0, huber=1.0, materialise=False, iters=20) -> float:
         r = self._r(r, self.n_cam)
         t = np.ascontiguousarray(t, np.float64)

@@ -160,6 +160,15 @@ __device__ inline void moments_to_block(const double m[16], const CamParams* __r
     blk[9] = m[15];
 }
 
+// Translation-only block (spherical_bundle_adjuster.cpp:948-1002): d res / d t = +I, so
+// H = (sum w) I and g = sum w res.  m = {sum w, sum w res (3), ..., cost at [15]}.
+__device__ inline void moments_to_block_tran(const double m[16], double blk[10])
+{
+    blk[0] = m[0]; blk[1] = 0; blk[2] = 0; blk[3] = m[0]; blk[4] = 0; blk[5] = m[0];
+    blk[6] = m[1]; blk[7] = m[2]; blk[8] = m[3];
+    blk[9] = m[15];
+}
+
 // ---- reductions ---------------------------------------------------------------------------------
 __device__ inline double warp_sum(double v)
 {
@@ -226,6 +235,7 @@ struct LMArrays {
     LMState* st;
     int n_cam;
     double d1;         // uniform depth of camera 1 (folded into the rotation tables)
+    int tran;          // 1: the free block is the translation (tables depend on the FIXED rotation: never rebuilt)
 };
 
 // Trust-region bookkeeping restated from Ceres' TrustRegionMinimizer / LevenbergMarquardtStrategy
@@ -352,7 +362,7 @@ __device__ void lm_decide(const LMArrays A, double* sh)
         if (s_accept == 0) break;
     }
     __syncthreads();
-    if (!S.done)
+    if (!S.done && !A.tran)
         for (int c = tid; c < n_cam; c += nthr) {
             double r[3] = {A.xc[3 * c], A.xc[3 * c + 1], A.xc[3 * c + 2]};
             write_cam_params(r, A.d1, A.params + c);
@@ -372,7 +382,7 @@ __global__ void __launch_bounds__(EVAL_THREADS) ba_decide_kernel(LMArrays A)
 constexpr int NMOM = 16;
 
 __device__ void fold_items(const double* __restrict__ partial, const int* __restrict__ item_ptr, int n_items, int n_cam,
-                           const CamParams* __restrict__ params, double d1, double* __restrict__ blk)
+                           const CamParams* __restrict__ params, double d1, int tran, double* __restrict__ blk)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (item_ptr == nullptr) {
@@ -399,7 +409,7 @@ __device__ void fold_items(const double* __restrict__ partial, const int* __rest
                 for (int w = 0; w < EVAL_WARPS; w++) t += red[w][k];
                 m[k] = t;
             }
-            moments_to_block(m, params, d1, blk);
+            if (tran) moments_to_block_tran(m, blk); else moments_to_block(m, params, d1, blk);
         }
         __syncthreads();
         return;
@@ -414,7 +424,7 @@ __device__ void fold_items(const double* __restrict__ partial, const int* __rest
             for (int it = item_ptr[c]; it < item_ptr[c + 1]; it++)
 #pragma unroll
                 for (int k = 0; k < NMOM; k++) acc[k] += partial[(size_t)it * NMOM + k];
-            moments_to_block(acc, params + c, d1, blk + 10 * c);
+            if (tran) moments_to_block_tran(acc, blk + 10 * c); else moments_to_block(acc, params + c, d1, blk + 10 * c);
         }
     } else {
         // many items per camera: one warp per camera, lane-strided ordered sums + butterfly
@@ -427,7 +437,7 @@ __device__ void fold_items(const double* __restrict__ partial, const int* __rest
                 for (int k = 0; k < NMOM; k++) acc[k] += partial[(size_t)it * NMOM + k];
 #pragma unroll
             for (int k = 0; k < NMOM; k++) acc[k] = warp_sum(acc[k]);
-            if (lane == 0) moments_to_block(acc, params + c, d1, blk + 10 * c);
+            if (lane == 0) { if (tran) moments_to_block_tran(acc, blk + 10 * c); else moments_to_block(acc, params + c, d1, blk + 10 * c); }
         }
     }
 }
@@ -435,8 +445,8 @@ __device__ void fold_items(const double* __restrict__ partial, const int* __rest
 // Stand-alone fold for problems with many cameras: one warp per camera over the whole grid (the
 // in-kernel fold runs in a single CTA, which is only right when there are few cameras).
 __global__ void __launch_bounds__(EVAL_THREADS) ba_fold_kernel(const double* __restrict__ partial, const int* __restrict__ item_ptr, int n_cam,
-                                                              const CamParams* __restrict__ params, double d1, double* __restrict__ blk,
-                                                              const int* __restrict__ done)
+                                                              const CamParams* __restrict__ params, double d1, int tran,
+                                                              double* __restrict__ blk, const int* __restrict__ done)
 {
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * EVAL_WARPS + (threadIdx.x >> 5);
@@ -449,7 +459,7 @@ __global__ void __launch_bounds__(EVAL_THREADS) ba_fold_kernel(const double* __r
         for (int k = 0; k < NMOM; k++) acc[k] += partial[(size_t)it * NMOM + k];
 #pragma unroll
     for (int k = 0; k < NMOM; k++) acc[k] = warp_sum(acc[k]);
-    if (lane == 0) moments_to_block(acc, params + c, d1, blk + 10 * c);
+    if (lane == 0) { if (tran) moments_to_block_tran(acc, blk + 10 * c); else moments_to_block(acc, params + c, d1, blk + 10 * c); }
 }
 
 struct EvalArgs {
@@ -467,22 +477,51 @@ struct EvalArgs {
     double* partial;
     double* blk_out;
     unsigned int* ticket;
+    const double* tvec;  // translation-only mode: per-camera t [n_cam x 3] on the device (NULL: the uniform k.t)
+    int tran;            // 1: accumulate the translation-block moments {sum w, sum w res}
     const int* done;  // LM solve: skip the whole evaluation once the solver has converged (NULL = always run)
     float* res;  // optional materialised outputs (caller order)
     float* jac;
     SolveConsts k;
 };
 
-// 128-bit streaming load: the observations are read once per evaluation, keep them out of L1.
-__device__ __forceinline__ float4 ld_stream(const float4* p)
+// ---- observation staging: per-warp shared-memory ring filled by TMA 1-D bulk copies ----------------------
+// Every warp streams its work items through BULK_STAGES x 32 observations of shared memory.  One lane
+// issues `cp.async.bulk` for the next chunk of b1 and b2 (512 B each) and the bytes land asynchronously
+// on a per-warp mbarrier, so the memory-level parallelism (3 chunks = 3 KB in flight per warp, 72 KB per
+// SM at 24 resident warps) is fixed by construction instead of by register allocation and instruction
+// scheduling of explicit prefetch loads.
+constexpr int BULK_STAGES = 4;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
 {
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bar_expect(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity)
+{
+    const uint32_t addr = smem_addr(bar);
+    uint32_t ok = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) break;
+        if (clock64() - t0 > 4000000000ll) __trap();   // a protocol bug traps instead of hanging the GPU
+    }
 }
 
 // MODE 0: partials only (ba_fold_kernel follows); 1: the last CTA folds; 2: the last CTA folds and runs the LM decision.
-template <bool WRITE, int MODE>
+// DEVN: the observation count is read from device memory (fused pair pipeline); a separate instantiation
+// because routing the common path's count through that load measurably de-tunes its inner loop.
+template <bool WRITE, int MODE, bool TRAN, bool DEVN>
 __global__ void __launch_bounds__(EVAL_THREADS, 3) ba_rot_eval_kernel(EvalArgs E, LMArrays A)
 {
     __shared__ double sh[EVAL_THREADS];
@@ -491,6 +530,8 @@ __global__ void __launch_bounds__(EVAL_THREADS, 3) ba_rot_eval_kernel(EvalArgs E
     // -d1*dR/dr_k (27 fp32).  Shared memory (broadcast reads) instead of registers: three CTAs per SM.
     __shared__ __align__(16) double s_R[EVAL_WARPS][10];
     __shared__ __align__(16) float s_M[WRITE ? EVAL_WARPS : 1][28];
+    __shared__ __align__(128) float4 s_obs[EVAL_WARPS][BULK_STAGES][2][32];   // [warp][stage][b1|b2][lane]
+    __shared__ __align__(8) uint64_t s_bar[EVAL_WARPS][BULK_STAGES];
     if (E.done && *E.done) return;  // converged earlier in this launch chunk
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -499,7 +540,15 @@ __global__ void __launch_bounds__(EVAL_THREADS, 3) ba_rot_eval_kernel(EvalArgs E
     const double d2 = E.k.d2, huber = E.k.huber, hub2 = huber * huber;
     const double t0 = E.k.t[0], t1 = E.k.t[1], t2 = E.k.t[2];
     const double* Rs = &s_R[wib][0];
-    const int n_obs = E.n_obs_dev ? min(E.n_obs, *E.n_obs_dev) : E.n_obs;
+    const int n_obs = DEVN ? min(E.n_obs, *E.n_obs_dev) : E.n_obs;
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < BULK_STAGES; k++)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&s_bar[wib][k])), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t gchunk = 0;   // chunks this warp has consumed so far: ring position and mbarrier phase
     // Uniform layout (one camera): a warp keeps its moments across all of its work items and the CTA
     // publishes ONE partial, so the final fold is over gridDim.x entries instead of n_items.
     const bool uniform = (E.items == nullptr);
@@ -515,11 +564,21 @@ __global__ void __launch_bounds__(EVAL_THREADS, 3) ba_rot_eval_kernel(EvalArgs E
             item.count = min(E.item_len, n_obs - it * E.item_len);
             item.cam = 0;
         }
-        // first observation of every lane goes in flight before the tables are staged
-        const float4* q1 = E.b1 + item.start + lane;
-        const float4* q2 = E.b2 + item.start + lane;
-        float4 n1 = make_float4(0.f, 0.f, 0.f, 0.f), n2 = n1;
-        if (lane < item.count) { n1 = ld_stream(q1); n2 = ld_stream(q2); }
+        // chunks of 32 observations; the first BULK_STAGES-1 go in flight before the tables are staged
+        const float4* g1 = E.b1 + item.start;
+        const float4* g2 = E.b2 + item.start;
+        const int n_chunks = (item.count + 31) >> 5;
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < BULK_STAGES - 1; c++)
+                if (c < n_chunks) {
+                    const int st = (int)((gchunk + c) % BULK_STAGES);
+                    const uint32_t bytes = (uint32_t)min(32, item.count - 32 * c) * 16u;
+                    bar_expect(&s_bar[wib][st], 2 * bytes);
+                    bulk_load(&s_obs[wib][st][0][0], g1 + 32 * c, bytes, &s_bar[wib][st]);
+                    bulk_load(&s_obs[wib][st][1][0], g2 + 32 * c, bytes, &s_bar[wib][st]);
+                }
+        }
         {
             const CamParams* P = E.params + item.cam;
             __syncwarp();
@@ -527,24 +586,34 @@ __global__ void __launch_bounds__(EVAL_THREADS, 3) ba_rot_eval_kernel(EvalArgs E
             if (WRITE && lane < 27) s_M[WRITE ? wib : 0][lane] = P->nM[lane];
             __syncwarp();
         }
+        // translation-only mode: this camera's candidate t replaces the uniform one
+        const double u0 = TRAN ? E.tvec[3 * item.cam] : t0, u1 = TRAN ? E.tvec[3 * item.cam + 1] : t1, u2 = TRAN ? E.tvec[3 * item.cam + 2] : t2;
 
         if (!uniform) {
 #pragma unroll
             for (int k = 0; k < NMOM; k++) acc[k] = 0;
         }
-        // two observations per lane in flight ahead of the math
-        float4 m1 = n1, m2 = n2;
-        if (lane + 32 < item.count) { m1 = ld_stream(q1 + 32); m2 = ld_stream(q2 + 32); }
 
-        for (int o = lane; o < item.count; o += 32) {
-            const float4 p1 = n1, p2 = n2;
-            n1 = m1; n2 = m2;
-            if (o + 64 < item.count) { m1 = ld_stream(q1 + (o - lane) + 64); m2 = ld_stream(q2 + (o - lane) + 64); }   // prefetch
+        for (int c = 0; c < n_chunks; c++, gchunk++) {
+            // refill the stage that was consumed one iteration ago (the __syncwarp below ordered its reads)
+            if (lane == 0 && c + BULK_STAGES - 1 < n_chunks) {
+                const int cc = c + BULK_STAGES - 1;
+                const int st = (int)((gchunk + BULK_STAGES - 1) % BULK_STAGES);
+                const uint32_t bytes = (uint32_t)min(32, item.count - 32 * cc) * 16u;
+                bar_expect(&s_bar[wib][st], 2 * bytes);
+                bulk_load(&s_obs[wib][st][0][0], g1 + 32 * cc, bytes, &s_bar[wib][st]);
+                bulk_load(&s_obs[wib][st][1][0], g2 + 32 * cc, bytes, &s_bar[wib][st]);
+            }
+            const int st = (int)(gchunk % BULK_STAGES);
+            bar_wait(&s_bar[wib][st], (uint32_t)((gchunk / BULK_STAGES) & 1));
+            const int o = 32 * c + lane;
+            if (o < item.count) {
+            const float4 p1 = s_obs[wib][st][0][lane], p2 = s_obs[wib][st][1][lane];
             // residual in fp64: res = d2*b2 - (d1*R*b1 - t)   (spherical_bundle_adjuster.cpp:896-916)
             const double bx = (double)p1.x, by = (double)p1.y, bz = (double)p1.z;
-            const double rx = fma(d2, (double)p2.x, t0) - (Rs[0] * bx + Rs[1] * by + Rs[2] * bz);
-            const double ry = fma(d2, (double)p2.y, t1) - (Rs[3] * bx + Rs[4] * by + Rs[5] * bz);
-            const double rz = fma(d2, (double)p2.z, t2) - (Rs[6] * bx + Rs[7] * by + Rs[8] * bz);
+            const double rx = fma(d2, (double)p2.x, u0) - (Rs[0] * bx + Rs[1] * by + Rs[2] * bz);
+            const double ry = fma(d2, (double)p2.y, u1) - (Rs[3] * bx + Rs[4] * by + Rs[5] * bz);
+            const double rz = fma(d2, (double)p2.z, u2) - (Rs[6] * bx + Rs[7] * by + Rs[8] * bz);
             const double s = rx * rx + ry * ry + rz * rz;
             // Huber: rho' = 1 (s <= a^2) or a/sqrt(s); rho = s or 2 a sqrt(s) - a^2
             double rho = s, w = 1.0;
@@ -558,6 +627,16 @@ __global__ void __launch_bounds__(EVAL_THREADS, 3) ba_rot_eval_kernel(EvalArgs E
                 rho = 2.0 * huber * (s * y) - hub2;
             }
             // weighted moments: S += w b b^T (6), C[b][a] += w b_b res_a (9), cost += rho/2
+            if (TRAN) {   // translation block: J = +I
+                acc[0] += w;
+                acc[1] = fma(w, rx, acc[1]); acc[2] = fma(w, ry, acc[2]); acc[3] = fma(w, rz, acc[3]);
+                acc[15] = fma(0.5, rho, acc[15]);
+                if (WRITE && E.res) {
+                    const int64_t i = item.start + o;
+                    const int64_t dst = E.perm ? (int64_t)E.perm[i] : i;
+                    E.res[3 * dst] = (float)rx; E.res[3 * dst + 1] = (float)ry; E.res[3 * dst + 2] = (float)rz;
+                }
+            } else {
             const double wx = w * bx, wy = w * by, wz = w * bz;
             acc[0] = fma(wx, bx, acc[0]); acc[1] = fma(wx, by, acc[1]); acc[2] = fma(wx, bz, acc[2]);
             acc[3] = fma(wy, by, acc[3]); acc[4] = fma(wy, bz, acc[4]); acc[5] = fma(wz, bz, acc[5]);
@@ -583,6 +662,9 @@ __global__ void __launch_bounds__(EVAL_THREADS, 3) ba_rot_eval_kernel(EvalArgs E
                     for (int a = 0; a < 9; a++) E.jac[9 * dst + a] = J[a];
                 }
             }
+            }   // !TRAN
+            }   // o < item.count
+            __syncwarp();   // every lane is done with this stage before lane 0 refills it
         }
         if (!uniform) {
 #pragma unroll
@@ -621,7 +703,7 @@ __global__ void __launch_bounds__(EVAL_THREADS, 3) ba_rot_eval_kernel(EvalArgs E
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    fold_items(E.partial, E.item_ptr, E.items ? E.n_items : (int)gridDim.x, E.n_cam, E.params, E.k.d1, E.blk_out);
+    fold_items(E.partial, E.item_ptr, E.items ? E.n_items : (int)gridDim.x, E.n_cam, E.params, E.k.d1, TRAN ? 1 : 0, E.blk_out);
     if (threadIdx.x == 0) *E.ticket = 0;
     if (MODE == 2) {
         __syncthreads();
@@ -689,6 +771,7 @@ struct sba_ba_problem {
     void* allreduce_user = nullptr;
     int eval_blocks = 1;
     int item_len = 32;
+    double* fixed = nullptr;          // translation-only solves: the fixed rotations [n_cam x 3] on the device
     const int* n_obs_dev = nullptr;   // actual observation count on the device (n_obs is then the capacity)
     bool borrowed = false;   // b1/b2 belong to the caller (fused pipeline): not returned to the cache
 };
@@ -699,7 +782,7 @@ static void free_problem(sba_ba_problem* p)
     sba::BlockCache& C = p->ctx->cache;
     if (p->borrowed) p->b1 = p->b2 = nullptr;
     void* dev[] = {p->b1, p->b2, p->perm, p->items, p->item_ptr, p->partial, p->params, p->x, p->xc, p->blk_cur, p->blk_cand, p->scale,
-                   p->state, p->ticket};
+                   p->state, p->ticket, p->fixed};
     for (void* d : dev) C.put(d, false);
     C.put(p->h_state, true);
     C.put(p->h_x, true);
@@ -727,7 +810,7 @@ static EvalArgs make_eval_args(sba_ba_problem* p, const double t[3], double d1, 
     E.b1 = p->b1; E.b2 = p->b2; E.perm = p->perm; E.items = p->items; E.item_ptr = p->item_ptr;
     E.item_len = p->item_len; E.n_obs = (int)p->n_obs; E.n_obs_dev = p->n_obs_dev;
     E.n_items = p->n_items; E.n_cam = p->n_cam; E.params = p->params; E.partial = p->partial;
-    E.blk_out = blk_out; E.ticket = p->ticket; E.res = res; E.jac = jac; E.done = nullptr;
+    E.blk_out = blk_out; E.ticket = p->ticket; E.res = res; E.jac = jac; E.done = nullptr; E.tvec = nullptr; E.tran = 0;
     E.k.t[0] = t[0]; E.k.t[1] = t[1]; E.k.t[2] = t[2];
     E.k.d1 = d1; E.k.d2 = d2; E.k.huber = huber;
     return E;
@@ -737,7 +820,7 @@ static LMArrays make_lm_arrays(sba_ba_problem* p)
 {
     LMArrays A;
     A.x = p->x; A.xc = p->xc; A.blk_cur = p->blk_cur; A.blk_cand = p->blk_cand; A.scale = p->scale;
-    A.params = p->params; A.st = p->state; A.n_cam = p->n_cam; A.d1 = 1.0;
+    A.params = p->params; A.st = p->state; A.n_cam = p->n_cam; A.d1 = 1.0; A.tran = 0;
     return A;
 }
 
@@ -759,13 +842,26 @@ static int launch_eval(sba_ba_problem* p, const EvalArgs& E, const LMArrays& A, 
     const bool big = p->n_cam > FOLD_IN_KERNEL_MAX_CAMS;
     const bool fuse = decide && !big && !p->allreduce;
     prof_begin(p->ctx, SBA_KERNEL_BA_EVAL);
-    if (big) ba_rot_eval_kernel<WRITE, 0><<<p->eval_blocks, EVAL_THREADS, 0, st>>>(E, A);
-    else if (fuse) ba_rot_eval_kernel<WRITE, 2><<<p->eval_blocks, EVAL_THREADS, 0, st>>>(E, A);
-    else ba_rot_eval_kernel<WRITE, 1><<<p->eval_blocks, EVAL_THREADS, 0, st>>>(E, A);
+    const dim3 grid(p->eval_blocks), block(EVAL_THREADS);
+    if (E.n_obs_dev && !WRITE && !E.tran && !big) {
+        if (fuse) ba_rot_eval_kernel<false, 2, false, true><<<grid, block, 0, st>>>(E, A);
+        else ba_rot_eval_kernel<false, 1, false, true><<<grid, block, 0, st>>>(E, A);
+    } else if (E.n_obs_dev) {
+        sba::set_error("device-side observation count is only supported for fused single-camera rotation solves");
+        return SBA_ERR_UNSUPPORTED;
+    } else if (E.tran) {
+        if (big) ba_rot_eval_kernel<WRITE, 0, true, false><<<grid, block, 0, st>>>(E, A);
+        else if (fuse) ba_rot_eval_kernel<WRITE, 2, true, false><<<grid, block, 0, st>>>(E, A);
+        else ba_rot_eval_kernel<WRITE, 1, true, false><<<grid, block, 0, st>>>(E, A);
+    } else {
+        if (big) ba_rot_eval_kernel<WRITE, 0, false, false><<<grid, block, 0, st>>>(E, A);
+        else if (fuse) ba_rot_eval_kernel<WRITE, 2, false, false><<<grid, block, 0, st>>>(E, A);
+        else ba_rot_eval_kernel<WRITE, 1, false, false><<<grid, block, 0, st>>>(E, A);
+    }
     prof_end(p->ctx, SBA_KERNEL_BA_EVAL);
     SBA_LAUNCHED(p->ctx);
     if (big) {
-        ba_fold_kernel<<<(p->n_cam + EVAL_WARPS - 1) / EVAL_WARPS, EVAL_THREADS, 0, st>>>(E.partial, E.item_ptr, p->n_cam, E.params, E.k.d1, E.blk_out, E.done);
+        ba_fold_kernel<<<(p->n_cam + EVAL_WARPS - 1) / EVAL_WARPS, EVAL_THREADS, 0, st>>>(E.partial, E.item_ptr, p->n_cam, E.params, E.k.d1, E.tran, E.blk_out, E.done);
         SBA_LAUNCHED(p->ctx);
     }
     SBA_CUDA(cudaGetLastError());
@@ -1031,7 +1127,19 @@ static int enqueue_chunk(sba_ba_problem* p, const EvalArgs& E, const LMArrays& A
 // (2) stream side, no synchronisation (capturable in a CUDA graph): mailboxes -> device, rotation
 // tables, the first chunk of evaluations, state (+ parameters) back to the mailboxes.
 // Evaluations that start after convergence return immediately (state.done).
-int ba_solve_enqueue(sba_ba_problem* p, const double t[3], double d1, double d2, double huber, int max_iter, int* launched)
+// Evaluation / LM arguments of a solve in either mode (rotation free: t uniform and fixed;
+// translation free: the rotations in p->fixed are fixed and t comes from the candidate vector).
+static void solve_args(sba_ba_problem* p, const double t[3], double d1, double d2, double huber, bool tran, EvalArgs* E, LMArrays* A)
+{
+    const double zero[3] = {0, 0, 0};
+    *E = make_eval_args(p, tran ? zero : t, d1, d2, huber, nullptr, nullptr, p->blk_cand);
+    E->done = &p->state->done;
+    *A = make_lm_arrays(p);
+    A->d1 = d1;
+    if (tran) { E->tvec = p->xc; E->tran = 1; A->tran = 1; }
+}
+
+int ba_solve_enqueue(sba_ba_problem* p, const double t[3], double d1, double d2, double huber, int max_iter, int* launched, bool tran)
 {
     sba_ctx* c = p->ctx;
     cudaStream_t st = c->stream;
@@ -1039,12 +1147,12 @@ int ba_solve_enqueue(sba_ba_problem* p, const double t[3], double d1, double d2,
     SBA_CUDA(cudaMemcpyAsync(p->x, p->h_x, (size_t)n_cam * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
     SBA_CUDA(cudaMemcpyAsync(p->xc, p->x, (size_t)n_cam * 3 * sizeof(double), cudaMemcpyDeviceToDevice, st));
     SBA_CUDA(cudaMemcpyAsync(p->state, p->h_state, sizeof(LMState), cudaMemcpyHostToDevice, st));
-    ba_cam_params_kernel<<<(n_cam + 127) / 128, 128, 0, st>>>(p->xc, n_cam, d1, p->params);
+    // rotation tables: from the starting rotations, or once from the fixed ones
+    ba_cam_params_kernel<<<(n_cam + 127) / 128, 128, 0, st>>>(tran ? p->fixed : p->xc, n_cam, d1, p->params);
     SBA_LAUNCHED(c);
-    EvalArgs E = make_eval_args(p, t, d1, d2, huber, nullptr, nullptr, p->blk_cand);
-    E.done = &p->state->done;
-    LMArrays A = make_lm_arrays(p);
-    A.d1 = d1;
+    EvalArgs E;
+    LMArrays A;
+    solve_args(p, t, d1, d2, huber, tran, &E, &A);
     const int n = std::min(LM_CHUNK, max_iter + 1);
     SBA_TRY(enqueue_chunk(p, E, A, n));
     *launched = n;
@@ -1053,7 +1161,7 @@ int ba_solve_enqueue(sba_ba_problem* p, const double t[3], double d1, double d2,
 
 // (3) wait for the enqueued chunk; keep going chunk by chunk until the solver reports done.
 int ba_solve_finish(sba_ba_problem* p, double* r_out, const double t[3], double d1, double d2, double huber, int max_iter, int launched,
-                    sba_solve_summary* summary)
+                    sba_solve_summary* summary, bool tran)
 {
     sba_ctx* c = p->ctx;
     cudaStream_t st = c->stream;
@@ -1061,10 +1169,9 @@ int ba_solve_finish(sba_ba_problem* p, double* r_out, const double t[3], double 
     const int max_evals = max_iter + 1;
     SBA_CUDA(cudaStreamSynchronize(st));
     if (!p->h_state->done && launched < max_evals) {
-        EvalArgs E = make_eval_args(p, t, d1, d2, huber, nullptr, nullptr, p->blk_cand);
-        E.done = &p->state->done;
-        LMArrays A = make_lm_arrays(p);
-        A.d1 = d1;
+        EvalArgs E;
+        LMArrays A;
+        solve_args(p, t, d1, d2, huber, tran, &E, &A);
         while (!p->h_state->done && launched < max_evals) {
             const int n = std::min(LM_CHUNK, max_evals - launched);
             SBA_TRY(enqueue_chunk(p, E, A, n));
@@ -1102,8 +1209,73 @@ int sba_ba_rot_solve(sba_ba_problem* p, double* r_inout, const double t[3], doub
     // h_x / h_state are pinned mailboxes of this problem; every earlier use ended with a synchronise
     ba_solve_prepare_host(p, r_inout, max_iter);
     int launched = 0;
-    SBA_TRY(ba_solve_enqueue(p, t, d1, d2, huber, max_iter, &launched));
-    return ba_solve_finish(p, r_inout, t, d1, d2, huber, max_iter, launched, summary);
+    SBA_TRY(ba_solve_enqueue(p, t, d1, d2, huber, max_iter, &launched, false));
+    return ba_solve_finish(p, r_inout, t, d1, d2, huber, max_iter, launched, summary, false);
+}
+
+static int upload_fixed(sba_ba_problem* p, const double* r_fixed)
+{
+    sba_ctx* c = p->ctx;
+    const size_t bytes = (size_t)p->n_cam * 3 * sizeof(double);
+    if (!p->fixed) SBA_CUDA(c->cache.get((void**)&p->fixed, bytes, false));
+    SBA_CUDA(cudaStreamSynchronize(c->stream));   // the pinned mailbox h_x is reused as the staging buffer
+    memcpy(p->h_x, r_fixed, bytes);
+    SBA_CUDA(cudaMemcpyAsync(p->fixed, p->h_x, bytes, cudaMemcpyHostToDevice, c->stream));
+    SBA_CUDA(cudaStreamSynchronize(c->stream));
+    return SBA_OK;
+}
+
+int sba_ba_tran_solve(sba_ba_problem* p, const double* r_fixed, double* t_inout, double d1, double d2, double huber, int max_iter,
+                      sba_solve_summary* summary)
+{
+    SBA_CHECK_ARG(p && r_fixed && t_inout && max_iter >= 0);
+    SBA_CUDA(cudaSetDevice(p->ctx->device));
+    SBA_TRY(upload_fixed(p, r_fixed));
+    ba_solve_prepare_host(p, t_inout, max_iter);
+    const double unused[3] = {0, 0, 0};
+    int launched = 0;
+    SBA_TRY(ba_solve_enqueue(p, unused, d1, d2, huber, max_iter, &launched, true));
+    return ba_solve_finish(p, t_inout, unused, d1, d2, huber, max_iter, launched, summary, true);
+}
+
+int sba_ba_tran_eval(sba_ba_problem* p, const double* r_fixed, const double* tv, double d1, double d2, double huber, float* res, double* H,
+                     double* g, double* cost, int mem)
+{
+    SBA_CHECK_ARG(p && r_fixed && tv);
+    sba_ctx* c = p->ctx;
+    SBA_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const int n_cam = p->n_cam;
+    SBA_TRY(upload_fixed(p, r_fixed));
+    SBA_TRY(upload_rotations(p, tv, p->xc));   // the translations ride in the candidate vector
+    ba_cam_params_kernel<<<(n_cam + 127) / 128, 128, 0, st>>>(p->fixed, n_cam, d1, p->params);
+    SBA_LAUNCHED(c);
+    float* d_res;
+    double *d_H, *d_g, *d_cost;
+    SBA_TRY(stage_out(c, res, (size_t)3 * p->n_obs, mem, SCR_OUT0, &d_res));
+    SBA_TRY(stage_out(c, H, (size_t)6 * n_cam, mem, SCR_OUT2, &d_H));
+    SBA_TRY(stage_out(c, g, (size_t)3 * n_cam, mem, SCR_OUT3, &d_g));
+    SBA_TRY(stage_out(c, cost, (size_t)n_cam, mem, SCR_OUT4, &d_cost));
+    const double zero[3] = {0, 0, 0};
+    EvalArgs E = make_eval_args(p, zero, d1, d2, huber, d_res, nullptr, p->blk_cand);
+    E.tvec = p->xc;
+    E.tran = 1;
+    LMArrays A = make_lm_arrays(p);
+    A.d1 = d1;
+    A.tran = 1;
+    if (d_res) SBA_TRY(launch_eval<true>(p, E, A, false, nullptr));
+    else SBA_TRY(launch_eval<false>(p, E, A, false, nullptr));
+    if (p->allreduce && p->allreduce(p->blk_cand, (int64_t)n_cam * 10, p->allreduce_user) != 0) {
+        sba::set_error("allreduce callback failed");
+        return SBA_ERR_COMM;
+    }
+    ba_unpack_blocks_kernel<<<(n_cam + 127) / 128, 128, 0, st>>>(p->blk_cand, n_cam, d_H, d_g, d_cost);
+    SBA_LAUNCHED(c);
+    SBA_TRY(copy_out(c, res, d_res, (size_t)3 * p->n_obs, mem));
+    SBA_TRY(copy_out(c, H, d_H, (size_t)6 * n_cam, mem));
+    SBA_TRY(copy_out(c, g, d_g, (size_t)3 * n_cam, mem));
+    SBA_TRY(copy_out(c, cost, d_cost, (size_t)n_cam, mem));
+    return finish(c, mem);
 }
 
 int sba_ba_rot_eval_timed(sba_ba_problem* p, const double* r, const double t[3], double d1, double d2, double huber, int materialise,

@@ -222,9 +222,9 @@ void pipeline_release(sba_ctx* c);
 
 // ba.cu: the LM solve in three parts so that the stream part can be captured in a CUDA graph
 void ba_solve_prepare_host(sba_ba_problem* p, const double* r0, int max_iter);
-int ba_solve_enqueue(sba_ba_problem* p, const double t[3], double d1, double d2, double huber, int max_iter, int* launched);
+int ba_solve_enqueue(sba_ba_problem* p, const double t[3], double d1, double d2, double huber, int max_iter, int* launched, bool tran = false);
 int ba_solve_finish(sba_ba_problem* p, double* r_out, const double t[3], double d1, double d2, double huber, int max_iter, int launched,
-                    sba_solve_summary* summary);
+                    sba_solve_summary* summary, bool tran = false);
 
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -155,3 +155,19 @@ def test_ba_oracle_multi_camera_blocks_are_independent():
         assert np.allclose(H[c], Hc[0], rtol=1e-12) and np.allclose(g[c], gc[0], rtol=1e-10, atol=1e-12)
     r, s = oracle.ba_rot_solve(b1, b2, cam, r0)
     assert np.abs(r - r_true).max() < 5e-4
+
+
+def test_ba_tran_only_oracle():
+    # translation block (spherical_bundle_adjuster.cpp:948-1002): d res / d t = +I
+    b1, b2, cam, r_true = synth.make_bearings(800, noise=0.0, seed=2)
+    t_true = np.array([[0.03, -0.02, 0.01]])
+    X2 = b2 - t_true
+    res, H, g, cost = oracle.ba_tran_eval(b1, X2, None, r_true, t_true)
+    assert np.abs(res).max() < 1e-14 and np.allclose(H[0], [800, 0, 0, 800, 0, 800])
+    tv, s = oracle.ba_tran_solve(b1, X2, None, r_true, np.zeros((1, 3)))
+    assert np.abs(tv - t_true).max() < 1e-9
+    eps = 1e-6
+    t0 = np.array([0.1, 0.2, -0.1])
+    c = lambda t: oracle.ba_tran_eval(b1, b2, None, r_true, t[None])[3][0]
+    fd = np.array([(c(t0 + eps * np.eye(3)[k]) - c(t0 - eps * np.eye(3)[k])) / (2 * eps) for k in range(3)])
+    assert np.abs(fd - oracle.ba_tran_eval(b1, b2, None, r_true, t0[None])[2][0]).max() < 1e-6
