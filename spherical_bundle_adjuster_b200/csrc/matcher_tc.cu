@@ -160,7 +160,7 @@ struct Partition {
 // ---- 1. prepare ------------------------------------------------------------------------------------------
 // 16 threads per row, 4 floats each.  Rows >= n are padding: zeros, norm = +inf (train) so they never win.
 __global__ void tc_prep_kernel(const float* __restrict__ x, int n, int n_pad, __nv_bfloat16* __restrict__ out, float* __restrict__ norm,
-                               float pad_norm)
+                               float pad_norm, float* __restrict__ max_norm /* optional: running maximum of the finite norms */)
 {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     const int row = gid >> 4, part = gid & 15;
@@ -182,22 +182,10 @@ __global__ void tc_prep_kernel(const float* __restrict__ x, int n, int n_pad, __
     __nv_bfloat16* dst = out + (size_t)row * KP;
     *reinterpret_cast<uint2*>(dst + part * 4) = *reinterpret_cast<const uint2*>(hi);
     *reinterpret_cast<uint2*>(dst + DIM + part * 4) = *reinterpret_cast<const uint2*>(lo);
-    if (part == 0) norm[row] = row < n ? s : pad_norm;
-}
-
-// Largest finite train norm (for the error bound), one CTA.
-__global__ void tc_max_norm_kernel(const float* __restrict__ nb, int nt, float* __restrict__ out)
-{
-    __shared__ float sh[256];
-    float m = 0.f;
-    for (int i = threadIdx.x; i < nt; i += 256) m = fmaxf(m, nb[i]);
-    sh[threadIdx.x] = m;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s) sh[threadIdx.x] = fmaxf(sh[threadIdx.x], sh[threadIdx.x + s]);
-        __syncthreads();
+    if (part == 0) {
+        norm[row] = row < n ? s : pad_norm;
+        if (max_norm && row < n) atomicMax((int*)max_norm, __float_as_int(s));   // non-negative floats order like ints
     }
-    if (threadIdx.x == 0) *out = sh[0];
 }
 
 // ---- 2. the tensor-core kernel ---------------------------------------------------------------------------
@@ -568,30 +556,68 @@ tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ 
 }
 
 // ---- 4. exact fallback for queued rows --------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+// A queued row needs an exact scan of the whole train set.  The scan of each row is cut into S ranges
+// handled by different CTAs (S chosen on the device from the queue length so that a handful of rows at
+// 64k train rows still use the whole chip, while thousands of rows fall back to one CTA per row), then
+// tc_fallback_merge_kernel merges a row's S partial top-2 lists in range order.
+constexpr int FB_THREADS = 128;
+constexpr int FB_MAX_SPLIT = 64;
+
+__host__ __device__ inline int fb_splits(int n_rows, int grid) { return n_rows <= 0 ? 1 : max(1, min(FB_MAX_SPLIT, (2 * grid) / n_rows)); }
+
+__global__ void __launch_bounds__(FB_THREADS)
 tc_fallback_kernel(const float* __restrict__ q, const float* __restrict__ t, int nt, const int* __restrict__ fb_list,
-                   const int* __restrict__ fb_count, Top2* __restrict__ top)
+                   const int* __restrict__ fb_count, Top2* __restrict__ parts)
 {
-    __shared__ Top2 sh[128];
-    __shared__ float qs[DIM];
+    __shared__ Top2 sh[FB_THREADS];
+    __shared__ __align__(16) float qs[DIM];
     const int n = *fb_count;
-    for (int k = blockIdx.x; k < n; k += gridDim.x) {
-        const int row = fb_list[k];
+    if (n == 0) return;
+    const int S = fb_splits(n, gridDim.x);
+    const int span = (nt + S - 1) / S;
+    for (int item = blockIdx.x; item < n * S; item += gridDim.x) {
+        const int row = fb_list[item / S], sp = item % S;
+        const int j0 = sp * span, j1 = min(nt, j0 + span);
         __syncthreads();
         if (threadIdx.x < DIM) qs[threadIdx.x] = q[(size_t)row * DIM + threadIdx.x];
         __syncthreads();
+        float qv[DIM];
+#pragma unroll
+        for (int k = 0; k < DIM / 4; k++) {
+            const float4 b = reinterpret_cast<const float4*>(qs)[k];
+            qv[4 * k] = b.x; qv[4 * k + 1] = b.y; qv[4 * k + 2] = b.z; qv[4 * k + 3] = b.w;
+        }
         Top2 best = top2_empty();
-        for (int j = threadIdx.x; j < nt; j += 128) {
-            const float d = __fsqrt_rn(l2sqr_opencv<DIM>(qs, t + (size_t)j * DIM));
+        for (int j = j0 + threadIdx.x; j < j1; j += FB_THREADS) {
+            float tv[DIM];
+            const float4* tp = reinterpret_cast<const float4*>(t + (size_t)j * DIM);
+#pragma unroll
+            for (int k = 0; k < DIM / 4; k++) {
+                const float4 a = __ldg(tp + k);
+                tv[4 * k] = a.x; tv[4 * k + 1] = a.y; tv[4 * k + 2] = a.z; tv[4 * k + 3] = a.w;
+            }
+            const float d = __fsqrt_rn(l2sqr_opencv<DIM>(qv, tv));
             top2_push_ordered(best, d, j);
         }
         sh[threadIdx.x] = best;
         __syncthreads();
-        for (int s = 64; s > 0; s >>= 1) {
+        for (int s = FB_THREADS / 2; s > 0; s >>= 1) {
             if ((int)threadIdx.x < s) sh[threadIdx.x] = top2_merge(sh[threadIdx.x], sh[threadIdx.x + s]);
             __syncthreads();
         }
-        if (threadIdx.x == 0) top[row] = sh[0];
+        if (threadIdx.x == 0) parts[item] = sh[0];
+    }
+}
+
+__global__ void tc_fallback_merge_kernel(const int* __restrict__ fb_list, const int* __restrict__ fb_count, const Top2* __restrict__ parts,
+                                         int scan_grid, Top2* __restrict__ top)
+{
+    const int n = *fb_count;
+    const int S = fb_splits(n, scan_grid);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        Top2 r = parts[(size_t)k * S];
+        for (int sp = 1; sp < S; sp++) r = top2_merge(r, parts[(size_t)k * S + sp]);
+        top[fb_list[k]] = r;
     }
 }
 
@@ -665,6 +691,9 @@ int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, 
     const size_t o_cv = off; off = align_up(off + (size_t)nq_pad * slots * 16);
     const size_t o_ci = off; off = align_up(off + (size_t)nq_pad * slots * 16);
     const size_t o_fl = off; off = align_up(off + (size_t)nq * 4);
+    const int fb_grid = 4 * c->sm_count;
+    const size_t fb_parts = std::max<size_t>((size_t)nq, (size_t)2 * fb_grid + FB_MAX_SPLIT);   // >= n_rows * fb_splits(n_rows, fb_grid) for every n_rows
+    const size_t o_fp = off; off = align_up(off + fb_parts * sizeof(Top2));
     const size_t o_misc = off; off = align_up(off + 64);
     SBA_TRY(c->scratch[SCR_WORK2].ensure(off, st));
     uint8_t* ws = c->scratch[SCR_WORK2].as<uint8_t>();
@@ -675,16 +704,15 @@ int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, 
     float4* d_cv = (float4*)(ws + o_cv);
     int4* d_ci = (int4*)(ws + o_ci);
     int* d_fl = (int*)(ws + o_fl);
+    Top2* d_fparts = (Top2*)(ws + o_fp);
     int* d_fb_count = (int*)(ws + o_misc);
     float* d_nbmax = (float*)(ws + o_misc + 4);
     float* d_dbg = (float*)(ws + o_misc + 8);
 
     SBA_CUDA(cudaMemsetAsync(ws + o_misc, 0, 64, st));
-    tc_prep_kernel<<<(nq_pad * 16 + 255) / 256, 256, 0, st>>>(d_q, nq, nq_pad, dA, d_na, 0.f);
+    tc_prep_kernel<<<(nq_pad * 16 + 255) / 256, 256, 0, st>>>(d_q, nq, nq_pad, dA, d_na, 0.f, nullptr);
     SBA_LAUNCHED(c);
-    tc_prep_kernel<<<(nt_pad * 16 + 255) / 256, 256, 0, st>>>(d_t, nt, nt_pad, dB, d_nb, INFINITY);
-    SBA_LAUNCHED(c);
-    tc_max_norm_kernel<<<1, 256, 0, st>>>(d_nb, nt, d_nbmax);
+    tc_prep_kernel<<<(nt_pad * 16 + 255) / 256, 256, 0, st>>>(d_t, nt, nt_pad, dB, d_nb, INFINITY, d_nbmax);   // d_nbmax zeroed by the memset above
     SBA_LAUNCHED(c);
 
     CUtensorMap map_a, map_b;
@@ -699,7 +727,9 @@ int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, 
 
     tc_rerank_kernel<<<(nq + RR_ROWS - 1) / RR_ROWS, RR_THREADS, 0, st>>>(d_q, nq, d_t, nt, d_na, d_nbmax, part, d_cv, d_ci, slots, d_top, d_fl, d_fb_count, d_dbg);
     SBA_LAUNCHED(c);
-    tc_fallback_kernel<<<std::min(nq, 4 * c->sm_count), 128, 0, st>>>(d_q, d_t, nt, d_fl, d_fb_count, d_top);
+    tc_fallback_kernel<<<fb_grid, FB_THREADS, 0, st>>>(d_q, d_t, nt, d_fl, d_fb_count, d_fparts);
+    SBA_LAUNCHED(c);
+    tc_fallback_merge_kernel<<<std::min((nq + 127) / 128, c->sm_count), 128, 0, st>>>(d_fl, d_fb_count, d_fparts, fb_grid, d_top);
     SBA_LAUNCHED(c);
     SBA_CUDA(cudaGetLastError());
     // diagnostics land in the pinned mailbox; read by sba_match_last_stats after a synchronise

@@ -1,0 +1,11 @@
+import sys, os
+sys.path.insert(0, "/root/repo")
+import numpy as np, torch
+from spherical_bundle_adjuster_b200 import Context, MATCH_TENSOR, synth
+ctx = Context(0)
+for n in (16384, 32768, 65536):
+    A, B, truth = synth.make_descriptors(n, n, 64, seed=n)
+    dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    m = ctx.match_two_image(dA, dB, 0.3, algo=MATCH_TENSOR)
+    st = ctx.match_stats()
+    print(n, "fallback rows", st.n_fallback_rows, "max_rel_err", st.max_rel_err, "tiles", st.n_tiles)
