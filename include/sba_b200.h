@@ -167,6 +167,22 @@ int sba_ba_problem_destroy(sba_ba_problem* p);
 typedef int (*sba_allreduce_fn)(void* device_buffer, int64_t count, void* user);
 int sba_ba_problem_set_allreduce(sba_ba_problem* p, sba_allreduce_fn fn, void* user);
 
+/* Peer-memory exchange (one process per GPU on one NVLink/NVSwitch box): instead of a host-launched
+ * all-reduce between kernels, the evaluation kernel itself publishes this rank's [n_cam x 10] blocks in
+ * a buffer every peer has mapped (CUDA IPC), waits for the peers' sequence flags over NVLink and sums all
+ * ranks' blocks in rank order -- identical bits on every rank, one kernel launch per LM iteration.
+ *   1. every rank: sba_comm_create(ctx, rank, world, max_cameras, &comm, handle)   (handle: 64 bytes)
+ *   2. ranks exchange the handles out of band (torch.distributed all_gather in the harness)
+ *   3. every rank: sba_comm_connect(comm, all_handles)     (world x 64 bytes, in rank order)
+ *   4. sba_ba_problem_set_comm(problem, comm) on the problem holding this rank's residual shard.
+ * All ranks must then issue the same sequence of solves/evaluations on their problems. */
+typedef struct sba_comm sba_comm;
+#define SBA_COMM_HANDLE_BYTES 64
+int sba_comm_create(sba_ctx* ctx, int rank, int world, int max_cameras, sba_comm** out, void* ipc_handle_out);
+int sba_comm_connect(sba_comm* comm, const void* ipc_handles);
+int sba_comm_destroy(sba_comm* comm);
+int sba_ba_problem_set_comm(sba_ba_problem* p, sba_comm* comm);
+
 /* One evaluation at rotations r [n_cam x 3] (axis-angle, host pointer always).
  * Outputs, each optional (NULL to skip), located per `mem`:
  *   res  n_obs x 3 fp32 and jac n_obs x 9 fp32 (row-major d res_a / d r_k): the RAW functor values

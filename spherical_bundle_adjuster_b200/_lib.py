@@ -20,7 +20,8 @@ EXPORTED = [
     "sba_ctx_synchronize", "sba_ctx_launch_count", "sba_ctx_set_profiling", "sba_ctx_kernel_ms", "sba_equi2cube", "sba_equi2cube_face", "sba_equi2cube_lut",
     "sba_cube2equi_points", "sba_pixels_to_bearings", "sba_knn2_ratio", "sba_match_last_stats", "sba_gather_matches",
     "sba_ba_problem_create", "sba_ba_problem_destroy", "sba_ba_problem_set_allreduce", "sba_ba_rot_eval",
-    "sba_ba_rot_solve", "sba_ba_rot_eval_timed", "sba_pair_rotation", "sba_ba_tran_eval", "sba_ba_tran_solve",
+    "sba_ba_rot_solve", "sba_ba_rot_eval_timed", "sba_pair_rotation", "sba_ba_tran_eval", "sba_ba_tran_solve", "sba_comm_create", "sba_comm_connect", "sba_comm_destroy",
+    "sba_ba_problem_set_comm",
 ]
 
 
@@ -83,6 +84,10 @@ def load():
     lib.sba_ba_problem_set_allreduce.argtypes = [vp, ALLREDUCE_FN, vp]
     lib.sba_ba_rot_eval.argtypes = [vp, vp, vp, f64, f64, f64, vp, vp, vp, vp, vp, i32]
     lib.sba_ba_rot_solve.argtypes = [vp, vp, vp, f64, f64, f64, i32, C.POINTER(SolveSummary)]
+    lib.sba_comm_create.argtypes = [vp, i32, i32, i32, C.POINTER(vp), vp]
+    lib.sba_comm_connect.argtypes = [vp, vp]
+    lib.sba_comm_destroy.argtypes = [vp]
+    lib.sba_ba_problem_set_comm.argtypes = [vp, vp]
     lib.sba_ba_tran_eval.argtypes = [vp, vp, vp, f64, f64, f64, vp, vp, vp, vp, i32]
     lib.sba_ba_tran_solve.argtypes = [vp, vp, vp, f64, f64, f64, i32, C.POINTER(SolveSummary)]
     lib.sba_ba_rot_eval_timed.argtypes = [vp, vp, vp, f64, f64, f64, i32, i32, C.POINTER(f32)]

@@ -249,6 +249,30 @@ class Context:
         return BAProblem(self, b1, b2, cam, n_cam)
 
 
+class PeerComm:
+    """Peer-memory exchange group for residual-sharded BA (wraps ``sba_comm``): one per process, all GPUs of
+    one NVLink box.  ``torch.distributed`` only carries the 64-byte IPC handles at set-up."""
+
+    def __init__(self, ctx: "Context", rank: int, world: int, max_cameras: int, group=None):
+        import torch.distributed as dist
+        self.ctx = ctx
+        self._lib = ctx._lib
+        self._h = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        check(self._lib.sba_comm_create(ctx._h, rank, world, max_cameras, C.byref(self._h), handle))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        blob = b"".join(handles)
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        check(self._lib.sba_comm_connect(self._h, buf))
+        dist.barrier(group=group)
+
+    def close(self):
+        if self._h:
+            self._lib.sba_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+
 def _bearings4(b, f32t):
     """n x 3 or n x 4 -> contiguous n x 4 float32 (x, y, z, 0)."""
     if _is_tensor(b):
@@ -310,6 +334,11 @@ class BAProblem:
 
         self._cb = _lib.ALLREDUCE_FN(_tramp)
         check(self._lib.sba_ba_problem_set_allreduce(self._h, self._cb, None))
+
+    def set_comm(self, comm: "PeerComm | None"):
+        """Sum the per-camera blocks over ranks inside the evaluation kernel (NVLink peer memory)."""
+        self._comm = comm   # keep it alive
+        check(self._lib.sba_ba_problem_set_comm(self._h, comm._h if comm is not None else None))
 
     @staticmethod
     def _r(r, n_cam):

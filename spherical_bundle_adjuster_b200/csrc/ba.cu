@@ -206,6 +206,94 @@ __device__ inline double block_max(double v, double* sh)
     return r;
 }
 
+// ---- peer-memory exchange of the per-camera blocks (one CTA) ------------------------------------------------
+constexpr int COMM_MAX_WORLD = 16;
+
+constexpr int COMM_MAX_SLICES = 64;
+constexpr int COMM_HEADER_BYTES = COMM_MAX_SLICES * 8;   // one sequence flag per slice, then the data
+
+struct CommDev {
+    double* data[COMM_MAX_WORLD];               // every rank's exchange buffer: [2 slots][stride] doubles
+    volatile unsigned long long* flag[COMM_MAX_WORLD];   // every rank's per-slice sequence flags [COMM_MAX_SLICES]
+    unsigned long long* seq;                    // this rank's private count of completed exchanges (local memory)
+    unsigned int* ticket;                       // multi-CTA exchange: last CTA to finish advances seq
+    int rank, world, stride;
+};
+
+// blk[0..count) <- sum over ranks, in rank order.  Called by ONE CTA with all EVAL_THREADS threads.
+// Slot = sequence parity: a rank can only overwrite a slot two exchanges later, and to get there it must have
+// seen every peer's NEXT flag, which a peer raises only after it finished reading this one.
+__device__ void comm_exchange(const CommDev& cd, double* __restrict__ blk, int count)
+{
+    const unsigned long long seq = *cd.seq;
+    const int slot = (int)(seq & 1) * cd.stride;
+    double* mine = cd.data[cd.rank] + slot;
+    for (int i = threadIdx.x; i < count; i += EVAL_THREADS) mine[i] = blk[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) cd.flag[cd.rank][0] = seq + 1;        // publish (slice 0 covers the whole vector here)
+    if ((int)threadIdx.x < cd.world) {                            // one thread per peer waits for its flag
+        const long long t0 = clock64();
+        while (cd.flag[threadIdx.x][0] < seq + 1) {
+            if (clock64() - t0 > 20000000000ll) __trap();        // a lost peer traps instead of hanging the GPU
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    for (int i = threadIdx.x; i < count; i += EVAL_THREADS) {
+        double s = 0;
+        for (int r = 0; r < cd.world; r++) s += __ldcv(cd.data[r] + slot + i);   // no stale cached copy of peer memory
+        blk[i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *cd.seq = seq + 1;
+    __syncthreads();
+}
+
+// Stand-alone exchange for large block vectors (many cameras): CTA b owns slice b of the vector and its own
+// sequence flag, so the NVLink reads of all slices run concurrently; the last CTA to finish advances seq.
+__global__ void __launch_bounds__(EVAL_THREADS) ba_exchange_kernel(CommDev cd, double* blk, int count, int slice_len,
+                                                                  const int* __restrict__ done)
+{
+    if (done && *done) return;
+    const unsigned long long seq = *cd.seq;
+    const int slot = (int)(seq & 1) * cd.stride;
+    const int i0 = blockIdx.x * slice_len, i1 = min(count, i0 + slice_len);
+    double* mine = cd.data[cd.rank] + slot;
+    for (int i = i0 + threadIdx.x; i < i1; i += EVAL_THREADS) mine[i] = blk[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) cd.flag[cd.rank][blockIdx.x] = seq + 1;
+    if ((int)threadIdx.x < cd.world) {
+        const long long t0 = clock64();
+        while (cd.flag[threadIdx.x][blockIdx.x] < seq + 1) {
+            if (clock64() - t0 > 20000000000ll) __trap();
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    for (int i = i0 + threadIdx.x; i < i1; i += EVAL_THREADS) {
+        double v[COMM_MAX_WORLD];
+#pragma unroll
+        for (int r = 0; r < COMM_MAX_WORLD; r++)
+            if (r < cd.world) v[r] = __ldcv(cd.data[r] + slot + i);      // all peers' loads in flight together
+        double sum = 0;
+#pragma unroll
+        for (int r = 0; r < COMM_MAX_WORLD; r++)
+            if (r < cd.world) sum += v[r];                               // rank order
+        blk[i] = sum;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int tk = atomicAdd(cd.ticket, 1u);
+        if (tk == gridDim.x - 1) {
+            *cd.ticket = 0;
+            *cd.seq = seq + 1;
+        }
+    }
+}
+
 // ---- Ceres-default Levenberg-Marquardt decision (single CTA) ---------------------------------------
 __device__ inline int solve3_spd(const double H[6], const double dd[3], const double rhs[3], double x[3])
 {
@@ -479,6 +567,7 @@ struct EvalArgs {
     unsigned int* ticket;
     const double* tvec;  // translation-only mode: per-camera t [n_cam x 3] on the device (NULL: the uniform k.t)
     int tran;            // 1: accumulate the translation-block moments {sum w, sum w res}
+    const CommDev* comm;  // peer-memory exchange after the fold (NULL: single GPU or host all-reduce callback)
     const int* done;  // LM solve: skip the whole evaluation once the solver has converged (NULL = always run)
     float* res;  // optional materialised outputs (caller order)
     float* jac;
@@ -705,6 +794,10 @@ __global__ void __launch_bounds__(EVAL_THREADS, 3) ba_rot_eval_kernel(EvalArgs E
     __threadfence();
     fold_items(E.partial, E.item_ptr, E.items ? E.n_items : (int)gridDim.x, E.n_cam, E.params, E.k.d1, TRAN ? 1 : 0, E.blk_out);
     if (threadIdx.x == 0) *E.ticket = 0;
+    if (E.comm) {          // sharded residuals: sum every rank's blocks over NVLink before anything looks at them
+        __syncthreads();
+        comm_exchange(*E.comm, E.blk_out, E.n_cam * 10);
+    }
     if (MODE == 2) {
         __syncthreads();
         lm_decide(A, sh);
@@ -771,6 +864,8 @@ struct sba_ba_problem {
     void* allreduce_user = nullptr;
     int eval_blocks = 1;
     int item_len = 32;
+    const CommDev* comm_host = nullptr; // host copy of the descriptor (kernel argument of the stand-alone exchange)
+    const CommDev* comm_dev = nullptr;  // device copy of the peer-exchange descriptor (owned by the sba_comm)
     double* fixed = nullptr;          // translation-only solves: the fixed rotations [n_cam x 3] on the device
     const int* n_obs_dev = nullptr;   // actual observation count on the device (n_obs is then the capacity)
     bool borrowed = false;   // b1/b2 belong to the caller (fused pipeline): not returned to the cache
@@ -810,7 +905,7 @@ static EvalArgs make_eval_args(sba_ba_problem* p, const double t[3], double d1, 
     E.b1 = p->b1; E.b2 = p->b2; E.perm = p->perm; E.items = p->items; E.item_ptr = p->item_ptr;
     E.item_len = p->item_len; E.n_obs = (int)p->n_obs; E.n_obs_dev = p->n_obs_dev;
     E.n_items = p->n_items; E.n_cam = p->n_cam; E.params = p->params; E.partial = p->partial;
-    E.blk_out = blk_out; E.ticket = p->ticket; E.res = res; E.jac = jac; E.done = nullptr; E.tvec = nullptr; E.tran = 0;
+    E.blk_out = blk_out; E.ticket = p->ticket; E.res = res; E.jac = jac; E.done = nullptr; E.tvec = nullptr; E.tran = 0; E.comm = p->comm_dev;
     E.k.t[0] = t[0]; E.k.t[1] = t[1]; E.k.t[2] = t[2];
     E.k.d1 = d1; E.k.d2 = d2; E.k.huber = huber;
     return E;
@@ -840,7 +935,7 @@ static int launch_eval(sba_ba_problem* p, const EvalArgs& E, const LMArrays& A, 
 {
     cudaStream_t st = p->ctx->stream;
     const bool big = p->n_cam > FOLD_IN_KERNEL_MAX_CAMS;
-    const bool fuse = decide && !big && !p->allreduce;
+    const bool fuse = decide && !big && !p->allreduce;   // a peer-memory comm does NOT prevent fusing: the exchange runs inside the kernel
     prof_begin(p->ctx, SBA_KERNEL_BA_EVAL);
     const dim3 grid(p->eval_blocks), block(EVAL_THREADS);
     if (E.n_obs_dev && !WRITE && !E.tran && !big) {
@@ -863,6 +958,12 @@ static int launch_eval(sba_ba_problem* p, const EvalArgs& E, const LMArrays& A, 
     if (big) {
         ba_fold_kernel<<<(p->n_cam + EVAL_WARPS - 1) / EVAL_WARPS, EVAL_THREADS, 0, st>>>(E.partial, E.item_ptr, p->n_cam, E.params, E.k.d1, E.tran, E.blk_out, E.done);
         SBA_LAUNCHED(p->ctx);
+        if (p->comm_dev) {
+            const int count = p->n_cam * 10;
+            const int slice_len = std::max(512, (count + sba::COMM_MAX_SLICES - 1) / sba::COMM_MAX_SLICES);
+            ba_exchange_kernel<<<(count + slice_len - 1) / slice_len, EVAL_THREADS, 0, st>>>(*p->comm_host, E.blk_out, count, slice_len, E.done);
+            SBA_LAUNCHED(p->ctx);
+        }
     }
     SBA_CUDA(cudaGetLastError());
     if (fused) *fused = fuse;
@@ -1044,6 +1145,98 @@ int sba_ba_problem_set_allreduce(sba_ba_problem* p, sba_allreduce_fn fn, void* u
     SBA_CHECK_ARG(p != nullptr);
     p->allreduce = fn;
     p->allreduce_user = user;
+    return SBA_OK;
+}
+
+}  // extern "C"
+
+// Host side of the peer-memory exchange.  Each rank's buffer: [64 per-slice sequence flags][2 slots x stride doubles].
+struct sba_comm {
+    sba_ctx* ctx = nullptr;
+    int rank = 0, world = 1, stride = 0;
+    uint8_t* local = nullptr;
+    void* peer_base[sba::COMM_MAX_WORLD] = {};
+    sba::CommDev host{};
+    sba::CommDev* dev = nullptr;
+    unsigned long long* seq = nullptr;
+    bool connected = false;
+};
+
+extern "C" {
+
+int sba_comm_create(sba_ctx* c, int rank, int world, int max_cameras, sba_comm** out, void* ipc_handle_out)
+{
+    SBA_CHECK_ARG(c && out && ipc_handle_out && world >= 1 && world <= sba::COMM_MAX_WORLD && rank >= 0 && rank < world && max_cameras >= 1);
+    static_assert(sizeof(cudaIpcMemHandle_t) == SBA_COMM_HANDLE_BYTES, "IPC handle size");
+    SBA_CUDA(cudaSetDevice(c->device));
+    sba_comm* m = new sba_comm();
+    m->ctx = c; m->rank = rank; m->world = world;
+    m->stride = (max_cameras * 10 + 15) / 16 * 16;
+    const size_t bytes = sba::COMM_HEADER_BYTES + (size_t)2 * m->stride * sizeof(double);
+    cudaIpcMemHandle_t h;
+    if (cudaMalloc((void**)&m->local, bytes) != cudaSuccess || cudaMemset(m->local, 0, bytes) != cudaSuccess ||
+        cudaIpcGetMemHandle(&h, m->local) != cudaSuccess) {
+        sba::set_error("sba_comm_create: %s", cudaGetErrorString(cudaGetLastError()));
+        if (m->local) cudaFree(m->local);
+        delete m;
+        return SBA_ERR_COMM;
+    }
+    memcpy(ipc_handle_out, &h, sizeof(h));
+    *out = m;
+    return SBA_OK;
+}
+
+int sba_comm_connect(sba_comm* m, const void* ipc_handles)
+{
+    SBA_CHECK_ARG(m && ipc_handles && !m->connected);
+    SBA_CUDA(cudaSetDevice(m->ctx->device));
+    for (int r = 0; r < m->world; r++) {
+        if (r == m->rank) m->peer_base[r] = m->local;
+        else {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, (const uint8_t*)ipc_handles + (size_t)r * SBA_COMM_HANDLE_BYTES, sizeof(h));
+            cudaError_t e = cudaIpcOpenMemHandle(&m->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                sba::set_error("cudaIpcOpenMemHandle(rank %d): %s (peers must be GPUs of one NVLink/PCIe-P2P box)", r, cudaGetErrorString(e));
+                return SBA_ERR_COMM;
+            }
+        }
+        m->host.flag[r] = (volatile unsigned long long*)m->peer_base[r];
+        m->host.data[r] = (double*)((uint8_t*)m->peer_base[r] + sba::COMM_HEADER_BYTES);
+    }
+    m->host.rank = m->rank; m->host.world = m->world; m->host.stride = m->stride;
+    SBA_CUDA(cudaMalloc((void**)&m->seq, 2 * sizeof(unsigned long long)));
+    SBA_CUDA(cudaMemset(m->seq, 0, 2 * sizeof(unsigned long long)));
+    m->host.seq = m->seq;
+    m->host.ticket = (unsigned int*)(m->seq + 1);
+    SBA_CUDA(cudaMalloc((void**)&m->dev, sizeof(sba::CommDev)));
+    SBA_CUDA(cudaMemcpy(m->dev, &m->host, sizeof(sba::CommDev), cudaMemcpyHostToDevice));
+    m->connected = true;
+    return SBA_OK;
+}
+
+int sba_comm_destroy(sba_comm* m)
+{
+    if (!m) return SBA_OK;
+    cudaSetDevice(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+    for (int r = 0; r < m->world; r++)
+        if (r != m->rank && m->peer_base[r]) cudaIpcCloseMemHandle(m->peer_base[r]);
+    if (m->dev) cudaFree(m->dev);
+    if (m->seq) cudaFree(m->seq);
+    if (m->local) cudaFree(m->local);
+    delete m;
+    return SBA_OK;
+}
+
+int sba_ba_problem_set_comm(sba_ba_problem* p, sba_comm* m)
+{
+    SBA_CHECK_ARG(p != nullptr);
+    if (!m) { p->comm_dev = nullptr; p->comm_host = nullptr; return SBA_OK; }
+    SBA_CHECK_ARG(m->connected && p->n_cam * 10 <= m->stride && m->ctx == p->ctx);
+    p->comm_dev = m->dev;
+    p->comm_host = &m->host;
+    p->allreduce = nullptr;
     return SBA_OK;
 }
 

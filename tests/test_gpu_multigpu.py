@@ -15,11 +15,11 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, exchange="nccl"):
     import torch
     import torch.distributed as dist
 
-    from spherical_bundle_adjuster_b200 import Context, sharding, synth
+    from spherical_bundle_adjuster_b200 import Context, PeerComm, sharding, synth
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -29,7 +29,12 @@ def _worker(rank, world, port, out):
     lo, hi = sharding.shard_range(n, rank, world)
     ctx = Context(rank)
     prob = ctx.ba_problem(b1f[lo:hi], b2f[lo:hi], cam[lo:hi], n_cam)
-    prob.set_allreduce(sharding.make_nccl_allreduce(torch.device("cuda", rank)))
+    comm = None
+    if exchange == "peer":      # blocks summed inside the evaluation kernel over NVLink peer memory
+        comm = PeerComm(ctx, rank, world, max_cameras=n_cam)
+        prob.set_comm(comm)
+    else:                       # host-launched NCCL all-reduce between the evaluation and the decision kernels
+        prob.set_allreduce(sharding.make_nccl_allreduce(torch.device("cuda", rank)))
     r0 = r_true + 0.05
     r, s = prob.solve(r0)
     ev = prob.eval(r0)                                  # all-reduced blocks of the full problem
@@ -38,12 +43,16 @@ def _worker(rank, world, port, out):
     if rank == 0:
         out.put((gathered, ev["H"], ev["cost"], b1f, b2f, cam, r0))
     dist.barrier()
-    prob.close(); ctx.close()
+    prob.close()
+    if comm is not None:
+        comm.close()
+    ctx.close()
     dist.destroy_process_group()
 
 
 @pytest.mark.timeout(300)
-def test_ba_residual_sharded_nccl():
+@pytest.mark.parametrize("exchange", ["nccl", "peer"])
+def test_ba_residual_sharded(exchange):
     import torch
     import torch.multiprocessing as mp
 
@@ -54,7 +63,7 @@ def test_ba_residual_sharded_nccl():
     mpc = mp.get_context("spawn")
     q = mpc.Queue()
     port = _free_port()
-    procs = [mpc.Process(target=_worker, args=(k, world, port, q)) for k in range(world)]
+    procs = [mpc.Process(target=_worker, args=(k, world, port, q, exchange)) for k in range(world)]
     for p in procs:
         p.start()
     gathered, H, cost, b1f, b2f, cam, r0 = q.get(timeout=240)

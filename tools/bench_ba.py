@@ -18,7 +18,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-from spherical_bundle_adjuster_b200 import Context, sharding, synth  # noqa: E402
+from spherical_bundle_adjuster_b200 import Context, PeerComm, sharding, synth  # noqa: E402
 
 
 def peaks():
@@ -52,6 +52,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     ctx = Context(local)
     hbm = peaks()
+    exchange = os.environ.get("SBA_EXCHANGE", "peer")     # peer (in-kernel NVLink exchange) | nccl (host-launched all-reduce)
+    comm = PeerComm(ctx, rank, world, max_cameras=1024) if (world > 1 and exchange == "peer") else None
     configs = [("C4: 1024 cameras, 1M observations (L2-resident: HBM fraction not claimed)", 1_000_000, 1024),
                ("C4 x64: 1024 cameras, 64M observations (2 GB >> L2)", 64_000_000, 1024),
                ("single camera, 16M observations", 16_000_000, 1)]
@@ -62,15 +64,21 @@ def main():
         prob = ctx.ba_problem(b1, b2, cam if n_cam > 1 else None, n_cam)
         del b1, b2, cam
         r0 = r_true + 0.02
-        out = {"config": name, "n_gpus": world, "obs_per_gpu": n}
+        out = {"config": name, "n_gpus": world, "obs_per_gpu": n, "exchange": exchange if world > 1 else None}
         if world == 1:
             for mat, bytes_per in ((False, 32), (True, 80)):
                 ms = prob.eval_timed(r0, materialise=mat, iters=20)
                 gbs = n * bytes_per / (ms * 1e-3) / 1e9
                 out["materialised" if mat else "fused"] = {"kernel_ms": ms, "evals_per_s": n / (ms * 1e-3), "bytes_per_obs": bytes_per,
                                                            "achieved_gbs": gbs, "peak_gbs": hbm, "frac": gbs / hbm}
+        elif comm is not None:
+            prob.set_comm(comm)
         else:
             prob.set_allreduce(sharding.make_nccl_allreduce(dev))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        prob.solve(r0, max_iter=50)                       # warm-up solve (allocations, NCCL communicator)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
