@@ -216,6 +216,25 @@ int sba_ba_tran_eval(sba_ba_problem* p, const double* r_fixed, const double* t, 
 int sba_ba_tran_solve(sba_ba_problem* p, const double* r_fixed, double* t_inout, double d1, double d2, double huber_delta,
                       int max_iter, sba_solve_summary* summary);
 
+/* Depth-only block (ba_spherical_costfunctor_d_only, spherical_bundle_adjuster.cpp:1005-1063): per match
+ * the free block is its own depth pair d[i] = (d1, d2) >= 0; residuals d2*b2 - (R(r)(d1*b1) - t) and the two
+ * barrier terms lambda*exp(-c*d); no loss function.  One camera pair only (n_cam == 1).
+ *   sba_ba_d_eval   raw functor values: res [n x 5], jac [n x 10] (row-major 5 x 2), cost [n] = 1/2 |res|^2.
+ *   sba_ba_d_solve  the first ceres::Solve of solve_problem (:196-197): LM over all blocks as ONE problem,
+ *                   bounds handled like Ceres (projection + projected Armijo line search).  d_inout [n x 2]
+ *                   lives where `mem` says; line_search_trials (optional) counts trial points beyond alpha = 1. */
+int sba_ba_d_eval(sba_ba_problem* p, const double r[3], const double t[3], const double* d, double lambda, double c,
+                  double* res, double* jac, double* cost, int mem);
+int sba_ba_d_solve(sba_ba_problem* p, const double r[3], const double t[3], double* d_inout, double lambda, double c,
+                   int max_iter, sba_solve_summary* summary, int* line_search_trials, int mem);
+
+/* spherical_bundle_adjuster::solve_problem (spherical_bundle_adjuster.cpp:183-217): depth stage, rotation
+ * stage, translation stage, each a full LM solve starting from the previous stage's result.  r_inout,
+ * t_inout: host 3-vectors (init_rot, init_tran); d_inout [n x 2] (init_d) where `mem` says;
+ * summaries: optional array of three (depth, rotation, translation). */
+int sba_ba_solve_problem(sba_ba_problem* p, double r_inout[3], double t_inout[3], double* d_inout, double huber_delta,
+                         int max_iter, sba_solve_summary summaries[3], int mem);
+
 /* Device-timed evaluation loop for benchmarking: runs `iters` fused evaluations (residual +
  * Jacobian + per-camera normal equations) back to back at r and returns the mean kernel time. */
 int sba_ba_rot_eval_timed(sba_ba_problem* p, const double* r, const double t[3], double d1, double d2, double huber_delta,

@@ -60,6 +60,10 @@ def _load():
                                      C.c_int, C.c_void_p]
     lib.orc_ba_tran_eval.argtypes = [f64p, f64p, i32p, C.c_int, f64p, f64p, C.c_int, C.c_double, C.c_double, C.c_double, f64p, f64p, f64p, f64p]
     lib.orc_ba_tran_solve.argtypes = [f64p, f64p, i32p, C.c_int, f64p, f64p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p]
+    lib.orc_ba_d_functor.argtypes = [f64p, f64p, f64p, f64p, f64p, C.c_double, C.c_double, f64p, f64p]
+    lib.orc_ba_d_solve.argtypes = [f64p, f64p, C.c_int, f64p, f64p, f64p, C.c_double, C.c_double, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    lib.orc_ls_next_step.restype = C.c_double
+    lib.orc_ls_next_step.argtypes = [C.c_double] * 5 + [C.c_int] + [C.c_double] * 5
     return lib
 
 
@@ -214,6 +218,37 @@ def ba_tran_solve(b1, b2, cam, r, t0, d1=1.0, d2=1.0, huber=1.0, max_iter=50):
     lib().orc_ba_tran_solve(_p(b1, C.c_double), _p(b2, C.c_double), _p(cam, C.c_int32), len(b1), _p(r, C.c_double), _p(tv, C.c_double), len(r),
                             d1, d2, huber, max_iter, C.byref(s))
     return tv, LMSummary(s.iterations, s.num_successful, s.termination, s.initial_cost, s.final_cost, s.final_radius)
+
+
+def ba_d_functor(b1, b2, r, t, d, lam=1.0, c=1.0):
+    """One depth-only residual block: (res[5], J[5, 2]).  spherical_bundle_adjuster.cpp:1005-1032."""
+    a = [np.ascontiguousarray(v, np.float64).reshape(-1) for v in (b1, b2, r, t, d)]
+    res, J = np.zeros(5), np.zeros((5, 2))
+    lib().orc_ba_d_functor(*[_p(v, C.c_double) for v in a], lam, c, _p(res, C.c_double), _p(J, C.c_double))
+    return res, J
+
+
+def ba_d_solve(b1, b2, r, t, d0, lam=1.0, c=1.0, max_iter=50):
+    """Depth-only stage of solve_problem (:196-197): returns (d [n, 2], LMSummary, line-search trials beyond alpha=1)."""
+    b1 = np.ascontiguousarray(b1, np.float64).reshape(-1, 3)
+    b2 = np.ascontiguousarray(b2, np.float64).reshape(-1, 3)
+    r = np.ascontiguousarray(r, np.float64).reshape(3)
+    t = np.ascontiguousarray(t, np.float64).reshape(3)
+    d = np.ascontiguousarray(d0, np.float64).reshape(-1, 2).copy()
+    assert len(d) == len(b1) == len(b2)
+    s, nls = _CSummary(), C.c_int(0)
+    lib().orc_ba_d_solve(_p(b1, C.c_double), _p(b2, C.c_double), len(b1), _p(r, C.c_double), _p(t, C.c_double), _p(d, C.c_double),
+                         lam, c, max_iter, C.byref(s), C.byref(nls))
+    return d, LMSummary(s.iterations, s.num_successful, s.termination, s.initial_cost, s.final_cost, s.final_radius), nls.value
+
+
+def ls_next_step(f0, g0, cur, prev=None, min_step=None, max_step=None):
+    """Ceres' Armijo step-size interpolation (CUBIC): cur/prev = (x, value, gradient)."""
+    xp, fp, gp = prev if prev is not None else (0.0, 0.0, 0.0)
+    xc, fc, gc = cur
+    lo = 1e-3 * xc if min_step is None else min_step
+    hi = 0.6 * xc if max_step is None else max_step
+    return lib().orc_ls_next_step(f0, g0, xp, fp, gp, int(prev is not None), xc, fc, gc, lo, hi)
 
 
 # ------------------------------------------------------------------ the real reference (oracle/_ref)

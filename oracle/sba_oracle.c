@@ -630,3 +630,318 @@ done:
     sum->final_cost = cost; sum->final_radius = radius;
     free(H); free(g); free(c); free(Hn); free(gn); free(cn); free(scale); free(step); free(xn);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Depth-only block.  spherical_bundle_adjuster.cpp:1005-1032 (functor:
+ * 3 reprojection residuals + the two barrier residuals lambda*exp(-c*d)), :1034-1063 (one residual
+ * block per match over its own 2-vector init_d[i], NO loss function, lower bound 0 on both depths,
+ * lambda = c = 1.0, r = init_rot and t = init_tran constants), solved first at :196-197.
+ *
+ * Ceres pieces restated (PARITY UNPINNED, see the header):
+ *   - TrustRegionMinimizer on a bounds-constrained problem: x0 projected on the box, ParameterBlock::Plus
+ *     projects x+delta on the box, gradient tolerance tested on |x - Plus(x, -g)|_inf, and each valid LM
+ *     step goes through a projected ARMIJO line search (LineSearch defaults: CUBIC interpolation with
+ *     value+directional derivative at every trial, sufficient_function_decrease 1e-4,
+ *     max_line_search_step_contraction 1e-3, min_line_search_step_contraction 0.6,
+ *     min_line_search_step_size 1e-9, max_num_line_search_step_size_iterations 20).  The model cost
+ *     change is NOT recomputed for the shortened step.
+ *   - polynomial.cc: FindInterpolatingPolynomial (square Vandermonde-type system),
+ *     MinimizePolynomial (mid point, both ends, REAL PARTS of all roots of the derivative inside the
+ *     interval), FindPolynomialRoots (closed forms for degree 1 and 2, eigenvalues otherwise -- here a
+ *     Durand-Kerner iteration, same roots).
+ *   - linear solver: every parameter block is touched by exactly one residual block, so all blocks are
+ *     eliminated and ITERATIVE_SCHUR's reduced system is empty: the step is the exact back-substitution,
+ *     one damped 2x2 Cholesky per match.
+ * ---------------------------------------------------------------------------------------- */
+
+/* res[5]; J[10] row-major 5x2: J[2*a+k] = d res_a / d d_k. */
+void orc_ba_d_functor(const double b1[3], const double b2[3], const double r[3], const double t[3], const double d[2],
+                      double lambda, double c, double res[5], double J[10])
+{
+    double X1[3] = {b1[0] * d[0], b1[1] * d[0], b1[2] * d[0]};
+    double X1r[3], u[3];
+    orc_angle_axis_rotate_point(r, X1, X1r);
+    for (int a = 0; a < 3; a++) res[a] = b2[a] * d[1] - (X1r[a] - t[a]);
+    double e0 = lambda * exp(-c * d[0]), e1 = lambda * exp(-c * d[1]);
+    res[3] = e0;
+    res[4] = e1;
+    if (J) {
+        orc_angle_axis_rotate_point(r, b1, u);      /* d X1r / d d0 = R b1 */
+        for (int a = 0; a < 3; a++) { J[2 * a] = -u[a]; J[2 * a + 1] = b2[a]; }
+        J[6] = -c * e0; J[7] = 0.0;
+        J[8] = 0.0;     J[9] = -c * e1;
+    }
+}
+
+typedef struct { double x, value, gradient; int value_valid, gradient_valid; } orc_sample;
+
+static double poly_eval(const double *p, int deg, double x)
+{
+    double v = 0;
+    for (int k = 0; k <= deg; k++) v = v * x + p[k];
+    return v;
+}
+
+/* polynomial.cc FindInterpolatingPolynomial: coefficients in decreasing powers; returns the degree. */
+static int poly_fit(const orc_sample *s, int ns, double *coef)
+{
+    int nc = 0;
+    for (int i = 0; i < ns; i++) nc += s[i].value_valid + s[i].gradient_valid;
+    int deg = nc - 1, row = 0;
+    double A[6][7];
+    for (int i = 0; i < ns; i++) {
+        if (s[i].value_valid) {
+            for (int j = 0; j <= deg; j++) A[row][j] = pow(s[i].x, deg - j);
+            A[row][nc] = s[i].value; row++;
+        }
+        if (s[i].gradient_valid) {
+            for (int j = 0; j < deg; j++) A[row][j] = (deg - j) * pow(s[i].x, deg - j - 1);
+            A[row][deg] = 0.0;
+            A[row][nc] = s[i].gradient; row++;
+        }
+    }
+    /* Gaussian elimination with full pivoting (Ceres: a rank-revealing dense solve) */
+    int colperm[6];
+    for (int j = 0; j < nc; j++) colperm[j] = j;
+    for (int k = 0; k < nc; k++) {
+        int pr = k, pc = k; double best = -1;
+        for (int i = k; i < nc; i++) for (int j = k; j < nc; j++) if (fabs(A[i][j]) > best) { best = fabs(A[i][j]); pr = i; pc = j; }
+        if (pr != k) for (int j = 0; j <= nc; j++) { double tmp = A[k][j]; A[k][j] = A[pr][j]; A[pr][j] = tmp; }
+        if (pc != k) { for (int i = 0; i < nc; i++) { double tmp = A[i][k]; A[i][k] = A[i][pc]; A[i][pc] = tmp; } int ti = colperm[k]; colperm[k] = colperm[pc]; colperm[pc] = ti; }
+        if (A[k][k] == 0.0) continue;
+        for (int i = k + 1; i < nc; i++) {
+            double f = A[i][k] / A[k][k];
+            for (int j = k; j <= nc; j++) A[i][j] -= f * A[k][j];
+        }
+    }
+    double y[6];
+    for (int k = nc - 1; k >= 0; k--) {
+        double v = A[k][nc];
+        for (int j = k + 1; j < nc; j++) v -= A[k][j] * y[j];
+        y[k] = (A[k][k] != 0.0) ? v / A[k][k] : 0.0;
+    }
+    for (int k = 0; k < nc; k++) coef[colperm[k]] = y[k];
+    return deg;
+}
+
+/* Real parts of all roots of p (degree deg, decreasing powers).  Returns how many were written. */
+static int poly_root_real_parts(const double *p_in, int deg_in, double *re)
+{
+    const double *p = p_in; int deg = deg_in;
+    while (deg > 0 && p[0] == 0.0) { p++; deg--; }          /* RemoveLeadingZeros */
+    if (deg == 0) return 0;
+    if (deg == 1) { re[0] = -p[1] / p[0]; return 1; }
+    if (deg == 2) {                                          /* FindQuadraticPolynomialRoots */
+        double a = p[0], b = p[1], c = p[2], D = b * b - 4 * a * c, sD = sqrt(fabs(D));
+        if (D >= 0) {
+            if (b >= 0) { re[0] = (-b - sD) / (2.0 * a); re[1] = (2.0 * c) / (-b - sD); }
+            else { re[0] = (2.0 * c) / (-b + sD); re[1] = (-b + sD) / (2.0 * a); }
+        } else { re[0] = re[1] = -b / (2.0 * a); }
+        return 2;
+    }
+    /* Durand-Kerner on the monic polynomial, complex arithmetic by hand (degree <= 4 here) */
+    double m[8], zr[8], zi[8], bound = 0;
+    for (int k = 0; k <= deg; k++) m[k] = p[k] / p[0];
+    for (int k = 1; k <= deg; k++) bound = fmax(bound, fabs(m[k]));
+    bound = 1.0 + bound;
+    for (int k = 0; k < deg; k++) {                          /* spiral of starting points */
+        double ang = 2.0 * M_PI * k / deg + 0.4, rad = bound * (0.5 + 0.5 * (k + 1) / deg);
+        zr[k] = rad * cos(ang); zi[k] = rad * sin(ang);
+    }
+    for (int it = 0; it < 2000; it++) {
+        double change = 0;
+        for (int k = 0; k < deg; k++) {
+            double pr = 1.0, pi = 0.0;                       /* p(z_k), Horner */
+            for (int j = 1; j <= deg; j++) { double nr = pr * zr[k] - pi * zi[k] + m[j], ni = pr * zi[k] + pi * zr[k]; pr = nr; pi = ni; }
+            double qr = 1.0, qi = 0.0;                       /* prod (z_k - z_j) */
+            for (int j = 0; j < deg; j++) if (j != k) {
+                double dr = zr[k] - zr[j], di = zi[k] - zi[j];
+                double nr = qr * dr - qi * di, ni = qr * di + qi * dr; qr = nr; qi = ni;
+            }
+            double den = qr * qr + qi * qi;
+            if (den == 0.0) { zr[k] += 1e-8 * bound; continue; }
+            double wr = (pr * qr + pi * qi) / den, wi = (pi * qr - pr * qi) / den;
+            zr[k] -= wr; zi[k] -= wi;
+            change = fmax(change, fabs(wr) + fabs(wi));
+        }
+        if (change <= 1e-15 * bound) break;
+    }
+    for (int k = 0; k < deg; k++) re[k] = zr[k];
+    return deg;
+}
+
+/* polynomial.cc MinimizePolynomial */
+static double poly_minimize(const double *p, int deg, double x_min, double x_max)
+{
+    double best_x = 0.5 * (x_min + x_max), best_v = poly_eval(p, deg, best_x);
+    double v = poly_eval(p, deg, x_min);
+    if (v < best_v) { best_v = v; best_x = x_min; }
+    v = poly_eval(p, deg, x_max);
+    if (v < best_v) { best_v = v; best_x = x_max; }
+    if (deg <= 1) return best_x;
+    double dp[6], re[6];
+    for (int k = 0; k < deg; k++) dp[k] = (deg - k) * p[k];
+    int nr = poly_root_real_parts(dp, deg - 1, re);
+    for (int k = 0; k < nr; k++) {
+        if (re[k] < x_min || re[k] > x_max) continue;
+        v = poly_eval(p, deg, re[k]);
+        if (v < best_v) { best_v = v; best_x = re[k]; }
+    }
+    return best_x;
+}
+
+/* line_search.cc LineSearch::InterpolatingPolynomialMinimizingStepSize, CUBIC interpolation */
+static double ls_next_step(const orc_sample *lower, const orc_sample *prev, const orc_sample *cur, double min_step, double max_step)
+{
+    if (!cur->value_valid) return fmin(fmax(cur->x * 0.5, min_step), max_step);
+    orc_sample s[3]; int ns = 0;
+    s[ns++] = *lower; s[ns++] = *cur;
+    if (prev->value_valid) s[ns++] = *prev;
+    double coef[6];
+    int deg = poly_fit(s, ns, coef);
+    return poly_minimize(coef, deg, min_step, max_step);
+}
+
+/* exported for the unit test of the polynomial machinery */
+double orc_ls_next_step(double f0, double g0, double xp, double fp, double gp, int prev_valid, double xc, double fc, double gc,
+                        double min_step, double max_step)
+{
+    orc_sample lo = {0.0, f0, g0, 1, 1}, pv = {xp, fp, gp, prev_valid, prev_valid}, cu = {xc, fc, gc, 1, 1};
+    return ls_next_step(&lo, &pv, &cu, min_step, max_step);
+}
+
+/* cost (and gradient, if grad != NULL) at a point that is already feasible */
+static double d_cost_grad(const double *b1, const double *b2, int n, const double r[3], const double t[3], const double *x,
+                          double lambda, double c, double *grad)
+{
+    double cost = 0;
+#pragma omp parallel for reduction(+ : cost) schedule(static)
+    for (int i = 0; i < n; i++) {
+        double f[5], J[10];
+        orc_ba_d_functor(b1 + 3 * i, b2 + 3 * i, r, t, x + 2 * i, lambda, c, f, grad ? J : NULL);
+        double s = 0;
+        for (int a = 0; a < 5; a++) s += f[a] * f[a];
+        cost += 0.5 * s;
+        if (grad) for (int k = 0; k < 2; k++) {
+            double gk = 0;
+            for (int a = 0; a < 5; a++) gk += J[2 * a + k] * f[a];
+            grad[2 * i + k] = gk;
+        }
+    }
+    return cost;
+}
+
+/* d: n x 2 depths, updated in place.  ls_evals (optional): line-search trial points beyond alpha = 1. */
+void orc_ba_d_solve(const double *b1, const double *b2, int n, const double r[3], const double t[3], double *d,
+                    double lambda, double c, int max_iter, orc_lm_summary *sum, int *ls_evals)
+{
+    const double min_diag = 1e-6, max_diag = 1e32, min_rel_dec = 1e-3;
+    const double ftol = 1e-6, gtol = 1e-10, ptol = 1e-8, max_radius = 1e16, min_radius = 1e-32;
+    const double ls_suff = 1e-4, ls_max_contr = 1e-3, ls_min_contr = 0.6, ls_min_step = 1e-9;
+    const int ls_max_iter = 20;
+    double radius = 1e4, dec_factor = 2.0;
+    int consecutive_invalid = 0, n_ls = 0;
+    const int np = 2 * n;
+    double *g = malloc(sizeof(double) * np), *scale = malloc(sizeof(double) * np), *delta = malloc(sizeof(double) * np);
+    double *xc = malloc(sizeof(double) * np), *gc = malloc(sizeof(double) * np), *H = malloc(sizeof(double) * 3 * n);
+
+    for (int k = 0; k < np; k++) d[k] = fmax(d[k], 0.0);        /* IterationZero: project on the box */
+    double cost = d_cost_grad(b1, b2, n, r, t, d, lambda, c, g);
+    sum->initial_cost = cost; sum->iterations = 0; sum->num_successful = 0; sum->termination = 0;
+    int fresh = 1, first = 1;
+
+    for (;;) {
+        /* FinalizeIterationAndCheckIfMinimizerCanContinue: iteration limit, gradient, radius */
+        if (sum->iterations >= max_iter) { sum->termination = 0; break; }
+        if (fresh) {
+            /* J^T J blocks at x (the Jacobian only changes when x does) */
+            for (int i = 0; i < n; i++) {
+                double f[5], J[10];
+                orc_ba_d_functor(b1 + 3 * i, b2 + 3 * i, r, t, d + 2 * i, lambda, c, f, J);
+                double h00 = 0, h01 = 0, h11 = 0;
+                for (int a = 0; a < 5; a++) { h00 += J[2 * a] * J[2 * a]; h01 += J[2 * a] * J[2 * a + 1]; h11 += J[2 * a + 1] * J[2 * a + 1]; }
+                H[3 * i] = h00; H[3 * i + 1] = h01; H[3 * i + 2] = h11;
+                if (first) { scale[2 * i] = 1.0 / (1.0 + sqrt(h00)); scale[2 * i + 1] = 1.0 / (1.0 + sqrt(h11)); }
+            }
+            first = 0; fresh = 0;
+        }
+        double gmax = 0;
+        for (int k = 0; k < np; k++) gmax = fmax(gmax, fabs(d[k] - fmax(d[k] - g[k], 0.0)));
+        if (gmax <= gtol) { sum->termination = 2; break; }
+        if (radius < min_radius) { sum->termination = 4; break; }
+        sum->iterations++;
+
+        /* LevenbergMarquardtStrategy::ComputeStep on the column-scaled Jacobian, block by block */
+        double model_dec = 0, gdot = 0, dinf = 0, x_norm2 = 0;
+        int bad = 0;
+        for (int i = 0; i < n; i++) {
+            const double s0 = scale[2 * i], s1 = scale[2 * i + 1];
+            double a00 = H[3 * i] * s0 * s0, a01 = H[3 * i + 1] * s0 * s1, a11 = H[3 * i + 2] * s1 * s1;
+            double g0 = g[2 * i] * s0, g1 = g[2 * i + 1] * s1;
+            double d0 = fmin(fmax(a00, min_diag), max_diag) / radius, d1 = fmin(fmax(a11, min_diag), max_diag) / radius;
+            double m00 = a00 + d0, m11 = a11 + d1;
+            if (!(m00 > 0.0)) { bad = 1; break; }
+            double l00 = sqrt(m00), l10 = a01 / l00, t11 = m11 - l10 * l10;
+            if (!(t11 > 0.0)) { bad = 1; break; }
+            double l11 = sqrt(t11);
+            double y0 = -g0 / l00, y1 = (-g1 - l10 * y0) / l11;
+            double ds1 = y1 / l11, ds0 = (y0 - l10 * ds1) / l00;
+            double Hd0 = a00 * ds0 + a01 * ds1, Hd1 = a01 * ds0 + a11 * ds1;
+            model_dec -= (g0 * ds0 + g1 * ds1) + 0.5 * (ds0 * Hd0 + ds1 * Hd1);
+            delta[2 * i] = ds0 * s0; delta[2 * i + 1] = ds1 * s1;
+            gdot += g[2 * i] * delta[2 * i] + g[2 * i + 1] * delta[2 * i + 1];
+            dinf = fmax(dinf, fmax(fabs(delta[2 * i]), fabs(delta[2 * i + 1])));
+            x_norm2 += d[2 * i] * d[2 * i] + d[2 * i + 1] * d[2 * i + 1];
+        }
+        if (bad || !(model_dec > 0.0)) {
+            if (++consecutive_invalid >= 5) { sum->termination = 4; break; }
+            radius *= 0.5;
+            continue;
+        }
+        consecutive_invalid = 0;
+
+        /* TrustRegionMinimizer::DoLineSearch: projected Armijo search along delta, first trial alpha = 1 */
+        double alpha = 1.0;
+        {
+            orc_sample lower = {0.0, cost, gdot, 1, 1}, prev = {0, 0, 0, 0, 0}, cur;
+            int ls_it = 0, ok = 1;
+            double a = 1.0;
+            for (;;) {
+                for (int k = 0; k < np; k++) xc[k] = fmax(d[k] + a * delta[k], 0.0);
+                double v = d_cost_grad(b1, b2, n, r, t, xc, lambda, c, gc), dg = 0;
+                for (int k = 0; k < np; k++) dg += delta[k] * gc[k];
+                cur.x = a; cur.value = v; cur.gradient = dg; cur.value_valid = cur.gradient_valid = isfinite(v) ? 1 : 0;
+                if (cur.value_valid && !(v > cost + ls_suff * gdot * a)) break;
+                if (++ls_it >= ls_max_iter) { ok = 0; break; }
+                double na = ls_next_step(&lower, &prev, &cur, ls_max_contr * a, ls_min_contr * a);
+                if (na * dinf < ls_min_step) { ok = 0; break; }
+                prev = cur; a = na; n_ls++;
+            }
+            if (ok) alpha = a;
+        }
+
+        /* ComputeCandidatePointAndEvaluateCost */
+        double step_norm2 = 0;
+        for (int k = 0; k < np; k++) { xc[k] = fmax(d[k] + alpha * delta[k], 0.0); step_norm2 += (d[k] - xc[k]) * (d[k] - xc[k]); }
+        double new_cost = d_cost_grad(b1, b2, n, r, t, xc, lambda, c, gc);
+
+        if (sqrt(step_norm2) <= ptol * (sqrt(x_norm2) + ptol)) { sum->termination = 3; break; }
+        double cost_change = cost - new_cost;
+        if (fabs(cost_change) <= ftol * cost) { sum->termination = 1; break; }
+        double rel_dec = cost_change / model_dec;
+        if (rel_dec > min_rel_dec) {
+            memcpy(d, xc, sizeof(double) * np);
+            memcpy(g, gc, sizeof(double) * np);
+            cost = new_cost; fresh = 1;
+            sum->num_successful++;
+            double q = 2.0 * rel_dec - 1.0;
+            radius = fmin(max_radius, radius / fmax(1.0 / 3.0, 1.0 - q * q * q));
+            dec_factor = 2.0;
+        } else {
+            radius = radius / dec_factor; dec_factor *= 2.0;
+        }
+    }
+    sum->final_cost = cost; sum->final_radius = radius;
+    if (ls_evals) *ls_evals = n_ls;
+    free(g); free(scale); free(delta); free(xc); free(gc); free(H);
+}

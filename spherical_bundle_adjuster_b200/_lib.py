@@ -21,7 +21,7 @@ EXPORTED = [
     "sba_cube2equi_points", "sba_pixels_to_bearings", "sba_knn2_ratio", "sba_match_last_stats", "sba_gather_matches",
     "sba_ba_problem_create", "sba_ba_problem_destroy", "sba_ba_problem_set_allreduce", "sba_ba_rot_eval",
     "sba_ba_rot_solve", "sba_ba_rot_eval_timed", "sba_pair_rotation", "sba_ba_tran_eval", "sba_ba_tran_solve", "sba_comm_create", "sba_comm_connect", "sba_comm_destroy",
-    "sba_ba_problem_set_comm",
+    "sba_ba_problem_set_comm", "sba_ba_d_eval", "sba_ba_d_solve", "sba_ba_solve_problem",
 ]
 
 
@@ -90,6 +90,9 @@ def load():
     lib.sba_ba_problem_set_comm.argtypes = [vp, vp]
     lib.sba_ba_tran_eval.argtypes = [vp, vp, vp, f64, f64, f64, vp, vp, vp, vp, i32]
     lib.sba_ba_tran_solve.argtypes = [vp, vp, vp, f64, f64, f64, i32, C.POINTER(SolveSummary)]
+    lib.sba_ba_d_eval.argtypes = [vp, vp, vp, vp, f64, f64, vp, vp, vp, i32]
+    lib.sba_ba_d_solve.argtypes = [vp, vp, vp, vp, f64, f64, i32, C.POINTER(SolveSummary), C.POINTER(i32), i32]
+    lib.sba_ba_solve_problem.argtypes = [vp, vp, vp, vp, f64, i32, C.POINTER(SolveSummary * 3), i32]
     lib.sba_ba_rot_eval_timed.argtypes = [vp, vp, vp, f64, f64, f64, i32, i32, C.POINTER(f32)]
     lib.sba_pair_rotation.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, vp, i32, i32, vp, vp, f32, vp, vp, f64, f64, f64, i32,
                                       vp, vp, vp, C.POINTER(PairResult), i32]

@@ -390,6 +390,42 @@ class BAProblem:
         check(self._lib.sba_ba_tran_solve(self._h, _ptr(r), _ptr(tv), d1, d2, huber, max_iter, C.byref(s)))
         return tv, s
 
+    # ---- depth-only block and the three-stage sequence (single camera pair) --------------------------------
+    def _d(self, d):
+        d = np.ascontiguousarray(d, np.float64).reshape(-1, 2)
+        if len(d) != self.n_obs:
+            raise ValueError(f"expected {self.n_obs} depth pairs, got {len(d)}")
+        return d
+
+    def d_eval(self, r, t, d, lam=1.0, c=1.0):
+        """Raw depth-only functor values (res [n, 5], jac [n, 5, 2], cost [n]); spherical_bundle_adjuster.cpp:1005-1032."""
+        r, t, d = self._r(r, 1).reshape(3), np.ascontiguousarray(t, np.float64).reshape(3), self._d(d)
+        res, jac, cost = np.empty((self.n_obs, 5)), np.empty((self.n_obs, 5, 2)), np.empty(self.n_obs)
+        check(self._lib.sba_ba_d_eval(self._h, _ptr(r), _ptr(t), _ptr(d), lam, c, _ptr(res), _ptr(jac), _ptr(cost), SBA_MEM_HOST))
+        return res, jac, cost
+
+    def d_solve(self, r, t, d0, lam=1.0, c=1.0, max_iter=50):
+        """Depth stage of solve_problem (:196-197): returns (d [n, 2], summary, line-search trials beyond alpha = 1)."""
+        r, t = self._r(r, 1).reshape(3), np.ascontiguousarray(t, np.float64).reshape(3)
+        if _is_tensor(d0) and d0.is_cuda:   # device mode: depths stay in HBM
+            d = d0.to(torch.float64).reshape(-1, 2).contiguous().clone()
+            if d.shape[0] != self.n_obs:
+                raise ValueError(f"expected {self.n_obs} depth pairs, got {d.shape[0]}")
+            mem = SBA_MEM_DEVICE
+        else:
+            d, mem = self._d(d0).copy(), SBA_MEM_HOST
+        s, nls = _lib.SolveSummary(), C.c_int32(0)
+        check(self._lib.sba_ba_d_solve(self._h, _ptr(r), _ptr(t), _ptr(d), lam, c, max_iter, C.byref(s), C.byref(nls), mem))
+        return d, s, int(nls.value)
+
+    def solve_problem(self, r0, t0, d0, huber=1.0, max_iter=50):
+        """spherical_bundle_adjuster::solve_problem (:183-217): depth -> rotation -> translation.
+        Returns (r [3], t [3], d [n, 2], [summary_d, summary_rot, summary_tran])."""
+        r, t, d = self._r(r0, 1).reshape(3).copy(), np.ascontiguousarray(t0, np.float64).reshape(3).copy(), self._d(d0).copy()
+        sums = (_lib.SolveSummary * 3)()
+        check(self._lib.sba_ba_solve_problem(self._h, _ptr(r), _ptr(t), _ptr(d), huber, max_iter, C.byref(sums), SBA_MEM_HOST))
+        return r, t, d, list(sums)
+
     def eval_timed(self, r, t=(0.0, 0.0, 0.0), d1=1.0, d2=1.0, huber=1.0, materialise=False, iters=20) -> float:
         r = self._r(r, self.n_cam)
         t = np.ascontiguousarray(t, np.float64)

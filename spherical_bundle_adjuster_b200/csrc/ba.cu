@@ -1284,6 +1284,11 @@ int sba_ba_rot_eval(sba_ba_problem* p, const double* r, const double t[3], doubl
 
 namespace sba {
 
+BaView ba_problem_view(sba_ba_problem* p)
+{
+    return BaView{p->ctx, p->b1, p->b2, p->n_obs, p->n_cam, p->n_obs_dev};
+}
+
 constexpr int LM_CHUNK = 6;   // evaluations enqueued between two looks at the solver state
 
 // (1) host side only: starting point and a fresh solver state into the problem's pinned mailboxes.

@@ -217,6 +217,18 @@ inline void prof_end(sba_ctx* c, int id)
 int ba_problem_create_impl(sba_ctx* c, const float* b1, const float* b2, const int32_t* cam, int64_t n_obs, int n_cam, int mem, bool borrow,
                            const int* d_n_obs, sba_ba_problem** out);
 
+// ba.cu: what the other translation units may see of a problem (ba_depth.cu runs its own kernels over the
+// same observations)
+struct BaView {
+    sba_ctx* ctx;
+    const float4* b1;
+    const float4* b2;
+    int64_t n_obs;
+    int n_cam;
+    const int* n_obs_dev;
+};
+BaView ba_problem_view(sba_ba_problem* p);
+
 // pipeline.cu: drop the cached pair graphs (context teardown)
 void pipeline_release(sba_ctx* c);
 

@@ -1,6 +1,8 @@
 // facade_demo.cpp -- exercises the drop-in classes end to end on files written by the Python tests:
 //   facade_demo <dir>   reads <dir>/{im.bin,desc1.bin,desc2.bin,key1.bin,key2.bin,meta.txt}
 //                       writes <dir>/{strip.bin,face3.bin,matches.bin,rot.bin}
+//                       and, when <dir>/sp_b1.bin is there (sp_b1, sp_b2: n x 3 doubles; sp_init: r0, t0, d0),
+//                       runs solve_problem and writes <dir>/sp_out.bin (r, t, iterations of the 3 stages, d [n x 2])
 // (tests/test_gpu_facade.py compares those with the oracle).
 #include <cstdio>
 #include <fstream>
@@ -59,6 +61,22 @@ int main(int argc, char** argv)
         sba_solve_summary s = sba.adjust_rotation(left, right, w, h, rot);
         double out[5] = {rot[0], rot[1], rot[2], (double)s.iterations, s.final_cost};
         dump(dir + "/rot.bin", out, 5);
+        auto sb1 = slurp<double>(dir + "/sp_b1.bin");
+        if (!sb1.empty()) {
+            auto sb2 = slurp<double>(dir + "/sp_b2.bin"), init = slurp<double>(dir + "/sp_init.bin");
+            const int n = (int)(sb1.size() / 3);
+            std::vector<cv::Point3d> L(n), R(n);
+            for (int i = 0; i < n; i++) { L[i] = cv::Point3d(sb1[3 * i], sb1[3 * i + 1], sb1[3 * i + 2]); R[i] = cv::Point3d(sb2[3 * i], sb2[3 * i + 1], sb2[3 * i + 2]); }
+            double r0[3] = {init[0], init[1], init[2]}, t0[3] = {init[3], init[4], init[5]};
+            std::vector<std::array<double, 2>> init_d(n);
+            for (auto& d : init_d) d[0] = d[1] = init[6];
+            sba_solver_options opt;
+            sba.solve_problem(opt, L, R, r0, t0, init_d, n);
+            std::vector<double> o = {r0[0], r0[1], r0[2], t0[0], t0[1], t0[2], (double)sba.stage_summaries[0].iterations,
+                                     (double)sba.stage_summaries[1].iterations, (double)sba.stage_summaries[2].iterations};
+            for (auto& d : init_d) { o.push_back(d[0]); o.push_back(d[1]); }
+            dump(dir + "/sp_out.bin", o.data(), o.size());
+        }
         std::printf("facade_demo: %zu matches, rotation %.9f %.9f %.9f, %d LM iterations\n", matches.size(), rot[0], rot[1], rot[2], s.iterations);
     } catch (const std::exception& ex) {
         std::cerr << "facade_demo failed: " << ex.what() << "\n";

@@ -4,21 +4,91 @@
 
 #include "sba_host_ctx.hpp"
 
+#include <cmath>
+#include <cstdio>
+
+namespace {
+
+// unit vectors as the float4 records the device problem reads
+sba_ba_problem* make_problem(std::vector<cv::Point3d>& left, std::vector<cv::Point3d>& right, int match_num)
+{
+    std::vector<float> b1(4 * (size_t)match_num), b2(4 * (size_t)match_num);
+    for (int i = 0; i < match_num; i++) {
+        b1[4 * i] = (float)left[i].x; b1[4 * i + 1] = (float)left[i].y; b1[4 * i + 2] = (float)left[i].z; b1[4 * i + 3] = 0.f;
+        b2[4 * i] = (float)right[i].x; b2[4 * i + 1] = (float)right[i].y; b2[4 * i + 2] = (float)right[i].z; b2[4 * i + 3] = 0.f;
+    }
+    sba_ba_problem* prob = nullptr;
+    sba_host::check(sba_ba_problem_create(sba_host::ctx(), b1.data(), b2.data(), nullptr, match_num, 1, SBA_MEM_HOST, &prob));
+    return prob;
+}
+
+const char* termination_name(int t)
+{
+    switch (t) {
+        case 0: return "NO_CONVERGENCE";
+        case 4: return "FAILURE";
+        default: return "CONVERGENCE";
+    }
+}
+
+}  // namespace
+
+sba_solve_summary ba_spherical_costfunctor_d_only::solve(std::vector<cv::Point3d>& left, std::vector<cv::Point3d>& right, double* init_rot,
+                                                         double* init_tran, std::vector<std::array<double, 2>>& init_d, int match_num,
+                                                         int max_num_iterations)
+{
+    sba_solve_summary sum{};
+    if (match_num <= 0) return sum;
+    sba_ba_problem* prob = make_problem(left, right, match_num);
+    // std::array<double, 2> is two contiguous doubles: init_d.data() is the [n x 2] table
+    int status = sba_ba_d_solve(prob, init_rot, init_tran, init_d[0].data(), 1.0, 1.0 /* lambda, c: :1058-1059 */, max_num_iterations, &sum,
+                                nullptr, SBA_MEM_HOST);
+    sba_ba_problem_destroy(prob);
+    sba_host::check(status);
+    return sum;
+}
+
+sba_solve_summary ba_spherical_costfunctor_tran_only::solve(std::vector<cv::Point3d>& left, std::vector<cv::Point3d>& right, double* init_rot,
+                                                            double* init_tran, std::vector<std::array<double, 2>>& init_d, int match_num,
+                                                            int max_num_iterations)
+{
+    sba_solve_summary sum{};
+    if (match_num <= 0) return sum;
+    const double d1 = init_d.size() > 0 ? init_d[0][0] : 1.0, d2 = init_d.size() > 1 ? init_d[1][0] : d1;   // :998-999
+    sba_ba_problem* prob = make_problem(left, right, match_num);
+    int status = sba_ba_tran_solve(prob, init_rot, init_tran, d1, d2, 1.0, max_num_iterations, &sum);
+    sba_ba_problem_destroy(prob);
+    sba_host::check(status);
+    return sum;
+}
+
+void spherical_bundle_adjuster::solve_problem(sba_solver_options& opt, std::vector<cv::Point3d>& left, std::vector<cv::Point3d>& right,
+                                              double* init_rot, double* init_tran, std::vector<std::array<double, 2>>& init_d, int match_num)
+{
+    for (auto& s : stage_summaries) s = sba_solve_summary{};
+    if (match_num < 2) return;
+    sba_ba_problem* prob = make_problem(left, right, match_num);   // one upload for the three stages
+    int status = sba_ba_solve_problem(prob, init_rot, init_tran, init_d[0].data(), 1.0, opt.max_num_iterations, stage_summaries, SBA_MEM_HOST);
+    sba_ba_problem_destroy(prob);
+    sba_host::check(status);
+    if (opt.minimizer_progress_to_stdout) {
+        for (const auto& s : stage_summaries)   // the shape of ceres' Summary::BriefReport (:198, :204, :210)
+            std::printf("Ceres Solver Report: Iterations: %d, Initial cost: %e, Final cost: %e, Termination: %s\n", s.iterations,
+                        s.initial_cost, s.final_cost, termination_name(s.termination));
+        std::printf("rotation vector in degree %g %g %g\n", init_rot[0] / M_PI * 180.0, init_rot[1] / M_PI * 180.0, init_rot[2] / M_PI * 180.0);
+        std::printf("translation vector %g %g %g\n", init_tran[0], init_tran[1], init_tran[2]);
+    }
+}
+
 sba_solve_summary ba_spherical_costfunctor_rot_only::solve(std::vector<cv::Point3d>& left, std::vector<cv::Point3d>& right, double* init_rot,
                                                            double* init_tran, std::vector<std::array<double, 2>>& init_d, int match_num,
                                                            int max_num_iterations)
 {
     sba_solve_summary sum{};
     if (match_num <= 0) return sum;
-    std::vector<float> b1(4 * (size_t)match_num), b2(4 * (size_t)match_num);
-    for (int i = 0; i < match_num; i++) {
-        b1[4 * i] = (float)left[i].x; b1[4 * i + 1] = (float)left[i].y; b1[4 * i + 2] = (float)left[i].z; b1[4 * i + 3] = 0.f;
-        b2[4 * i] = (float)right[i].x; b2[4 * i + 1] = (float)right[i].y; b2[4 * i + 2] = (float)right[i].z; b2[4 * i + 3] = 0.f;
-    }
     // the reference hands init_d[0][0] and init_d[1][0] to EVERY residual (:941-942); preserved
     const double d1 = init_d.size() > 0 ? init_d[0][0] : 1.0, d2 = init_d.size() > 1 ? init_d[1][0] : d1;
-    sba_ba_problem* prob = nullptr;
-    sba_host::check(sba_ba_problem_create(sba_host::ctx(), b1.data(), b2.data(), nullptr, match_num, 1, SBA_MEM_HOST, &prob));
+    sba_ba_problem* prob = make_problem(left, right, match_num);
     int status = sba_ba_rot_solve(prob, init_rot, init_tran, d1, d2, 1.0 /* HuberLoss(1.0), :943 */, max_num_iterations, &sum);
     sba_ba_problem_destroy(prob);
     sba_host::check(status);

@@ -27,6 +27,41 @@ struct ba_spherical_costfunctor_rot_only
                                  , int max_num_iterations = 50);
 };
 
+// Depth-only block (spherical_bundle_adjuster.cpp:1005-1063): every match owns its depth pair init_d[i],
+// bounded below by 0, no loss function, lambda = c = 1.  init_d is updated in place.
+struct ba_spherical_costfunctor_d_only
+{
+    static sba_solve_summary solve(std::vector<cv::Point3d>& key_point_left_rect
+                                 , std::vector<cv::Point3d>& key_point_right_rect
+                                 , double* init_rot
+                                 , double* init_tran
+                                 , std::vector<std::array<double, 2>>& init_d
+                                 , int match_num
+                                 , int max_num_iterations = 50);
+};
+
+// Translation-only block (spherical_bundle_adjuster.cpp:948-1002): init_tran is updated in place.
+struct ba_spherical_costfunctor_tran_only
+{
+    static sba_solve_summary solve(std::vector<cv::Point3d>& key_point_left_rect
+                                 , std::vector<cv::Point3d>& key_point_right_rect
+                                 , double* init_rot
+                                 , double* init_tran
+                                 , std::vector<std::array<double, 2>>& init_d
+                                 , int match_num
+                                 , int max_num_iterations = 50);
+};
+
+// The three fields of ceres::Solver::Options the reference sets (spherical_bundle_adjuster.cpp:334-338);
+// linear_solver_type is not needed: every stage's reduced system is empty, the exact block solve IS the
+// ITERATIVE_SCHUR answer.
+struct sba_solver_options
+{
+    int max_num_iterations = 50;
+    bool minimizer_progress_to_stdout = true;
+    int num_threads = 1;
+};
+
 class spherical_bundle_adjuster
 {
     public:
@@ -43,6 +78,18 @@ class spherical_bundle_adjuster
     // rotation-only solve.  Returns the rotation vector in rot[3].
     sba_solve_summary adjust_rotation(const std::vector<cv::KeyPoint>& left_key, const std::vector<cv::KeyPoint>& right_key, int im_width,
                                       int im_height, double rot[3]);
+
+    // The reference's private solve_problem (spherical_bundle_adjuster.cpp:183-217), public here so callers
+    // that have their own front-end can use it: depth stage -> rotation stage -> translation stage, all three
+    // parameter sets updated in place; prints the three brief reports when the options ask for progress.
+    void solve_problem(sba_solver_options& opt
+                    , std::vector<cv::Point3d>& key_point_left_rect
+                    , std::vector<cv::Point3d>& key_point_right_rect
+                    , double* init_rot
+                    , double* init_tran
+                    , std::vector<std::array<double, 2>>& init_d
+                    , int match_num);
+    sba_solve_summary stage_summaries[3] = {};   // depth, rotation, translation of the last solve_problem
 
     double result_rot[3] = {0, 0, 0};
 

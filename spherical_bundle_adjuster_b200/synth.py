@@ -62,6 +62,24 @@ def make_bearings(n: int, rotvec=(0.1, -0.35, 0.6), noise: float = 1e-3, outlier
     return b1, b2, cam, r_true
 
 
+def make_two_view(n: int, rotvec=(0.05, -0.1, 0.2), tran=(0.3, 0.1, -0.2), noise: float = 1e-3, outlier_frac: float = 0.05,
+                  seed: int = 5, depth_range=(2.0, 8.0)):
+    """Points at depth seen from two spherical cameras related by X2 = R X1 - t (the model of the
+    reference's functors, spherical_bundle_adjuster.cpp:844-868).  Returns (b1, b2 [n,3] f64 unit
+    bearings, r [3], t [3], depths [n,2] = |X1|, |X2|); the first share of matches are outliers."""
+    rng = np.random.default_rng(seed)
+    X1 = unit_rows(rng.standard_normal((n, 3))) * rng.uniform(depth_range[0], depth_range[1], n)[:, None]
+    r, t = np.asarray(rotvec, np.float64), np.asarray(tran, np.float64)
+    X2 = X1 @ rotvec_to_matrix(r).T - t
+    depths = np.stack([np.linalg.norm(X1, axis=1), np.linalg.norm(X2, axis=1)], axis=1)
+    b1 = unit_rows(unit_rows(X1) + noise * rng.standard_normal((n, 3)))
+    b2 = unit_rows(X2)
+    n_out = int(n * outlier_frac)
+    if n_out:
+        b2[:n_out] = unit_rows(rng.standard_normal((n_out, 3)))
+    return b1, b2, r, t, depths
+
+
 def make_erp_image(w: int, h: int, seed: int = 3) -> np.ndarray:
     """Seeded uint8 ERP image [h, w, 3] (smooth gradient + noise so neighbouring pixels differ)."""
     rng = np.random.default_rng(seed)

@@ -23,8 +23,14 @@ def test_cpp_facade_end_to_end(tmp_path):
     im.tofile(d + "/im.bin"); pair["desc1"].tofile(d + "/desc1.bin"); pair["desc2"].tofile(d + "/desc2.bin")
     pair["key1_xy"].tofile(d + "/key1.bin"); pair["key2_xy"].tofile(d + "/key2.bin")
     open(d + "/meta.txt", "w").write(f"{w} {h} {cs} {n1} {n2}\n")
+    # inputs of the three-stage solve_problem (spherical_bundle_adjuster.cpp:183-217)
+    sb1, sb2, r_true, t_true, _ = synth.make_two_view(1500, seed=9)
+    sb1, sb2 = sb1.astype(np.float32).astype(np.float64), sb2.astype(np.float32).astype(np.float64)
+    r0, t0 = r_true + [0.02, -0.01, 0.03], t_true + [0.03, 0.02, -0.04]
+    sb1.tofile(d + "/sp_b1.bin"); sb2.tofile(d + "/sp_b2.bin"); np.concatenate([r0, t0, [1.0]]).tofile(d + "/sp_init.bin")
     r = subprocess.run([DEMO, d], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("Ceres Solver Report") == 3
 
     strip = np.fromfile(d + "/strip.bin", np.uint8).reshape(cs, 6 * cs, 3)
     assert np.array_equal(strip, oracle.equi2cube_all(im, cs))
@@ -40,3 +46,11 @@ def test_cpp_facade_end_to_end(tmp_path):
     r_or, s_or = oracle.ba_rot_solve(b1, b2, None, np.zeros((1, 3)))
     assert np.abs(rot[:3] - r_or[0]).max() < 1e-6 and int(rot[3]) == s_or.iterations
     assert np.linalg.norm(rot[:3] - pair["r_true"]) < 1e-4
+
+    sp = np.fromfile(d + "/sp_out.bin", np.float64)
+    d_ref, s_d, _ = oracle.ba_d_solve(sb1, sb2, r0, t0, np.full((1500, 2), 1.0))
+    r_ref, s_r = oracle.ba_rot_solve(sb1, sb2, None, r0[None], t0, d_ref[0, 0], d_ref[1, 0], 1.0)
+    t_ref, s_t = oracle.ba_tran_solve(sb1, sb2, None, r_ref, t0[None], d_ref[0, 0], d_ref[1, 0], 1.0)
+    assert np.abs(sp[:3] - r_ref[0]).max() < 1e-6 and np.abs(sp[3:6] - t_ref[0]).max() < 1e-6
+    assert int(sp[6]) == s_d.iterations
+    assert np.all(np.abs(sp[9:].reshape(-1, 2) - d_ref) <= 1e-7 * np.maximum(1.0, np.abs(d_ref)))

@@ -171,3 +171,72 @@ def test_ba_tran_only_oracle():
     c = lambda t: oracle.ba_tran_eval(b1, b2, None, r_true, t[None])[3][0]
     fd = np.array([(c(t0 + eps * np.eye(3)[k]) - c(t0 - eps * np.eye(3)[k])) / (2 * eps) for k in range(3)])
     assert np.abs(fd - oracle.ba_tran_eval(b1, b2, None, r_true, t0[None])[2][0]).max() < 1e-6
+
+
+def test_ba_depth_only_functor_oracle():
+    # depth block (spherical_bundle_adjuster.cpp:1005-1032): Jacobian against central differences
+    b1, b2, r, t, _ = synth.make_two_view(20, seed=1)
+    d = np.array([1.3, 0.4])
+    for i in range(20):
+        res, J = oracle.ba_d_functor(b1[i], b2[i], r, t, d, 1.5, 0.8)
+        assert res.shape == (5,) and abs(res[3] - 1.5 * np.exp(-0.8 * 1.3)) < 1e-15
+        for k in range(2):
+            e = np.zeros(2); e[k] = 1e-6
+            fd = (oracle.ba_d_functor(b1[i], b2[i], r, t, d + e, 1.5, 0.8)[0] - oracle.ba_d_functor(b1[i], b2[i], r, t, d - e, 1.5, 0.8)[0]) / 2e-6
+            assert np.abs(fd - J[:, k]).max() < 1e-9
+
+
+def _hermite_min(samples, lo, hi):
+    """Independent restatement with numpy: fit value+gradient samples, minimise over [lo, hi] the way
+    Ceres' MinimizePolynomial does (mid point, ends, real parts of the derivative's roots)."""
+    nc = 2 * len(samples)
+    A, b = [], []
+    for x, v, g in samples:
+        A.append([x ** (nc - 1 - j) for j in range(nc)]); b.append(v)
+        A.append([(nc - 1 - j) * x ** (nc - 2 - j) if j < nc - 1 else 0.0 for j in range(nc)]); b.append(g)
+    p = np.linalg.solve(np.array(A), np.array(b))
+    cands = [0.5 * (lo + hi), lo, hi] + [z.real for z in np.roots(np.polyder(p)) if lo <= z.real <= hi]
+    vals = [np.polyval(p, x) for x in cands]
+    return cands[int(np.argmin(vals))]
+
+
+def test_line_search_interpolation_oracle():
+    # two-sample (cubic) and three-sample (quintic) fits, incl. a case whose derivative has complex roots
+    cases = [
+        ((10.0, -4.0), (1.0, 12.0, 9.0), None),
+        ((10.0, -4.0), (0.3, 9.9, 2.5), (1.0, 12.0, 9.0)),
+        ((5.0, -1.0), (1.0, 5.5, 0.2), None),
+        ((5.0, -1.0), (0.6, 5.2, -0.1), (1.0, 5.5, 0.2)),
+        ((1.0, -100.0), (1.0, 50.0, 400.0), None),
+    ]
+    for (f0, g0), cur, prev in cases:
+        got = oracle.ls_next_step(f0, g0, cur, prev)
+        samples = [(0.0, f0, g0), cur] + ([prev] if prev is not None else [])
+        want = _hermite_min(samples, 1e-3 * cur[0], 0.6 * cur[0])
+        assert abs(got - want) <= 1e-9 * max(1.0, abs(want)), (got, want)
+
+
+def test_ba_depth_only_solve_oracle():
+    from scipy.optimize import least_squares
+    b1, b2, r, t, depths = synth.make_two_view(60, seed=3, outlier_frac=0.1)
+    d, s, nls = oracle.ba_d_solve(b1, b2, r, t, np.full((60, 2), 1.0))
+    assert s.termination == 1 and s.final_cost < s.initial_cost and np.all(d >= 0)
+    # every block is independent: scipy's bounded trust-region solver on single blocks lands at the same
+    # minimiser up to the function-tolerance slack Ceres stops with
+    for i in range(0, 60, 7):
+        sol = least_squares(lambda x: oracle.ba_d_functor(b1[i], b2[i], r, t, x)[0], [1.0, 1.0], bounds=(0, np.inf), xtol=1e-14, ftol=1e-14, gtol=1e-14)
+        assert np.abs(sol.x - d[i]).max() < 2e-2
+    # no barrier: outliers are pushed onto the bound and stay feasible
+    d2, s2, _ = oracle.ba_d_solve(b1, b2, r, t, np.full((60, 2), 1.0), 0.0, 1.0)
+    assert np.all(d2 >= 0) and (d2 == 0).any()
+    # infeasible start is projected first (IterationZero)
+    d3, s3, _ = oracle.ba_d_solve(b1, b2, r, t, np.full((60, 2), -2.0))
+    d4, s4, _ = oracle.ba_d_solve(b1, b2, r, t, np.zeros((60, 2)))
+    assert np.array_equal(d3, d4) and s3.iterations == s4.iterations
+    # stiff barrier exercises the Armijo interpolation
+    b1, b2, r, t, _ = synth.make_two_view(400, seed=400)
+    d5, s5, nls5 = oracle.ba_d_solve(b1, b2, r, t, np.full((400, 2), 5.0), 20.0, 8.0)
+    assert nls5 > 0 and s5.final_cost < s5.initial_cost
+    # iteration cap
+    _, s6, _ = oracle.ba_d_solve(b1, b2, r, t, np.full((400, 2), 5.0), 1.0, 1.0, 3)
+    assert s6.iterations == 3 and s6.termination == 0
