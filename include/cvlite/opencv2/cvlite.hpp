@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <iostream>
 #include <memory>
@@ -23,6 +24,7 @@ typedef unsigned char uchar;
 
 #define CV_CN_SHIFT 3
 #define CV_8U 0
+#define CV_32S 4
 #define CV_32F 5
 #define CV_64F 6
 #define CV_MAKETYPE(depth, cn) (((depth)&7) + (((cn)-1) << CV_CN_SHIFT))
@@ -30,6 +32,7 @@ typedef unsigned char uchar;
 #define CV_8UC3 CV_MAKETYPE(CV_8U, 3)
 #define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
 #define CV_64FC1 CV_MAKETYPE(CV_64F, 1)
+#define CV_32SC2 CV_MAKETYPE(CV_32S, 2)
 
 namespace cv {
 
@@ -48,6 +51,27 @@ typedef Vec<double, 3> Vec3d;
 typedef Vec<double, 2> Vec2d;
 typedef Vec<float, 3> Vec3f;
 typedef Vec<int, 2> Vec2i;
+template <typename T, int N> inline Vec<T, N> operator-(const Vec<T, N>& a, const Vec<T, N>& b)
+{
+    Vec<T, N> r;
+    for (int i = 0; i < N; i++) r.val[i] = a.val[i] - b.val[i];
+    return r;
+}
+
+template <typename T> struct Rect_ {
+    T x, y, width, height;
+    Rect_() : x(0), y(0), width(0), height(0) {}
+    Rect_(T x_, T y_, T w_, T h_) : x(x_), y(y_), width(w_), height(h_) {}
+};
+typedef Rect_<int> Rect;
+
+// element type -> type code, for the typed matrices below
+template <typename T> struct DataType;
+template <> struct DataType<uchar> { enum { type = CV_8UC1 }; };
+template <> struct DataType<float> { enum { type = CV_32FC1 }; };
+template <> struct DataType<double> { enum { type = CV_64FC1 }; };
+template <> struct DataType<Vec<int, 2>> { enum { type = CV_32SC2 }; };
+template <> struct DataType<Vec<uchar, 3>> { enum { type = CV_8UC3 }; };
 
 template <typename T> struct Point_ {
     T x, y;
@@ -119,11 +143,82 @@ public:
     }
     template <typename T> T* ptr(int r = 0) { return (T*)(data + (size_t)r * cols * elemSize()); }
     template <typename T> const T* ptr(int r = 0) const { return (const T*)(data + (size_t)r * cols * elemSize()); }
+    template <typename T> T& at(int r, int c) { return ((T*)data)[(size_t)r * cols + c]; }
+    template <typename T> const T& at(int r, int c) const { return ((const T*)data)[(size_t)r * cols + c]; }
+    // Sub-matrix header sharing the parent's storage.  Only full-width row bands are representable in this
+    // continuous-only carrier (that is the one shape the reference takes: spherical_surf.cpp:132,139).
+    Mat operator()(const Rect& roi) const
+    {
+        if (roi.x != 0 || roi.width != cols || roi.y < 0 || roi.y + roi.height > rows) { std::cerr << "cvlite: only full-width row bands\n"; std::abort(); }
+        Mat m;
+        m.rows = roi.height; m.cols = cols; m.type_ = type_; m.store_ = store_;
+        m.data = data + (size_t)roi.y * cols * elemSize();
+        return m;
+    }
 
 private:
     int type_;
     std::shared_ptr<std::vector<uchar>> store_;
 };
+
+// Typed matrix with the `Mat_<T>(r, c) << a, b, c ...` initialiser (opencv2/core/mat.hpp).
+template <typename T> class Mat_;
+template <typename T> class MatCommaInitializer_ {
+public:
+    MatCommaInitializer_(Mat_<T>* m) : m_(m), k_(0) {}
+    template <typename T2> MatCommaInitializer_<T>& operator,(T2 v)
+    {
+        ((T*)m_->data)[k_++] = (T)v;
+        return *this;
+    }
+    operator Mat_<T>() const { return *m_; }
+    operator Mat() const { return *m_; }
+    Mat_<T>* m_;
+    size_t k_;
+};
+template <typename T> class Mat_ : public Mat {
+public:
+    Mat_() : Mat() {}
+    Mat_(int r, int c) : Mat(r, c, DataType<T>::type) {}
+    T& operator()(int r, int c) { return this->template at<T>(r, c); }
+};
+template <typename T, typename T2> inline MatCommaInitializer_<T> operator<<(const Mat_<T>& m, T2 v)
+{
+    MatCommaInitializer_<T> ci(const_cast<Mat_<T>*>(&m));
+    return (ci, v);
+}
+typedef Mat_<Vec2i> Mat2i;
+typedef Mat_<double> Mat1d;
+
+// Matrix product of CV_64FC1 matrices (the reference multiplies 3x3 rotation factors, spherical_surf.cpp:42).
+inline Mat operator*(const Mat& a, const Mat& b)
+{
+    if (a.type() != CV_64FC1 || b.type() != CV_64FC1 || a.cols != b.rows) { std::cerr << "cvlite: operator* is CV_64FC1 only\n"; std::abort(); }
+    Mat c(a.rows, b.cols, CV_64FC1);
+    for (int i = 0; i < a.rows; i++)
+        for (int j = 0; j < b.cols; j++) {
+            double s = 0;
+            for (int k = 0; k < a.cols; k++) s += a.at<double>(i, k) * b.at<double>(k, j);
+            c.at<double>(i, j) = s;
+        }
+    return c;
+}
+
+// Vertical concatenation of equally wide, same-type matrices (cv::vconcat, array form).
+inline void vconcat(const Mat* src, size_t n, Mat& dst)
+{
+    int rows = 0, cols = 0, type = 0;
+    for (size_t i = 0; i < n; i++) if (!src[i].empty()) { rows += src[i].rows; cols = src[i].cols; type = src[i].type(); }
+    Mat out(rows, cols, type);
+    size_t off = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (src[i].empty()) continue;
+        const size_t bytes = src[i].total() * src[i].elemSize();
+        std::memcpy(out.data + off, src[i].data, bytes);
+        off += bytes;
+    }
+    dst = out;
+}
 
 // Horizontal concatenation of equally tall, same-type matrices (cv::hconcat).
 inline void hconcat(const std::vector<Mat>& src, Mat& dst)

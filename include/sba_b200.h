@@ -142,6 +142,29 @@ int sba_gather_matches(sba_ctx* ctx, const float* key_left_xy, const float* key_
                        const int32_t* train_idx, int n_matches, float* out_left_xy, float* out_right_xy, int mem);
 
 /* ---------------------------------------------------------------------------------------------
+ * spherical_surf front-end geometry (spherical_surf.cpp:17-123; the crops of do_all :137-153)
+ *
+ *   sba_eular2rot           eular2rot (:17-45): float Euler angles -> 3x3 row-major doubles, host arithmetic
+ *                           identical to the reference's (float-precision factors, (Rz Ry) Rx in double).
+ *   sba_crop_rotated_lut    source index row*w+col of every pixel of the (h/4) x w band for one pitch, -1 where
+ *                           the bounds check of :100 fails; bit-identical to the reference's index arithmetic.
+ *   sba_crop_rotated_image  crop_rotated_image (:79-109) for n_images frames: out [n][h/4][w][3]; pixels the
+ *                           reference leaves unwritten are 0.
+ *   sba_spherical_crops     the four bands do_all cuts from an image (pitch 45, the plain band im(roi),
+ *                           pitch -45, pitch -90) in ONE gather: out [n][4][h/4][w][3].
+ *   sba_rotate_pixels       rotate_pixel (:48-77) on n (row, col) pairs with eular2rot(0, RAD(pitch), 0).
+ *   sba_rotate_pixels_mat   the same with an arbitrary 3x3 rotation (row-major doubles), as rotate_pixel's signature allows.
+ *   sba_rotate_keypoints    rotate_keypoint (:111-123): n (x, y) keypoints in band coordinates, in place.
+ * ------------------------------------------------------------------------------------------- */
+int sba_eular2rot(const float theta[3], double R_out[9]);
+int sba_crop_rotated_lut(sba_ctx* ctx, int w, int h, float pitch_deg, int32_t* lut_out, int* n_patched, int mem);
+int sba_crop_rotated_image(sba_ctx* ctx, const uint8_t* erp, int w, int h, int n_images, float pitch_deg, uint8_t* out, int mem);
+int sba_spherical_crops(sba_ctx* ctx, const uint8_t* erp, int w, int h, int n_images, uint8_t* out, int mem);
+int sba_rotate_pixels(sba_ctx* ctx, const int32_t* rc_in, int n, float pitch_deg, int w, int h, int32_t* rc_out, int mem);
+int sba_rotate_pixels_mat(sba_ctx* ctx, const int32_t* rc_in, int n, const double R[9], int w, int h, int32_t* rc_out, int mem);
+int sba_rotate_keypoints(sba_ctx* ctx, float* xy_inout, int n, float pitch_inv_deg, int w, int h, int mem);
+
+/* ---------------------------------------------------------------------------------------------
  * Rotation-only bundle adjustment
  * (replaces ba_spherical_costfunctor_rot_only + ceres::Solve, spherical_bundle_adjuster.cpp:892-945,
  *  :183-217, :334-338)

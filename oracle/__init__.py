@@ -62,6 +62,11 @@ def _load():
     lib.orc_ba_tran_solve.argtypes = [f64p, f64p, i32p, C.c_int, f64p, f64p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p]
     lib.orc_ba_d_functor.argtypes = [f64p, f64p, f64p, f64p, f64p, C.c_double, C.c_double, f64p, f64p]
     lib.orc_ba_d_solve.argtypes = [f64p, f64p, C.c_int, f64p, f64p, f64p, C.c_double, C.c_double, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    lib.orc_eular2rot.argtypes = [f32p, f64p]
+    lib.orc_rotate_pixel.argtypes = [C.c_int, C.c_int, f64p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.orc_crop_rotated_lut.argtypes = [C.c_float, C.c_int, C.c_int, i32p]
+    lib.orc_crop_rotated_image.argtypes = [u8p, C.c_int, C.c_int, C.c_float, u8p]
+    lib.orc_rotate_keypoints.argtypes = [C.c_float, f32p, C.c_int, C.c_int, C.c_int]
     lib.orc_ls_next_step.restype = C.c_double
     lib.orc_ls_next_step.argtypes = [C.c_double] * 5 + [C.c_int] + [C.c_double] * 5
     return lib
@@ -251,6 +256,50 @@ def ls_next_step(f0, g0, cur, prev=None, min_step=None, max_step=None):
     return lib().orc_ls_next_step(f0, g0, xp, fp, gp, int(prev is not None), xc, fc, gc, lo, hi)
 
 
+# ------------------------------------------------------------------ spherical_surf geometry
+def eular2rot(theta) -> np.ndarray:
+    th = np.ascontiguousarray(theta, np.float32).reshape(3)
+    R = np.zeros(9)
+    lib().orc_eular2rot(_p(th, C.c_float), _p(R, C.c_double))
+    return R.reshape(3, 3)
+
+
+def pitch_rotation(pitch_deg: float) -> np.ndarray:
+    """eular2rot(Vec3f(0, RAD(pitch), 0)) as crop_rotated_image / rotate_keypoint build it."""
+    return eular2rot([0.0, np.float32(np.pi * float(np.float32(pitch_deg)) / 180.0), 0.0])
+
+
+def rotate_pixels(rc: np.ndarray, pitch_deg: float, w: int, h: int) -> np.ndarray:
+    rc = np.ascontiguousarray(rc, np.int32).reshape(-1, 2)
+    R = np.ascontiguousarray(pitch_rotation(pitch_deg).reshape(-1))
+    out = np.empty_like(rc)
+    a, b = C.c_int(0), C.c_int(0)
+    for k in range(len(rc)):
+        lib().orc_rotate_pixel(int(rc[k, 0]), int(rc[k, 1]), _p(R, C.c_double), w, h, C.byref(a), C.byref(b))
+        out[k] = (a.value, b.value)
+    return out
+
+
+def crop_rotated_lut(pitch_deg: float, w: int, h: int) -> np.ndarray:
+    lut = np.empty((h // 4, w), np.int32)
+    lib().orc_crop_rotated_lut(pitch_deg, w, h, _p(lut, C.c_int32))
+    return lut
+
+
+def crop_rotated_image(im: np.ndarray, pitch_deg: float) -> np.ndarray:
+    im = np.ascontiguousarray(im, np.uint8)
+    h, w, _ = im.shape
+    out = np.empty((h // 4, w, 3), np.uint8)
+    lib().orc_crop_rotated_image(_p(im, C.c_uint8), w, h, pitch_deg, _p(out, C.c_uint8))
+    return out
+
+
+def rotate_keypoints(xy: np.ndarray, pitch_inv_deg: float, w: int, h: int) -> np.ndarray:
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2).copy()
+    lib().orc_rotate_keypoints(pitch_inv_deg, _p(xy, C.c_float), len(xy), w, h)
+    return xy
+
+
 # ------------------------------------------------------------------ the real reference (oracle/_ref)
 def ref_available() -> bool:
     return os.path.exists(_REF_PATH)
@@ -266,6 +315,10 @@ def ref():
             raise RuntimeError("oracle/_ref/libsba_ref.so not built (needs /root/reference at build time)")
         r = C.CDLL(_REF_PATH)
         u8p, f32p = C.POINTER(C.c_uint8), C.POINTER(C.c_float)
+        r.ref_eular2rot.argtypes = [f32p, C.POINTER(C.c_double)]
+        r.ref_rotate_pixels.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_float, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        r.ref_crop_rotated_image.argtypes = [u8p, C.c_int, C.c_int, C.c_float, C.c_int, u8p]
+        r.ref_rotate_keypoints.argtypes = [C.c_float, f32p, C.c_int, C.c_int, C.c_int]
         r.ref_equi2cube_all.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, u8p]
         r.ref_equi2cube_face.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, u8p]
         r.ref_cube2equi_points.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, f32p]
@@ -299,3 +352,31 @@ def ref_cube2equi_points(xy: np.ndarray, cs: int, w: int, h: int) -> np.ndarray:
     out = np.empty_like(xy)
     ref().ref_cube2equi_points(_p(xy, C.c_float), len(xy), cs, w, h, _p(out, C.c_float))
     return out
+
+
+def ref_eular2rot(theta) -> np.ndarray:
+    th = np.ascontiguousarray(theta, np.float32).reshape(3)
+    R = np.zeros(9)
+    ref().ref_eular2rot(_p(th, C.c_float), _p(R, C.c_double))
+    return R.reshape(3, 3)
+
+
+def ref_rotate_pixels(rc: np.ndarray, pitch_deg: float, w: int, h: int) -> np.ndarray:
+    rc = np.ascontiguousarray(rc, np.int32).reshape(-1, 2)
+    out = np.empty_like(rc)
+    ref().ref_rotate_pixels(_p(rc, C.c_int), len(rc), pitch_deg, w, h, _p(out, C.c_int))
+    return out
+
+
+def ref_crop_rotated_image(im: np.ndarray, pitch_deg: float, nthreads: int = 0) -> np.ndarray:
+    im = np.ascontiguousarray(im, np.uint8)
+    h, w, _ = im.shape
+    out = np.empty((h // 4, w, 3), np.uint8)
+    ref().ref_crop_rotated_image(_p(im, C.c_uint8), w, h, pitch_deg, nthreads or max_threads(), _p(out, C.c_uint8))
+    return out
+
+
+def ref_rotate_keypoints(xy: np.ndarray, pitch_inv_deg: float, w: int, h: int) -> np.ndarray:
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2).copy()
+    ref().ref_rotate_keypoints(pitch_inv_deg, _p(xy, C.c_float), len(xy), w, h)
+    return xy

@@ -12,6 +12,11 @@
 
 #include "equi2cube.hpp"
 #include "equi2cube_surf.hpp"
+// crop_rotated_image and rotate_keypoint are private members of the reference class (spherical_surf.hpp:19-20);
+// the checker reaches them without touching the reference source
+#define private public
+#include "spherical_surf.hpp"
+#undef private
 
 static void unavailable(const char* what)
 {
@@ -68,6 +73,49 @@ void ref_cube2equi_points(const float* xy_in, int n, int cs, int w, int h, float
         xy_out[2 * k] = out.x;
         xy_out[2 * k + 1] = out.y;
     }
+}
+
+// ---- spherical_surf (spherical_surf.cpp:17-123) ---------------------------------------------------
+
+// theta: Euler angles as the float triple the reference passes; R: 3x3 row-major doubles.
+void ref_eular2rot(const float theta[3], double R[9])
+{
+    spherical_surf s;
+    cv::Mat m = s.eular2rot(cv::Vec3f(theta[0], theta[1], theta[2]));
+    std::memcpy(R, m.data, 9 * sizeof(double));
+}
+
+// rc_in / rc_out: n (row, col) integer pairs; the rotation is eular2rot(0, RAD(pitch_deg), 0) like both callers build it.
+void ref_rotate_pixels(const int* rc_in, int n, float pitch_deg, int w, int h, int* rc_out)
+{
+    spherical_surf s;
+    cv::Mat rot = s.eular2rot(cv::Vec3f(0, RAD(pitch_deg), 0));
+    for (int k = 0; k < n; k++) {
+        cv::Vec2i o = s.rotate_pixel(cv::Vec2i(rc_in[2 * k], rc_in[2 * k + 1]), rot, w, h);
+        rc_out[2 * k] = o[0];
+        rc_out[2 * k + 1] = o[1];
+    }
+}
+
+// out: (h/4) x w x 3.  Pixels whose source falls outside the image are left as the reference leaves them
+// (unwritten); the shim's Mat storage starts zeroed, so they read 0 here.
+void ref_crop_rotated_image(const unsigned char* im, int w, int h, float pitch_deg, int nthreads, unsigned char* out)
+{
+    cv::Mat m(h, w, CV_8UC3, (void*)im);
+    spherical_surf s;
+    omp_set_num_threads(nthreads);
+    cv::Mat o = s.crop_rotated_image(pitch_deg, m);
+    std::memcpy(out, o.data, (size_t)(h / 4) * w * 3);
+}
+
+// xy: n keypoints (x, y) in the cropped band's coordinates, rotated in place (spherical_surf.cpp:111-123).
+void ref_rotate_keypoints(float pitch_inv_deg, float* xy, int n, int w, int h)
+{
+    std::vector<cv::KeyPoint> key(n);
+    for (int k = 0; k < n; k++) { key[k].pt.x = xy[2 * k]; key[k].pt.y = xy[2 * k + 1]; }
+    spherical_surf s;
+    s.rotate_keypoint(pitch_inv_deg, key, w, h);
+    for (int k = 0; k < n; k++) { xy[2 * k] = key[k].pt.x; xy[2 * k + 1] = key[k].pt.y; }
 }
 
 }  // extern "C"

@@ -945,3 +945,105 @@ void orc_ba_d_solve(const double *b1, const double *b2, int n, const double r[3]
     if (ls_evals) *ls_evals = n_ls;
     free(g); free(scale); free(delta); free(xc); free(gc); free(H);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * spherical_surf front-end geometry.  spherical_surf.cpp:17-45 (eular2rot),
+ * :48-77 (rotate_pixel), :79-109 (crop_rotated_image), :111-123 (rotate_keypoint).
+ * Pinned against the reference's own spherical_surf.cpp compiled into oracle/_ref.
+ * ---------------------------------------------------------------------------------------- */
+#include <limits.h>
+
+/* The Euler angles arrive as floats (cv::Vec3f) and <cmath>'s float overloads of sin/cos are the ones
+ * picked, so the factors carry float precision widened to double (spherical_surf.cpp:20-38);
+ * R = (R_z * R_y) * R_x in double (:42). */
+void orc_eular2rot(const float theta[3], double R[9])
+{
+    double cx = cosf(theta[0]), sx = sinf(theta[0]), cy = cosf(theta[1]), sy = sinf(theta[1]), cz = cosf(theta[2]), sz = sinf(theta[2]);
+    double Rx[9] = {1, 0, 0, 0, cx, -sx, 0, sx, cx};
+    double Ry[9] = {cy, 0, sy, 0, 1, 0, -sy, 0, cy};
+    double Rz[9] = {cz, -sz, 0, sz, cz, 0, 0, 0, 1};
+    double T[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            double s = 0;
+            for (int k = 0; k < 3; k++) s += Rz[3 * i + k] * Ry[3 * k + j];
+            T[3 * i + j] = s;
+        }
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            double s = 0;
+            for (int k = 0; k < 3; k++) s += T[3 * i + k] * Rx[3 * k + j];
+            R[3 * i + j] = s;
+        }
+}
+
+/* RAD(x) of spherical_surf.hpp:6, narrowed to float by the Vec3f constructor (:88, :113) */
+static float pitch_to_float_rad(float pitch_deg) { return (float)(M_PI * (pitch_deg) / 180.0); }
+
+/* double -> int the way the reference's x86 build converts (cvttsd2si): NaN and out-of-range give INT_MIN */
+static int trunc_to_int(double v)
+{
+    if (!(v > -2147483649.0 && v < 2147483648.0)) return INT_MIN;
+    return (int)v;
+}
+
+/* spherical_surf.cpp:48-77.  (row, col) in, (row, col) out. */
+void orc_rotate_pixel(int row, int col, const double R[9], int width, int height, int *row_out, int *col_out)
+{
+    double lat = M_PI * row / height, lon = 2 * M_PI * col / width;
+    double v[3] = {sin(lat) * cos(lon), sin(lat) * sin(lon), cos(lat)};
+    double q[3];
+    for (int a = 0; a < 3; a++) q[a] = R[3 * a] * v[0] + R[3 * a + 1] * v[1] + R[3 * a + 2] * v[2];
+    double th = acos(q[2]), ph = atan2(q[1], q[0]);
+    if (ph < 0) ph += M_PI * 2;
+    *row_out = trunc_to_int(height * th / M_PI);
+    *col_out = trunc_to_int(width * ph / (2 * M_PI));
+}
+
+/* Source index (row*w + col) of every pixel of the cropped band, -1 where the bounds check of
+ * spherical_surf.cpp:100 fails (the reference leaves those output pixels unwritten). */
+void orc_crop_rotated_lut(float pitch_deg, int w, int h, int32_t *lut)
+{
+    float th[3] = {0.f, pitch_to_float_rad(pitch_deg), 0.f};
+    double R[9];
+    orc_eular2rot(th, R);
+    const int rows = h / 4, off = h * 3 / 8;
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < rows; i++)
+        for (int j = 0; j < w; j++) {
+            int r, c;
+            orc_rotate_pixel(i + off, j, R, w, h, &r, &c);
+            lut[(size_t)i * w + j] = (r >= 0 && c >= 0 && r < h && c < w) ? r * w + c : -1;
+        }
+}
+
+/* spherical_surf.cpp:79-109.  out: (h/4) x w x 3; unwritten pixels are set to 0 (the reference leaves
+ * them uninitialised). */
+void orc_crop_rotated_image(const uint8_t *im, int w, int h, float pitch_deg, uint8_t *out)
+{
+    const int rows = h / 4;
+    int32_t *lut = (int32_t *)malloc(sizeof(int32_t) * (size_t)rows * w);
+    orc_crop_rotated_lut(pitch_deg, w, h, lut);
+#pragma omp parallel for schedule(static)
+    for (int64_t p = 0; p < (int64_t)rows * w; p++) {
+        if (lut[p] >= 0) memcpy(out + 3 * p, im + 3 * (size_t)lut[p], 3);
+        else memset(out + 3 * p, 0, 3);
+    }
+    free(lut);
+}
+
+/* spherical_surf.cpp:111-123.  xy: n keypoints (x, y) in band coordinates, rotated in place
+ * (integer truncation of both coordinates before the rotation, integer results stored as float). */
+void orc_rotate_keypoints(float pitch_inv_deg, float *xy, int n, int w, int h)
+{
+    float th[3] = {0.f, pitch_to_float_rad(pitch_inv_deg), 0.f};
+    double R[9];
+    orc_eular2rot(th, R);
+    for (int k = 0; k < n; k++) {
+        int offset_i = (int)(xy[2 * k + 1] + (float)(h * 3 / 8));
+        int r, c;
+        orc_rotate_pixel(offset_i, (int)xy[2 * k], R, w, h, &r, &c);
+        xy[2 * k] = (float)c;
+        xy[2 * k + 1] = (float)r;
+    }
+}

@@ -22,6 +22,7 @@ EXPORTED = [
     "sba_ba_problem_create", "sba_ba_problem_destroy", "sba_ba_problem_set_allreduce", "sba_ba_rot_eval",
     "sba_ba_rot_solve", "sba_ba_rot_eval_timed", "sba_pair_rotation", "sba_ba_tran_eval", "sba_ba_tran_solve", "sba_comm_create", "sba_comm_connect", "sba_comm_destroy",
     "sba_ba_problem_set_comm", "sba_ba_d_eval", "sba_ba_d_solve", "sba_ba_solve_problem",
+    "sba_eular2rot", "sba_crop_rotated_lut", "sba_crop_rotated_image", "sba_spherical_crops", "sba_rotate_pixels", "sba_rotate_pixels_mat", "sba_rotate_keypoints",
 ]
 
 
@@ -90,6 +91,13 @@ def load():
     lib.sba_ba_problem_set_comm.argtypes = [vp, vp]
     lib.sba_ba_tran_eval.argtypes = [vp, vp, vp, f64, f64, f64, vp, vp, vp, vp, i32]
     lib.sba_ba_tran_solve.argtypes = [vp, vp, vp, f64, f64, f64, i32, C.POINTER(SolveSummary)]
+    lib.sba_eular2rot.argtypes = [vp, vp]
+    lib.sba_crop_rotated_lut.argtypes = [vp, i32, i32, f32, vp, C.POINTER(i32), i32]
+    lib.sba_crop_rotated_image.argtypes = [vp, vp, i32, i32, i32, f32, vp, i32]
+    lib.sba_spherical_crops.argtypes = [vp, vp, i32, i32, i32, vp, i32]
+    lib.sba_rotate_pixels.argtypes = [vp, vp, i32, f32, i32, i32, vp, i32]
+    lib.sba_rotate_pixels_mat.argtypes = [vp, vp, i32, vp, i32, i32, vp, i32]
+    lib.sba_rotate_keypoints.argtypes = [vp, vp, i32, f32, i32, i32, i32]
     lib.sba_ba_d_eval.argtypes = [vp, vp, vp, vp, f64, f64, vp, vp, vp, i32]
     lib.sba_ba_d_solve.argtypes = [vp, vp, vp, vp, f64, f64, i32, C.POINTER(SolveSummary), C.POINTER(i32), i32]
     lib.sba_ba_solve_problem.argtypes = [vp, vp, vp, vp, f64, i32, C.POINTER(SolveSummary * 3), i32]

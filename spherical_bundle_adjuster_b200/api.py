@@ -152,6 +152,63 @@ class Context:
         check(self._lib.sba_equi2cube_lut(self._h, w, h, cube_size, _ptr(lut), SBA_MEM_HOST))
         return lut
 
+    # -- spherical_surf.hpp:16-20 (eular2rot, rotate_pixel, crop_rotated_image, rotate_keypoint)
+    def eular2rot(self, theta) -> np.ndarray:
+        th = np.ascontiguousarray(theta, np.float32).reshape(3)
+        R = np.empty(9, np.float64)
+        check(self._lib.sba_eular2rot(_ptr(th), _ptr(R)))
+        return R.reshape(3, 3)
+
+    def crop_rotated_lut(self, w: int, h: int, pitch_deg: float):
+        """Source-index table of one pitched band ((h/4) x w, -1 = no source) and how many entries the host settled."""
+        lut = np.empty((h // 4, w), np.int32)
+        n = C.c_int32(0)
+        check(self._lib.sba_crop_rotated_lut(self._h, w, h, float(pitch_deg), _ptr(lut), C.byref(n), SBA_MEM_HOST))
+        return lut, int(n.value)
+
+    def crop_rotated_image(self, erp, pitch_deg: float):
+        """``spherical_surf::crop_rotated_image``; erp [h, w, 3] or [n, h, w, 3] -> [.., h/4, w, 3]."""
+        erp = _as(erp, np.uint8, torch.uint8 if torch else None)
+        batched = erp.ndim == 4
+        n = erp.shape[0] if batched else 1
+        h, w = erp.shape[-3], erp.shape[-2]
+        shape = (n, h // 4, w, 3) if batched else (h // 4, w, 3)
+        out = _empty_like_kind(erp, shape, np.uint8, torch.uint8 if torch else None)
+        check(self._lib.sba_crop_rotated_image(self._h, _ptr(erp), w, h, n, float(pitch_deg), _ptr(out), _mem_of(erp, out)))
+        return out
+
+    def spherical_crops(self, erp):
+        """The four bands of ``spherical_surf::do_all`` (pitch 45, plain band, -45, -90): [.., 4, h/4, w, 3]."""
+        erp = _as(erp, np.uint8, torch.uint8 if torch else None)
+        batched = erp.ndim == 4
+        n = erp.shape[0] if batched else 1
+        h, w = erp.shape[-3], erp.shape[-2]
+        shape = (n, 4, h // 4, w, 3) if batched else (4, h // 4, w, 3)
+        out = _empty_like_kind(erp, shape, np.uint8, torch.uint8 if torch else None)
+        check(self._lib.sba_spherical_crops(self._h, _ptr(erp), w, h, n, _ptr(out), _mem_of(erp, out)))
+        return out
+
+    def rotate_pixels(self, rc, pitch_deg: float, w: int, h: int):
+        rc = _as(rc, np.int32, torch.int32 if torch else None).reshape(-1, 2)
+        out = _empty_like_kind(rc, rc.shape, np.int32, torch.int32 if torch else None)
+        check(self._lib.sba_rotate_pixels(self._h, _ptr(rc), rc.shape[0], float(pitch_deg), w, h, _ptr(out), _mem_of(rc, out)))
+        return out
+
+    def rotate_pixels_mat(self, rc, R, w: int, h: int):
+        """``spherical_surf::rotate_pixel`` with an arbitrary rotation matrix (3x3 doubles)."""
+        rc = np.ascontiguousarray(rc, np.int32).reshape(-1, 2)
+        R = np.ascontiguousarray(R, np.float64).reshape(9)
+        out = np.empty_like(rc)
+        check(self._lib.sba_rotate_pixels_mat(self._h, _ptr(rc), rc.shape[0], _ptr(R), w, h, _ptr(out), SBA_MEM_HOST))
+        return out
+
+    def rotate_keypoints(self, xy, pitch_inv_deg: float, w: int, h: int):
+        """``spherical_surf::rotate_keypoint`` on a copy of xy [n, 2]."""
+        xy = _as(xy, np.float32, torch.float32 if torch else None).reshape(-1, 2)
+        xy = xy.clone() if _is_tensor(xy) else xy.copy()
+        check(self._lib.sba_rotate_keypoints(self._h, _ptr(xy), xy.shape[0], float(pitch_inv_deg), w, h, _mem_of(xy)))
+        return xy
+
     # -- equi2cube_surf.hpp:12
     def cube2equi_points(self, xy, cube_size: int, w: int, h: int):
         xy = _as(xy, np.float32, torch.float32 if torch else None).reshape(-1, 2)

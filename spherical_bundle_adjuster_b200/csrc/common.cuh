@@ -122,6 +122,14 @@ struct RemapPlan {
     int n_clamped = 0;
 };
 
+// spherical_surf front-end: source index of every pixel of the cropped band for one pitch (spherical.cu)
+struct CropPlan {
+    int w, h;
+    float pitch_deg;
+    int32_t* lut = nullptr;   // device, (h/4) x w; -1 = the reference's bounds check fails
+    int n_patched = 0;
+};
+
 // Named scratch slots (one DevBuf each) so independent stages never alias.
 enum ScratchSlot {
     SCR_IN0 = 0, SCR_IN1, SCR_IN2, SCR_IN3, SCR_OUT0, SCR_OUT1, SCR_OUT2, SCR_OUT3, SCR_OUT4,
@@ -143,6 +151,8 @@ struct sba_ctx {
     sba::DevBuf scratch[sba::SCR_COUNT];
     sba::BlockCache cache;
     std::map<std::tuple<int, int, int>, sba::RemapPlan> plans;
+    std::map<std::tuple<int, int, uint32_t>, sba::CropPlan> crop_plans;   // keyed by (w, h, bits of the pitch)
+    std::map<std::pair<int, int>, int32_t*> band_plans;                  // the four bands of spherical_surf::do_all in one table
     sba_match_stats match_stats{};
     int* pinned_i32 = nullptr;  // small pinned host mailbox (64 ints) for scalar read-backs
     bool profiling = false;
@@ -228,6 +238,10 @@ struct BaView {
     const int* n_obs_dev;
 };
 BaView ba_problem_view(sba_ba_problem* p);
+
+// remap.cu: out[img][p] = erp[img][lut[p]] (3-byte pixels); masked tables hold -1 for "no source", which gives 0
+int launch_lut_gather(sba_ctx* c, const uint8_t* d_erp, int64_t src_bytes, const int32_t* lut, int rows, int cols, uint8_t* d_out, int n_images,
+                      bool masked);
 
 // pipeline.cu: drop the cached pair graphs (context teardown)
 void pipeline_release(sba_ctx* c);

@@ -78,6 +78,10 @@ int sba_ctx_destroy(sba_ctx* c)
     c->cache.release_all();
     for (auto& kv : c->plans)
         if (kv.second.lut) cudaFree(kv.second.lut);
+    for (auto& kv : c->crop_plans)
+        if (kv.second.lut) cudaFree(kv.second.lut);
+    for (auto& kv : c->band_plans)
+        if (kv.second) cudaFree(kv.second);
     if (c->pinned_i32) cudaFreeHost(c->pinned_i32);
     for (int k = 0; k < 3; k++) {
         if (c->prof_e0[k]) cudaEventDestroy(c->prof_e0[k]);

@@ -121,6 +121,8 @@ static int get_plan(sba_ctx* c, int w, int h, int cs, RemapPlan** out)
 //            free) so that lanes 0..23 write the warp's 384 bytes as 24 aligned 16-byte stores.
 // Requirements (checked by the launcher): image bases 4-byte aligned, output base 16-byte aligned,
 // P*3 % 16 == 0; pixels past the last full 128-pixel group of an image go to remap_gather1_kernel.
+// MASKED: table entries < 0 mean "no source pixel" and produce 0 (spherical_surf's bounds check).
+template <bool MASKED>
 __global__ void __launch_bounds__(256)
 remap_gather_warp_kernel(const uint8_t* __restrict__ erp, const int32_t* __restrict__ lut, uint8_t* __restrict__ out,
                          int64_t src_bytes_per_image, int64_t P, int64_t groups128, int n_images)
@@ -138,7 +140,7 @@ remap_gather_warp_kernel(const uint8_t* __restrict__ erp, const int32_t* __restr
         uint32_t w0[4], w1[4], sh[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {          // all loads first (memory-level parallelism)
-            const int64_t a = (int64_t)idx[k] * 3;
+            const int64_t a = (int64_t)((MASKED && idx[k] < 0) ? 0 : idx[k]) * 3;
             const int64_t wi = a >> 2;
             sh[k] = (uint32_t)(a & 3) * 8;
             w0[k] = __ldg(words + wi);
@@ -146,7 +148,10 @@ remap_gather_warp_kernel(const uint8_t* __restrict__ erp, const int32_t* __restr
         }
         uint32_t v[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) v[k] = __funnelshift_r(w0[k], w1[k], sh[k]) & 0x00FFFFFFu;
+        for (int k = 0; k < 4; k++) {
+            v[k] = __funnelshift_r(w0[k], w1[k], sh[k]) & 0x00FFFFFFu;
+            if (MASKED && idx[k] < 0) v[k] = 0u;
+        }
         __syncwarp();
         stage[wib][lane * 3 + 0] = v[0] | (v[1] << 24);
         stage[wib][lane * 3 + 1] = (v[1] >> 8) | (v[2] << 16);
@@ -173,8 +178,9 @@ __global__ void remap_gather1_kernel(const uint8_t* __restrict__ erp, const int3
         int64_t p = p_first + (g - (int64_t)img * per);
         int i = (int)(p / cols), j = (int)(p - (int64_t)i * cols);
         int32_t s = __ldg(lut + (int64_t)i * lut_row_stride + face_off + j);
-        const uint8_t* q = erp + (int64_t)img * src_bytes_per_image + (int64_t)s * 3;
         uint8_t* o = out + ((int64_t)img * P + p) * 3;
+        if (s < 0) { o[0] = o[1] = o[2] = 0; continue; }   // masked tables only (the cube tables hold no negative entry)
+        const uint8_t* q = erp + (int64_t)img * src_bytes_per_image + (int64_t)s * 3;
         o[0] = __ldg(q); o[1] = __ldg(q + 1); o[2] = __ldg(q + 2);
     }
 }
@@ -214,31 +220,41 @@ __global__ void gather_matches_kernel(const float2* __restrict__ kl, const float
     orr[k] = kr[ti[k]];
 }
 
+// Table-driven gather of n_images images: out[img][p] = erp[img][lut[p]] for p in [0, rows*cols).
+int launch_lut_gather(sba_ctx* c, const uint8_t* d_erp, int64_t src_bytes, const int32_t* lut, int rows, int cols, uint8_t* d_out, int n_images,
+                      bool masked)
+{
+    const int64_t P = (int64_t)rows * cols;
+    const bool fast_ok = ((uintptr_t)d_erp % 4 == 0) && (src_bytes % 4 == 0) && ((uintptr_t)d_out % 16 == 0) && ((uintptr_t)lut % 16 == 0) &&
+                         ((P * 3) % 16 == 0 || n_images == 1) && P >= 128;
+    int64_t done_px = 0;
+    if (fast_ok) {
+        const int64_t groups = P / 128, total = groups * n_images;
+        // persistent-style grid: a multiple of the SM count, 8 resident CTAs (64 warps) per SM
+        int blocks = (int)std::min<int64_t>(ceil_div64(total, 8), (int64_t)c->sm_count * 8);
+        if (blocks >= c->sm_count) blocks = blocks / c->sm_count * c->sm_count;
+        if (masked) remap_gather_warp_kernel<true><<<blocks, 256, 0, c->stream>>>(d_erp, lut, d_out, src_bytes, P, groups, n_images);
+        else remap_gather_warp_kernel<false><<<blocks, 256, 0, c->stream>>>(d_erp, lut, d_out, src_bytes, P, groups, n_images);
+        SBA_LAUNCHED(c);
+        done_px = groups * 128;
+    }
+    if (done_px < P) {   // tail of every image (or everything when the fast path does not apply)
+        int64_t total = (P - done_px) * n_images;
+        int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)c->sm_count * 32);
+        remap_gather1_kernel<<<blocks, 256, 0, c->stream>>>(d_erp, lut, d_out, src_bytes, rows, cols, cols, 0, n_images, done_px);
+        SBA_LAUNCHED(c);
+    }
+    SBA_CUDA(cudaGetLastError());
+    return SBA_OK;
+}
+
 static int launch_gather(sba_ctx* c, const uint8_t* d_erp, const RemapPlan* plan, uint8_t* d_out, int n_images, int face)
 {
     int cs = plan->cs;
     int64_t src_bytes = (int64_t)plan->w * plan->h * 3;
     prof_begin(c, SBA_KERNEL_REMAP);
     if (face < 0) {
-        int64_t P = (int64_t)cs * 6 * cs;
-        const bool fast_ok = ((uintptr_t)d_erp % 4 == 0) && (src_bytes % 4 == 0) && ((uintptr_t)d_out % 16 == 0) &&
-                             ((P * 3) % 16 == 0 || n_images == 1) && P >= 128;
-        int64_t done_px = 0;
-        if (fast_ok) {
-            const int64_t groups = P / 128, total = groups * n_images;
-            // persistent-style grid: a multiple of the SM count, 8 resident CTAs (64 warps) per SM
-            int blocks = (int)std::min<int64_t>(ceil_div64(total, 8), (int64_t)c->sm_count * 8);
-            if (blocks >= c->sm_count) blocks = blocks / c->sm_count * c->sm_count;
-            remap_gather_warp_kernel<<<blocks, 256, 0, c->stream>>>(d_erp, plan->lut, d_out, src_bytes, P, groups, n_images);
-            SBA_LAUNCHED(c);
-            done_px = groups * 128;
-        }
-        if (done_px < P) {   // tail of every image (or everything when the fast path does not apply)
-            int64_t total = (P - done_px) * n_images;
-            int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)c->sm_count * 32);
-            remap_gather1_kernel<<<blocks, 256, 0, c->stream>>>(d_erp, plan->lut, d_out, src_bytes, cs, 6 * cs, 6 * cs, 0, n_images, done_px);
-            SBA_LAUNCHED(c);
-        }
+        SBA_TRY(launch_lut_gather(c, d_erp, src_bytes, plan->lut, cs, 6 * cs, d_out, n_images, false));
     } else {
         int64_t total = (int64_t)cs * cs * n_images;
         int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)c->sm_count * 32);

@@ -61,6 +61,41 @@ int main(int argc, char** argv)
         sba_solve_summary s = sba.adjust_rotation(left, right, w, h, rot);
         double out[5] = {rot[0], rot[1], rot[2], (double)s.iterations, s.final_cost};
         dump(dir + "/rot.bin", out, 5);
+        // spherical_surf: the four bands, one pitched crop, and the post-SURF part on supplied band keypoints/descriptors
+        // (ss_k{l,r}.bin: 4 x m x 2 floats, ss_d{l,r}.bin: 4 x m x 64 floats)
+        auto skl = slurp<float>(dir + "/ss_kl.bin");
+        if (!skl.empty()) {
+            spherical_surf ss;
+            cv::Mat bands[4];
+            ss.crop_bands(erp, bands);
+            for (int b = 0; b < 4; b++) dump(dir + "/ss_band" + std::to_string(b) + ".bin", bands[b].data, bands[b].total() * 3);
+            cv::Mat c45 = ss.crop_rotated_image(45, erp);
+            dump(dir + "/ss_crop45.bin", c45.data, c45.total() * 3);
+            cv::Mat rot = ss.eular2rot(cv::Vec3f(0, RAD(-45), 0));
+            cv::Vec2i px = ss.rotate_pixel(cv::Vec2i(h / 2, w / 3), rot, w, h);
+            auto skr = slurp<float>(dir + "/ss_kr.bin"), sdl = slurp<float>(dir + "/ss_dl.bin"), sdr = slurp<float>(dir + "/ss_dr.bin");
+            const int m = (int)(skl.size() / 8);
+            std::vector<cv::KeyPoint> kl[4], kr[4];
+            cv::Mat dl[4], dr[4];
+            for (int b = 0; b < 4; b++) {
+                kl[b].resize(m); kr[b].resize(m);
+                for (int i = 0; i < m; i++) {
+                    kl[b][i].pt.x = skl[2 * (b * m + i)]; kl[b][i].pt.y = skl[2 * (b * m + i) + 1];
+                    kr[b][i].pt.x = skr[2 * (b * m + i)]; kr[b][i].pt.y = skr[2 * (b * m + i) + 1];
+                }
+                dl[b] = cv::Mat(m, 64, CV_32FC1, sdl.data() + (size_t)b * m * 64);
+                dr[b] = cv::Mat(m, 64, CV_32FC1, sdr.data() + (size_t)b * m * 64);
+            }
+            std::vector<cv::KeyPoint> L, R;
+            std::vector<cv::DMatch> mm2;
+            ss.lift_and_match(kl, kr, dl, dr, w, h, L, R, mm2);
+            std::vector<float> o = {(float)px[0], (float)px[1]};
+            for (size_t i = 0; i < mm2.size(); i++) {
+                o.push_back((float)mm2[i].queryIdx); o.push_back((float)mm2[i].trainIdx);
+                o.push_back(L[i].pt.x); o.push_back(L[i].pt.y); o.push_back(R[i].pt.x); o.push_back(R[i].pt.y);
+            }
+            dump(dir + "/ss_out.bin", o.data(), o.size());
+        }
         auto sb1 = slurp<double>(dir + "/sp_b1.bin");
         if (!sb1.empty()) {
             auto sb2 = slurp<double>(dir + "/sp_b2.bin"), init = slurp<double>(dir + "/sp_init.bin");

@@ -122,15 +122,42 @@ sba_solve_summary spherical_bundle_adjuster::adjust_rotation(const std::vector<c
     return sum;
 }
 
+void spherical_bundle_adjuster::adjust(const std::vector<cv::KeyPoint>& left_key, const std::vector<cv::KeyPoint>& right_key, int im_width,
+                                       int im_height, const double init_rot[3], const double init_tran[3])
+{
+    const int n = (int)left_key.size();
+    for (int k = 0; k < 3; k++) { result_rot[k] = init_rot[k]; result_tran[k] = init_tran[k]; }
+    result_d.assign(n, std::array<double, 2>{{expected_d, expected_d}});   // :325-326
+    if (n < 2) return;
+    // pixel -> radian -> unit vector in double (:268-298), both sides in one batch
+    std::vector<float> px(4 * (size_t)n);
+    std::vector<double> b(6 * (size_t)n);
+    for (int i = 0; i < n; i++) {
+        px[2 * i] = left_key[i].pt.x; px[2 * i + 1] = left_key[i].pt.y;
+        px[2 * (n + i)] = right_key[i].pt.x; px[2 * (n + i) + 1] = right_key[i].pt.y;
+    }
+    sba_host::check(sba_pixels_to_bearings(sba_host::ctx(), px.data(), 2 * n, im_width, im_height, nullptr, b.data(), SBA_MEM_HOST));
+    std::vector<cv::Point3d> L(n), R(n);
+    for (int i = 0; i < n; i++) {
+        L[i] = cv::Point3d(b[3 * i], b[3 * i + 1], b[3 * i + 2]);
+        R[i] = cv::Point3d(b[3 * (n + i)], b[3 * (n + i) + 1], b[3 * (n + i) + 2]);
+    }
+    sba_solver_options options;              // :333-338
+    options.max_num_iterations = 50;
+    options.minimizer_progress_to_stdout = true;
+    options.num_threads = num_proc;
+    solve_problem(options, L, R, result_rot, result_tran, result_d, n);
+}
+
 void spherical_bundle_adjuster::do_bundle_adjustment(const cv::Mat& im_left, const cv::Mat& im_right)
 {
     std::vector<cv::KeyPoint> left_key, right_key;
     int match_size = 0, total_key_num = 0;
     cv::Mat match_output;
-    equi2cube_surf fm;
+    spherical_surf fm;                       // :263-266
     fm.set_omp(num_proc);
-    fm.set_cube_size(600);   // test/feature_test.cpp:198
     fm.do_all(im_left, im_right, left_key, right_key, match_size, match_output, total_key_num);
-    result_rot[0] = result_rot[1] = result_rot[2] = 0.0;
-    adjust_rotation(left_key, right_key, im_left.cols, im_left.rows, result_rot);
+    const double init_rot[3] = {expected_roll / 180 * M_PI, expected_pitch / 180 * M_PI, expected_yaw / 180 * M_PI};   // :328
+    const double init_tran[3] = {expected_tx, expected_ty, expected_tz};                                                // :329
+    adjust(left_key, right_key, im_left.cols, im_left.rows, init_rot, init_tran);
 }

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "equi2cube_surf.hpp"
+#include "spherical_surf.hpp"
 #include "sba_b200.h"
 
 struct ba_spherical_costfunctor_rot_only
@@ -70,9 +71,16 @@ class spherical_bundle_adjuster
     ~spherical_bundle_adjuster() {}
 
     void set_omp(int num_proc);
-    // Cubemap front-end (equi2cube_surf, cube 600 like the reference's test) -> bearings -> rotation-only
-    // solve from a zero rotation.  Needs SURF (real OpenCV) for the front-end.
+    // spherical_surf front-end (:252-266) -> bearings (:268-298) -> solve_problem (:333-345), as the reference.
+    // The reference seeds the solve with initial_guess (its 8-point voting, :47-181 -- host code, not built
+    // here); this facade starts from the expected_* values the object was constructed with, which is the
+    // reference's own commented-out alternative (:328-329).  Needs SURF (real OpenCV) for the front-end.
     void do_bundle_adjustment(const cv::Mat &im_left, const cv::Mat &im_right);
+
+    // Everything of do_bundle_adjustment after the front-end: matched ERP keypoints -> bearings -> three-stage
+    // solve from (init_rot, init_tran, expected_d).  Results in result_rot / result_tran / result_d.
+    void adjust(const std::vector<cv::KeyPoint>& left_key, const std::vector<cv::KeyPoint>& right_key, int im_width, int im_height,
+                const double init_rot[3], const double init_tran[3]);
 
     // The post-SURF part: matched ERP keypoints -> bearings (spherical_bundle_adjuster.cpp:268-298) ->
     // rotation-only solve.  Returns the rotation vector in rot[3].
@@ -92,6 +100,8 @@ class spherical_bundle_adjuster
     sba_solve_summary stage_summaries[3] = {};   // depth, rotation, translation of the last solve_problem
 
     double result_rot[3] = {0, 0, 0};
+    double result_tran[3] = {0, 0, 0};
+    std::vector<std::array<double, 2>> result_d;
 
     private:
     double expected_roll, expected_pitch, expected_yaw, expected_tx, expected_ty, expected_tz, expected_d;

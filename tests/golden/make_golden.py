@@ -60,8 +60,33 @@ def lut_from_ref(w, h, cs):
     return synth.decode_index_image(strip)
 
 
+def spherical_surf_case():
+    """spherical_surf.npz: crop tables, crop samples and rotated keypoints from the REAL reference
+    (spherical_surf.cpp compiled into oracle/_ref).  The table is recovered by pushing an index image through
+    the reference's crop_rotated_image; a second pass with an all-255 image tells "source pixel 0" from "unwritten"."""
+    w, h, seed = 1024, 512, 17
+    pitches = np.array([45.0, -45.0, -90.0, 30.5], np.float32)
+    im = synth.make_erp_image(w, h, seed=seed)
+    rng = np.random.default_rng(5)
+    keys = (rng.uniform(0, 1, (300, 2)) * [w - 1, h / 4 - 1]).astype(np.float32)
+    shas, samples, rotated = [], [], []
+    for p in pitches:
+        idx = synth.decode_index_image(oracle.ref_crop_rotated_image(synth.index_image(w, h), float(p))).astype(np.int64)
+        # tell "source pixel 0" from "unwritten": an all-ones image stays 0 only where nothing was written
+        written = oracle.ref_crop_rotated_image(np.full((h, w, 3), 255, np.uint8), float(p))[:, :, 0] == 255
+        lut = np.where(written, idx, -1).astype(np.int32)
+        shas.append(hashlib.sha256(lut.tobytes()).hexdigest())
+        samples.append(oracle.ref_crop_rotated_image(im, float(p))[::37, ::41])
+        rotated.append(oracle.ref_rotate_keypoints(keys, float(p), w, h))
+    np.savez_compressed(os.path.join(HERE, "spherical_surf.npz"), w=w, h=h, seed=seed, pitches=pitches, lut_sha256=np.array(shas),
+                        crop_samples=np.stack(samples), keys=keys, keys_rotated=np.stack(rotated))
+
+
 def main():
     assert oracle.ref_available(), "build oracle/_ref first (needs /root/reference)"
+    spherical_surf_case()
+    if "--only-spherical" in sys.argv:
+        return
     matcher_case("matcher_64.npz", 96, 130, 64, 11)
     matcher_case("matcher_128.npz", 70, 65, 128, 12)
     matcher_case("matcher_ragged.npz", 33, 5, 64, 13)

@@ -28,6 +28,13 @@ def test_cpp_facade_end_to_end(tmp_path):
     sb1, sb2 = sb1.astype(np.float32).astype(np.float64), sb2.astype(np.float32).astype(np.float64)
     r0, t0 = r_true + [0.02, -0.01, 0.03], t_true + [0.03, 0.02, -0.04]
     sb1.tofile(d + "/sp_b1.bin"); sb2.tofile(d + "/sp_b2.bin"); np.concatenate([r0, t0, [1.0]]).tofile(d + "/sp_init.bin")
+    # inputs of the spherical_surf post-SURF part: 4 bands x m keypoints/descriptors per side
+    m = 300
+    rng = np.random.default_rng(12)
+    ss_kl = (rng.uniform(0, 1, (4, m, 2)) * [w - 1, h / 4 - 1]).astype(np.float32)
+    ss_kr = (rng.uniform(0, 1, (4, m, 2)) * [w - 1, h / 4 - 1]).astype(np.float32)
+    ss_dl, ss_dr = synth.make_descriptors(4 * m, 4 * m, 64, seed=13)[:2]
+    ss_kl.tofile(d + "/ss_kl.bin"); ss_kr.tofile(d + "/ss_kr.bin"); ss_dl.tofile(d + "/ss_dl.bin"); ss_dr.tofile(d + "/ss_dr.bin")
     r = subprocess.run([DEMO, d], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("Ceres Solver Report") == 3
@@ -54,3 +61,28 @@ def test_cpp_facade_end_to_end(tmp_path):
     assert np.abs(sp[:3] - r_ref[0]).max() < 1e-6 and np.abs(sp[3:6] - t_ref[0]).max() < 1e-6
     assert int(sp[6]) == s_d.iterations
     assert np.all(np.abs(sp[9:].reshape(-1, 2) - d_ref) <= 1e-7 * np.maximum(1.0, np.abs(d_ref)))
+
+    # spherical_surf facade (spherical_surf.cpp:79-232 minus SURF)
+    pitches = (45.0, 0.0, -45.0, -90.0)
+    for b, pitch in enumerate(pitches):
+        band = np.fromfile(d + f"/ss_band{b}.bin", np.uint8).reshape(h // 4, w, 3)
+        want = im[h * 3 // 8: h * 3 // 8 + h // 4] if b == 1 else oracle.crop_rotated_image(im, pitch)
+        assert np.array_equal(band, want)
+    assert np.array_equal(np.fromfile(d + "/ss_crop45.bin", np.uint8).reshape(h // 4, w, 3), oracle.crop_rotated_image(im, 45.0))
+    so = np.fromfile(d + "/ss_out.bin", np.float32)
+    assert np.array_equal(so[:2].astype(np.int32), oracle.rotate_pixels(np.array([[h // 2, w // 3]]), -45.0, w, h)[0])
+    lifted = []
+    for keys in (ss_kl, ss_kr):
+        parts = []
+        for b, pitch in enumerate(pitches):
+            if b == 1:
+                k = keys[b].copy(); k[:, 1] = k[:, 1] + np.float32(h * 3 // 8)
+            else:
+                k = oracle.rotate_keypoints(keys[b], pitch, w, h)
+            parts.append(k)
+        lifted.append(np.concatenate(parts))
+    qi2, ti2, _ = oracle.match_two_image(ss_dl, ss_dr, 0.3)
+    rows = so[2:].reshape(-1, 6)
+    assert len(rows) == len(qi2) > 0
+    assert np.array_equal(rows[:, 0].astype(np.int32), qi2) and np.array_equal(rows[:, 1].astype(np.int32), ti2)
+    assert np.array_equal(rows[:, 2:4], lifted[0][qi2]) and np.array_equal(rows[:, 4:6], lifted[1][ti2])

@@ -240,3 +240,32 @@ def test_ba_depth_only_solve_oracle():
     # iteration cap
     _, s6, _ = oracle.ba_d_solve(b1, b2, r, t, np.full((400, 2), 5.0), 1.0, 1.0, 3)
     assert s6.iterations == 3 and s6.termination == 0
+
+
+@pytest.mark.skipif(not oracle.ref_available(), reason="oracle/_ref not built")
+def test_spherical_surf_oracle_pinned_to_reference():
+    # spherical_surf.cpp:17-123 restated in oracle/sba_oracle.c vs the reference's own file compiled into oracle/_ref
+    for th in ([0, 0.3, 0], [0.1, -0.7, 1.2], [0, np.float32(np.pi * 45 / 180), 0]):
+        assert np.array_equal(oracle.eular2rot(th), oracle.ref_eular2rot(th))
+    rng = np.random.default_rng(0)
+    for (w, h) in ((1024, 512), (1000, 500), (258, 130)):
+        im = synth.make_erp_image(w, h, seed=1)
+        rc = np.stack([rng.integers(0, h, 500), rng.integers(0, w, 500)], axis=1).astype(np.int32)
+        xy = (rng.uniform(0, 1, (800, 2)) * [w - 1, h / 4 - 1]).astype(np.float32)
+        for pitch in (45.0, -45.0, -90.0, 30.5):
+            assert np.array_equal(oracle.crop_rotated_image(im, pitch), oracle.ref_crop_rotated_image(im, pitch))
+            assert np.array_equal(oracle.rotate_pixels(rc, pitch, w, h), oracle.ref_rotate_pixels(rc, pitch, w, h))
+            assert np.array_equal(oracle.rotate_keypoints(xy, pitch, w, h), oracle.ref_rotate_keypoints(xy, pitch, w, h))
+    # the -90 degree crop of a 1024x512 image has a pixel whose source is undefined (NaN): skipped by the reference
+    assert (oracle.crop_rotated_lut(-90.0, 1024, 512) < 0).sum() >= 1
+
+
+def test_spherical_surf_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "spherical_surf.npz"))
+    w, h = int(g["w"]), int(g["h"])
+    im = synth.make_erp_image(w, h, seed=int(g["seed"]))
+    for k, pitch in enumerate(g["pitches"]):
+        lut = oracle.crop_rotated_lut(float(pitch), w, h)
+        assert hashlib.sha256(lut.tobytes()).hexdigest() == str(g["lut_sha256"][k])
+        assert np.array_equal(oracle.crop_rotated_image(im, float(pitch))[::37, ::41], g["crop_samples"][k])
+        assert np.array_equal(oracle.rotate_keypoints(g["keys"], float(pitch), w, h), g["keys_rotated"][k])
