@@ -113,30 +113,36 @@ static int get_plan(sba_ctx* c, int w, int h, int cs, RemapPlan** out)
 }
 
 // ---- the gather -------------------------------------------------------------------------------
-// Fast path.  A warp owns 128 adjacent strip pixels (384 output bytes).
-//   gather : each pixel's 3 bytes come from the aligned 32-bit word that holds its first byte, plus the
-//            next word only when the pixel straddles it (byte offset 2 or 3): ~1.5 loads per pixel
-//            instead of 3 byte loads, extracted with a funnel shift;
-//   store  : the 12 packed bytes of each lane go through shared memory (3-word lane stride: conflict
-//            free) so that lanes 0..23 write the warp's 384 bytes as 24 aligned 16-byte stores.
-// Requirements (checked by the launcher): image bases 4-byte aligned, output base 16-byte aligned,
+// Fast path.  A warp owns 128 adjacent output pixels (384 output bytes), four rounds of 32.
+//   gather : in round k lane l fetches pixel 32k+l, so the 32 lanes of one load instruction read ~32 ADJACENT
+//            source pixels (100-140 contiguous bytes: one or two L1 wavefronts instead of the four to six a
+//            4-pixels-per-lane layout costs).  A pixel's 3 bytes come from the aligned 32-bit word holding its
+//            first byte, plus the next word only when it straddles (byte offset 2 or 3), extracted with a
+//            funnel shift;
+//   store  : pixels go to shared memory one word each (conflict free), each lane reads back ITS four adjacent
+//            pixels as one 16-byte load, packs them to 12 bytes, and a second staging row lets lanes 0..23 write
+//            the warp's 384 bytes as 24 aligned 16-byte stores.
+// Requirements (checked by the launcher): image bases 4-byte aligned, table and output bases 16-byte aligned,
 // P*3 % 16 == 0; pixels past the last full 128-pixel group of an image go to remap_gather1_kernel.
 // MASKED: table entries < 0 mean "no source pixel" and produce 0 (spherical_surf's bounds check).
 template <bool MASKED>
 __global__ void __launch_bounds__(256)
 remap_gather_warp_kernel(const uint8_t* __restrict__ erp, const int32_t* __restrict__ lut, uint8_t* __restrict__ out,
-                         int64_t src_bytes_per_image, int64_t P, int64_t groups128, int n_images)
+                         int64_t src_bytes_per_image, int64_t P, int groups128, int n_images)
 {
+    __shared__ __align__(16) uint32_t pix[8][128];
     __shared__ __align__(16) uint32_t stage[8][96];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int64_t total = groups128 * n_images;
+    const int total = groups128 * n_images;          // 32-bit group arithmetic (the launcher splits larger batches)
     const int64_t last_word = src_bytes_per_image / 4 - 1;
-    for (int64_t g = (int64_t)blockIdx.x * 8 + wib; g < total; g += (int64_t)gridDim.x * 8) {
-        const int img = (int)(g / groups128);
-        const int64_t grp = g - (int64_t)img * groups128;
+    for (int g = blockIdx.x * 8 + wib; g < total; g += gridDim.x * 8) {
+        const int img = g / groups128;
+        const int grp = g - img * groups128;
         const uint32_t* words = reinterpret_cast<const uint32_t*>(erp + (int64_t)img * src_bytes_per_image);
-        const int4 s = __ldg(reinterpret_cast<const int4*>(lut) + grp * 32 + lane);
-        const int idx[4] = {s.x, s.y, s.z, s.w};
+        const int32_t* tab = lut + (int64_t)grp * 128 + lane;
+        int idx[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) idx[k] = __ldg(tab + 32 * k);
         uint32_t w0[4], w1[4], sh[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {          // all loads first (memory-level parallelism)
@@ -146,22 +152,24 @@ remap_gather_warp_kernel(const uint8_t* __restrict__ erp, const int32_t* __restr
             w0[k] = __ldg(words + wi);
             w1[k] = (sh[k] > 8) ? __ldg(words + min(wi + 1, last_word)) : 0u;
         }
-        uint32_t v[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            v[k] = __funnelshift_r(w0[k], w1[k], sh[k]) & 0x00FFFFFFu;
-            if (MASKED && idx[k] < 0) v[k] = 0u;
+            uint32_t v = __funnelshift_r(w0[k], w1[k], sh[k]) & 0x00FFFFFFu;
+            if (MASKED && idx[k] < 0) v = 0u;
+            pix[wib][32 * k + lane] = v;
         }
         __syncwarp();
-        stage[wib][lane * 3 + 0] = v[0] | (v[1] << 24);
-        stage[wib][lane * 3 + 1] = (v[1] >> 8) | (v[2] << 16);
-        stage[wib][lane * 3 + 2] = (v[2] >> 16) | (v[3] << 8);
+        const uint4 q = *reinterpret_cast<const uint4*>(&pix[wib][4 * lane]);   // pixels 4*lane .. 4*lane+3
+        stage[wib][lane * 3 + 0] = q.x | (q.y << 24);
+        stage[wib][lane * 3 + 1] = (q.y >> 8) | (q.z << 16);
+        stage[wib][lane * 3 + 2] = (q.z >> 16) | (q.w << 8);
         __syncwarp();
         if (lane < 24) {
-            const uint4 q = *reinterpret_cast<const uint4*>(&stage[wib][lane * 4]);
-            uint8_t* dst = out + ((int64_t)img * P + grp * 128) * 3 + lane * 16;
-            *reinterpret_cast<uint4*>(dst) = q;
+            const uint4 o = *reinterpret_cast<const uint4*>(&stage[wib][lane * 4]);
+            uint8_t* dst = out + ((int64_t)img * P + (int64_t)grp * 128) * 3 + lane * 16;
+            *reinterpret_cast<uint4*>(dst) = o;
         }
+        __syncwarp();   // both staging rows are rewritten by the next group
     }
 }
 
@@ -229,13 +237,20 @@ int launch_lut_gather(sba_ctx* c, const uint8_t* d_erp, int64_t src_bytes, const
                          ((P * 3) % 16 == 0 || n_images == 1) && P >= 128;
     int64_t done_px = 0;
     if (fast_ok) {
-        const int64_t groups = P / 128, total = groups * n_images;
-        // persistent-style grid: a multiple of the SM count, 8 resident CTAs (64 warps) per SM
-        int blocks = (int)std::min<int64_t>(ceil_div64(total, 8), (int64_t)c->sm_count * 8);
-        if (blocks >= c->sm_count) blocks = blocks / c->sm_count * c->sm_count;
-        if (masked) remap_gather_warp_kernel<true><<<blocks, 256, 0, c->stream>>>(d_erp, lut, d_out, src_bytes, P, groups, n_images);
-        else remap_gather_warp_kernel<false><<<blocks, 256, 0, c->stream>>>(d_erp, lut, d_out, src_bytes, P, groups, n_images);
-        SBA_LAUNCHED(c);
+        const int64_t groups = P / 128;
+        const int per_launch = (int)std::max<int64_t>(1, std::min<int64_t>(n_images, ((int64_t)1 << 30) / groups));   // 32-bit group ids in the kernel
+        for (int first = 0; first < n_images; first += per_launch) {
+            const int nimg = std::min(per_launch, n_images - first);
+            const int64_t total = groups * nimg;
+            // persistent-style grid: a multiple of the SM count, 8 resident CTAs (64 warps) per SM
+            int blocks = (int)std::min<int64_t>(ceil_div64(total, 8), (int64_t)c->sm_count * 8);
+            if (blocks >= c->sm_count) blocks = blocks / c->sm_count * c->sm_count;
+            const uint8_t* src = d_erp + (int64_t)first * src_bytes;
+            uint8_t* dst = d_out + (int64_t)first * P * 3;
+            if (masked) remap_gather_warp_kernel<true><<<blocks, 256, 0, c->stream>>>(src, lut, dst, src_bytes, P, (int)groups, nimg);
+            else remap_gather_warp_kernel<false><<<blocks, 256, 0, c->stream>>>(src, lut, dst, src_bytes, P, (int)groups, nimg);
+            SBA_LAUNCHED(c);
+        }
         done_px = groups * 128;
     }
     if (done_px < P) {   // tail of every image (or everything when the fast path does not apply)
