@@ -36,6 +36,7 @@ sys.path.insert(0, ROOT)
 
 W, H, CS, NKP, DIM = 3840, 1920, 960, 16384, 64
 RATIO = 0.3
+IN_FLIGHT = int(os.environ.get("SBA_BENCH_IN_FLIGHT", "4"))   # library contexts (streams + host threads) per GPU
 POOL = 6  # distinct pairs resident in HBM and cycled through: 6 x 52.7 MB = 316 MB >> 126 MB L2
 
 
@@ -74,38 +75,99 @@ class PairRunner:
                                                  want_matches=True)
         return np.array(res.rotation), res.n_matches, matches, res
 
+    def begin(self, d):
+        """sba_pair_rotation_begin: queue the pair, do not wait."""
+        return self.ctx.pair_rotation_begin(d["im1"], d["im2"], d["desc1"], d["desc2"], d["key1"], d["key2"], CS, ratio=RATIO, want_matches=True)
 
-def clocks_sampler_start(path):
-    q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-    try:
-        f = open(path, "w")
-        return subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"], stdout=f,
-                                stderr=subprocess.DEVNULL), f
-    except Exception:
-        return None, None
+    @staticmethod
+    def collect(call):
+        """sba_pair_rotation_end: wait for the pair and read its results."""
+        res, matches, _ = call.end()
+        return np.array(res.rotation), res.n_matches, matches, res
 
 
-def clocks_summary(path, device_index):
-    out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
-    try:
-        rows = [r.split(",") for r in open(path).read().strip().splitlines()]
-        rows = [[c.strip() for c in r] for r in rows if len(r) >= 9 and r[0].strip() == str(device_index)]
-        if not rows:
-            return out
-        sm = [float(r[1]) for r in rows]
-        out["sm_mhz"] = float(np.median(sm))
-        out["sm_max_mhz"] = float(rows[0][2])
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = set()
-        for r in rows:
-            for nme, v in zip(names, r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nme)
-        out["reasons"] = sorted(reasons)
-    except Exception:
-        pass
-    return out
+class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed regions (B200_PROFILING.md's clocks line) through
+    NVML in a background thread; falls back to a line-buffered `nvidia-smi -lms` child when NVML is unavailable."""
+
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+
+    def __init__(self, device_index, path):
+        self.idx, self.path = device_index, path
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        import threading
+        self._threading = threading
+        self._stop = threading.Event()
+        self._thread = self._proc = self._fh = None
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        bits = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)) if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons") \
+                            else int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        for name, bit in self.REASONS.items():
+                            if bits & bit:
+                                self.reasons.add(name)
+                    except Exception:
+                        pass
+                    self._stop.wait(0.02)
+            self._thread = self._threading.Thread(target=loop, daemon=True)
+            self._thread.start()
+        except Exception:
+            q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            try:
+                self._fh = open(self.path, "w")
+                self._proc = subprocess.Popen(["stdbuf", "-oL", "nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                                              stdout=self._fh, stderr=subprocess.DEVNULL)
+            except Exception:
+                self._proc = None
+        return self
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=1.0)
+        if self._proc is not None:
+            self._proc.terminate()
+            try:
+                self._proc.wait(timeout=2.0)
+            except Exception:
+                pass
+            self._fh.close()
+            self._parse_csv()
+        try:   # keep the raw samples beside the number
+            with open(self.path + ".summary", "w") as f:
+                f.write(json.dumps(self.summary()) + "\n")
+        except Exception:
+            pass
+
+    def _parse_csv(self):
+        try:
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for line in open(self.path).read().strip().splitlines():
+                r = [c.strip() for c in line.split(",")]
+                if len(r) < 9 or r[0] != str(self.idx):
+                    continue
+                self.samples.append(float(r[1]))
+                self.max_mhz = float(r[2])
+                for nme, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nme)
+        except Exception:
+            pass
+
+    def summary(self):
+        return dict(sm_mhz=float(np.median(self.samples)) if self.samples else None, sm_max_mhz=self.max_mhz,
+                    reasons=sorted(self.reasons), samples=len(self.samples))
 
 
 def bench_ours(args):
@@ -121,8 +183,13 @@ def bench_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    ctx = Context(local_rank)
-    runner = PairRunner(ctx)
+    # IN_FLIGHT library contexts per GPU, each on its own non-blocking stream: while one pair's result is still
+    # on its way to the host, the next pair's kernels (device-resident run) or uploads (end-to-end run) are already
+    # queued through sba_pair_rotation_begin / _end.  Pairs are independent.
+    streams = [torch.cuda.Stream(dev) for _ in range(IN_FLIGHT)]
+    ctxs = [Context(local_rank, stream=st.cuda_stream) for st in streams]
+    runners = [PairRunner(c) for c in ctxs]
+    ctx, runner = ctxs[0], runners[0]
     peaks = _peaks()
 
     pool_host = make_pool(POOL, seed0=1000 * (rank + 1))
@@ -139,52 +206,70 @@ def bench_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up: builds the remap plan, sizes the scratch buffers and lets the library see every pool
-    #      entry twice (first call eager, second call captured into its CUDA graph); checks the answer once
+    def timed_steps(data, steps):
+        """Exactly `steps` pairs, step k on context k % IN_FLIGHT: a pair's result is collected only when its context
+        is needed again, so up to IN_FLIGHT pairs are queued at any time (one host thread, no extra copies).
+        Device time from the start event to the last end event of any stream.  Returns (ms, result of the last pair)."""
+        barrier()
+        start = torch.cuda.Event(enable_timing=True)
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(IN_FLIGHT)]
+        pending = [None] * IN_FLIGHT
+        out = None
+        start.record(streams[0])
+        for k in range(steps):
+            j = k % IN_FLIGHT
+            if pending[j] is not None:
+                out = runners[j].collect(pending[j])
+            pending[j] = runners[j].begin(data[k % POOL])
+        for j in [(steps + i) % IN_FLIGHT for i in range(IN_FLIGHT)]:      # oldest first
+            if pending[j] is not None:
+                out = runners[j].collect(pending[j])
+            ends[j].record(streams[j])
+        barrier()
+        return max(start.elapsed_time(e) for e in ends), out
+
+    # ---- warm-up: builds the remap plan, sizes the scratch buffers of every context and lets the library see
+    #      every pool entry; checks the answer once
     n_warm = max(3, args.warmup, 2 * POOL)
-    for k in range(n_warm):
-        r, nm, m, s = runner.run(resident[k % POOL])
+    for rn in runners:
+        for k in range(n_warm):
+            r, nm, m, s = rn.run(resident[k % POOL])
     truth = pool_host[(n_warm - 1) % POOL]["r_true"]
     assert np.linalg.norm(r - truth) < 1e-3, (r, truth)
 
-    # ---- device-resident timed region: exactly K steps, CUDA events on the launching stream
+    # ---- device-resident timed region: exactly K steps, CUDA events on the launching streams
     clk_path = os.path.join(ROOT, "gpurun_out", f"clocks_rank{rank}.csv")
     os.makedirs(os.path.dirname(clk_path), exist_ok=True)
-    proc, fh = clocks_sampler_start(clk_path) if rank == 0 else (None, None)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = ctx.launch_count
-    barrier()
-    e0.record()
-    for k in range(args.steps):
-        runner.run(resident[k % POOL])
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    launches = ctx.launch_count - launches0
+    sampler = ClockSampler(local_rank, clk_path).start() if rank == 0 else None
+    launches0 = sum(c.launch_count for c in ctxs)
+    ms_total, _ = timed_steps(resident, args.steps)
+    launches = sum(c.launch_count for c in ctxs) - launches0
 
-    # ---- per-kernel device times (CUDA events around the dominant kernels), outside the timed region
+    # ---- per-kernel device times (CUDA events around the dominant kernels), one context alone, outside the timed region
     ctx.set_profiling(True)
     match_ms, remap_ms, ba_ms = [], [], []
     for k in range(min(args.steps, 10)):
         runner.run(resident[k % POOL])
         match_ms.append(ctx.kernel_ms(0)); remap_ms.append(ctx.kernel_ms(1)); ba_ms.append(ctx.kernel_ms(2))
     ctx.set_profiling(False)
+    # one pair at a time on one context, for reference next to the pipelined number
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(streams[0])
+    for k in range(min(args.steps, 20)):
+        runner.run(resident[k % POOL])
+    e1.record(streams[0])
+    barrier()
+    ms_serial = e0.elapsed_time(e1) / min(args.steps, 20)
 
     # ---- end-to-end timed region: pinned host -> device every step, results read back
-    d2h_bytes = 0
-    for k in range(n_warm):                                     # warm-up of the host-buffer path (staging buffers, second stream, graphs)
-        runner.run(pinned[k % POOL])
-    barrier()
-    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for k in range(args.steps):
-        r, nm, m, s = runner.run(pinned[k % POOL])              # host buffers in, match list + rotation out
-        d2h_bytes = 3 * 4 * nm + 4 + 24 * 2
-    t1.record()
-    barrier()
-    ms_e2e = t0.elapsed_time(t1)
-    if proc is not None:
-        proc.terminate(); fh.close()
+    for rn in runners:
+        for k in range(n_warm):                                 # warm-up of the host-buffer path (staging buffers, second stream)
+            rn.run(pinned[k % POOL])
+    ms_e2e, (r, nm, m, s) = timed_steps(pinned, args.steps)     # host buffers in, match list + rotation out
+    d2h_bytes = 3 * 4 * nm + 4 + 24 * 2
+    if sampler is not None:
+        sampler.stop()
 
     times = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -208,9 +293,9 @@ def bench_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32 (matcher distances; bf16x3 tensor filter) / f64 (BA residual, LM)",
         "data": "synthetic",
         "config": {"workload": "C2: 3840x1920 ERP pair, cube 960, 16384x16384 SURF-64 kNN2+ratio 0.3, rotation BA",
-                   "pairs_per_step_per_gpu": 1, "l2_policy": f"inputs larger than L2: {POOL} resident pairs ({POOL * h2d_bytes / 1e6:.0f} MB) cycled",
+                   "pairs_per_step_per_gpu": 1, "pairs_in_flight_per_gpu": IN_FLIGHT, "ms_per_pair_one_at_a_time": ms_serial, "l2_policy": f"inputs larger than L2: {POOL} resident pairs ({POOL * h2d_bytes / 1e6:.0f} MB) cycled",
                    "matcher_algo": algo, "matches_per_pair": int(nm), "lm_iterations": int(s.lm_iterations),
-                   "api": "sba_pair_rotation (one C-ABI call per pair)"},
+                   "api": "sba_pair_rotation_begin/_end (one C-ABI call pair per ERP pair)"},
         "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes)},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "matcher distance kernel (" + algo + ")", "bound": "tensor", "achieved": achieved, "peak": peak,
@@ -219,7 +304,7 @@ def bench_ours(args):
                      "algorithmic_flops_per_launch": flops, "kernel_ms": mk * 1e3},
         "stage_ms": {"match_kernel": float(np.mean(match_ms)), "remap_kernel_per_image": float(np.mean(remap_ms)),
                      "ba_eval_kernel_last": float(np.mean(ba_ms))},
-        "clocks": clocks_summary(clk_path, local_rank),
+        "clocks": sampler.summary(),
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(budget_s=args.cpu_budget)

@@ -294,6 +294,20 @@ int sba_pair_rotation(sba_ctx* ctx, const uint8_t* erp_left, const uint8_t* erp_
                       int max_iter, int32_t* query_idx_out, int32_t* train_idx_out, float* dist_out,
                       sba_pair_result* result, int mem);
 
+/* The same call split in two so that a host thread can keep several pairs in flight (one per context):
+ * _begin queues all stream work of the pair and returns without waiting; _end waits for it, finishes the
+ * solve if its first batch of evaluations was not enough, copies the requested outputs back and fills
+ * `result`.  All buffers passed to _begin must stay valid until _end returns.  One call in flight per
+ * context (the staging buffers belong to the context): pipelining N pairs takes N contexts on N streams. */
+typedef struct sba_pair_call sba_pair_call;
+int sba_pair_rotation_begin(sba_ctx* ctx, const uint8_t* erp_left, const uint8_t* erp_right, int w, int h, int cube_size,
+                            uint8_t* strip_left_out, uint8_t* strip_right_out, const float* desc_left, int n_left,
+                            const float* desc_right, int n_right, int dim, const float* key_left_xy, const float* key_right_xy,
+                            float ratio, const double r0[3], const double t[3], double d1, double d2, double huber_delta,
+                            int max_iter, int32_t* query_idx_out, int32_t* train_idx_out, float* dist_out, int mem,
+                            sba_pair_call** call_out);
+int sba_pair_rotation_end(sba_pair_call* call, sba_pair_result* result);
+
 #ifdef __cplusplus
 }
 #endif

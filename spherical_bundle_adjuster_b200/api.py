@@ -272,6 +272,14 @@ class Context:
                       ratio: float = 0.3, r0=(0.0, 0.0, 0.0), t=(0.0, 0.0, 0.0), d1=1.0, d2=1.0, huber=1.0, max_iter=50,
                       want_matches: bool = True, want_strips: bool = False):
         """Returns (PairResult, matches (query_idx, train_idx, dist) or None, strips or None)."""
+        return self.pair_rotation_begin(im_left, im_right, desc_left, desc_right, key_left_xy, key_right_xy, cube_size, w, h, ratio, r0, t,
+                                        d1, d2, huber, max_iter, want_matches, want_strips, _blocking=True).end()
+
+    def pair_rotation_begin(self, im_left, im_right, desc_left, desc_right, key_left_xy, key_right_xy, cube_size: int, w: int = 0, h: int = 0,
+                            ratio: float = 0.3, r0=(0.0, 0.0, 0.0), t=(0.0, 0.0, 0.0), d1=1.0, d2=1.0, huber=1.0, max_iter=50,
+                            want_matches: bool = True, want_strips: bool = False, _blocking: bool = False) -> "PairCall":
+        """Queue one pair and return at once; ``.end()`` on the returned call collects what ``pair_rotation`` returns.
+        One call in flight per context: keep N pairs in flight with N contexts on N streams."""
         u8t = torch.uint8 if torch else None
         f32t = torch.float32 if torch else None
         i32t = torch.int32 if torch else None
@@ -293,17 +301,46 @@ class Context:
             sr = _empty_like_kind(dl, (cube_size, 6 * cube_size, 3), np.uint8, u8t)
         r0 = np.ascontiguousarray(r0, np.float64)
         t = np.ascontiguousarray(t, np.float64)
-        res = _lib.PairResult()
-        check(self._lib.sba_pair_rotation(self._h, _ptr(iml), _ptr(imr), w, h, cube_size, _ptr(sl), _ptr(sr), _ptr(dl), nl, _ptr(dr), nr, dim,
-                                          _ptr(kl), _ptr(kr), ratio, _ptr(r0), _ptr(t), d1, d2, huber, max_iter, _ptr(qi), _ptr(ti), _ptr(dd),
-                                          C.byref(res), mem))
-        n = res.n_matches
-        matches = (qi[:n], ti[:n], dd[:n]) if want_matches else None
-        return res, matches, ((sl, sr) if sl is not None else None)
+        call = PairCall(self, (iml, imr, dl, dr, kl, kr, r0, t), qi, ti, dd, sl, sr)
+        args = (self._h, _ptr(iml), _ptr(imr), w, h, cube_size, _ptr(sl), _ptr(sr), _ptr(dl), nl, _ptr(dr), nr, dim,
+                _ptr(kl), _ptr(kr), ratio, _ptr(r0), _ptr(t), d1, d2, huber, max_iter, _ptr(qi), _ptr(ti), _ptr(dd))
+        if _blocking:   # the one-call entry point (also the only one that may replay a CUDA graph)
+            check(self._lib.sba_pair_rotation(*args, C.byref(call._res), mem))
+            call._done = True
+        else:
+            check(self._lib.sba_pair_rotation_begin(*args, mem, C.byref(call._h)))
+        return call
 
     # -- bundle adjustment
     def ba_problem(self, b1, b2, cam=None, n_cam: int = 1) -> "BAProblem":
         return BAProblem(self, b1, b2, cam, n_cam)
+
+
+class PairCall:
+    """A pair queued by ``Context.pair_rotation_begin`` (wraps ``sba_pair_call``); keeps every buffer alive until ``end``."""
+
+    def __init__(self, ctx, inputs, qi, ti, dd, sl, sr):
+        self._ctx, self._inputs = ctx, inputs
+        self._qi, self._ti, self._dd, self._sl, self._sr = qi, ti, dd, sl, sr
+        self._h = C.c_void_p()
+        self._res = _lib.PairResult()
+        self._done = False
+
+    def end(self):
+        if not self._done:
+            check(self._ctx._lib.sba_pair_rotation_end(self._h, C.byref(self._res)))
+            self._done = True
+            self._h = C.c_void_p()
+        res, n = self._res, self._res.n_matches
+        matches = (self._qi[:n], self._ti[:n], self._dd[:n]) if self._qi is not None else None
+        return res, matches, ((self._sl, self._sr) if self._sl is not None else None)
+
+    def __del__(self):
+        try:
+            if not self._done and self._h:
+                self.end()
+        except Exception:
+            pass
 
 
 class PeerComm:

@@ -154,6 +154,7 @@ struct sba_ctx {
     std::map<std::tuple<int, int, uint32_t>, sba::CropPlan> crop_plans;   // keyed by (w, h, bits of the pitch)
     std::map<std::pair<int, int>, int32_t*> band_plans;                  // the four bands of spherical_surf::do_all in one table
     sba_match_stats match_stats{};
+    bool pair_pending = false;  // a sba_pair_rotation_begin whose _end has not run yet (pipeline.cu)
     int* pinned_i32 = nullptr;  // small pinned host mailbox (64 ints) for scalar read-backs
     bool profiling = false;
     cudaEvent_t prof_e0[3] = {nullptr, nullptr, nullptr}, prof_e1[3] = {nullptr, nullptr, nullptr};

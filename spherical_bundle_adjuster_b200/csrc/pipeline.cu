@@ -230,9 +230,84 @@ void pipeline_release(sba_ctx* c)
     c->graph_ev = nullptr;
 }
 
+static PairKey make_key(const uint8_t* erp_left, const uint8_t* erp_right, int w, int h, int cube_size, uint8_t* strip_left_out,
+                        uint8_t* strip_right_out, const float* desc_left, int n_left, const float* desc_right, int n_right, int dim,
+                        const float* key_left_xy, const float* key_right_xy, float ratio, const double t[3], double d1, double d2,
+                        double huber_delta, int max_iter, int32_t* query_idx_out, int32_t* train_idx_out, float* dist_out, int mem)
+{
+    PairKey key;
+    memset(&key, 0, sizeof(key));
+    key.erp_l = erp_left; key.erp_r = erp_right; key.strip_l = strip_left_out; key.strip_r = strip_right_out;
+    key.desc_l = desc_left; key.desc_r = desc_right; key.key_l = key_left_xy; key.key_r = key_right_xy;
+    key.qi = query_idx_out; key.ti = train_idx_out; key.dist = dist_out;
+    key.w = w; key.h = h; key.cs = cube_size; key.n_left = n_left; key.n_right = n_right; key.dim = dim; key.mem = mem; key.max_iter = max_iter;
+    key.ratio = ratio; key.t[0] = t[0]; key.t[1] = t[1]; key.t[2] = t[2]; key.d1 = d1; key.d2 = d2; key.huber = huber_delta;
+    return key;
+}
+
 }  // namespace sba
 
+// One pair whose stream work is queued but whose results have not been collected yet.
+struct sba_pair_call {
+    sba_ctx* c;
+    sba::PairKey key;
+    sba::PairState ps;
+    sba_ba_problem* prob;
+    int launched;
+    double r0[3];
+};
+
 extern "C" {
+
+int sba_pair_rotation_begin(sba_ctx* c, const uint8_t* erp_left, const uint8_t* erp_right, int w, int h, int cube_size, uint8_t* strip_left_out,
+                            uint8_t* strip_right_out, const float* desc_left, int n_left, const float* desc_right, int n_right, int dim,
+                            const float* key_left_xy, const float* key_right_xy, float ratio, const double r0[3], const double t[3], double d1,
+                            double d2, double huber_delta, int max_iter, int32_t* query_idx_out, int32_t* train_idx_out, float* dist_out,
+                            int mem, sba_pair_call** call_out)
+{
+    SBA_CHECK_ARG(c && call_out && w > 0 && h > 0 && cube_size > 0 && n_left >= 0 && n_right >= 0 && max_iter >= 0);
+    SBA_CHECK_ARG(desc_left && desc_right && key_left_xy && key_right_xy && r0 && t);
+    SBA_CHECK_ARG((erp_left == nullptr) == (erp_right == nullptr));
+    *call_out = nullptr;
+    if (c->pair_pending) {
+        sba::set_error("a pair is already in flight on this context (its staging buffers are in use): call sba_pair_rotation_end first, "
+                       "or use one context per pair in flight");
+        return SBA_ERR_INVALID;
+    }
+    SBA_CUDA(cudaSetDevice(c->device));
+    sba_pair_call* call = new sba_pair_call();
+    call->c = c;
+    call->key = make_key(erp_left, erp_right, w, h, cube_size, strip_left_out, strip_right_out, desc_left, n_left, desc_right, n_right, dim,
+                         key_left_xy, key_right_xy, ratio, t, d1, d2, huber_delta, max_iter, query_idx_out, train_idx_out, dist_out, mem);
+    call->prob = nullptr;
+    call->launched = 0;
+    for (int k = 0; k < 3; k++) call->r0[k] = r0[k];
+    const int status = enqueue_pair(c, call->key, r0, &call->prob, &call->launched, &call->ps);
+    if (status != SBA_OK) {
+        cudaStreamSynchronize(c->stream);
+        if (call->prob) sba_ba_problem_destroy(call->prob);
+        delete call;
+        return status;
+    }
+    c->pair_pending = true;
+    *call_out = call;
+    return SBA_OK;
+}
+
+int sba_pair_rotation_end(sba_pair_call* call, sba_pair_result* result)
+{
+    SBA_CHECK_ARG(call && result);
+    sba_ctx* c = call->c;
+    SBA_CUDA(cudaSetDevice(c->device));
+    memset(result, 0, sizeof(*result));
+    for (int k = 0; k < 3; k++) result->rotation[k] = call->r0[k];
+    int status = finish_pair(c, call->key, call->prob, call->launched, call->ps, call->r0, result);
+    if (status != SBA_OK || call->key.mem == SBA_MEM_DEVICE) cudaStreamSynchronize(c->stream);   // the problem's buffers go back to the cache
+    if (call->prob) sba_ba_problem_destroy(call->prob);
+    c->pair_pending = false;
+    delete call;
+    return status;
+}
 
 int sba_pair_rotation(sba_ctx* c, const uint8_t* erp_left, const uint8_t* erp_right, int w, int h, int cube_size, uint8_t* strip_left_out,
                       uint8_t* strip_right_out, const float* desc_left, int n_left, const float* desc_right, int n_right, int dim,
@@ -247,13 +322,12 @@ int sba_pair_rotation(sba_ctx* c, const uint8_t* erp_left, const uint8_t* erp_ri
     memset(result, 0, sizeof(*result));
     result->rotation[0] = r0[0]; result->rotation[1] = r0[1]; result->rotation[2] = r0[2];
 
-    PairKey key;
-    memset(&key, 0, sizeof(key));
-    key.erp_l = erp_left; key.erp_r = erp_right; key.strip_l = strip_left_out; key.strip_r = strip_right_out;
-    key.desc_l = desc_left; key.desc_r = desc_right; key.key_l = key_left_xy; key.key_r = key_right_xy;
-    key.qi = query_idx_out; key.ti = train_idx_out; key.dist = dist_out;
-    key.w = w; key.h = h; key.cs = cube_size; key.n_left = n_left; key.n_right = n_right; key.dim = dim; key.mem = mem; key.max_iter = max_iter;
-    key.ratio = ratio; key.t[0] = t[0]; key.t[1] = t[1]; key.t[2] = t[2]; key.d1 = d1; key.d2 = d2; key.huber = huber_delta;
+    if (c->pair_pending) {
+        sba::set_error("a pair is already in flight on this context: call sba_pair_rotation_end first");
+        return SBA_ERR_INVALID;
+    }
+    const PairKey key = make_key(erp_left, erp_right, w, h, cube_size, strip_left_out, strip_right_out, desc_left, n_left, desc_right, n_right, dim,
+                                 key_left_xy, key_right_xy, ratio, t, d1, d2, huber_delta, max_iter, query_idx_out, train_idx_out, dist_out, mem);
 
     // Opt-in (SBA_PAIR_GRAPHS=1): measured on B200 at C2 with six alternating buffer sets the replay path
     // (450-500 us per pair) loses to the plain stream path (373 us) -- after the device-side match count

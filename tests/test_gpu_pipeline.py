@@ -109,3 +109,40 @@ print(out)
         runs[flag] = eval(r.stdout.strip().splitlines()[-1])
     assert runs["0"] == runs["1"]
     assert runs["0"][0][1] > 1000 and runs["0"][0] == runs["0"][2] and runs["0"][1] == runs["0"][3]
+
+
+@pytest.mark.parametrize("kind", ["host", "device"])
+def test_pair_rotation_begin_end_keeps_pairs_in_flight(kind):
+    """sba_pair_rotation_begin/_end: three pairs queued on three contexts (own streams) before any result is
+    collected give exactly what the blocking call gives; a second begin on a busy context is refused."""
+    import torch
+    from spherical_bundle_adjuster_b200 import Context, SbaError
+    w, h, cs, n = 1024, 512, 256, 2500
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    ctxs = [Context(0, stream=s.cuda_stream) for s in streams]
+    data = []
+    for k in range(3):
+        pair = synth.make_pair(n, n - 31 * k, cs=cs, seed=40 + k, rotvec=(0.1 * k - 0.1, 0.2, -0.3))
+        a = [synth.make_erp_image(w, h, seed=2 * k), synth.make_erp_image(w, h, seed=2 * k + 1), pair["desc1"], pair["desc2"], pair["key1_xy"],
+             pair["key2_xy"]]
+        if kind == "device":
+            a = [torch.from_numpy(x).cuda() for x in a]
+        else:
+            a = [torch.from_numpy(x).pin_memory() for x in a]
+        data.append(a)
+    torch.cuda.synchronize()
+    want = [ctxs[0].pair_rotation(*a, cs, want_strips=True) for a in data]
+    calls = [ctxs[k].pair_rotation_begin(*data[k], cs, want_strips=True) for k in range(3)]
+    with pytest.raises(SbaError):
+        ctxs[1].pair_rotation_begin(*data[0], cs)
+    got = [c.end() for c in reversed(calls)][::-1]          # collect in another order than queued
+    torch.cuda.synchronize()
+    tonp = lambda x: x.cpu().numpy() if hasattr(x, "cpu") else np.asarray(x)
+    for (r0, m0, s0), (r1, m1, s1) in zip(want, got):
+        assert r0.n_matches == r1.n_matches > 0 and np.array_equal(np.array(r0.rotation), np.array(r1.rotation))
+        for a, b in zip(m0 + s0, m1 + s1):
+            assert np.array_equal(tonp(a), tonp(b))
+    again = ctxs[1].pair_rotation_begin(*data[0], cs).end()   # the context is free again after end()
+    assert again[0].n_matches == want[0][0].n_matches
+    for c in ctxs:
+        c.close()
