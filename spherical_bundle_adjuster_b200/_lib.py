@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsba_b200.so")
+LIB_PATH = os.environ.get("SBA_B200_LIB") or os.path.join(_HERE, "libsba_b200.so")   # override: debug builds under build/
 
 SBA_MEM_HOST, SBA_MEM_DEVICE = 0, 1
 MATCH_AUTO, MATCH_SIMT_EXACT, MATCH_TENSOR = 0, 1, 2

@@ -233,6 +233,20 @@ __device__ __forceinline__ void cand_reset(Cand& c)
     for (int k = 0; k < NCAND; k++) { c.v[k] = __int_as_float(0x7f800000); c.id[k] = -1; }
 }
 
+#ifdef SBA_TC_TRACE
+// Debug build only (make TRACE=1): per-CTA time stamps, read back by tools/tc_trace.py through sba_tc_trace_buffer().
+__device__ unsigned long long g_tc_trace[148 * 16];
+__device__ __forceinline__ unsigned long long gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define TC_TRACE(slot) do { g_tc_trace[(blockIdx.x % 148) * 16 + (slot)] = gtime(); } while (0)
+#else
+#define TC_TRACE(slot) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(THREADS, 1)
 tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const float* __restrict__ nb,
               Partition part, float4* __restrict__ cand_v, int4* __restrict__ cand_id, int slots)
@@ -253,6 +267,7 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     uint32_t* tmem_slot = (uint32_t*)(bars + 6 + 2 * STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) TC_TRACE(0);   // CTA start
     // this CTA's span of tiles, walked with 32-bit incremental (query block, train tile) indices
     const int t_begin = (int)part.start(blockIdx.x), n_tiles = (int)part.start(blockIdx.x + 1) - t_begin;
     const int ntb = part.ntb;
@@ -273,6 +288,7 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) TC_TRACE(1);   // set-up done
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -323,6 +339,8 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             mbar_wait(acc_empty + acc, (uint32_t)(((n >> 1) & 1) ^ 1));
             mbar_wait(b_full + s, ring_phase);
             tcgen05_fence_after();
+            if (n == 0 && is_leader) TC_TRACE(2);              // first operands landed
+            if (n == n_tiles - 1 && is_leader) TC_TRACE(3);    // last tile's MMAs about to issue
             // descriptors address 16-byte units: stage stride and k-block stride are plain adds
             const uint64_t dB_hi = dB0 + (uint64_t)(s * ((2 * B_KBLOCK_BYTES) >> 4));
             const uint64_t dB_lo = dB_hi + (B_KBLOCK_BYTES >> 4);
@@ -376,6 +394,8 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             }
             mbar_wait(acc_full + acc, (uint32_t)((n >> 1) & 1));
             tcgen05_fence_after();
+            if (warp == 4 && lane == 0 && n == 0) TC_TRACE(4);             // first accumulator ready
+            if (warp == 4 && lane == 0 && n == n_tiles - 1) TC_TRACE(5);   // last accumulator ready
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS + slice * 64);
             uint32_t buf[2][32];
             TMEM_LD_X32(buf[0], taddr);
@@ -400,10 +420,25 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 }
                 const float gm = fminf(fminf(fminf(cm[0], cm[1]), fminf(cm[2], cm[3])), fminf(fminf(cm[4], cm[5]), fminf(cm[6], cm[7])));
                 if (__any_sync(0xffffffffu, gm < cand.v[3])) {
+                    // While a span is young its lists are far from saturated and SOME lane of the warp wants to insert for
+                    // almost every chunk, so a per-chunk insert would run for all eight chunks of every group.  Instead
+                    // each lane inserts its best chunk of the group, and only if a second chunk of the same group also
+                    // beats the (updated) fourth-best value -- rare after a few tiles -- are the others visited.
                     const int id0 = tb * (BN / CHUNK) + csub * 16 + g * 8;
+                    int c1 = 7;
 #pragma unroll
-                    for (int c = 0; c < 8; c++)
-                        if (__any_sync(0xffffffffu, cm[c] < cand.v[3])) cand_insert_bf(cand, cm[c], id0 + c);
+                    for (int c = 6; c >= 0; c--) c1 = (cm[c] == gm) ? c : c1;          // first chunk holding the minimum
+                    cand_insert_bf(cand, gm, id0 + c1);
+                    float m2 = __int_as_float(0x7f800000);
+#pragma unroll
+                    for (int c = 0; c < 8; c++) m2 = fminf(m2, c == c1 ? __int_as_float(0x7f800000) : cm[c]);
+                    if (__any_sync(0xffffffffu, m2 < cand.v[3])) {
+#pragma unroll
+                        for (int c = 0; c < 8; c++) {
+                            const float v = (c == c1) ? __int_as_float(0x7f800000) : cm[c];
+                            if (__any_sync(0xffffffffu, v < cand.v[3])) cand_insert_bf(cand, v, id0 + c);
+                        }
+                    }
                 }
             }
             if (tb_next == 0 || n + 1 == n_tiles) {   // last tile of this query block in the span: publish
@@ -418,8 +453,13 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         }
     }
 
+    if (warp == 4 && lane == 0) TC_TRACE(6);   // epilogue of warp 4 done
     tcgen05_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) { TC_TRACE(7); }
+#ifdef SBA_TC_TRACE
+    if (threadIdx.x == 0) g_tc_trace[(blockIdx.x % 148) * 16 + 8] = (unsigned long long)n_tiles;
+#endif
     if (warp == 1) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -741,3 +781,10 @@ int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, 
 }
 
 }  // namespace sba
+
+#ifdef SBA_TC_TRACE
+extern "C" int sba_tc_trace_read(unsigned long long* out /* [148 x 16] */)
+{
+    return cudaMemcpyFromSymbol(out, sba::tc::g_tc_trace, sizeof(unsigned long long) * 148 * 16) == cudaSuccess ? 0 : -1;
+}
+#endif
