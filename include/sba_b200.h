@@ -165,6 +165,25 @@ int sba_rotate_pixels_mat(sba_ctx* ctx, const int32_t* rc_in, int n, const doubl
 int sba_rotate_keypoints(sba_ctx* ctx, float* xy_inout, int n, float pitch_inv_deg, int w, int h, int mem);
 
 /* ---------------------------------------------------------------------------------------------
+ * Initial guess of the bundle adjuster (spherical_bundle_adjuster.cpp:47-181)
+ *
+ * b1, b2: n x 3 doubles (unit bearings, key_point_*_rect); idx: [n_samples x sample_n] row indices of the
+ * random subsets (the reference: 80 subsets of n/4 matches drawn with std::random_shuffle, :126-137) -- all
+ * three live where `mem` says; every output is a host pointer.
+ *   sba_eight_point_null         per subset the null direction e [9] of its n x 9 epipolar system (the last row
+ *                                of vt in :69, sign arbitrary) and/or the packed upper triangle of A^T A [45].
+ *   sba_essential_to_candidates  :71-114 for one e: Euler angles of the two rotation candidates, unit translation,
+ *                                validity flags (host arithmetic only).  {R1, R2} does not depend on the sign of e or
+ *                                on SVD conventions; their order and the sign of T do (as with OpenCV).
+ *   sba_initial_guess            the whole of :117-181: candidates of every subset, then the vote.
+ * ------------------------------------------------------------------------------------------- */
+int sba_eight_point_null(sba_ctx* ctx, const double* b1, const double* b2, int n, const int32_t* idx, int n_samples, int sample_n,
+                         double* ata_out, double* e_out, int mem);
+int sba_essential_to_candidates(const double e[9], float R1_vec[3], float R2_vec[3], float T_vec[3], int* R1_valid, int* R2_valid);
+int sba_initial_guess(sba_ctx* ctx, const double* b1, const double* b2, int n, const int32_t* idx, int n_samples, int sample_n,
+                      float R_vec_out[3], float T_vec_out[3], int* n_candidates, int mem);
+
+/* ---------------------------------------------------------------------------------------------
  * Rotation-only bundle adjustment
  * (replaces ba_spherical_costfunctor_rot_only + ceres::Solve, spherical_bundle_adjuster.cpp:892-945,
  *  :183-217, :334-338)

@@ -67,6 +67,12 @@ def _load():
     lib.orc_crop_rotated_lut.argtypes = [C.c_float, C.c_int, C.c_int, i32p]
     lib.orc_crop_rotated_image.argtypes = [u8p, C.c_int, C.c_int, C.c_float, u8p]
     lib.orc_rotate_keypoints.argtypes = [C.c_float, f32p, C.c_int, C.c_int, C.c_int]
+    lib.orc_essential_to_candidates.argtypes = [f64p, f32p, f32p, f32p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.orc_eight_point_null.argtypes = [f64p, f64p, i32p, C.c_int, f64p, f64p]
+    lib.orc_vote_rotation.restype = C.c_int
+    lib.orc_vote_rotation.argtypes = [f32p, C.c_int]
+    lib.orc_initial_guess.restype = C.c_int
+    lib.orc_initial_guess.argtypes = [f64p, f64p, i32p, C.c_int, C.c_int, f32p, f32p, f32p, C.POINTER(C.c_int)]
     lib.orc_ls_next_step.restype = C.c_double
     lib.orc_ls_next_step.argtypes = [C.c_double] * 5 + [C.c_int] + [C.c_double] * 5
     return lib
@@ -254,6 +260,39 @@ def ls_next_step(f0, g0, cur, prev=None, min_step=None, max_step=None):
     lo = 1e-3 * xc if min_step is None else min_step
     hi = 0.6 * xc if max_step is None else max_step
     return lib().orc_ls_next_step(f0, g0, xp, fp, gp, int(prev is not None), xc, fc, gc, lo, hi)
+
+
+# ------------------------------------------------------------------ initial guess (8-point voting)
+def eight_point_null(b1, b2, idx=None):
+    """Null direction e [9] (sign arbitrary) and singular values [9] of the epipolar system of one subset."""
+    b1 = np.ascontiguousarray(b1, np.float64).reshape(-1, 3)
+    b2 = np.ascontiguousarray(b2, np.float64).reshape(-1, 3)
+    idx = None if idx is None else np.ascontiguousarray(idx, np.int32)
+    n = len(b1) if idx is None else len(idx)
+    e, sv = np.zeros(9), np.zeros(9)
+    lib().orc_eight_point_null(_p(b1, C.c_double), _p(b2, C.c_double), _p(idx, C.c_int32), n, _p(e, C.c_double), _p(sv, C.c_double))
+    return e, sv
+
+
+def essential_to_candidates(e):
+    """(R1_vec, R2_vec, T_vec float32 [3], R1_valid, R2_valid) of eight_point_estimation from the null direction."""
+    e = np.ascontiguousarray(e, np.float64).reshape(9)
+    R1, R2, T = np.zeros(3, np.float32), np.zeros(3, np.float32), np.zeros(3, np.float32)
+    v1, v2 = C.c_int(0), C.c_int(0)
+    lib().orc_essential_to_candidates(_p(e, C.c_double), _p(R1, C.c_float), _p(R2, C.c_float), _p(T, C.c_float), C.byref(v1), C.byref(v2))
+    return R1, R2, T, bool(v1.value), bool(v2.value)
+
+
+def initial_guess(b1, b2, idx):
+    """initial_guess with explicit subsets idx [n_samples, sample_n]: (R_vec [3] f32, T_vec [3] f32, winner, candidates [r, 3])."""
+    b1 = np.ascontiguousarray(b1, np.float64).reshape(-1, 3)
+    b2 = np.ascontiguousarray(b2, np.float64).reshape(-1, 3)
+    idx = np.ascontiguousarray(idx, np.int32)
+    ns, sn = idx.shape
+    R, T, cand, nc = np.zeros(3, np.float32), np.zeros(3, np.float32), np.zeros((2 * ns, 3), np.float32), C.c_int(0)
+    best = lib().orc_initial_guess(_p(b1, C.c_double), _p(b2, C.c_double), _p(idx, C.c_int32), ns, sn, _p(R, C.c_float), _p(T, C.c_float),
+                                   _p(cand, C.c_float), C.byref(nc))
+    return R, T, best, cand[:nc.value]
 
 
 # ------------------------------------------------------------------ spherical_surf geometry

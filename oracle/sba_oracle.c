@@ -1047,3 +1047,189 @@ void orc_rotate_keypoints(float pitch_inv_deg, float *xy, int n, int w, int h)
         xy[2 * k + 1] = (float)r;
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Initial guess.  spherical_bundle_adjuster.cpp:47-115 (eight_point_estimation),
+ * :117-181 (initial_guess: 80 random quarter-size subsets, two rotation candidates each, the one
+ * closest to the others wins), :24-45 (rot2euler), :14-22 (max_vec).
+ *
+ * Third-party pieces (OpenCV, restated; pinned against cv2.SVDecomp / cv2.decomposeEssentialMat of the
+ * installed OpenCV in tests/test_oracle.py up to the sign freedoms of an SVD):
+ *   - cv::SVDecomp: singular values in decreasing order, vt rows to match.  Here: one-sided Jacobi
+ *     (Hestenes) on the columns.  The reference only uses the LAST row of vt (the null direction, sign
+ *     arbitrary) of the n x 9 system, and U diag(w0, w1, 0) Vt of the 3 x 3 one (unique).
+ *   - cv::decomposeEssentialMat: SVD; U, Vt negated if their determinant is negative;
+ *     R1 = U W Vt, R2 = U W^T Vt with W = [0 1 0; -1 0 0; 0 0 1]; t = third column of U.
+ *     {R1, R2} is invariant under the SVD's sign freedoms, their ORDER and the sign of t are not.
+ * ---------------------------------------------------------------------------------------- */
+
+/* One-sided Jacobi SVD of A (m x n, n <= 9, row-major): V (n x n, columns = right singular vectors) and
+ * singular values, sorted in decreasing order.  A is overwritten by U*diag(w). */
+static void jacobi_svd(double *A, int m, int n, double *w, double *V)
+{
+    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) V[i * n + j] = (i == j);
+    for (int sweep = 0; sweep < 60; sweep++) {
+        double off = 0;
+        for (int p = 0; p < n - 1; p++)
+            for (int q = p + 1; q < n; q++) {
+                double a = 0, b = 0, c = 0;
+                for (int i = 0; i < m; i++) { double x = A[i * n + p], y = A[i * n + q]; a += x * x; b += y * y; c += x * y; }
+                if (fabs(c) <= 1e-300 || fabs(c) <= DBL_EPSILON * sqrt(a * b)) continue;
+                off = fmax(off, fabs(c) / sqrt(a * b));
+                double zeta = (b - a) / (2.0 * c);
+                double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+                for (int i = 0; i < m; i++) {
+                    double x = A[i * n + p], y = A[i * n + q];
+                    A[i * n + p] = cs * x - sn * y; A[i * n + q] = sn * x + cs * y;
+                }
+                for (int i = 0; i < n; i++) {
+                    double x = V[i * n + p], y = V[i * n + q];
+                    V[i * n + p] = cs * x - sn * y; V[i * n + q] = sn * x + cs * y;
+                }
+            }
+        if (off < 1e-15) break;
+    }
+    for (int j = 0; j < n; j++) { double s = 0; for (int i = 0; i < m; i++) s += A[i * n + j] * A[i * n + j]; w[j] = sqrt(s); }
+    for (int j = 0; j < n - 1; j++) {       /* selection sort, decreasing */
+        int best = j;
+        for (int k = j + 1; k < n; k++) if (w[k] > w[best]) best = k;
+        if (best != j) {
+            double tw = w[j]; w[j] = w[best]; w[best] = tw;
+            for (int i = 0; i < m; i++) { double tmp = A[i * n + j]; A[i * n + j] = A[i * n + best]; A[i * n + best] = tmp; }
+            for (int i = 0; i < n; i++) { double tmp = V[i * n + j]; V[i * n + j] = V[i * n + best]; V[i * n + best] = tmp; }
+        }
+    }
+}
+
+static double det3(const double *M)
+{
+    return M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
+}
+
+static void mul3(const double *A, const double *B, double *C)
+{
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { double s = 0; for (int k = 0; k < 3; k++) s += A[3 * i + k] * B[3 * k + j]; C[3 * i + j] = s; }
+}
+
+/* full 3x3 SVD M = U diag(w) Vt from the one-sided Jacobi (U completed by a cross product when w2 ~ 0) */
+static void svd3(const double *M, double *U, double *w, double *Vt)
+{
+    double A[9], V[9];
+    memcpy(A, M, sizeof(A));
+    jacobi_svd(A, 3, 3, w, V);
+    for (int j = 0; j < 3; j++)
+        for (int i = 0; i < 3; i++) U[3 * i + j] = (w[j] > 1e-12 * w[0]) ? A[3 * i + j] / w[j] : 0.0;
+    if (!(w[2] > 1e-12 * w[0])) {     /* rank 2: third left vector = u0 x u1 */
+        U[2] = U[3] * U[7] - U[6] * U[4];
+        U[5] = U[6] * U[1] - U[0] * U[7];
+        U[8] = U[0] * U[4] - U[3] * U[1];
+    }
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Vt[3 * i + j] = V[3 * j + i];
+}
+
+/* spherical_bundle_adjuster.cpp:24-45 */
+static void rot2euler(const double *R, float out[3])
+{
+    float sy = (float)sqrt(R[0] * R[0] + R[3] * R[3]);
+    if (!(sy < 1e-6)) {
+        out[0] = (float)atan2(R[7], R[8]); out[1] = (float)atan2(-R[6], sy); out[2] = (float)atan2(R[3], R[0]);
+    } else {
+        out[0] = (float)atan2(-R[5], R[4]); out[1] = (float)atan2(-R[6], sy); out[2] = 0.f;
+    }
+}
+
+/* spherical_bundle_adjuster.cpp:14-22 applied to the absolute values (:101-104) */
+static double max_vec_abs(const float v[3])
+{
+    float a = fabsf(v[0]), b = fabsf(v[1]), c = fabsf(v[2]);
+    if (a > b && a > c) return a;
+    else if (b > c) return b;
+    return c;
+}
+
+/* From the null direction e (9 numbers, any sign) to the outputs of eight_point_estimation (:71-114). */
+void orc_essential_to_candidates(const double e[9], float R1_vec[3], float R2_vec[3], float T_vec[3], int *R1_valid, int *R2_valid)
+{
+    double U[9], w[3], Vt[9], D[9] = {0}, T[9], Ec[9];
+    svd3(e, U, w, Vt);
+    D[0] = w[0]; D[4] = w[1]; D[8] = 0.0;                     /* w_f.at<double>(0, 2) = 0 (:74) */
+    mul3(U, D, T); mul3(T, Vt, Ec);
+    svd3(Ec, U, w, Vt);                                        /* decomposeEssentialMat (:80) */
+    if (det3(U) < 0) for (int k = 0; k < 9; k++) U[k] = -U[k];
+    if (det3(Vt) < 0) for (int k = 0; k < 9; k++) Vt[k] = -Vt[k];
+    const double W[9] = {0, 1, 0, -1, 0, 0, 0, 0, 1}, Wt[9] = {0, -1, 0, 1, 0, 0, 0, 0, 1};
+    double R1[9], R2[9];
+    mul3(U, W, T); mul3(T, Vt, R1);
+    mul3(U, Wt, T); mul3(T, Vt, R2);
+    rot2euler(R1, R1_vec);
+    rot2euler(R2, R2_vec);
+    T_vec[0] = (float)U[2]; T_vec[1] = (float)U[5]; T_vec[2] = (float)U[8];
+    *R1_valid = max_vec_abs(R1_vec) < 1.57;
+    *R2_valid = max_vec_abs(R2_vec) < 1.57;
+}
+
+/* Null direction of the n x 9 epipolar system of one subset (:53-69): rows kron(left_i, right_i). */
+void orc_eight_point_null(const double *b1, const double *b2, const int32_t *idx, int n, double e[9], double sv[9])
+{
+    double *A = (double *)malloc(sizeof(double) * 9 * (size_t)n), w[9], V[81];
+    for (int i = 0; i < n; i++) {
+        const double *l = b1 + 3 * (size_t)(idx ? idx[i] : i), *r = b2 + 3 * (size_t)(idx ? idx[i] : i);
+        for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) A[9 * (size_t)i + 3 * a + b] = l[a] * r[b];
+    }
+    jacobi_svd(A, n, 9, w, V);
+    for (int k = 0; k < 9; k++) e[k] = V[k * 9 + 8];
+    if (sv) memcpy(sv, w, sizeof(w));
+    free(A);
+}
+
+static int cmp_double(const void *a, const void *b) { double x = *(const double *)a, y = *(const double *)b; return (x > y) - (x < y); }
+
+/* The vote of initial_guess (:160-180) over the collected candidates.  Returns the winning index. */
+int orc_vote_rotation(const float *R_arr, int r)
+{
+    double *dist = (double *)malloc(sizeof(double) * r), *dn = (double *)malloc(sizeof(double) * r);
+    for (int i = 0; i < r; i++) {
+        for (int j = 0; j < r; j++) {
+            float d0 = R_arr[3 * i] - R_arr[3 * j], d1 = R_arr[3 * i + 1] - R_arr[3 * j + 1], d2 = R_arr[3 * i + 2] - R_arr[3 * j + 2];
+            dn[j] = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);      /* float arithmetic on Vec3f elements */
+        }
+        qsort(dn, r, sizeof(double), cmp_double);
+        int lo = (int)(r * 0.2), hi = (int)(r * 0.8);
+        double s = 0;
+        for (int k = lo; k < hi; k++) s += dn[k];
+        dist[i] = s / ((hi - lo) * 1.0);
+    }
+    int best = 0;
+    for (int i = 1; i < r; i++) if (dist[i] < dist[best]) best = i;
+    free(dist); free(dn);
+    return best;
+}
+
+/* initial_guess with the subsets given explicitly: idx [n_samples x sample_n] (the reference draws them with
+ * std::random_shuffle, :126-137).  cand_R (optional, capacity 2*n_samples x 3) receives the candidate list. */
+int orc_initial_guess(const double *b1, const double *b2, const int32_t *idx, int n_samples, int sample_n, float R_out[3], float T_out[3],
+                      float *cand_R, int *n_cand)
+{
+    float *Ra = (float *)malloc(sizeof(float) * 6 * n_samples), *Ta = (float *)malloc(sizeof(float) * 6 * n_samples);
+    int r = 0;
+    for (int s = 0; s < n_samples; s++) {
+        double e[9];
+        float R1[3], R2[3], T[3];
+        int v1, v2;
+        orc_eight_point_null(b1, b2, idx + (size_t)s * sample_n, sample_n, e, NULL);
+        orc_essential_to_candidates(e, R1, R2, T, &v1, &v2);
+        if (v1) { memcpy(Ra + 3 * r, R1, 12); memcpy(Ta + 3 * r, T, 12); r++; }
+        if (v2) { memcpy(Ra + 3 * r, R2, 12); memcpy(Ta + 3 * r, T, 12); r++; }
+    }
+    if (n_cand) *n_cand = r;
+    if (cand_R) memcpy(cand_R, Ra, sizeof(float) * 3 * r);
+    int best = -1;
+    if (r > 0) {
+        best = orc_vote_rotation(Ra, r);
+        memcpy(R_out, Ra + 3 * best, 12);
+        memcpy(T_out, Ta + 3 * best, 12);
+    }
+    free(Ra); free(Ta);
+    return best;
+}

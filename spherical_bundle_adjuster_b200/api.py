@@ -152,6 +152,34 @@ class Context:
         check(self._lib.sba_equi2cube_lut(self._h, w, h, cube_size, _ptr(lut), SBA_MEM_HOST))
         return lut
 
+    # -- spherical_bundle_adjuster.cpp:47-181 (eight_point_estimation, initial_guess)
+    def eight_point_null(self, b1, b2, idx):
+        """Per subset (rows of idx [n_samples, sample_n]): null direction e [n_samples, 9] and packed A^T A [n_samples, 45]."""
+        b1 = np.ascontiguousarray(b1, np.float64).reshape(-1, 3)
+        b2 = np.ascontiguousarray(b2, np.float64).reshape(-1, 3)
+        idx = np.ascontiguousarray(idx, np.int32)
+        ns, sn = idx.shape
+        e, ata = np.empty((ns, 9)), np.empty((ns, 45))
+        check(self._lib.sba_eight_point_null(self._h, _ptr(b1), _ptr(b2), len(b1), _ptr(idx), ns, sn, _ptr(ata), _ptr(e), SBA_MEM_HOST))
+        return e, ata
+
+    def essential_to_candidates(self, e):
+        e = np.ascontiguousarray(e, np.float64).reshape(9)
+        R1, R2, T = np.empty(3, np.float32), np.empty(3, np.float32), np.empty(3, np.float32)
+        v1, v2 = C.c_int32(0), C.c_int32(0)
+        check(self._lib.sba_essential_to_candidates(_ptr(e), _ptr(R1), _ptr(R2), _ptr(T), C.byref(v1), C.byref(v2)))
+        return R1, R2, T, bool(v1.value), bool(v2.value)
+
+    def initial_guess(self, b1, b2, idx):
+        """``spherical_bundle_adjuster::initial_guess`` with explicit subsets: (R_vec [3] f32, T_vec [3] f32, n_candidates)."""
+        b1 = np.ascontiguousarray(b1, np.float64).reshape(-1, 3)
+        b2 = np.ascontiguousarray(b2, np.float64).reshape(-1, 3)
+        idx = np.ascontiguousarray(idx, np.int32)
+        ns, sn = idx.shape
+        R, T, nc = np.empty(3, np.float32), np.empty(3, np.float32), C.c_int32(0)
+        check(self._lib.sba_initial_guess(self._h, _ptr(b1), _ptr(b2), len(b1), _ptr(idx), ns, sn, _ptr(R), _ptr(T), C.byref(nc), SBA_MEM_HOST))
+        return R, T, int(nc.value)
+
     # -- spherical_surf.hpp:16-20 (eular2rot, rotate_pixel, crop_rotated_image, rotate_keypoint)
     def eular2rot(self, theta) -> np.ndarray:
         th = np.ascontiguousarray(theta, np.float32).reshape(3)

@@ -1,0 +1,325 @@
+// initial.cu -- the bundle adjuster's initial guess.
+//
+// Replaces spherical_bundle_adjuster.cpp:47-115 (eight_point_estimation) and :117-181 (initial_guess):
+// 80 random quarter-size subsets of the matches, for each the null direction of the n x 9 epipolar system
+// (rows kron(left_i, right_i)), the two rotation candidates of the corrected essential matrix, and a vote
+// for the candidate closest to the others.
+//
+// What is data parallel is the n x 9 system: the reference runs a Jacobi SVD on every one of the 80 tall
+// matrices.  Only the right singular vector of the smallest singular value is used, and that is the
+// eigenvector of the smallest eigenvalue of A^T A -- 45 sums over the subset.  So the device does ONE pass
+// over all subsets (`eight_point_ata_kernel`: a CTA per (subset, row chunk), 45 fp64 accumulators per thread,
+// fixed-order reduction; `eight_point_fold_kernel` adds the chunks in order), and the eighty 9 x 9 symmetric
+// eigenproblems plus the 3 x 3 algebra of decomposeEssentialMat (a few hundred flops each) finish on the host
+// side of the ABI.  Squaring the condition number costs nothing here: sigma_min/sigma_max is ~1e-1..1e-3, the
+// null direction agrees with a direct SVD to ~1e-12 (tested against the oracle's one-sided Jacobi).
+//
+// The subsets are an INPUT (index table): the reference draws them with std::random_shuffle, which the C++
+// facade reproduces with the same libstdc++ call, while tests pass seeded tables.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace sba {
+
+constexpr int ATA_THREADS = 256;
+constexpr int ATA_ROWS_PER_CTA = 4096;
+constexpr int ATA_N = 45;   // upper triangle of the symmetric 9 x 9, row by row
+
+__global__ void __launch_bounds__(ATA_THREADS)
+eight_point_ata_kernel(const double* __restrict__ b1, const double* __restrict__ b2, const int32_t* __restrict__ idx, int sample_n, int n_chunks,
+                       double* __restrict__ partial /* [n_samples][n_chunks][45] */)
+{
+    const int sample = blockIdx.x / n_chunks, chunk = blockIdx.x - sample * n_chunks;
+    const int32_t* rows = idx + (size_t)sample * sample_n;
+    const int r0 = chunk * ATA_ROWS_PER_CTA, r1 = min(sample_n, r0 + ATA_ROWS_PER_CTA);
+    double acc[ATA_N];
+#pragma unroll
+    for (int k = 0; k < ATA_N; k++) acc[k] = 0.0;
+    for (int i = r0 + threadIdx.x; i < r1; i += ATA_THREADS) {
+        const int32_t m = __ldg(rows + i);
+        const double* l = b1 + 3 * (size_t)m;
+        const double* r = b2 + 3 * (size_t)m;
+        const double lx = l[0], ly = l[1], lz = l[2], rx = r[0], ry = r[1], rz = r[2];
+        const double a[9] = {lx * rx, lx * ry, lx * rz, ly * rx, ly * ry, ly * rz, lz * rx, lz * ry, lz * rz};   // :59-67
+        int k = 0;
+#pragma unroll
+        for (int p = 0; p < 9; p++)
+#pragma unroll
+            for (int q = p; q < 9; q++) acc[k++] += a[p] * a[q];
+    }
+    __shared__ double s_red[ATA_THREADS / 32][ATA_N];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < ATA_N; k++) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_red[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < ATA_N) {
+        double v = s_red[0][threadIdx.x];
+        for (int w = 1; w < ATA_THREADS / 32; w++) v += s_red[w][threadIdx.x];
+        partial[(size_t)blockIdx.x * ATA_N + threadIdx.x] = v;
+    }
+}
+
+__global__ void eight_point_fold_kernel(const double* __restrict__ partial, int n_samples, int n_chunks, double* __restrict__ ata)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_samples * ATA_N) return;
+    const int sample = g / ATA_N, k = g - sample * ATA_N;
+    double v = 0.0;
+    for (int c = 0; c < n_chunks; c++) v += partial[((size_t)sample * n_chunks + c) * ATA_N + k];   // chunk order: deterministic
+    ata[g] = v;
+}
+
+// ---- host algebra ---------------------------------------------------------------------------------------
+
+// Cyclic Jacobi on a symmetric n x n matrix (n <= 9): eigenvalues on the diagonal of S, eigenvectors in the columns of V.
+static void jacobi_eigen(double* S, int n, double* V)
+{
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) V[i * n + j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 64; sweep++) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < n; i++) {
+            diag += S[i * n + i] * S[i * n + i];
+            for (int j = i + 1; j < n; j++) off += S[i * n + j] * S[i * n + j];
+        }
+        if (off <= 1e-32 * diag) break;
+        for (int p = 0; p < n - 1; p++)
+            for (int q = p + 1; q < n; q++) {
+                const double apq = S[p * n + q];
+                if (apq == 0.0) continue;
+                const double theta = (S[q * n + q] - S[p * n + p]) / (2.0 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < n; k++) {   // S <- S J
+                    const double skp = S[k * n + p], skq = S[k * n + q];
+                    S[k * n + p] = c * skp - s * skq;
+                    S[k * n + q] = s * skp + c * skq;
+                }
+                for (int k = 0; k < n; k++) {   // S <- J^T S
+                    const double spk = S[p * n + k], sqk = S[q * n + k];
+                    S[p * n + k] = c * spk - s * sqk;
+                    S[q * n + k] = s * spk + c * sqk;
+                }
+                for (int k = 0; k < n; k++) {
+                    const double vkp = V[k * n + p], vkq = V[k * n + q];
+                    V[k * n + p] = c * vkp - s * vkq;
+                    V[k * n + q] = s * vkp + c * vkq;
+                }
+            }
+    }
+}
+
+// eigenvector of the smallest eigenvalue of the packed upper triangle (45 numbers)
+static void null_direction(const double* packed, double e[9])
+{
+    double S[81], V[81];
+    int k = 0;
+    for (int p = 0; p < 9; p++)
+        for (int q = p; q < 9; q++) { S[p * 9 + q] = packed[k]; S[q * 9 + p] = packed[k]; k++; }
+    jacobi_eigen(S, 9, V);
+    int best = 0;
+    for (int j = 1; j < 9; j++)
+        if (S[j * 9 + j] < S[best * 9 + best]) best = j;
+    for (int i = 0; i < 9; i++) e[i] = V[i * 9 + best];
+}
+
+static void mat3_mul(const double* A, const double* B, double* C)
+{
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+
+static double mat3_det(const double* M)
+{
+    return M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
+}
+
+// M = U diag(w) Vt with w decreasing, through the eigen-decomposition of M^T M; u_0, u_1 = M v_j / w_j, u_2 = +-(u_0 x u_1).
+static void svd_3x3(const double* M, double* U, double* w, double* Vt)
+{
+    double S[9], V[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) S[3 * i + j] = M[i] * M[j] + M[3 + i] * M[3 + j] + M[6 + i] * M[6 + j];
+    jacobi_eigen(S, 3, V);
+    int order[3] = {0, 1, 2};
+    std::sort(order, order + 3, [&](int a, int b) { return S[4 * a] > S[4 * b]; });
+    for (int j = 0; j < 3; j++) {
+        const int c = order[j];
+        w[j] = std::sqrt(std::max(S[4 * c], 0.0));
+        for (int i = 0; i < 3; i++) Vt[3 * j + i] = V[3 * i + c];
+    }
+    for (int j = 0; j < 2; j++) {
+        const double* v = Vt + 3 * j;
+        for (int i = 0; i < 3; i++) U[3 * i + j] = (w[j] > 0.0) ? (M[3 * i] * v[0] + M[3 * i + 1] * v[1] + M[3 * i + 2] * v[2]) / w[j] : 0.0;
+    }
+    // Third left vector: u_0 x u_1, oriented like M v_2 when the third singular value is significant.  (w_2 comes out of
+    // an eigenvalue of M^T M, so anything below ~sqrt(eps) w_0 is rounding noise and M v_2 / w_2 would be garbage --
+    // the essential matrix is handed back here with w_2 forced to exactly zero.)
+    U[2] = U[3] * U[7] - U[6] * U[4];
+    U[5] = U[6] * U[1] - U[0] * U[7];
+    U[8] = U[0] * U[4] - U[3] * U[1];
+    if (w[2] > 1e-6 * w[0]) {
+        const double* v = Vt + 6;
+        double dot = 0.0;
+        for (int i = 0; i < 3; i++) dot += U[3 * i + 2] * (M[3 * i] * v[0] + M[3 * i + 1] * v[1] + M[3 * i + 2] * v[2]);
+        if (dot < 0.0) for (int i = 0; i < 3; i++) U[3 * i + 2] = -U[3 * i + 2];
+    }
+}
+
+// rot2euler, spherical_bundle_adjuster.cpp:24-45 (float results)
+static void rot_to_euler(const double* R, float out[3])
+{
+    const float sy = (float)std::sqrt(R[0] * R[0] + R[3] * R[3]);
+    if (!(sy < 1e-6)) {
+        out[0] = (float)std::atan2(R[7], R[8]);
+        out[1] = (float)std::atan2(-R[6], (double)sy);
+        out[2] = (float)std::atan2(R[3], R[0]);
+    } else {
+        out[0] = (float)std::atan2(-R[5], R[4]);
+        out[1] = (float)std::atan2(-R[6], (double)sy);
+        out[2] = 0.f;
+    }
+}
+
+// max_vec of the absolute values, with the reference's branch order (:14-22, :101-104)
+static double max_abs_component(const float v[3])
+{
+    const float a = std::fabs(v[0]), b = std::fabs(v[1]), c = std::fabs(v[2]);
+    if (a > b && a > c) return a;
+    if (b > c) return b;
+    return c;
+}
+
+static void essential_to_candidates(const double e[9], float R1_vec[3], float R2_vec[3], float T_vec[3], bool* v1, bool* v2)
+{
+    double U[9], w[3], Vt[9], T[9], Ec[9];
+    svd_3x3(e, U, w, Vt);
+    const double D[9] = {w[0], 0, 0, 0, w[1], 0, 0, 0, 0};      // third singular value forced to zero (:74-77)
+    mat3_mul(U, D, T);
+    mat3_mul(T, Vt, Ec);
+    svd_3x3(Ec, U, w, Vt);                                        // cv::decomposeEssentialMat (:81)
+    if (mat3_det(U) < 0) for (double& x : U) x = -x;
+    if (mat3_det(Vt) < 0) for (double& x : Vt) x = -x;
+    const double W[9] = {0, 1, 0, -1, 0, 0, 0, 0, 1}, Wt[9] = {0, -1, 0, 1, 0, 0, 0, 0, 1};
+    double R1[9], R2[9];
+    mat3_mul(U, W, T); mat3_mul(T, Vt, R1);
+    mat3_mul(U, Wt, T); mat3_mul(T, Vt, R2);
+    rot_to_euler(R1, R1_vec);
+    rot_to_euler(R2, R2_vec);
+    T_vec[0] = (float)U[2]; T_vec[1] = (float)U[5]; T_vec[2] = (float)U[8];
+    *v1 = max_abs_component(R1_vec) < 1.57;
+    *v2 = max_abs_component(R2_vec) < 1.57;
+}
+
+// the vote of initial_guess (:160-180): mean of the middle 60 % of the distances to all candidates, smallest wins
+static int vote(const std::vector<float>& R)
+{
+    const int r = (int)(R.size() / 3);
+    std::vector<double> dist(r), dn(r);
+    for (int i = 0; i < r; i++) {
+        for (int j = 0; j < r; j++) {
+            const float d0 = R[3 * i] - R[3 * j], d1 = R[3 * i + 1] - R[3 * j + 1], d2 = R[3 * i + 2] - R[3 * j + 2];
+            dn[j] = std::sqrt(d0 * d0 + d1 * d1 + d2 * d2);   // float arithmetic, like the Vec3f expression (:167-169)
+        }
+        std::sort(dn.begin(), dn.end());
+        const int lo = (int)(r * 0.2), hi = (int)(r * 0.8);
+        double s = 0.0;
+        for (int k = lo; k < hi; k++) s += dn[k];
+        dist[i] = s / ((hi - lo) * 1.0);
+    }
+    return (int)(std::min_element(dist.begin(), dist.end()) - dist.begin());
+}
+
+// A^T A of every subset on the device -> host.  ata: [n_samples x 45].
+static int ata_of_subsets(sba_ctx* c, const double* b1, const double* b2, int n, const int32_t* idx, int n_samples, int sample_n, int mem,
+                          std::vector<double>& ata)
+{
+    cudaStream_t st = c->stream;
+    const double *d_b1, *d_b2;
+    const int32_t* d_idx;
+    SBA_TRY(stage_in(c, b1, (size_t)3 * n, mem, SCR_IN0, &d_b1));
+    SBA_TRY(stage_in(c, b2, (size_t)3 * n, mem, SCR_IN1, &d_b2));
+    SBA_TRY(stage_in(c, idx, (size_t)n_samples * sample_n, mem, SCR_IN2, &d_idx));
+    const int n_chunks = (sample_n + ATA_ROWS_PER_CTA - 1) / ATA_ROWS_PER_CTA;
+    SBA_TRY(c->scratch[SCR_WORK0].ensure((size_t)n_samples * n_chunks * ATA_N * sizeof(double), st));
+    SBA_TRY(c->scratch[SCR_WORK1].ensure((size_t)n_samples * ATA_N * sizeof(double), st));
+    double* d_partial = c->scratch[SCR_WORK0].as<double>();
+    double* d_ata = c->scratch[SCR_WORK1].as<double>();
+    eight_point_ata_kernel<<<n_samples * n_chunks, ATA_THREADS, 0, st>>>(d_b1, d_b2, d_idx, sample_n, n_chunks, d_partial);
+    SBA_LAUNCHED(c);
+    eight_point_fold_kernel<<<(n_samples * ATA_N + 255) / 256, 256, 0, st>>>(d_partial, n_samples, n_chunks, d_ata);
+    SBA_LAUNCHED(c);
+    SBA_CUDA(cudaGetLastError());
+    ata.resize((size_t)n_samples * ATA_N);
+    SBA_CUDA(cudaMemcpyAsync(ata.data(), d_ata, ata.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SBA_CUDA(cudaStreamSynchronize(st));
+    return SBA_OK;
+}
+
+}  // namespace sba
+
+using namespace sba;
+
+extern "C" {
+
+int sba_eight_point_null(sba_ctx* c, const double* b1, const double* b2, int n, const int32_t* idx, int n_samples, int sample_n, double* ata_out,
+                         double* e_out, int mem)
+{
+    SBA_CHECK_ARG(c && b1 && b2 && idx && n > 0 && n_samples > 0 && sample_n > 0 && (ata_out || e_out));
+    SBA_CUDA(cudaSetDevice(c->device));
+    std::vector<double> ata;
+    SBA_TRY(ata_of_subsets(c, b1, b2, n, idx, n_samples, sample_n, mem, ata));
+    if (ata_out) std::memcpy(ata_out, ata.data(), ata.size() * sizeof(double));
+    if (e_out)
+        for (int s = 0; s < n_samples; s++) null_direction(ata.data() + (size_t)s * ATA_N, e_out + 9 * (size_t)s);
+    return SBA_OK;
+}
+
+int sba_essential_to_candidates(const double e[9], float R1_vec[3], float R2_vec[3], float T_vec[3], int* R1_valid, int* R2_valid)
+{
+    SBA_CHECK_ARG(e && R1_vec && R2_vec && T_vec && R1_valid && R2_valid);
+    bool v1, v2;
+    essential_to_candidates(e, R1_vec, R2_vec, T_vec, &v1, &v2);
+    *R1_valid = v1;
+    *R2_valid = v2;
+    return SBA_OK;
+}
+
+int sba_initial_guess(sba_ctx* c, const double* b1, const double* b2, int n, const int32_t* idx, int n_samples, int sample_n, float R_vec_out[3],
+                      float T_vec_out[3], int* n_candidates, int mem)
+{
+    SBA_CHECK_ARG(c && b1 && b2 && idx && n > 0 && n_samples > 0 && sample_n > 0 && R_vec_out && T_vec_out);
+    SBA_CUDA(cudaSetDevice(c->device));
+    std::vector<double> ata;
+    SBA_TRY(ata_of_subsets(c, b1, b2, n, idx, n_samples, sample_n, mem, ata));
+    std::vector<float> R_arr, T_arr;
+    for (int s = 0; s < n_samples; s++) {
+        double e[9];
+        float R1[3], R2[3], T[3];
+        bool v1, v2;
+        null_direction(ata.data() + (size_t)s * ATA_N, e);
+        essential_to_candidates(e, R1, R2, T, &v1, &v2);
+        if (v1) { R_arr.insert(R_arr.end(), R1, R1 + 3); T_arr.insert(T_arr.end(), T, T + 3); }     // :148-157
+        if (v2) { R_arr.insert(R_arr.end(), R2, R2 + 3); T_arr.insert(T_arr.end(), T, T + 3); }
+    }
+    if (n_candidates) *n_candidates = (int)(R_arr.size() / 3);
+    if (R_arr.empty()) {
+        sba::set_error("initial guess: no subset produced a rotation candidate below 1.57 rad");
+        return SBA_ERR_INVALID;
+    }
+    const int best = vote(R_arr);
+    for (int k = 0; k < 3; k++) { R_vec_out[k] = R_arr[3 * best + k]; T_vec_out[k] = T_arr[3 * best + k]; }
+    return SBA_OK;
+}
+
+}  // extern "C"

@@ -105,6 +105,11 @@ int main(int argc, char** argv)
             double r0[3] = {init[0], init[1], init[2]}, t0[3] = {init[3], init[4], init[5]};
             std::vector<std::array<double, 2>> init_d(n);
             for (auto& d : init_d) d[0] = d[1] = init[6];
+            cv::Vec3f Rg, Tg;
+            std::srand(1);                                    // the reference never seeds: std::rand starts from 1
+            sba.initial_guess(w, h, L, R, Rg, Tg, n);
+            float ig[6] = {Rg[0], Rg[1], Rg[2], Tg[0], Tg[1], Tg[2]};
+            dump(dir + "/ig_out.bin", ig, 6);
             sba_solver_options opt;
             sba.solve_problem(opt, L, R, r0, t0, init_d, n);
             std::vector<double> o = {r0[0], r0[1], r0[2], t0[0], t0[1], t0[2], (double)sba.stage_summaries[0].iterations,

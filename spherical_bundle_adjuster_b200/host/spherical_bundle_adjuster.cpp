@@ -5,6 +5,7 @@
 #include "sba_host_ctx.hpp"
 
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 
 namespace {
@@ -122,13 +123,52 @@ sba_solve_summary spherical_bundle_adjuster::adjust_rotation(const std::vector<c
     return sum;
 }
 
+static void flatten(const std::vector<cv::Point3d>& pts, int n, std::vector<double>& out)
+{
+    out.resize(3 * (size_t)n);
+    for (int i = 0; i < n; i++) { out[3 * i] = pts[i].x; out[3 * i + 1] = pts[i].y; out[3 * i + 2] = pts[i].z; }
+}
+
+void spherical_bundle_adjuster::eight_point_estimation(int, int, std::vector<cv::Point3d>& left, std::vector<cv::Point3d>& right, cv::Vec3f& R1_vec,
+                                                       cv::Vec3f& R2_vec, cv::Vec3f& T_vec, bool& R1_valid, bool& R2_valid, int match_size)
+{
+    std::vector<double> b1, b2;
+    flatten(left, match_size, b1);
+    flatten(right, match_size, b2);
+    std::vector<int32_t> idx(match_size);
+    std::iota(idx.begin(), idx.end(), 0);
+    double e[9];
+    sba_host::check(sba_eight_point_null(sba_host::ctx(), b1.data(), b2.data(), match_size, idx.data(), 1, match_size, nullptr, e, SBA_MEM_HOST));
+    int v1 = 0, v2 = 0;
+    sba_host::check(sba_essential_to_candidates(e, R1_vec.val, R2_vec.val, T_vec.val, &v1, &v2));
+    R1_valid = v1 != 0;
+    R2_valid = v2 != 0;
+}
+
+void spherical_bundle_adjuster::initial_guess(int, int, std::vector<cv::Point3d>& left, std::vector<cv::Point3d>& right, cv::Vec3f& R_vec_out,
+                                              cv::Vec3f& T_vec_out, int match_size)
+{
+    // :124-137: 80 times a fresh shuffle, the first quarter of it is the subset
+    const int n_samples = 80, sample_n = (int)(match_size * 0.25);
+    std::vector<int32_t> idx((size_t)n_samples * sample_n);
+    for (int s = 0; s < n_samples; s++) {
+        random_array rand_arr(match_size);
+        for (int i = 0; i < sample_n; i++) idx[(size_t)s * sample_n + i] = rand_arr.get_rand();
+    }
+    std::vector<double> b1, b2;
+    flatten(left, match_size, b1);
+    flatten(right, match_size, b2);
+    sba_host::check(sba_initial_guess(sba_host::ctx(), b1.data(), b2.data(), match_size, idx.data(), n_samples, sample_n, R_vec_out.val,
+                                      T_vec_out.val, nullptr, SBA_MEM_HOST));
+}
+
 void spherical_bundle_adjuster::adjust(const std::vector<cv::KeyPoint>& left_key, const std::vector<cv::KeyPoint>& right_key, int im_width,
-                                       int im_height, const double init_rot[3], const double init_tran[3])
+                                       int im_height, const double* init_rot, const double* init_tran)
 {
     const int n = (int)left_key.size();
-    for (int k = 0; k < 3; k++) { result_rot[k] = init_rot[k]; result_tran[k] = init_tran[k]; }
+    for (int k = 0; k < 3; k++) { result_rot[k] = init_rot ? init_rot[k] : 0.0; result_tran[k] = init_tran ? init_tran[k] : 0.0; }
     result_d.assign(n, std::array<double, 2>{{expected_d, expected_d}});   // :325-326
-    if (n < 2) return;
+    if (n < 8) return;
     // pixel -> radian -> unit vector in double (:268-298), both sides in one batch
     std::vector<float> px(4 * (size_t)n);
     std::vector<double> b(6 * (size_t)n);
@@ -141,6 +181,11 @@ void spherical_bundle_adjuster::adjust(const std::vector<cv::KeyPoint>& left_key
     for (int i = 0; i < n; i++) {
         L[i] = cv::Point3d(b[3 * i], b[3 * i + 1], b[3 * i + 2]);
         R[i] = cv::Point3d(b[3 * (n + i)], b[3 * (n + i) + 1], b[3 * (n + i) + 2]);
+    }
+    if (!init_rot || !init_tran) {
+        cv::Vec3f R_vec_out, T_vec_out;                                     // :302-306
+        initial_guess(im_width, im_height, L, R, R_vec_out, T_vec_out, n);
+        for (int k = 0; k < 3; k++) { result_rot[k] = -R_vec_out[k]; result_tran[k] = T_vec_out[k]; }   // :330-331
     }
     sba_solver_options options;              // :333-338
     options.max_num_iterations = 50;
@@ -157,7 +202,5 @@ void spherical_bundle_adjuster::do_bundle_adjustment(const cv::Mat& im_left, con
     spherical_surf fm;                       // :263-266
     fm.set_omp(num_proc);
     fm.do_all(im_left, im_right, left_key, right_key, match_size, match_output, total_key_num);
-    const double init_rot[3] = {expected_roll / 180 * M_PI, expected_pitch / 180 * M_PI, expected_yaw / 180 * M_PI};   // :328
-    const double init_tran[3] = {expected_tx, expected_ty, expected_tz};                                                // :329
-    adjust(left_key, right_key, im_left.cols, im_left.rows, init_rot, init_tran);
+    adjust(left_key, right_key, im_left.cols, im_left.rows);
 }

@@ -6,7 +6,9 @@
 // `add_residual(problem, ...)` followed by `ceres::Solve(opt, &problem, &summary)` did
 // (spherical_bundle_adjuster.cpp:202-203), on the GPU.
 #pragma once
+#include <algorithm>
 #include <array>
+#include <numeric>
 #include <vector>
 
 #include "equi2cube_surf.hpp"
@@ -71,16 +73,27 @@ class spherical_bundle_adjuster
     ~spherical_bundle_adjuster() {}
 
     void set_omp(int num_proc);
-    // spherical_surf front-end (:252-266) -> bearings (:268-298) -> solve_problem (:333-345), as the reference.
-    // The reference seeds the solve with initial_guess (its 8-point voting, :47-181 -- host code, not built
-    // here); this facade starts from the expected_* values the object was constructed with, which is the
-    // reference's own commented-out alternative (:328-329).  Needs SURF (real OpenCV) for the front-end.
+    // spherical_surf front-end (:252-266) -> bearings (:268-298) -> initial_guess (:302-306) -> solve_problem
+    // (:333-345), the reference's call chain.  Needs SURF (real OpenCV) for the front-end.
     void do_bundle_adjustment(const cv::Mat &im_left, const cv::Mat &im_right);
 
-    // Everything of do_bundle_adjustment after the front-end: matched ERP keypoints -> bearings -> three-stage
-    // solve from (init_rot, init_tran, expected_d).  Results in result_rot / result_tran / result_d.
+    // Everything of do_bundle_adjustment after the front-end: matched ERP keypoints -> bearings -> initial guess
+    // -> three-stage solve.  init_rot/init_tran: NULL = run initial_guess like the reference (negated Euler angles
+    // fed as the angle-axis start, :330-331); otherwise start from the given values.
+    // Results in result_rot / result_tran / result_d.
     void adjust(const std::vector<cv::KeyPoint>& left_key, const std::vector<cv::KeyPoint>& right_key, int im_width, int im_height,
-                const double init_rot[3], const double init_tran[3]);
+                const double* init_rot = nullptr, const double* init_tran = nullptr);
+
+    // private in the reference (spherical_bundle_adjuster.hpp:26-38)
+    void eight_point_estimation(int im_width, int im_height
+                                , std::vector<cv::Point3d>& key_point_left_rect, std::vector<cv::Point3d>& key_point_right_rect
+                                , cv::Vec3f& R1_vec, cv::Vec3f& R2_vec, cv::Vec3f& T_vec
+                                , bool& R1_valid, bool& R2_valid
+                                , int match_size);
+    void initial_guess(int im_width, int im_height
+                        , std::vector<cv::Point3d>& key_point_left_rect, std::vector<cv::Point3d>& key_point_right_rect
+                        , cv::Vec3f& R_vec_out, cv::Vec3f& T_vec_out
+                        , int match_size);
 
     // The post-SURF part: matched ERP keypoints -> bearings (spherical_bundle_adjuster.cpp:268-298) ->
     // rotation-only solve.  Returns the rotation vector in rot[3].
@@ -106,4 +119,29 @@ class spherical_bundle_adjuster
     private:
     double expected_roll, expected_pitch, expected_yaw, expected_tx, expected_ty, expected_tz, expected_d;
     int num_proc = 1;
+};
+
+// spherical_bundle_adjuster.hpp:182-210 of the reference: a shuffled 0..size-1 handed out one by one.  Same
+// libstdc++ call (std::random_shuffle on std::rand), so the subsets are the ones the reference would draw.
+class random_array
+{
+    public:
+    random_array(int size) : rand_arr(size)
+    {
+        size_ = size;
+        count_ = 0;
+        std::iota(rand_arr.begin(), rand_arr.end(), 0);
+        std::random_shuffle(rand_arr.begin(), rand_arr.end());
+    }
+    int get_rand()
+    {
+        int retval = rand_arr[count_];
+        count_ = (count_ + 1) % size_;
+        return retval;
+    }
+
+    private:
+    int size_;
+    std::vector<int> rand_arr;
+    int count_;
 };

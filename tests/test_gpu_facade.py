@@ -86,3 +86,21 @@ def test_cpp_facade_end_to_end(tmp_path):
     assert len(rows) == len(qi2) > 0
     assert np.array_equal(rows[:, 0].astype(np.int32), qi2) and np.array_equal(rows[:, 1].astype(np.int32), ti2)
     assert np.array_equal(rows[:, 2:4], lifted[0][qi2]) and np.array_equal(rows[:, 4:6], lifted[1][ti2])
+
+    # initial_guess through the facade: the subsets come from std::random_shuffle on std::rand (seeded 1 by the demo,
+    # which is also the C library's state when the reference starts); the same draws are replayed here with libc
+    import ctypes
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(1)
+    n_sp, sample_n = 1500, int(1500 * 0.25)
+    idx = np.empty((80, sample_n), np.int32)
+    for s_ in range(80):
+        perm = list(range(n_sp))
+        for i in range(1, n_sp):                       # libstdc++'s std::random_shuffle
+            j = libc.rand() % (i + 1)
+            perm[i], perm[j] = perm[j], perm[i]
+        idx[s_] = perm[:sample_n]
+    ig = np.fromfile(d + "/ig_out.bin", np.float32)
+    oR, oT, best, cand = oracle.initial_guess(sb1, sb2, idx)
+    assert np.abs(ig[:3] - oR).max() < 2e-6
+    assert min(np.abs(ig[3:] - oT).max(), np.abs(ig[3:] + oT).max()) < 2e-6

@@ -269,3 +269,37 @@ def test_spherical_surf_golden(golden_dir):
         assert hashlib.sha256(lut.tobytes()).hexdigest() == str(g["lut_sha256"][k])
         assert np.array_equal(oracle.crop_rotated_image(im, float(pitch))[::37, ::41], g["crop_samples"][k])
         assert np.array_equal(oracle.rotate_keypoints(g["keys"], float(pitch), w, h), g["keys_rotated"][k])
+
+
+def test_initial_guess_oracle_pinned_to_opencv():
+    """eight_point_estimation's linear algebra (spherical_bundle_adjuster.cpp:53-82) against the installed OpenCV:
+    cv2.SVDecomp and cv2.decomposeEssentialMat are the calls the reference makes."""
+    cv2 = pytest.importorskip("cv2")
+    b1, b2, r, t, _ = synth.make_two_view(2000, seed=3, outlier_frac=0.05)
+    rng = np.random.default_rng(0)
+    idx = np.stack([rng.permutation(2000)[:500] for _ in range(12)]).astype(np.int32)
+
+    def rot2euler(R):
+        sy = np.float32(np.sqrt(R[0, 0] ** 2 + R[1, 0] ** 2))
+        return np.array([np.arctan2(R[2, 1], R[2, 2]), np.arctan2(-R[2, 0], sy), np.arctan2(R[1, 0], R[0, 0])], np.float32)
+
+    for s in range(len(idx)):
+        A = np.einsum("na,nb->nab", b1[idx[s]], b2[idx[s]]).reshape(-1, 9)
+        w, u, vt = cv2.SVDecomp(A)
+        e, sv = oracle.eight_point_null(b1, b2, idx[s])
+        assert np.abs(e * np.sign(e @ vt[-1]) - vt[-1]).max() < 1e-12 and np.allclose(sv, w.ravel(), rtol=1e-10)
+        w2, u2, vt2 = cv2.SVDecomp(vt[-1].reshape(3, 3))
+        w2[2] = 0
+        R1, R2, tt = cv2.decomposeEssentialMat(u2 @ np.diag(w2.ravel()) @ vt2)
+        o1, o2, oT, v1, v2 = oracle.essential_to_candidates(e)
+        c1, c2 = rot2euler(R1), rot2euler(R2)
+        same = max(np.abs(o1 - c1).max(), np.abs(o2 - c2).max())
+        swap = max(np.abs(o1 - c2).max(), np.abs(o2 - c1).max())
+        assert min(same, swap) < 1e-6 and np.abs(np.abs(oT) - np.abs(tt.ravel())).max() < 1e-6
+    # the vote: hand-made candidates, the tight cluster wins over the stragglers
+    cand = np.concatenate([np.float32([0.1, 0.2, 0.3]) + 1e-3 * rng.standard_normal((30, 3)).astype(np.float32),
+                           rng.uniform(-1.5, 1.5, (10, 3)).astype(np.float32)])
+    win = oracle.lib().orc_vote_rotation(oracle._p(np.ascontiguousarray(cand), __import__("ctypes").c_float), len(cand))
+    assert win < 30
+    R, T, best, c = oracle.initial_guess(b1, b2, idx)
+    assert best >= 0 and len(c) >= len(idx)
