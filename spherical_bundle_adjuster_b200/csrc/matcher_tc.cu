@@ -479,12 +479,13 @@ constexpr int RR_THREADS = 128;
 constexpr int RR_ROWS = RR_THREADS / 16;
 constexpr int RR_PER_THREAD = 4;   // up to 16*4 = 64 candidate entries (16 slots) merged by shuffles; more -> serial path
 
-__global__ void __launch_bounds__(RR_THREADS)
+__global__ void __launch_bounds__(RR_THREADS, 4)
 tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, int nt, const float* __restrict__ na,
                  const float* __restrict__ nb_max, Partition part, const float4* __restrict__ cand_v, const int4* __restrict__ cand_id,
                  int slots, Top2* __restrict__ top, int* __restrict__ fb_list, int* __restrict__ fb_count, float* __restrict__ dbg_max_err)
 {
     __shared__ __align__(16) float qs[RR_ROWS][DIM];
+    __shared__ __align__(16) float ts[RR_ROWS][4 * NCAND][DIM + 4];   // the candidate rows of every query of the CTA
     __shared__ float win_v[RR_ROWS][NCAND];
     __shared__ int win_id[RR_ROWS][NCAND];
     const int tid = threadIdx.x, grp = tid >> 4, e = tid & 15;
@@ -541,18 +542,37 @@ tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ 
     const int chunk = win_id[grp][e >> 2];
     const float chunk_v = win_v[grp][e >> 2];
 
-    // b) exact distance of this thread's train row
+    // b) exact distance of this thread's train row.  The 16 candidate rows of a query are fetched COOPERATIVELY --
+    //    for each row the 16 threads of the group read its 256 contiguous bytes as one float4 each, so a load
+    //    instruction touches 4 lines per warp instead of 32 -- parked in shared memory (row stride 68 floats: the
+    //    float4 reads below are conflict free) and then read back row-per-thread.
+    {
+        float4 stage[8];
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+#pragma unroll
+            for (int cc = 0; cc < 8; cc++) {
+                const int c = half * 8 + cc;
+                const int cj = win_id[grp][c >> 2] * CHUNK + (c & 3);
+                const bool ok = win_id[grp][c >> 2] >= 0 && cj < nt;
+                stage[cc] = ok ? __ldg(reinterpret_cast<const float4*>(t + (size_t)cj * DIM) + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int cc = 0; cc < 8; cc++) *reinterpret_cast<float4*>(&ts[grp][half * 8 + cc][4 * e]) = stage[cc];
+        }
+    }
+    __syncwarp();
     const int j = chunk * CHUNK + (e & 3);
     const bool valid = chunk >= 0 && j < nt;
     Top2 best = top2_empty();
     float exact_v = INF;
     if (valid) {
         float tv[DIM], qv[DIM];
-        const float4* tp = reinterpret_cast<const float4*>(t + (size_t)j * DIM);
+        const float4* tp = reinterpret_cast<const float4*>(&ts[grp][e][0]);
         const float4* qp = reinterpret_cast<const float4*>(&qs[grp][0]);
 #pragma unroll
         for (int k = 0; k < DIM / 4; k++) {
-            const float4 a = __ldg(tp + k);
+            const float4 a = tp[k];
             tv[4 * k] = a.x; tv[4 * k + 1] = a.y; tv[4 * k + 2] = a.z; tv[4 * k + 3] = a.w;
             const float4 b = qp[k];
             qv[4 * k] = b.x; qv[4 * k + 1] = b.y; qv[4 * k + 2] = b.z; qv[4 * k + 3] = b.w;
