@@ -382,12 +382,14 @@ def bench_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 200 for the GPU arm, 8 for the CPU reference arm)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 8 if args.impl == "reference" else 200
     if args.impl == "reference":
         bench_reference(args)
     else:
