@@ -299,7 +299,10 @@ def bench_ours(args):
         "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes)},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "matcher distance kernel (" + algo + ")", "bound": "tensor", "achieved": achieved, "peak": peak,
-                     "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                     "unit": "TFLOP/s", "frac": achieved / peak,
+                     # DRAM bytes of one launch from the ncu --set full capture of this kernel at this size
+                     # (profiles/r01_ncu_final_prof_tc_r01d.txt: 8.48 MB read, 0 written = the bf16 operands once)
+                     "traffic": 8480256 if (NKP, DIM) == (16384, 64) else None, "traffic_unit": "bytes of DRAM traffic per launch (ncu)",
                      "peak_source": peaks["source"] + " bf16 dense, sustained (kernel timed inside the step)",
                      "algorithmic_flops_per_launch": flops, "kernel_ms": mk * 1e3},
         "stage_ms": {"match_kernel": float(np.mean(match_ms)), "remap_kernel_per_image": float(np.mean(remap_ms)),

@@ -66,3 +66,23 @@ def test_initial_guess_matches_oracle(ctx, n, outliers):
         from scipy.spatial.transform import Rotation as Rot
         eul = Rot.from_rotvec(r).inv().as_euler("xyz")
         assert np.abs(R - eul).max() < 5e-3
+
+
+def test_initial_guess_without_valid_candidate_is_an_error(ctx):
+    """Both rotation candidates of every subset above 1.57 rad: the reference would index an empty vector (:179);
+    the library reports it."""
+    from spherical_bundle_adjuster_b200 import SbaError
+    from scipy.spatial.transform import Rotation as Rot
+    rng = np.random.default_rng(1)
+    X1 = synth.unit_rows(rng.standard_normal((400, 3))) * rng.uniform(2, 8, (400, 1))
+    R = Rot.from_euler("xyz", [3.0, 0.0, 0.0]).as_matrix()      # a 172 degree roll: |angle| > 1.57 for both candidates
+    X2 = X1 @ R.T - np.array([0.3, 0.1, -0.2])
+    b1, b2 = synth.unit_rows(X1), synth.unit_rows(X2)
+    idx = _subsets(400, 10, seed=4)
+    oR, oT, best, cand = oracle.initial_guess(b1, b2, idx)
+    if len(cand) == 0:
+        with pytest.raises(SbaError):
+            ctx.initial_guess(b1, b2, idx)
+    else:   # geometry happened to leave a valid twisted-pair member: results must still agree
+        R_, T_, nc = ctx.initial_guess(b1, b2, idx)
+        assert nc == len(cand) and np.abs(R_ - oR).max() < 2e-6

@@ -53,7 +53,7 @@ def test_crop_batched_and_device_mode(ctx):
     assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), want)
 
 
-@pytest.mark.parametrize("w,h", [(1024, 512), (3840, 1920)])
+@pytest.mark.parametrize("w,h", [(1024, 512), (3840, 1920), (1000, 500), (258, 130)])
 def test_four_bands_in_one_gather(ctx, w, h):
     im = synth.make_erp_image(w, h, seed=7)
     bands = ctx.spherical_crops(im)
@@ -85,3 +85,14 @@ def test_rotate_pixels_anywhere(ctx):
     rc[:4] = [[0, 0], [h // 2, 0], [h // 2, w // 2], [h - 1, w - 1]]
     for pitch in (45.0, -90.0, 12.25):
         assert np.array_equal(ctx.rotate_pixels(rc, pitch, w, h), oracle.rotate_pixels(rc, pitch, w, h))
+
+
+def test_empty_and_invalid_inputs(ctx):
+    from spherical_bundle_adjuster_b200 import SbaError
+    assert ctx.rotate_keypoints(np.zeros((0, 2), np.float32), 45.0, 1024, 512).shape == (0, 2)
+    assert ctx.rotate_pixels(np.zeros((0, 2), np.int32), 45.0, 1024, 512).shape == (0, 2)
+    with pytest.raises(SbaError):
+        ctx.crop_rotated_image(np.zeros((3, 8, 3), np.uint8), 45.0)       # fewer than 4 rows: no band
+    # keypoints outside the band (and outside the image) go through the direct computation, like the reference
+    xy = np.array([[10.0, -40.0], [2000.0, 300.0], [5.5, 127.9]], np.float32)
+    assert np.array_equal(ctx.rotate_keypoints(xy, -45.0, 1024, 512), oracle.rotate_keypoints(xy, -45.0, 1024, 512))
