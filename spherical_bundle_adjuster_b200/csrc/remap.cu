@@ -7,10 +7,9 @@
 //   The source index of an output pixel depends only on the geometry (w, h, cube_size), so it is
 //   computed once into an int32 table ("remap plan", cached per geometry in the context) and every
 //   frame after that is a pure table-driven gather:  4 B index read + 3 B gathered + 3 B written per
-//   output pixel.  Each thread produces 4 adjacent strip pixels = 12 output bytes = three aligned
-//   32-bit stores; a warp writes 384 contiguous bytes.  Neighbouring strip pixels map to
-//   neighbouring source pixels of (mostly) one ERP row, so the byte gathers hit L1/L2 lines that the
-//   same warp already touched.
+//   output pixel.  A warp owns 128 adjacent strip pixels: lanes walk adjacent pixels when gathering (a load
+//   instruction then touches the few source lines one short curve segment crosses) and the warp's 384 output
+//   bytes leave as 24 aligned 16-byte stores (details at remap_gather_warp_kernel).
 //   The table is built on the device with the reference's fp64 formula.  CUDA's fp64 acos/atan2 are
 //   not correctly rounded, so any pixel whose continuous source coordinate lies within 1e-6 of an
 //   integer (the only place a last-ulp difference can flip the truncation; ~0.6 % of pixels: axes
