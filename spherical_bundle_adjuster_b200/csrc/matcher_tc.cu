@@ -227,6 +227,16 @@ __device__ __forceinline__ void cand_insert_bf(Cand& c, float m, int id)
     }
 }
 
+// (d0, d1) = -2 * (a0, a1) + (c0, c1) with one fma.rn.f32x2
+__device__ __forceinline__ void ffma2(float& d0, float& d1, uint32_t a0, uint32_t a1, float c0, float c1)
+{
+    uint64_t a, c, d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(a0), "r"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(c0), "f"(c1));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(0xC0000000C0000000ull), "l"(c));   // -2.0f twice
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+
 __device__ __forceinline__ void cand_reset(Cand& c)
 {
 #pragma unroll
@@ -412,10 +422,10 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
                     const float4 nv = *reinterpret_cast<const float4*>(wnb + g * 32 + c * 4);
-                    const float v0 = fmaf(-2.f, __uint_as_float(r[c * 4 + 0]), nv.x);
-                    const float v1 = fmaf(-2.f, __uint_as_float(r[c * 4 + 1]), nv.y);
-                    const float v2 = fmaf(-2.f, __uint_as_float(r[c * 4 + 2]), nv.z);
-                    const float v3 = fmaf(-2.f, __uint_as_float(r[c * 4 + 3]), nv.w);
+                    // |b|^2 - 2 a.b for two columns per instruction (packed fp32 FMA, same rounding as two fmaf)
+                    float v0, v1, v2, v3;
+                    ffma2(v0, v1, r[c * 4 + 0], r[c * 4 + 1], nv.x, nv.y);
+                    ffma2(v2, v3, r[c * 4 + 2], r[c * 4 + 3], nv.z, nv.w);
                     cm[c] = fminf(fminf(v0, v1), fminf(v2, v3));
                 }
                 const float gm = fminf(fminf(fminf(cm[0], cm[1]), fminf(cm[2], cm[3])), fminf(fminf(cm[4], cm[5]), fminf(cm[6], cm[7])));
