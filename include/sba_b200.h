@@ -89,6 +89,15 @@ int sba_equi2cube_face(sba_ctx* ctx, const uint8_t* erp, int w, int h, int cube_
 
 /* Build (or fetch from the cache) the index table: lut_out[cube_size][6*cube_size] int32 source
  * pixel indices (row*w + col).  lut_out may be NULL to only warm the cache. */
+/* The table-driven gathers (cube strips, spherical_surf bands) exist in two kernels: a direct gather and a tiled one
+ * that stages each output tile's source bounding box in shared memory with bulk copies.  Which is faster depends on
+ * the table and on the batch size, and is measured once when a plan is built (2 frames; a batch larger than L2).
+ * mode 0 = use that choice, 1 = always direct, 2 = tiled wherever the geometry allows it (tests run both).
+ * sba_remap_plan_info reports what the trials of a cube plan found: tiled_preferred bit 0 = small batches, bit 1 = large;
+ * trial_ms = {small direct, small tiled, large direct, large tiled}. */
+int sba_ctx_set_remap_kernel(sba_ctx* ctx, int mode);
+int sba_remap_plan_info(sba_ctx* ctx, int w, int h, int cube_size, int* tiled_available, int* tiled_preferred, int* n_tiles,
+                        int* n_fallback_tiles, float trial_ms[4]);
 int sba_equi2cube_lut(sba_ctx* ctx, int w, int h, int cube_size, int32_t* lut_out, int mem);
 
 /* equi2cube_surf::cube2equi_pixel for n keypoints (equi2cube_surf.cpp:19-76).

@@ -117,6 +117,18 @@ class Context:
     def launch_count(self) -> int:
         return int(self._lib.sba_ctx_launch_count(self._h))
 
+    def set_remap_kernel(self, mode: int):
+        """0 = per-plan choice from the timed trial, 1 = direct gather, 2 = tiled gather wherever possible."""
+        check(self._lib.sba_ctx_set_remap_kernel(self._h, int(mode)))
+
+    def remap_plan_info(self, w: int, h: int, cube_size: int) -> dict:
+        a, p, n, f = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        ms = (C.c_float * 4)()
+        check(self._lib.sba_remap_plan_info(self._h, w, h, cube_size, C.byref(a), C.byref(p), C.byref(n), C.byref(f), C.byref(ms)))
+        return dict(tiled_available=bool(a.value), tiled_preferred_small=bool(p.value & 1), tiled_preferred_large=bool(p.value & 2),
+                    n_tiles=n.value, n_fallback_tiles=f.value, trial_ms=dict(small_direct=float(ms[0]), small_tiled=float(ms[1]),
+                                                                             large_direct=float(ms[2]), large_tiled=float(ms[3])))
+
     def set_profiling(self, enable: bool):
         check(self._lib.sba_ctx_set_profiling(self._h, int(enable)))
 

@@ -35,6 +35,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
+#include "bulk.cuh"
 
 namespace sba {
 
@@ -581,31 +582,6 @@ struct EvalArgs {
 // SM at 24 resident warps) is fixed by construction instead of by register allocation and instruction
 // scheduling of explicit prefetch loads.
 constexpr int BULK_STAGES = 4;
-
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(smem_dst)),
-                 "l"(gsrc), "r"(bytes), "r"(smem_addr(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void bar_expect(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity)
-{
-    const uint32_t addr = smem_addr(bar);
-    uint32_t ok = 0;
-    const long long t0 = clock64();
-    while (true) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-        if (ok) break;
-        if (clock64() - t0 > 4000000000ll) __trap();   // a protocol bug traps instead of hanging the GPU
-    }
-}
 
 // MODE 0: partials only (ba_fold_kernel follows); 1: the last CTA folds; 2: the last CTA folds and runs the LM decision.
 // DEVN: the observation count is read from device memory (fused pair pipeline); a separate instantiation

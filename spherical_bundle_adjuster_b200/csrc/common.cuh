@@ -115,8 +115,27 @@ struct BlockCache {
     }
 };
 
+// Second form of a gather table for the tiled kernel (remap.cu): per 16 x 128 output tile the bounding box of its
+// source pixels (staged in shared memory by bulk copies) and per pixel its byte offset inside that box.
+struct TileBox {
+    int32_t src_off;      // byte offset of the box inside one source image (16-byte aligned); < 0: box too large, gather directly
+    uint16_t nrows;       // source rows covered
+    uint16_t row_bytes;   // bytes staged per row (multiple of 16)
+};
+struct TiledPlan {
+    TileBox* tiles = nullptr;   // device, tiles_y x tiles_x
+    uint32_t* rel = nullptr;    // device, rows x cols; 0xFFFFFFFF = no source pixel
+    int tiles_x = 0, tiles_y = 0;
+    int n_fallback = 0;
+    // set by timed trials at plan construction: does the tiled kernel beat the direct gather for this table -- on a couple
+    // of frames (sources stay in L2) and on a batch that streams from HBM (8 frames)?  [0] = small, [1] = large batches
+    bool preferred[2] = {false, false};
+    float trial_ms[2][2] = {{0.f, 0.f}, {0.f, 0.f}};   // [batch class][direct, tiled]
+};
+
 struct RemapPlan {
     int w, h, cs;
+    TiledPlan tiled;
     int32_t* lut = nullptr;  // device, cs x 6cs
     int n_patched = 0;       // near-integer pixels resolved with the host libm
     int n_clamped = 0;
@@ -153,7 +172,9 @@ struct sba_ctx {
     std::map<std::tuple<int, int, int>, sba::RemapPlan> plans;
     std::map<std::tuple<int, int, uint32_t>, sba::CropPlan> crop_plans;   // keyed by (w, h, bits of the pitch)
     std::map<std::pair<int, int>, int32_t*> band_plans;                  // the four bands of spherical_surf::do_all in one table
+    std::map<std::pair<int, int>, sba::TiledPlan> band_tiled;             // ... and its tiled form
     sba_match_stats match_stats{};
+    int remap_kernel = 0;       // 0 = per-plan choice from the timed trial, 1 = direct gather, 2 = tiled gather (sba_ctx_set_remap_kernel)
     bool pair_pending = false;  // a sba_pair_rotation_begin whose _end has not run yet (pipeline.cu)
     int* pinned_i32 = nullptr;  // small pinned host mailbox (64 ints) for scalar read-backs
     bool profiling = false;
@@ -242,7 +263,10 @@ BaView ba_problem_view(sba_ba_problem* p);
 
 // remap.cu: out[img][p] = erp[img][lut[p]] (3-byte pixels); masked tables hold -1 for "no source", which gives 0
 int launch_lut_gather(sba_ctx* c, const uint8_t* d_erp, int64_t src_bytes, const int32_t* lut, int rows, int cols, uint8_t* d_out, int n_images,
-                      bool masked);
+                      bool masked, const TiledPlan* tiled = nullptr, int src_w = 0);
+// remap.cu: derive the tiled form of a finished table (source image w x h)
+int build_tiled_plan(sba_ctx* c, const int32_t* lut, int rows, int cols, int w, int h, bool masked, TiledPlan* out);
+void free_tiled_plan(TiledPlan* tp);
 
 // pipeline.cu: drop the cached pair graphs (context teardown)
 void pipeline_release(sba_ctx* c);

@@ -76,8 +76,11 @@ int sba_ctx_destroy(sba_ctx* c)
     sba::pipeline_release(c);
     for (auto& b : c->scratch) b.release();
     c->cache.release_all();
-    for (auto& kv : c->plans)
+    for (auto& kv : c->plans) {
         if (kv.second.lut) cudaFree(kv.second.lut);
+        sba::free_tiled_plan(&kv.second.tiled);
+    }
+    for (auto& kv : c->band_tiled) sba::free_tiled_plan(&kv.second);
     for (auto& kv : c->crop_plans)
         if (kv.second.lut) cudaFree(kv.second.lut);
     for (auto& kv : c->band_plans)

@@ -15,9 +15,11 @@
 //   integer (the only place a last-ulp difference can flip the truncation; ~0.6 % of pixels: axes
 //   and diagonals) is re-evaluated on the host with the same glibc libm the reference links and
 //   patched in.  The table is therefore bit-identical to the reference's index arithmetic.
+#include <climits>
 #include <cmath>
 
 #include "common.cuh"
+#include "bulk.cuh"
 #include "geometry.cuh"
 
 #ifndef M_PI
@@ -106,6 +108,7 @@ static int get_plan(sba_ctx* c, int w, int h, int cs, RemapPlan** out)
         SBA_CUDA(cudaStreamSynchronize(c->stream));  // `what` goes out of scope
     }
     plan.n_clamped = cnt[1];
+    SBA_TRY(build_tiled_plan(c, plan.lut, cs, 6 * cs, w, h, false, &plan.tiled));
     auto ins = c->plans.emplace(key, plan);
     *out = &ins.first->second;
     return SBA_OK;
@@ -172,6 +175,232 @@ remap_gather_warp_kernel(const uint8_t* __restrict__ erp, const int32_t* __restr
     }
 }
 
+// ---- tiled variant ------------------------------------------------------------------------------------------
+// The direct gather above is bound by the L1 data pipe: a run of 32 output pixels maps onto a short curve that
+// crosses ~6 source rows, every row is another 128-byte line, and each line costs a wavefront -- four per load
+// instruction, eight load instructions per 128 pixels.  Here a CTA owns a 16 x 128 output tile whose source pixels
+// lie in a compact bounding box (median 15 KB at 4K -> cube 960): the box is staged in shared memory by 1-D bulk
+// copies, one per source row, issued by warp 0 -- the TMA engine moves the bytes, the LSU pipe does not see them --
+// and the per-pixel gathers become shared-memory loads (bank conflicts instead of lines).  Tiles whose box exceeds
+// TILE_BOX_MAX (around the poles of the top and bottom faces a face row maps onto a wide arc) keep the direct
+// gather inside the same kernel.  `rel` holds each pixel's byte offset inside its tile's box.
+constexpr int TILE_H = 16, TILE_W = 128;
+constexpr int TILE_BOX_MAX = 24576;
+
+__global__ void __launch_bounds__(256)
+tile_build_kernel(const int32_t* __restrict__ lut, int rows, int cols, int w, TileBox* __restrict__ tiles, uint32_t* __restrict__ rel,
+                  int* __restrict__ n_fallback)
+{
+    __shared__ int s_rmin, s_rmax, s_cmin, s_cmax;
+    __shared__ TileBox s_box;
+    const int tiles_x = cols / TILE_W;
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    if (threadIdx.x == 0) { s_rmin = INT_MAX; s_rmax = -1; s_cmin = INT_MAX; s_cmax = -1; }
+    __syncthreads();
+    constexpr int PER_THREAD = TILE_H * TILE_W / 256;
+    int idx[PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < PER_THREAD; k++) {
+        const int pl = k * 256 + threadIdx.x, ly = pl >> 7, lx = pl & 127;
+        const int y = ty * TILE_H + ly;
+        idx[k] = (y < rows) ? __ldg(lut + (int64_t)y * cols + tx * TILE_W + lx) : -1;
+        if (idx[k] >= 0) {
+            const int r = idx[k] / w, cc = idx[k] - r * w;
+            atomicMin(&s_rmin, r); atomicMax(&s_rmax, r);
+            atomicMin(&s_cmin, cc); atomicMax(&s_cmax, cc);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        TileBox b;
+        if (s_rmax < 0) { b.src_off = 0; b.nrows = 0; b.row_bytes = 0; }   // nothing to fetch (fully masked tile)
+        else {
+            const int c0 = (s_cmin * 3) & ~15, c1 = (s_cmax * 3 + 3 + 15) & ~15;
+            const int nrows = s_rmax - s_rmin + 1, row_bytes = c1 - c0;
+            if ((int64_t)nrows * row_bytes > TILE_BOX_MAX || nrows > 65535) { b.src_off = -1; b.nrows = 0; b.row_bytes = 0; atomicAdd(n_fallback, 1); }
+            else { b.src_off = s_rmin * w * 3 + c0; b.nrows = (uint16_t)nrows; b.row_bytes = (uint16_t)row_bytes; }
+        }
+        s_box = b;
+        tiles[blockIdx.x] = b;
+    }
+    __syncthreads();
+    const TileBox b = s_box;
+    const int r0 = (b.src_off >= 0 && b.nrows) ? b.src_off / (w * 3) : 0;
+    const int c0b = (b.src_off >= 0 && b.nrows) ? b.src_off - r0 * w * 3 : 0;
+#pragma unroll
+    for (int k = 0; k < PER_THREAD; k++) {
+        const int pl = k * 256 + threadIdx.x, ly = pl >> 7, lx = pl & 127;
+        const int y = ty * TILE_H + ly;
+        if (y >= rows) continue;
+        uint32_t v = 0xFFFFFFFFu;
+        if (idx[k] >= 0 && b.src_off >= 0) {
+            const int r = idx[k] / w, cc = idx[k] - r * w;
+            v = (uint32_t)((r - r0) * (int)b.row_bytes + (cc * 3 - c0b));
+        }
+        rel[(int64_t)y * cols + tx * TILE_W + lx] = v;
+    }
+}
+
+template <bool MASKED>
+__global__ void __launch_bounds__(256)
+remap_gather_tiled_kernel(const uint8_t* __restrict__ erp, const int32_t* __restrict__ lut, const uint32_t* __restrict__ rel,
+                          const TileBox* __restrict__ tiles, uint8_t* __restrict__ out, int64_t src_bytes_per_image, int src_row_bytes, int rows,
+                          int cols, int tiles_x, int tiles_per_image, int n_images)
+{
+    __shared__ __align__(128) uint8_t box[TILE_BOX_MAX + 16];
+    __shared__ __align__(16) uint32_t pix[8][128];
+    __shared__ __align__(16) uint32_t stage[8][96];
+    __shared__ __align__(8) uint64_t bar;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { bar_init(&bar, 1); bar_init_fence(); }
+    __syncthreads();
+    uint32_t phase = 0;
+    const int64_t P = (int64_t)rows * cols;
+    const int64_t last_word = src_bytes_per_image / 4 - 1;
+    const int total = tiles_per_image * n_images;
+    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        const int img = item / tiles_per_image, tile = item - img * tiles_per_image;
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        const TileBox tb = tiles[tile];
+        const uint8_t* src = erp + (int64_t)img * src_bytes_per_image;
+        const bool staged = tb.src_off >= 0;
+        if (staged && tb.nrows && wib == 0) {
+            if (lane == 0) bar_expect(&bar, (uint32_t)tb.nrows * tb.row_bytes);
+            __syncwarp();
+            for (int r = lane; r < tb.nrows; r += 32)
+                bulk_load(box + (size_t)r * tb.row_bytes, src + tb.src_off + (int64_t)r * src_row_bytes, tb.row_bytes, &bar);
+        }
+        bool waited = !(staged && tb.nrows);
+#pragma unroll 1
+        for (int rr = 0; rr < TILE_H / 8; rr++) {
+            const int y = ty * TILE_H + wib * (TILE_H / 8) + rr;
+            if (y < rows) {
+                const int64_t px0 = (int64_t)y * cols + tx * TILE_W;
+                uint32_t v[4];
+                if (staged) {
+                    uint32_t off[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) off[k] = __ldg(rel + px0 + 32 * k + lane);
+                    if (!waited) { bar_wait(&bar, phase); waited = true; }
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t o = (off[k] == 0xFFFFFFFFu) ? 0u : off[k];
+                        const uint32_t* wp = reinterpret_cast<const uint32_t*>(box + (o & ~3u));
+                        const uint32_t sh = (o & 3u) * 8u;
+                        const uint32_t w0 = wp[0], w1 = (sh > 8u) ? wp[1] : 0u;
+                        v[k] = __funnelshift_r(w0, w1, sh) & 0x00FFFFFFu;
+                        if (MASKED && off[k] == 0xFFFFFFFFu) v[k] = 0u;
+                    }
+                } else {
+                    const uint32_t* words = reinterpret_cast<const uint32_t*>(src);
+                    int idx[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) idx[k] = __ldg(lut + px0 + 32 * k + lane);
+                    uint32_t w0[4], w1[4], sh[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int64_t a = (int64_t)((MASKED && idx[k] < 0) ? 0 : idx[k]) * 3;
+                        const int64_t wi = a >> 2;
+                        sh[k] = (uint32_t)(a & 3) * 8;
+                        w0[k] = __ldg(words + wi);
+                        w1[k] = (sh[k] > 8) ? __ldg(words + min(wi + 1, last_word)) : 0u;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        v[k] = __funnelshift_r(w0[k], w1[k], sh[k]) & 0x00FFFFFFu;
+                        if (MASKED && idx[k] < 0) v[k] = 0u;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) pix[wib][32 * k + lane] = v[k];
+                __syncwarp();
+                const uint4 q = *reinterpret_cast<const uint4*>(&pix[wib][4 * lane]);
+                stage[wib][lane * 3 + 0] = q.x | (q.y << 24);
+                stage[wib][lane * 3 + 1] = (q.y >> 8) | (q.z << 16);
+                stage[wib][lane * 3 + 2] = (q.z >> 16) | (q.w << 8);
+                __syncwarp();
+                if (lane < 24) {
+                    const uint4 o = *reinterpret_cast<const uint4*>(&stage[wib][lane * 4]);
+                    *reinterpret_cast<uint4*>(out + ((int64_t)img * P + px0) * 3 + lane * 16) = o;
+                }
+                __syncwarp();
+            }
+        }
+        if (!waited) bar_wait(&bar, phase);      // warps whose rows fall outside the image still consume the phase
+        if (staged && tb.nrows) phase ^= 1u;
+        __syncthreads();                          // the box is refilled for the next tile
+    }
+}
+
+void free_tiled_plan(TiledPlan* tp)
+{
+    if (tp->tiles) cudaFree(tp->tiles);
+    if (tp->rel) cudaFree(tp->rel);
+    *tp = TiledPlan();
+}
+
+int build_tiled_plan(sba_ctx* c, const int32_t* lut, int rows, int cols, int w, int h, bool masked, TiledPlan* out)
+{
+    *out = TiledPlan();
+    // geometry the tiled kernel can take: whole 128-pixel tile columns, 16-byte aligned source rows, offsets within 31 bits
+    if (cols % TILE_W != 0 || (w * 3) % 16 != 0 || (int64_t)w * h * 3 >= ((int64_t)1 << 31)) return SBA_OK;
+    TiledPlan tp;
+    tp.tiles_x = cols / TILE_W;
+    tp.tiles_y = (rows + TILE_H - 1) / TILE_H;
+    const int n_tiles = tp.tiles_x * tp.tiles_y;
+    SBA_CUDA(cudaMalloc(&tp.tiles, (size_t)n_tiles * sizeof(TileBox)));
+    SBA_CUDA(cudaMalloc(&tp.rel, (size_t)rows * cols * sizeof(uint32_t)));
+    SBA_TRY(c->scratch[SCR_WORK1].ensure(sizeof(int), c->stream));
+    int* d_cnt = c->scratch[SCR_WORK1].as<int>();
+    SBA_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int), c->stream));
+    tile_build_kernel<<<n_tiles, 256, 0, c->stream>>>(lut, rows, cols, w, tp.tiles, tp.rel, d_cnt);
+    SBA_LAUNCHED(c);
+    SBA_CUDA(cudaGetLastError());
+    SBA_CUDA(cudaMemcpyAsync(&tp.n_fallback, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    SBA_CUDA(cudaStreamSynchronize(c->stream));
+
+    // Which kernel is faster depends on the table (how many source rows a tile's box spans decides how many bulk
+    // copies it takes) and on whether the sources stream from HBM or sit in L2, so both kernels are timed once per
+    // plan on scratch frames: 2 frames (the per-pair calls) and a batch larger than L2.
+    const size_t src_bytes = (size_t)w * h * 3, out_bytes = (size_t)rows * cols * 3;
+    const int big = (int)std::min<size_t>(8, std::max<size_t>(3, ((size_t)160 << 20) / src_bytes + 1));
+    SBA_TRY(c->scratch[SCR_WORK3].ensure(big * src_bytes, c->stream));
+    SBA_TRY(c->scratch[SCR_WORK4].ensure(big * out_bytes, c->stream));
+    SBA_CUDA(cudaMemsetAsync(c->scratch[SCR_WORK3].p, 0x5a, big * src_bytes, c->stream));
+    cudaEvent_t e0, e1;
+    SBA_CUDA(cudaEventCreate(&e0));
+    SBA_CUDA(cudaEventCreate(&e1));
+    const int saved_mode = c->remap_kernel;
+    int rc = SBA_OK;
+    for (int cls = 0; cls < 2 && rc == SBA_OK; cls++) {
+        const int frames = cls == 0 ? 2 : big;
+        for (int variant = 0; variant < 2 && rc == SBA_OK; variant++) {
+            c->remap_kernel = variant == 0 ? 1 : 2;
+            float best = 1e30f;
+            for (int rep = 0; rep < 4 && rc == SBA_OK; rep++) {
+                cudaEventRecord(e0, c->stream);
+                rc = launch_lut_gather(c, c->scratch[SCR_WORK3].as<uint8_t>(), (int64_t)src_bytes, lut, rows, cols, c->scratch[SCR_WORK4].as<uint8_t>(),
+                                       frames, masked, &tp, w);
+                cudaEventRecord(e1, c->stream);
+                cudaEventSynchronize(e1);
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, e0, e1);
+                if (rep > 0) best = std::min(best, ms);
+            }
+            tp.trial_ms[cls][variant] = best;
+        }
+        tp.preferred[cls] = tp.trial_ms[cls][1] < 0.95f * tp.trial_ms[cls][0];
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    c->remap_kernel = saved_mode;
+    c->scratch[SCR_WORK3].release();   // the trial buffers are large and never needed again
+    c->scratch[SCR_WORK4].release();
+    if (rc != SBA_OK) { free_tiled_plan(&tp); return rc; }
+    *out = tp;
+    return SBA_OK;
+}
+
 // Generic path: one thread per pixel; handles odd sizes, unaligned bases and single faces
 // (`lut_row_stride`/`face_off` select a cs-wide window of the strip table).
 __global__ void remap_gather1_kernel(const uint8_t* __restrict__ erp, const int32_t* __restrict__ lut, uint8_t* __restrict__ out,
@@ -229,9 +458,24 @@ __global__ void gather_matches_kernel(const float2* __restrict__ kl, const float
 
 // Table-driven gather of n_images images: out[img][p] = erp[img][lut[p]] for p in [0, rows*cols).
 int launch_lut_gather(sba_ctx* c, const uint8_t* d_erp, int64_t src_bytes, const int32_t* lut, int rows, int cols, uint8_t* d_out, int n_images,
-                      bool masked)
+                      bool masked, const TiledPlan* tiled, int src_w)
 {
     const int64_t P = (int64_t)rows * cols;
+    const bool want_tiled = tiled && tiled->tiles && (c->remap_kernel == 2 || (c->remap_kernel == 0 && tiled->preferred[n_images >= 3 ? 1 : 0]));
+    if (want_tiled && (uintptr_t)d_erp % 16 == 0 && src_bytes % 16 == 0 && (uintptr_t)d_out % 16 == 0 &&
+        (P * 3) % 16 == 0 && (int64_t)tiled->tiles_x * tiled->tiles_y * n_images < ((int64_t)1 << 31)) {
+        const int per_image = tiled->tiles_x * tiled->tiles_y, total = per_image * n_images;
+        const int blocks = std::min(total, c->sm_count * 6);
+        if (masked)
+            remap_gather_tiled_kernel<true><<<blocks, 256, 0, c->stream>>>(d_erp, lut, tiled->rel, tiled->tiles, d_out, src_bytes, src_w * 3, rows,
+                                                                            cols, tiled->tiles_x, per_image, n_images);
+        else
+            remap_gather_tiled_kernel<false><<<blocks, 256, 0, c->stream>>>(d_erp, lut, tiled->rel, tiled->tiles, d_out, src_bytes, src_w * 3, rows,
+                                                                             cols, tiled->tiles_x, per_image, n_images);
+        SBA_LAUNCHED(c);
+        SBA_CUDA(cudaGetLastError());
+        return SBA_OK;
+    }
     const bool fast_ok = ((uintptr_t)d_erp % 4 == 0) && (src_bytes % 4 == 0) && ((uintptr_t)d_out % 16 == 0) && ((uintptr_t)lut % 16 == 0) &&
                          ((P * 3) % 16 == 0 || n_images == 1) && P >= 128;
     int64_t done_px = 0;
@@ -268,7 +512,7 @@ static int launch_gather(sba_ctx* c, const uint8_t* d_erp, const RemapPlan* plan
     int64_t src_bytes = (int64_t)plan->w * plan->h * 3;
     prof_begin(c, SBA_KERNEL_REMAP);
     if (face < 0) {
-        SBA_TRY(launch_lut_gather(c, d_erp, src_bytes, plan->lut, cs, 6 * cs, d_out, n_images, false));
+        SBA_TRY(launch_lut_gather(c, d_erp, src_bytes, plan->lut, cs, 6 * cs, d_out, n_images, false, &plan->tiled, plan->w));
     } else {
         int64_t total = (int64_t)cs * cs * n_images;
         int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)c->sm_count * 32);
@@ -285,6 +529,29 @@ static int launch_gather(sba_ctx* c, const uint8_t* d_erp, const RemapPlan* plan
 using namespace sba;
 
 extern "C" {
+
+int sba_ctx_set_remap_kernel(sba_ctx* c, int mode)
+{
+    SBA_CHECK_ARG(c && mode >= 0 && mode <= 2);
+    c->remap_kernel = mode;
+    return SBA_OK;
+}
+
+int sba_remap_plan_info(sba_ctx* c, int w, int h, int cs, int* tiled_available, int* tiled_preferred, int* n_tiles, int* n_fallback_tiles,
+                        float trial_ms[4])
+{
+    SBA_CHECK_ARG(c && w > 0 && h > 0 && cs > 0);
+    SBA_CUDA(cudaSetDevice(c->device));
+    RemapPlan* plan;
+    SBA_TRY(get_plan(c, w, h, cs, &plan));
+    const TiledPlan& tp = plan->tiled;
+    if (tiled_available) *tiled_available = tp.tiles != nullptr;
+    if (tiled_preferred) *tiled_preferred = (tp.preferred[0] ? 1 : 0) | (tp.preferred[1] ? 2 : 0);
+    if (n_tiles) *n_tiles = tp.tiles_x * tp.tiles_y;
+    if (n_fallback_tiles) *n_fallback_tiles = tp.n_fallback;
+    if (trial_ms) for (int k = 0; k < 4; k++) trial_ms[k] = tp.trial_ms[k >> 1][k & 1];
+    return SBA_OK;
+}
 
 int sba_equi2cube_lut(sba_ctx* c, int w, int h, int cs, int32_t* lut_out, int mem)
 {

@@ -218,7 +218,11 @@ static int get_band_plan(sba_ctx* c, int w, int h, int32_t** out)
         }
     }
     SBA_CUDA(cudaGetLastError());
+    TiledPlan tp;
+    int rc = build_tiled_plan(c, lut, 4 * (h / 4), w, w, h, true, &tp);
+    if (rc != SBA_OK) { cudaFree(lut); return rc; }
     c->band_plans.emplace(key, lut);
+    c->band_tiled.emplace(key, tp);
     *out = lut;
     return SBA_OK;
 }
@@ -364,7 +368,7 @@ int sba_spherical_crops(sba_ctx* c, const uint8_t* erp, int w, int h, int n_imag
     SBA_TRY(stage_in(c, erp, in_bytes, mem, SCR_IN0, &d_in));
     SBA_TRY(stage_out(c, out, out_bytes, mem, SCR_OUT0, &d_out));
     prof_begin(c, SBA_KERNEL_REMAP);
-    SBA_TRY(launch_lut_gather(c, d_in, (int64_t)w * h * 3, lut, 4 * (h / 4), w, d_out, n_images, true));
+    SBA_TRY(launch_lut_gather(c, d_in, (int64_t)w * h * 3, lut, 4 * (h / 4), w, d_out, n_images, true, &c->band_tiled[std::make_pair(w, h)], w));
     prof_end(c, SBA_KERNEL_REMAP);
     SBA_TRY(copy_out(c, out, d_out, out_bytes, mem));
     return finish(c, mem);

@@ -54,8 +54,17 @@ def test_crop_batched_and_device_mode(ctx):
 
 
 @pytest.mark.parametrize("w,h", [(1024, 512), (3840, 1920), (1000, 500), (258, 130)])
-def test_four_bands_in_one_gather(ctx, w, h):
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_four_bands_in_one_gather(ctx, w, h, mode):
     im = synth.make_erp_image(w, h, seed=7)
+    ctx.set_remap_kernel(mode)          # per-plan choice, direct gather, tiled gather (where the geometry allows it)
+    try:
+        _check_bands(ctx, im, w, h)
+    finally:
+        ctx.set_remap_kernel(0)
+
+
+def _check_bands(ctx, im, w, h):
     bands = ctx.spherical_crops(im)
     assert bands.shape == (4, h // 4, w, 3)
     assert np.array_equal(bands[0], oracle.crop_rotated_image(im, 45.0))
