@@ -151,10 +151,28 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 struct Partition {
     int nqb, ntb, n_ctas;
     long long T;
-    __host__ __device__ long long start(int c) const { return (long long)c * T / n_ctas; }
+    // Entering a query block costs a CTA about `bcost` tiles' worth of time (the A operand reload drains the MMA
+    // pipeline and the candidate lists start empty again), so spans are cut in COST space: every block start
+    // weighs bcost tiles.  Position x in cost space -> tile index; the weight sits before the block's first tile.
+    int bcost;
+    __host__ __device__ long long cost_total() const { return T + (long long)bcost * nqb; }
+    __host__ __device__ long long tile_at(long long x) const
+    {
+        const long long per = ntb + bcost, q = x / per, rem = x - q * per;
+        return q * ntb + (rem > bcost ? rem - bcost : 0);
+    }
+    __host__ __device__ long long start(int c) const { return tile_at((long long)c * cost_total() / n_ctas); }
     // the CTA whose span contains tile t
-    __host__ __device__ int cta_of(long long t) const { return (int)(((t + 1) * n_ctas - 1) / T); }
-    __host__ __device__ int max_slots() const { return (n_ctas + nqb - 1) / nqb + 1; }
+    __host__ __device__ int cta_of(long long t) const
+    {
+        const long long x = t + (long long)bcost * (t / ntb + 1);
+        int k = (int)(x * n_ctas / cost_total());
+        if (k >= n_ctas) k = n_ctas - 1;
+        while (k + 1 < n_ctas && start(k + 1) <= t) k++;
+        while (k > 0 && start(k) > t) k--;
+        return k;
+    }
+    __host__ __device__ int max_slots() const { return (n_ctas + nqb - 1) / nqb + 2; }
 };
 
 // ---- 1. prepare ------------------------------------------------------------------------------------------
@@ -749,6 +767,9 @@ int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, 
     Partition part;
     part.nqb = nqb; part.ntb = ntb; part.T = (long long)nqb * ntb;
     part.n_ctas = (int)std::min<long long>(c->sm_count, part.T);
+    // measured with the trace build at 16k x 16k: spans that cross into a new query block finish ~8 us (5-6 tiles) late;
+    // capped so that no span can come out empty
+    part.bcost = (int)std::min<long long>(5, part.T / part.n_ctas / 4);
     const int slots = part.max_slots() * SUBSLOTS;
 
     // workspace carve-up (one buffer)
