@@ -36,7 +36,7 @@ sys.path.insert(0, ROOT)
 
 W, H, CS, NKP, DIM = 3840, 1920, 960, 16384, 64
 RATIO = 0.3
-IN_FLIGHT = int(os.environ.get("SBA_BENCH_IN_FLIGHT", "4"))   # library contexts (streams + host threads) per GPU
+IN_FLIGHT = int(os.environ.get("SBA_BENCH_IN_FLIGHT", "6"))   # library contexts (streams + host threads) per GPU
 POOL = 6  # distinct pairs resident in HBM and cycled through: 6 x 52.7 MB = 316 MB >> 126 MB L2
 
 
