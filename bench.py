@@ -304,7 +304,9 @@ def bench_ours(args):
                      # (profiles/r01_ncu_final_prof_tc_r01d.txt: 8.48 MB read, 0 written = the bf16 operands once)
                      "traffic": 8480256 if (NKP, DIM) == (16384, 64) else None, "traffic_unit": "bytes of DRAM traffic per launch (ncu)",
                      "peak_source": peaks["source"] + " bf16 dense, sustained (kernel timed inside the step)",
-                     "algorithmic_flops_per_launch": flops, "kernel_ms": mk * 1e3},
+                     "algorithmic_flops_per_launch": flops, "kernel_ms": mk * 1e3,
+                     # the exact-fp32 result costs three bf16 products (hi.hi + hi.lo + lo.hi): what the tensor pipe itself sustains
+                     "bf16_products_per_result": 3, "tensor_pipe_frac_incl_split_products": 3.0 * achieved / peak},
         "stage_ms": {"match_kernel": float(np.mean(match_ms)), "remap_kernel_per_image": float(np.mean(remap_ms)),
                      "ba_eval_kernel_last": float(np.mean(ba_ms))},
         "clocks": sampler.summary(),
