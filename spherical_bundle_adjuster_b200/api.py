@@ -298,6 +298,24 @@ class Context:
         check(self._lib.sba_match_last_stats(self._h, C.byref(s)))
         return s
 
+    def match_begin(self, desc1, desc2, ratio: float = 0.3, algo: int = MATCH_AUTO) -> "MatchCall":
+        """Queue ``match_two_image`` on CUDA tensors and return at once (nothing is copied to the host);
+        ``.end()`` waits for this context's stream and returns the MatchResult.  Several contexts on their own
+        streams keep several image pairs in flight (all-pairs matching of a sequence, BASELINE config 3)."""
+        q = _as(desc1, np.float32, torch.float32)
+        t = _as(desc2, np.float32, torch.float32)
+        if _mem_of(q, t) != SBA_MEM_DEVICE:
+            raise SbaError("match_begin takes CUDA tensors")
+        nq, nt, dim = q.shape[0], t.shape[0], q.shape[1]
+        qi = torch.empty(max(nq, 1), dtype=torch.int32, device=q.device)
+        ti = torch.empty(max(nq, 1), dtype=torch.int32, device=q.device)
+        dd = torch.empty(max(nq, 1), dtype=torch.float32, device=q.device)
+        nm = torch.zeros(1, dtype=torch.int32, device=q.device)
+        torch.cuda.current_stream(q.device).synchronize()      # the count was just zeroed on torch's stream
+        check(self._lib.sba_knn2_ratio(self._h, _ptr(q), nq, _ptr(t), nt, dim, ratio, _ptr(qi), _ptr(ti), _ptr(dd), _ptr(nm), None, None,
+                                       SBA_MEM_DEVICE, algo))
+        return MatchCall(self, (q, t), qi, ti, dd, nm)
+
     def gather_matches(self, key_left_xy, key_right_xy, query_idx, train_idx):
         n = int(query_idx.shape[0])
         ol = torch.empty((n, 2), dtype=torch.float32, device=key_left_xy.device)
@@ -354,6 +372,18 @@ class Context:
     # -- bundle adjustment
     def ba_problem(self, b1, b2, cam=None, n_cam: int = 1) -> "BAProblem":
         return BAProblem(self, b1, b2, cam, n_cam)
+
+
+class MatchCall:
+    """A match queued by ``Context.match_begin``; keeps its buffers alive until ``end``."""
+
+    def __init__(self, ctx, inputs, qi, ti, dd, nm):
+        self._ctx, self._inputs, self._qi, self._ti, self._dd, self._nm = ctx, inputs, qi, ti, dd, nm
+
+    def end(self) -> "MatchResult":
+        self._ctx.synchronize()
+        n = int(self._nm.item())
+        return MatchResult(self._qi[:n], self._ti[:n], self._dd[:n], None, None)
 
 
 class PairCall:
