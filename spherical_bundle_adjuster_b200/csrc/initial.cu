@@ -31,7 +31,7 @@ constexpr int ATA_ROWS_PER_CTA = 4096;
 constexpr int ATA_N = 45;   // upper triangle of the symmetric 9 x 9, row by row
 
 __global__ void __launch_bounds__(ATA_THREADS)
-eight_point_ata_kernel(const double* __restrict__ b1, const double* __restrict__ b2, const int32_t* __restrict__ idx, int sample_n, int n_chunks,
+eight_point_ata_kernel(const double* __restrict__ b1, const double* __restrict__ b2, int n, const int32_t* __restrict__ idx, int sample_n, int n_chunks,
                        double* __restrict__ partial /* [n_samples][n_chunks][45] */)
 {
     const int sample = blockIdx.x / n_chunks, chunk = blockIdx.x - sample * n_chunks;
@@ -42,6 +42,7 @@ eight_point_ata_kernel(const double* __restrict__ b1, const double* __restrict__
     for (int k = 0; k < ATA_N; k++) acc[k] = 0.0;
     for (int i = r0 + threadIdx.x; i < r1; i += ATA_THREADS) {
         const int32_t m = __ldg(rows + i);
+        if (m < 0 || m >= n) continue;   // an index outside the match list contributes nothing
         const double* l = b1 + 3 * (size_t)m;
         const double* r = b2 + 3 * (size_t)m;
         const double lx = l[0], ly = l[1], lz = l[2], rx = r[0], ry = r[1], rz = r[2];
@@ -255,7 +256,7 @@ static int ata_of_subsets(sba_ctx* c, const double* b1, const double* b2, int n,
     SBA_TRY(c->scratch[SCR_WORK1].ensure((size_t)n_samples * ATA_N * sizeof(double), st));
     double* d_partial = c->scratch[SCR_WORK0].as<double>();
     double* d_ata = c->scratch[SCR_WORK1].as<double>();
-    eight_point_ata_kernel<<<n_samples * n_chunks, ATA_THREADS, 0, st>>>(d_b1, d_b2, d_idx, sample_n, n_chunks, d_partial);
+    eight_point_ata_kernel<<<n_samples * n_chunks, ATA_THREADS, 0, st>>>(d_b1, d_b2, n, d_idx, sample_n, n_chunks, d_partial);
     SBA_LAUNCHED(c);
     eight_point_fold_kernel<<<(n_samples * ATA_N + 255) / 256, 256, 0, st>>>(d_partial, n_samples, n_chunks, d_ata);
     SBA_LAUNCHED(c);
