@@ -177,12 +177,9 @@ struct Partition {
 
 // ---- 1. prepare ------------------------------------------------------------------------------------------
 // 16 threads per row, 4 floats each.  Rows >= n are padding: zeros, norm = +inf (train) so they never win.
-__global__ void tc_prep_kernel(const float* __restrict__ x, int n, int n_pad, __nv_bfloat16* __restrict__ out, float* __restrict__ norm,
-                               float pad_norm, float* __restrict__ max_norm /* optional: running maximum of the finite norms */)
+__device__ __forceinline__ void prep_row(const float* __restrict__ x, int n, int row, int part, __nv_bfloat16* __restrict__ out, float* __restrict__ norm,
+                                         float pad_norm, float* __restrict__ max_norm)
 {
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int row = gid >> 4, part = gid & 15;
-    if (row >= n_pad) return;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (row < n) v = __ldg(reinterpret_cast<const float4*>(x + (size_t)row * DIM) + part);
     const float f[4] = {v.x, v.y, v.z, v.w};
@@ -204,6 +201,17 @@ __global__ void tc_prep_kernel(const float* __restrict__ x, int n, int n_pad, __
         norm[row] = row < n ? s : pad_norm;
         if (max_norm && row < n) atomicMax((int*)max_norm, __float_as_int(s));   // non-negative floats order like ints
     }
+}
+
+// Both descriptor sets in one launch: rows [0, nq_pad) are queries, the rest train rows.
+__global__ void tc_prep_kernel(const float* __restrict__ q, int nq, int nq_pad, __nv_bfloat16* __restrict__ outA, float* __restrict__ na,
+                               const float* __restrict__ t, int nt, int nt_pad, __nv_bfloat16* __restrict__ outB, float* __restrict__ nb,
+                               float* __restrict__ nb_max /* running maximum of the finite train norms */)
+{
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = gid >> 4, part = gid & 15;      // 16 threads per row, 4 floats each; a half-warp never straddles the two sets
+    if (row < nq_pad) prep_row(q, nq, row, part, outA, na, 0.f, nullptr);
+    else if (row < nq_pad + nt_pad) prep_row(t, nt, row - nq_pad, part, outB, nb, INFINITY, nb_max);
 }
 
 // ---- 2. the tensor-core kernel ---------------------------------------------------------------------------
@@ -801,9 +809,7 @@ int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, 
     float* d_dbg = (float*)(ws + o_misc + 8);
 
     SBA_CUDA(cudaMemsetAsync(ws + o_misc, 0, 64, st));
-    tc_prep_kernel<<<(nq_pad * 16 + 255) / 256, 256, 0, st>>>(d_q, nq, nq_pad, dA, d_na, 0.f, nullptr);
-    SBA_LAUNCHED(c);
-    tc_prep_kernel<<<(nt_pad * 16 + 255) / 256, 256, 0, st>>>(d_t, nt, nt_pad, dB, d_nb, INFINITY, d_nbmax);   // d_nbmax zeroed by the memset above
+    tc_prep_kernel<<<((nq_pad + nt_pad) * 16 + 255) / 256, 256, 0, st>>>(d_q, nq, nq_pad, dA, d_na, d_t, nt, nt_pad, dB, d_nb, d_nbmax);   // d_nbmax zeroed by the memset above
     SBA_LAUNCHED(c);
 
     CUtensorMap map_a, map_b;
