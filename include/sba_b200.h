@@ -145,6 +145,19 @@ typedef struct sba_match_stats {
 } sba_match_stats;
 int sba_match_last_stats(sba_ctx* ctx, sba_match_stats* out);
 
+/* A descriptor set that takes part in many matches (every frame of a sequence in all-pairs matching, the train set of
+ * a sharded sweep) can be handed over once: the fp32 rows are copied to the device and, for 64-d rows, split into the
+ * bf16 form the tensor-core kernel reads, so that step is not repeated per match.  The set is immutable and may be
+ * used by any context of the same device.  sba_knn2_ratio_prepared is sba_knn2_ratio on two such sets (outputs and
+ * `mem` as there; identical results). */
+typedef struct sba_descriptors sba_descriptors;
+int sba_descriptors_create(sba_ctx* ctx, const float* desc, int n, int dim, int mem, sba_descriptors** out);
+int sba_descriptors_destroy(sba_descriptors* d);
+int sba_descriptors_count(const sba_descriptors* d);
+int sba_knn2_ratio_prepared(sba_ctx* ctx, const sba_descriptors* query, const sba_descriptors* train, float ratio,
+                            int32_t* query_idx_out, int32_t* train_idx_out, float* dist_out, int32_t* n_matches_out,
+                            int32_t* knn_idx_out, float* knn_dist_out, int mem, int algo);
+
 /* Gather matched keypoints (equi2cube_surf.cpp:107-113): out_left[i] = key_left[query_idx[i]],
  * out_right[i] = key_right[train_idx[i]] on (x, y) float pairs. */
 int sba_gather_matches(sba_ctx* ctx, const float* key_left_xy, const float* key_right_xy, const int32_t* query_idx,

@@ -2,6 +2,6 @@
 descriptor matching (kNN k=2 + ratio test) and rotation-only spherical bundle adjustment, as
 hand-written sm_100a CUDA kernels behind the C ABI in ``include/sba_b200.h``."""
 from ._lib import MATCH_AUTO, MATCH_SIMT_EXACT, MATCH_TENSOR, SbaError  # noqa: F401
-from .api import BAProblem, Context, MatchResult, PeerComm  # noqa: F401
+from .api import BAProblem, Context, Descriptors, MatchResult, PeerComm  # noqa: F401
 
-__all__ = ["Context", "BAProblem", "MatchResult", "PeerComm", "SbaError", "MATCH_AUTO", "MATCH_SIMT_EXACT", "MATCH_TENSOR"]
+__all__ = ["Context", "BAProblem", "Descriptors", "MatchResult", "PeerComm", "SbaError", "MATCH_AUTO", "MATCH_SIMT_EXACT", "MATCH_TENSOR"]

@@ -25,6 +25,7 @@ EXPORTED = [
     "sba_eular2rot", "sba_crop_rotated_lut", "sba_crop_rotated_image", "sba_spherical_crops", "sba_rotate_pixels", "sba_rotate_pixels_mat", "sba_rotate_keypoints",
     "sba_pair_rotation_begin", "sba_pair_rotation_end", "sba_eight_point_null", "sba_essential_to_candidates", "sba_initial_guess",
     "sba_ctx_set_remap_kernel", "sba_remap_plan_info",
+    "sba_descriptors_create", "sba_descriptors_destroy", "sba_descriptors_count", "sba_knn2_ratio_prepared",
 ]
 
 
@@ -106,6 +107,10 @@ def load():
     lib.sba_ba_rot_eval_timed.argtypes = [vp, vp, vp, f64, f64, f64, i32, i32, C.POINTER(f32)]
     lib.sba_pair_rotation.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, vp, i32, i32, vp, vp, f32, vp, vp, f64, f64, f64, i32,
                                       vp, vp, vp, C.POINTER(PairResult), i32]
+    lib.sba_descriptors_create.argtypes = [vp, vp, i32, i32, i32, C.POINTER(vp)]
+    lib.sba_descriptors_destroy.argtypes = [vp]
+    lib.sba_descriptors_count.argtypes = [vp]
+    lib.sba_knn2_ratio_prepared.argtypes = [vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, i32, i32]
     lib.sba_ctx_set_remap_kernel.argtypes = [vp, i32]
     lib.sba_remap_plan_info.argtypes = [vp, i32, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(f32 * 4)]
     lib.sba_eight_point_null.argtypes = [vp, vp, vp, i32, vp, i32, i32, vp, vp, i32]

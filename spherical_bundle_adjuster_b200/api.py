@@ -268,6 +268,15 @@ class Context:
     # -- feature_matcher.hpp:34
     def match_two_image(self, desc1, desc2, ratio: float = 0.3, algo: int = MATCH_AUTO, want_knn: bool = False) -> MatchResult:
         """``feature_matcher::match_two_image``: kNN(k=2) + ratio test, survivors in query order."""
+        if isinstance(desc1, Descriptors) and isinstance(desc2, Descriptors):
+            nq = len(desc1)
+            qi, ti, dd = np.empty(max(nq, 1), np.int32), np.empty(max(nq, 1), np.int32), np.empty(max(nq, 1), np.float32)
+            ki = np.empty((nq, 2), np.int32) if want_knn else None
+            kd = np.empty((nq, 2), np.float32) if want_knn else None
+            nm = C.c_int32(0)
+            check(self._lib.sba_knn2_ratio_prepared(self._h, desc1._h, desc2._h, ratio, _ptr(qi), _ptr(ti), _ptr(dd), C.cast(C.byref(nm), C.c_void_p),
+                                                    _ptr(ki), _ptr(kd), SBA_MEM_HOST, algo))
+            return MatchResult(qi[:nm.value], ti[:nm.value], dd[:nm.value], ki, kd)
         f32t = torch.float32 if torch else None
         i32t = torch.int32 if torch else None
         q = _as(desc1, np.float32, f32t)
@@ -298,22 +307,35 @@ class Context:
         check(self._lib.sba_match_last_stats(self._h, C.byref(s)))
         return s
 
+    def prepare_descriptors(self, desc) -> "Descriptors":
+        """Hand a descriptor set over once (``sba_descriptors_create``); pass the result to match_two_image / match_begin
+        in place of the array for every match it takes part in."""
+        return Descriptors(self, desc)
+
     def match_begin(self, desc1, desc2, ratio: float = 0.3, algo: int = MATCH_AUTO) -> "MatchCall":
         """Queue ``match_two_image`` on CUDA tensors and return at once (nothing is copied to the host);
         ``.end()`` waits for this context's stream and returns the MatchResult.  Several contexts on their own
         streams keep several image pairs in flight (all-pairs matching of a sequence, BASELINE config 3)."""
-        q = _as(desc1, np.float32, torch.float32)
-        t = _as(desc2, np.float32, torch.float32)
-        if _mem_of(q, t) != SBA_MEM_DEVICE:
-            raise SbaError("match_begin takes CUDA tensors")
-        nq, nt, dim = q.shape[0], t.shape[0], q.shape[1]
-        qi = torch.empty(max(nq, 1), dtype=torch.int32, device=q.device)
-        ti = torch.empty(max(nq, 1), dtype=torch.int32, device=q.device)
-        dd = torch.empty(max(nq, 1), dtype=torch.float32, device=q.device)
-        nm = torch.zeros(1, dtype=torch.int32, device=q.device)
-        torch.cuda.current_stream(q.device).synchronize()      # the count was just zeroed on torch's stream
-        check(self._lib.sba_knn2_ratio(self._h, _ptr(q), nq, _ptr(t), nt, dim, ratio, _ptr(qi), _ptr(ti), _ptr(dd), _ptr(nm), None, None,
-                                       SBA_MEM_DEVICE, algo))
+        prepared = isinstance(desc1, Descriptors) and isinstance(desc2, Descriptors)
+        if prepared:
+            q, t, nq = desc1, desc2, len(desc1)
+            dev = torch.device("cuda", self.device)
+        else:
+            q = _as(desc1, np.float32, torch.float32)
+            t = _as(desc2, np.float32, torch.float32)
+            if _mem_of(q, t) != SBA_MEM_DEVICE:
+                raise SbaError("match_begin takes CUDA tensors or prepared descriptor sets")
+            nq, nt, dim, dev = q.shape[0], t.shape[0], q.shape[1], q.device
+        qi = torch.empty(max(nq, 1), dtype=torch.int32, device=dev)
+        ti = torch.empty(max(nq, 1), dtype=torch.int32, device=dev)
+        dd = torch.empty(max(nq, 1), dtype=torch.float32, device=dev)
+        nm = torch.zeros(1, dtype=torch.int32, device=dev)
+        torch.cuda.current_stream(dev).synchronize()      # the count was just zeroed on torch's stream
+        if prepared:
+            check(self._lib.sba_knn2_ratio_prepared(self._h, q._h, t._h, ratio, _ptr(qi), _ptr(ti), _ptr(dd), _ptr(nm), None, None, SBA_MEM_DEVICE, algo))
+        else:
+            check(self._lib.sba_knn2_ratio(self._h, _ptr(q), nq, _ptr(t), nt, dim, ratio, _ptr(qi), _ptr(ti), _ptr(dd), _ptr(nm), None, None,
+                                           SBA_MEM_DEVICE, algo))
         return MatchCall(self, (q, t), qi, ti, dd, nm)
 
     def gather_matches(self, key_left_xy, key_right_xy, query_idx, train_idx):
@@ -372,6 +394,30 @@ class Context:
     # -- bundle adjustment
     def ba_problem(self, b1, b2, cam=None, n_cam: int = 1) -> "BAProblem":
         return BAProblem(self, b1, b2, cam, n_cam)
+
+
+class Descriptors:
+    """A descriptor set resident on the device in the matcher's prepared form (wraps ``sba_descriptors``)."""
+
+    def __init__(self, ctx: "Context", desc):
+        self._lib = ctx._lib
+        self._h = C.c_void_p()
+        d = _as(desc, np.float32, torch.float32 if torch else None)
+        check(self._lib.sba_descriptors_create(ctx._h, _ptr(d), d.shape[0], d.shape[1] if d.ndim == 2 else 64, _mem_of(d), C.byref(self._h)))
+
+    def __len__(self):
+        return int(self._lib.sba_descriptors_count(self._h))
+
+    def close(self):
+        if self._h:
+            self._lib.sba_descriptors_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class MatchCall:

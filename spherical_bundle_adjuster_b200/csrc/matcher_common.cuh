@@ -1,5 +1,6 @@
 // matcher_common.cuh -- pieces shared by the exact SIMT matcher and the tensor-core matcher.
 #pragma once
+#include <cuda_bf16.h>
 #include <climits>
 
 #include "common.cuh"
@@ -77,6 +78,16 @@ __device__ inline float l2sqr_opencv(const float* __restrict__ a, const float* _
     }
     return __fadd_rn(__fadd_rn(s[0], s[2]), __fadd_rn(s[1], s[3]));
 }
+
+// A descriptor set prepared once for the tensor-core matcher (bf16 hi/lo rows, norms, largest norm) -- see
+// sba_descriptors_create.  n_pad is a multiple of 256 (serves as query block and as train tiles), pad norms are +inf.
+struct PreparedSet {
+    const float* raw;               // fp32 rows on the device [n x dim]
+    const __nv_bfloat16* prep;      // [n_pad x 128] or NULL when dim != 64
+    const float* norm;              // [n_pad]
+    const float* max_norm;          // device scalar
+    int n, n_pad, dim;
+};
 
 // Runs after either matcher: per-query top-2 -> optional raw kNN output + ratio-test flags.
 int launch_knn_finish(sba_ctx* c, const Top2* d_top2, int nq, float ratio, int32_t* d_query_idx, int32_t* d_train_idx, float* d_dist,

@@ -295,7 +295,8 @@ static int run_simt(sba_ctx* c, const float* d_q, int nq, const float* d_t, int 
 }
 
 // defined in matcher_tc.cu
-int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, int dim, Top2* d_top);
+int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, int dim, Top2* d_top, const PreparedSet* pq, const PreparedSet* pt);
+int knn2_prepare_set(sba_ctx* c, const float* d_raw, int n, int n_pad, __nv_bfloat16* prep, float* norm, float* max_norm);
 bool knn2_tensor_applicable(int nq, int nt, int dim);
 bool knn2_tensor_preferred(int nq, int nt, int dim);
 
@@ -309,10 +310,22 @@ __global__ void fill_empty_top2_kernel(Top2* top, int nq)
 
 using namespace sba;
 
+// A descriptor set kept on the device in both forms (sba_descriptors_create).
+struct sba_descriptors {
+    int device = 0;
+    float* raw = nullptr;
+    __nv_bfloat16* prep = nullptr;
+    float* norm = nullptr;          // [n_pad] + the maximum in the last slot
+    sba::PreparedSet set{};
+};
+
 extern "C" {
 
-int sba_knn2_ratio(sba_ctx* c, const float* q, int nq, const float* t, int nt, int dim, float ratio, int32_t* query_idx, int32_t* train_idx,
-                   float* dist, int32_t* n_matches, int32_t* knn_idx, float* knn_dist, int mem, int algo)
+// Shared by the two entry points: q/t are fp32 rows where `mem` says, unless the side comes prepared (then its rows
+// already live on the device).
+static int knn2_ratio_impl(sba_ctx* c, const float* q, int nq, const float* t, int nt, int dim, float ratio, int32_t* query_idx, int32_t* train_idx,
+                           float* dist, int32_t* n_matches, int32_t* knn_idx, float* knn_dist, int mem, int algo, const PreparedSet* pq,
+                           const PreparedSet* pt)
 {
     SBA_CHECK_ARG(c && nq >= 0 && nt >= 0 && n_matches);
     SBA_CHECK_ARG(nq == 0 || (q && query_idx && train_idx && dist));
@@ -329,9 +342,9 @@ int sba_knn2_ratio(sba_ctx* c, const float* q, int nq, const float* t, int nt, i
         else SBA_CUDA(cudaMemsetAsync(n_matches, 0, sizeof(int32_t), st));
         return finish(c, mem);
     }
-    const float *d_q, *d_t;
-    SBA_TRY(stage_in(c, q, (size_t)nq * dim, mem, SCR_IN0, &d_q));
-    SBA_TRY(stage_in(c, t, (size_t)nt * dim, mem, SCR_IN1, &d_t));
+    const float *d_q = q, *d_t = t;
+    if (!pq) SBA_TRY(stage_in(c, q, (size_t)nq * dim, mem, SCR_IN0, &d_q));
+    if (!pt) SBA_TRY(stage_in(c, t, (size_t)nt * dim, mem, SCR_IN1, &d_t));
     int32_t *d_qi, *d_ti, *d_n, *d_ki;
     float *d_d, *d_kd;
     SBA_TRY(stage_out(c, query_idx, (size_t)nq, mem, SCR_OUT0, &d_qi));
@@ -358,7 +371,7 @@ int sba_knn2_ratio(sba_ctx* c, const float* q, int nq, const float* t, int nt, i
             set_error("tensor-core matcher does not apply to nq=%d nt=%d dim=%d", nq, nt, dim);
             return SBA_ERR_UNSUPPORTED;
         }
-        SBA_TRY(knn2_tensor(c, d_q, nq, d_t, nt, dim, d_top));
+        SBA_TRY(knn2_tensor(c, d_q, nq, d_t, nt, dim, d_top, (pq && pq->prep) ? pq : nullptr, (pt && pt->prep) ? pt : nullptr));
     } else {
         use = SBA_MATCH_SIMT_EXACT;
         if (dim == 64) SBA_TRY(run_simt<64>(c, d_q, nq, d_t, nt, d_top));
@@ -378,6 +391,71 @@ int sba_knn2_ratio(sba_ctx* c, const float* q, int nq, const float* t, int nt, i
         SBA_TRY(copy_out(c, knn_dist, d_kd, (size_t)2 * nq, mem));
     }
     return finish(c, mem);
+}
+
+int sba_knn2_ratio(sba_ctx* c, const float* q, int nq, const float* t, int nt, int dim, float ratio, int32_t* query_idx, int32_t* train_idx,
+                   float* dist, int32_t* n_matches, int32_t* knn_idx, float* knn_dist, int mem, int algo)
+{
+    return knn2_ratio_impl(c, q, nq, t, nt, dim, ratio, query_idx, train_idx, dist, n_matches, knn_idx, knn_dist, mem, algo, nullptr, nullptr);
+}
+
+int sba_descriptors_create(sba_ctx* c, const float* desc, int n, int dim, int mem, sba_descriptors** out)
+{
+    SBA_CHECK_ARG(c && out && n >= 0 && (n == 0 || desc));
+    *out = nullptr;
+    if (dim != 64 && dim != 128) {
+        set_error("descriptor dimension %d not supported (SURF: 64 or 128)", dim);
+        return SBA_ERR_UNSUPPORTED;
+    }
+    SBA_CUDA(cudaSetDevice(c->device));
+    sba_descriptors* d = new sba_descriptors();
+    d->device = c->device;
+    d->set.n = n; d->set.dim = dim; d->set.n_pad = (n + 255) / 256 * 256;
+    auto fail = [&](cudaError_t e) { set_error("%s", cudaGetErrorString(e)); sba_descriptors_destroy(d); return SBA_ERR_CUDA; };
+    cudaError_t e;
+    const size_t raw_bytes = (size_t)std::max(n, 1) * dim * sizeof(float);
+    if ((e = cudaMalloc(&d->raw, raw_bytes)) != cudaSuccess) return fail(e);
+    if (n > 0 && (e = cudaMemcpyAsync(d->raw, desc, (size_t)n * dim * sizeof(float), mem == SBA_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
+                                      c->stream)) != cudaSuccess)
+        return fail(e);
+    d->set.raw = d->raw;
+    if (dim == 64 && n > 0) {
+        if ((e = cudaMalloc(&d->prep, (size_t)d->set.n_pad * 128 * sizeof(__nv_bfloat16))) != cudaSuccess) return fail(e);
+        if ((e = cudaMalloc(&d->norm, (size_t)d->set.n_pad * sizeof(float) + sizeof(float))) != cudaSuccess) return fail(e);
+        float* max_norm = d->norm + d->set.n_pad;
+        int rc = knn2_prepare_set(c, d->raw, n, d->set.n_pad, d->prep, d->norm, max_norm);
+        if (rc != SBA_OK) { sba_descriptors_destroy(d); return rc; }
+        d->set.prep = d->prep; d->set.norm = d->norm; d->set.max_norm = max_norm;
+    }
+    if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return fail(e);   // usable from any context / stream of this device from here on
+    *out = d;
+    return SBA_OK;
+}
+
+int sba_descriptors_destroy(sba_descriptors* d)
+{
+    if (!d) return SBA_OK;
+    cudaSetDevice(d->device);
+    cudaDeviceSynchronize();          // a match that reads the set may still be queued on some stream
+    if (d->raw) cudaFree(d->raw);
+    if (d->prep) cudaFree(d->prep);
+    if (d->norm) cudaFree(d->norm);
+    delete d;
+    return SBA_OK;
+}
+
+int sba_descriptors_count(const sba_descriptors* d) { return d ? d->set.n : 0; }
+
+int sba_knn2_ratio_prepared(sba_ctx* c, const sba_descriptors* query, const sba_descriptors* train, float ratio, int32_t* query_idx,
+                            int32_t* train_idx, float* dist, int32_t* n_matches, int32_t* knn_idx, float* knn_dist, int mem, int algo)
+{
+    SBA_CHECK_ARG(c && query && train);
+    if (query->set.dim != train->set.dim || query->device != c->device || train->device != c->device) {
+        set_error("prepared descriptor sets must share the dimension and live on the context's device");
+        return SBA_ERR_INVALID;
+    }
+    return knn2_ratio_impl(c, query->set.raw, query->set.n, train->set.raw, train->set.n, query->set.dim, ratio, query_idx, train_idx, dist,
+                           n_matches, knn_idx, knn_dist, mem, algo, &query->set, &train->set);
 }
 
 int sba_match_last_stats(sba_ctx* c, sba_match_stats* out)

@@ -762,7 +762,20 @@ bool knn2_tensor_applicable(int nq, int nt, int dim) { return dim == tc::DIM && 
 // Heuristic used by SBA_MATCH_AUTO: below ~1M pair distances the exact SIMT kernel's latency wins.
 bool knn2_tensor_preferred(int nq, int nt, int dim) { return dim == tc::DIM && (long long)nq * nt >= (1ll << 20) && nt >= 1024; }
 
-int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, int dim, Top2* d_top)
+// The bf16 split of one descriptor set into caller-owned buffers (sba_descriptors_create): prep [n_pad x 128],
+// norm [n_pad] with +inf on the padding rows, *max_norm = largest finite norm.
+int knn2_prepare_set(sba_ctx* c, const float* d_raw, int n, int n_pad, __nv_bfloat16* prep, float* norm, float* max_norm)
+{
+    using namespace tc;
+    SBA_CUDA(cudaMemsetAsync(max_norm, 0, sizeof(float), c->stream));
+    tc_prep_kernel<<<(n_pad * 16 + 255) / 256, 256, 0, c->stream>>>(nullptr, 0, 0, nullptr, nullptr, d_raw, n, n_pad, prep, norm, max_norm);
+    SBA_LAUNCHED(c);
+    SBA_CUDA(cudaGetLastError());
+    return SBA_OK;
+}
+
+// pq / pt: optional prepared forms of the query / train set (then the bf16 split of that side is not redone)
+int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, int dim, Top2* d_top, const PreparedSet* pq, const PreparedSet* pt)
 {
     using namespace tc;
     if (dim != DIM) {
@@ -771,7 +784,7 @@ int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, 
     }
     cudaStream_t st = c->stream;
     const int nqb = (nq + BM - 1) / BM, ntb = (nt + BN - 1) / BN;
-    const int nq_pad = nqb * BM, nt_pad = ntb * BN;
+    const int nq_pad = pq ? pq->n_pad : nqb * BM, nt_pad = pt ? pt->n_pad : ntb * BN;
     Partition part;
     part.nqb = nqb; part.ntb = ntb; part.T = (long long)nqb * ntb;
     part.n_ctas = (int)std::min<long long>(c->sm_count, part.T);
@@ -796,25 +809,30 @@ int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, 
     const size_t o_misc = off; off = align_up(off + 64);
     SBA_TRY(c->scratch[SCR_WORK2].ensure(off, st));
     uint8_t* ws = c->scratch[SCR_WORK2].as<uint8_t>();
-    __nv_bfloat16* dA = (__nv_bfloat16*)(ws + o_a);
-    __nv_bfloat16* dB = (__nv_bfloat16*)(ws + o_b);
-    float* d_na = (float*)(ws + o_na);
-    float* d_nb = (float*)(ws + o_nb);
+    const __nv_bfloat16* dA = pq ? pq->prep : (const __nv_bfloat16*)(ws + o_a);
+    const __nv_bfloat16* dB = pt ? pt->prep : (const __nv_bfloat16*)(ws + o_b);
+    const float* d_na = pq ? pq->norm : (const float*)(ws + o_na);
+    const float* d_nb = pt ? pt->norm : (const float*)(ws + o_nb);
     float4* d_cv = (float4*)(ws + o_cv);
     int4* d_ci = (int4*)(ws + o_ci);
     int* d_fl = (int*)(ws + o_fl);
     Top2* d_fparts = (Top2*)(ws + o_fp);
     int* d_fb_count = (int*)(ws + o_misc);
-    float* d_nbmax = (float*)(ws + o_misc + 4);
+    const float* d_nbmax = pt ? pt->max_norm : (const float*)(ws + o_misc + 4);
     float* d_dbg = (float*)(ws + o_misc + 8);
 
     SBA_CUDA(cudaMemsetAsync(ws + o_misc, 0, 64, st));
-    tc_prep_kernel<<<((nq_pad + nt_pad) * 16 + 255) / 256, 256, 0, st>>>(d_q, nq, nq_pad, dA, d_na, d_t, nt, nt_pad, dB, d_nb, d_nbmax);   // d_nbmax zeroed by the memset above
-    SBA_LAUNCHED(c);
+    if (!pq || !pt) {   // split whichever side arrives as plain fp32 rows (a side that is prepared counts zero rows here)
+        const int rows_a = pq ? 0 : nq_pad, rows_b = pt ? 0 : nt_pad;
+        tc_prep_kernel<<<((rows_a + rows_b) * 16 + 255) / 256, 256, 0, st>>>(d_q, nq, rows_a, (__nv_bfloat16*)(ws + o_a), (float*)(ws + o_na), d_t, nt, rows_b,
+                                                                            (__nv_bfloat16*)(ws + o_b), (float*)(ws + o_nb),
+                                                                            (float*)(ws + o_misc + 4));   // the maximum was zeroed by the memset above
+        SBA_LAUNCHED(c);
+    }
 
     CUtensorMap map_a, map_b;
-    SBA_TRY(make_map(&map_a, dA, nq_pad, BM));
-    SBA_TRY(make_map(&map_b, dB, nt_pad, BN));
+    SBA_TRY(make_map(&map_a, (void*)dA, nq_pad, BM));
+    SBA_TRY(make_map(&map_b, (void*)dB, nt_pad, BN));
     SBA_CUDA(cudaFuncSetAttribute(tc_knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     prof_begin(c, SBA_KERNEL_MATCH);
     tc_knn_kernel<<<part.n_ctas, THREADS, SMEM_BYTES, st>>>(map_a, map_b, d_nb, part, d_cv, d_ci, slots);

@@ -12,6 +12,7 @@ from spherical_bundle_adjuster_b200 import Context, sharding
 F = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
 K = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+PREP = int(sys.argv[4]) if len(sys.argv) > 4 else 1     # 1: every frame handed over once (sba_descriptors_create), 0: raw tensors per match
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -27,6 +28,8 @@ for f in range(F):     # every frame: the same scene descriptors, shuffled and p
 pairs = sharding.shard_pairs(F, rank, world)
 streams = [torch.cuda.Stream(dev) for _ in range(K)]
 ctxs = [Context(local, stream=s.cuda_stream) for s in streams]
+if PREP:
+    frames = [ctxs[f % K].prepare_descriptors(d) for f, d in enumerate(frames)]
 for c in ctxs:   # warm-up: scratch buffers of every context
     c.match_begin(frames[0], frames[1]).end()
 torch.cuda.synchronize()
@@ -54,6 +57,6 @@ if rank == 0:
     total = int(t[1])
     print(json.dumps({"workload": f"C3: {F} frames x {N} SURF-64 descriptors, all {F * (F - 1) // 2} pairs", "n_gpus": world, "pairs": total,
                       "ms_total": ms, "pairs_per_s": total / (ms * 1e-3), "ms_per_pair_per_gpu": ms * world / total if total else None,
-                      "contexts_in_flight": K, "matches_total": int(t[2]), "algorithmic_tflops": 2.0 * 64 * N * N * total / (ms * 1e-3) / 1e12}))
+                      "contexts_in_flight": K, "prepared_sets": bool(PREP), "matches_total": int(t[2]), "algorithmic_tflops": 2.0 * 64 * N * N * total / (ms * 1e-3) / 1e12}))
 if world > 1:
     dist.destroy_process_group()
