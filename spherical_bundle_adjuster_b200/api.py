@@ -630,10 +630,17 @@ class BAProblem:
 
     def solve_problem(self, r0, t0, d0, huber=1.0, max_iter=50):
         """spherical_bundle_adjuster::solve_problem (:183-217): depth -> rotation -> translation.
-        Returns (r [3], t [3], d [n, 2], [summary_d, summary_rot, summary_tran])."""
-        r, t, d = self._r(r0, 1).reshape(3).copy(), np.ascontiguousarray(t0, np.float64).reshape(3).copy(), self._d(d0).copy()
+        Returns (r [3], t [3], d [n, 2], [summary_d, summary_rot, summary_tran]); d0 may be a CUDA tensor (stays on the device)."""
+        r, t = self._r(r0, 1).reshape(3).copy(), np.ascontiguousarray(t0, np.float64).reshape(3).copy()
+        if _is_tensor(d0) and d0.is_cuda:
+            d = d0.to(torch.float64).reshape(-1, 2).contiguous().clone()
+            if d.shape[0] != self.n_obs:
+                raise ValueError(f"expected {self.n_obs} depth pairs, got {d.shape[0]}")
+            mem = SBA_MEM_DEVICE
+        else:
+            d, mem = self._d(d0).copy(), SBA_MEM_HOST
         sums = (_lib.SolveSummary * 3)()
-        check(self._lib.sba_ba_solve_problem(self._h, _ptr(r), _ptr(t), _ptr(d), huber, max_iter, C.byref(sums), SBA_MEM_HOST))
+        check(self._lib.sba_ba_solve_problem(self._h, _ptr(r), _ptr(t), _ptr(d), huber, max_iter, C.byref(sums), mem))
         return r, t, d, list(sums)
 
     def eval_timed(self, r, t=(0.0, 0.0, 0.0), d1=1.0, d2=1.0, huber=1.0, materialise=False, iters=20) -> float:

@@ -107,3 +107,18 @@ def test_depth_rejects_multi_camera(ctx):
     prob = ctx.ba_problem(b1.astype(np.float32), b2.astype(np.float32), cam, 2)
     with pytest.raises(Exception):
         prob.d_solve(np.zeros(3), np.zeros(3), np.ones((64, 2)))
+
+
+def test_depth_and_three_stage_solve_with_device_buffers(ctx):
+    """The depth table may live on the device (SBA_MEM_DEVICE): same results as with host buffers."""
+    import torch
+    n = 4000
+    prob, b1, b2, r_true, t_true, _ = _problem(ctx, n, seed=21)
+    r0, t0 = r_true + np.array([0.01, 0.02, -0.01]), t_true + np.array([-0.02, 0.01, 0.02])
+    d0 = np.full((n, 2), 1.0)
+    d_h, s_h, _ = prob.d_solve(r0, t0, d0)
+    d_d, s_d, _ = prob.d_solve(r0, t0, torch.from_numpy(d0).cuda())
+    assert d_d.is_cuda and np.array_equal(d_d.cpu().numpy(), d_h) and s_d.iterations == s_h.iterations
+    rh, th, dh, _ = prob.solve_problem(r0, t0, d0)
+    rd, td, dd, _ = prob.solve_problem(r0, t0, torch.from_numpy(d0).cuda())
+    assert np.array_equal(rh, rd) and np.array_equal(th, td) and np.array_equal(dd.cpu().numpy(), dh)
