@@ -37,6 +37,7 @@ sys.path.insert(0, ROOT)
 W, H, CS, NKP, DIM = 3840, 1920, 960, 16384, 64
 RATIO = 0.3
 IN_FLIGHT = int(os.environ.get("SBA_BENCH_IN_FLIGHT", "6"))   # library contexts (streams + host threads) per GPU
+MATCHER_CTAS = int(os.environ.get("SBA_BENCH_MATCHER_CTAS", "0"))   # 0 = one persistent matcher CTA per SM
 POOL = 6  # distinct pairs resident in HBM and cycled through: 6 x 52.7 MB = 316 MB >> 126 MB L2
 
 
@@ -188,6 +189,9 @@ def bench_ours(args):
     # queued through sba_pair_rotation_begin / _end.  Pairs are independent.
     streams = [torch.cuda.Stream(dev) for _ in range(IN_FLIGHT)]
     ctxs = [Context(local_rank, stream=st.cuda_stream) for st in streams]
+    if MATCHER_CTAS:
+        for c in ctxs:
+            c.set_matcher_ctas(MATCHER_CTAS)
     runners = [PairRunner(c) for c in ctxs]
     ctx, runner = ctxs[0], runners[0]
     peaks = _peaks()

@@ -96,6 +96,9 @@ int sba_equi2cube_face(sba_ctx* ctx, const uint8_t* erp, int w, int h, int cube_
  * sba_remap_plan_info reports what the trials of a cube plan found: tiled_preferred bit 0 = small batches, bit 1 = large;
  * trial_ms = {small direct, small tiled, large direct, large tiled}. */
 int sba_ctx_set_remap_kernel(sba_ctx* ctx, int mode);
+/* Persistent CTAs of the tensor-core matcher (one per SM by default; 0 restores that).  With several pairs in flight on
+ * one GPU, half the SMs per match lets two matches run side by side on longer spans. */
+int sba_ctx_set_matcher_ctas(sba_ctx* ctx, int n_ctas);
 int sba_remap_plan_info(sba_ctx* ctx, int w, int h, int cube_size, int* tiled_available, int* tiled_preferred, int* n_tiles,
                         int* n_fallback_tiles, float trial_ms[4]);
 int sba_equi2cube_lut(sba_ctx* ctx, int w, int h, int cube_size, int32_t* lut_out, int mem);

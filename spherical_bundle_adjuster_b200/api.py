@@ -117,6 +117,10 @@ class Context:
     def launch_count(self) -> int:
         return int(self._lib.sba_ctx_launch_count(self._h))
 
+    def set_matcher_ctas(self, n_ctas: int):
+        """Persistent CTAs of the tensor-core matcher (0 = one per SM)."""
+        check(self._lib.sba_ctx_set_matcher_ctas(self._h, int(n_ctas)))
+
     def set_remap_kernel(self, mode: int):
         """0 = per-plan choice from the timed trial, 1 = direct gather, 2 = tiled gather wherever possible."""
         check(self._lib.sba_ctx_set_remap_kernel(self._h, int(mode)))

@@ -174,6 +174,7 @@ struct sba_ctx {
     std::map<std::pair<int, int>, int32_t*> band_plans;                  // the four bands of spherical_surf::do_all in one table
     std::map<std::pair<int, int>, sba::TiledPlan> band_tiled;             // ... and its tiled form
     sba_match_stats match_stats{};
+    int matcher_ctas = 0;       // persistent CTAs of the tensor-core matcher; 0 = one per SM (sba_ctx_set_matcher_ctas)
     int remap_kernel = 0;       // 0 = per-plan choice from the timed trial, 1 = direct gather, 2 = tiled gather (sba_ctx_set_remap_kernel)
     bool pair_pending = false;  // a sba_pair_rotation_begin whose _end has not run yet (pipeline.cu)
     int* pinned_i32 = nullptr;  // small pinned host mailbox (64 ints) for scalar read-backs

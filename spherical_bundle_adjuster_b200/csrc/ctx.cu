@@ -99,6 +99,13 @@ int sba_ctx_destroy(sba_ctx* c)
     return SBA_OK;
 }
 
+int sba_ctx_set_matcher_ctas(sba_ctx* c, int n_ctas)
+{
+    SBA_CHECK_ARG(c && n_ctas >= 0);
+    c->matcher_ctas = n_ctas;
+    return SBA_OK;
+}
+
 int sba_ctx_set_stream(sba_ctx* c, void* stream)
 {
     SBA_CHECK_ARG(c != nullptr);

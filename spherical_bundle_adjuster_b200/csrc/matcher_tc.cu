@@ -787,7 +787,7 @@ int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, 
     const int nq_pad = pq ? pq->n_pad : nqb * BM, nt_pad = pt ? pt->n_pad : ntb * BN;
     Partition part;
     part.nqb = nqb; part.ntb = ntb; part.T = (long long)nqb * ntb;
-    part.n_ctas = (int)std::min<long long>(c->sm_count, part.T);
+    part.n_ctas = (int)std::min<long long>(c->matcher_ctas > 0 ? std::min(c->matcher_ctas, c->sm_count) : c->sm_count, part.T);
     // measured with the trace build at 16k x 16k: spans that cross into a new query block finish ~8 us (5-6 tiles) late;
     // capped so that no span can come out empty
     part.bcost = (int)std::min<long long>(5, part.T / part.n_ctas / 4);

@@ -123,3 +123,18 @@ def test_matcher_full_size_properties(ctx):
     rows = np.random.default_rng(0).choice(16384, 256, replace=False)
     idx, dist = oracle.knn2_l2(A[rows], B)
     assert np.array_equal(ms.knn_idx[rows], idx) and np.array_equal(ms.knn_dist[rows].view(np.uint32), dist.view(np.uint32))
+
+
+@pytest.mark.parametrize("n_ctas", [1, 37, 74])
+def test_tensor_path_with_fewer_persistent_ctas(ctx, n_ctas):
+    """sba_ctx_set_matcher_ctas: the span partition changes, the result does not."""
+    A, B, _ = synth.make_descriptors(3000, 5000, 64, seed=77)
+    want = oracle.match_two_image(A, B, 0.3)
+    ctx.set_matcher_ctas(n_ctas)
+    try:
+        m = ctx.match_two_image(A, B, 0.3, algo=MATCH_TENSOR)
+        assert ctx.match_stats().n_ctas == n_ctas
+    finally:
+        ctx.set_matcher_ctas(0)
+    assert np.array_equal(m.query_idx, want[0]) and np.array_equal(m.train_idx, want[1])
+    assert np.array_equal(m.distance.view(np.uint32), want[2].view(np.uint32))
