@@ -23,6 +23,7 @@ rank runs the same number of pairs per step).
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -214,6 +215,8 @@ def bench_ours(args):
         """Exactly `steps` pairs, step k on context k % IN_FLIGHT: a pair's result is collected only when its context
         is needed again, so up to IN_FLIGHT pairs are queued at any time (one host thread, no extra copies).
         Device time from the start event to the last end event of any stream.  Returns (ms, result of the last pair)."""
+        gc.collect()
+        gc.disable()          # a collector pause inside a ~40 ms window would show up as a missing pair or two
         barrier()
         start = torch.cuda.Event(enable_timing=True)
         ends = [torch.cuda.Event(enable_timing=True) for _ in range(IN_FLIGHT)]
@@ -230,6 +233,7 @@ def bench_ours(args):
                 out = runners[j].collect(pending[j])
             ends[j].record(streams[j])
         barrier()
+        gc.enable()
         return max(start.elapsed_time(e) for e in ends), out
 
     # ---- warm-up: builds the remap plan, sizes the scratch buffers of every context and lets the library see
