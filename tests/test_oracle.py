@@ -303,3 +303,42 @@ def test_initial_guess_oracle_pinned_to_opencv():
     assert win < 30
     R, T, best, c = oracle.initial_guess(b1, b2, idx)
     assert best >= 0 and len(c) >= len(idx)
+
+
+def test_spherical_surf_geometry_properties():
+    """Size-independent properties of the pitched-band mapping (spherical_surf.cpp:48-109)."""
+    rng = np.random.default_rng(7)
+    for (w, h) in ((512, 256), (1000, 500), (3840, 1920)):
+        for pitch in (45.0, -45.0, -90.0, 17.5):
+            lut = oracle.crop_rotated_lut(pitch, w, h)
+            assert lut.shape == (h // 4, w) and lut.max() < w * h and lut.min() >= -1
+            # rotating by the pitch and back lands within a pixel (two truncations) of where it started, modulo the
+            # azimuth wrap -- away from the poles, where a column step is a large angle
+            rc = np.stack([rng.integers(h * 3 // 8, h * 5 // 8, 300), rng.integers(0, w, 300)], axis=1).astype(np.int32)
+            fwd = oracle.rotate_pixels(rc, pitch, w, h)
+            ok = (fwd[:, 0] > h // 8) & (fwd[:, 0] < h * 7 // 8)
+            back = oracle.rotate_pixels(fwd[ok], -pitch, w, h)
+            dr = np.abs(back[:, 0] - rc[ok, 0])
+            dc = np.abs(back[:, 1] - rc[ok, 1]); dc = np.minimum(dc, w - dc)
+            assert dr.max() <= 2 and dc.max() <= 3, (w, h, pitch, dr.max(), dc.max())
+        # pitch 0 is the identity on the band up to the truncation of the round trip through radians (which is why the
+        # reference takes the plain ROI for its unrotated band instead, spherical_surf.cpp:139)
+        ident = oracle.crop_rotated_lut(0.0, w, h)
+        rows, cols = ident // w, ident % w
+        want_r = (np.arange(h // 4)[:, None] + h * 3 // 8) * np.ones((1, w), np.int64)
+        want_c = np.ones((h // 4, 1), np.int64) * np.arange(w)[None, :]
+        assert np.abs(rows - want_r).max() <= 1 and np.abs(cols - want_c).max() <= 1
+        assert (rows == want_r).mean() > 0.9 and (cols == want_c).mean() > 0.75
+
+
+def test_depth_block_is_separable():
+    """Every match is its own block: solving a subset alone reaches the same depths as inside the full problem when
+    both runs are driven to the same number of (all accepted) iterations is not guaranteed -- but the fully converged
+    optimum is, so compare optima reached with generous iteration caps."""
+    b1, b2, r, t, _ = synth.make_two_view(40, seed=9, outlier_frac=0.0, noise=1e-3)
+    d_all, s_all, _ = oracle.ba_d_solve(b1, b2, r, t, np.full((40, 2), 1.0), 1.0, 1.0, 500)
+    d_sub, s_sub, _ = oracle.ba_d_solve(b1[:10], b2[:10], r, t, np.full((10, 2), 1.0), 1.0, 1.0, 500)
+    assert np.abs(d_all[:10] - d_sub).max() < 5e-2 * np.abs(d_sub).max()
+    # cost is the sum of the per-match costs
+    per = sum(0.5 * (oracle.ba_d_functor(b1[i], b2[i], r, t, d_all[i])[0] ** 2).sum() for i in range(40))
+    assert abs(per - s_all.final_cost) < 1e-9 * max(1.0, per)
