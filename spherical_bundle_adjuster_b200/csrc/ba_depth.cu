@@ -195,7 +195,7 @@ __device__ inline double ls_next_step(const LsSample& lower, const LsSample& pre
 // ---- the decision, one thread -----------------------------------------------------------------------
 // Ceres TrustRegionMinimizer (bounds-constrained), LevenbergMarquardtStrategy and ArmijoLineSearch
 // defaults; S = the folded sums of the pass that just finished.
-__device__ inline void depth_decide(DepthState& st, const double* S)
+__device__ __noinline__ void depth_decide(DepthState& st, const double* S)
 {
     const double min_rel_dec = 1e-3, ftol = 1e-6, gtol = 1e-10, ptol = 1e-8, max_radius = 1e16, min_radius = 1e-32;
     const double ls_suff = 1e-4, ls_max_contr = 1e-3, ls_min_contr = 0.6, ls_min_step = 1e-9;
@@ -286,7 +286,7 @@ __device__ inline DepthPoint depth_point(const double u[3], const double b[3], c
     return P;
 }
 
-__global__ void __launch_bounds__(DEPTH_THREADS) ba_depth_pass_kernel(DepthArgs A)
+__global__ void __launch_bounds__(DEPTH_THREADS, 2) ba_depth_pass_kernel(DepthArgs A)
 {
     __shared__ double s_red[DEPTH_THREADS / 32][DEPTH_SUMS];
     __shared__ bool s_last;
@@ -302,9 +302,26 @@ __global__ void __launch_bounds__(DEPTH_THREADS) ba_depth_pass_kernel(DepthArgs 
 #pragma unroll
     for (int k = 0; k < DEPTH_SUMS; k++) acc[k] = 0.0;
 
-    for (int i = blockIdx.x * DEPTH_THREADS + threadIdx.x; i < A.n; i += gridDim.x * DEPTH_THREADS) {
-        const float4 p1 = __ldg(A.b1 + i), p2 = __ldg(A.b2 + i);
-        double2 xv = reinterpret_cast<const double2*>(xin)[i];
+    // the loads of the next match are issued before the (long, fp64) arithmetic of this one: two matches' worth of
+    // bytes in flight per thread keeps HBM busy at the occupancy this kernel's register count allows
+    const int stride = gridDim.x * DEPTH_THREADS;
+    int i = blockIdx.x * DEPTH_THREADS + threadIdx.x;
+    float4 n1 = make_float4(0.f, 0.f, 0.f, 0.f), n2 = n1;
+    double2 nx = make_double2(0.0, 0.0), ns = nx;
+    if (i < A.n) {
+        n1 = __ldg(A.b1 + i); n2 = __ldg(A.b2 + i);
+        nx = reinterpret_cast<const double2*>(xin)[i];
+        if (!first) ns = reinterpret_cast<const double2*>(A.scale)[i];
+    }
+    for (; i < A.n; i += stride) {
+        const float4 p1 = n1, p2 = n2;
+        double2 xv = nx;
+        const double2 sc_loaded = ns;
+        if (i + stride < A.n) {
+            n1 = __ldg(A.b1 + i + stride); n2 = __ldg(A.b2 + i + stride);
+            nx = reinterpret_cast<const double2*>(xin)[i + stride];
+            if (!first) ns = reinterpret_cast<const double2*>(A.scale)[i + stride];
+        }
         if (first) {   // IterationZero: project the starting point on the box
             xv.x = fmax(xv.x, 0.0); xv.y = fmax(xv.y, 0.0);
             reinterpret_cast<double2*>(xin)[i] = xv;
@@ -322,7 +339,7 @@ __global__ void __launch_bounds__(DEPTH_THREADS) ba_depth_pass_kernel(DepthArgs 
             sc.x = 1.0 / (1.0 + sqrt(h00)); sc.y = 1.0 / (1.0 + sqrt(h11));
             reinterpret_cast<double2*>(A.scale)[i] = sc;
         } else {
-            sc = reinterpret_cast<const double2*>(A.scale)[i];
+            sc = sc_loaded;
         }
         // LevenbergMarquardtStrategy::ComputeStep on the column-scaled block
         const double a00 = h00 * sc.x * sc.x, a01 = h01 * sc.x * sc.y, a11 = h11 * sc.y * sc.y;
@@ -454,7 +471,7 @@ static void rotation_matrix_host(const double r[3], double R[9])
 static int depth_grid(int n, int sm_count)
 {
     int g = (n + DEPTH_THREADS - 1) / DEPTH_THREADS;
-    const int cap = sm_count * 8;
+    const int cap = sm_count * 2;   // persistent: two resident CTAs per SM (114 registers), each thread walks its matches with the next one prefetched
     if (g > cap) g = cap;
     return g < 1 ? 1 : g;
 }
