@@ -33,3 +33,31 @@ def test_reference_arm_prints_the_contract_line():
 def test_reference_arm_is_silent_on_other_ranks():
     r = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_gpu_arm_prints_the_contract_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "12", "--warmup", "3", "--cpu-budget", "2"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+        assert key in d, key
+    assert "impl" not in d and d["n_gpus"] == 1 and d["steps"] == 12 and d["warmup"] >= 3 and d["scaling"] == "weak"
+    assert d["value"] > 100 and abs(d["ms_per_step"] * d["value"] - 1000.0) < 1.0      # pairs/s and ms per pair agree
+    e = d["e2e"]
+    assert 0 < e["value"] < d["value"] and e["h2d_bytes_per_step"] > 50_000_000 and e["d2h_bytes_per_step"] > 0
+    assert d["gpu_launches"] >= 12 * 10
+    rf = d["roofline"]
+    assert rf["bound"] == "tensor" and rf["unit"] == "TFLOP/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9 and 0 < rf["frac"] < 1 / 3 + 1e-6
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] > 0 and isinstance(cb["sample"], str)
+    ck = d["clocks"]
+    assert ck["sm_mhz"] and ck["sm_max_mhz"] and not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(ck["reasons"]))
+    assert "workload" in d["config"] and "model" not in d["config"]
