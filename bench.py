@@ -1,23 +1,35 @@
 #!/usr/bin/env python
 """bench.py -- the reference's headline metric on BASELINE.json's config, on N B200s of one node.
 
-Workload (config.workload "C2"): one ERP pair per step --
+Workload (config.workload "C2"), per ERP pair --
     equi2cube of both 3840x1920 images (cube 960) -> kNN(k=2)+ratio match of 16384 x 16384 SURF-64
     descriptors -> matched keypoints cube->ERP -> bearings -> rotation-only BA (LM, <= 50 iterations).
 SURF itself is out of scope (non-free, stays on the host in the reference): keypoints/descriptors are
 synthetic with planted correspondences (spherical_bundle_adjuster_b200/synth.py).
 
-metric  ERP pairs/sec.   value = device-resident throughput, e2e = through host buffers (pinned
-host -> device copies of both images, descriptors and keypoints, and the device -> host read of the
-matches + rotation inside the timed region).  roofline = the matcher's distance kernel against the
-measured bf16 tensor peak (algorithmic 2*D*N*M flops only).  cpu_baseline = the CPU path timed on this
-box's host cores (the reference's own equi2cube code from oracle/_ref when built, cv2.BFMatcher --
-the library call the reference's matcher makes -- and the oracle's LM port).
+A STEP is a batch of PAIRS_PER_STEP (64) pairs per GPU, so the driver's 20-step protocol times >= 0.2 s of
+steady state.  --warmup W runs exactly W untimed steps before each timed region; building the remap plan and
+sizing every context's buffers happens in an unreported prologue before that.
 
-Multi-GPU (--gpus N under torchrun): pairs shard across ranks with no collective ("weak": every
-rank runs the same number of pairs per step).
+metric  "ERP pairs/s".  value = device-resident throughput (inputs already in HBM when the timed region
+starts), e2e = the same pairs through sba_pair_rotation_begin/_end with pinned HOST buffers (copies of both
+images, descriptors and keypoints in, match list + rotation out, inside the timed region); e2e_reference_order =
+the same with the remap first and both cube strips copied back to the host, as equi2cube_surf::do_all hands
+them to the host-side SURF (equi2cube_surf.cpp:85-94).  roofline = the matcher's distance kernel against the
+measured bf16 tensor peak (algorithmic 2*D*N*M flops only).  cpu_baseline = the CPU path timed on this box's
+host cores (the reference's own equi2cube code from oracle/_ref when built, cv2.BFMatcher -- the library call
+the reference's matcher makes -- and the oracle's LM port).
 
-    python bench.py --gpus 1 --steps 20 --warmup 3
+Multi-GPU (--gpus N under torchrun): pairs shard across ranks with no collective ("weak": every rank runs the
+same number of pairs per step).  After the headline timing, outside the timed region, the two sharded paths
+that DO cut one problem across ranks run with their parity checks and land on the same JSON line:
+  ba_sharded    BASELINE config 4 (1024 cameras / 1 M observations, and a 64 M variant): residual-sharded LM
+                solve, blocks summed over NVLink peer memory inside the evaluation kernel and by an NCCL
+                all-reduce callback; all ranks bit-equal, rotation <= 1e-6 rad from the N=1 solve of the same data;
+  match_sharded BASELINE config 5 (16k and 64k): query row-blocks per rank, lists gathered in rank order and
+                compared with one single-GPU match_two_image on rank 0.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
     python bench.py --impl reference --steps 3 --warmup 1
 """
 from __future__ import annotations
@@ -37,9 +49,14 @@ sys.path.insert(0, ROOT)
 
 W, H, CS, NKP, DIM = 3840, 1920, 960, 16384, 64
 RATIO = 0.3
-IN_FLIGHT = int(os.environ.get("SBA_BENCH_IN_FLIGHT", "6"))   # library contexts (streams + host threads) per GPU
+PAIRS_PER_STEP = int(os.environ.get("SBA_BENCH_PAIRS_PER_STEP", "64"))   # pairs per step per GPU
+IN_FLIGHT = int(os.environ.get("SBA_BENCH_IN_FLIGHT", "6"))   # library contexts (one stream each) per GPU
 MATCHER_CTAS = int(os.environ.get("SBA_BENCH_MATCHER_CTAS", "0"))   # 0 = one persistent matcher CTA per SM
 POOL = 6  # distinct pairs resident in HBM and cycled through: 6 x 52.7 MB = 316 MB >> 126 MB L2
+METRIC = "ERP pairs/s"
+# identical in both arms (the driver compares the dicts): only what defines the workload
+CONFIG = {"workload": "C2: 3840x1920 ERP pair, cube 960, 16384x16384 SURF-64 kNN2+ratio 0.3, rotation BA",
+          "erp": [W, H], "cube_size": CS, "keypoints_per_image": NKP, "descriptor_dim": DIM, "ratio": RATIO, "lm_max_iterations": 50}
 
 
 def _peaks():
@@ -65,21 +82,31 @@ def make_pool(n_pairs: int, seed0: int):
 
 # ------------------------------------------------------------------------------------------- ours
 class PairRunner:
-    """The hot path for one pair on one GPU: ONE C-ABI call (sba_pair_rotation) per pair."""
+    """The hot path for one pair on one GPU: ONE C-ABI call pair (sba_pair_rotation_begin/_end) per ERP pair."""
 
     def __init__(self, ctx):
         self.ctx = ctx
+        self.host_out = None     # pinned result buffers of this context (host-buffer runs): copies back stay asynchronous
 
-    def run(self, d):
+    def _out(self, d, strips):
+        import torch
+        if d["desc1"].is_cuda:
+            return None
+        if self.host_out is None:
+            pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+            self.host_out = {"qi": pin((NKP,), torch.int32), "ti": pin((NKP,), torch.int32), "dd": pin((NKP,), torch.float32),
+                             "sl": pin((CS, 6 * CS, 3), torch.uint8), "sr": pin((CS, 6 * CS, 3), torch.uint8)}
+        return self.host_out
+
+    def run(self, d, strips=False):
         """d: dict of tensors im1, im2, desc1, desc2, key1, key2 -- CUDA tensors (device-resident run) or
         pinned host tensors (end-to-end run: the call copies them in and the match list + rotation out)."""
-        res, matches, _ = self.ctx.pair_rotation(d["im1"], d["im2"], d["desc1"], d["desc2"], d["key1"], d["key2"], CS, ratio=RATIO,
-                                                 want_matches=True)
-        return np.array(res.rotation), res.n_matches, matches, res
+        return self.collect(self.begin(d, strips))
 
-    def begin(self, d):
+    def begin(self, d, strips=False):
         """sba_pair_rotation_begin: queue the pair, do not wait."""
-        return self.ctx.pair_rotation_begin(d["im1"], d["im2"], d["desc1"], d["desc2"], d["key1"], d["key2"], CS, ratio=RATIO, want_matches=True)
+        return self.ctx.pair_rotation_begin(d["im1"], d["im2"], d["desc1"], d["desc2"], d["key1"], d["key2"], CS, ratio=RATIO, want_matches=True,
+                                            want_strips=strips, out=self._out(d, strips))
 
     @staticmethod
     def collect(call):
@@ -172,6 +199,17 @@ class ClockSampler:
                     reasons=sorted(self.reasons), samples=len(self.samples))
 
 
+def _ncu_traffic():
+    """DRAM bytes of one launch of the distance kernel from the committed ncu --set full capture of this size
+    (profiles/matcher_ncu_traffic.json, written from the capture named inside it), or None."""
+    p = os.path.join(ROOT, "profiles", "matcher_ncu_traffic.json")
+    try:
+        d = json.load(open(p))
+        return int(d["dram_bytes_per_launch"]), d.get("source")
+    except Exception:
+        return None, None
+
+
 def bench_ours(args):
     import torch
     import torch.distributed as dist
@@ -204,121 +242,163 @@ def bench_ours(args):
               for k, src in [("im1", "im1"), ("im2", "im2"), ("desc1", "desc1"), ("desc2", "desc2"), ("key1", "key1_xy"), ("key2", "key2_xy")]}
         pinned.append(hp)
         resident.append({k: v.to(dev) for k, v in hp.items()})
-    h2d_bytes = sum(v.numel() * v.element_size() for v in pinned[0].values())
+    h2d_bytes_pair = sum(v.numel() * v.element_size() for v in pinned[0].values())
+    strip_bytes_pair = 2 * CS * 6 * CS * 3
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_steps(data, steps):
-        """Exactly `steps` pairs, step k on context k % IN_FLIGHT: a pair's result is collected only when its context
-        is needed again, so up to IN_FLIGHT pairs are queued at any time (one host thread, no extra copies).
-        Device time from the start event to the last end event of any stream.  Returns (ms, result of the last pair)."""
-        gc.collect()
-        gc.disable()          # a collector pause inside a ~40 ms window would show up as a missing pair or two
-        barrier()
-        start = torch.cuda.Event(enable_timing=True)
-        ends = [torch.cuda.Event(enable_timing=True) for _ in range(IN_FLIGHT)]
+    def run_pairs(data, n_pairs, strips=False):
+        """`n_pairs` pairs, pair k on context k % IN_FLIGHT: a pair's result is collected only when its context
+        is needed again, so up to IN_FLIGHT pairs are queued at any time (one host thread, no extra copies)."""
         pending = [None] * IN_FLIGHT
         out = None
-        start.record(streams[0])
-        for k in range(steps):
+        for k in range(n_pairs):
             j = k % IN_FLIGHT
             if pending[j] is not None:
                 out = runners[j].collect(pending[j])
-            pending[j] = runners[j].begin(data[k % POOL])
-        for j in [(steps + i) % IN_FLIGHT for i in range(IN_FLIGHT)]:      # oldest first
+            pending[j] = runners[j].begin(data[k % POOL], strips)
+        for j in [(n_pairs + i) % IN_FLIGHT for i in range(IN_FLIGHT)]:      # oldest first
             if pending[j] is not None:
                 out = runners[j].collect(pending[j])
+        return out
+
+    def timed_region(data, warmup, steps, strips=False):
+        """`warmup` untimed steps, then exactly `steps` steps of PAIRS_PER_STEP pairs between two barriers.
+        Device time from the start event to the last end event of any stream.  Returns (ms, result of the last pair)."""
+        for _ in range(warmup):
+            run_pairs(data, PAIRS_PER_STEP, strips)
+        gc.collect()
+        gc.disable()          # a collector pause would show up as a few missing pairs
+        barrier()
+        start = torch.cuda.Event(enable_timing=True)
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(IN_FLIGHT)]
+        start.record(streams[0])
+        for st in streams[1:]:
+            st.wait_event(start)                                            # no stream starts before the start event
+        l0 = sum(c.launch_count for c in ctxs)
+        out = run_pairs(data, steps * PAIRS_PER_STEP, strips)
+        for j in range(IN_FLIGHT):
             ends[j].record(streams[j])
         barrier()
         gc.enable()
-        return max(start.elapsed_time(e) for e in ends), out
+        return max(start.elapsed_time(e) for e in ends), out, sum(c.launch_count for c in ctxs) - l0
 
-    # ---- warm-up: builds the remap plan, sizes the scratch buffers of every context and lets the library see
-    #      every pool entry; checks the answer once
-    n_warm = max(3, args.warmup, 2 * POOL)
+    # ---- prologue (unreported): builds the remap plan, sizes the scratch buffers of every context in both modes
+    #      and lets the library see every pool entry; checks the answer once
+    t_pro = time.perf_counter()
     for rn in runners:
-        for k in range(n_warm):
-            r, nm, m, s = rn.run(resident[k % POOL])
-    truth = pool_host[(n_warm - 1) % POOL]["r_true"]
+        for k in range(POOL):
+            r, nm, m, s = rn.run(resident[k])
+        rn.run(pinned[0]); rn.run(pinned[1], strips=True)
+    truth = pool_host[POOL - 1]["r_true"]
     assert np.linalg.norm(r - truth) < 1e-3, (r, truth)
+    prologue_s = time.perf_counter() - t_pro
 
     # ---- device-resident timed region: exactly K steps, CUDA events on the launching streams
     clk_path = os.path.join(ROOT, "gpurun_out", f"clocks_rank{rank}.csv")
     os.makedirs(os.path.dirname(clk_path), exist_ok=True)
     sampler = ClockSampler(local_rank, clk_path).start() if rank == 0 else None
-    launches0 = sum(c.launch_count for c in ctxs)
-    ms_total, _ = timed_steps(resident, args.steps)
-    launches = sum(c.launch_count for c in ctxs) - launches0
+    ms_total, _, launches_timed = timed_region(resident, args.warmup, args.steps)
 
-    # ---- per-kernel device times (CUDA events around the dominant kernels), one context alone, outside the timed region
+    # ---- end-to-end timed regions: pinned host -> device every pair, results read back
+    ms_e2e, (r, nm, m, s), _ = timed_region(pinned, args.warmup, args.steps)              # strips stay on the device
+    ms_e2e_ro, _, _ = timed_region(pinned, args.warmup, args.steps, strips=True)          # reference order: remap first, strips to the host
+    d2h_pair = 3 * 4 * nm + 4 + 24 * 2
+    if sampler is not None:
+        sampler.stop()
+
+    # ---- per-kernel device times (CUDA events around the dominant kernels), one context alone, outside the timed regions
     ctx.set_profiling(True)
     match_ms, remap_ms, ba_ms = [], [], []
-    for k in range(min(args.steps, 10)):
+    for k in range(10):
         runner.run(resident[k % POOL])
         match_ms.append(ctx.kernel_ms(0)); remap_ms.append(ctx.kernel_ms(1)); ba_ms.append(ctx.kernel_ms(2))
     ctx.set_profiling(False)
     # one pair at a time on one context, for reference next to the pipelined number
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = ctx.launch_count
     e0.record(streams[0])
-    for k in range(min(args.steps, 20)):
+    for k in range(20):
         runner.run(resident[k % POOL])
     e1.record(streams[0])
     barrier()
-    ms_serial = e0.elapsed_time(e1) / min(args.steps, 20)
+    ms_serial = e0.elapsed_time(e1) / 20
+    launches_one_pair = (ctx.launch_count - l0) / 20.0
 
-    # ---- end-to-end timed region: pinned host -> device every step, results read back
-    for rn in runners:
-        for k in range(n_warm):                                 # warm-up of the host-buffer path (staging buffers, second stream)
-            rn.run(pinned[k % POOL])
-    ms_e2e, (r, nm, m, s) = timed_steps(pinned, args.steps)     # host buffers in, match list + rotation out
-    d2h_bytes = 3 * 4 * nm + 4 + 24 * 2
-    if sampler is not None:
-        sampler.stop()
-
-    times = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    times = torch.tensor([ms_total, ms_e2e, ms_e2e_ro], dtype=torch.float64, device=dev)
+    per_rank = [torch.empty_like(times) for _ in range(world)]
     if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = float(times[0]), float(times[1])
+        dist.all_gather(per_rank, times)
+    else:
+        per_rank = [times]
+    per_rank = [[float(x) for x in t] for t in per_rank]
+    ms_total, ms_e2e, ms_e2e_ro = (max(t[i] for t in per_rank) for i in range(3))
+
+    # ---- the two paths that cut ONE problem across ranks, with parity asserted (outside the timed regions)
+    sharded = {}
+    if world > 1 and not args.no_sharded:
+        from spherical_bundle_adjuster_b200 import multigpu
+        for c in ctxs[1:]:
+            c.close()
+        del resident
+        torch.cuda.empty_cache()
+        sctx = Context(local_rank)                                      # on torch's current stream: the NCCL callback enqueues there
+        ba = []
+        for n_obs, n_cam in ((1_000_000, 1024), (64_000_000, 1024), (16_000_000, 1)):
+            ba.append(multigpu.sharded_ba_solve(sctx, rank, world, dev, n_obs, n_cam))
+            torch.cuda.empty_cache()
+        mt = [multigpu.sharded_match(sctx, rank, world, dev, n) for n in (16384, 65536)]
+        sharded = {"ba_sharded": {"parity_ok": all(b["parity_ok"] for b in ba), "problems": ba},
+                   "match_sharded": {"parity_ok": all(x["parity_ok"] for x in mt), "sizes": mt}}
+        sctx.close()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    pairs = args.steps * world
+    pairs = args.steps * PAIRS_PER_STEP * world
     flops = 2.0 * DIM * NKP * NKP
     mk = float(np.mean(match_ms)) * 1e-3
     stats = ctx.match_stats()
-    algo = {1: "simt_fp32_exact", 2: "tcgen05_bf16x3+exact_rerank"}.get(stats.algo_used, "?")
+    algo = {1: "simt_fp32_exact", 2: "tcgen05_filter+exact_rerank"}.get(stats.algo_used, "?")
     achieved = flops / mk / 1e12
-    peak = peaks["bf16_tflops_sustained"]
+    peak = peaks["bf16_tflops"]
+    traffic, traffic_src = _ncu_traffic()
+    pcie = lambda ms: PAIRS_PER_STEP * args.steps * h2d_bytes_pair / (ms * 1e-3) / 1e9
     line = {
-        "metric": "ERP pairs/sec end-to-end", "value": pairs / (ms_total * 1e-3), "unit": "pairs/s", "n_gpus": world,
-        "steps": args.steps, "warmup": n_warm, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (matcher distances; bf16x3 tensor filter) / f64 (BA residual, LM)",
-        "data": "synthetic",
-        "config": {"workload": "C2: 3840x1920 ERP pair, cube 960, 16384x16384 SURF-64 kNN2+ratio 0.3, rotation BA",
-                   "pairs_per_step_per_gpu": 1, "pairs_in_flight_per_gpu": IN_FLIGHT, "ms_per_pair_one_at_a_time": ms_serial, "l2_policy": f"inputs larger than L2: {POOL} resident pairs ({POOL * h2d_bytes / 1e6:.0f} MB) cycled",
-                   "matcher_algo": algo, "matches_per_pair": int(nm), "lm_iterations": int(s.lm_iterations),
-                   "api": "sba_pair_rotation_begin/_end (one C-ABI call pair per ERP pair)"},
-        "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes)},
-        "gpu_launches": int(launches),
+        "metric": METRIC, "value": pairs / (ms_total * 1e-3), "unit": "pairs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (matcher distances; bf16 tensor filter) / f64 (BA residual, LM)",
+        "data": "synthetic", "config": CONFIG,
+        "value_is": "device-resident: inputs already in HBM when the timed region starts; e2e is the host-buffer number",
+        "run": {"pairs_per_step_per_gpu": PAIRS_PER_STEP, "pairs_in_flight_per_gpu": IN_FLIGHT, "ms_per_pair_one_at_a_time": ms_serial,
+                "launches_per_pair_one_at_a_time": launches_one_pair,
+                "l2_policy": f"inputs larger than L2: {POOL} resident pairs ({POOL * h2d_bytes_pair / 1e6:.0f} MB) cycled",
+                "matcher_algo": algo, "matches_per_pair": int(nm), "lm_iterations": int(s.lm_iterations), "prologue_s": prologue_s,
+                "api": "sba_pair_rotation_begin/_end (one C-ABI call pair per ERP pair)"},
+        "per_rank_ms": {"device_resident": [t[0] for t in per_rank], "e2e": [t[1] for t in per_rank], "e2e_reference_order": [t[2] for t in per_rank]},
+        "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d_bytes_pair * PAIRS_PER_STEP),
+                "d2h_bytes_per_step": int(d2h_pair * PAIRS_PER_STEP), "note": "cube strips stay on the device",
+                "h2d_gbs_per_gpu": pcie(ms_e2e)},
+        "e2e_reference_order": {"value": pairs / (ms_e2e_ro * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d_bytes_pair * PAIRS_PER_STEP),
+                                "d2h_bytes_per_step": int((d2h_pair + strip_bytes_pair) * PAIRS_PER_STEP), "h2d_gbs_per_gpu": pcie(ms_e2e_ro),
+                                "note": "remap first, both cube strips copied to the host inside the timed region (equi2cube_surf.cpp:85-94)"},
+        "gpu_launches": int(launches_timed),
         "roofline": {"kernel": "matcher distance kernel (" + algo + ")", "bound": "tensor", "achieved": achieved, "peak": peak,
                      "unit": "TFLOP/s", "frac": achieved / peak,
-                     # DRAM bytes of one launch from the ncu --set full capture of this kernel at this size
-                     # (profiles/r01_ncu_final_prof_tc_r01d.txt: 8.48 MB read, 0 written = the bf16 operands once)
-                     "traffic": 8480256 if (NKP, DIM) == (16384, 64) else None, "traffic_unit": "bytes of DRAM traffic per launch (ncu)",
-                     "peak_source": peaks["source"] + " bf16 dense, sustained (kernel timed inside the step)",
-                     "algorithmic_flops_per_launch": flops, "kernel_ms": mk * 1e3,
-                     # the exact-fp32 result costs three bf16 products (hi.hi + hi.lo + lo.hi): what the tensor pipe itself sustains
-                     "bf16_products_per_result": 3, "tensor_pipe_frac_incl_split_products": 3.0 * achieved / peak},
+                     "traffic": traffic, "traffic_unit": "bytes of DRAM traffic per launch (ncu --set full)", "traffic_source": traffic_src,
+                     "peak_source": peaks["source"] + " bf16 dense, burst (kernel timed alone with CUDA events, one context)",
+                     "algorithmic_flops_per_launch": flops, "kernel_ms": mk * 1e3},
         "stage_ms": {"match_kernel": float(np.mean(match_ms)), "remap_kernel_per_image": float(np.mean(remap_ms)),
                      "ba_eval_kernel_last": float(np.mean(ba_ms))},
         "clocks": sampler.summary(),
     }
+    line.update(sharded)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(budget_s=args.cpu_budget)
     print(json.dumps(line))
@@ -372,22 +452,22 @@ def bench_reference(args):
     import oracle
     threads = os.cpu_count() or 1
     pool = make_pool(2, seed0=1000)
-    for _ in range(max(1, args.warmup)):
-        cpu_pair(pool[0], threads)
+    for k in range(args.warmup):
+        cpu_pair(pool[k % 2], threads)
     t0 = time.perf_counter()
     for k in range(args.steps):
         r, nm = cpu_pair(pool[k % 2], threads)
     dt = time.perf_counter() - t0
     v = args.steps / dt
     kind = "reference" if oracle.ref_available() else "port"
-    line = {"impl": "reference", "metric": "ERP pairs/sec end-to-end", "value": v, "unit": "pairs/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
-            "steps": args.steps, "warmup": max(1, args.warmup), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 (matcher) / f64 (remap index math, BA)", "data": "synthetic",
-            "config": {"workload": "C2: 3840x1920 ERP pair, cube 960, 16384x16384 SURF-64 kNN2+ratio 0.3, rotation BA",
-                       "pairs_per_step": 1, "matches_per_pair": int(nm)},
-            "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": kind,
-                             "sample": f"{args.steps} full C2 pairs; equi2cube = " + ("reference's own equi2cube.cpp via oracle/_ref" if kind == "reference" else "oracle port")
-                                       + "; matcher = cv2.BFMatcher; BA = oracle LM port (Ceres absent)"},
+    sample = (f"{args.steps} steps of ONE full C2 pair each (a bounded sample of the GPU arm's {PAIRS_PER_STEP}-pair step); equi2cube = "
+              + ("reference's own equi2cube.cpp via oracle/_ref" if kind == "reference" else "oracle port")
+              + "; matcher = cv2.BFMatcher; BA = oracle LM port (Ceres absent)")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (matcher) / f64 (remap index math, BA)", "data": "synthetic", "config": CONFIG,
+            "run": {"pairs_per_step": 1, "matches_per_pair": int(nm)},
+            "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -395,14 +475,15 @@ def bench_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 200 for the GPU arm, 8 for the CPU reference arm)")
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 20 for the GPU arm, 8 for the CPU reference arm)")
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the residual-sharded BA and row-block-sharded matcher checks")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()
     if args.steps is None:
-        args.steps = 8 if args.impl == "reference" else 200
+        args.steps = 8 if args.impl == "reference" else 20
     if args.impl == "reference":
         bench_reference(args)
     else:

@@ -361,9 +361,11 @@ class Context:
 
     def pair_rotation_begin(self, im_left, im_right, desc_left, desc_right, key_left_xy, key_right_xy, cube_size: int, w: int = 0, h: int = 0,
                             ratio: float = 0.3, r0=(0.0, 0.0, 0.0), t=(0.0, 0.0, 0.0), d1=1.0, d2=1.0, huber=1.0, max_iter=50,
-                            want_matches: bool = True, want_strips: bool = False, _blocking: bool = False) -> "PairCall":
+                            want_matches: bool = True, want_strips: bool = False, _blocking: bool = False, out: dict | None = None) -> "PairCall":
         """Queue one pair and return at once; ``.end()`` on the returned call collects what ``pair_rotation`` returns.
-        One call in flight per context: keep N pairs in flight with N contexts on N streams."""
+        One call in flight per context: keep N pairs in flight with N contexts on N streams.
+        ``out`` may hold preallocated result buffers (keys qi, ti, dd, sl, sr) of the same kind as the inputs --
+        pinned host tensors keep the device -> host copies asynchronous."""
         u8t = torch.uint8 if torch else None
         f32t = torch.float32 if torch else None
         i32t = torch.int32 if torch else None
@@ -376,19 +378,20 @@ class Context:
         mem = _mem_of(iml, imr, dl, dr, kl, kr)
         nl, nr = dl.shape[0], dr.shape[0]
         dim = dl.shape[1]
-        qi = _empty_like_kind(dl, (max(nl, 1),), np.int32, i32t) if want_matches else None
-        ti = _empty_like_kind(dl, (max(nl, 1),), np.int32, i32t) if want_matches else None
-        dd = _empty_like_kind(dl, (max(nl, 1),), np.float32, f32t) if want_matches else None
+        out = out or {}
+        qi = out.get("qi", _empty_like_kind(dl, (max(nl, 1),), np.int32, i32t)) if want_matches else None
+        ti = out.get("ti", _empty_like_kind(dl, (max(nl, 1),), np.int32, i32t)) if want_matches else None
+        dd = out.get("dd", _empty_like_kind(dl, (max(nl, 1),), np.float32, f32t)) if want_matches else None
         sl = sr = None
         if want_strips and iml is not None:
-            sl = _empty_like_kind(dl, (cube_size, 6 * cube_size, 3), np.uint8, u8t)
-            sr = _empty_like_kind(dl, (cube_size, 6 * cube_size, 3), np.uint8, u8t)
+            sl = out.get("sl", _empty_like_kind(dl, (cube_size, 6 * cube_size, 3), np.uint8, u8t))
+            sr = out.get("sr", _empty_like_kind(dl, (cube_size, 6 * cube_size, 3), np.uint8, u8t))
         r0 = np.ascontiguousarray(r0, np.float64)
         t = np.ascontiguousarray(t, np.float64)
         call = PairCall(self, (iml, imr, dl, dr, kl, kr, r0, t), qi, ti, dd, sl, sr)
         args = (self._h, _ptr(iml), _ptr(imr), w, h, cube_size, _ptr(sl), _ptr(sr), _ptr(dl), nl, _ptr(dr), nr, dim,
                 _ptr(kl), _ptr(kr), ratio, _ptr(r0), _ptr(t), d1, d2, huber, max_iter, _ptr(qi), _ptr(ti), _ptr(dd))
-        if _blocking:   # the one-call entry point (also the only one that may replay a CUDA graph)
+        if _blocking:   # the one-call entry point
             check(self._lib.sba_pair_rotation(*args, C.byref(call._res), mem))
             call._done = True
         else:

@@ -1298,7 +1298,7 @@ static int enqueue_chunk(sba_ba_problem* p, const EvalArgs& E, const LMArrays& A
     return SBA_OK;
 }
 
-// (2) stream side, no synchronisation (capturable in a CUDA graph): mailboxes -> device, rotation
+// (2) stream side, no synchronisation: mailboxes -> device, rotation
 // tables, the first chunk of evaluations, state (+ parameters) back to the mailboxes.
 // Evaluations that start after convergence return immediately (state.done).
 // Evaluation / LM arguments of a solve in either mode (rotation free: t uniform and fixed;

@@ -185,11 +185,6 @@ struct sba_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copy_ev[2] = {nullptr, nullptr};
     cudaEvent_t main_ev = nullptr;
-    // CUDA graphs of the fused pair pipeline (pipeline.cu), keyed by the call's buffers and parameters
-    std::vector<void*> pair_graphs;
-    int64_t pair_clock = 0;
-    cudaStream_t graph_stream = nullptr;
-    cudaEvent_t graph_ev = nullptr;
 };
 
 namespace sba {
@@ -269,10 +264,7 @@ int launch_lut_gather(sba_ctx* c, const uint8_t* d_erp, int64_t src_bytes, const
 int build_tiled_plan(sba_ctx* c, const int32_t* lut, int rows, int cols, int w, int h, bool masked, TiledPlan* out);
 void free_tiled_plan(TiledPlan* tp);
 
-// pipeline.cu: drop the cached pair graphs (context teardown)
-void pipeline_release(sba_ctx* c);
-
-// ba.cu: the LM solve in three parts so that the stream part can be captured in a CUDA graph
+// ba.cu: the LM solve in three parts (host mailboxes, stream work, collection) so a caller can queue it without waiting
 void ba_solve_prepare_host(sba_ba_problem* p, const double* r0, int max_iter);
 int ba_solve_enqueue(sba_ba_problem* p, const double t[3], double d1, double d2, double huber, int max_iter, int* launched, bool tran = false);
 int ba_solve_finish(sba_ba_problem* p, double* r_out, const double t[3], double d1, double d2, double huber, int max_iter, int launched,

@@ -73,7 +73,6 @@ int sba_ctx_destroy(sba_ctx* c)
     if (!c) return SBA_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    sba::pipeline_release(c);
     for (auto& b : c->scratch) b.release();
     c->cache.release_all();
     for (auto& kv : c->plans) {

@@ -10,12 +10,9 @@
 // waits for the host: the match count lives in device memory (the bearing kernel and the BA kernels read
 // it there), so the host's only round trip is the LM state after each chunk of evaluations.
 //
-// Optional CUDA-graph replay (SBA_PAIR_GRAPHS=1).  The second time a call arrives with the same buffers
-// and parameters its whole stream work (about 25 kernels and copies: remap x2, the matcher pipeline, the
-// bearing kernel, solver set-up and the first chunk of LM evaluations, result read-back) is captured
-// into a graph that owns its BA problem; later calls write the starting rotation into the problem's
-// pinned mailbox, launch the graph and synchronise once.  Off by default: see the measurement note at
-// the switch below.
+// No CUDA-graph replay: a captured pair bakes the context's scratch addresses into the graph, which a later,
+// larger call may reallocate; it also measured slower than the plain stream path (0.45 vs 0.37 ms per pair in
+// round 1), so the path was removed instead of guarded.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -46,24 +43,12 @@ __global__ void pair_points_kernel(const float2* __restrict__ key_l, const float
     b2[i] = make_float4((float)x, (float)y, (float)z, 0.f);
 }
 
-// Everything that identifies one call's stream work (a graph is only replayed for an identical key).
+// Everything that identifies one call's stream work.
 struct PairKey {
     const void *erp_l, *erp_r, *strip_l, *strip_r, *desc_l, *desc_r, *key_l, *key_r, *qi, *ti, *dist;
     int w, h, cs, n_left, n_right, dim, mem, max_iter;
     float ratio;
     double t[3], d1, d2, huber;
-};
-
-struct PairGraph {
-    PairKey key;
-    int seen = 0;
-    bool disabled = false;
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t exec = nullptr;
-    sba_ba_problem* prob = nullptr;
-    int launched = 0;
-    int64_t n_launches = 0;   // kernels inside the graph (for sba_ctx_launch_count)
-    int64_t last_use = 0;
 };
 
 struct PairState {   // what enqueue hands to finish
@@ -73,16 +58,8 @@ struct PairState {   // what enqueue hands to finish
     bool have_solve;
 };
 
-static bool host_ptr_is_pinned(const void* p)
-{
-    if (!p) return true;
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return a.type == cudaMemoryTypeHost;
-}
-
 // All stream work of one pair on c->stream, no synchronisation.  *prob: in = an existing problem to
-// reuse (graph replay capture) or NULL; out = the problem the solve was enqueued on (NULL if none).
+// reuse or NULL; out = the problem the solve was enqueued on (NULL if none).
 static int enqueue_pair(sba_ctx* c, const PairKey& a, const double r0[3], sba_ba_problem** prob, int* launched, PairState* ps)
 {
     cudaStream_t st = c->stream;
@@ -99,7 +76,9 @@ static int enqueue_pair(sba_ctx* c, const PairKey& a, const double r0[3], sba_ba
     const size_t im_bytes = (size_t)w * h * 3, strip_bytes = (size_t)cube_size * 6 * cube_size * 3;
     const uint8_t *d_im0 = nullptr, *d_im1 = nullptr;
     const float *d_desc0, *d_desc1, *d_key0, *d_key1;
-    const bool overlap = erp_left && mem == SBA_MEM_HOST;
+    // When the caller wants the strips back in host memory the reference's order is kept instead: images first,
+    // remap, strips on their way to the host (equi2cube_surf.cpp:85-94 hands them to the host-side detector), then the match.
+    const bool overlap = erp_left && mem == SBA_MEM_HOST && !strip_left_out && !strip_right_out;
     if (erp_left && !overlap) {
         SBA_TRY(stage_in(c, erp_left, im_bytes, mem, SCR_PIPE_IM0, &d_im0));
         SBA_TRY(stage_in(c, erp_right, im_bytes, mem, SCR_PIPE_IM1, &d_im1));
@@ -178,7 +157,7 @@ static int enqueue_pair(sba_ctx* c, const PairKey& a, const double r0[3], sba_ba
         SBA_LAUNCHED(c);
         // ---- rotation-only bundle adjustment on the bearings in place: set-up + first chunk of evaluations
         if (!*prob) SBA_TRY(ba_problem_create_impl(c, d_b, d_b + (size_t)4 * n_left, nullptr, n_left, 1, D, /*borrow=*/true, d_n, prob));
-        ba_solve_prepare_host(*prob, r0, a.max_iter);   // pinned mailboxes; a graph replay rewrites them before each launch
+        ba_solve_prepare_host(*prob, r0, a.max_iter);   // pinned mailboxes
         SBA_TRY(ba_solve_enqueue(*prob, a.t, a.d1, a.d2, a.huber, a.max_iter, launched));
     }
     if (overlap) SBA_TRY(remap_both());
@@ -210,24 +189,6 @@ static int finish_pair(sba_ctx* c, const PairKey& a, sba_ba_problem* prob, int l
         SBA_TRY(copy_out(c, (float*)a.dist, (const float*)ps.d_dist, (size_t)n, a.mem));
     }
     return finish(c, a.mem);
-}
-
-static void destroy_graph(PairGraph* g)
-{
-    if (g->exec) cudaGraphExecDestroy(g->exec);
-    if (g->graph) cudaGraphDestroy(g->graph);
-    if (g->prob) sba_ba_problem_destroy(g->prob);
-    delete g;
-}
-
-void pipeline_release(sba_ctx* c)
-{
-    for (void* v : c->pair_graphs) destroy_graph((PairGraph*)v);
-    c->pair_graphs.clear();
-    if (c->graph_stream) cudaStreamDestroy(c->graph_stream);
-    if (c->graph_ev) cudaEventDestroy(c->graph_ev);
-    c->graph_stream = nullptr;
-    c->graph_ev = nullptr;
 }
 
 static PairKey make_key(const uint8_t* erp_left, const uint8_t* erp_right, int w, int h, int cube_size, uint8_t* strip_left_out,
@@ -315,126 +276,12 @@ int sba_pair_rotation(sba_ctx* c, const uint8_t* erp_left, const uint8_t* erp_ri
                       double d2, double huber_delta, int max_iter, int32_t* query_idx_out, int32_t* train_idx_out, float* dist_out,
                       sba_pair_result* result, int mem)
 {
-    SBA_CHECK_ARG(c && result && w > 0 && h > 0 && cube_size > 0 && n_left >= 0 && n_right >= 0 && max_iter >= 0);
-    SBA_CHECK_ARG(desc_left && desc_right && key_left_xy && key_right_xy && r0 && t);
-    SBA_CHECK_ARG((erp_left == nullptr) == (erp_right == nullptr));
-    SBA_CUDA(cudaSetDevice(c->device));
-    memset(result, 0, sizeof(*result));
-    result->rotation[0] = r0[0]; result->rotation[1] = r0[1]; result->rotation[2] = r0[2];
-
-    if (c->pair_pending) {
-        sba::set_error("a pair is already in flight on this context: call sba_pair_rotation_end first");
-        return SBA_ERR_INVALID;
-    }
-    const PairKey key = make_key(erp_left, erp_right, w, h, cube_size, strip_left_out, strip_right_out, desc_left, n_left, desc_right, n_right, dim,
-                                 key_left_xy, key_right_xy, ratio, t, d1, d2, huber_delta, max_iter, query_idx_out, train_idx_out, dist_out, mem);
-
-    // Opt-in (SBA_PAIR_GRAPHS=1): measured on B200 at C2 with six alternating buffer sets the replay path
-    // (450-500 us per pair) loses to the plain stream path (373 us) -- after the device-side match count
-    // removed the mid-pipeline host wait the pipeline is bounded by kernel time and dependencies, not by
-    // launch overhead.  Kept for callers that reuse ONE buffer set (345 us vs 368 us there).
-    static const bool graphs_on = std::getenv("SBA_PAIR_GRAPHS") != nullptr;
-    const bool graphable = graphs_on && !c->profiling && n_left > 0 && n_right > 0;
-    PairGraph* g = nullptr;
-    if (graphable) {
-        for (void* v : c->pair_graphs)
-            if (memcmp(&((PairGraph*)v)->key, &key, sizeof(key)) == 0) { g = (PairGraph*)v; break; }
-        if (!g) {
-            if (c->pair_graphs.size() >= 16) {   // evict the least recently used entry
-                size_t lru = 0;
-                for (size_t k = 1; k < c->pair_graphs.size(); k++)
-                    if (((PairGraph*)c->pair_graphs[k])->last_use < ((PairGraph*)c->pair_graphs[lru])->last_use) lru = k;
-                cudaStreamSynchronize(c->stream);
-                if (c->graph_stream) cudaStreamSynchronize(c->graph_stream);
-                destroy_graph((PairGraph*)c->pair_graphs[lru]);
-                c->pair_graphs.erase(c->pair_graphs.begin() + lru);
-            }
-            g = new PairGraph();
-            g->key = key;
-            c->pair_graphs.push_back(g);
-        }
-        g->last_use = ++c->pair_clock;
-    }
-
-    PairState ps{};
-    cudaStream_t user_stream = c->stream;
-
-    // ---- capture on the second sighting of a key
-    if (g && !g->exec && !g->disabled && g->seen >= 1) {
-        bool ok = true;
-        if (mem == SBA_MEM_HOST) {
-            const void* hp[] = {erp_left, erp_right, strip_left_out, strip_right_out, desc_left, desc_right, key_left_xy, key_right_xy};
-            for (const void* p : hp) ok = ok && host_ptr_is_pinned(p);   // graph memcpy nodes need page-locked host memory
-        }
-        if (ok && !c->graph_stream) {
-            ok = cudaStreamCreate(&c->graph_stream) == cudaSuccess &&   // blocking stream: ordered with the legacy default stream
-                 cudaEventCreateWithFlags(&c->graph_ev, cudaEventDisableTiming) == cudaSuccess;
-        }
-        if (ok) {
-            cudaStreamSynchronize(user_stream);
-            c->stream = c->graph_stream;
-            sba_ba_problem* prob = nullptr;
-            int launched = 0;
-            int status = SBA_ERR_CUDA;
-            const int64_t launches_before = c->launches;
-            if (cudaStreamBeginCapture(c->graph_stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
-                status = enqueue_pair(c, key, r0, &prob, &launched, &ps);
-                cudaGraph_t graph = nullptr;
-                cudaError_t e = cudaStreamEndCapture(c->graph_stream, &graph);
-                if (status == SBA_OK && e == cudaSuccess && graph && cudaGraphInstantiate(&g->exec, graph, 0) == cudaSuccess) {
-                    g->graph = graph;
-                    g->prob = prob;
-                    g->launched = launched;
-                    g->n_launches = c->launches - launches_before;
-                } else {
-                    if (graph) cudaGraphDestroy(graph);
-                    g->exec = nullptr;
-                    status = SBA_ERR_CUDA;
-                }
-            }
-            c->stream = user_stream;
-            c->launches = launches_before;   // nothing ran yet: captured launches are counted per replay
-            if (!g->exec) {
-                cudaGetLastError();
-                g->disabled = true;   // fall back to the eager path for this key from now on
-                if (prob) sba_ba_problem_destroy(prob);
-            }
-        } else {
-            g->disabled = true;
-        }
-    }
-
-    // ---- replay
-    if (g && g->exec) {
-        if (g->prob) ba_solve_prepare_host(g->prob, r0, max_iter);
-        // order the graph after whatever the caller already queued on its stream
-        SBA_CUDA(cudaEventRecord(c->graph_ev, user_stream));
-        SBA_CUDA(cudaStreamWaitEvent(c->graph_stream, c->graph_ev, 0));
-        SBA_CUDA(cudaGraphLaunch(g->exec, c->graph_stream));
-        c->launches += g->n_launches;
-        c->stream = c->graph_stream;
-        // the pointers enqueue_pair chose are a pure function of the key: recompute them for finish
-        ps.dev_lists = (mem == SBA_MEM_DEVICE);
-        const size_t nq = (size_t)n_left;
-        int32_t* s_qi = c->scratch[SCR_PIPE_MATCH].as<int32_t>();
-        ps.d_qi = (ps.dev_lists && query_idx_out) ? query_idx_out : s_qi;
-        ps.d_ti = (ps.dev_lists && train_idx_out) ? train_idx_out : s_qi + nq;
-        ps.d_dist = (ps.dev_lists && dist_out) ? dist_out : (float*)(s_qi + 2 * nq);
-        ps.have_solve = true;
-        int status = finish_pair(c, key, g->prob, g->launched, ps, r0, result);
-        if (status == SBA_OK) cudaStreamSynchronize(c->graph_stream);
-        c->stream = user_stream;
-        return status;
-    }
-
-    // ---- eager path (first sighting of a key, graphs disabled, or capture not possible)
-    if (g) g->seen++;
-    sba_ba_problem* prob = nullptr;
-    int launched = 0;
-    int status = enqueue_pair(c, key, r0, &prob, &launched, &ps);
-    if (status == SBA_OK) status = finish_pair(c, key, prob, launched, ps, r0, result);
-    if (prob) sba_ba_problem_destroy(prob);
-    return status;
+    SBA_CHECK_ARG(result != nullptr);
+    sba_pair_call* call = nullptr;
+    SBA_TRY(sba_pair_rotation_begin(c, erp_left, erp_right, w, h, cube_size, strip_left_out, strip_right_out, desc_left, n_left, desc_right, n_right,
+                                    dim, key_left_xy, key_right_xy, ratio, r0, t, d1, d2, huber_delta, max_iter, query_idx_out, train_idx_out,
+                                    dist_out, mem, &call));
+    return sba_pair_rotation_end(call, result);
 }
 
 }  // extern "C"

@@ -79,6 +79,61 @@ def test_pair_rotation_no_matches_and_no_images(ctx):
     assert np.allclose(res.rotation, (0.1, 0.2, 0.3))                            # initial value returned untouched
 
 
+def test_pair_rotation_repeatable_across_buffer_growth(ctx):
+    """The same pair gives bit-identical results before and after a LARGER call on the same context forced every
+    scratch buffer to be reallocated (the hazard the removed graph-replay path had: stale addresses)."""
+    w, h, cs = 1024, 512, 256
+    def run(n, seed):
+        pair = synth.make_pair(n, n, cs=cs, seed=seed, rotvec=(0.1, -0.2, 0.3))
+        im1, im2 = synth.make_erp_image(w, h, seed=2), synth.make_erp_image(w, h, seed=3)
+        res, (qi, ti, dd), _ = ctx.pair_rotation(im1, im2, pair["desc1"], pair["desc2"], pair["key1_xy"], pair["key2_xy"], cs)
+        return tuple(res.rotation), res.n_matches, res.lm_iterations, qi.copy(), ti.copy(), dd.copy()
+    a = run(2000, 5)
+    run(9000, 6)                                        # grows SCR_PIPE_*, the matcher workspace and the BA blocks
+    b = run(2000, 5)
+    assert a[:3] == b[:3] and a[1] > 500
+    for x, y in zip(a[3:], b[3:]):
+        assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("kind", ["host", "device"])
+def test_pair_rotation_single_call(ctx, kind):
+    """sba_pair_rotation (one C-ABI call: remap x2 + match + cube2equi + bearings + rotation BA) against
+    the oracle run stage by stage, with host buffers and with device tensors."""
+    import torch
+    w, h, cs, n = 1024, 512, 256, 3000
+    pair = synth.make_pair(n, n - 77, cs=cs, seed=12, rotvec=(-0.2, 0.15, 0.4))
+    im1, im2 = synth.make_erp_image(w, h, seed=2), synth.make_erp_image(w, h, seed=3)
+    args = [im1, im2, pair["desc1"], pair["desc2"], pair["key1_xy"], pair["key2_xy"]]
+    if kind == "device":
+        args = [torch.from_numpy(a).cuda() for a in args]
+    res, (qi, ti, dd), (s1, s2) = ctx.pair_rotation(*args, cs, want_strips=True)
+    if kind == "device":
+        torch.cuda.synchronize()
+        qi, ti, dd, s1, s2 = [x.cpu().numpy() for x in (qi, ti, dd, s1, s2)]
+    assert np.array_equal(s1, oracle.equi2cube_all(im1, cs)) and np.array_equal(s2, oracle.equi2cube_all(im2, cs))
+    oqi, oti, odd = oracle.match_two_image(pair["desc1"], pair["desc2"], 0.3)
+    assert res.n_matches == len(oqi) and np.array_equal(qi, oqi) and np.array_equal(ti, oti)
+    assert np.array_equal(dd.view(np.uint32), odd.view(np.uint32))
+    e1 = oracle.cube2equi_points(pair["key1_xy"][oqi], cs, w, h); e2 = oracle.cube2equi_points(pair["key2_xy"][oti], cs, w, h)
+    b1 = oracle.pixels_to_bearings(e1, w, h).astype(np.float32).astype(np.float64)
+    b2 = oracle.pixels_to_bearings(e2, w, h).astype(np.float32).astype(np.float64)
+    r_or, s_or = oracle.ba_rot_solve(b1, b2, None, np.zeros((1, 3)))
+    r = np.array(res.rotation)
+    assert np.abs(r - r_or[0]).max() < 1e-6 and res.lm_iterations == s_or.iterations
+    assert np.linalg.norm(r - pair["r_true"]) < 1e-4
+
+
+def test_pair_rotation_no_matches_and_no_images(ctx):
+    rng = np.random.default_rng(0)
+    q = synth.unit_rows(rng.standard_normal((200, 64))).astype(np.float32)
+    t = synth.unit_rows(rng.standard_normal((300, 64))).astype(np.float32)      # unrelated sets: nothing survives
+    k1 = rng.uniform(0, 100, (200, 2)).astype(np.float32); k2 = rng.uniform(0, 100, (300, 2)).astype(np.float32)
+    res, (qi, ti, dd), strips = ctx.pair_rotation(None, None, q, t, k1, k2, 128, w=512, h=256, r0=(0.1, 0.2, 0.3))
+    assert res.n_matches == 0 and len(qi) == 0 and strips is None
+    assert np.allclose(res.rotation, (0.1, 0.2, 0.3))                            # initial value returned untouched
+
+
 def test_pair_rotation_graph_replay_matches_eager():
     """Opt-in CUDA-graph replay (SBA_PAIR_GRAPHS=1): third and later calls with the same buffers replay a
     captured graph; results must equal the eager path bit for bit, also when the start rotation changes."""
