@@ -44,21 +44,34 @@ constexpr int DIM = 64;            // descriptor length handled by this path
 constexpr int KP = 2 * DIM;        // bf16 per prepared row: [hi(64) | lo(64)]
 constexpr int BM = 256;            // query rows per block: two UMMA M=128 row-halves share every B tile
 constexpr int BN = 128;            // train rows per tile (UMMA N)
-constexpr int CHUNK = 4;           // columns per candidate chunk
+constexpr int CHUNK = 8;           // columns per candidate chunk
 constexpr int NCAND = 4;           // candidate chunks kept per list
 constexpr int STAGES = 4;          // B smem ring
 constexpr int EPI_WARPS = 16;      // 4 TMEM lane quarters x 4 column slices
 constexpr int SUBSLOTS = 2;        // candidate lists per query row per CTA span (2 column slices per row-half)
-constexpr int THREADS = 128 + EPI_WARPS * 32;   // warp0 TMA, warp1 MMA, warps 2-3 idle, warps 4-19 epilogue
+constexpr int EPI_WARP0 = 3;      // first epilogue warp
+constexpr int THREADS = (EPI_WARP0 + EPI_WARPS) * 32;   // warp0 TMA, warps 1-2 MMA issuers (even / odd tiles), warps 3-18 epilogue: 608 threads -> 104 registers each
 constexpr int A_KBLOCK_BYTES = BM * 128;   // one 64-wide bf16 k-block of A: 32 KB
 constexpr int B_KBLOCK_BYTES = BN * 128;   // 16 KB
 constexpr int SMEM_A = 2 * A_KBLOCK_BYTES;                 // hi, lo
 constexpr int SMEM_B = STAGES * 2 * B_KBLOCK_BYTES;        // stages x {hi, lo}
 constexpr int SMEM_NB = EPI_WARPS * 64 * 4;                 // |b|^2 staging, 64 columns per epilogue warp
-constexpr int SMEM_BYTES = SMEM_A + SMEM_B + SMEM_NB + 256 /*barriers*/ + 1024 /*alignment slack*/;
+constexpr int SMEM_BYTES = SMEM_A + SMEM_B + SMEM_NB + 256 /*barriers: 18 x 8 B + the TMEM slot*/ + 1024 /*alignment slack*/;
 constexpr int ACC_COLS = 2 * BN;   // TMEM columns per accumulator stage: row-half 0 | row-half 1
 constexpr uint32_t TMEM_COLS = 512;
-constexpr float DELTA_COEF = 4e-5f;  // |approx - exact| <= DELTA_COEF * (|a|^2 + max|b|^2), see DESIGN.md
+constexpr float DELTA_COEF = 4e-5f;  // |approx - exact| <= DELTA_COEF * (|a|^2 + max|b|^2): derivation at tc_rerank_kernel
+// Candidate keys (epilogue): a chunk minimum with the chunk's id in the low mantissa bits, so that ONE fp32 min / max
+// moves value and id together.  9 bits: [8] = "old" flag, [7:3] tile inside the current 32-tile window, [2:0] chunk of
+// the thread's 64 columns -- or, for entries that survived a window change, flag | list slot (the absolute chunk id of
+// such an entry sits in a side register).  Truncating 9 mantissa bits moves a value by < 2^-14 of its magnitude.
+constexpr uint32_t KEY_ID_MASK = 0x1FFu;
+constexpr uint32_t KEY_OLD = 0x100u;
+constexpr uint32_t KEY_CHUNK_MASK = 0x7u;      // the chunk bits alone (set first; window bits are added to the winners only)
+constexpr int KEY_WINDOW = 32;                 // tiles per id window
+constexpr uint32_t KEY_BIG = 0x7f7fffffu;      // FLT_MAX: an insert of this value is a no-op
+constexpr uint32_t KEY_EMPTY = 0x7f000000u;    // value of an empty list entry (1.7e38, finite: keys must never be NaN)
+constexpr float KEY_TRUNC_REL = 3.0f / 16384.0f;   // bound test margin for the truncation + id bits, relative to |B| (see tc_rerank_kernel)
+constexpr float PAD_NORM = 1e30f;              // |b|^2 of padding train rows: huge but finite (inf would turn keys into NaN)
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -80,7 +93,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     const uint32_t addr = smem_u32(bar);
     uint32_t ok = 0;
-    const long long t0 = clock64();
+    long long t0 = 0;
     while (true) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -90,7 +103,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
             : "r"(addr), "r"(parity)
             : "memory");
         if (ok) break;
-        if (clock64() - t0 > 4000000000ll) __trap();
+        // the clock is only read once a wait has failed (the common case returns on the first try)
+        if (t0 == 0) t0 = clock64();
+        else if (clock64() - t0 > 60000000000ll) __trap();   // ~30 s: a protocol bug, not ordinary skew
     }
 }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1)
@@ -211,7 +226,7 @@ __global__ void tc_prep_kernel(const float* __restrict__ q, int nq, int nq_pad, 
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     const int row = gid >> 4, part = gid & 15;      // 16 threads per row, 4 floats each; a half-warp never straddles the two sets
     if (row < nq_pad) prep_row(q, nq, row, part, outA, na, 0.f, nullptr);
-    else if (row < nq_pad + nt_pad) prep_row(t, nt, row - nq_pad, part, outB, nb, INFINITY, nb_max);
+    else if (row < nq_pad + nt_pad) prep_row(t, nt, row - nq_pad, part, outB, nb, PAD_NORM, nb_max);
 }
 
 // ---- 2. the tensor-core kernel ---------------------------------------------------------------------------
@@ -269,6 +284,44 @@ __device__ __forceinline__ void cand_reset(Cand& c)
     for (int k = 0; k < NCAND; k++) { c.v[k] = __int_as_float(0x7f800000); c.id[k] = -1; }
 }
 
+// ---- key lists: the four smallest keys of everything inserted so far, sorted, in four registers --------------
+// Insert = a 7-instruction min/max chain, no predicates, no moves.  Keys are unique (distinct ids), so nothing is lost.
+__device__ __forceinline__ void key_insert(float (&k)[NCAND], float x)
+{
+    const float t = fmaxf(k[0], x); k[0] = fminf(k[0], x);
+    const float u = fmaxf(k[1], t); k[1] = fminf(k[1], t);
+    const float w = fmaxf(k[2], u); k[2] = fminf(k[2], u);
+    k[3] = fminf(k[3], w);
+}
+
+__device__ __forceinline__ void key_reset(float (&k)[NCAND], int (&abs_id)[NCAND])
+{
+#pragma unroll
+    for (int i = 0; i < NCAND; i++) { k[i] = __uint_as_float(KEY_EMPTY | KEY_OLD | (uint32_t)i); abs_id[i] = -1; }
+}
+
+// End of an id window: every entry becomes "old" -- its absolute chunk id moves to the side register of its slot.
+// chunk_base = absolute id of chunk 0 of the window's first tile for this thread's column half.
+__device__ __forceinline__ void key_flush(float (&k)[NCAND], int (&abs_id)[NCAND], int chunk_base)
+{
+    int na[NCAND];
+#pragma unroll
+    for (int i = 0; i < NCAND; i++) {
+        const uint32_t kb = __float_as_uint(k[i]);
+        const uint32_t idf = kb & KEY_ID_MASK;
+        const uint32_t sl = idf & 3u;
+        int old = abs_id[0];
+        old = sl == 1u ? abs_id[1] : old;
+        old = sl == 2u ? abs_id[2] : old;
+        old = sl == 3u ? abs_id[3] : old;
+        const int fresh = chunk_base + (int)((idf >> 3) & 31u) * (BN / CHUNK) + (int)(idf & 7u);
+        na[i] = (idf & KEY_OLD) ? old : fresh;
+        k[i] = __uint_as_float((kb & ~KEY_ID_MASK) | KEY_OLD | (uint32_t)i);
+    }
+#pragma unroll
+    for (int i = 0; i < NCAND; i++) abs_id[i] = na[i];
+}
+
 #ifdef SBA_TC_TRACE
 // Debug build only (make TRACE=1): per-CTA time stamps, read back by tools/tc_trace.py through sba_tc_trace_buffer().
 __device__ unsigned long long g_tc_trace[148 * 16];
@@ -298,9 +351,11 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     uint64_t* a_empty = bars + 1;
     uint64_t* b_full = bars + 2;               // [STAGES]
     uint64_t* b_empty = bars + 2 + STAGES;     // [STAGES]
-    uint64_t* acc_full = bars + 2 + 2 * STAGES;   // [2]
-    uint64_t* acc_empty = bars + 4 + 2 * STAGES;  // [2]
-    uint32_t* tmem_slot = (uint32_t*)(bars + 6 + 2 * STAGES);
+    // accumulator barriers per (stage, row-half): the epilogue warps of row-half 0 start on a tile while the MMAs of
+    // row-half 1 are still running, which also keeps the two halves' warps out of phase on every scheduler
+    uint64_t* acc_full = bars + 2 + 2 * STAGES;   // [2 stages][2 halves]
+    uint64_t* acc_empty = bars + 6 + 2 * STAGES;  // [2 stages][2 halves]
+    uint32_t* tmem_slot = (uint32_t*)(bars + 10 + 2 * STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) TC_TRACE(0);   // CTA start
@@ -311,9 +366,9 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
-        mbar_init(a_empty, 1);
+        mbar_init(a_empty, 2);   // one arrival per MMA issuer warp
         for (int s = 0; s < STAGES; s++) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, EPI_WARPS); }
+        for (int s = 0; s < 4; s++) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, EPI_WARPS / 2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -341,81 +396,115 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                     seg++;
                 }
                 mbar_wait(b_empty + s, ring_phase ^ 1);
+#ifdef SBA_TC_EXP_NOTMA   // experiment (trace builds): B tiles are loaded for the first ring pass only -- WRONG results, timing probe
+                if (n >= STAGES) { mbar_arrive(b_full + s); } else
+#endif
+                {
                 mbar_expect_tx(b_full + s, 2 * B_KBLOCK_BYTES);
                 uint8_t* dst = sB + s * (2 * B_KBLOCK_BYTES);
                 tma_load_2d(dst, &map_b, b_full + s, 0, tb * BN);
                 tma_load_2d(dst + B_KBLOCK_BYTES, &map_b, b_full + s, DIM, tb * BN);
+                }
                 if (++s == STAGES) { s = 0; ring_phase ^= 1; }
                 new_seg = (++tb == ntb);
                 if (new_seg) { tb = 0; qb++; }
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
-        // The whole warp walks the tile loop in lock-step (waits included) so every descriptor is
-        // warp-uniform and lives in uniform registers; only the tcgen05 instructions themselves are
-        // issued by one elected lane.
+    } else if (warp == 1 || warp == 2) {
+        // ===== MMA issuers: warp 1 takes the even tiles of the span (accumulator stage 0), warp 2 the odd ones =====
+        // The tensor pipe's queue is shallow: measured with the probe builds (Makefile `trace EXP=...`), a single
+        // issuing warp costs 0.27 us of idle pipe per tile -- its barrier waits, fences and commits -- on top of
+        // 35 ns per MMA.  Two issuers hide each other's per-tile overhead; tiles are independent (own accumulator
+        // stage, own B stage), so no ordering between the two warps is needed.
+        // Each warp walks the tile loop in lock-step (waits included) so every descriptor is warp-uniform and
+        // lives in uniform registers; only the tcgen05 instructions themselves are issued by one elected lane.
         uint32_t is_leader;
         asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(is_leader));
+        const int my_parity = warp - 1;
         int tb = tb0, seg = 0, s = 0;
         uint32_t ring_phase = 0;
-        bool new_seg = true;
+        bool new_seg = true, issued_in_block = false;
         const uint32_t sa = smem_u32(sA);
         // row-half h of the query block: rows 128h.. of each A k-block
         const uint64_t dA_hi0 = make_smem_desc(sa), dA_hi1 = make_smem_desc(sa + 128 * 128);
         const uint64_t dA_lo0 = make_smem_desc(sa + A_KBLOCK_BYTES), dA_lo1 = make_smem_desc(sa + A_KBLOCK_BYTES + 128 * 128);
         const uint64_t dB0 = make_smem_desc(smem_u32(sB));
         for (int n = 0; n < n_tiles; n++) {
-            if (new_seg) {
-                mbar_wait(a_full, seg & 1);
-                seg++;
-            }
-            const int acc = n & 1;
-            mbar_wait(acc_empty + acc, (uint32_t)(((n >> 1) & 1) ^ 1));
-            mbar_wait(b_full + s, ring_phase);
-            tcgen05_fence_after();
-            if (n == 0 && is_leader) TC_TRACE(2);              // first operands landed
-            if (n == n_tiles - 1 && is_leader) TC_TRACE(3);    // last tile's MMAs about to issue
-            // descriptors address 16-byte units: stage stride and k-block stride are plain adds
-            const uint64_t dB_hi = dB0 + (uint64_t)(s * ((2 * B_KBLOCK_BYTES) >> 4));
-            const uint64_t dB_lo = dB_hi + (B_KBLOCK_BYTES >> 4);
-            const uint32_t d0 = tmem_base + (uint32_t)(acc * ACC_COLS), d1 = d0 + BN;
-            if (is_leader) {
-                // hi.hi + hi.lo + lo.hi ; each 64-wide k-block is four K=16 steps, 32 B apart
+            const bool mine = (n & 1) == my_parity;
+            if (new_seg) seg++;
+            if (mine) {
+                if (!issued_in_block) mbar_wait(a_full, (seg - 1) & 1);   // first tile of this warp in the query block
+                const int acc = n & 1;
+                mbar_wait(acc_empty + 2 * acc, (uint32_t)(((n >> 1) & 1) ^ 1));
+                mbar_wait(b_full + s, ring_phase);
+                tcgen05_fence_after();
+                if (n == 0 && is_leader) TC_TRACE(2);              // first operands landed
+                if (n == n_tiles - 1 && is_leader) TC_TRACE(3);    // last tile's MMAs about to issue
+                // descriptors address 16-byte units: stage stride and k-block stride are plain adds
+                const uint64_t dB_hi = dB0 + (uint64_t)(s * ((2 * B_KBLOCK_BYTES) >> 4));
+                const uint64_t dB_lo = dB_hi + (B_KBLOCK_BYTES >> 4);
+                const uint32_t d0 = tmem_base + (uint32_t)(acc * ACC_COLS), d1 = d0 + BN;
+                if (is_leader) {
+                    // hi.hi + hi.lo + lo.hi ; each 64-wide k-block is four K=16 steps, 32 B apart
 #pragma unroll
-                for (int k = 0; k < 4; k++) umma_bf16(d0, dA_hi0 + 2 * k, dB_hi + 2 * k, IDESC, k > 0);
+                    for (int k = 0; k < 4; k++) umma_bf16(d0, dA_hi0 + 2 * k, dB_hi + 2 * k, IDESC, k > 0);
+#ifndef SBA_TC_EXP_1PROD   // experiment (trace builds): one product only -- WRONG results, timing probe
 #pragma unroll
-                for (int k = 0; k < 4; k++) umma_bf16(d0, dA_hi0 + 2 * k, dB_lo + 2 * k, IDESC, 1);
+                    for (int k = 0; k < 4; k++) umma_bf16(d0, dA_hi0 + 2 * k, dB_lo + 2 * k, IDESC, 1);
 #pragma unroll
-                for (int k = 0; k < 4; k++) umma_bf16(d0, dA_lo0 + 2 * k, dB_hi + 2 * k, IDESC, 1);
+                    for (int k = 0; k < 4; k++) umma_bf16(d0, dA_lo0 + 2 * k, dB_hi + 2 * k, IDESC, 1);
+#endif
+                    tcgen05_commit(acc_full + 2 * acc);      // row-half 0 ready for its epilogue warps
+                }
+                mbar_wait(acc_empty + 2 * acc + 1, (uint32_t)(((n >> 1) & 1) ^ 1));
+                tcgen05_fence_after();
+                if (is_leader) {
 #pragma unroll
-                for (int k = 0; k < 4; k++) umma_bf16(d1, dA_hi1 + 2 * k, dB_hi + 2 * k, IDESC, k > 0);
+                    for (int k = 0; k < 4; k++) umma_bf16(d1, dA_hi1 + 2 * k, dB_hi + 2 * k, IDESC, k > 0);
+#ifndef SBA_TC_EXP_1PROD
 #pragma unroll
-                for (int k = 0; k < 4; k++) umma_bf16(d1, dA_hi1 + 2 * k, dB_lo + 2 * k, IDESC, 1);
+                    for (int k = 0; k < 4; k++) umma_bf16(d1, dA_hi1 + 2 * k, dB_lo + 2 * k, IDESC, 1);
 #pragma unroll
-                for (int k = 0; k < 4; k++) umma_bf16(d1, dA_lo1 + 2 * k, dB_hi + 2 * k, IDESC, 1);
-                tcgen05_commit(b_empty + s);     // B stage free once these MMAs have read it
-                tcgen05_commit(acc_full + acc);  // accumulator ready for the epilogue
+                    for (int k = 0; k < 4; k++) umma_bf16(d1, dA_lo1 + 2 * k, dB_hi + 2 * k, IDESC, 1);
+#endif
+                    tcgen05_commit(b_empty + s);             // B stage free once these MMAs have read it
+                    tcgen05_commit(acc_full + 2 * acc + 1);  // row-half 1 ready
+                }
+                issued_in_block = true;
             }
             if (++s == STAGES) { s = 0; ring_phase ^= 1; }
             new_seg = (++tb == ntb);
             if (new_seg) tb = 0;
-            if ((new_seg || n + 1 == n_tiles) && is_leader) tcgen05_commit(a_empty);   // last tile of this query block in the span
+            if (new_seg || n + 1 == n_tiles) {   // last tile of this query block in the span: A may be overwritten once BOTH
+                                                 // warps' MMAs on it are complete (a_empty counts two arrivals)
+                if (is_leader) {
+                    if (issued_in_block) tcgen05_commit(a_empty);
+                    else mbar_arrive(a_empty);   // this warp had no tile in the block
+                }
+                issued_in_block = false;
+            }
             __syncwarp();
         }
-    } else if (warp >= 4) {
-        // ===== epilogue warps: TMEM lane quarter = warp % 4, column slice = (warp - 4) / 4 =====
+    } else if (warp >= EPI_WARP0) {
+        // ===== epilogue warps: TMEM lane quarter = warp % 4 (hardware rule), column slice = (warp - EPI_WARP0) / 4 =====
         const int quarter = warp & 3;
-        const int slice = (warp - 4) >> 2;            // 0..3: 64 accumulator columns each
+        const int slice = (warp - EPI_WARP0) >> 2;    // 0..3: 64 accumulator columns each
         const int half = slice >> 1;                  // which M=128 row-half those columns belong to
         const int csub = slice & 1;                   // which 64 train columns of the tile
         const int row = half * 128 + quarter * 32 + lane;   // row inside the 256-row query block
-        float* wnb = sNB + (warp - 4) * 64;           // this warp's |b|^2 staging (warp-synchronous)
+        float* wnb = sNB + (warp - EPI_WARP0) * 64;   // this warp's |b|^2 staging (warp-synchronous)
         const float* nb_col = nb + csub * 64 + lane;
-        Cand cand;
-        cand_reset(cand);
+        float key[NCAND];
+        int abs_id[NCAND];
+        key_reset(key, abs_id);
+        // the chunk numbers 1..7 in registers the compiler cannot fold: (m & ~7) | c is then ONE LOP3 (immediate mask, register id)
+        uint32_t creg[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) creg[c] = (uint32_t)c + (blockDim.y - 1u);   // blockDim.y == 1: a zero the compiler cannot see
         int qb = qb0, tb = tb0;
+        int tw = 0;                                   // tile inside the current id window
+        int chunk_base = tb0 * (BN / CHUNK) + csub * 8;   // absolute id of the window's first chunk for this column half
         float nb0 = __ldg(nb_col + (size_t)tb * BN), nb1 = __ldg(nb_col + (size_t)tb * BN + 32);
         for (int n = 0; n < n_tiles; n++) {
             const int acc = n & 1;
@@ -428,68 +517,100 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 nb0 = __ldg(nb_col + (size_t)tb_next * BN);
                 nb1 = __ldg(nb_col + (size_t)tb_next * BN + 32);
             }
-            mbar_wait(acc_full + acc, (uint32_t)((n >> 1) & 1));
+            mbar_wait(acc_full + 2 * acc + half, (uint32_t)((n >> 1) & 1));
             tcgen05_fence_after();
-            if (warp == 4 && lane == 0 && n == 0) TC_TRACE(4);             // first accumulator ready
-            if (warp == 4 && lane == 0 && n == n_tiles - 1) TC_TRACE(5);   // last accumulator ready
+            if (warp == EPI_WARP0 && lane == 0 && n == 0) TC_TRACE(4);             // first accumulator ready
+            if (warp == EPI_WARP0 && lane == 0 && n == n_tiles - 1) TC_TRACE(5);   // last accumulator ready
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS + slice * 64);
-            uint32_t buf[2][32];
-            TMEM_LD_X32(buf[0], taddr);
-            TMEM_LD_X32(buf[1], taddr + 32);
+            uint32_t buf[64];
+#ifdef SBA_TC_EXP_NOLDTM   // experiment (trace builds): the accumulators are never read -- WRONG results, timing probe
+#pragma unroll
+            for (int i = 0; i < 64; i++) buf[i] = taddr + i;
+#else
+            TMEM_LD_X32(buf, taddr);
+            TMEM_LD_X32((buf + 32), taddr + 32);
             tmem_ld_wait();
+#endif
             // release the accumulator stage as soon as its values sit in registers
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty + acc);
+            if (lane == 0) mbar_arrive(acc_empty + 2 * acc + half);
+#ifdef SBA_TC_EXP_NOEPI   // experiment (trace builds): accumulators are read and dropped -- WRONG results, timing probe
+            if (buf[0] == 0x12345678u && buf[63] == 0x9abcdef0u) key[0] = 0.f;
+#else
+            // eight chunk keys: minimum of 8 columns of |b|^2 - 2 a.b, chunk number in the three lowest mantissa bits
+            float ck[8];
 #pragma unroll
-            for (int g = 0; g < 2; g++) {
-                const uint32_t* r = buf[g];
-                float cm[8];
+            for (int c = 0; c < 8; c++) {
+                const float4 na4 = *reinterpret_cast<const float4*>(wnb + c * 8);
+                const float4 nb4 = *reinterpret_cast<const float4*>(wnb + c * 8 + 4);
+                float v0, v1, v2, v3, v4, v5, v6, v7;   // packed fp32 FMAs, same rounding as eight fmaf
+                ffma2(v0, v1, buf[c * 8 + 0], buf[c * 8 + 1], na4.x, na4.y);
+                ffma2(v2, v3, buf[c * 8 + 2], buf[c * 8 + 3], na4.z, na4.w);
+                ffma2(v4, v5, buf[c * 8 + 4], buf[c * 8 + 5], nb4.x, nb4.y);
+                ffma2(v6, v7, buf[c * 8 + 6], buf[c * 8 + 7], nb4.z, nb4.w);
+                const float m = fminf(fminf(fminf(fminf(v0, v1), v2), fminf(fminf(v3, v4), v5)), fminf(v6, v7));
+                ck[c] = __uint_as_float((__float_as_uint(m) & ~KEY_CHUNK_MASK) | creg[c]);
+            }
+            // smallest (gk) and second smallest (m2) of the eight chunk keys: 18 min/max
+            const float lo0 = fminf(ck[0], ck[1]), hi0 = fmaxf(ck[0], ck[1]);
+            const float lo1 = fminf(ck[2], ck[3]), hi1 = fmaxf(ck[2], ck[3]);
+            const float lo2 = fminf(ck[4], ck[5]), hi2 = fmaxf(ck[4], ck[5]);
+            const float lo3 = fminf(ck[6], ck[7]), hi3 = fmaxf(ck[6], ck[7]);
+            const float l01 = fminf(lo0, lo1), h01 = fmaxf(lo0, lo1);
+            const float l23 = fminf(lo2, lo3), h23 = fmaxf(lo2, lo3);
+            const float gk = fminf(l01, l23);
+            // window bits go onto the winners only: key = value bits above the id field | tile-in-window | chunk
+            const uint32_t idb = (uint32_t)tw << 3;                        // warp-uniform
+            const uint32_t keep = ~KEY_ID_MASK | KEY_CHUNK_MASK;
+            const float gkf = __uint_as_float((__float_as_uint(gk) & keep) | idb);
+            // Common case: at most the tile's best chunk enters the list (one 7-instruction chain for the whole warp).
+            // If for SOME lane a second chunk also beats its fourth-best key, both go in and the third smallest is
+            // looked at; only when that one qualifies too -- always while a list is still filling, rarely afterwards --
+            // do all eight keys run through the chain.
+            if (__any_sync(0xffffffffu, gkf < key[3])) {
+                key_insert(key, gkf);
+                const float m2 = fminf(fminf(fminf(fmaxf(l01, l23), h01), h23), fminf(fminf(hi0, hi1), fminf(hi2, hi3)));
+                const float m2f = __uint_as_float((__float_as_uint(m2) & keep) | idb);
+                if (__any_sync(0xffffffffu, m2f < key[3])) {
+                    key_insert(key, m2f);
+                    float m3 = __uint_as_float(KEY_BIG);
 #pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    const float4 nv = *reinterpret_cast<const float4*>(wnb + g * 32 + c * 4);
-                    // |b|^2 - 2 a.b for two columns per instruction (packed fp32 FMA, same rounding as two fmaf)
-                    float v0, v1, v2, v3;
-                    ffma2(v0, v1, r[c * 4 + 0], r[c * 4 + 1], nv.x, nv.y);
-                    ffma2(v2, v3, r[c * 4 + 2], r[c * 4 + 3], nv.z, nv.w);
-                    cm[c] = fminf(fminf(v0, v1), fminf(v2, v3));
-                }
-                const float gm = fminf(fminf(fminf(cm[0], cm[1]), fminf(cm[2], cm[3])), fminf(fminf(cm[4], cm[5]), fminf(cm[6], cm[7])));
-                if (__any_sync(0xffffffffu, gm < cand.v[3])) {
-                    // While a span is young its lists are far from saturated and SOME lane of the warp wants to insert for
-                    // almost every chunk, so a per-chunk insert would run for all eight chunks of every group.  Instead
-                    // each lane inserts its best chunk of the group, and only if a second chunk of the same group also
-                    // beats the (updated) fourth-best value -- rare after a few tiles -- are the others visited.
-                    const int id0 = tb * (BN / CHUNK) + csub * 16 + g * 8;
-                    int c1 = 7;
-#pragma unroll
-                    for (int c = 6; c >= 0; c--) c1 = (cm[c] == gm) ? c : c1;          // first chunk holding the minimum
-                    cand_insert_bf(cand, gm, id0 + c1);
-                    float m2 = __int_as_float(0x7f800000);
-#pragma unroll
-                    for (int c = 0; c < 8; c++) m2 = fminf(m2, c == c1 ? __int_as_float(0x7f800000) : cm[c]);
-                    if (__any_sync(0xffffffffu, m2 < cand.v[3])) {
+                    for (int c = 0; c < 8; c++) m3 = fminf(m3, ck[c] > m2 ? ck[c] : __uint_as_float(KEY_BIG));
+                    const float m3f = __uint_as_float((__float_as_uint(m3) & keep) | idb);
+                    if (__any_sync(0xffffffffu, m3f < key[3])) {
 #pragma unroll
                         for (int c = 0; c < 8; c++) {
-                            const float v = (c == c1) ? __int_as_float(0x7f800000) : cm[c];
-                            if (__any_sync(0xffffffffu, v < cand.v[3])) cand_insert_bf(cand, v, id0 + c);
+                            const float x = __uint_as_float((__float_as_uint(ck[c]) & keep) | idb);
+                            key_insert(key, ck[c] > m2 ? x : __uint_as_float(KEY_BIG));
                         }
                     }
                 }
             }
-            if (tb_next == 0 || n + 1 == n_tiles) {   // last tile of this query block in the span: publish
+#endif
+            const bool block_end = (tb_next == 0 || n + 1 == n_tiles);   // last tile of this query block in the span
+            if (++tw == KEY_WINDOW || block_end) {
+                key_flush(key, abs_id, chunk_base);
+                tw = 0;
+                chunk_base = tb_next * (BN / CHUNK) + csub * 8;
+            }
+            if (block_end) {   // publish
                 const int slot = ((int)blockIdx.x - part.cta_of((long long)qb * ntb)) * SUBSLOTS + csub;
                 const size_t o = ((size_t)qb * BM + row) * slots + slot;
-                cand_v[o] = make_float4(cand.v[0], cand.v[1], cand.v[2], cand.v[3]);
-                cand_id[o] = make_int4(cand.id[0], cand.id[1], cand.id[2], cand.id[3]);
-                cand_reset(cand);
+                float pv[NCAND];
+#pragma unroll
+                for (int i = 0; i < NCAND; i++)
+                    pv[i] = abs_id[i] < 0 ? __int_as_float(0x7f800000) : __uint_as_float(__float_as_uint(key[i]) & ~KEY_ID_MASK);
+                cand_v[o] = make_float4(pv[0], pv[1], pv[2], pv[3]);
+                cand_id[o] = make_int4(abs_id[0], abs_id[1], abs_id[2], abs_id[3]);
+                key_reset(key, abs_id);
                 qb++;
             }
             tb = tb_next;
         }
     }
 
-    if (warp == 4 && lane == 0) TC_TRACE(6);   // epilogue of warp 4 done
+    if (warp == EPI_WARP0 && lane == 0) TC_TRACE(6);   // epilogue of the first epilogue warp done
     tcgen05_fence_before();
     __syncthreads();
     if (threadIdx.x == 0) { TC_TRACE(7); }
@@ -503,17 +624,38 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 }
 
 // ---- 3. exact re-rank ---------------------------------------------------------------------------------------
+// The bound test and its margin.  For a train row j outside the evaluated chunks the tensor pass guarantees
+//   approx_j >= B        (B = fourth best chunk key of the row, id bits cleared),
+// and the row is final iff no such j can beat the exact second best:  d1^2 < B + |a|^2 - delta,  where delta must
+// cover  |approx_j - (dsq_j - |a|^2)|  with dsq_j the fp32 value cv::BFMatcher itself would compute.  With A = |a|,
+// Bn = |b_j|, u = 2^-24, and "scale" = |a|^2 + max_j |b_j|^2 >= A^2 + Bn^2 >= 2 A Bn:
+//   (1) bf16 split: x = hi + lo + r with |r_k| <= 2^-18 |x_k|; the dropped products lo.lo, r.b, a.r are each
+//       <= 2^-18 |a_k b_k|, so |a.b - (hi.hi + hi.lo + lo.hi)| <= 3 * 2^-18 A Bn = 1.14e-5 A Bn;
+//   (2) the 192 bf16 products are exact in fp32; their accumulation in the tensor core is at worst a sequential
+//       truncating fp32 sum: <= 192 * 2^-23 A Bn = 2.3e-5 A Bn (observed: an order of magnitude less);
+//   (3) v = fma(-2, S, |b|^2) rounds once (6e-8 scale); |a|^2 and |b|^2 are 64-term fp32 sums (<= 2e-6 of themselves);
+//   (4) OpenCV's dsq: every (a_k - b_k) and its square round once, 16 accumulators of 4 terms, 4 + 2 combining adds:
+//       <= 10 u dsq <= 6e-7 (A + Bn)^2 <= 1.2e-6 scale.
+//   approx = |b|^2 - 2 S, so (1) and (2) enter twice: 2 (1.14e-5 + 2.3e-5) A Bn <= 3.44e-5 scale; with (3) and (4):
+//   delta <= 3.8e-5 scale  ->  DELTA_COEF = 4e-5.  The largest error actually seen is reported by sba_match_last_stats
+//   (4-5e-6 on random-sign unit rows, 1.3e-5 on all-positive rows; tests/test_gpu_matcher.py holds both).
+//   (5) candidate keys: clearing 9 mantissa bits of a chunk minimum and of B moves each by < 2^-14 of its magnitude,
+//       and keys that differ only in their id bits may be ordered either way: 3 * 2^-14 |B| = KEY_TRUNC_REL |B| on top.
 // 16 threads per query row (8 rows per 128-thread CTA).
 //   a) the row's candidate lists (one per span slot) are merged by rank counting: thread e holds up to
 //      RR_PER_THREAD entries, every entry's rank = number of entries that sort before it (value, then
 //      position), obtained with width-16 shuffles -- no divergent branches.  Ranks 0..3 are the merged
-//      best chunks, the value of rank 3 is the bound B.
-//   b) thread e evaluates train row 4*chunk[e/4] + e%4 EXACTLY: its 256-byte row and the query row are
-//      fetched with 128-bit loads into registers and combined in OpenCV's order (l2sqr_opencv).
-//   c) top-2 by (distance, index) over the 16 threads, then the safety test against B.
+//      best chunks (8 train rows each).
+//   b) phase 0: the 16 train rows of the two best chunks are evaluated EXACTLY, one per thread: the 256-byte rows are
+//      fetched cooperatively, parked in shared memory and combined with the query row in OpenCV's order
+//      (l2sqr_opencv); top-2 by (distance, index) over the 16 threads.  Every other train row has an approximate
+//      value >= the third best chunk key, so the row is final if its exact second best clears that bound by the margin.
+//   c) phase 1, only for rows that are not final yet: the same for chunks 2 and 3, bound = the fourth best key.
+//      Rows that still fail go to the exact fallback.
 constexpr int RR_THREADS = 128;
 constexpr int RR_ROWS = RR_THREADS / 16;
 constexpr int RR_PER_THREAD = 4;   // up to 16*4 = 64 candidate entries (16 slots) merged by shuffles; more -> serial path
+static_assert(CHUNK == 8 && NCAND == 4, "the re-rank evaluates two chunks of 8 rows per phase with 16 threads");
 
 __global__ void __launch_bounds__(RR_THREADS, 4)
 tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, int nt, const float* __restrict__ na,
@@ -521,7 +663,7 @@ tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ 
                  int slots, Top2* __restrict__ top, int* __restrict__ fb_list, int* __restrict__ fb_count, float* __restrict__ dbg_max_err)
 {
     __shared__ __align__(16) float qs[RR_ROWS][DIM];
-    __shared__ __align__(16) float ts[RR_ROWS][4 * NCAND][DIM + 4];   // the candidate rows of every query of the CTA
+    __shared__ __align__(16) float ts[RR_ROWS][16][DIM + 4];   // the candidate rows of every query of the CTA (one phase)
     __shared__ float win_v[RR_ROWS][NCAND];
     __shared__ int win_id[RR_ROWS][NCAND];
     const int tid = threadIdx.x, grp = tid >> 4, e = tid & 15;
@@ -574,76 +716,90 @@ tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ 
         for (int k = 0; k < NCAND; k++) { win_v[grp][k] = c.v[k]; win_id[grp][k] = c.id[k]; }
     }
     __syncwarp();
-    const float B = win_v[grp][NCAND - 1];
-    const int chunk = win_id[grp][e >> 2];
-    const float chunk_v = win_v[grp][e >> 2];
 
-    // b) exact distance of this thread's train row.  The 16 candidate rows of a query are fetched COOPERATIVELY --
-    //    for each row the 16 threads of the group read its 256 contiguous bytes as one float4 each, so a load
-    //    instruction touches 4 lines per warp instead of 32 -- parked in shared memory (row stride 68 floats: the
-    //    float4 reads below are conflict free) and then read back row-per-thread.
-    {
-        float4 stage[8];
-#pragma unroll
-        for (int half = 0; half < 2; half++) {
-#pragma unroll
-            for (int cc = 0; cc < 8; cc++) {
-                const int c = half * 8 + cc;
-                const int cj = win_id[grp][c >> 2] * CHUNK + (c & 3);
-                const bool ok = win_id[grp][c >> 2] >= 0 && cj < nt;
-                stage[cc] = ok ? __ldg(reinterpret_cast<const float4*>(t + (size_t)cj * DIM) + e) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int cc = 0; cc < 8; cc++) *reinterpret_cast<float4*>(&ts[grp][half * 8 + cc][4 * e]) = stage[cc];
-        }
-    }
-    __syncwarp();
-    const int j = chunk * CHUNK + (e & 3);
-    const bool valid = chunk >= 0 && j < nt;
+    const float na_r = na[r];
+    const float scale = na_r + *nb_max;
     Top2 best = top2_empty();
-    float exact_v = INF;
-    if (valid) {
-        float tv[DIM], qv[DIM];
-        const float4* tp = reinterpret_cast<const float4*>(&ts[grp][e][0]);
-        const float4* qp = reinterpret_cast<const float4*>(&qs[grp][0]);
+    bool final_row = false;
 #pragma unroll
-        for (int k = 0; k < DIM / 4; k++) {
-            const float4 a = tp[k];
-            tv[4 * k] = a.x; tv[4 * k + 1] = a.y; tv[4 * k + 2] = a.z; tv[4 * k + 3] = a.w;
-            const float4 b = qp[k];
-            qv[4 * k] = b.x; qv[4 * k + 1] = b.y; qv[4 * k + 2] = b.z; qv[4 * k + 3] = b.w;
+    for (int phase = 0; phase < 2; phase++) {
+        const bool need = !final_row;
+        if (phase == 1 && !__any_sync(0xffffffffu, need)) break;   // the common case: every row of the warp was settled by phase 0
+        // b) the 16 candidate rows of this phase (chunks 2*phase, 2*phase + 1), fetched COOPERATIVELY -- for each row the 16
+        //    threads of the group read its 256 contiguous bytes as one float4 each, so a load instruction touches 4 lines per
+        //    warp instead of 32 -- parked in shared memory (row stride 68 floats: the float4 reads below are conflict free).
+        {
+            float4 stage[8];
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                const int cid = win_id[grp][2 * phase + half];
+#pragma unroll
+                for (int cc = 0; cc < 8; cc++) {
+                    const int cj = cid * CHUNK + cc;
+                    const bool ok = need && cid >= 0 && cj < nt;
+                    stage[cc] = ok ? __ldg(reinterpret_cast<const float4*>(t + (size_t)cj * DIM) + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int cc = 0; cc < 8; cc++) *reinterpret_cast<float4*>(&ts[grp][half * 8 + cc][4 * e]) = stage[cc];
+            }
         }
-        const float dsq = l2sqr_opencv<DIM>(qv, tv);
-        best.d0 = __fsqrt_rn(dsq);
-        best.i0 = j;
-        exact_v = dsq - na[r];   // exact value on the scale of the approximate ones
-    }
-    // diagnostics: |chunk minimum (approx) - min over its 4 rows (exact)|, relative to the bound scale
-    float gmin = exact_v;
-    gmin = fminf(gmin, __shfl_xor_sync(0xffffffffu, gmin, 1));
-    gmin = fminf(gmin, __shfl_xor_sync(0xffffffffu, gmin, 2));
-    // c) top-2 over the 16 threads of the row
+        __syncwarp();
+        const int chunk = win_id[grp][2 * phase + (e >> 3)];
+        const float chunk_v = win_v[grp][2 * phase + (e >> 3)];
+        const int j = chunk * CHUNK + (e & 7);
+        const bool valid = need && chunk >= 0 && j < nt;
+        Top2 cur = top2_empty();
+        float exact_v = INF;
+        if (valid) {
+            float tv[DIM], qv[DIM];
+            const float4* tp = reinterpret_cast<const float4*>(&ts[grp][e][0]);
+            const float4* qp = reinterpret_cast<const float4*>(&qs[grp][0]);
 #pragma unroll
-    for (int o = 1; o < 16; o <<= 1) {
-        Top2 other;
-        other.d0 = __shfl_xor_sync(0xffffffffu, best.d0, o);
-        other.d1 = __shfl_xor_sync(0xffffffffu, best.d1, o);
-        other.i0 = __shfl_xor_sync(0xffffffffu, best.i0, o);
-        other.i1 = __shfl_xor_sync(0xffffffffu, best.i1, o);
-        best = top2_merge(best, other);
-    }
-    const float scale = na[r] + *nb_max;
-    if (active && dbg_max_err && (e & 3) == 0 && chunk >= 0 && gmin < INF && scale > 0.f) {
-        const float err = fabsf(gmin - chunk_v) / scale;
-        atomicMax((int*)dbg_max_err, __float_as_int(err));   // non-negative floats order like ints
+            for (int k = 0; k < DIM / 4; k++) {
+                const float4 a = tp[k];
+                tv[4 * k] = a.x; tv[4 * k + 1] = a.y; tv[4 * k + 2] = a.z; tv[4 * k + 3] = a.w;
+                const float4 b = qp[k];
+                qv[4 * k] = b.x; qv[4 * k + 1] = b.y; qv[4 * k + 2] = b.z; qv[4 * k + 3] = b.w;
+            }
+            const float dsq = l2sqr_opencv<DIM>(qv, tv);
+            cur.d0 = __fsqrt_rn(dsq);
+            cur.i0 = j;
+            exact_v = dsq - na_r;   // exact value on the scale of the approximate ones
+        }
+        // diagnostics: |chunk key (approx) - min over its 8 rows (exact)|, relative to the bound scale
+        float gmin = exact_v;
+        gmin = fminf(gmin, __shfl_xor_sync(0xffffffffu, gmin, 1));
+        gmin = fminf(gmin, __shfl_xor_sync(0xffffffffu, gmin, 2));
+        gmin = fminf(gmin, __shfl_xor_sync(0xffffffffu, gmin, 4));
+        if (active && need && dbg_max_err && (e & 7) == 0 && chunk >= 0 && gmin < INF && scale > 0.f) {
+            // net of the key truncation (< 2^-14 |key|, covered separately by KEY_TRUNC_REL): what DELTA_COEF has to cover
+            const float err = fmaxf(0.f, fabsf(gmin - chunk_v) - fabsf(chunk_v) * (1.f / 16384.f)) / scale;
+            atomicMax((int*)dbg_max_err, __float_as_int(err));   // non-negative floats order like ints
+        }
+        // top-2 over the 16 threads of the row, then into the running result
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+            Top2 other;
+            other.d0 = __shfl_xor_sync(0xffffffffu, cur.d0, o);
+            other.d1 = __shfl_xor_sync(0xffffffffu, cur.d1, o);
+            other.i0 = __shfl_xor_sync(0xffffffffu, cur.i0, o);
+            other.i1 = __shfl_xor_sync(0xffffffffu, cur.i1, o);
+            cur = top2_merge(cur, other);
+        }
+        if (need) {
+            best = top2_merge(best, cur);
+            // final iff no row outside the evaluated chunks can reach the second best:  d1^2 (rounded up) < B + |a|^2 - delta,
+            // B = the best key that was NOT evaluated yet (phase 0: rank 2) or the last evaluated one (phase 1: rank 3)
+            const float B = win_v[grp][phase == 0 ? 2 : NCAND - 1];
+            const float delta = DELTA_COEF * scale + KEY_TRUNC_REL * fabsf(B);
+            const float d1sq_up = best.d1 * best.d1 * (1.f + 5e-7f);
+            final_row = !(B < INF) || (best.i1 != KNN_MISSING && d1sq_up < B + na_r - delta);
+        }
+        __syncwarp();
     }
     if (active && e == 0) {
-        // final iff no row outside the candidate chunks can reach the second best:
-        //   d1^2 (rounded up) < B + |a|^2 - delta
-        const float delta = DELTA_COEF * scale;
-        const float d1sq_up = best.d1 * best.d1 * (1.f + 5e-7f);
-        const bool safe = !(B < INF) || (best.i1 != KNN_MISSING && d1sq_up < B + na[r] - delta);
-        if (safe) top[row] = best;
+        if (final_row) top[row] = best;
         else {
             const int k = atomicAdd(fb_count, 1);
             fb_list[k] = row;

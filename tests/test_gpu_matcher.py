@@ -107,6 +107,39 @@ def test_tensor_path_error_bound_and_fallback(ctx):
     assert ctx.match_stats().max_rel_err < 1e-5
 
 
+@pytest.mark.parametrize("kind", ["all_positive", "dominant_component", "norm_decades", "tiny_and_huge"])
+def test_tensor_path_adversarial_error_bound(ctx, kind):
+    """Inputs built to stress the filter's error bound (derivation next to DELTA_COEF in matcher_tc.cu): all-positive
+    SIFT-like rows (every product of a dot product has the same sign, |a.b| ~ |a||b|), rows with one dominant component,
+    norms spanning four decades.  The kNN tables must still equal the exact SIMT kernel bit for bit and the largest
+    filter error the kernel saw must stay under the assumed 4e-5 (|a|^2 + max|b|^2)."""
+    rng = np.random.default_rng(123)
+    nq, nt = 2048, 4096
+    if kind == "all_positive":
+        A = synth.unit_rows(np.abs(rng.standard_normal((nq, 64)))).astype(np.float32)
+        B = synth.unit_rows(np.abs(rng.standard_normal((nt, 64)))).astype(np.float32)
+        B[:512] = synth.unit_rows(A[:512].astype(np.float64) + 0.01 * np.abs(rng.standard_normal((512, 64)))).astype(np.float32)
+    elif kind == "dominant_component":
+        A = (0.02 * rng.standard_normal((nq, 64))).astype(np.float32); A[np.arange(nq), rng.integers(0, 64, nq)] = 1.0
+        B = (0.02 * rng.standard_normal((nt, 64))).astype(np.float32); B[np.arange(nt), rng.integers(0, 64, nt)] = 1.0
+    elif kind == "norm_decades":
+        A = (synth.unit_rows(rng.standard_normal((nq, 64))) * 10.0 ** rng.uniform(-2, 2, (nq, 1))).astype(np.float32)
+        B = (synth.unit_rows(rng.standard_normal((nt, 64))) * 10.0 ** rng.uniform(-2, 2, (nt, 1))).astype(np.float32)
+    else:
+        A = (synth.unit_rows(rng.standard_normal((nq, 64))) * np.where(rng.random((nq, 1)) < 0.5, 1e-3, 1e3)).astype(np.float32)
+        B = (synth.unit_rows(rng.standard_normal((nt, 64))) * np.where(rng.random((nt, 1)) < 0.5, 1e-3, 1e3)).astype(np.float32)
+    mt = ctx.match_two_image(A, B, 0.3, algo=MATCH_TENSOR, want_knn=True)
+    st = ctx.match_stats()
+    ms = ctx.match_two_image(A, B, 0.3, algo=MATCH_SIMT_EXACT, want_knn=True)
+    assert st.algo_used == MATCH_TENSOR
+    assert 0.0 <= st.max_rel_err < 4e-5, (kind, st.max_rel_err)
+    assert np.array_equal(mt.knn_idx, ms.knn_idx) and np.array_equal(mt.knn_dist.view(np.uint32), ms.knn_dist.view(np.uint32))
+    assert np.array_equal(mt.query_idx, ms.query_idx) and np.array_equal(mt.train_idx, ms.train_idx)
+    idx, dist = oracle.knn2_l2(A[:64], B)
+    assert np.array_equal(mt.knn_idx[:64], idx) and np.array_equal(mt.knn_dist[:64].view(np.uint32), dist.view(np.uint32))
+    print(kind, "fallback rows", st.n_fallback_rows, "max_rel_err", st.max_rel_err)
+
+
 def test_matcher_full_size_properties(ctx):
     """BASELINE config-2 size (16k x 16k): the oracle needs ~1 min here, so check size-independent
     properties: every planted pair is recovered exactly, AUTO == SIMT bit-for-bit, and a sampled
@@ -123,6 +156,34 @@ def test_matcher_full_size_properties(ctx):
     rows = np.random.default_rng(0).choice(16384, 256, replace=False)
     idx, dist = oracle.knn2_l2(A[rows], B)
     assert np.array_equal(ms.knn_idx[rows], idx) and np.array_equal(ms.knn_dist[rows].view(np.uint32), dist.view(np.uint32))
+
+
+@pytest.mark.timeout(900)
+def test_matcher_c2_all_rows_against_oracle(ctx):
+    """BASELINE config 2, every one of the 16 384 rows: the tensor path's full kNN table equals the oracle's (OpenMP, ~1 min)."""
+    A, B, _ = synth.make_descriptors(16384, 16384, 64, seed=3)
+    ma = ctx.match_two_image(A, B, 0.3, algo=MATCH_TENSOR, want_knn=True)
+    oracle.set_threads(os.cpu_count() or 1)
+    idx, dist = oracle.knn2_l2(A, B)
+    assert np.array_equal(ma.knn_idx, idx) and np.array_equal(ma.knn_dist.view(np.uint32), dist.view(np.uint32))
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("nq,nt,seed", [(65536, 65536, 1), (50001, 63999, 2)])
+def test_matcher_sweep_top_size_against_exact_kernel(ctx, nq, nt, seed):
+    """BASELINE config 5's largest size (and a ragged one): tensor path vs the exact SIMT kernel, full kNN tables bit for bit,
+    with forty duplicates of one train row (more exact ties than a candidate list holds -> fallback rows)."""
+    import torch
+    A, B, _ = synth.make_descriptors(nq, nt, 64, seed=seed)
+    B[100:140] = B[99]
+    a, b = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    t = ctx.match_two_image(a, b, 0.3, algo=MATCH_TENSOR, want_knn=True)
+    st = ctx.match_stats()
+    s = ctx.match_two_image(a, b, 0.3, algo=MATCH_SIMT_EXACT, want_knn=True)
+    torch.cuda.synchronize()
+    assert torch.equal(t.knn_idx, s.knn_idx) and torch.equal(t.knn_dist.view(torch.int32), s.knn_dist.view(torch.int32))
+    assert len(t) == len(s) and torch.equal(t.query_idx, s.query_idx) and torch.equal(t.train_idx, s.train_idx)
+    assert st.n_fallback_rows >= 1 and st.max_rel_err < 4e-5
 
 
 @pytest.mark.parametrize("n_ctas", [1, 37, 74])
