@@ -56,7 +56,7 @@ constexpr int B_KBLOCK_BYTES = BN * 128;   // 16 KB
 constexpr int SMEM_A = 2 * A_KBLOCK_BYTES;                 // hi, lo
 constexpr int SMEM_B = STAGES * 2 * B_KBLOCK_BYTES;        // stages x {hi, lo}
 constexpr int SMEM_NB = EPI_WARPS * 64 * 4;                 // |b|^2 staging, 64 columns per epilogue warp
-constexpr int SMEM_BYTES = SMEM_A + SMEM_B + SMEM_NB + 256 /*barriers: 18 x 8 B + the TMEM slot*/ + 1024 /*alignment slack*/;
+constexpr int SMEM_BYTES = SMEM_A + SMEM_B + SMEM_NB + 256 /*barriers: 20 x 8 B + the TMEM slot*/ + 1024 /*alignment slack*/;
 constexpr int ACC_COLS = 2 * BN;   // TMEM columns per accumulator stage: row-half 0 | row-half 1
 constexpr uint32_t TMEM_COLS = 512;
 constexpr float DELTA_COEF = 4e-5f;  // |approx - exact| <= DELTA_COEF * (|a|^2 + max|b|^2): derivation at tc_rerank_kernel
@@ -355,7 +355,8 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     // row-half 1 are still running, which also keeps the two halves' warps out of phase on every scheduler
     uint64_t* acc_full = bars + 2 + 2 * STAGES;   // [2 stages][2 halves]
     uint64_t* acc_empty = bars + 6 + 2 * STAGES;  // [2 stages][2 halves]
-    uint32_t* tmem_slot = (uint32_t*)(bars + 10 + 2 * STAGES);
+    uint64_t* turn = bars + 10 + 2 * STAGES;      // [2]: issue-order token between the two MMA issuer warps
+    uint32_t* tmem_slot = (uint32_t*)(bars + 12 + 2 * STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) TC_TRACE(0);   // CTA start
@@ -369,6 +370,8 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         mbar_init(a_empty, 2);   // one arrival per MMA issuer warp
         for (int s = 0; s < STAGES; s++) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
         for (int s = 0; s < 4; s++) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, EPI_WARPS / 2); }
+        mbar_init(turn + 0, 1);
+        mbar_init(turn + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -438,6 +441,10 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 const int acc = n & 1;
                 mbar_wait(acc_empty + 2 * acc, (uint32_t)(((n >> 1) & 1) ^ 1));
                 mbar_wait(b_full + s, ring_phase);
+                // issue order: the tensor pipe runs MMAs in the order they arrive, so tile n+1 must not be issued before ALL of
+                // tile n has been (interleaved tiles would finish together and starve the epilogue's two-stage hand-over).
+                // The other warp passes the token as soon as its last MMA is queued; everything above already happened.
+                mbar_wait(turn + my_parity, (uint32_t)((n >> 1) & 1) ^ (uint32_t)(my_parity ^ 1));
                 tcgen05_fence_after();
                 if (n == 0 && is_leader) TC_TRACE(2);              // first operands landed
                 if (n == n_tiles - 1 && is_leader) TC_TRACE(3);    // last tile's MMAs about to issue
@@ -468,6 +475,7 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 #pragma unroll
                     for (int k = 0; k < 4; k++) umma_bf16(d1, dA_lo1 + 2 * k, dB_hi + 2 * k, IDESC, 1);
 #endif
+                    mbar_arrive(turn + (my_parity ^ 1));     // the other issuer may queue the next tile
                     tcgen05_commit(b_empty + s);             // B stage free once these MMAs have read it
                     tcgen05_commit(acc_full + 2 * acc + 1);  // row-half 1 ready
                 }
