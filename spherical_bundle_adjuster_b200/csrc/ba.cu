@@ -36,6 +36,7 @@
 
 #include "common.cuh"
 #include "bulk.cuh"
+#include "geometry.cuh"
 
 namespace sba {
 
@@ -72,15 +73,17 @@ __device__ inline void rot_and_derivs(const double r[3], double R[9], double dR[
 {
     double theta2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
     if (theta2 > DBL_EPSILON) {
-        double th = sqrt(theta2), s, c;
+        // one rsqrt instead of a square root and twelve divisions: this runs on the serial path of every LM iteration
+        const double inv_th = rsqrt(theta2), th = theta2 * inv_th;
+        double s, c;
         sincos(th, &s, &c);
-        double w[3] = {r[0] / th, r[1] / th, r[2] / th};
+        double w[3] = {r[0] * inv_th, r[1] * inv_th, r[2] * inv_th};
         double K[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
         for (int a = 0; a < 3; a++)
             for (int b = 0; b < 3; b++) R[3 * a + b] = (a == b ? c : 0.0) + s * K[3 * a + b] + (1.0 - c) * w[a] * w[b];
         for (int k = 0; k < 3; k++) {
             double dw[3];
-            for (int a = 0; a < 3; a++) dw[a] = ((a == k ? 1.0 : 0.0) - w[a] * w[k]) / th;
+            for (int a = 0; a < 3; a++) dw[a] = ((a == k ? 1.0 : 0.0) - w[a] * w[k]) * inv_th;
             double dK[9] = {0, -dw[2], dw[1], dw[2], 0, -dw[0], -dw[1], dw[0], 0};
             for (int a = 0; a < 3; a++)
                 for (int b = 0; b < 3; b++)
@@ -780,6 +783,276 @@ __global__ void __launch_bounds__(EVAL_THREADS, 3) ba_rot_eval_kernel(EvalArgs E
     }
 }
 
+// ---- one launch for a whole image pair's rotation solve (fused pair pipeline) ------------------------------------------
+// A C2-sized pair has ~8 k matches: one evaluation is 256 KB of bearings and under a microsecond of arithmetic spread
+// over a few SMs, so a solve made of one launch per LM evaluation (plus the bearing and table kernels before it) is
+// launch gaps and global-memory round trips, not work.  This kernel does everything between the match list and the
+// rotation in ONE launch of ONE thread-block cluster (16 CTAs, falling back to 8):
+//   1. matched keypoints -> ERP pixels -> unit bearings (equi2cube_surf.cpp:96-113 gather + cube2equi_pixel,
+//      spherical_bundle_adjuster.cpp:271-298), written to b1/b2 (each thread later re-reads only what it wrote);
+//   2. the LM loop: every CTA accumulates the moments of its observations (same arithmetic as ba_rot_eval_kernel)
+//      and stores its 16 sums straight into CTA 0's shared memory (distributed shared memory); after a cluster
+//      barrier CTA 0 adds them in rank order, runs the trust-region decision (lm_decide_single: lm_decide with the
+//      one-camera sums written out, one thread) and pushes the next candidate's rotation table and the done flag into
+//      every CTA's shared memory; second cluster barrier.  No global-memory hand-over inside an iteration.
+constexpr int PAIR_SOLVE_CLUSTER = 16;
+constexpr int PAIR_SOLVE_THREADS = 512;
+constexpr int PAIR_SOLVE_WARPS = PAIR_SOLVE_THREADS / 32;
+
+struct PairSolveArgs {
+    const float2* key_l;
+    const float2* key_r;
+    const int32_t* qi;
+    const int32_t* ti;
+    const int32_t* d_n;   // match count on the device
+    int cap, cs, w, h;
+    float4* b1;
+    float4* b2;
+    SolveConsts k;
+};
+
+// Damped 3x3 solve for the one-thread decision of the fused pair kernel.  Same Cholesky as solve3_spd, but every
+// division / square root is a reciprocal (__drcp_rn) or rsqrt() (inline MUFU seed + Newton, <= 1 ulp) times a multiply:
+// a correctly rounded fp64 division or square root is a ~40-instruction subroutine, and this code runs once, serially,
+// on the critical path of every LM iteration.  Results differ from solve3_spd in the last bit or two.
+__device__ inline int solve3_spd_fast(const double H[6], const double dd[3], const double rhs[3], double x[3])
+{
+    const double a00 = H[0] + dd[0], a01 = H[1], a02 = H[2], a11 = H[3] + dd[1], a12 = H[4], a22 = H[5] + dd[2];
+    if (!(a00 > 0.0)) return 1;
+    const double i00 = rsqrt(a00), l10 = a01 * i00, l20 = a02 * i00;      // 1 / l00
+    const double t11 = a11 - l10 * l10;
+    if (!(t11 > 0.0)) return 1;
+    const double i11 = rsqrt(t11), l21 = (a12 - l20 * l10) * i11;
+    const double t22 = a22 - l20 * l20 - l21 * l21;
+    if (!(t22 > 0.0)) return 1;
+    const double i22 = rsqrt(t22);
+    const double y0 = rhs[0] * i00, y1 = (rhs[1] - l10 * y0) * i11, y2 = (rhs[2] - l20 * y0 - l21 * y1) * i22;
+    x[2] = y2 * i22;
+    x[1] = (y1 - l21 * x[2]) * i11;
+    x[0] = (y0 - l10 * x[1] - l20 * x[2]) * i00;
+    return 0;
+}
+
+// lm_decide for ONE camera, one thread: every block_sum / block_max of lm_decide is over a single term here, so the
+// decisions (and the bits) are the same.  Returns with *A.st updated; A.params holds the tables of the new candidate.
+__device__ void lm_decide_single(const LMArrays A)
+{
+    const double min_diag = 1e-6, max_diag = 1e32, min_rel_dec = 1e-3;
+    const double ftol = 1e-6, gtol = 1e-10, ptol = 1e-8, max_radius = 1e16, min_radius = 1e-32;
+    LMState S = *A.st;
+    const double total_new = A.blk_cand[9];
+    int accept = 0;
+    S.evals++;
+    if (S.phase == 0) {
+        S.cost = total_new; S.initial_cost = total_new; S.phase = 1;
+        accept = 2;
+    } else {
+        const double cost_change = S.cost - total_new;
+        if (fabs(cost_change) <= ftol * S.cost) { S.termination = 1; S.done = 1; }
+        else {
+            const double rel = cost_change * __drcp_rn(S.model_dec);
+            if (rel > min_rel_dec) {
+                accept = 1;
+                S.cost = total_new;
+                S.num_successful++;
+                const double q = 2.0 * rel - 1.0;
+                S.radius = S.radius * __drcp_rn(fmax(1.0 / 3.0, 1.0 - q * q * q));
+                S.radius = fmin(max_radius, S.radius);
+                S.dec_factor = 2.0;
+            } else {
+                S.radius = S.radius * __drcp_rn(S.dec_factor);   // dec_factor is a power of two: exact
+                S.dec_factor *= 2.0;
+            }
+        }
+    }
+    if (accept) {
+        double gm = 0;
+        for (int k = 0; k < 10; k++) A.blk_cur[k] = A.blk_cand[k];
+        for (int k = 0; k < 3; k++) {
+            if (accept == 1) A.x[k] = A.xc[k];
+            gm = fmax(gm, fabs(A.blk_cand[6 + k]));
+        }
+        if (accept == 2) {
+            // 1 / (1 + sqrt(h)) with sqrt(h) = h * rsqrt(h)
+            const double h0 = A.blk_cand[0], h1 = A.blk_cand[3], h2 = A.blk_cand[5];
+            A.scale[0] = __drcp_rn(1.0 + (h0 > 0.0 ? h0 * rsqrt(h0) : 0.0));
+            A.scale[1] = __drcp_rn(1.0 + (h1 > 0.0 ? h1 * rsqrt(h1) : 0.0));
+            A.scale[2] = __drcp_rn(1.0 + (h2 > 0.0 ? h2 * rsqrt(h2) : 0.0));
+        }
+        if (gm <= gtol) { S.termination = 2; S.done = 1; }
+    }
+    if (!S.done && S.radius <= min_radius) { S.termination = 4; S.done = 1; }
+    while (!S.done) {
+        if (S.iter >= S.max_iter) { S.termination = 0; S.done = 1; break; }
+        const double radius = S.radius;
+        const double* B = A.blk_cur;
+        const double* s = A.scale;
+        double Hs[6] = {B[0] * s[0] * s[0], B[1] * s[0] * s[1], B[2] * s[0] * s[2], B[3] * s[1] * s[1], B[4] * s[1] * s[2], B[5] * s[2] * s[2]};
+        double gs[3] = {B[6] * s[0], B[7] * s[1], B[8] * s[2]};
+        const double inv_radius = __drcp_rn(radius);
+        double dd[3] = {fmin(fmax(Hs[0], min_diag), max_diag) * inv_radius, fmin(fmax(Hs[3], min_diag), max_diag) * inv_radius,
+                        fmin(fmax(Hs[5], min_diag), max_diag) * inv_radius};
+        double rhs[3] = {-gs[0], -gs[1], -gs[2]}, ds[3] = {0, 0, 0};
+        const int bad = solve3_spd_fast(Hs, dd, rhs, ds);
+        double Hd[3] = {Hs[0] * ds[0] + Hs[1] * ds[1] + Hs[2] * ds[2], Hs[1] * ds[0] + Hs[3] * ds[1] + Hs[4] * ds[2],
+                        Hs[2] * ds[0] + Hs[4] * ds[1] + Hs[5] * ds[2]};
+        double md = 0, sn2 = 0, xn2 = 0;
+        md -= (gs[0] * ds[0] + gs[1] * ds[1] + gs[2] * ds[2]) + 0.5 * (ds[0] * Hd[0] + ds[1] * Hd[1] + ds[2] * Hd[2]);
+        for (int a = 0; a < 3; a++) {
+            const double st = ds[a] * s[a], xv = A.x[a];
+            A.xc[a] = xv + st;
+            sn2 += st * st;
+            xn2 += xv * xv;
+        }
+        S.iter++;
+        if (bad || !(md > 0.0)) {
+            if (++S.consecutive_invalid >= 5) { S.termination = 4; S.done = 1; }
+            else {
+                S.radius *= 0.5;
+                if (S.radius <= min_radius) { S.termination = 4; S.done = 1; }
+            }
+            continue;   // retry in place: H and g do not change
+        }
+        S.consecutive_invalid = 0;
+        S.model_dec = md;
+        if ((sn2 > 0.0 ? sn2 * rsqrt(sn2) : 0.0) <= ptol * ((xn2 > 0.0 ? xn2 * rsqrt(xn2) : 0.0) + ptol)) { S.termination = 3; S.done = 1; }
+        break;
+    }
+    if (!S.done) {
+        double r[3] = {A.xc[0], A.xc[1], A.xc[2]};
+        write_cam_params(r, A.d1, A.params);
+    }
+    *A.st = S;
+}
+
+}  // namespace sba
+
+#include <cooperative_groups.h>
+
+namespace sba {
+
+#ifdef SBA_TC_TRACE
+// Debug build only (make trace): time stamps of rank 0 / thread 0, read back through sba_ps_trace_read().
+__device__ unsigned long long g_ps_trace[64];
+#define PS_TRACE(slot) do { if (rank == 0 && tid == 0 && (slot) < 64) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_ps_trace[(slot)] = t_; } } while (0)
+#else
+#define PS_TRACE(slot) do { } while (0)
+#endif
+
+__global__ void __launch_bounds__(PAIR_SOLVE_THREADS) ba_pair_solve_kernel(PairSolveArgs P, LMArrays A)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned int rank = cluster.block_rank(), nblk = cluster.num_blocks();
+    __shared__ double s_cta[PAIR_SOLVE_WARPS][NMOM];
+    __shared__ double s_part[PAIR_SOLVE_CLUSTER][NMOM];   // rank 0's copy receives every CTA's sums
+    __shared__ double s_R[9];
+    __shared__ int s_done;
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    const int n = min(P.cap, *P.d_n);
+    const int stride = nblk * PAIR_SOLVE_THREADS;
+    const double d1 = P.k.d1, d2 = P.k.d2, huber = P.k.huber, hub2 = huber * huber;
+    const double t0 = P.k.t[0], t1 = P.k.t[1], t2 = P.k.t[2];
+    int gen_ = 0;
+    PS_TRACE(0);
+    cluster.sync();                // every CTA of the cluster is running: its shared memory may be written remotely from here on
+    if (rank == 0 && tid == 0) {   // the starting rotation's tables: d1 * R into every CTA, derivative tables into A.params
+        double r[3] = {A.xc[0], A.xc[1], A.xc[2]};
+        write_cam_params(r, d1, A.params);
+        for (unsigned int q = 0; q < nblk; q++) {
+            double* dst = cluster.map_shared_rank(s_R, q);
+            for (int a = 0; a < 9; a++) dst[a] = A.params->Rd[a];
+            *cluster.map_shared_rank(&s_done, q) = 0;
+        }
+    }
+    // 1. bearings of this thread's matches
+    for (int i = rank * PAIR_SOLVE_THREADS + tid; i < n; i += stride) {
+        const float2 kl = P.key_l[P.qi[i]], kr = P.key_r[P.ti[i]];
+        float ex, ey;
+        double x, y, z;
+        cube2equi_point(kl.x, kl.y, P.cs, P.w, P.h, &ex, &ey);
+        pixel_to_bearing(ex, ey, (double)P.w, (double)P.h, &x, &y, &z);
+        P.b1[i] = make_float4((float)x, (float)y, (float)z, 0.f);
+        cube2equi_point(kr.x, kr.y, P.cs, P.w, P.h, &ex, &ey);
+        pixel_to_bearing(ex, ey, (double)P.w, (double)P.h, &x, &y, &z);
+        P.b2[i] = make_float4((float)x, (float)y, (float)z, 0.f);
+    }
+    PS_TRACE(1);
+    cluster.sync();
+    PS_TRACE(2);
+    // 2. the LM loop: one pass per evaluation
+    while (true) {
+        double acc[NMOM];
+#pragma unroll
+        for (int k = 0; k < NMOM; k++) acc[k] = 0;
+        for (int i = rank * PAIR_SOLVE_THREADS + tid; i < n; i += stride) {
+            const float4 p1 = P.b1[i], p2 = P.b2[i];
+            const double bx = (double)p1.x, by = (double)p1.y, bz = (double)p1.z;
+            const double rx = fma(d2, (double)p2.x, t0) - (s_R[0] * bx + s_R[1] * by + s_R[2] * bz);
+            const double ry = fma(d2, (double)p2.y, t1) - (s_R[3] * bx + s_R[4] * by + s_R[5] * bz);
+            const double rz = fma(d2, (double)p2.z, t2) - (s_R[6] * bx + s_R[7] * by + s_R[8] * bz);
+            const double s = rx * rx + ry * ry + rz * rz;
+            double rho = s, w = 1.0;
+            if (huber > 0.0 && s > hub2) {   // Huber: rho' = a / sqrt(s), rho = 2 a sqrt(s) - a^2 (same refinement as ba_rot_eval_kernel)
+                float y0;
+                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"((float)s));
+                double y = (double)y0;
+                y = y * (1.5 - 0.5 * s * y * y);
+                y = y * (1.5 - 0.5 * s * y * y);
+                w = huber * y;
+                rho = 2.0 * huber * (s * y) - hub2;
+            }
+            const double wx = w * bx, wy = w * by, wz = w * bz;
+            acc[0] = fma(wx, bx, acc[0]); acc[1] = fma(wx, by, acc[1]); acc[2] = fma(wx, bz, acc[2]);
+            acc[3] = fma(wy, by, acc[3]); acc[4] = fma(wy, bz, acc[4]); acc[5] = fma(wz, bz, acc[5]);
+            acc[6] = fma(wx, rx, acc[6]); acc[7] = fma(wx, ry, acc[7]); acc[8] = fma(wx, rz, acc[8]);
+            acc[9] = fma(wy, rx, acc[9]); acc[10] = fma(wy, ry, acc[10]); acc[11] = fma(wy, rz, acc[11]);
+            acc[12] = fma(wz, rx, acc[12]); acc[13] = fma(wz, ry, acc[13]); acc[14] = fma(wz, rz, acc[14]);
+            acc[15] = fma(0.5, rho, acc[15]);
+        }
+#pragma unroll
+        for (int k = 0; k < NMOM; k++) acc[k] = warp_sum(acc[k]);
+        if (lane == 0)
+#pragma unroll
+            for (int k = 0; k < NMOM; k++) s_cta[wib][k] = acc[k];
+        __syncthreads();
+        if (tid < NMOM) {   // this CTA's sums -> CTA 0's shared memory
+            double t = 0;
+            for (int w8 = 0; w8 < PAIR_SOLVE_WARPS; w8++) t += s_cta[w8][tid];
+            cluster.map_shared_rank(&s_part[0][0], 0)[rank * NMOM + tid] = t;
+        }
+        PS_TRACE(3 + 4 * gen_);
+        cluster.sync();
+        PS_TRACE(4 + 4 * gen_);
+        if (rank == 0) {   // warp 0: fold in rank order (16 lanes), moments -> block and the decision (lane 0), broadcast (one lane per CTA)
+            if (tid < NMOM) {
+                double t = 0;
+                for (unsigned int q = 0; q < nblk; q++) t += s_part[q][tid];   // rank order
+                s_cta[0][tid] = t;
+            }
+            __syncwarp();
+            if (tid == 0) {
+                moments_to_block(&s_cta[0][0], A.params, d1, A.blk_cand);   // A.params: the tables of the candidate just evaluated
+                lm_decide_single(A);                                         // ... and now of the next one
+            }
+            __syncwarp();
+            if (tid < (int)nblk) {
+                const int done = *((volatile int*)&A.st->done);
+                double* dst = cluster.map_shared_rank(s_R, tid);
+                if (!done)
+#pragma unroll
+                    for (int a = 0; a < 9; a++) dst[a] = ((volatile double*)A.params->Rd)[a];
+                *cluster.map_shared_rank(&s_done, tid) = done;
+            }
+        }
+        PS_TRACE(5 + 4 * gen_);
+        cluster.sync();
+        PS_TRACE(6 + 4 * gen_);
+        gen_++;
+        if (s_done) break;
+    }
+}
+
 // blocks [n_cam x 10] -> H [n_cam x 6], g [n_cam x 3], cost [n_cam]
 __global__ void ba_unpack_blocks_kernel(const double* __restrict__ blk, int n_cam, double* __restrict__ H, double* __restrict__ g,
                                         double* __restrict__ cost)
@@ -1333,6 +1606,53 @@ int ba_solve_enqueue(sba_ba_problem* p, const double t[3], double d1, double d2,
     return SBA_OK;
 }
 
+// Fused alternative to (2) for the pair pipeline: keypoints + match list in, the whole solve enqueued as ONE launch.
+int ba_pair_solve_enqueue(sba_ba_problem* p, const float* key_l, const float* key_r, const int32_t* qi, const int32_t* ti, const int32_t* d_n,
+                          int cap, int cs, int w, int h, const double t[3], double d1, double d2, double huber, int max_iter, int* launched)
+{
+    sba_ctx* c = p->ctx;
+    cudaStream_t st = c->stream;
+    SBA_CUDA(cudaMemcpyAsync(p->x, p->h_x, 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    SBA_CUDA(cudaMemcpyAsync(p->xc, p->x, 3 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    SBA_CUDA(cudaMemcpyAsync(p->state, p->h_state, sizeof(LMState), cudaMemcpyHostToDevice, st));
+    PairSolveArgs P;
+    P.key_l = (const float2*)key_l; P.key_r = (const float2*)key_r; P.qi = qi; P.ti = ti; P.d_n = d_n;
+    P.cap = cap; P.cs = cs; P.w = w; P.h = h; P.b1 = p->b1; P.b2 = p->b2;
+    P.k.t[0] = t[0]; P.k.t[1] = t[1]; P.k.t[2] = t[2]; P.k.d1 = d1; P.k.d2 = d2; P.k.huber = huber;
+    LMArrays A = make_lm_arrays(p);
+    A.d1 = d1;
+    // one cluster: 16 CTAs (needs the non-portable cluster size attribute), else the portable 8
+    static int cluster_size = 0;
+    if (cluster_size == 0) {
+        cluster_size = 8;
+        if (cudaFuncSetAttribute(ba_pair_solve_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+            cudaLaunchConfig_t probe = {};
+            cudaLaunchAttribute pa[1];
+            pa[0].id = cudaLaunchAttributeClusterDimension;
+            pa[0].val.clusterDim.x = PAIR_SOLVE_CLUSTER; pa[0].val.clusterDim.y = 1; pa[0].val.clusterDim.z = 1;
+            probe.gridDim = dim3(PAIR_SOLVE_CLUSTER); probe.blockDim = dim3(PAIR_SOLVE_THREADS); probe.attrs = pa; probe.numAttrs = 1;
+            int n_clusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&n_clusters, ba_pair_solve_kernel, &probe) == cudaSuccess && n_clusters >= 1) cluster_size = PAIR_SOLVE_CLUSTER;
+        }
+        cudaGetLastError();
+    }
+    const int grid = std::max(1, std::min(cluster_size, (cap + PAIR_SOLVE_THREADS - 1) / PAIR_SOLVE_THREADS));   // small pairs: a smaller cluster
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)grid; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(PAIR_SOLVE_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+    prof_begin(c, SBA_KERNEL_BA_EVAL);
+    SBA_CUDA(cudaLaunchKernelEx(&cfg, ba_pair_solve_kernel, P, A));
+    prof_end(c, SBA_KERNEL_BA_EVAL);
+    SBA_LAUNCHED(c);
+    SBA_CUDA(cudaGetLastError());
+    SBA_CUDA(cudaMemcpyAsync(p->h_state, p->state, sizeof(LMState), cudaMemcpyDeviceToHost, st));
+    SBA_CUDA(cudaMemcpyAsync(p->h_x, p->x, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    *launched = max_iter + 1;   // the kernel runs the solve to completion: ba_solve_finish has nothing to add
+    return SBA_OK;
+}
+
 // (3) wait for the enqueued chunk; keep going chunk by chunk until the solver reports done.
 int ba_solve_finish(sba_ba_problem* p, double* r_out, const double t[3], double d1, double d2, double huber, int max_iter, int launched,
                     sba_solve_summary* summary, bool tran)
@@ -1497,3 +1817,10 @@ int sba_ba_rot_eval_timed(sba_ba_problem* p, const double* r, const double t[3],
 }
 
 }  // extern "C"
+
+#ifdef SBA_TC_TRACE
+extern "C" int sba_ps_trace_read(unsigned long long* out /* [64] */)
+{
+    return cudaMemcpyFromSymbol(out, sba::g_ps_trace, sizeof(unsigned long long) * 64) == cudaSuccess ? 0 : -1;
+}
+#endif

@@ -156,6 +156,7 @@ enum ScratchSlot {
     // buffers owned by the fused pair pipeline (pipeline.cu); the stage entry points never touch them
     SCR_PIPE_IM0, SCR_PIPE_IM1, SCR_PIPE_STRIP0, SCR_PIPE_STRIP1, SCR_PIPE_DESC0, SCR_PIPE_DESC1, SCR_PIPE_KEY0, SCR_PIPE_KEY1,
     SCR_PIPE_MATCH, SCR_PIPE_PTS, SCR_PIPE_BEAR,
+    SCR_FIN_COUNTS,   // epoch-tagged survivor counts of knn2_finalize_kernel
     SCR_COUNT
 };
 
@@ -174,6 +175,10 @@ struct sba_ctx {
     std::map<std::pair<int, int>, int32_t*> band_plans;                  // the four bands of spherical_surf::do_all in one table
     std::map<std::pair<int, int>, sba::TiledPlan> band_tiled;             // ... and its tiled form
     sba_match_stats match_stats{};
+    unsigned int fin_epoch = 0;   // call counter of knn2_finalize_kernel (tags its count slots)
+    const void* fb_parts = nullptr;   // tensor matcher -> finalize: partial top-2 lists of the exact fallback (Top2*), queue length, scan grid
+    const int* fb_count = nullptr;
+    int fb_grid = 0;
     int matcher_ctas = 0;       // persistent CTAs of the tensor-core matcher; 0 = one per SM (sba_ctx_set_matcher_ctas)
     int remap_kernel = 0;       // 0 = per-plan choice from the timed trial, 1 = direct gather, 2 = tiled gather (sba_ctx_set_remap_kernel)
     bool pair_pending = false;  // a sba_pair_rotation_begin whose _end has not run yet (pipeline.cu)
@@ -260,6 +265,8 @@ BaView ba_problem_view(sba_ba_problem* p);
 // remap.cu: out[img][p] = erp[img][lut[p]] (3-byte pixels); masked tables hold -1 for "no source", which gives 0
 int launch_lut_gather(sba_ctx* c, const uint8_t* d_erp, int64_t src_bytes, const int32_t* lut, int rows, int cols, uint8_t* d_out, int n_images,
                       bool masked, const TiledPlan* tiled = nullptr, int src_w = 0);
+// remap.cu: both images of a pair (separate device buffers) through equi2cube::get_all, one launch when possible
+int equi2cube_pair(sba_ctx* c, const uint8_t* d_im0, const uint8_t* d_im1, int w, int h, int cs, uint8_t* d_s0, uint8_t* d_s1);
 // remap.cu: derive the tiled form of a finished table (source image w x h)
 int build_tiled_plan(sba_ctx* c, const int32_t* lut, int rows, int cols, int w, int h, bool masked, TiledPlan* out);
 void free_tiled_plan(TiledPlan* tp);
@@ -267,6 +274,9 @@ void free_tiled_plan(TiledPlan* tp);
 // ba.cu: the LM solve in three parts (host mailboxes, stream work, collection) so a caller can queue it without waiting
 void ba_solve_prepare_host(sba_ba_problem* p, const double* r0, int max_iter);
 int ba_solve_enqueue(sba_ba_problem* p, const double t[3], double d1, double d2, double huber, int max_iter, int* launched, bool tran = false);
+// the pair pipeline's one-launch variant of ba_solve_enqueue: matched keypoints -> bearings -> the whole LM solve
+int ba_pair_solve_enqueue(sba_ba_problem* p, const float* key_l, const float* key_r, const int32_t* qi, const int32_t* ti, const int32_t* d_n,
+                          int cap, int cs, int w, int h, const double t[3], double d1, double d2, double huber, int max_iter, int* launched);
 int ba_solve_finish(sba_ba_problem* p, double* r_out, const double t[3], double d1, double d2, double huber, int max_iter, int launched,
                     sba_solve_summary* summary, bool tran = false);
 

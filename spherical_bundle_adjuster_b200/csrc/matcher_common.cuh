@@ -8,6 +8,11 @@
 namespace sba {
 
 constexpr int KNN_MISSING = INT_MAX;  // internal "no neighbour" index (sorts after every real index)
+constexpr int KNN_FALLBACK = INT_MAX - 1;   // marker in a Top2's i0: the row was queued for the exact fallback, i1 = its queue position
+constexpr int FB_MAX_SPLIT = 64;
+
+// a queued row's exact scan is cut into this many ranges (chosen on the device from the queue length)
+__host__ __device__ inline int fb_splits(int n_rows, int grid) { return n_rows <= 0 ? 1 : max(1, min(FB_MAX_SPLIT, (2 * grid) / n_rows)); }
 
 struct Top2 {
     float d0, d1;
@@ -91,6 +96,6 @@ struct PreparedSet {
 
 // Runs after either matcher: per-query top-2 -> optional raw kNN output + ratio-test flags.
 int launch_knn_finish(sba_ctx* c, const Top2* d_top2, int nq, float ratio, int32_t* d_query_idx, int32_t* d_train_idx, float* d_dist,
-                      int32_t* d_n_matches, int32_t* d_knn_idx, float* d_knn_dist);
+                      int32_t* d_n_matches, int32_t* d_knn_idx, float* d_knn_dist, const Top2* d_fb_parts, const int* d_fb_count, int fb_grid);
 
 }  // namespace sba

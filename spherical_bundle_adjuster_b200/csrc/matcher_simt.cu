@@ -148,26 +148,40 @@ __global__ void knn2_merge_splits_kernel(const Top2* __restrict__ parts, int nq,
     out[i] = r;
 }
 
-// Ratio test (feature_matcher.cpp:47-56) + ordered compaction of the survivors, two small kernels:
-//   knn2_flags_kernel    1024 queries per CTA: raw kNN output, keep flag, per-CTA survivor count;
-//   knn2_compact_kernel  each CTA sums the counts of the CTAs before it (<= a few hundred values),
-//                        scans its own flags and scatters -- survivors stay in ascending query order.
+// Ratio test (feature_matcher.cpp:47-56) + ordered compaction of the survivors in ONE launch (knn2_finalize_kernel):
+// 1024 queries per CTA.  Every CTA publishes its survivor count tagged with the call's epoch, then sums the counts of
+// the CTAs before it (spinning only on counts that are not there yet -- all of them are written within a microsecond of
+// the launch, so this is one hop, not a chain), scans its own flags and scatters: survivors stay in ascending query
+// order.  Rows the tensor path queued for the exact fallback arrive as a marker in `top` (i0 == KNN_FALLBACK, i1 =
+// position in the queue) and their partial top-2 lists (one per scanned range) are merged here in range order.
 constexpr int FIN_THREADS = 1024;
+constexpr int FIN_EPOCH_SHIFT = 11;   // counts are <= 1024
 
 __device__ inline int keep_flag(const Top2& r, float ratio)
 {
     return (r.i0 != KNN_MISSING && r.i1 != KNN_MISSING && r.d0 < __fmul_rn(ratio, r.d1)) ? 1 : 0;
 }
 
-__global__ void __launch_bounds__(FIN_THREADS) knn2_flags_kernel(const Top2* __restrict__ top, int nq, float ratio, int32_t* __restrict__ knn_idx,
-                                                                float* __restrict__ knn_dist, int* __restrict__ block_counts)
+__global__ void __launch_bounds__(FIN_THREADS)
+knn2_finalize_kernel(const Top2* __restrict__ top, int nq, float ratio, int32_t* __restrict__ knn_idx, float* __restrict__ knn_dist,
+                     int32_t* __restrict__ query_idx, int32_t* __restrict__ train_idx, float* __restrict__ dist, int32_t* __restrict__ n_matches,
+                     unsigned int* __restrict__ counts, unsigned int epoch, const Top2* __restrict__ fb_parts, const int* __restrict__ fb_count,
+                     int fb_grid)
 {
-    __shared__ int warp_cnt[32];
+    __shared__ int warp_off[32];
+    __shared__ int s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int i = blockIdx.x * FIN_THREADS + tid;
+    Top2 r = top2_empty();
     int keep = 0;
     if (i < nq) {
-        const Top2 r = top[i];
+        r = top[i];
+        if (fb_parts && r.i0 == KNN_FALLBACK) {
+            const int S = fb_splits(*fb_count, fb_grid);
+            const Top2* part = fb_parts + (size_t)r.i1 * S;
+            r = part[0];
+            for (int sp = 1; sp < S; sp++) r = top2_merge(r, part[sp]);
+        }
         if (knn_idx) {
             knn_idx[2 * i] = r.i0 != KNN_MISSING ? r.i0 : -1;
             knn_idx[2 * i + 1] = r.i1 != KNN_MISSING ? r.i1 : -1;
@@ -179,50 +193,10 @@ __global__ void __launch_bounds__(FIN_THREADS) knn2_flags_kernel(const Top2* __r
         keep = keep_flag(r, ratio);
     }
     const unsigned ball = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) warp_cnt[warp] = __popc(ball);
-    __syncthreads();
-    if (warp == 0) {
-        int v = warp_cnt[lane];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) block_counts[blockIdx.x] = v;
-    }
-}
-
-__global__ void __launch_bounds__(FIN_THREADS) knn2_compact_kernel(const Top2* __restrict__ top, int nq, float ratio, const int* __restrict__ block_counts,
-                                                                  int32_t* __restrict__ query_idx, int32_t* __restrict__ train_idx,
-                                                                  float* __restrict__ dist, int32_t* __restrict__ n_matches)
-{
-    __shared__ int warp_off[32];
-    __shared__ int s_base;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // exclusive prefix of the CTAs before this one
-    int part = 0;
-    for (int b = tid; b < (int)blockIdx.x; b += FIN_THREADS) part += block_counts[b];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if (lane == 0) warp_off[warp] = part;
-    __syncthreads();
-    if (warp == 0) {
-        int v = warp_off[lane];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) s_base = v;
-    }
-    __syncthreads();
-    const int base = s_base;
-    const int i = blockIdx.x * FIN_THREADS + tid;
-    Top2 r = top2_empty();
-    int keep = 0;
-    if (i < nq) {
-        r = top[i];
-        keep = keep_flag(r, ratio);
-    }
-    const unsigned ball = __ballot_sync(0xffffffffu, keep);
     const int prefix = __popc(ball & ((1u << lane) - 1));
-    __syncthreads();
     if (lane == 0) warp_off[warp] = __popc(ball);
     __syncthreads();
+    int total = 0;
     if (warp == 0) {
         const int v = warp_off[lane];
         int incl = v;
@@ -232,11 +206,28 @@ __global__ void __launch_bounds__(FIN_THREADS) knn2_compact_kernel(const Top2* _
             if (lane >= o) incl += n;
         }
         warp_off[lane] = incl - v;
-        if (lane == 31 && blockIdx.x == gridDim.x - 1) *n_matches = base + incl;
+        total = __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 0) {
+            __threadfence();
+            ((volatile unsigned int*)counts)[blockIdx.x] = (epoch << FIN_EPOCH_SHIFT) | (unsigned int)total;
+        }
+        // counts of the CTAs before this one (this warp strides over them)
+        int before = 0;
+        for (int b = lane; b < (int)blockIdx.x; b += 32) {
+            unsigned int v2;
+            do { v2 = ((volatile unsigned int*)counts)[b]; } while ((v2 >> FIN_EPOCH_SHIFT) != epoch);
+            before += (int)(v2 & ((1u << FIN_EPOCH_SHIFT) - 1));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+        if (lane == 0) {
+            s_base = before;
+            if (blockIdx.x == gridDim.x - 1) *n_matches = before + total;
+        }
     }
     __syncthreads();
     if (keep) {
-        const int pos = base + warp_off[warp] + prefix;
+        const int pos = s_base + warp_off[warp] + prefix;
         query_idx[pos] = i;
         train_idx[pos] = r.i0;
         dist[pos] = r.d0;
@@ -244,14 +235,19 @@ __global__ void __launch_bounds__(FIN_THREADS) knn2_compact_kernel(const Top2* _
 }
 
 int launch_knn_finish(sba_ctx* c, const Top2* d_top2, int nq, float ratio, int32_t* d_query_idx, int32_t* d_train_idx, float* d_dist,
-                      int32_t* d_n_matches, int32_t* d_knn_idx, float* d_knn_dist)
+                      int32_t* d_n_matches, int32_t* d_knn_idx, float* d_knn_dist, const Top2* d_fb_parts, const int* d_fb_count, int fb_grid)
 {
     const int nblocks = (nq + FIN_THREADS - 1) / FIN_THREADS;
-    SBA_TRY(c->scratch[SCR_WORK4].ensure((size_t)nblocks * sizeof(int), c->stream));
-    int* d_counts = c->scratch[SCR_WORK4].as<int>();
-    knn2_flags_kernel<<<nblocks, FIN_THREADS, 0, c->stream>>>(d_top2, nq, ratio, d_knn_idx, d_knn_dist, d_counts);
-    SBA_LAUNCHED(c);
-    knn2_compact_kernel<<<nblocks, FIN_THREADS, 0, c->stream>>>(d_top2, nq, ratio, d_counts, d_query_idx, d_train_idx, d_dist, d_n_matches);
+    // the epoch-tagged count slots live in their own grow-only buffer; a fresh (or regrown) buffer and an epoch wrap start from zeros
+    const size_t cap_before = c->scratch[SCR_FIN_COUNTS].cap;
+    SBA_TRY(c->scratch[SCR_FIN_COUNTS].ensure((size_t)nblocks * sizeof(unsigned int), c->stream));
+    c->fin_epoch = (c->fin_epoch + 1) & ((1u << (32 - FIN_EPOCH_SHIFT)) - 1);
+    if (c->scratch[SCR_FIN_COUNTS].cap != cap_before || c->fin_epoch == 0) {
+        SBA_CUDA(cudaMemsetAsync(c->scratch[SCR_FIN_COUNTS].p, 0, c->scratch[SCR_FIN_COUNTS].cap, c->stream));
+        if (c->fin_epoch == 0) c->fin_epoch = 1;
+    }
+    knn2_finalize_kernel<<<nblocks, FIN_THREADS, 0, c->stream>>>(d_top2, nq, ratio, d_knn_idx, d_knn_dist, d_query_idx, d_train_idx, d_dist, d_n_matches,
+                                                                c->scratch[SCR_FIN_COUNTS].as<unsigned int>(), c->fin_epoch, d_fb_parts, d_fb_count, fb_grid);
     SBA_LAUNCHED(c);
     SBA_CUDA(cudaGetLastError());
     return SBA_OK;
@@ -337,6 +333,7 @@ static int knn2_ratio_impl(sba_ctx* c, const float* q, int nq, const float* t, i
     SBA_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     c->match_stats = sba_match_stats{};
+    c->fb_parts = nullptr; c->fb_count = nullptr; c->fb_grid = 0;   // set by the tensor path when it queues fallback rows
     if (nq == 0) {
         if (mem == SBA_MEM_HOST) *n_matches = 0;
         else SBA_CUDA(cudaMemsetAsync(n_matches, 0, sizeof(int32_t), st));
@@ -378,7 +375,7 @@ static int knn2_ratio_impl(sba_ctx* c, const float* q, int nq, const float* t, i
         else SBA_TRY(run_simt<128>(c, d_q, nq, d_t, nt, d_top));
     }
     c->match_stats.algo_used = use;
-    SBA_TRY(launch_knn_finish(c, d_top, nq, ratio, d_qi, d_ti, d_d, d_n, d_ki, d_kd));
+    SBA_TRY(launch_knn_finish(c, d_top, nq, ratio, d_qi, d_ti, d_d, d_n, d_ki, d_kd, (const Top2*)c->fb_parts, c->fb_count, c->fb_grid));
     if (mem == SBA_MEM_HOST) {
         SBA_CUDA(cudaMemcpyAsync(c->pinned_i32, d_n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         SBA_CUDA(cudaStreamSynchronize(st));

@@ -811,6 +811,9 @@ tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ 
         else {
             const int k = atomicAdd(fb_count, 1);
             fb_list[k] = row;
+            Top2 mark;                       // knn2_finalize_kernel merges the fallback's partial lists for this row
+            mark.d0 = mark.d1 = 0.f; mark.i0 = KNN_FALLBACK; mark.i1 = k;
+            top[row] = mark;
         }
     }
 }
@@ -818,13 +821,9 @@ tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ 
 // ---- 4. exact fallback for queued rows --------------------------------------------------------------------------
 // A queued row needs an exact scan of the whole train set.  The scan of each row is cut into S ranges
 // handled by different CTAs (S chosen on the device from the queue length so that a handful of rows at
-// 64k train rows still use the whole chip, while thousands of rows fall back to one CTA per row), then
-// tc_fallback_merge_kernel merges a row's S partial top-2 lists in range order.
+// 64k train rows still use the whole chip, while thousands of rows fall back to one CTA per row); the
+// row's S partial top-2 lists are merged in range order by knn2_finalize_kernel (matcher_simt.cu).
 constexpr int FB_THREADS = 128;
-constexpr int FB_MAX_SPLIT = 64;
-
-__host__ __device__ inline int fb_splits(int n_rows, int grid) { return n_rows <= 0 ? 1 : max(1, min(FB_MAX_SPLIT, (2 * grid) / n_rows)); }
-
 __global__ void __launch_bounds__(FB_THREADS)
 tc_fallback_kernel(const float* __restrict__ q, const float* __restrict__ t, int nt, const int* __restrict__ fb_list,
                    const int* __restrict__ fb_count, Top2* __restrict__ parts)
@@ -866,18 +865,6 @@ tc_fallback_kernel(const float* __restrict__ q, const float* __restrict__ t, int
             __syncthreads();
         }
         if (threadIdx.x == 0) parts[item] = sh[0];
-    }
-}
-
-__global__ void tc_fallback_merge_kernel(const int* __restrict__ fb_list, const int* __restrict__ fb_count, const Top2* __restrict__ parts,
-                                         int scan_grid, Top2* __restrict__ top)
-{
-    const int n = *fb_count;
-    const int S = fb_splits(n, scan_grid);
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        Top2 r = parts[(size_t)k * S];
-        for (int sp = 1; sp < S; sp++) r = top2_merge(r, parts[(size_t)k * S + sp]);
-        top[fb_list[k]] = r;
     }
 }
 
@@ -1008,8 +995,7 @@ int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, 
     SBA_LAUNCHED(c);
     tc_fallback_kernel<<<fb_grid, FB_THREADS, 0, st>>>(d_q, d_t, nt, d_fl, d_fb_count, d_fparts);
     SBA_LAUNCHED(c);
-    tc_fallback_merge_kernel<<<std::min((nq + 127) / 128, c->sm_count), 128, 0, st>>>(d_fl, d_fb_count, d_fparts, fb_grid, d_top);
-    SBA_LAUNCHED(c);
+    c->fb_parts = d_fparts; c->fb_count = d_fb_count; c->fb_grid = fb_grid;   // merged per row by knn2_finalize_kernel
     SBA_CUDA(cudaGetLastError());
     // diagnostics land in the pinned mailbox; read by sba_match_last_stats after a synchronise
     SBA_CUDA(cudaMemcpyAsync(c->pinned_i32 + 8, d_fb_count, 12, cudaMemcpyDeviceToHost, st));

@@ -22,27 +22,6 @@ using namespace sba;
 
 namespace sba {
 
-// Matched keypoints -> BA bearings in one pass (equi2cube_surf.cpp:96-113 gather + cube2equi_pixel, then
-// spherical_bundle_adjuster.cpp:271-298 pixel -> bearing).  The match count is read from device memory
-// so the host never waits for it; threads past the count write nothing.
-__global__ void pair_points_kernel(const float2* __restrict__ key_l, const float2* __restrict__ key_r, const int32_t* __restrict__ qi,
-                                   const int32_t* __restrict__ ti, const int32_t* __restrict__ d_n, int cap, int cs, int w, int h,
-                                   float4* __restrict__ b1, float4* __restrict__ b2)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n = min(cap, *d_n);
-    if (i >= n) return;
-    const float2 kl = key_l[qi[i]], kr = key_r[ti[i]];
-    float ex, ey;
-    double x, y, z;
-    cube2equi_point(kl.x, kl.y, cs, w, h, &ex, &ey);
-    pixel_to_bearing(ex, ey, (double)w, (double)h, &x, &y, &z);
-    b1[i] = make_float4((float)x, (float)y, (float)z, 0.f);
-    cube2equi_point(kr.x, kr.y, cs, w, h, &ex, &ey);
-    pixel_to_bearing(ex, ey, (double)w, (double)h, &x, &y, &z);
-    b2[i] = make_float4((float)x, (float)y, (float)z, 0.f);
-}
-
 // Everything that identifies one call's stream work.
 struct PairKey {
     const void *erp_l, *erp_r, *strip_l, *strip_r, *desc_l, *desc_r, *key_l, *key_r, *qi, *ti, *dist;
@@ -118,10 +97,8 @@ static int enqueue_pair(sba_ctx* c, const PairKey& a, const double r0[3], sba_ba
         else { SBA_TRY(c->scratch[SCR_PIPE_STRIP0].ensure(strip_bytes, st)); d_s0 = c->scratch[SCR_PIPE_STRIP0].as<uint8_t>(); }
         if (dev_out && strip_right_out) d_s1 = strip_right_out;
         else { SBA_TRY(c->scratch[SCR_PIPE_STRIP1].ensure(strip_bytes, st)); d_s1 = c->scratch[SCR_PIPE_STRIP1].as<uint8_t>(); }
-        if (overlap) SBA_CUDA(cudaStreamWaitEvent(st, c->copy_ev[0], 0));
-        SBA_TRY(sba_equi2cube(c, d_im0, w, h, 1, cube_size, d_s0, SBA_MEM_DEVICE));
-        if (overlap) SBA_CUDA(cudaStreamWaitEvent(st, c->copy_ev[1], 0));
-        SBA_TRY(sba_equi2cube(c, d_im1, w, h, 1, cube_size, d_s1, SBA_MEM_DEVICE));
+        if (overlap) SBA_CUDA(cudaStreamWaitEvent(st, c->copy_ev[1], 0));   // recorded after both uploads on the copy stream
+        SBA_TRY(equi2cube_pair(c, d_im0, d_im1, w, h, cube_size, d_s0, d_s1));
         if (!dev_out) {
             SBA_TRY(copy_out(c, strip_left_out, d_s0, strip_bytes, mem));
             SBA_TRY(copy_out(c, strip_right_out, d_s1, strip_bytes, mem));
@@ -152,13 +129,12 @@ static int enqueue_pair(sba_ctx* c, const PairKey& a, const double r0[3], sba_ba
         // ---- matched keypoints -> bearings (capacity n_left; the kernel stops at the device-side count)
         SBA_TRY(c->scratch[SCR_PIPE_BEAR].ensure((size_t)2 * n_left * 4 * sizeof(float), st));
         float* d_b = c->scratch[SCR_PIPE_BEAR].as<float>();   // [cap] float4 left bearings, [cap] float4 right bearings
-        pair_points_kernel<<<(n_left + 255) / 256, 256, 0, st>>>((const float2*)d_key0, (const float2*)d_key1, ps->d_qi, ps->d_ti, d_n, n_left,
-                                                                cube_size, w, h, (float4*)d_b, (float4*)d_b + n_left);
-        SBA_LAUNCHED(c);
-        // ---- rotation-only bundle adjustment on the bearings in place: set-up + first chunk of evaluations
+        // ---- matched keypoints -> bearings + the whole rotation-only solve in ONE launch (ba_pair_solve_kernel); the
+        //      bearings land in d_b, which the problem borrows, so later stages can still read them
         if (!*prob) SBA_TRY(ba_problem_create_impl(c, d_b, d_b + (size_t)4 * n_left, nullptr, n_left, 1, D, /*borrow=*/true, d_n, prob));
         ba_solve_prepare_host(*prob, r0, a.max_iter);   // pinned mailboxes
-        SBA_TRY(ba_solve_enqueue(*prob, a.t, a.d1, a.d2, a.huber, a.max_iter, launched));
+        SBA_TRY(ba_pair_solve_enqueue(*prob, d_key0, d_key1, ps->d_qi, ps->d_ti, d_n, n_left, cube_size, w, h, a.t, a.d1, a.d2, a.huber, a.max_iter,
+                                      launched));
     }
     if (overlap) SBA_TRY(remap_both());
     SBA_CUDA(cudaGetLastError());

@@ -130,17 +130,22 @@ static int get_plan(sba_ctx* c, int w, int h, int cs, RemapPlan** out)
 template <bool MASKED>
 __global__ void __launch_bounds__(256)
 remap_gather_warp_kernel(const uint8_t* __restrict__ erp, const int32_t* __restrict__ lut, uint8_t* __restrict__ out,
-                         int64_t src_bytes_per_image, int64_t P, int groups128, int n_images)
+                         int64_t src_bytes_per_image, int64_t P, int groups128, int n_images,
+                         const uint8_t* __restrict__ erp2 = nullptr, uint8_t* __restrict__ out2 = nullptr, int n_first = 0)
 {
+    // erp2/out2: a second, separately allocated run of images (images >= n_first come from there) -- lets the pair pipeline
+    // remap its two ERP images, which live in two buffers, with ONE launch.
     __shared__ __align__(16) uint32_t pix[8][128];
     __shared__ __align__(16) uint32_t stage[8][96];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int total = groups128 * n_images;          // 32-bit group arithmetic (the launcher splits larger batches)
     const int64_t last_word = src_bytes_per_image / 4 - 1;
     for (int g = blockIdx.x * 8 + wib; g < total; g += gridDim.x * 8) {
-        const int img = g / groups128;
+        int img = g / groups128;
         const int grp = g - img * groups128;
-        const uint32_t* words = reinterpret_cast<const uint32_t*>(erp + (int64_t)img * src_bytes_per_image);
+        const bool second = erp2 != nullptr && img >= n_first;
+        if (second) img -= n_first;
+        const uint32_t* words = reinterpret_cast<const uint32_t*>((second ? erp2 : erp) + (int64_t)img * src_bytes_per_image);
         const int32_t* tab = lut + (int64_t)grp * 128 + lane;
         int idx[4];
 #pragma unroll
@@ -168,7 +173,7 @@ remap_gather_warp_kernel(const uint8_t* __restrict__ erp, const int32_t* __restr
         __syncwarp();
         if (lane < 24) {
             const uint4 o = *reinterpret_cast<const uint4*>(&stage[wib][lane * 4]);
-            uint8_t* dst = out + ((int64_t)img * P + (int64_t)grp * 128) * 3 + lane * 16;
+            uint8_t* dst = (second ? out2 : out) + ((int64_t)img * P + (int64_t)grp * 128) * 3 + lane * 16;
             *reinterpret_cast<uint4*>(dst) = o;
         }
         __syncwarp();   // both staging rows are rewritten by the next group
@@ -504,6 +509,32 @@ int launch_lut_gather(sba_ctx* c, const uint8_t* d_erp, int64_t src_bytes, const
     }
     SBA_CUDA(cudaGetLastError());
     return SBA_OK;
+}
+
+// equi2cube::get_all of the two images of a pair (two separate device buffers in, two out) with one launch when the fast
+// kernel applies; otherwise two ordinary calls.
+int equi2cube_pair(sba_ctx* c, const uint8_t* d_im0, const uint8_t* d_im1, int w, int h, int cs, uint8_t* d_s0, uint8_t* d_s1)
+{
+    RemapPlan* plan;
+    SBA_TRY(get_plan(c, w, h, cs, &plan));
+    const int64_t P = (int64_t)cs * 6 * cs, src_bytes = (int64_t)w * h * 3;
+    auto ok4 = [](const void* p) { return (uintptr_t)p % 4 == 0; };
+    auto ok16 = [](const void* p) { return (uintptr_t)p % 16 == 0; };
+    const bool tiled_wins = c->remap_kernel == 2 || (c->remap_kernel == 0 && plan->tiled.tiles && plan->tiled.preferred[0]);
+    if (!tiled_wins && ok4(d_im0) && ok4(d_im1) && src_bytes % 4 == 0 && ok16(d_s0) && ok16(d_s1) && ok16(plan->lut) && P % 128 == 0 &&
+        P / 128 < ((int64_t)1 << 29)) {
+        const int groups = (int)(P / 128);
+        int blocks = (int)std::min<int64_t>(ceil_div64((int64_t)groups * 2, 8), (int64_t)c->sm_count * 8);
+        if (blocks >= c->sm_count) blocks = blocks / c->sm_count * c->sm_count;
+        prof_begin(c, SBA_KERNEL_REMAP);
+        remap_gather_warp_kernel<false><<<blocks, 256, 0, c->stream>>>(d_im0, plan->lut, d_s0, src_bytes, P, groups, 2, d_im1, d_s1, 1);
+        prof_end(c, SBA_KERNEL_REMAP);
+        SBA_LAUNCHED(c);
+        SBA_CUDA(cudaGetLastError());
+        return SBA_OK;
+    }
+    SBA_TRY(sba_equi2cube(c, d_im0, w, h, 1, cs, d_s0, SBA_MEM_DEVICE));
+    return sba_equi2cube(c, d_im1, w, h, 1, cs, d_s1, SBA_MEM_DEVICE);
 }
 
 static int launch_gather(sba_ctx* c, const uint8_t* d_erp, const RemapPlan* plan, uint8_t* d_out, int n_images, int face)
