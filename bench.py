@@ -365,7 +365,7 @@ def bench_ours(args):
     flops = 2.0 * DIM * NKP * NKP
     mk = float(np.mean(match_ms)) * 1e-3
     stats = ctx.match_stats()
-    algo = {1: "simt_fp32_exact", 2: "tcgen05_filter+exact_rerank"}.get(stats.algo_used, "?")
+    algo = {1: "simt_fp32_exact", 2: "tcgen05_bf16x3_filter+exact_rerank", 3: "tcgen05_fp16_filter+exact_rerank"}.get(stats.algo_used, "?")
     achieved = flops / mk / 1e12
     peak = peaks["bf16_tflops"]
     traffic, traffic_src = _ncu_traffic()

@@ -129,7 +129,8 @@ int sba_pixels_to_bearings(sba_ctx* ctx, const float* xy, int n, int w, int h, f
 typedef enum sba_match_algo {
     SBA_MATCH_AUTO = 0,
     SBA_MATCH_SIMT_EXACT = 1, /* fp32 CUDA-core brute force in OpenCV's arithmetic order */
-    SBA_MATCH_TENSOR = 2      /* tcgen05 bf16x3 candidate filter + exact fp32 re-rank */
+    SBA_MATCH_TENSOR = 2,     /* tcgen05 bf16x3 candidate filter + exact fp32 re-rank; what AUTO picks for large sets */
+    SBA_MATCH_TENSOR_FP16 = 3 /* tcgen05 single-product fp16 candidate filter (a third of the tensor work, wider safety margin, more rows through the exact fallback) + exact fp32 re-rank */
 } sba_match_algo;
 
 int sba_knn2_ratio(sba_ctx* ctx, const float* q, int nq, const float* t, int nt, int dim, float ratio,

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SBA_B200_LIB") or os.path.join(_HERE, "libsba_b200.so")   # override: debug builds under build/
 
 SBA_MEM_HOST, SBA_MEM_DEVICE = 0, 1
-MATCH_AUTO, MATCH_SIMT_EXACT, MATCH_TENSOR = 0, 1, 2
+MATCH_AUTO, MATCH_SIMT_EXACT, MATCH_TENSOR, MATCH_TENSOR_FP16 = 0, 1, 2, 3
 
 # every symbol include/sba_b200.h declares (tests check the .so exports all of them)
 EXPORTED = [

@@ -14,7 +14,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from ._lib import MATCH_AUTO, MATCH_SIMT_EXACT, MATCH_TENSOR, SBA_MEM_DEVICE, SBA_MEM_HOST, SbaError, check
+from ._lib import MATCH_AUTO, MATCH_SIMT_EXACT, MATCH_TENSOR, MATCH_TENSOR_FP16, SBA_MEM_DEVICE, SBA_MEM_HOST, SbaError, check
 
 try:  # torch is only plumbing: device memory, streams, torch.distributed
     import torch

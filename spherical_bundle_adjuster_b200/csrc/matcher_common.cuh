@@ -10,9 +10,14 @@ namespace sba {
 constexpr int KNN_MISSING = INT_MAX;  // internal "no neighbour" index (sorts after every real index)
 constexpr int KNN_FALLBACK = INT_MAX - 1;   // marker in a Top2's i0: the row was queued for the exact fallback, i1 = its queue position
 constexpr int FB_MAX_SPLIT = 64;
+constexpr int FB_ROWS = 32;     // queued rows evaluated together against one staged range of the train set
 
-// a queued row's exact scan is cut into this many ranges (chosen on the device from the queue length)
-__host__ __device__ inline int fb_splits(int n_rows, int grid) { return n_rows <= 0 ? 1 : max(1, min(FB_MAX_SPLIT, (2 * grid) / n_rows)); }
+// The exact scan of the queued rows is cut into this many train ranges (chosen on the device from the queue length):
+// work items = ranges x groups of FB_ROWS rows, enough of them to fill `grid` CTAs whatever the queue length.
+__host__ __device__ inline int fb_splits(int n_rows, int grid)
+{
+    return n_rows <= 0 ? 1 : max(1, min(FB_MAX_SPLIT, (grid * FB_ROWS + n_rows - 1) / n_rows));
+}
 
 struct Top2 {
     float d0, d1;
@@ -88,7 +93,8 @@ __device__ inline float l2sqr_opencv(const float* __restrict__ a, const float* _
 // sba_descriptors_create.  n_pad is a multiple of 256 (serves as query block and as train tiles), pad norms are +inf.
 struct PreparedSet {
     const float* raw;               // fp32 rows on the device [n x dim]
-    const __nv_bfloat16* prep;      // [n_pad x 128] or NULL when dim != 64
+    const __nv_bfloat16* prep;      // [n_pad x 128] bf16 hi|lo or NULL when dim != 64
+    const void* prep16;             // [n_pad x 64] fp16 rows (or NULL)
     const float* norm;              // [n_pad]
     const float* max_norm;          // device scalar
     int n, n_pad, dim;

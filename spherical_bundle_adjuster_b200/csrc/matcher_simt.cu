@@ -291,8 +291,8 @@ static int run_simt(sba_ctx* c, const float* d_q, int nq, const float* d_t, int 
 }
 
 // defined in matcher_tc.cu
-int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, int dim, Top2* d_top, const PreparedSet* pq, const PreparedSet* pt);
-int knn2_prepare_set(sba_ctx* c, const float* d_raw, int n, int n_pad, __nv_bfloat16* prep, float* norm, float* max_norm);
+int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, int dim, Top2* d_top, const PreparedSet* pq, const PreparedSet* pt, int products);
+int knn2_prepare_set(sba_ctx* c, const float* d_raw, int n, int n_pad, __nv_bfloat16* prep, float* norm, float* max_norm, void* prep16);
 bool knn2_tensor_applicable(int nq, int nt, int dim);
 bool knn2_tensor_preferred(int nq, int nt, int dim);
 
@@ -311,6 +311,7 @@ struct sba_descriptors {
     int device = 0;
     float* raw = nullptr;
     __nv_bfloat16* prep = nullptr;
+    void* prep16 = nullptr;
     float* norm = nullptr;          // [n_pad] + the maximum in the last slot
     sba::PreparedSet set{};
 };
@@ -359,16 +360,19 @@ static int knn2_ratio_impl(sba_ctx* c, const float* q, int nq, const float* t, i
     }
 
     int use = algo;
+    // AUTO takes the bf16-split filter: measured on B200 the single-product fp16 filter saves nothing in the distance kernel (it is
+    // bound by its epilogue, not by the tensor pipe) and its wider margin sends ~0.3 % of the rows to the exact fallback
     if (use == SBA_MATCH_AUTO) use = knn2_tensor_preferred(nq, nt, dim) ? SBA_MATCH_TENSOR : SBA_MATCH_SIMT_EXACT;
     if (nt == 0) {
         fill_empty_top2_kernel<<<(nq + 255) / 256, 256, 0, st>>>(d_top, nq);
         SBA_LAUNCHED(c);
-    } else if (use == SBA_MATCH_TENSOR) {
+    } else if (use == SBA_MATCH_TENSOR || use == SBA_MATCH_TENSOR_FP16) {
         if (!knn2_tensor_applicable(nq, nt, dim)) {
             set_error("tensor-core matcher does not apply to nq=%d nt=%d dim=%d", nq, nt, dim);
             return SBA_ERR_UNSUPPORTED;
         }
-        SBA_TRY(knn2_tensor(c, d_q, nq, d_t, nt, dim, d_top, (pq && pq->prep) ? pq : nullptr, (pt && pt->prep) ? pt : nullptr));
+        SBA_TRY(knn2_tensor(c, d_q, nq, d_t, nt, dim, d_top, (pq && pq->prep) ? pq : nullptr, (pt && pt->prep) ? pt : nullptr,
+                            use == SBA_MATCH_TENSOR ? 3 : 1));
     } else {
         use = SBA_MATCH_SIMT_EXACT;
         if (dim == 64) SBA_TRY(run_simt<64>(c, d_q, nq, d_t, nt, d_top));
@@ -419,10 +423,11 @@ int sba_descriptors_create(sba_ctx* c, const float* desc, int n, int dim, int me
     if (dim == 64 && n > 0) {
         if ((e = cudaMalloc(&d->prep, (size_t)d->set.n_pad * 128 * sizeof(__nv_bfloat16))) != cudaSuccess) return fail(e);
         if ((e = cudaMalloc(&d->norm, (size_t)d->set.n_pad * sizeof(float) + sizeof(float))) != cudaSuccess) return fail(e);
+        if ((e = cudaMalloc(&d->prep16, (size_t)d->set.n_pad * 64 * 2)) != cudaSuccess) return fail(e);
         float* max_norm = d->norm + d->set.n_pad;
-        int rc = knn2_prepare_set(c, d->raw, n, d->set.n_pad, d->prep, d->norm, max_norm);
+        int rc = knn2_prepare_set(c, d->raw, n, d->set.n_pad, d->prep, d->norm, max_norm, d->prep16);
         if (rc != SBA_OK) { sba_descriptors_destroy(d); return rc; }
-        d->set.prep = d->prep; d->set.norm = d->norm; d->set.max_norm = max_norm;
+        d->set.prep = d->prep; d->set.norm = d->norm; d->set.max_norm = max_norm; d->set.prep16 = d->prep16;
     }
     if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return fail(e);   // usable from any context / stream of this device from here on
     *out = d;
@@ -436,6 +441,7 @@ int sba_descriptors_destroy(sba_descriptors* d)
     cudaDeviceSynchronize();          // a match that reads the set may still be queued on some stream
     if (d->raw) cudaFree(d->raw);
     if (d->prep) cudaFree(d->prep);
+    if (d->prep16) cudaFree(d->prep16);
     if (d->norm) cudaFree(d->norm);
     delete d;
     return SBA_OK;

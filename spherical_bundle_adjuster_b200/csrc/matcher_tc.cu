@@ -33,6 +33,7 @@
 // Roofline: tensor pipe.  Algorithmic flops 2*D*N*M; the three bf16 products cost 3x that on the pipe.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "matcher_common.cuh"
 
@@ -51,15 +52,25 @@ constexpr int EPI_WARPS = 16;      // 4 TMEM lane quarters x 4 column slices
 constexpr int SUBSLOTS = 2;        // candidate lists per query row per CTA span (2 column slices per row-half)
 constexpr int EPI_WARP0 = 3;      // first epilogue warp
 constexpr int THREADS = (EPI_WARP0 + EPI_WARPS) * 32;   // warp0 TMA, warps 1-2 MMA issuers (even / odd tiles), warps 3-18 epilogue: 608 threads -> 104 registers each
-constexpr int A_KBLOCK_BYTES = BM * 128;   // one 64-wide bf16 k-block of A: 32 KB
+constexpr int A_KBLOCK_BYTES = BM * 128;   // one 64-wide 16-bit k-block of A: 32 KB
 constexpr int B_KBLOCK_BYTES = BN * 128;   // 16 KB
-constexpr int SMEM_A = 2 * A_KBLOCK_BYTES;                 // hi, lo
-constexpr int SMEM_B = STAGES * 2 * B_KBLOCK_BYTES;        // stages x {hi, lo}
-constexpr int SMEM_NB = EPI_WARPS * 64 * 4;                 // |b|^2 staging, 64 columns per epilogue warp
-constexpr int SMEM_BYTES = SMEM_A + SMEM_B + SMEM_NB + 256 /*barriers: 20 x 8 B + the TMEM slot*/ + 1024 /*alignment slack*/;
+// Two filter schemes, template parameter P = tensor products per result:
+//   P = 3  bf16 split  x = hi + lo: hi.hi + hi.lo + lo.hi, error ~2^-16 |a||b|  (rows of 128 bf16: [hi | lo])
+//   P = 1  plain fp16 rows: ONE product, error ~2^-10 |a||b|; a third of the tensor work, paid for with a wider safety
+//          margin in the re-rank (more rows go to the exact fallback)
+template <int P> struct Scheme {
+    static constexpr int KBLOCKS = P == 3 ? 2 : 1;                        // 64-wide k-blocks per prepared row
+    static constexpr int ROW_ELEMS = KBLOCKS * DIM;                        // 16-bit elements per prepared row
+    static constexpr int SMEM_A = KBLOCKS * A_KBLOCK_BYTES;
+    static constexpr int B_STAGE_BYTES = KBLOCKS * B_KBLOCK_BYTES;
+    static constexpr int SMEM_B = STAGES * B_STAGE_BYTES;
+    static constexpr int SMEM_NB = EPI_WARPS * 64 * 4;                     // |b|^2 of each epilogue warp's columns
+    static constexpr int SMEM_BYTES = SMEM_A + SMEM_B + SMEM_NB + 256 /*barriers: 20 x 8 B + the TMEM slot*/ + 1024 /*alignment slack*/;
+};
 constexpr int ACC_COLS = 2 * BN;   // TMEM columns per accumulator stage: row-half 0 | row-half 1
 constexpr uint32_t TMEM_COLS = 512;
-constexpr float DELTA_COEF = 4e-5f;  // |approx - exact| <= DELTA_COEF * (|a|^2 + max|b|^2): derivation at tc_rerank_kernel
+constexpr float DELTA_COEF = 4e-5f;  // bf16 x 3: |approx - exact| <= DELTA_COEF * (|a|^2 + max|b|^2): derivation at tc_rerank_kernel
+constexpr float DELTA_COEF_FP16 = 1.0e-3f;   // fp16 x 1: same place
 // Candidate keys (epilogue): a chunk minimum with the chunk's id in the low mantissa bits, so that ONE fp32 min / max
 // moves value and id together.  9 bits: [8] = "old" flag, [7:3] tile inside the current 32-tile window, [2:0] chunk of
 // the thread's 64 columns -- or, for entries that survived a window change, flag | list slot (the absolute chunk id of
@@ -148,6 +159,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr)
 
 // kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, N=128, M=128.
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// the same with fp16 operands (A / B format fields 0)
+constexpr uint32_t IDESC_F16 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 #define TMEM_LD_X32(r, taddr)                                                                                                  \
     asm volatile(                                                                                                              \
@@ -193,7 +206,7 @@ struct Partition {
 // ---- 1. prepare ------------------------------------------------------------------------------------------
 // 16 threads per row, 4 floats each.  Rows >= n are padding: zeros, norm = +inf (train) so they never win.
 __device__ __forceinline__ void prep_row(const float* __restrict__ x, int n, int row, int part, __nv_bfloat16* __restrict__ out, float* __restrict__ norm,
-                                         float pad_norm, float* __restrict__ max_norm)
+                                         float pad_norm, float* __restrict__ max_norm, __half* __restrict__ out16)
 {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (row < n) v = __ldg(reinterpret_cast<const float4*>(x + (size_t)row * DIM) + part);
@@ -209,9 +222,17 @@ __device__ __forceinline__ void prep_row(const float* __restrict__ x, int n, int
     }
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, 16);
-    __nv_bfloat16* dst = out + (size_t)row * KP;
-    *reinterpret_cast<uint2*>(dst + part * 4) = *reinterpret_cast<const uint2*>(hi);
-    *reinterpret_cast<uint2*>(dst + DIM + part * 4) = *reinterpret_cast<const uint2*>(lo);
+    if (out) {
+        __nv_bfloat16* dst = out + (size_t)row * KP;
+        *reinterpret_cast<uint2*>(dst + part * 4) = *reinterpret_cast<const uint2*>(hi);
+        *reinterpret_cast<uint2*>(dst + DIM + part * 4) = *reinterpret_cast<const uint2*>(lo);
+    }
+    if (out16) {   // plain fp16 rows (the fp16 filter): see the range note at tc_rerank_kernel
+        __align__(8) __half h[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) h[k] = __float2half_rn(f[k]);
+        *reinterpret_cast<uint2*>(out16 + (size_t)row * DIM + part * 4) = *reinterpret_cast<const uint2*>(h);
+    }
     if (part == 0) {
         norm[row] = row < n ? s : pad_norm;
         if (max_norm && row < n) atomicMax((int*)max_norm, __float_as_int(s));   // non-negative floats order like ints
@@ -219,14 +240,16 @@ __device__ __forceinline__ void prep_row(const float* __restrict__ x, int n, int
 }
 
 // Both descriptor sets in one launch: rows [0, nq_pad) are queries, the rest train rows.
+// out*: bf16 hi|lo rows (P = 3) or NULL; out16*: fp16 rows (P = 1) or NULL.  na_max / nb_max: largest squared norms.
 __global__ void tc_prep_kernel(const float* __restrict__ q, int nq, int nq_pad, __nv_bfloat16* __restrict__ outA, float* __restrict__ na,
                                const float* __restrict__ t, int nt, int nt_pad, __nv_bfloat16* __restrict__ outB, float* __restrict__ nb,
-                               float* __restrict__ nb_max /* running maximum of the finite train norms */)
+                               float* __restrict__ nb_max /* running maximum of the finite train norms */, float* __restrict__ na_max,
+                               __half* __restrict__ out16A, __half* __restrict__ out16B)
 {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     const int row = gid >> 4, part = gid & 15;      // 16 threads per row, 4 floats each; a half-warp never straddles the two sets
-    if (row < nq_pad) prep_row(q, nq, row, part, outA, na, 0.f, nullptr);
-    else if (row < nq_pad + nt_pad) prep_row(t, nt, row - nq_pad, part, outB, nb, PAD_NORM, nb_max);
+    if (row < nq_pad) prep_row(q, nq, row, part, outA, na, 0.f, na_max, out16A);
+    else if (row < nq_pad + nt_pad) prep_row(t, nt, row - nq_pad, part, outB, nb, PAD_NORM, nb_max, out16B);
 }
 
 // ---- 2. the tensor-core kernel ---------------------------------------------------------------------------
@@ -336,16 +359,19 @@ __device__ __forceinline__ unsigned long long gtime()
 #define TC_TRACE(slot) do { } while (0)
 #endif
 
+template <int P>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const float* __restrict__ nb,
               Partition part, float4* __restrict__ cand_v, int4* __restrict__ cand_id, int slots)
 {
+    using S = Scheme<P>;
+    constexpr int SMEM_A = S::SMEM_A, SMEM_B = S::SMEM_B, SMEM_NB = S::SMEM_NB, B_STAGE_BYTES = S::B_STAGE_BYTES;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment for the 128B-swizzle atoms; offset arithmetic keeps the shared address space
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* sA = smem;                       // [2 kblocks][256 rows][128 B]
-    uint8_t* sB = smem + SMEM_A;              // [STAGES][2 kblocks][128 rows][128 B]
-    float* sNB = (float*)(smem + SMEM_A + SMEM_B);  // [EPI_WARPS][64]: |b|^2 of each epilogue warp's columns
+    uint8_t* sA = smem;                       // [kblocks][256 rows][128 B]
+    uint8_t* sB = smem + SMEM_A;              // [STAGES][kblocks][128 rows][128 B]
+    float* sNB = (float*)(smem + SMEM_A + SMEM_B);  // [EPI_WARPS][64 (x2)]: |b|^2 (and row scales) of each epilogue warp's columns
     uint64_t* bars = (uint64_t*)(smem + SMEM_A + SMEM_B + SMEM_NB);
     uint64_t* a_full = bars + 0;
     uint64_t* a_empty = bars + 1;
@@ -395,7 +421,7 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                     mbar_wait(a_empty, (seg & 1) ^ 1);
                     mbar_expect_tx(a_full, SMEM_A);
                     tma_load_2d(sA, &map_a, a_full, 0, qb * BM);
-                    tma_load_2d(sA + A_KBLOCK_BYTES, &map_a, a_full, DIM, qb * BM);
+                    if (P == 3) tma_load_2d(sA + A_KBLOCK_BYTES, &map_a, a_full, DIM, qb * BM);
                     seg++;
                 }
                 mbar_wait(b_empty + s, ring_phase ^ 1);
@@ -403,10 +429,10 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 if (n >= STAGES) { mbar_arrive(b_full + s); } else
 #endif
                 {
-                mbar_expect_tx(b_full + s, 2 * B_KBLOCK_BYTES);
-                uint8_t* dst = sB + s * (2 * B_KBLOCK_BYTES);
+                mbar_expect_tx(b_full + s, B_STAGE_BYTES);
+                uint8_t* dst = sB + s * B_STAGE_BYTES;
                 tma_load_2d(dst, &map_b, b_full + s, 0, tb * BN);
-                tma_load_2d(dst + B_KBLOCK_BYTES, &map_b, b_full + s, DIM, tb * BN);
+                if (P == 3) tma_load_2d(dst + B_KBLOCK_BYTES, &map_b, b_full + s, DIM, tb * BN);
                 }
                 if (++s == STAGES) { s = 0; ring_phase ^= 1; }
                 new_seg = (++tb == ntb);
@@ -449,18 +475,20 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 if (n == 0 && is_leader) TC_TRACE(2);              // first operands landed
                 if (n == n_tiles - 1 && is_leader) TC_TRACE(3);    // last tile's MMAs about to issue
                 // descriptors address 16-byte units: stage stride and k-block stride are plain adds
-                const uint64_t dB_hi = dB0 + (uint64_t)(s * ((2 * B_KBLOCK_BYTES) >> 4));
+                const uint64_t dB_hi = dB0 + (uint64_t)(s * (B_STAGE_BYTES >> 4));
                 const uint64_t dB_lo = dB_hi + (B_KBLOCK_BYTES >> 4);
                 const uint32_t d0 = tmem_base + (uint32_t)(acc * ACC_COLS), d1 = d0 + BN;
                 if (is_leader) {
                     // hi.hi + hi.lo + lo.hi ; each 64-wide k-block is four K=16 steps, 32 B apart
 #pragma unroll
-                    for (int k = 0; k < 4; k++) umma_bf16(d0, dA_hi0 + 2 * k, dB_hi + 2 * k, IDESC, k > 0);
+                    for (int k = 0; k < 4; k++) umma_bf16(d0, dA_hi0 + 2 * k, dB_hi + 2 * k, P == 3 ? IDESC : IDESC_F16, k > 0);
 #ifndef SBA_TC_EXP_1PROD   // experiment (trace builds): one product only -- WRONG results, timing probe
+                    if (P == 3) {
 #pragma unroll
-                    for (int k = 0; k < 4; k++) umma_bf16(d0, dA_hi0 + 2 * k, dB_lo + 2 * k, IDESC, 1);
+                        for (int k = 0; k < 4; k++) umma_bf16(d0, dA_hi0 + 2 * k, dB_lo + 2 * k, IDESC, 1);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) umma_bf16(d0, dA_lo0 + 2 * k, dB_hi + 2 * k, IDESC, 1);
+                        for (int k = 0; k < 4; k++) umma_bf16(d0, dA_lo0 + 2 * k, dB_hi + 2 * k, IDESC, 1);
+                    }
 #endif
                     tcgen05_commit(acc_full + 2 * acc);      // row-half 0 ready for its epilogue warps
                 }
@@ -468,12 +496,14 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 tcgen05_fence_after();
                 if (is_leader) {
 #pragma unroll
-                    for (int k = 0; k < 4; k++) umma_bf16(d1, dA_hi1 + 2 * k, dB_hi + 2 * k, IDESC, k > 0);
+                    for (int k = 0; k < 4; k++) umma_bf16(d1, dA_hi1 + 2 * k, dB_hi + 2 * k, P == 3 ? IDESC : IDESC_F16, k > 0);
 #ifndef SBA_TC_EXP_1PROD
+                    if (P == 3) {
 #pragma unroll
-                    for (int k = 0; k < 4; k++) umma_bf16(d1, dA_hi1 + 2 * k, dB_lo + 2 * k, IDESC, 1);
+                        for (int k = 0; k < 4; k++) umma_bf16(d1, dA_hi1 + 2 * k, dB_lo + 2 * k, IDESC, 1);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) umma_bf16(d1, dA_lo1 + 2 * k, dB_hi + 2 * k, IDESC, 1);
+                        for (int k = 0; k < 4; k++) umma_bf16(d1, dA_lo1 + 2 * k, dB_hi + 2 * k, IDESC, 1);
+                    }
 #endif
                     mbar_arrive(turn + (my_parity ^ 1));     // the other issuer may queue the next tile
                     tcgen05_commit(b_empty + s);             // B stage free once these MMAs have read it
@@ -668,7 +698,8 @@ static_assert(CHUNK == 8 && NCAND == 4, "the re-rank evaluates two chunks of 8 r
 __global__ void __launch_bounds__(RR_THREADS, 4)
 tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, int nt, const float* __restrict__ na,
                  const float* __restrict__ nb_max, Partition part, const float4* __restrict__ cand_v, const int4* __restrict__ cand_id,
-                 int slots, Top2* __restrict__ top, int* __restrict__ fb_list, int* __restrict__ fb_count, float* __restrict__ dbg_max_err)
+                 int slots, Top2* __restrict__ top, int* __restrict__ fb_list, int* __restrict__ fb_count, float* __restrict__ dbg_max_err,
+                 float delta_coef, const float* __restrict__ na_max)
 {
     __shared__ __align__(16) float qs[RR_ROWS][DIM];
     __shared__ __align__(16) float ts[RR_ROWS][16][DIM + 4];   // the candidate rows of every query of the CTA (one phase)
@@ -727,6 +758,10 @@ tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ 
 
     const float na_r = na[r];
     const float scale = na_r + *nb_max;
+    // fp16 filter only (na_max != NULL): plain fp16 rows are as good as the analysis assumes while the data sits inside fp16's
+    // range -- elements below 65504, and norms not so small that whole sets turn subnormal.  Outside that window no row is
+    // trusted: everything goes through the exact fallback (slow, never wrong).
+    const bool range_ok = na_max == nullptr || (*na_max < 1e9f && *nb_max < 1e9f && fmaxf(*na_max, *nb_max) > 1e-7f);
     Top2 best = top2_empty();
     bool final_row = false;
 #pragma unroll
@@ -800,9 +835,9 @@ tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ 
             // final iff no row outside the evaluated chunks can reach the second best:  d1^2 (rounded up) < B + |a|^2 - delta,
             // B = the best key that was NOT evaluated yet (phase 0: rank 2) or the last evaluated one (phase 1: rank 3)
             const float B = win_v[grp][phase == 0 ? 2 : NCAND - 1];
-            const float delta = DELTA_COEF * scale + KEY_TRUNC_REL * fabsf(B);
+            const float delta = delta_coef * scale + KEY_TRUNC_REL * fabsf(B);
             const float d1sq_up = best.d1 * best.d1 * (1.f + 5e-7f);
-            final_row = !(B < INF) || (best.i1 != KNN_MISSING && d1sq_up < B + na_r - delta);
+            final_row = range_ok && (!(B < INF) || (best.i1 != KNN_MISSING && d1sq_up < B + na_r - delta));
         }
         __syncwarp();
     }
@@ -819,52 +854,79 @@ tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ 
 }
 
 // ---- 4. exact fallback for queued rows --------------------------------------------------------------------------
-// A queued row needs an exact scan of the whole train set.  The scan of each row is cut into S ranges
-// handled by different CTAs (S chosen on the device from the queue length so that a handful of rows at
-// 64k train rows still use the whole chip, while thousands of rows fall back to one CTA per row); the
-// row's S partial top-2 lists are merged in range order by knn2_finalize_kernel (matcher_simt.cu).
-constexpr int FB_THREADS = 128;
+// A queued row needs an exact scan of the whole train set.  Rows are taken FB_ROWS at a time and the train set is cut
+// into S ranges (S chosen on the device from the queue length: fb_splits); a work item = (row group, range).  The CTA
+// stages its range in shared memory 64 train rows at a time and every staged chunk is used by all rows of the group,
+// so the train set is read from L2 once per row GROUP, not once per row: a few dozen queued rows -- what the fp16
+// filter's wider margin produces at 16k x 16k -- cost microseconds, and a few thousand (adversarial norms) still spread
+// over the whole chip.  knn2_finalize_kernel merges a row's S partial top-2 lists in range order.
+constexpr int FB_THREADS = 256;
+constexpr int FB_CHUNK = 64;                 // train rows staged at a time
+constexpr int FB_PITCH = DIM + 1;            // padded row pitch: lane l reads row l, conflict free
+
 __global__ void __launch_bounds__(FB_THREADS)
 tc_fallback_kernel(const float* __restrict__ q, const float* __restrict__ t, int nt, const int* __restrict__ fb_list,
                    const int* __restrict__ fb_count, Top2* __restrict__ parts)
 {
-    __shared__ Top2 sh[FB_THREADS];
-    __shared__ __align__(16) float qs[DIM];
+    __shared__ float qs[FB_ROWS][DIM];
+    __shared__ float ts[FB_CHUNK][FB_PITCH];
     const int n = *fb_count;
     if (n == 0) return;
     const int S = fb_splits(n, gridDim.x);
-    const int span = (nt + S - 1) / S;
-    for (int item = blockIdx.x; item < n * S; item += gridDim.x) {
-        const int row = fb_list[item / S], sp = item % S;
+    const int span = ((nt + S - 1) / S + FB_CHUNK - 1) / FB_CHUNK * FB_CHUNK;   // whole chunks per range
+    const int n_groups = (n + FB_ROWS - 1) / FB_ROWS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int ROWS_PER_WARP = FB_ROWS / (FB_THREADS / 32);
+    for (int item = blockIdx.x; item < n_groups * S; item += gridDim.x) {
+        const int grp = item / S, sp = item - grp * S;
+        const int k0 = grp * FB_ROWS, nk = min(FB_ROWS, n - k0);
         const int j0 = sp * span, j1 = min(nt, j0 + span);
         __syncthreads();
-        if (threadIdx.x < DIM) qs[threadIdx.x] = q[(size_t)row * DIM + threadIdx.x];
-        __syncthreads();
-        float qv[DIM];
-#pragma unroll
-        for (int k = 0; k < DIM / 4; k++) {
-            const float4 b = reinterpret_cast<const float4*>(qs)[k];
-            qv[4 * k] = b.x; qv[4 * k + 1] = b.y; qv[4 * k + 2] = b.z; qv[4 * k + 3] = b.w;
+        for (int i = threadIdx.x; i < FB_ROWS * DIM; i += FB_THREADS) {
+            const int r = i / DIM;
+            qs[r][i - r * DIM] = r < nk ? q[(size_t)fb_list[k0 + r] * DIM + (i - r * DIM)] : 0.f;
         }
-        Top2 best = top2_empty();
-        for (int j = j0 + threadIdx.x; j < j1; j += FB_THREADS) {
-            float tv[DIM];
-            const float4* tp = reinterpret_cast<const float4*>(t + (size_t)j * DIM);
+        Top2 best[ROWS_PER_WARP];
 #pragma unroll
-            for (int k = 0; k < DIM / 4; k++) {
-                const float4 a = __ldg(tp + k);
-                tv[4 * k] = a.x; tv[4 * k + 1] = a.y; tv[4 * k + 2] = a.z; tv[4 * k + 3] = a.w;
-            }
-            const float d = __fsqrt_rn(l2sqr_opencv<DIM>(qv, tv));
-            top2_push_ordered(best, d, j);
-        }
-        sh[threadIdx.x] = best;
-        __syncthreads();
-        for (int s = FB_THREADS / 2; s > 0; s >>= 1) {
-            if ((int)threadIdx.x < s) sh[threadIdx.x] = top2_merge(sh[threadIdx.x], sh[threadIdx.x + s]);
+        for (int r = 0; r < ROWS_PER_WARP; r++) best[r] = top2_empty();
+        for (int c0 = j0; c0 < j1; c0 += FB_CHUNK) {
             __syncthreads();
+            for (int i = threadIdx.x; i < FB_CHUNK * DIM / 4; i += FB_THREADS) {      // coalesced 16-byte loads, scalar stores (padded pitch)
+                const int r = i / (DIM / 4), c4 = i - r * (DIM / 4);
+                const float4 v = (c0 + r < nt) ? __ldg(reinterpret_cast<const float4*>(t + (size_t)(c0 + r) * DIM) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                ts[r][4 * c4] = v.x; ts[r][4 * c4 + 1] = v.y; ts[r][4 * c4 + 2] = v.z; ts[r][4 * c4 + 3] = v.w;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < ROWS_PER_WARP; r++) {
+                const int qr = warp * ROWS_PER_WARP + r;
+                if (qr >= nk) break;                       // warp-uniform
+#pragma unroll
+                for (int hh = 0; hh < FB_CHUNK / 32; hh++) {
+                    const int jr = hh * 32 + lane, j = c0 + jr;
+                    if (j < j1) {
+                        const float d = __fsqrt_rn(l2sqr_opencv<DIM>(&qs[qr][0], &ts[jr][0]));
+                        top2_push_ordered(best[r], d, j);   // a lane sees its train rows in increasing order
+                    }
+                }
+            }
         }
-        if (threadIdx.x == 0) parts[item] = sh[0];
+#pragma unroll
+        for (int r = 0; r < ROWS_PER_WARP; r++) {
+            const int qr = warp * ROWS_PER_WARP + r;
+            if (qr >= nk) break;
+            Top2 b = best[r];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                Top2 other;
+                other.d0 = __shfl_xor_sync(0xffffffffu, b.d0, o);
+                other.d1 = __shfl_xor_sync(0xffffffffu, b.d1, o);
+                other.i0 = __shfl_xor_sync(0xffffffffu, b.i0, o);
+                other.i1 = __shfl_xor_sync(0xffffffffu, b.i1, o);
+                b = top2_merge(b, other);
+            }
+            if (lane == 0) parts[(size_t)(k0 + qr) * S + sp] = b;
+        }
     }
 }
 
@@ -885,16 +947,16 @@ static EncodeTiledFn get_encode_fn()
     return fn;
 }
 
-// rows x KP bf16, row-major; box = 64 columns (128 B) x box_rows, 128B swizzle
-static int make_map(CUtensorMap* map, void* base, int rows, int box_rows)
+// rows x row_elems 16-bit elements, row-major; box = 64 columns (128 B) x box_rows, 128B swizzle
+static int make_map(CUtensorMap* map, void* base, int rows, int box_rows, int row_elems)
 {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled entry point not available");
         return SBA_ERR_CUDA;
     }
-    cuuint64_t dims[2] = {(cuuint64_t)KP, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)KP * sizeof(__nv_bfloat16)};
+    cuuint64_t dims[2] = {(cuuint64_t)row_elems, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)row_elems * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -913,26 +975,30 @@ bool knn2_tensor_applicable(int nq, int nt, int dim) { return dim == tc::DIM && 
 // Heuristic used by SBA_MATCH_AUTO: below ~1M pair distances the exact SIMT kernel's latency wins.
 bool knn2_tensor_preferred(int nq, int nt, int dim) { return dim == tc::DIM && (long long)nq * nt >= (1ll << 20) && nt >= 1024; }
 
-// The bf16 split of one descriptor set into caller-owned buffers (sba_descriptors_create): prep [n_pad x 128],
-// norm [n_pad] with +inf on the padding rows, *max_norm = largest finite norm.
-int knn2_prepare_set(sba_ctx* c, const float* d_raw, int n, int n_pad, __nv_bfloat16* prep, float* norm, float* max_norm)
+// Both prepared forms of one descriptor set into caller-owned buffers (sba_descriptors_create): prep [n_pad x 128] bf16 hi|lo,
+// prep16 [n_pad x 64] fp16, norm [n_pad] (PAD_NORM on the padding rows), *max_norm = largest real norm.
+int knn2_prepare_set(sba_ctx* c, const float* d_raw, int n, int n_pad, __nv_bfloat16* prep, float* norm, float* max_norm, void* prep16)
 {
     using namespace tc;
     SBA_CUDA(cudaMemsetAsync(max_norm, 0, sizeof(float), c->stream));
-    tc_prep_kernel<<<(n_pad * 16 + 255) / 256, 256, 0, c->stream>>>(nullptr, 0, 0, nullptr, nullptr, d_raw, n, n_pad, prep, norm, max_norm);
+    tc_prep_kernel<<<(n_pad * 16 + 255) / 256, 256, 0, c->stream>>>(nullptr, 0, 0, nullptr, nullptr, d_raw, n, n_pad, prep, norm, max_norm, nullptr, nullptr,
+                                                                    (__half*)prep16);
     SBA_LAUNCHED(c);
     SBA_CUDA(cudaGetLastError());
     return SBA_OK;
 }
 
-// pq / pt: optional prepared forms of the query / train set (then the bf16 split of that side is not redone)
-int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, int dim, Top2* d_top, const PreparedSet* pq, const PreparedSet* pt)
+// pq / pt: optional prepared forms of the query / train set (then that side is not converted again).
+// products: 3 = bf16 split filter, 1 = fp16 filter (see tc::Scheme).
+int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, int dim, Top2* d_top, const PreparedSet* pq, const PreparedSet* pt,
+                int products)
 {
     using namespace tc;
     if (dim != DIM) {
         set_error("tensor-core matcher handles dim %d only", DIM);
         return SBA_ERR_UNSUPPORTED;
     }
+    const bool f16 = products == 1;
     cudaStream_t st = c->stream;
     const int nqb = (nq + BM - 1) / BM, ntb = (nt + BN - 1) / BN;
     const int nq_pad = pq ? pq->n_pad : nqb * BM, nt_pad = pt ? pt->n_pad : ntb * BN;
@@ -943,25 +1009,27 @@ int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, 
     // capped so that no span can come out empty
     part.bcost = (int)std::min<long long>(5, part.T / part.n_ctas / 4);
     const int slots = part.max_slots() * SUBSLOTS;
+    const int row_bytes = f16 ? DIM * 2 : KP * 2;
 
     // workspace carve-up (one buffer)
     auto align_up = [](size_t v) { return (v + 1023) & ~(size_t)1023; };
     size_t off = 0;
-    const size_t o_a = off; off = align_up(off + (size_t)nq_pad * KP * 2);
-    const size_t o_b = off; off = align_up(off + (size_t)nt_pad * KP * 2);
+    const size_t o_a = off; off = align_up(off + (size_t)nq_pad * row_bytes);
+    const size_t o_b = off; off = align_up(off + (size_t)nt_pad * row_bytes);
     const size_t o_na = off; off = align_up(off + (size_t)nq_pad * 4);
     const size_t o_nb = off; off = align_up(off + (size_t)nt_pad * 4);
     const size_t o_cv = off; off = align_up(off + (size_t)nq_pad * slots * 16);
     const size_t o_ci = off; off = align_up(off + (size_t)nq_pad * slots * 16);
     const size_t o_fl = off; off = align_up(off + (size_t)nq * 4);
-    const int fb_grid = 4 * c->sm_count;
-    const size_t fb_parts = std::max<size_t>((size_t)nq, (size_t)2 * fb_grid + FB_MAX_SPLIT);   // >= n_rows * fb_splits(n_rows, fb_grid) for every n_rows
+    const int fb_grid = 2 * c->sm_count;
+    // >= n_rows * fb_splits(n_rows, fb_grid) for every n_rows <= nq: FB_MAX_SPLIT lists per row while the queue is short, then ~fb_grid * FB_ROWS + n_rows
+    const size_t fb_parts = (size_t)nq + (size_t)fb_grid * FB_ROWS + (size_t)FB_MAX_SPLIT * std::min<size_t>((size_t)nq, (size_t)fb_grid * FB_ROWS / FB_MAX_SPLIT + 1);
     const size_t o_fp = off; off = align_up(off + fb_parts * sizeof(Top2));
     const size_t o_misc = off; off = align_up(off + 64);
     SBA_TRY(c->scratch[SCR_WORK2].ensure(off, st));
     uint8_t* ws = c->scratch[SCR_WORK2].as<uint8_t>();
-    const __nv_bfloat16* dA = pq ? pq->prep : (const __nv_bfloat16*)(ws + o_a);
-    const __nv_bfloat16* dB = pt ? pt->prep : (const __nv_bfloat16*)(ws + o_b);
+    const void* dA = pq ? (f16 ? (const void*)pq->prep16 : (const void*)pq->prep) : (const void*)(ws + o_a);
+    const void* dB = pt ? (f16 ? (const void*)pt->prep16 : (const void*)pt->prep) : (const void*)(ws + o_b);
     const float* d_na = pq ? pq->norm : (const float*)(ws + o_na);
     const float* d_nb = pt ? pt->norm : (const float*)(ws + o_nb);
     float4* d_cv = (float4*)(ws + o_cv);
@@ -971,27 +1039,35 @@ int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, 
     int* d_fb_count = (int*)(ws + o_misc);
     const float* d_nbmax = pt ? pt->max_norm : (const float*)(ws + o_misc + 4);
     float* d_dbg = (float*)(ws + o_misc + 8);
+    const float* d_namax = pq ? pq->max_norm : (const float*)(ws + o_misc + 12);
 
     SBA_CUDA(cudaMemsetAsync(ws + o_misc, 0, 64, st));
-    if (!pq || !pt) {   // split whichever side arrives as plain fp32 rows (a side that is prepared counts zero rows here)
+    if (!pq || !pt) {   // convert whichever side arrives as plain fp32 rows (a side that is prepared counts zero rows here)
         const int rows_a = pq ? 0 : nq_pad, rows_b = pt ? 0 : nt_pad;
-        tc_prep_kernel<<<((rows_a + rows_b) * 16 + 255) / 256, 256, 0, st>>>(d_q, nq, rows_a, (__nv_bfloat16*)(ws + o_a), (float*)(ws + o_na), d_t, nt, rows_b,
-                                                                            (__nv_bfloat16*)(ws + o_b), (float*)(ws + o_nb),
-                                                                            (float*)(ws + o_misc + 4));   // the maximum was zeroed by the memset above
+        tc_prep_kernel<<<((rows_a + rows_b) * 16 + 255) / 256, 256, 0, st>>>(
+            d_q, nq, rows_a, f16 ? nullptr : (__nv_bfloat16*)(ws + o_a), (float*)(ws + o_na), d_t, nt, rows_b, f16 ? nullptr : (__nv_bfloat16*)(ws + o_b),
+            (float*)(ws + o_nb), (float*)(ws + o_misc + 4), (float*)(ws + o_misc + 12),   // the maxima were zeroed by the memset above
+            f16 ? (__half*)(ws + o_a) : nullptr, f16 ? (__half*)(ws + o_b) : nullptr);
         SBA_LAUNCHED(c);
     }
 
     CUtensorMap map_a, map_b;
-    SBA_TRY(make_map(&map_a, (void*)dA, nq_pad, BM));
-    SBA_TRY(make_map(&map_b, (void*)dB, nt_pad, BN));
-    SBA_CUDA(cudaFuncSetAttribute(tc_knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SBA_TRY(make_map(&map_a, (void*)dA, nq_pad, BM, row_bytes / 2));
+    SBA_TRY(make_map(&map_b, (void*)dB, nt_pad, BN, row_bytes / 2));
     prof_begin(c, SBA_KERNEL_MATCH);
-    tc_knn_kernel<<<part.n_ctas, THREADS, SMEM_BYTES, st>>>(map_a, map_b, d_nb, part, d_cv, d_ci, slots);
+    if (f16) {
+        SBA_CUDA(cudaFuncSetAttribute(tc_knn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Scheme<1>::SMEM_BYTES));
+        tc_knn_kernel<1><<<part.n_ctas, THREADS, Scheme<1>::SMEM_BYTES, st>>>(map_a, map_b, d_nb, part, d_cv, d_ci, slots);
+    } else {
+        SBA_CUDA(cudaFuncSetAttribute(tc_knn_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Scheme<3>::SMEM_BYTES));
+        tc_knn_kernel<3><<<part.n_ctas, THREADS, Scheme<3>::SMEM_BYTES, st>>>(map_a, map_b, d_nb, part, d_cv, d_ci, slots);
+    }
     prof_end(c, SBA_KERNEL_MATCH);
     SBA_LAUNCHED(c);
     SBA_CUDA(cudaGetLastError());
 
-    tc_rerank_kernel<<<(nq + RR_ROWS - 1) / RR_ROWS, RR_THREADS, 0, st>>>(d_q, nq, d_t, nt, d_na, d_nbmax, part, d_cv, d_ci, slots, d_top, d_fl, d_fb_count, d_dbg);
+    tc_rerank_kernel<<<(nq + RR_ROWS - 1) / RR_ROWS, RR_THREADS, 0, st>>>(d_q, nq, d_t, nt, d_na, d_nbmax, part, d_cv, d_ci, slots, d_top, d_fl, d_fb_count, d_dbg,
+                                                                         f16 ? DELTA_COEF_FP16 : DELTA_COEF, f16 ? d_namax : nullptr);
     SBA_LAUNCHED(c);
     tc_fallback_kernel<<<fb_grid, FB_THREADS, 0, st>>>(d_q, d_t, nt, d_fl, d_fb_count, d_fparts);
     SBA_LAUNCHED(c);

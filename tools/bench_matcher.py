@@ -10,7 +10,7 @@ import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch, torch.distributed as dist
-from spherical_bundle_adjuster_b200 import Context, MATCH_SIMT_EXACT, MATCH_TENSOR, sharding, synth
+from spherical_bundle_adjuster_b200 import Context, MATCH_SIMT_EXACT, MATCH_TENSOR, MATCH_TENSOR_FP16, sharding, synth
 
 def main():
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -24,7 +24,7 @@ def main():
         lo, hi = sharding.shard_range(n, rank, world)             # this rank's query rows
         dA, dB = torch.from_numpy(A[lo:hi]).to(dev), torch.from_numpy(B).to(dev)
         row = {"n": n, "n_gpus": world}
-        for name, algo in (("tensor", MATCH_TENSOR), ("simt", MATCH_SIMT_EXACT)):
+        for name, algo in (("tensor_fp16", MATCH_TENSOR_FP16), ("tensor_bf16x3", MATCH_TENSOR), ("simt", MATCH_SIMT_EXACT)):
             if algo == MATCH_SIMT_EXACT and n > 16384: continue
             ctx.set_profiling(True)
             for _ in range(2): m = ctx.match_two_image(dA, dB, 0.3, algo=algo)
