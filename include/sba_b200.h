@@ -263,7 +263,8 @@ int sba_ba_rot_eval(sba_ba_problem* p, const double* r, const double t[3], doubl
 typedef struct sba_solve_summary {
     int iterations;      /* LM iterations run (successful + unsuccessful + invalid) */
     int num_successful;
-    int termination;     /* 0 max iterations, 1 function tol, 2 gradient tol, 3 parameter tol, 4 failure */
+    int termination;     /* 0 max iterations, 1 function tol, 2 gradient tol, 3 parameter tol, 4 failure (five invalid steps in a row),
+                            5 minimum trust-region radius reached (Ceres reports CONVERGENCE for it) */
     int evaluations;     /* residual+Jacobian passes over the observations */
     double initial_cost;
     double final_cost;

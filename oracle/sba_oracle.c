@@ -490,7 +490,7 @@ static int solve3_spd(const double H[6], const double dd[3], const double rhs[3]
 typedef struct {
     int iterations;            /* LM iterations executed (successful + unsuccessful) */
     int num_successful;
-    int termination;           /* 0 max-iter, 1 function tol, 2 gradient tol, 3 parameter tol, 4 failure */
+    int termination;           /* 0 max-iter, 1 function tol, 2 gradient tol, 3 parameter tol, 4 failure (5 invalid steps in a row), 5 minimum trust-region radius (Ceres: CONVERGENCE) */
     double initial_cost;
     double final_cost;
     double final_radius;
@@ -591,7 +591,7 @@ static void lm_solve(int mode, const double *b1, const double *b2, const int32_t
              * LevenbergMarquardtStrategy::StepIsInvalid): radius *= 0.5, at most 5 in a row */
             if (++consecutive_invalid >= 5) { sum->termination = 4; break; }
             radius *= 0.5;
-            if (radius <= min_radius) { sum->termination = 4; break; }
+            if (radius < min_radius) { sum->termination = 5; break; }
             continue;
         }
         consecutive_invalid = 0;
@@ -624,7 +624,7 @@ static void lm_solve(int mode, const double *b1, const double *b2, const int32_t
             radius = radius / dec_factor; dec_factor *= 2.0;
         }
         /* MinTrustRegionRadiusReached (checked between iterations) */
-        if (radius <= min_radius) { sum->termination = 4; break; }
+        if (radius < min_radius) { sum->termination = 5; break; }
     }
 done:
     sum->final_cost = cost; sum->final_radius = radius;
@@ -868,7 +868,7 @@ void orc_ba_d_solve(const double *b1, const double *b2, int n, const double r[3]
         double gmax = 0;
         for (int k = 0; k < np; k++) gmax = fmax(gmax, fabs(d[k] - fmax(d[k] - g[k], 0.0)));
         if (gmax <= gtol) { sum->termination = 2; break; }
-        if (radius < min_radius) { sum->termination = 4; break; }
+        if (radius < min_radius) { sum->termination = 5; break; }
         sum->iterations++;
 
         /* LevenbergMarquardtStrategy::ComputeStep on the column-scaled Jacobian, block by block */

@@ -212,6 +212,9 @@ __device__ inline double block_max(double v, double* sh)
 
 // ---- peer-memory exchange of the per-camera blocks (one CTA) ------------------------------------------------
 constexpr int COMM_MAX_WORLD = 16;
+// Peer waits give up after ~2 minutes of SM clock: long enough for ordinary rank skew (first-call plan builds, a rank busy on the
+// host, a time-sliced GPU), short enough that a dead peer surfaces as a CUDA error instead of a hung box.
+constexpr long long COMM_TIMEOUT_CYCLES = 240000000000ll;
 
 constexpr int COMM_MAX_SLICES = 64;
 constexpr int COMM_HEADER_BYTES = COMM_MAX_SLICES * 8;   // one sequence flag per slice, then the data
@@ -239,7 +242,7 @@ __device__ void comm_exchange(const CommDev& cd, double* __restrict__ blk, int c
     if ((int)threadIdx.x < cd.world) {                            // one thread per peer waits for its flag
         const long long t0 = clock64();
         while (cd.flag[threadIdx.x][0] < seq + 1) {
-            if (clock64() - t0 > 20000000000ll) __trap();        // a lost peer traps instead of hanging the GPU
+            if (clock64() - t0 > COMM_TIMEOUT_CYCLES) __trap();  // a lost peer traps instead of hanging the GPU
         }
     }
     __threadfence_system();
@@ -271,7 +274,7 @@ __global__ void __launch_bounds__(EVAL_THREADS) ba_exchange_kernel(CommDev cd, d
     if ((int)threadIdx.x < cd.world) {
         const long long t0 = clock64();
         while (cd.flag[threadIdx.x][blockIdx.x] < seq + 1) {
-            if (clock64() - t0 > 20000000000ll) __trap();
+            if (clock64() - t0 > COMM_TIMEOUT_CYCLES) __trap();
         }
     }
     __threadfence_system();
@@ -394,7 +397,7 @@ __device__ void lm_decide(const LMArrays A, double* sh)
         if (tid == 0 && gmax <= gtol) { S.termination = 2; S.done = 1; }
     }
     __syncthreads();
-    if (tid == 0 && !S.done && S.radius <= min_radius) { S.termination = 4; S.done = 1; }
+    if (tid == 0 && !S.done && S.radius < min_radius) { S.termination = 5; S.done = 1; }   // Ceres: CONVERGENCE, "minimum trust region radius reached"
     __syncthreads();
 
     // next candidate (invalid steps retry in place: H and g do not change)
@@ -438,7 +441,7 @@ __device__ void lm_decide(const LMArrays A, double* sh)
                 if (++S.consecutive_invalid >= 5) { S.termination = 4; S.done = 1; }
                 else {
                     S.radius *= 0.5;
-                    if (S.radius <= min_radius) { S.termination = 4; S.done = 1; }
+                    if (S.radius < min_radius) { S.termination = 5; S.done = 1; }
                 }
                 s_accept = -1;
             } else {
@@ -881,7 +884,7 @@ __device__ void lm_decide_single(const LMArrays A)
         }
         if (gm <= gtol) { S.termination = 2; S.done = 1; }
     }
-    if (!S.done && S.radius <= min_radius) { S.termination = 4; S.done = 1; }
+    if (!S.done && S.radius < min_radius) { S.termination = 5; S.done = 1; }
     while (!S.done) {
         if (S.iter >= S.max_iter) { S.termination = 0; S.done = 1; break; }
         const double radius = S.radius;
@@ -909,7 +912,7 @@ __device__ void lm_decide_single(const LMArrays A)
             if (++S.consecutive_invalid >= 5) { S.termination = 4; S.done = 1; }
             else {
                 S.radius *= 0.5;
-                if (S.radius <= min_radius) { S.termination = 4; S.done = 1; }
+                if (S.radius < min_radius) { S.termination = 5; S.done = 1; }
             }
             continue;   // retry in place: H and g do not change
         }

@@ -209,7 +209,7 @@ __device__ __noinline__ void depth_decide(DepthState& st, const double* S)
         // FinalizeIterationAndCheckIfMinimizerCanContinue, then a new iteration
         if (st.iter >= st.max_iter) { st.termination = 0; st.done = 1; return; }
         if (S[7] <= gtol) { st.termination = 2; st.done = 1; return; }
-        if (st.radius < min_radius) { st.termination = 4; st.done = 1; return; }
+        if (st.radius < min_radius) { st.termination = 5; st.done = 1; return; }   // Ceres: CONVERGENCE, "minimum trust region radius reached"
         st.iter++;
         if (S[9] != 0.0 || !(S[1] > 0.0)) {   // invalid step: StepIsInvalid
             if (++st.consecutive_invalid >= 5) { st.termination = 4; st.done = 1; return; }

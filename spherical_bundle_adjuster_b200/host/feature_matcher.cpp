@@ -49,6 +49,11 @@ std::vector<cv::DMatch> feature_matcher::match_two_image(const cv::Mat& descript
     const int dim = nq ? descriptor1.cols : descriptor2.cols;
     std::vector<cv::DMatch> good_matches;
     if (nq == 0) return good_matches;
+    // the library reads the descriptors as dense fp32 rows: say so instead of reinterpreting whatever arrives
+    // (the reference hands cv::Mat to OpenCV's matcher, which converts / rejects on its own)
+    if (descriptor1.type() != CV_32FC1 || (nt && descriptor2.type() != CV_32FC1) || !descriptor1.isContinuous() || !descriptor2.isContinuous() ||
+        (nt && descriptor2.cols != dim) || (dim != 64 && dim != 128))
+        throw std::runtime_error("feature_matcher::match_two_image: descriptors must be continuous CV_32F matrices with 64 or 128 columns (SURF)");
     std::vector<int32_t> qi(nq), ti(nq);
     std::vector<float> dist(nq);
     int32_t n = 0;
