@@ -89,6 +89,32 @@ __device__ inline float l2sqr_opencv(const float* __restrict__ a, const float* _
     return __fadd_rn(__fadd_rn(s[0], s[2]), __fadd_rn(s[1], s[3]));
 }
 
+// The same value from 16-byte aligned rows read as float4 (shared memory: LDS.128), streaming: element 16c + 4u + l is
+// component l of piece 4c + u and goes to accumulator (u, l); each accumulator sees its terms in increasing c, as above.
+template <int DIM>
+__device__ inline float l2sqr_opencv_v4(const float4* __restrict__ a, const float4* __restrict__ b)
+{
+    float acc[4][4];
+#pragma unroll
+    for (int c = 0; c < DIM / 16; c++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const float4 x = a[4 * c + u], y = b[4 * c + u];
+            const float t0 = __fsub_rn(x.x, y.x), t1 = __fsub_rn(x.y, y.y), t2 = __fsub_rn(x.z, y.z), t3 = __fsub_rn(x.w, y.w);
+            if (c == 0) {
+                acc[u][0] = __fmul_rn(t0, t0); acc[u][1] = __fmul_rn(t1, t1); acc[u][2] = __fmul_rn(t2, t2); acc[u][3] = __fmul_rn(t3, t3);
+            } else {
+                acc[u][0] = __fadd_rn(acc[u][0], __fmul_rn(t0, t0)); acc[u][1] = __fadd_rn(acc[u][1], __fmul_rn(t1, t1));
+                acc[u][2] = __fadd_rn(acc[u][2], __fmul_rn(t2, t2)); acc[u][3] = __fadd_rn(acc[u][3], __fmul_rn(t3, t3));
+            }
+        }
+    }
+    float s[4];
+#pragma unroll
+    for (int l = 0; l < 4; l++) s[l] = __fadd_rn(__fadd_rn(__fadd_rn(acc[0][l], acc[1][l]), acc[2][l]), acc[3][l]);
+    return __fadd_rn(__fadd_rn(s[0], s[2]), __fadd_rn(s[1], s[3]));
+}
+
 // A descriptor set prepared once for the tensor-core matcher (bf16 hi/lo rows, norms, largest norm) -- see
 // sba_descriptors_create.  n_pad is a multiple of 256 (serves as query block and as train tiles), pad norms are +inf.
 struct PreparedSet {

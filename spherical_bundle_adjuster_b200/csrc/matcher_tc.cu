@@ -58,9 +58,12 @@ constexpr int B_KBLOCK_BYTES = BN * 128;   // 16 KB
 //   P = 3  bf16 split  x = hi + lo: hi.hi + hi.lo + lo.hi, error ~2^-16 |a||b|  (rows of 128 bf16: [hi | lo])
 //   P = 1  plain fp16 rows: ONE product, error ~2^-10 |a||b|; a third of the tensor work, paid for with a wider safety
 //          margin in the re-rank (more rows go to the exact fallback)
+//   P = 2  128-d descriptors (feature_matcher.cpp:13, extended SURF): plain fp16 rows of 128 = two 64-wide k-blocks, one
+//          product -- the same shared-memory footprint and the same epilogue as P = 3, 16 MMAs per tile
 template <int P> struct Scheme {
-    static constexpr int KBLOCKS = P == 3 ? 2 : 1;                        // 64-wide k-blocks per prepared row
-    static constexpr int ROW_ELEMS = KBLOCKS * DIM;                        // 16-bit elements per prepared row
+    static constexpr int D = P == 2 ? 128 : 64;                            // descriptor length
+    static constexpr int KBLOCKS = P == 1 ? 1 : 2;                         // 64-wide k-blocks per prepared row
+    static constexpr int ROW_ELEMS = KBLOCKS * 64;                         // 16-bit elements per prepared row
     static constexpr int SMEM_A = KBLOCKS * A_KBLOCK_BYTES;
     static constexpr int B_STAGE_BYTES = KBLOCKS * B_KBLOCK_BYTES;
     static constexpr int SMEM_B = STAGES * B_STAGE_BYTES;
@@ -70,7 +73,7 @@ template <int P> struct Scheme {
 constexpr int ACC_COLS = 2 * BN;   // TMEM columns per accumulator stage: row-half 0 | row-half 1
 constexpr uint32_t TMEM_COLS = 512;
 constexpr float DELTA_COEF = 4e-5f;  // bf16 x 3: |approx - exact| <= DELTA_COEF * (|a|^2 + max|b|^2): derivation at tc_rerank_kernel
-constexpr float DELTA_COEF_FP16 = 1.0e-3f;   // fp16 x 1: same place
+constexpr float DELTA_COEF_FP16 = 1.05e-3f;  // fp16 x 1 (64-d and 128-d): same place
 // Candidate keys (epilogue): a chunk minimum with the chunk's id in the low mantissa bits, so that ONE fp32 min / max
 // moves value and id together.  9 bits: [8] = "old" flag, [7:3] tile inside the current 32-tile window, [2:0] chunk of
 // the thread's 64 columns -- or, for entries that survived a window change, flag | list slot (the absolute chunk id of
@@ -204,12 +207,13 @@ struct Partition {
 };
 
 // ---- 1. prepare ------------------------------------------------------------------------------------------
-// 16 threads per row, 4 floats each.  Rows >= n are padding: zeros, norm = +inf (train) so they never win.
+// D/4 threads per row, 4 floats each.  Rows >= n are padding: zeros, norm = PAD_NORM (train) so they never win.
+template <int D>
 __device__ __forceinline__ void prep_row(const float* __restrict__ x, int n, int row, int part, __nv_bfloat16* __restrict__ out, float* __restrict__ norm,
                                          float pad_norm, float* __restrict__ max_norm, __half* __restrict__ out16)
 {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row < n) v = __ldg(reinterpret_cast<const float4*>(x + (size_t)row * DIM) + part);
+    if (row < n) v = __ldg(reinterpret_cast<const float4*>(x + (size_t)row * D) + part);
     const float f[4] = {v.x, v.y, v.z, v.w};
     __align__(8) __nv_bfloat16 hi[4];
     __align__(8) __nv_bfloat16 lo[4];
@@ -221,8 +225,8 @@ __device__ __forceinline__ void prep_row(const float* __restrict__ x, int n, int
         s = fmaf(f[k], f[k], s);
     }
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, 16);
-    if (out) {
+    for (int o = D / 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, D / 4);
+    if (out) {   // D == 64 only
         __nv_bfloat16* dst = out + (size_t)row * KP;
         *reinterpret_cast<uint2*>(dst + part * 4) = *reinterpret_cast<const uint2*>(hi);
         *reinterpret_cast<uint2*>(dst + DIM + part * 4) = *reinterpret_cast<const uint2*>(lo);
@@ -231,7 +235,7 @@ __device__ __forceinline__ void prep_row(const float* __restrict__ x, int n, int
         __align__(8) __half h[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) h[k] = __float2half_rn(f[k]);
-        *reinterpret_cast<uint2*>(out16 + (size_t)row * DIM + part * 4) = *reinterpret_cast<const uint2*>(h);
+        *reinterpret_cast<uint2*>(out16 + (size_t)row * D + part * 4) = *reinterpret_cast<const uint2*>(h);
     }
     if (part == 0) {
         norm[row] = row < n ? s : pad_norm;
@@ -241,15 +245,16 @@ __device__ __forceinline__ void prep_row(const float* __restrict__ x, int n, int
 
 // Both descriptor sets in one launch: rows [0, nq_pad) are queries, the rest train rows.
 // out*: bf16 hi|lo rows (P = 3) or NULL; out16*: fp16 rows (P = 1) or NULL.  na_max / nb_max: largest squared norms.
+template <int D>
 __global__ void tc_prep_kernel(const float* __restrict__ q, int nq, int nq_pad, __nv_bfloat16* __restrict__ outA, float* __restrict__ na,
                                const float* __restrict__ t, int nt, int nt_pad, __nv_bfloat16* __restrict__ outB, float* __restrict__ nb,
                                float* __restrict__ nb_max /* running maximum of the finite train norms */, float* __restrict__ na_max,
                                __half* __restrict__ out16A, __half* __restrict__ out16B)
 {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int row = gid >> 4, part = gid & 15;      // 16 threads per row, 4 floats each; a half-warp never straddles the two sets
-    if (row < nq_pad) prep_row(q, nq, row, part, outA, na, 0.f, na_max, out16A);
-    else if (row < nq_pad + nt_pad) prep_row(t, nt, row - nq_pad, part, outB, nb, PAD_NORM, nb_max, out16B);
+    const int row = gid / (D / 4), part = gid % (D / 4);   // D/4 threads per row, 4 floats each; a row never straddles two warps or the two sets
+    if (row < nq_pad) prep_row<D>(q, nq, row, part, outA, na, 0.f, na_max, out16A);
+    else if (row < nq_pad + nt_pad) prep_row<D>(t, nt, row - nq_pad, part, outB, nb, PAD_NORM, nb_max, out16B);
 }
 
 // ---- 2. the tensor-core kernel ---------------------------------------------------------------------------
@@ -421,7 +426,7 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                     mbar_wait(a_empty, (seg & 1) ^ 1);
                     mbar_expect_tx(a_full, SMEM_A);
                     tma_load_2d(sA, &map_a, a_full, 0, qb * BM);
-                    if (P == 3) tma_load_2d(sA + A_KBLOCK_BYTES, &map_a, a_full, DIM, qb * BM);
+                    if (P != 1) tma_load_2d(sA + A_KBLOCK_BYTES, &map_a, a_full, 64, qb * BM);
                     seg++;
                 }
                 mbar_wait(b_empty + s, ring_phase ^ 1);
@@ -432,7 +437,7 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 mbar_expect_tx(b_full + s, B_STAGE_BYTES);
                 uint8_t* dst = sB + s * B_STAGE_BYTES;
                 tma_load_2d(dst, &map_b, b_full + s, 0, tb * BN);
-                if (P == 3) tma_load_2d(dst + B_KBLOCK_BYTES, &map_b, b_full + s, DIM, tb * BN);
+                if (P != 1) tma_load_2d(dst + B_KBLOCK_BYTES, &map_b, b_full + s, 64, tb * BN);
                 }
                 if (++s == STAGES) { s = 0; ring_phase ^= 1; }
                 new_seg = (++tb == ntb);
@@ -488,6 +493,9 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                         for (int k = 0; k < 4; k++) umma_bf16(d0, dA_hi0 + 2 * k, dB_lo + 2 * k, IDESC, 1);
 #pragma unroll
                         for (int k = 0; k < 4; k++) umma_bf16(d0, dA_lo0 + 2 * k, dB_hi + 2 * k, IDESC, 1);
+                    } else if (P == 2) {   // second half of the 128-long rows
+#pragma unroll
+                        for (int k = 0; k < 4; k++) umma_bf16(d0, dA_lo0 + 2 * k, dB_lo + 2 * k, IDESC_F16, 1);
                     }
 #endif
                     tcgen05_commit(acc_full + 2 * acc);      // row-half 0 ready for its epilogue warps
@@ -503,6 +511,9 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                         for (int k = 0; k < 4; k++) umma_bf16(d1, dA_hi1 + 2 * k, dB_lo + 2 * k, IDESC, 1);
 #pragma unroll
                         for (int k = 0; k < 4; k++) umma_bf16(d1, dA_lo1 + 2 * k, dB_hi + 2 * k, IDESC, 1);
+                    } else if (P == 2) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) umma_bf16(d1, dA_lo1 + 2 * k, dB_lo + 2 * k, IDESC_F16, 1);
                     }
 #endif
                     mbar_arrive(turn + (my_parity ^ 1));     // the other issuer may queue the next tile
@@ -690,19 +701,23 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 //      value >= the third best chunk key, so the row is final if its exact second best clears that bound by the margin.
 //   c) phase 1, only for rows that are not final yet: the same for chunks 2 and 3, bound = the fourth best key.
 //      Rows that still fail go to the exact fallback.
-constexpr int RR_THREADS = 128;
-constexpr int RR_ROWS = RR_THREADS / 16;
+template <int D> struct RR {                       // 64-d: 8 query rows per 128-thread CTA; 128-d: 4 per 64-thread CTA (shared memory)
+    static constexpr int THREADS = D == 64 ? 128 : 64;
+    static constexpr int ROWS = THREADS / 16;
+};
 constexpr int RR_PER_THREAD = 4;   // up to 16*4 = 64 candidate entries (16 slots) merged by shuffles; more -> serial path
 static_assert(CHUNK == 8 && NCAND == 4, "the re-rank evaluates two chunks of 8 rows per phase with 16 threads");
 
-__global__ void __launch_bounds__(RR_THREADS, 4)
+template <int D>
+__global__ void __launch_bounds__(RR<D>::THREADS, 4)
 tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, int nt, const float* __restrict__ na,
                  const float* __restrict__ nb_max, Partition part, const float4* __restrict__ cand_v, const int4* __restrict__ cand_id,
                  int slots, Top2* __restrict__ top, int* __restrict__ fb_list, int* __restrict__ fb_count, float* __restrict__ dbg_max_err,
                  float delta_coef, const float* __restrict__ na_max)
 {
-    __shared__ __align__(16) float qs[RR_ROWS][DIM];
-    __shared__ __align__(16) float ts[RR_ROWS][16][DIM + 4];   // the candidate rows of every query of the CTA (one phase)
+    constexpr int RR_ROWS = RR<D>::ROWS, V4 = D / 64;   // V4: float4 pieces of a row per thread of the 16-thread group
+    __shared__ __align__(16) float qs[RR_ROWS][D];
+    __shared__ __align__(16) float ts[RR_ROWS][16][D + 4];   // the candidate rows of every query of the CTA (one phase)
     __shared__ float win_v[RR_ROWS][NCAND];
     __shared__ int win_id[RR_ROWS][NCAND];
     const int tid = threadIdx.x, grp = tid >> 4, e = tid & 15;
@@ -712,7 +727,8 @@ tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ 
     const float INF = __int_as_float(0x7f800000);
 
     // query rows of this CTA -> shared (coalesced 128-bit loads: 8 rows x 16 float4)
-    reinterpret_cast<float4*>(&qs[grp][0])[e] = __ldg(reinterpret_cast<const float4*>(q + (size_t)r * DIM) + e);
+#pragma unroll
+    for (int v = 0; v < V4; v++) reinterpret_cast<float4*>(&qs[grp][0])[e + 16 * v] = __ldg(reinterpret_cast<const float4*>(q + (size_t)r * D) + e + 16 * v);
     if (e < NCAND) { win_v[grp][e] = INF; win_id[grp][e] = -1; }
     __syncthreads();
 
@@ -772,7 +788,7 @@ tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ 
         //    threads of the group read its 256 contiguous bytes as one float4 each, so a load instruction touches 4 lines per
         //    warp instead of 32 -- parked in shared memory (row stride 68 floats: the float4 reads below are conflict free).
         {
-            float4 stage[8];
+            float4 stage[8][V4];
 #pragma unroll
             for (int half = 0; half < 2; half++) {
                 const int cid = win_id[grp][2 * phase + half];
@@ -780,11 +796,15 @@ tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ 
                 for (int cc = 0; cc < 8; cc++) {
                     const int cj = cid * CHUNK + cc;
                     const bool ok = need && cid >= 0 && cj < nt;
-                    stage[cc] = ok ? __ldg(reinterpret_cast<const float4*>(t + (size_t)cj * DIM) + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int v = 0; v < V4; v++)
+                        stage[cc][v] = ok ? __ldg(reinterpret_cast<const float4*>(t + (size_t)cj * D) + e + 16 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 __syncwarp();
 #pragma unroll
-                for (int cc = 0; cc < 8; cc++) *reinterpret_cast<float4*>(&ts[grp][half * 8 + cc][4 * e]) = stage[cc];
+                for (int cc = 0; cc < 8; cc++)
+#pragma unroll
+                    for (int v = 0; v < V4; v++) *reinterpret_cast<float4*>(&ts[grp][half * 8 + cc][4 * (e + 16 * v)]) = stage[cc][v];
             }
         }
         __syncwarp();
@@ -795,17 +815,8 @@ tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ 
         Top2 cur = top2_empty();
         float exact_v = INF;
         if (valid) {
-            float tv[DIM], qv[DIM];
-            const float4* tp = reinterpret_cast<const float4*>(&ts[grp][e][0]);
-            const float4* qp = reinterpret_cast<const float4*>(&qs[grp][0]);
-#pragma unroll
-            for (int k = 0; k < DIM / 4; k++) {
-                const float4 a = tp[k];
-                tv[4 * k] = a.x; tv[4 * k + 1] = a.y; tv[4 * k + 2] = a.z; tv[4 * k + 3] = a.w;
-                const float4 b = qp[k];
-                qv[4 * k] = b.x; qv[4 * k + 1] = b.y; qv[4 * k + 2] = b.z; qv[4 * k + 3] = b.w;
-            }
-            const float dsq = l2sqr_opencv<DIM>(qv, tv);
+            // straight from shared memory as float4 (row stride D + 4 floats: conflict free)
+            const float dsq = l2sqr_opencv_v4<D>(reinterpret_cast<const float4*>(&qs[grp][0]), reinterpret_cast<const float4*>(&ts[grp][e][0]));
             cur.d0 = __fsqrt_rn(dsq);
             cur.i0 = j;
             exact_v = dsq - na_r;   // exact value on the scale of the approximate ones
@@ -861,13 +872,15 @@ tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ 
 // filter's wider margin produces at 16k x 16k -- cost microseconds, and a few thousand (adversarial norms) still spread
 // over the whole chip.  knn2_finalize_kernel merges a row's S partial top-2 lists in range order.
 constexpr int FB_THREADS = 256;
-constexpr int FB_CHUNK = 64;                 // train rows staged at a time
-constexpr int FB_PITCH = DIM + 1;            // padded row pitch: lane l reads row l, conflict free
 
+template <int D>
 __global__ void __launch_bounds__(FB_THREADS)
 tc_fallback_kernel(const float* __restrict__ q, const float* __restrict__ t, int nt, const int* __restrict__ fb_list,
                    const int* __restrict__ fb_count, Top2* __restrict__ parts)
 {
+    constexpr int FB_CHUNK = D == 64 ? 64 : 32;   // train rows staged at a time
+    constexpr int FB_PITCH = D + 1;               // padded row pitch: lane l reads row l, conflict free
+    constexpr int DIM = D;
     __shared__ float qs[FB_ROWS][DIM];
     __shared__ float ts[FB_CHUNK][FB_PITCH];
     const int n = *fb_count;
@@ -970,10 +983,10 @@ static int make_map(CUtensorMap* map, void* base, int rows, int box_rows, int ro
 
 }  // namespace tc
 
-bool knn2_tensor_applicable(int nq, int nt, int dim) { return dim == tc::DIM && nq >= 1 && nt >= 1; }
+bool knn2_tensor_applicable(int nq, int nt, int dim) { return (dim == 64 || dim == 128) && nq >= 1 && nt >= 1; }
 
 // Heuristic used by SBA_MATCH_AUTO: below ~1M pair distances the exact SIMT kernel's latency wins.
-bool knn2_tensor_preferred(int nq, int nt, int dim) { return dim == tc::DIM && (long long)nq * nt >= (1ll << 20) && nt >= 1024; }
+bool knn2_tensor_preferred(int nq, int nt, int dim) { return (dim == 64 || dim == 128) && (long long)nq * nt >= (1ll << 20) && nt >= 1024; }
 
 // Both prepared forms of one descriptor set into caller-owned buffers (sba_descriptors_create): prep [n_pad x 128] bf16 hi|lo,
 // prep16 [n_pad x 64] fp16, norm [n_pad] (PAD_NORM on the padding rows), *max_norm = largest real norm.
@@ -981,24 +994,26 @@ int knn2_prepare_set(sba_ctx* c, const float* d_raw, int n, int n_pad, __nv_bflo
 {
     using namespace tc;
     SBA_CUDA(cudaMemsetAsync(max_norm, 0, sizeof(float), c->stream));
-    tc_prep_kernel<<<(n_pad * 16 + 255) / 256, 256, 0, c->stream>>>(nullptr, 0, 0, nullptr, nullptr, d_raw, n, n_pad, prep, norm, max_norm, nullptr, nullptr,
-                                                                    (__half*)prep16);
+    tc_prep_kernel<64><<<(n_pad * 16 + 255) / 256, 256, 0, c->stream>>>(nullptr, 0, 0, nullptr, nullptr, d_raw, n, n_pad, prep, norm, max_norm, nullptr, nullptr,
+                                                                        (__half*)prep16);
     SBA_LAUNCHED(c);
     SBA_CUDA(cudaGetLastError());
     return SBA_OK;
 }
 
-// pq / pt: optional prepared forms of the query / train set (then that side is not converted again).
-// products: 3 = bf16 split filter, 1 = fp16 filter (see tc::Scheme).
+// pq / pt: optional prepared forms of the query / train set (64-d only; then that side is not converted again).
+// products: 3 = bf16 split filter, 1 = fp16 filter (see tc::Scheme); 128-d descriptors always take the fp16 filter (mode 2).
 int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, int dim, Top2* d_top, const PreparedSet* pq, const PreparedSet* pt,
                 int products)
 {
     using namespace tc;
-    if (dim != DIM) {
-        set_error("tensor-core matcher handles dim %d only", DIM);
+    if (dim != 64 && dim != 128) {
+        set_error("tensor-core matcher handles 64- and 128-d descriptors only");
         return SBA_ERR_UNSUPPORTED;
     }
-    const bool f16 = products == 1;
+    const int mode = dim == 128 ? 2 : (products == 1 ? 1 : 3);
+    if (dim == 128) pq = pt = nullptr;           // prepared sets hold the 64-d forms only
+    const bool f16 = mode != 3;
     cudaStream_t st = c->stream;
     const int nqb = (nq + BM - 1) / BM, ntb = (nt + BN - 1) / BN;
     const int nq_pad = pq ? pq->n_pad : nqb * BM, nt_pad = pt ? pt->n_pad : ntb * BN;
@@ -1009,7 +1024,7 @@ int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, 
     // capped so that no span can come out empty
     part.bcost = (int)std::min<long long>(5, part.T / part.n_ctas / 4);
     const int slots = part.max_slots() * SUBSLOTS;
-    const int row_bytes = f16 ? DIM * 2 : KP * 2;
+    const int row_bytes = mode == 1 ? 128 : 256;   // 16-bit elements: 64 (fp16), 128 (bf16 hi|lo, or fp16 of a 128-d row)
 
     // workspace carve-up (one buffer)
     auto align_up = [](size_t v) { return (v + 1023) & ~(size_t)1023; };
@@ -1044,10 +1059,15 @@ int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, 
     SBA_CUDA(cudaMemsetAsync(ws + o_misc, 0, 64, st));
     if (!pq || !pt) {   // convert whichever side arrives as plain fp32 rows (a side that is prepared counts zero rows here)
         const int rows_a = pq ? 0 : nq_pad, rows_b = pt ? 0 : nt_pad;
-        tc_prep_kernel<<<((rows_a + rows_b) * 16 + 255) / 256, 256, 0, st>>>(
-            d_q, nq, rows_a, f16 ? nullptr : (__nv_bfloat16*)(ws + o_a), (float*)(ws + o_na), d_t, nt, rows_b, f16 ? nullptr : (__nv_bfloat16*)(ws + o_b),
-            (float*)(ws + o_nb), (float*)(ws + o_misc + 4), (float*)(ws + o_misc + 12),   // the maxima were zeroed by the memset above
-            f16 ? (__half*)(ws + o_a) : nullptr, f16 ? (__half*)(ws + o_b) : nullptr);
+        __nv_bfloat16* bA = f16 ? nullptr : (__nv_bfloat16*)(ws + o_a);
+        __nv_bfloat16* bB = f16 ? nullptr : (__nv_bfloat16*)(ws + o_b);
+        __half* hA = f16 ? (__half*)(ws + o_a) : nullptr;
+        __half* hB = f16 ? (__half*)(ws + o_b) : nullptr;
+        float *na_w = (float*)(ws + o_na), *nb_w = (float*)(ws + o_nb), *nbm = (float*)(ws + o_misc + 4), *nam = (float*)(ws + o_misc + 12);   // maxima zeroed above
+        if (dim == 64)
+            tc_prep_kernel<64><<<((rows_a + rows_b) * 16 + 255) / 256, 256, 0, st>>>(d_q, nq, rows_a, bA, na_w, d_t, nt, rows_b, bB, nb_w, nbm, nam, hA, hB);
+        else
+            tc_prep_kernel<128><<<((rows_a + rows_b) * 32 + 255) / 256, 256, 0, st>>>(d_q, nq, rows_a, bA, na_w, d_t, nt, rows_b, bB, nb_w, nbm, nam, hA, hB);
         SBA_LAUNCHED(c);
     }
 
@@ -1055,9 +1075,12 @@ int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, 
     SBA_TRY(make_map(&map_a, (void*)dA, nq_pad, BM, row_bytes / 2));
     SBA_TRY(make_map(&map_b, (void*)dB, nt_pad, BN, row_bytes / 2));
     prof_begin(c, SBA_KERNEL_MATCH);
-    if (f16) {
+    if (mode == 1) {
         SBA_CUDA(cudaFuncSetAttribute(tc_knn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Scheme<1>::SMEM_BYTES));
         tc_knn_kernel<1><<<part.n_ctas, THREADS, Scheme<1>::SMEM_BYTES, st>>>(map_a, map_b, d_nb, part, d_cv, d_ci, slots);
+    } else if (mode == 2) {
+        SBA_CUDA(cudaFuncSetAttribute(tc_knn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Scheme<2>::SMEM_BYTES));
+        tc_knn_kernel<2><<<part.n_ctas, THREADS, Scheme<2>::SMEM_BYTES, st>>>(map_a, map_b, d_nb, part, d_cv, d_ci, slots);
     } else {
         SBA_CUDA(cudaFuncSetAttribute(tc_knn_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Scheme<3>::SMEM_BYTES));
         tc_knn_kernel<3><<<part.n_ctas, THREADS, Scheme<3>::SMEM_BYTES, st>>>(map_a, map_b, d_nb, part, d_cv, d_ci, slots);
@@ -1066,10 +1089,19 @@ int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, 
     SBA_LAUNCHED(c);
     SBA_CUDA(cudaGetLastError());
 
-    tc_rerank_kernel<<<(nq + RR_ROWS - 1) / RR_ROWS, RR_THREADS, 0, st>>>(d_q, nq, d_t, nt, d_na, d_nbmax, part, d_cv, d_ci, slots, d_top, d_fl, d_fb_count, d_dbg,
-                                                                         f16 ? DELTA_COEF_FP16 : DELTA_COEF, f16 ? d_namax : nullptr);
-    SBA_LAUNCHED(c);
-    tc_fallback_kernel<<<fb_grid, FB_THREADS, 0, st>>>(d_q, d_t, nt, d_fl, d_fb_count, d_fparts);
+    const float dcoef = f16 ? DELTA_COEF_FP16 : DELTA_COEF;
+    const float* namax = f16 ? d_namax : nullptr;
+    if (dim == 64) {
+        tc_rerank_kernel<64><<<(nq + RR<64>::ROWS - 1) / RR<64>::ROWS, RR<64>::THREADS, 0, st>>>(d_q, nq, d_t, nt, d_na, d_nbmax, part, d_cv, d_ci, slots, d_top, d_fl,
+                                                                                               d_fb_count, d_dbg, dcoef, namax);
+        SBA_LAUNCHED(c);
+        tc_fallback_kernel<64><<<fb_grid, FB_THREADS, 0, st>>>(d_q, d_t, nt, d_fl, d_fb_count, d_fparts);
+    } else {
+        tc_rerank_kernel<128><<<(nq + RR<128>::ROWS - 1) / RR<128>::ROWS, RR<128>::THREADS, 0, st>>>(d_q, nq, d_t, nt, d_na, d_nbmax, part, d_cv, d_ci, slots, d_top,
+                                                                                                   d_fl, d_fb_count, d_dbg, dcoef, namax);
+        SBA_LAUNCHED(c);
+        tc_fallback_kernel<128><<<fb_grid, FB_THREADS, 0, st>>>(d_q, d_t, nt, d_fl, d_fb_count, d_fparts);
+    }
     SBA_LAUNCHED(c);
     c->fb_parts = d_fparts; c->fb_count = d_fb_count; c->fb_grid = fb_grid;   // merged per row by knn2_finalize_kernel
     SBA_CUDA(cudaGetLastError());

@@ -16,13 +16,8 @@ ERR_BOUND = {MATCH_TENSOR: 4e-5, MATCH_TENSOR_FP16: 1e-3}     # DELTA_COEF / DEL
 
 
 def _match(ctx, q, t, ratio, algo, **kw):
-    """The tensor-core path covers SURF-64; asking for it explicitly with 128-d descriptors must fail
-    loudly (AUTO routes those to the exact SIMT kernel)."""
-    dim = q.shape[1] if q.ndim == 2 and q.shape[0] else t.shape[1]
-    if algo in TENSOR_ALGOS and dim != 64:
-        with pytest.raises(SbaError):
-            ctx.match_two_image(q, t, ratio, algo=algo, **kw)
-        pytest.skip("tensor path: 64-d only")
+    """Both tensor-core filters cover SURF-64; 128-d descriptors (extended SURF) take the tensor path too (always the fp16
+    filter, whichever of the two is asked for)."""
     return ctx.match_two_image(q, t, ratio, algo=algo, **kw)
 
 
@@ -48,7 +43,7 @@ def test_matcher_matches_cv2_golden(ctx, golden_dir, name, algo):
 
 
 @pytest.mark.parametrize("algo", ALGOS)
-@pytest.mark.parametrize("nq,nt,dim", [(1000, 1000, 64), (777, 1301, 64), (130, 4097, 64), (2048, 300, 128), (5000, 3000, 64)])
+@pytest.mark.parametrize("nq,nt,dim", [(1000, 1000, 64), (777, 1301, 64), (130, 4097, 64), (2048, 300, 128), (5000, 3000, 64), (3000, 4100, 128)])
 def test_matcher_matches_oracle(ctx, nq, nt, dim, algo):
     A, B, _ = synth.make_descriptors(nq, nt, dim, seed=nq + nt)
     _check(_match(ctx, A, B, 0.3, algo, want_knn=True), A, B)
@@ -162,6 +157,23 @@ def test_matcher_full_size_properties(ctx):
     rows = np.random.default_rng(0).choice(16384, 256, replace=False)
     idx, dist = oracle.knn2_l2(A[rows], B)
     assert np.array_equal(ms.knn_idx[rows], idx) and np.array_equal(ms.knn_dist[rows].view(np.uint32), dist.view(np.uint32))
+
+
+def test_matcher_128d_tensor_path(ctx):
+    """128-d descriptors on the tensor path (feature_matcher.cpp:13 -- SURF's extended mode): 16 384 x 16 384 against the exact
+    SIMT kernel (full kNN tables, bit for bit) and a row sample against the oracle; AUTO must pick the tensor path."""
+    A, B, truth = synth.make_descriptors(16384, 16384, 128, seed=11)
+    B[200:230] = B[199]                                     # exact ties -> fallback rows
+    ma = ctx.match_two_image(A, B, 0.3, algo=MATCH_AUTO, want_knn=True)
+    st = ctx.match_stats()
+    assert st.algo_used == MATCH_TENSOR and 0.0 <= st.max_rel_err < ERR_BOUND[MATCH_TENSOR_FP16]
+    ms = ctx.match_two_image(A, B, 0.3, algo=MATCH_SIMT_EXACT, want_knn=True)
+    assert np.array_equal(ma.knn_idx, ms.knn_idx) and np.array_equal(ma.knn_dist.view(np.uint32), ms.knn_dist.view(np.uint32))
+    assert np.array_equal(ma.query_idx, ms.query_idx) and np.array_equal(ma.train_idx, ms.train_idx) and len(ma) > 4000
+    rows = np.random.default_rng(1).choice(16384, 128, replace=False)
+    idx, dist = oracle.knn2_l2(A[rows], B)
+    assert np.array_equal(ma.knn_idx[rows], idx) and np.array_equal(ma.knn_dist[rows].view(np.uint32), dist.view(np.uint32))
+    print("128-d: fallback rows", st.n_fallback_rows, "max_rel_err", st.max_rel_err)
 
 
 @pytest.mark.timeout(900)
