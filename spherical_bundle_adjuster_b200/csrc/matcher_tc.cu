@@ -50,7 +50,7 @@ constexpr int CHUNK = 8;           // columns per candidate chunk
 constexpr int NCAND = 4;           // candidate chunks kept per list
 constexpr int STAGES = 4;          // B smem ring
 constexpr int EPI_WARPS = 16;      // 4 TMEM lane quarters x 4 column slices
-constexpr int SUBSLOTS = 2;        // candidate lists per query row per CTA span (one per epilogue warp group = tile parity)
+constexpr int SUBSLOTS = 2;        // candidate lists per query row per CTA span (2 column slices per row-half)
 constexpr int EPI_WARP0 = 3;      // first epilogue warp
 constexpr int THREADS = (EPI_WARP0 + EPI_WARPS) * 32;   // warp0 TMA, warps 1-2 MMA issuers (even / odd tiles), warps 3-18 epilogue: 608 threads -> 104 registers each
 constexpr int A_KBLOCK_BYTES = BM * 128;   // one 64-wide 16-bit k-block of A: 32 KB
@@ -68,7 +68,7 @@ template <int P> struct Scheme {
     static constexpr int SMEM_A = KBLOCKS * A_KBLOCK_BYTES;
     static constexpr int B_STAGE_BYTES = KBLOCKS * B_KBLOCK_BYTES;
     static constexpr int SMEM_B = STAGES * B_STAGE_BYTES;
-    static constexpr int SMEM_NB = EPI_WARPS * BN * 4;                     // |b|^2 of each epilogue warp's 128 columns
+    static constexpr int SMEM_NB = EPI_WARPS * 64 * 4;                     // |b|^2 of each epilogue warp's columns
     static constexpr int SMEM_BYTES = SMEM_A + SMEM_B + SMEM_NB + 256 /*barriers: 20 x 8 B + the TMEM slot*/ + 1024 /*alignment slack*/;
 };
 constexpr int ACC_COLS = 2 * BN;   // TMEM columns per accumulator stage: row-half 0 | row-half 1
@@ -76,13 +76,13 @@ constexpr uint32_t TMEM_COLS = 512;
 constexpr float DELTA_COEF = 4e-5f;  // bf16 x 3: |approx - exact| <= DELTA_COEF * (|a|^2 + max|b|^2): derivation at tc_rerank_kernel
 constexpr float DELTA_COEF_FP16 = 1.05e-3f;  // fp16 x 1 (64-d and 128-d): same place
 // Candidate keys (epilogue): a chunk minimum with the chunk's id in the low mantissa bits, so that ONE fp32 min / max
-// moves value and id together.  9 bits: [8] = "old" flag, [7:4] own tile inside the current 16-tile window, [3:0] chunk of
-// the tile's 128 columns -- or, for entries that survived a window change, flag | list slot (the absolute chunk id of
+// moves value and id together.  9 bits: [8] = "old" flag, [7:3] tile inside the current 32-tile window, [2:0] chunk of
+// the thread's 64 columns -- or, for entries that survived a window change, flag | list slot (the absolute chunk id of
 // such an entry sits in a side register).  Truncating 9 mantissa bits moves a value by < 2^-14 of its magnitude.
 constexpr uint32_t KEY_ID_MASK = 0x1FFu;
 constexpr uint32_t KEY_OLD = 0x100u;
 constexpr uint32_t KEY_CHUNK_MASK = 0x7u;      // the chunk bits alone (set first; window bits are added to the winners only)
-constexpr int KEY_WINDOW = 16;                 // own tiles (every other tile of the span) per id window
+constexpr int KEY_WINDOW = 32;                 // tiles per id window
 constexpr uint32_t KEY_BIG = 0x7f7fffffu;      // FLT_MAX: an insert of this value is a no-op
 constexpr uint32_t KEY_EMPTY = 0x7f000000u;    // value of an empty list entry (1.7e38, finite: keys must never be NaN)
 constexpr float KEY_TRUNC_REL = 3.0f / 16384.0f;   // bound test margin for the truncation + id bits, relative to |B| (see tc_rerank_kernel)
@@ -343,7 +343,7 @@ __device__ __forceinline__ void key_flush(float (&k)[NCAND], int (&abs_id)[NCAND
         old = sl == 1u ? abs_id[1] : old;
         old = sl == 2u ? abs_id[2] : old;
         old = sl == 3u ? abs_id[3] : old;
-        const int fresh = chunk_base + (int)((idf >> 4) & 15u) * (2 * (BN / CHUNK)) + (int)(idf & 15u);   // own tiles are two tiles apart
+        const int fresh = chunk_base + (int)((idf >> 3) & 31u) * (BN / CHUNK) + (int)(idf & 7u);
         na[i] = (idf & KEY_OLD) ? old : fresh;
         k[i] = __uint_as_float((kb & ~KEY_ID_MASK) | KEY_OLD | (uint32_t)i);
     }
@@ -401,7 +401,7 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         mbar_init(a_full, 1);
         mbar_init(a_empty, 2);   // one arrival per MMA issuer warp
         for (int s = 0; s < STAGES; s++) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
-        for (int s = 0; s < 4; s++) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, EPI_WARPS / 4); }   // 4 warps (lane quarters) read a (stage, half)
+        for (int s = 0; s < 4; s++) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, EPI_WARPS / 2); }
         mbar_init(turn + 0, 1);
         mbar_init(turn + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -537,17 +537,14 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             __syncwarp();
         }
     } else if (warp >= EPI_WARP0) {
-        // ===== epilogue warps: TMEM lane quarter = warp % 4 (hardware rule); e >> 3 = row-half; (e >> 2) & 1 = which tiles =====
-        // A warp owns 32 query rows of one row-half and takes ALL 128 columns of every OTHER tile of the span (two passes of
-        // 64 columns), so the per-tile bookkeeping -- barrier wait, norm staging, addresses, window / publish checks -- is paid
-        // once per 128 columns, each warp has two tile times per tile, and the two groups run out of phase on every scheduler.
-        const int e = warp - EPI_WARP0;
+        // ===== epilogue warps: TMEM lane quarter = warp % 4 (hardware rule), column slice = (warp - EPI_WARP0) / 4 =====
         const int quarter = warp & 3;
-        const int grp = (e >> 2) & 1;                 // tile parity served = accumulator stage
-        const int half = e >> 3;                      // which M=128 row-half
+        const int slice = (warp - EPI_WARP0) >> 2;    // 0..3: 64 accumulator columns each
+        const int half = slice >> 1;                  // which M=128 row-half those columns belong to
+        const int csub = slice & 1;                   // which 64 train columns of the tile
         const int row = half * 128 + quarter * 32 + lane;   // row inside the 256-row query block
-        float* wnb = sNB + e * BN;                    // this warp's |b|^2 staging, 128 columns (warp-synchronous)
-        const float* nb_col = nb + lane;
+        float* wnb = sNB + (warp - EPI_WARP0) * 64;   // this warp's |b|^2 staging (warp-synchronous)
+        const float* nb_col = nb + csub * 64 + lane;
         float key[NCAND];
         int abs_id[NCAND];
         key_reset(key, abs_id);
@@ -556,111 +553,99 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 #pragma unroll
         for (int c = 0; c < 8; c++) creg[c] = (uint32_t)c + (blockDim.y - 1u);   // blockDim.y == 1: a zero the compiler cannot see
         int qb = qb0, tb = tb0;
-        int tw = 0;                                   // own tile inside the current id window
-        int chunk_base = 0;                           // absolute id of chunk 0 of the window's first own tile (set at that tile)
-        float nbv[4];
-        {
-            const int tb_first = (tb0 + grp < ntb) ? tb0 + grp : tb0 + grp - ntb;   // this warp's first tile (if the span has one)
-#pragma unroll
-            for (int k = 0; k < 4; k++) nbv[k] = (grp < n_tiles) ? __ldg(nb_col + (size_t)tb_first * BN + 32 * k) : 0.f;
-        }
+        int tw = 0;                                   // tile inside the current id window
+        int chunk_base = tb0 * (BN / CHUNK) + csub * 8;   // absolute id of the window's first chunk for this column half
+        float nb0 = __ldg(nb_col + (size_t)tb * BN), nb1 = __ldg(nb_col + (size_t)tb * BN + 32);
         for (int n = 0; n < n_tiles; n++) {
+            const int acc = n & 1;
+            __syncwarp();                             // every lane is done reading the previous tile's values
+            wnb[lane] = nb0;
+            wnb[lane + 32] = nb1;
+            __syncwarp();
             const int tb_next = (tb + 1 == ntb) ? 0 : tb + 1;
-            if ((n & 1) == grp) {
-                if (tw == 0) chunk_base = tb * (BN / CHUNK);
-                __syncwarp();                             // every lane is done reading the previous tile's values
-#pragma unroll
-                for (int k = 0; k < 4; k++) wnb[lane + 32 * k] = nbv[k];
-                __syncwarp();
-                if (n + 2 < n_tiles) {                    // prefetch the norms of this warp's next tile behind this tile's math
-                    const int tb2 = (tb + 2 < ntb) ? tb + 2 : tb + 2 - ntb;
-#pragma unroll
-                    for (int k = 0; k < 4; k++) nbv[k] = __ldg(nb_col + (size_t)tb2 * BN + 32 * k);
-                }
-                mbar_wait(acc_full + 2 * grp + half, (uint32_t)((n >> 1) & 1));
-                tcgen05_fence_after();
-                if (warp == EPI_WARP0 && lane == 0 && n == 0) TC_TRACE(4);             // first accumulator ready
-                if (e == 4 * ((n_tiles - 1) & 1) && lane == 0 && n == n_tiles - 1) TC_TRACE(5);   // last accumulator ready
-#pragma unroll
-                for (int pass = 0; pass < 2; pass++) {
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(grp * ACC_COLS + half * BN + pass * 64);
-                    uint32_t buf[64];
+            if (n + 1 < n_tiles) {                    // prefetch the next tile's norms behind this tile's math
+                nb0 = __ldg(nb_col + (size_t)tb_next * BN);
+                nb1 = __ldg(nb_col + (size_t)tb_next * BN + 32);
+            }
+            mbar_wait(acc_full + 2 * acc + half, (uint32_t)((n >> 1) & 1));
+            tcgen05_fence_after();
+            if (warp == EPI_WARP0 && lane == 0 && n == 0) TC_TRACE(4);             // first accumulator ready
+            if (warp == EPI_WARP0 && lane == 0 && n == n_tiles - 1) TC_TRACE(5);   // last accumulator ready
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS + slice * 64);
+            uint32_t buf[64];
 #ifdef SBA_TC_EXP_NOLDTM   // experiment (trace builds): the accumulators are never read -- WRONG results, timing probe
 #pragma unroll
-                    for (int i = 0; i < 64; i++) buf[i] = taddr + i;
+            for (int i = 0; i < 64; i++) buf[i] = taddr + i;
 #else
-                    TMEM_LD_X32(buf, taddr);
-                    TMEM_LD_X32((buf + 32), taddr + 32);
-                    tmem_ld_wait();
+            TMEM_LD_X32(buf, taddr);
+            TMEM_LD_X32((buf + 32), taddr + 32);
+            tmem_ld_wait();
 #endif
-                    if (pass == 1) {   // release the accumulator as soon as all 128 columns sit in registers
-                        tcgen05_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(acc_empty + 2 * grp + half);
-                    }
+            // release the accumulator stage as soon as its values sit in registers
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + 2 * acc + half);
 #ifdef SBA_TC_EXP_NOEPI   // experiment (trace builds): accumulators are read and dropped -- WRONG results, timing probe
-                    if (buf[0] == 0x12345678u && buf[63] == 0x9abcdef0u) key[0] = 0.f;
+            if (buf[0] == 0x12345678u && buf[63] == 0x9abcdef0u) key[0] = 0.f;
 #else
-                    // eight chunk keys: minimum of 8 columns of |b|^2 - 2 a.b, chunk number in the three lowest mantissa bits
-                    float ck[8];
+            // eight chunk keys: minimum of 8 columns of |b|^2 - 2 a.b, chunk number in the three lowest mantissa bits
+            float ck[8];
 #pragma unroll
-                    for (int c = 0; c < 8; c++) {
-                        const float4 na4 = *reinterpret_cast<const float4*>(wnb + pass * 64 + c * 8);
-                        const float4 nb4 = *reinterpret_cast<const float4*>(wnb + pass * 64 + c * 8 + 4);
-                        float v0, v1, v2, v3, v4, v5, v6, v7;   // packed fp32 FMAs, same rounding as eight fmaf
-                        ffma2(v0, v1, buf[c * 8 + 0], buf[c * 8 + 1], na4.x, na4.y);
-                        ffma2(v2, v3, buf[c * 8 + 2], buf[c * 8 + 3], na4.z, na4.w);
-                        ffma2(v4, v5, buf[c * 8 + 4], buf[c * 8 + 5], nb4.x, nb4.y);
-                        ffma2(v6, v7, buf[c * 8 + 6], buf[c * 8 + 7], nb4.z, nb4.w);
-                        const float m = fminf(fminf(fminf(fminf(v0, v1), v2), fminf(fminf(v3, v4), v5)), fminf(v6, v7));
-                        ck[c] = __uint_as_float((__float_as_uint(m) & ~KEY_CHUNK_MASK) | creg[c]);
-                    }
-                    // smallest (gk) and second smallest (m2) of the eight chunk keys: 18 min/max
-                    const float lo0 = fminf(ck[0], ck[1]), hi0 = fmaxf(ck[0], ck[1]);
-                    const float lo1 = fminf(ck[2], ck[3]), hi1 = fmaxf(ck[2], ck[3]);
-                    const float lo2 = fminf(ck[4], ck[5]), hi2 = fmaxf(ck[4], ck[5]);
-                    const float lo3 = fminf(ck[6], ck[7]), hi3 = fmaxf(ck[6], ck[7]);
-                    const float l01 = fminf(lo0, lo1), h01 = fmaxf(lo0, lo1);
-                    const float l23 = fminf(lo2, lo3), h23 = fmaxf(lo2, lo3);
-                    const float gk = fminf(l01, l23);
-                    // window bits go onto the winners only: key = value bits above the id field | own-tile-in-window | pass | chunk
-                    const uint32_t idb = ((uint32_t)tw << 4) | ((uint32_t)pass << 3);   // warp-uniform
-                    const uint32_t keep = ~KEY_ID_MASK | KEY_CHUNK_MASK;
-                    const float gkf = __uint_as_float((__float_as_uint(gk) & keep) | idb);
-                    // Common case: at most the best chunk of the 64 columns enters the list (one 7-instruction chain for the whole
-                    // warp).  If for SOME lane a second chunk also beats its fourth-best key, both go in and the third smallest is
-                    // looked at; only when that one qualifies too -- always while a list is still filling, rarely afterwards --
-                    // do all eight keys run through the chain.
-                    if (__any_sync(0xffffffffu, gkf < key[3])) {
-                        key_insert(key, gkf);
-                        const float m2 = fminf(fminf(fminf(fmaxf(l01, l23), h01), h23), fminf(fminf(hi0, hi1), fminf(hi2, hi3)));
-                        const float m2f = __uint_as_float((__float_as_uint(m2) & keep) | idb);
-                        if (__any_sync(0xffffffffu, m2f < key[3])) {
-                            key_insert(key, m2f);
-                            float m3 = __uint_as_float(KEY_BIG);
+            for (int c = 0; c < 8; c++) {
+                const float4 na4 = *reinterpret_cast<const float4*>(wnb + c * 8);
+                const float4 nb4 = *reinterpret_cast<const float4*>(wnb + c * 8 + 4);
+                float v0, v1, v2, v3, v4, v5, v6, v7;   // packed fp32 FMAs, same rounding as eight fmaf
+                ffma2(v0, v1, buf[c * 8 + 0], buf[c * 8 + 1], na4.x, na4.y);
+                ffma2(v2, v3, buf[c * 8 + 2], buf[c * 8 + 3], na4.z, na4.w);
+                ffma2(v4, v5, buf[c * 8 + 4], buf[c * 8 + 5], nb4.x, nb4.y);
+                ffma2(v6, v7, buf[c * 8 + 6], buf[c * 8 + 7], nb4.z, nb4.w);
+                const float m = fminf(fminf(fminf(fminf(v0, v1), v2), fminf(fminf(v3, v4), v5)), fminf(v6, v7));
+                ck[c] = __uint_as_float((__float_as_uint(m) & ~KEY_CHUNK_MASK) | creg[c]);
+            }
+            // smallest (gk) and second smallest (m2) of the eight chunk keys: 18 min/max
+            const float lo0 = fminf(ck[0], ck[1]), hi0 = fmaxf(ck[0], ck[1]);
+            const float lo1 = fminf(ck[2], ck[3]), hi1 = fmaxf(ck[2], ck[3]);
+            const float lo2 = fminf(ck[4], ck[5]), hi2 = fmaxf(ck[4], ck[5]);
+            const float lo3 = fminf(ck[6], ck[7]), hi3 = fmaxf(ck[6], ck[7]);
+            const float l01 = fminf(lo0, lo1), h01 = fmaxf(lo0, lo1);
+            const float l23 = fminf(lo2, lo3), h23 = fmaxf(lo2, lo3);
+            const float gk = fminf(l01, l23);
+            // window bits go onto the winners only: key = value bits above the id field | tile-in-window | chunk
+            const uint32_t idb = (uint32_t)tw << 3;                        // warp-uniform
+            const uint32_t keep = ~KEY_ID_MASK | KEY_CHUNK_MASK;
+            const float gkf = __uint_as_float((__float_as_uint(gk) & keep) | idb);
+            // Common case: at most the tile's best chunk enters the list (one 7-instruction chain for the whole warp).
+            // If for SOME lane a second chunk also beats its fourth-best key, both go in and the third smallest is
+            // looked at; only when that one qualifies too -- always while a list is still filling, rarely afterwards --
+            // do all eight keys run through the chain.
+            if (__any_sync(0xffffffffu, gkf < key[3])) {
+                key_insert(key, gkf);
+                const float m2 = fminf(fminf(fminf(fmaxf(l01, l23), h01), h23), fminf(fminf(hi0, hi1), fminf(hi2, hi3)));
+                const float m2f = __uint_as_float((__float_as_uint(m2) & keep) | idb);
+                if (__any_sync(0xffffffffu, m2f < key[3])) {
+                    key_insert(key, m2f);
+                    float m3 = __uint_as_float(KEY_BIG);
 #pragma unroll
-                            for (int c = 0; c < 8; c++) m3 = fminf(m3, ck[c] > m2 ? ck[c] : __uint_as_float(KEY_BIG));
-                            const float m3f = __uint_as_float((__float_as_uint(m3) & keep) | idb);
-                            if (__any_sync(0xffffffffu, m3f < key[3])) {
+                    for (int c = 0; c < 8; c++) m3 = fminf(m3, ck[c] > m2 ? ck[c] : __uint_as_float(KEY_BIG));
+                    const float m3f = __uint_as_float((__float_as_uint(m3) & keep) | idb);
+                    if (__any_sync(0xffffffffu, m3f < key[3])) {
 #pragma unroll
-                                for (int c = 0; c < 8; c++) {
-                                    const float x = __uint_as_float((__float_as_uint(ck[c]) & keep) | idb);
-                                    key_insert(key, ck[c] > m2 ? x : __uint_as_float(KEY_BIG));
-                                }
-                            }
+                        for (int c = 0; c < 8; c++) {
+                            const float x = __uint_as_float((__float_as_uint(ck[c]) & keep) | idb);
+                            key_insert(key, ck[c] > m2 ? x : __uint_as_float(KEY_BIG));
                         }
                     }
-#endif
                 }
-                tw++;
             }
+#endif
             const bool block_end = (tb_next == 0 || n + 1 == n_tiles);   // last tile of this query block in the span
-            if (tw == KEY_WINDOW || block_end) {
+            if (++tw == KEY_WINDOW || block_end) {
                 key_flush(key, abs_id, chunk_base);
                 tw = 0;
+                chunk_base = tb_next * (BN / CHUNK) + csub * 8;
             }
-            if (block_end) {   // publish (an empty list when this warp had no tile in the block)
-                const int slot = ((int)blockIdx.x - part.cta_of((long long)qb * ntb)) * SUBSLOTS + grp;
+            if (block_end) {   // publish
+                const int slot = ((int)blockIdx.x - part.cta_of((long long)qb * ntb)) * SUBSLOTS + csub;
                 const size_t o = ((size_t)qb * BM + row) * slots + slot;
                 float pv[NCAND];
 #pragma unroll
