@@ -958,15 +958,19 @@ __global__ void __launch_bounds__(PAIR_SOLVE_THREADS) ba_pair_solve_kernel(PairS
     const double t0 = P.k.t[0], t1 = P.k.t[1], t2 = P.k.t[2];
     int gen_ = 0;
     PS_TRACE(0);
-    cluster.sync();                // every CTA of the cluster is running: its shared memory may be written remotely from here on
-    if (rank == 0 && tid == 0) {   // the starting rotation's tables: d1 * R into every CTA, derivative tables into A.params
+    // The starting rotation's tables.  Every CTA builds its own copy of d1 * R (thread 0, before its bearing), and a SECOND thread
+    // of CTA 0 writes the derivative tables the first contraction needs -- nothing is broadcast and nobody waits for a single
+    // thread's serial fp64 code here; the bearings below hide it.
+    if (tid == 0) {
+        double r[3] = {A.xc[0], A.xc[1], A.xc[2]}, R[9], dR[3][9];
+        rot_and_derivs(r, R, dR);
+#pragma unroll
+        for (int a = 0; a < 9; a++) s_R[a] = d1 * R[a];
+        s_done = 0;
+    }
+    if (rank == 0 && tid == 32) {
         double r[3] = {A.xc[0], A.xc[1], A.xc[2]};
         write_cam_params(r, d1, A.params);
-        for (unsigned int q = 0; q < nblk; q++) {
-            double* dst = cluster.map_shared_rank(s_R, q);
-            for (int a = 0; a < 9; a++) dst[a] = A.params->Rd[a];
-            *cluster.map_shared_rank(&s_done, q) = 0;
-        }
     }
     // 1. bearings of this thread's matches
     for (int i = rank * PAIR_SOLVE_THREADS + tid; i < n; i += stride) {
@@ -981,7 +985,7 @@ __global__ void __launch_bounds__(PAIR_SOLVE_THREADS) ba_pair_solve_kernel(PairS
         P.b2[i] = make_float4((float)x, (float)y, (float)z, 0.f);
     }
     PS_TRACE(1);
-    cluster.sync();
+    cluster.sync();                // bearings done; every CTA of the cluster is running: shared memory may be written remotely from here on
     PS_TRACE(2);
     // 2. the LM loop: one pass per evaluation
     while (true) {

@@ -710,7 +710,7 @@ constexpr int RR_PER_THREAD = 4;   // up to 16*4 = 64 candidate entries (16 slot
 static_assert(CHUNK == 8 && NCAND == 4, "the re-rank evaluates two chunks of 8 rows per phase with 16 threads");
 
 template <int D>
-__global__ void __launch_bounds__(RR<D>::THREADS, 4)
+__global__ void __launch_bounds__(RR<D>::THREADS, D == 64 ? 6 : 4)   // 37 KB of shared memory per CTA: six fit an SM
 tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, int nt, const float* __restrict__ na,
                  const float* __restrict__ nb_max, Partition part, const float4* __restrict__ cand_v, const int4* __restrict__ cand_id,
                  int slots, Top2* __restrict__ top, int* __restrict__ fb_list, int* __restrict__ fb_count, float* __restrict__ dbg_max_err,
