@@ -740,30 +740,43 @@ tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ 
     const float* ev = reinterpret_cast<const float*>(cand_v + (size_t)r * slots);
     const int* ei = reinterpret_cast<const int*>(cand_id + (size_t)r * slots);
     if (n_ent <= 16 * RR_PER_THREAD) {
+        // Four selection rounds: every thread offers the best of the (<= 4) entries it holds, a width-16 xor butterfly finds the
+        // smallest (value, then position -- the same order the lists' slots have in memory), its owner retires it.
+        // ~150 instructions per thread; counting ranks over all pairs of entries cost ~800.
         float v[RR_PER_THREAD];
-        int id[RR_PER_THREAD], rank[RR_PER_THREAD];
+        int id[RR_PER_THREAD];
 #pragma unroll
         for (int k = 0; k < RR_PER_THREAD; k++) {
             const int pos = e + 16 * k;
             v[k] = pos < n_ent ? ev[pos] : INF;
             id[k] = pos < n_ent ? ei[pos] : -1;
-            rank[k] = 0;
         }
 #pragma unroll
-        for (int k2 = 0; k2 < RR_PER_THREAD; k2++) {
-            if (16 * k2 < n_ent) {   // uniform across the group
-#pragma unroll 4
-                for (int l = 0; l < 16; l++) {
-                    const float ov = __shfl_sync(0xffffffffu, v[k2], l, 16);
-                    const int opos = l + 16 * k2;
+        for (int round = 0; round < NCAND; round++) {
+            float bv = v[0];
+            int bk = 0;
 #pragma unroll
-                    for (int k = 0; k < RR_PER_THREAD; k++) rank[k] += (ov < v[k] || (ov == v[k] && opos < e + 16 * k)) ? 1 : 0;
-                }
+            for (int k = 1; k < RR_PER_THREAD; k++)
+                if (v[k] < bv) { bv = v[k]; bk = k; }            // strict: the lower position wins ties inside a thread
+            int bpos = e + 16 * bk;
+            float wv = bv;
+            int wpos = bpos;
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
+                const int opos = __shfl_xor_sync(0xffffffffu, wpos, o);
+                if (ov < wv || (ov == wv && opos < wpos)) { wv = ov; wpos = opos; }
+            }
+            // every thread of the group now knows the winner; its owner publishes the id and retires the entry
+            if (wpos == bpos && wv < INF) {
+                int wid = id[0];
+#pragma unroll
+                for (int k = 1; k < RR_PER_THREAD; k++) wid = (bk == k) ? id[k] : wid;
+                if (wid >= 0) { win_v[grp][round] = wv; win_id[grp][round] = wid; }
+#pragma unroll
+                for (int k = 0; k < RR_PER_THREAD; k++) v[k] = (bk == k) ? INF : v[k];
             }
         }
-#pragma unroll
-        for (int k = 0; k < RR_PER_THREAD; k++)
-            if (rank[k] < NCAND && id[k] >= 0) { win_v[grp][rank[k]] = v[k]; win_id[grp][rank[k]] = id[k]; }
     } else if (e == 0) {
         Cand c;
         cand_reset(c);
