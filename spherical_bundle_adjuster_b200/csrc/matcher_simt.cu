@@ -165,13 +165,22 @@ __device__ inline int keep_flag(const Top2& r, float ratio)
 __global__ void __launch_bounds__(FIN_THREADS)
 knn2_finalize_kernel(const Top2* __restrict__ top, int nq, float ratio, int32_t* __restrict__ knn_idx, float* __restrict__ knn_dist,
                      int32_t* __restrict__ query_idx, int32_t* __restrict__ train_idx, float* __restrict__ dist, int32_t* __restrict__ n_matches,
-                     unsigned int* __restrict__ counts, unsigned int epoch, const Top2* __restrict__ fb_parts, const int* __restrict__ fb_count,
+                     unsigned int* __restrict__ counts /* [-1] = arrival ticket */, unsigned int epoch, const Top2* __restrict__ fb_parts, const int* __restrict__ fb_count,
                      int fb_grid)
 {
     __shared__ int warp_off[32];
-    __shared__ int s_base;
+    __shared__ int s_base, s_blk;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int i = blockIdx.x * FIN_THREADS + tid;
+    // Logical block number = arrival order (a ticket in the slot BEFORE the counts): a block only ever waits for blocks that are
+    // already running, whatever order the hardware starts them in.  The last ticket resets the counter for the next call.
+    if (tid == 0) {
+        const unsigned int t = atomicAdd(counts - 1, 1u);
+        if (t == gridDim.x - 1) *(counts - 1) = 0u;
+        s_blk = (int)t;
+    }
+    __syncthreads();
+    const int blk = s_blk;
+    const int i = blk * FIN_THREADS + tid;
     Top2 r = top2_empty();
     int keep = 0;
     if (i < nq) {
@@ -209,11 +218,11 @@ knn2_finalize_kernel(const Top2* __restrict__ top, int nq, float ratio, int32_t*
         total = __shfl_sync(0xffffffffu, incl, 31);
         if (lane == 0) {
             __threadfence();
-            ((volatile unsigned int*)counts)[blockIdx.x] = (epoch << FIN_EPOCH_SHIFT) | (unsigned int)total;
+            ((volatile unsigned int*)counts)[blk] = (epoch << FIN_EPOCH_SHIFT) | (unsigned int)total;
         }
         // counts of the CTAs before this one (this warp strides over them)
         int before = 0;
-        for (int b = lane; b < (int)blockIdx.x; b += 32) {
+        for (int b = lane; b < blk; b += 32) {
             unsigned int v2;
             do { v2 = ((volatile unsigned int*)counts)[b]; } while ((v2 >> FIN_EPOCH_SHIFT) != epoch);
             before += (int)(v2 & ((1u << FIN_EPOCH_SHIFT) - 1));
@@ -222,7 +231,7 @@ knn2_finalize_kernel(const Top2* __restrict__ top, int nq, float ratio, int32_t*
         for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
         if (lane == 0) {
             s_base = before;
-            if (blockIdx.x == gridDim.x - 1) *n_matches = before + total;
+            if (blk == (int)gridDim.x - 1) *n_matches = before + total;
         }
     }
     __syncthreads();
@@ -240,14 +249,14 @@ int launch_knn_finish(sba_ctx* c, const Top2* d_top2, int nq, float ratio, int32
     const int nblocks = (nq + FIN_THREADS - 1) / FIN_THREADS;
     // the epoch-tagged count slots live in their own grow-only buffer; a fresh (or regrown) buffer and an epoch wrap start from zeros
     const size_t cap_before = c->scratch[SCR_FIN_COUNTS].cap;
-    SBA_TRY(c->scratch[SCR_FIN_COUNTS].ensure((size_t)nblocks * sizeof(unsigned int), c->stream));
+    SBA_TRY(c->scratch[SCR_FIN_COUNTS].ensure((size_t)(nblocks + 1) * sizeof(unsigned int), c->stream));   // counts + the ticket
     c->fin_epoch = (c->fin_epoch + 1) & ((1u << (32 - FIN_EPOCH_SHIFT)) - 1);
     if (c->scratch[SCR_FIN_COUNTS].cap != cap_before || c->fin_epoch == 0) {
         SBA_CUDA(cudaMemsetAsync(c->scratch[SCR_FIN_COUNTS].p, 0, c->scratch[SCR_FIN_COUNTS].cap, c->stream));
         if (c->fin_epoch == 0) c->fin_epoch = 1;
     }
     knn2_finalize_kernel<<<nblocks, FIN_THREADS, 0, c->stream>>>(d_top2, nq, ratio, d_knn_idx, d_knn_dist, d_query_idx, d_train_idx, d_dist, d_n_matches,
-                                                                c->scratch[SCR_FIN_COUNTS].as<unsigned int>(), c->fin_epoch, d_fb_parts, d_fb_count, fb_grid);
+                                                                c->scratch[SCR_FIN_COUNTS].as<unsigned int>() + 1, c->fin_epoch, d_fb_parts, d_fb_count, fb_grid);
     SBA_LAUNCHED(c);
     SBA_CUDA(cudaGetLastError());
     return SBA_OK;

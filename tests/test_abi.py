@@ -73,3 +73,17 @@ def test_cpp_facade_builds_and_fails_loudly_without_gpu(tmp_path):
     (tmp_path / "im.bin").write_bytes(bytes(8 * 4 * 3))
     r = subprocess.run([demo, str(tmp_path)], capture_output=True, text=True)
     assert r.returncode == 1 and "no CPU fallback" in r.stderr
+
+
+def test_python_constants_mirror_the_header_enums():
+    """_lib.py's algorithm / memory constants are the header's enum values (a silent mismatch would select the wrong kernel)."""
+    import re
+    from spherical_bundle_adjuster_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "sba_b200.h")).read()
+    def enum(name):
+        m = re.search(name + r"\s*=\s*(-?\d+)", hdr)
+        assert m, name
+        return int(m.group(1))
+    assert (_lib.MATCH_AUTO, _lib.MATCH_SIMT_EXACT, _lib.MATCH_TENSOR, _lib.MATCH_TENSOR_FP16) == \
+        (enum("SBA_MATCH_AUTO"), enum("SBA_MATCH_SIMT_EXACT"), enum("SBA_MATCH_TENSOR"), enum("SBA_MATCH_TENSOR_FP16"))
+    assert (_lib.SBA_MEM_HOST, _lib.SBA_MEM_DEVICE) == (enum("SBA_MEM_HOST"), enum("SBA_MEM_DEVICE"))
