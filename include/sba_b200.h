@@ -92,7 +92,9 @@ int sba_equi2cube_face(sba_ctx* ctx, const uint8_t* erp, int w, int h, int cube_
 /* The table-driven gathers (cube strips, spherical_surf bands) exist in two kernels: a direct gather and a tiled one
  * that stages each output tile's source bounding box in shared memory with bulk copies.  Which is faster depends on
  * the table and on the batch size, and is measured once when a plan is built (2 frames; a batch larger than L2).
- * mode 0 = use that choice, 1 = always direct, 2 = tiled wherever the geometry allows it (tests run both).
+ * A third kernel fetches the pixels of each 32 x 64 output tile in SOURCE order (a per-tile sorted form of the table), so
+ * that one load instruction walks along a source row instead of across many.
+ * mode 0 = use that choice, 1 = always direct, 2 = tiled / 3 = source-ordered wherever the geometry allows it (tests run all).
  * sba_remap_plan_info reports what the trials of a cube plan found: tiled_preferred bit 0 = small batches, bit 1 = large;
  * trial_ms = {small direct, small tiled, large direct, large tiled}. */
 int sba_ctx_set_remap_kernel(sba_ctx* ctx, int mode);
@@ -101,6 +103,11 @@ int sba_ctx_set_remap_kernel(sba_ctx* ctx, int mode);
 int sba_ctx_set_matcher_ctas(sba_ctx* ctx, int n_ctas);
 int sba_remap_plan_info(sba_ctx* ctx, int w, int h, int cube_size, int* tiled_available, int* tiled_preferred, int* n_tiles,
                         int* n_fallback_tiles, float trial_ms[4]);
+/* The source-ordered form of a cube plan: available, which kernel (1 direct, 2 tiled, 3 source-ordered) the trials picked
+ * for small (2 frames) and large batches, tile count, tiles whose source span does not fit the entry format (they read
+ * the ordinary table inside the same kernel), trial_ms = {small, large} of the source-ordered kernel. */
+int sba_remap_plan_sorted_info(sba_ctx* ctx, int w, int h, int cube_size, int* available, int* best_small, int* best_large,
+                               int* n_tiles, int* n_fallback_tiles, float trial_ms[2]);
 int sba_equi2cube_lut(sba_ctx* ctx, int w, int h, int cube_size, int32_t* lut_out, int mem);
 
 /* equi2cube_surf::cube2equi_pixel for n keypoints (equi2cube_surf.cpp:19-76).

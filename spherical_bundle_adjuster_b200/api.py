@@ -122,7 +122,7 @@ class Context:
         check(self._lib.sba_ctx_set_matcher_ctas(self._h, int(n_ctas)))
 
     def set_remap_kernel(self, mode: int):
-        """0 = per-plan choice from the timed trial, 1 = direct gather, 2 = tiled gather wherever possible."""
+        """0 = per-plan choice from the timed trial, 1 = direct gather, 2 = tiled / 3 = source-ordered gather wherever possible."""
         check(self._lib.sba_ctx_set_remap_kernel(self._h, int(mode)))
 
     def remap_plan_info(self, w: int, h: int, cube_size: int) -> dict:
@@ -131,7 +131,17 @@ class Context:
         check(self._lib.sba_remap_plan_info(self._h, w, h, cube_size, C.byref(a), C.byref(p), C.byref(n), C.byref(f), C.byref(ms)))
         return dict(tiled_available=bool(a.value), tiled_preferred_small=bool(p.value & 1), tiled_preferred_large=bool(p.value & 2),
                     n_tiles=n.value, n_fallback_tiles=f.value, trial_ms=dict(small_direct=float(ms[0]), small_tiled=float(ms[1]),
-                                                                             large_direct=float(ms[2]), large_tiled=float(ms[3])))
+                                                                             large_direct=float(ms[2]), large_tiled=float(ms[3])),
+                    sorted=self.remap_plan_sorted_info(w, h, cube_size))
+
+    def remap_plan_sorted_info(self, w: int, h: int, cube_size: int) -> dict:
+        """The source-ordered form of a cube plan and which kernel (1 direct, 2 tiled, 3 source-ordered) the trials picked."""
+        a, bs, bl, n, f = (C.c_int32(0) for _ in range(5))
+        ms = (C.c_float * 2)()
+        check(self._lib.sba_remap_plan_sorted_info(self._h, w, h, cube_size, C.byref(a), C.byref(bs), C.byref(bl), C.byref(n), C.byref(f),
+                                                   C.byref(ms)))
+        return dict(available=bool(a.value), best_small=bs.value, best_large=bl.value, n_tiles=n.value, n_fallback_tiles=f.value,
+                    trial_ms=dict(small=float(ms[0]), large=float(ms[1])))
 
     def set_profiling(self, enable: bool):
         check(self._lib.sba_ctx_set_profiling(self._h, int(enable)))

@@ -130,7 +130,14 @@ struct TiledPlan {
     // set by timed trials at plan construction: does the tiled kernel beat the direct gather for this table -- on a couple
     // of frames (sources stay in L2) and on a batch that streams from HBM (8 frames)?  [0] = small, [1] = large batches
     bool preferred[2] = {false, false};
-    float trial_ms[2][2] = {{0.f, 0.f}, {0.f, 0.f}};   // [batch class][direct, tiled]
+    float trial_ms[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};   // [batch class][direct, tiled, source-ordered]
+    // Third form (remap_gather_sorted_kernel): per 32 x 64 output tile its pixels listed in SOURCE order, one 32-bit entry
+    // each = (source pixel - tile base) << 11 | position inside the tile.
+    uint32_t* sorted = nullptr;      // device, s_tiles x 2048 entries
+    int32_t* sorted_base = nullptr;  // device, per tile: smallest source pixel index; < 0: offsets do not fit, gather from the table
+    int s_tiles_x = 0, s_tiles_y = 0;
+    int s_fallback = 0;
+    int best[2] = {1, 1};            // fastest kernel per batch class from the trials: 1 direct, 2 tiled, 3 source-ordered
 };
 
 struct RemapPlan {
@@ -180,7 +187,7 @@ struct sba_ctx {
     const int* fb_count = nullptr;
     int fb_grid = 0;
     int matcher_ctas = 0;       // persistent CTAs of the tensor-core matcher; 0 = one per SM (sba_ctx_set_matcher_ctas)
-    int remap_kernel = 0;       // 0 = per-plan choice from the timed trial, 1 = direct gather, 2 = tiled gather (sba_ctx_set_remap_kernel)
+    int remap_kernel = 0;       // 0 = per-plan choice from the timed trial, 1 = direct gather, 2 = tiled, 3 = source-ordered (sba_ctx_set_remap_kernel)
     bool pair_pending = false;  // a sba_pair_rotation_begin whose _end has not run yet (pipeline.cu)
     int* pinned_i32 = nullptr;  // small pinned host mailbox (64 ints) for scalar read-backs
     bool profiling = false;

@@ -244,6 +244,17 @@ __device__ __forceinline__ void prep_row(const float* __restrict__ x, int n, int
     }
 }
 
+#ifdef SBA_TC_TRACE
+// Debug build only: [0] = last thread of tc_prep_kernel to finish, [1] = first thread of tc_rerank_kernel to start (globaltimer, ns)
+__device__ unsigned long long g_tc_edge[2];
+__device__ __forceinline__ unsigned long long gtime_early()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
+
 // Both descriptor sets in one launch: rows [0, nq_pad) are queries, the rest train rows.
 // out*: bf16 hi|lo rows (P = 3) or NULL; out16*: fp16 rows (P = 1) or NULL.  na_max / nb_max: largest squared norms.
 template <int D>
@@ -256,6 +267,9 @@ __global__ void tc_prep_kernel(const float* __restrict__ q, int nq, int nq_pad, 
     const int row = gid / (D / 4), part = gid % (D / 4);   // D/4 threads per row, 4 floats each; a row never straddles two warps or the two sets
     if (row < nq_pad) prep_row<D>(q, nq, row, part, outA, na, 0.f, na_max, out16A);
     else if (row < nq_pad + nt_pad) prep_row<D>(t, nt, row - nq_pad, part, outB, nb, PAD_NORM, nb_max, out16B);
+#ifdef SBA_TC_TRACE
+    if (threadIdx.x == 0) atomicMax(&g_tc_edge[0], gtime_early());
+#endif
 }
 
 // ---- 2. the tensor-core kernel ---------------------------------------------------------------------------
@@ -726,6 +740,9 @@ tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ 
     const bool active = row < nq;
     const int r = active ? row : nq - 1;
     const float INF = __int_as_float(0x7f800000);
+#ifdef SBA_TC_TRACE
+    if (threadIdx.x == 0) atomicMin(&g_tc_edge[1], gtime_early());
+#endif
 
     // query rows of this CTA -> shared (coalesced 128-bit loads: 8 rows x 16 float4)
 #pragma unroll
@@ -1134,5 +1151,14 @@ int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, 
 extern "C" int sba_tc_trace_read(unsigned long long* out /* [148 x 16] */)
 {
     return cudaMemcpyFromSymbol(out, sba::tc::g_tc_trace, sizeof(unsigned long long) * 148 * 16) == cudaSuccess ? 0 : -1;
+}
+// edges[2]: end of the prep kernel, start of the re-rank kernel (ns); reset = 1 re-arms the min/max cells before a call
+extern "C" int sba_tc_trace_edges(unsigned long long* edges, int reset)
+{
+    if (reset) {
+        const unsigned long long init[2] = {0ull, ~0ull};
+        return cudaMemcpyToSymbol(sba::tc::g_tc_edge, init, sizeof(init)) == cudaSuccess ? 0 : -1;
+    }
+    return cudaMemcpyFromSymbol(edges, sba::tc::g_tc_edge, sizeof(unsigned long long) * 2) == cudaSuccess ? 0 : -1;
 }
 #endif

@@ -66,13 +66,17 @@ static int enqueue_pair(sba_ctx* c, const PairKey& a, const double r0[3], sba_ba
     SBA_TRY(stage_in(c, (const float*)a.desc_r, (size_t)n_right * dim, mem, SCR_PIPE_DESC1, &d_desc1));
     SBA_TRY(stage_in(c, (const float*)a.key_l, (size_t)n_left * 2, mem, SCR_PIPE_KEY0, &d_key0));
     SBA_TRY(stage_in(c, (const float*)a.key_r, (size_t)n_right * 2, mem, SCR_PIPE_KEY1, &d_key1));
+    // Device-resident pair: nothing on the device consumes the strips, so the remap runs on the side stream NEXT TO the pair
+    // solve (one 16-SM cluster) instead of in front of the matcher; one pair at a time that hides the solve's 50 us.
+    static const bool no_fork = getenv("SBA_PAIR_NO_FORK") != nullptr;   // measurement switch
+    const bool fork_remap = erp_left && mem == SBA_MEM_DEVICE && !no_fork;
+    if ((overlap || fork_remap) && !c->copy_stream) {
+        SBA_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        SBA_CUDA(cudaEventCreateWithFlags(&c->copy_ev[0], cudaEventDisableTiming));
+        SBA_CUDA(cudaEventCreateWithFlags(&c->copy_ev[1], cudaEventDisableTiming));
+        SBA_CUDA(cudaEventCreateWithFlags(&c->main_ev, cudaEventDisableTiming));
+    }
     if (overlap) {
-        if (!c->copy_stream) {
-            SBA_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-            SBA_CUDA(cudaEventCreateWithFlags(&c->copy_ev[0], cudaEventDisableTiming));
-            SBA_CUDA(cudaEventCreateWithFlags(&c->copy_ev[1], cudaEventDisableTiming));
-            SBA_CUDA(cudaEventCreateWithFlags(&c->main_ev, cudaEventDisableTiming));
-        }
         SBA_TRY(c->scratch[SCR_PIPE_IM0].ensure(im_bytes, st));
         SBA_TRY(c->scratch[SCR_PIPE_IM1].ensure(im_bytes, st));
         // the staging buffers may still be read by work already queued on the compute stream
@@ -105,7 +109,7 @@ static int enqueue_pair(sba_ctx* c, const PairKey& a, const double r0[3], sba_ba
         }
         return SBA_OK;
     };
-    if (!overlap) SBA_TRY(remap_both());
+    if (!overlap && !fork_remap) SBA_TRY(remap_both());
 
     // ---- feature_matcher::match_two_image.  The match list goes straight into the caller's device
     //      buffers when there are any; the count stays on the device until the very end.
@@ -125,6 +129,7 @@ static int enqueue_pair(sba_ctx* c, const PairKey& a, const double r0[3], sba_ba
 
     ps->have_solve = (n_left > 0 && n_right > 0);
     *launched = 0;
+    if (fork_remap) SBA_CUDA(cudaEventRecord(c->main_ev, st));   // the side stream's remap starts once the matcher is through
     if (ps->have_solve) {
         // ---- matched keypoints -> bearings (capacity n_left; the kernel stops at the device-side count)
         SBA_TRY(c->scratch[SCR_PIPE_BEAR].ensure((size_t)2 * n_left * 4 * sizeof(float), st));
@@ -137,6 +142,15 @@ static int enqueue_pair(sba_ctx* c, const PairKey& a, const double r0[3], sba_ba
                                       launched));
     }
     if (overlap) SBA_TRY(remap_both());
+    if (fork_remap) {
+        SBA_CUDA(cudaStreamWaitEvent(c->copy_stream, c->main_ev, 0));
+        c->stream = c->copy_stream;            // remap_both enqueues on the context's current stream
+        const int rc = remap_both();
+        c->stream = st;
+        SBA_TRY(rc);
+        SBA_CUDA(cudaEventRecord(c->copy_ev[0], c->copy_stream));
+        SBA_CUDA(cudaStreamWaitEvent(st, c->copy_ev[0], 0));   // join: whatever follows on the main stream sees the strips
+    }
     SBA_CUDA(cudaGetLastError());
     return SBA_OK;
 }

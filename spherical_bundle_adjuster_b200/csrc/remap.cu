@@ -337,36 +337,201 @@ remap_gather_tiled_kernel(const uint8_t* __restrict__ erp, const int32_t* __rest
     }
 }
 
+// ---- source-ordered variant ---------------------------------------------------------------------------------
+// What the direct gather pays for is LINES: the 32 pixels of one load instruction lie on a short output-row segment whose
+// sources cross ~6 source rows on the lateral faces and ~18 near the poles (9.9 distinct 128-byte lines per load on
+// average at 4K -> cube 960, and 7.5 more for the straddle load), and every line is a pass through the L1 data pipe.
+// The ORDER in which a tile's pixels are fetched is free, so the plan lists the pixels of each 32 x 64 output tile sorted
+// by SOURCE index: 32 consecutive entries are then a run along one or two source rows (2.5 + 2.4 lines per pixel group
+// instead of 9.9 + 7.5).  An entry is (source pixel - tile base) << 11 | position in the tile, still 4 bytes per pixel.
+// Pixels are scattered into a packed shared-memory image of the tile (byte stores), which leaves as aligned 16-byte
+// row chunks.  Entries with all offset bits set have no source pixel (masked tables, rows past the image) and write 0.
+constexpr int SORT_TH = 32, SORT_TW = 64, SORT_NPX = SORT_TH * SORT_TW, SORT_POS_BITS = 11;
+constexpr uint32_t SORT_REL_NONE = 0x1FFFFFu;
+constexpr int SORT_ROW_B = SORT_TW * 3;            // bytes per tile row
+constexpr int SORT_CHUNKS = SORT_ROW_B / 16;        // 16-byte chunks per tile row
+#ifndef SORT_BATCH
+#define SORT_BATCH 4
+#endif
+#ifndef SORT_CTAS_PER_SM
+#define SORT_CTAS_PER_SM 8
+#endif
+
+__global__ void __launch_bounds__(1024)
+sorted_build_kernel(const int32_t* __restrict__ lut, int rows, int cols, int32_t* __restrict__ bases, uint32_t* __restrict__ entries,
+                    int* __restrict__ n_fallback)
+{
+    __shared__ uint32_t key[SORT_NPX];
+    __shared__ int s_min, s_max;
+    const int tiles_x = cols / SORT_TW;
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    if (threadIdx.x == 0) { s_min = INT_MAX; s_max = -1; }
+    __syncthreads();
+    int idx[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int pl = k * 1024 + threadIdx.x, ly = pl / SORT_TW, lx = pl - ly * SORT_TW;
+        const int y = ty * SORT_TH + ly;
+        idx[k] = (y < rows) ? __ldg(lut + (int64_t)y * cols + tx * SORT_TW + lx) : -1;
+        if (idx[k] >= 0) { atomicMin(&s_min, idx[k]); atomicMax(&s_max, idx[k]); }
+    }
+    __syncthreads();
+    const int base = (s_max < 0) ? 0 : s_min;
+    const bool fits = (s_max < 0) || (uint32_t)(s_max - base) < SORT_REL_NONE;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int pl = k * 1024 + threadIdx.x;
+        const uint32_t rel = (idx[k] >= 0 && fits) ? (uint32_t)(idx[k] - base) : SORT_REL_NONE;
+        key[pl] = (rel << SORT_POS_BITS) | (uint32_t)pl;
+    }
+    __syncthreads();
+    // bitonic sort of the 2048 keys (position bits make them distinct)
+    for (int k = 2; k <= SORT_NPX; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const int t = threadIdx.x;
+            const int i = 2 * t - (t & (j - 1));       // the lower index of the pair this thread owns
+            const int p = i + j;
+            const uint32_t a = key[i], b = key[p];
+            const bool up = (i & k) == 0;
+            if ((a > b) == up) { key[i] = b; key[p] = a; }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) {
+        bases[blockIdx.x] = fits ? base : -1;
+        if (!fits) atomicAdd(n_fallback, 1);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; k++) entries[(int64_t)blockIdx.x * SORT_NPX + k * 1024 + threadIdx.x] = key[k * 1024 + threadIdx.x];
+}
+
+// (A variant that scattered one 32-bit word per pixel and packed rows afterwards, as the direct kernel does, halved the
+// shared-memory wavefronts but measured slower: 0.256 / 0.229 ms against 0.204 ms for 16 frames.)
+__device__ __forceinline__ void sorted_put(uint8_t* tb, uint32_t pos, uint32_t w0, uint32_t w1, uint32_t sh, bool none)
+{
+    uint32_t v = __funnelshift_r(w0, w1, sh);
+    if (none) v = 0u;
+    uint8_t* d = tb + pos * 3;
+    d[0] = (uint8_t)v; d[1] = (uint8_t)(v >> 8); d[2] = (uint8_t)(v >> 16);
+}
+
+__global__ void __launch_bounds__(256, SORT_CTAS_PER_SM)
+remap_gather_sorted_kernel(const uint8_t* __restrict__ erp, const int32_t* __restrict__ lut, const uint32_t* __restrict__ entries,
+                           const int32_t* __restrict__ bases, uint8_t* __restrict__ out, int64_t src_bytes_per_image, int rows, int cols,
+                           int tiles_x, int tiles_per_image, int n_images, const uint8_t* __restrict__ erp2 = nullptr,
+                           uint8_t* __restrict__ out2 = nullptr, int n_first = 0)
+{
+    __shared__ __align__(16) uint8_t tile[2][SORT_TH * SORT_ROW_B];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int total = tiles_per_image * n_images;
+    const int last_word = (int)(src_bytes_per_image / 4 - 1);
+    const int64_t P = (int64_t)rows * cols;
+    int buf = 0;
+    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        int img = item / tiles_per_image;
+        const int t = item - img * tiles_per_image;
+        const int ty = t / tiles_x, tx = t - ty * tiles_x;
+        const bool second = erp2 != nullptr && img >= n_first;
+        if (second) img -= n_first;
+        const uint32_t* words = reinterpret_cast<const uint32_t*>((second ? erp2 : erp) + (int64_t)img * src_bytes_per_image);
+        const int base = __ldg(bases + t);
+        uint8_t* tb = tile[buf];
+        if (base >= 0) {
+            const uint32_t* ent = entries + (int64_t)t * SORT_NPX + wib * (SORT_NPX / 8) + lane;
+#pragma unroll 1
+            for (int part = 0; part < 8 / SORT_BATCH; part++) {      // SORT_BATCH rounds of 32 pixels with all their loads in flight together
+                uint32_t e[SORT_BATCH], w0[SORT_BATCH], w1[SORT_BATCH];
+#pragma unroll
+                for (int k = 0; k < SORT_BATCH; k++) e[k] = __ldg(ent + (part * SORT_BATCH + k) * 32);
+#pragma unroll
+                for (int k = 0; k < SORT_BATCH; k++) {
+                    const uint32_t rel = e[k] >> SORT_POS_BITS;
+                    const int a = (rel == SORT_REL_NONE ? 0 : base + (int)rel) * 3;     // < 2^31: checked when the plan is built
+                    const int wi = a >> 2;
+                    w0[k] = __ldg(words + wi);
+                    w1[k] = (a & 2) ? __ldg(words + min(wi + 1, last_word)) : 0u;       // byte offset 2 or 3: the pixel straddles two words
+                }
+#pragma unroll
+                for (int k = 0; k < SORT_BATCH; k++) {
+                    const uint32_t rel = e[k] >> SORT_POS_BITS;
+                    const uint32_t sh = ((rel == SORT_REL_NONE ? 0u : (uint32_t)(base + (int)rel) * 3u) & 3u) * 8u;
+                    sorted_put(tb, e[k] & (SORT_NPX - 1), w0[k], w1[k], sh, rel == SORT_REL_NONE);
+                }
+            }
+        } else {   // offsets do not fit the entry format: this tile reads the ordinary table in output order
+#pragma unroll 1
+            for (int k = 0; k < 8; k++) {
+                const uint32_t pos = (uint32_t)(wib * (SORT_NPX / 8) + k * 32 + lane);
+                const int ly = pos / SORT_TW, lx = pos - ly * SORT_TW;
+                const int y = ty * SORT_TH + ly;
+                const int src = (y < rows) ? __ldg(lut + (int64_t)y * cols + tx * SORT_TW + lx) : -1;
+                const int a = (src < 0 ? 0 : src) * 3;
+                const int wi = a >> 2;
+                const uint32_t w0 = __ldg(words + wi);
+                const uint32_t w1 = (a & 2) ? __ldg(words + min(wi + 1, last_word)) : 0u;
+                sorted_put(tb, pos, w0, w1, (uint32_t)(a & 3) * 8u, src < 0);
+            }
+        }
+        __syncthreads();
+        uint8_t* dst0 = (second ? out2 : out) + ((int64_t)img * P + (int64_t)ty * SORT_TH * cols + (int64_t)tx * SORT_TW) * 3;
+        for (int ch = threadIdx.x; ch < SORT_TH * SORT_CHUNKS; ch += 256) {
+            const int r = ch / SORT_CHUNKS, cc = ch - r * SORT_CHUNKS;
+            if (ty * SORT_TH + r < rows)
+                *reinterpret_cast<uint4*>(dst0 + (int64_t)r * cols * 3 + cc * 16) = *reinterpret_cast<const uint4*>(tb + r * SORT_ROW_B + cc * 16);
+        }
+        buf ^= 1;   // the next tile is scattered into the other buffer; the barrier above orders the one after that
+    }
+}
+
 void free_tiled_plan(TiledPlan* tp)
 {
     if (tp->tiles) cudaFree(tp->tiles);
     if (tp->rel) cudaFree(tp->rel);
+    if (tp->sorted) cudaFree(tp->sorted);
+    if (tp->sorted_base) cudaFree(tp->sorted_base);
     *tp = TiledPlan();
 }
 
 int build_tiled_plan(sba_ctx* c, const int32_t* lut, int rows, int cols, int w, int h, bool masked, TiledPlan* out)
 {
     *out = TiledPlan();
-    // geometry the tiled kernel can take: whole 128-pixel tile columns, 16-byte aligned source rows, offsets within 31 bits
-    if (cols % TILE_W != 0 || (w * 3) % 16 != 0 || (int64_t)w * h * 3 >= ((int64_t)1 << 31)) return SBA_OK;
+    if ((int64_t)w * h * 3 >= ((int64_t)1 << 31)) return SBA_OK;   // both forms keep source byte offsets in 31 bits
     TiledPlan tp;
-    tp.tiles_x = cols / TILE_W;
-    tp.tiles_y = (rows + TILE_H - 1) / TILE_H;
-    const int n_tiles = tp.tiles_x * tp.tiles_y;
-    SBA_CUDA(cudaMalloc(&tp.tiles, (size_t)n_tiles * sizeof(TileBox)));
-    SBA_CUDA(cudaMalloc(&tp.rel, (size_t)rows * cols * sizeof(uint32_t)));
-    SBA_TRY(c->scratch[SCR_WORK1].ensure(sizeof(int), c->stream));
+    SBA_TRY(c->scratch[SCR_WORK1].ensure(2 * sizeof(int), c->stream));
     int* d_cnt = c->scratch[SCR_WORK1].as<int>();
-    SBA_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int), c->stream));
-    tile_build_kernel<<<n_tiles, 256, 0, c->stream>>>(lut, rows, cols, w, tp.tiles, tp.rel, d_cnt);
-    SBA_LAUNCHED(c);
+    SBA_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int), c->stream));
+    // tiled form: whole 128-pixel tile columns, 16-byte aligned source rows
+    if (cols % TILE_W == 0 && (w * 3) % 16 == 0) {
+        tp.tiles_x = cols / TILE_W;
+        tp.tiles_y = (rows + TILE_H - 1) / TILE_H;
+        const int n_tiles = tp.tiles_x * tp.tiles_y;
+        SBA_CUDA(cudaMalloc(&tp.tiles, (size_t)n_tiles * sizeof(TileBox)));
+        SBA_CUDA(cudaMalloc(&tp.rel, (size_t)rows * cols * sizeof(uint32_t)));
+        tile_build_kernel<<<n_tiles, 256, 0, c->stream>>>(lut, rows, cols, w, tp.tiles, tp.rel, d_cnt);
+        SBA_LAUNCHED(c);
+    }
+    // source-ordered form: whole 64-pixel tile columns
+    if (cols % SORT_TW == 0) {
+        tp.s_tiles_x = cols / SORT_TW;
+        tp.s_tiles_y = (rows + SORT_TH - 1) / SORT_TH;
+        const int n_tiles = tp.s_tiles_x * tp.s_tiles_y;
+        SBA_CUDA(cudaMalloc(&tp.sorted, (size_t)n_tiles * SORT_NPX * sizeof(uint32_t)));
+        SBA_CUDA(cudaMalloc(&tp.sorted_base, (size_t)n_tiles * sizeof(int32_t)));
+        sorted_build_kernel<<<n_tiles, 1024, 0, c->stream>>>(lut, rows, cols, tp.sorted_base, tp.sorted, d_cnt + 1);
+        SBA_LAUNCHED(c);
+    }
     SBA_CUDA(cudaGetLastError());
-    SBA_CUDA(cudaMemcpyAsync(&tp.n_fallback, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    int cnt[2];
+    SBA_CUDA(cudaMemcpyAsync(cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
     SBA_CUDA(cudaStreamSynchronize(c->stream));
+    tp.n_fallback = cnt[0];
+    tp.s_fallback = cnt[1];
+    if (!tp.tiles && !tp.sorted) { *out = tp; return SBA_OK; }
 
-    // Which kernel is faster depends on the table (how many source rows a tile's box spans decides how many bulk
-    // copies it takes) and on whether the sources stream from HBM or sit in L2, so both kernels are timed once per
-    // plan on scratch frames: 2 frames (the per-pair calls) and a batch larger than L2.
+    // Which kernel is fastest depends on the table (how many source rows a tile's box spans decides how many bulk
+    // copies the tiled kernel takes, how long the source runs of a tile are decides what source order buys) and on
+    // whether the sources stream from HBM or sit in L2, so the kernels are timed once per plan on scratch frames:
+    // 2 frames (the per-pair calls) and a batch larger than L2.
     const size_t src_bytes = (size_t)w * h * 3, out_bytes = (size_t)rows * cols * 3;
     const int big = (int)std::min<size_t>(8, std::max<size_t>(3, ((size_t)160 << 20) / src_bytes + 1));
     SBA_TRY(c->scratch[SCR_WORK3].ensure(big * src_bytes, c->stream));
@@ -379,8 +544,9 @@ int build_tiled_plan(sba_ctx* c, const int32_t* lut, int rows, int cols, int w, 
     int rc = SBA_OK;
     for (int cls = 0; cls < 2 && rc == SBA_OK; cls++) {
         const int frames = cls == 0 ? 2 : big;
-        for (int variant = 0; variant < 2 && rc == SBA_OK; variant++) {
-            c->remap_kernel = variant == 0 ? 1 : 2;
+        for (int variant = 0; variant < 3 && rc == SBA_OK; variant++) {
+            if ((variant == 1 && !tp.tiles) || (variant == 2 && !tp.sorted)) { tp.trial_ms[cls][variant] = 0.f; continue; }
+            c->remap_kernel = variant + 1;
             float best = 1e30f;
             for (int rep = 0; rep < 4 && rc == SBA_OK; rep++) {
                 cudaEventRecord(e0, c->stream);
@@ -394,7 +560,12 @@ int build_tiled_plan(sba_ctx* c, const int32_t* lut, int rows, int cols, int w, 
             }
             tp.trial_ms[cls][variant] = best;
         }
-        tp.preferred[cls] = tp.trial_ms[cls][1] < 0.95f * tp.trial_ms[cls][0];
+        // a challenger has to win by 5 % to displace the direct gather
+        tp.best[cls] = 1;
+        float best_ms = 0.95f * tp.trial_ms[cls][0];
+        for (int variant = 1; variant < 3; variant++)
+            if (tp.trial_ms[cls][variant] > 0.f && tp.trial_ms[cls][variant] < best_ms) { best_ms = tp.trial_ms[cls][variant]; tp.best[cls] = variant + 1; }
+        tp.preferred[cls] = tp.best[cls] == 2;
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
@@ -466,21 +637,18 @@ int launch_lut_gather(sba_ctx* c, const uint8_t* d_erp, int64_t src_bytes, const
                       bool masked, const TiledPlan* tiled, int src_w)
 {
     const int64_t P = (int64_t)rows * cols;
-    const bool want_tiled = tiled && tiled->tiles && (c->remap_kernel == 2 || (c->remap_kernel == 0 && tiled->preferred[n_images >= 3 ? 1 : 0]));
-    if (want_tiled && (uintptr_t)d_erp % 16 == 0 && src_bytes % 16 == 0 && (uintptr_t)d_out % 16 == 0 &&
-        (P * 3) % 16 == 0 && (int64_t)tiled->tiles_x * tiled->tiles_y * n_images < ((int64_t)1 << 31)) {
-        const int per_image = tiled->tiles_x * tiled->tiles_y, total = per_image * n_images;
-        const int blocks = std::min(total, c->sm_count * 6);
-        if (masked)
-            remap_gather_tiled_kernel<true><<<blocks, 256, 0, c->stream>>>(d_erp, lut, tiled->rel, tiled->tiles, d_out, src_bytes, src_w * 3, rows,
-                                                                            cols, tiled->tiles_x, per_image, n_images);
-        else
-            remap_gather_tiled_kernel<false><<<blocks, 256, 0, c->stream>>>(d_erp, lut, tiled->rel, tiled->tiles, d_out, src_bytes, src_w * 3, rows,
-                                                                             cols, tiled->tiles_x, per_image, n_images);
+    const int choice = c->remap_kernel != 0 ? c->remap_kernel : (tiled ? tiled->best[n_images >= 3 ? 1 : 0] : 1);
+    if (choice == 3 && tiled && tiled->sorted && (uintptr_t)d_erp % 4 == 0 && src_bytes % 4 == 0 && (uintptr_t)d_out % 16 == 0 &&
+        ((P * 3) % 16 == 0 || n_images == 1) && (int64_t)tiled->s_tiles_x * tiled->s_tiles_y * n_images < ((int64_t)1 << 31)) {
+        const int per_image = tiled->s_tiles_x * tiled->s_tiles_y, total = per_image * n_images;
+        const int blocks = std::min(total, c->sm_count * SORT_CTAS_PER_SM);
+        remap_gather_sorted_kernel<<<blocks, 256, 0, c->stream>>>(d_erp, lut, tiled->sorted, tiled->sorted_base, d_out, src_bytes, rows, cols,
+                                                                  tiled->s_tiles_x, per_image, n_images);
         SBA_LAUNCHED(c);
         SBA_CUDA(cudaGetLastError());
         return SBA_OK;
     }
+    const bool want_tiled = tiled && tiled->tiles && choice == 2;
     const bool fast_ok = ((uintptr_t)d_erp % 4 == 0) && (src_bytes % 4 == 0) && ((uintptr_t)d_out % 16 == 0) && ((uintptr_t)lut % 16 == 0) &&
                          ((P * 3) % 16 == 0 || n_images == 1) && P >= 128;
     int64_t done_px = 0;
@@ -520,8 +688,20 @@ int equi2cube_pair(sba_ctx* c, const uint8_t* d_im0, const uint8_t* d_im1, int w
     const int64_t P = (int64_t)cs * 6 * cs, src_bytes = (int64_t)w * h * 3;
     auto ok4 = [](const void* p) { return (uintptr_t)p % 4 == 0; };
     auto ok16 = [](const void* p) { return (uintptr_t)p % 16 == 0; };
-    const bool tiled_wins = c->remap_kernel == 2 || (c->remap_kernel == 0 && plan->tiled.tiles && plan->tiled.preferred[0]);
-    if (!tiled_wins && ok4(d_im0) && ok4(d_im1) && src_bytes % 4 == 0 && ok16(d_s0) && ok16(d_s1) && ok16(plan->lut) && P % 128 == 0 &&
+    const int choice = c->remap_kernel != 0 ? c->remap_kernel : plan->tiled.best[0];
+    if (choice == 3 && plan->tiled.sorted && ok4(d_im0) && ok4(d_im1) && src_bytes % 4 == 0 && ok16(d_s0) && ok16(d_s1)) {
+        const TiledPlan& tp = plan->tiled;
+        const int per_image = tp.s_tiles_x * tp.s_tiles_y;
+        const int blocks = std::min(per_image * 2, c->sm_count * SORT_CTAS_PER_SM);
+        prof_begin(c, SBA_KERNEL_REMAP);
+        remap_gather_sorted_kernel<<<blocks, 256, 0, c->stream>>>(d_im0, plan->lut, tp.sorted, tp.sorted_base, d_s0, src_bytes, cs, 6 * cs, tp.s_tiles_x,
+                                                                  per_image, 2, d_im1, d_s1, 1);
+        prof_end(c, SBA_KERNEL_REMAP);
+        SBA_LAUNCHED(c);
+        SBA_CUDA(cudaGetLastError());
+        return SBA_OK;
+    }
+    if (choice != 2 && ok4(d_im0) && ok4(d_im1) && src_bytes % 4 == 0 && ok16(d_s0) && ok16(d_s1) && ok16(plan->lut) && P % 128 == 0 &&
         P / 128 < ((int64_t)1 << 29)) {
         const int groups = (int)(P / 128);
         int blocks = (int)std::min<int64_t>(ceil_div64((int64_t)groups * 2, 8), (int64_t)c->sm_count * 8);
@@ -563,7 +743,7 @@ extern "C" {
 
 int sba_ctx_set_remap_kernel(sba_ctx* c, int mode)
 {
-    SBA_CHECK_ARG(c && mode >= 0 && mode <= 2);
+    SBA_CHECK_ARG(c && mode >= 0 && mode <= 3);
     c->remap_kernel = mode;
     return SBA_OK;
 }
@@ -581,6 +761,23 @@ int sba_remap_plan_info(sba_ctx* c, int w, int h, int cs, int* tiled_available, 
     if (n_tiles) *n_tiles = tp.tiles_x * tp.tiles_y;
     if (n_fallback_tiles) *n_fallback_tiles = tp.n_fallback;
     if (trial_ms) for (int k = 0; k < 4; k++) trial_ms[k] = tp.trial_ms[k >> 1][k & 1];
+    return SBA_OK;
+}
+
+int sba_remap_plan_sorted_info(sba_ctx* c, int w, int h, int cs, int* available, int* best_small, int* best_large, int* n_tiles,
+                               int* n_fallback_tiles, float trial_ms[2])
+{
+    SBA_CHECK_ARG(c && w > 0 && h > 0 && cs > 0);
+    SBA_CUDA(cudaSetDevice(c->device));
+    RemapPlan* plan;
+    SBA_TRY(get_plan(c, w, h, cs, &plan));
+    const TiledPlan& tp = plan->tiled;
+    if (available) *available = tp.sorted != nullptr;
+    if (best_small) *best_small = tp.best[0];
+    if (best_large) *best_large = tp.best[1];
+    if (n_tiles) *n_tiles = tp.s_tiles_x * tp.s_tiles_y;
+    if (n_fallback_tiles) *n_fallback_tiles = tp.s_fallback;
+    if (trial_ms) { trial_ms[0] = tp.trial_ms[0][2]; trial_ms[1] = tp.trial_ms[1][2]; }
     return SBA_OK;
 }
 

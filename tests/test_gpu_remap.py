@@ -83,18 +83,42 @@ def test_pixels_to_bearings(ctx):
     assert ctx.pixels_to_bearings(np.zeros((0, 2), np.float32), 64, 32).shape == (0, 4)   # empty input
 
 
-@pytest.mark.parametrize("mode", [1, 2])
-def test_both_gather_kernels_give_the_same_strips(ctx, mode):
-    """Direct and tiled (bulk-copy staged) gather, forced in turn: bit-identical strips on a geometry with
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_all_gather_kernels_give_the_same_strips(ctx, mode):
+    """Direct, tiled (bulk-copy staged) and source-ordered gather, forced in turn: bit-identical strips on a geometry with
     fallback tiles (poles of the top and bottom faces) and a batch of frames."""
     w, h, cs = 2048, 1024, 512
     ims = np.stack([synth.make_erp_image(w, h, seed=s) for s in range(3)])
     want = np.stack([oracle.equi2cube_all(im, cs) for im in ims])
     info = ctx.remap_plan_info(w, h, cs)
     assert info["tiled_available"] and 0 < info["n_fallback_tiles"] < info["n_tiles"]
+    assert info["sorted"]["available"] and info["sorted"]["n_fallback_tiles"] == 0
     ctx.set_remap_kernel(mode)
     try:
         assert np.array_equal(ctx.equi2cube(ims, cs), want)
         assert np.array_equal(ctx.equi2cube(ims[1], cs), want[1])
+    finally:
+        ctx.set_remap_kernel(0)
+
+
+def test_source_ordered_gather_odd_geometries(ctx):
+    """Source-ordered gather: a strip width that is no multiple of the 64-pixel tile (cube 80: the form is not built and the
+    direct gather runs), a small cube, and the tile-local fallback -- 64-pixel faces over an 8K source make a tile's source
+    span exceed the 21-bit offsets of an entry."""
+    for (w, h, cs) in [(512, 256, 80), (640, 320, 192)]:
+        im = synth.make_erp_image(w, h, seed=3)
+        ctx.set_remap_kernel(3)
+        try:
+            assert ctx.remap_plan_info(w, h, cs)["sorted"]["available"] == ((6 * cs) % 64 == 0)
+            assert np.array_equal(ctx.equi2cube(im, cs), oracle.equi2cube_all(im, cs))
+        finally:
+            ctx.set_remap_kernel(0)
+    w, h, cs = 8192, 4096, 64          # 64-pixel faces over an 8K source: every tile spans hundreds of source rows
+    im = synth.make_erp_image(w, h, seed=5)
+    ctx.set_remap_kernel(3)
+    try:
+        info = ctx.remap_plan_info(w, h, cs)["sorted"]
+        assert info["available"] and info["n_fallback_tiles"] > 0
+        assert np.array_equal(ctx.equi2cube(im, cs), oracle.equi2cube_all(im, cs))
     finally:
         ctx.set_remap_kernel(0)

@@ -53,11 +53,11 @@ def test_crop_batched_and_device_mode(ctx):
     assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), want)
 
 
-@pytest.mark.parametrize("w,h", [(1024, 512), (3840, 1920), (1000, 500), (258, 130)])
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("w,h", [(1024, 512), (3840, 1920), (1000, 500), (258, 130), (1024, 520)])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_four_bands_in_one_gather(ctx, w, h, mode):
     im = synth.make_erp_image(w, h, seed=7)
-    ctx.set_remap_kernel(mode)          # per-plan choice, direct gather, tiled gather (where the geometry allows it)
+    ctx.set_remap_kernel(mode)          # per-plan choice, direct, tiled, source-ordered gather (where the geometry allows it)
     try:
         _check_bands(ctx, im, w, h)
     finally:
