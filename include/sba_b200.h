@@ -101,6 +101,12 @@ int sba_ctx_set_remap_kernel(sba_ctx* ctx, int mode);
 /* Persistent CTAs of the tensor-core matcher (one per SM by default; 0 restores that).  With several pairs in flight on
  * one GPU, half the SMs per match lets two matches run side by side on longer spans. */
 int sba_ctx_set_matcher_ctas(sba_ctx* ctx, int n_ctas);
+/* Programmatic dependent launch along the kernel chain of a match / a pair (prep -> distance kernel -> re-rank -> fallback ->
+ * finalize -> pair solve): each kernel is scheduled while its predecessor drains and waits on the device before touching
+ * memory.  A latency knob: one C2 pair at a time 254 -> 240 us on B200, but several pairs in flight on one GPU lose ~3 % of
+ * their throughput (waiting CTAs keep other pairs' kernels off their SMs), so it is off by default (env SBA_PDL=1 turns it
+ * on for every new context).  Results are identical either way. */
+int sba_ctx_set_dependent_launch(sba_ctx* ctx, int enable);
 int sba_remap_plan_info(sba_ctx* ctx, int w, int h, int cube_size, int* tiled_available, int* tiled_preferred, int* n_tiles,
                         int* n_fallback_tiles, float trial_ms[4]);
 /* The source-ordered form of a cube plan: available, which kernel (1 direct, 2 tiled, 3 source-ordered) the trials picked

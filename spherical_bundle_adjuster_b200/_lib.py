@@ -24,7 +24,7 @@ EXPORTED = [
     "sba_ba_problem_set_comm", "sba_ba_d_eval", "sba_ba_d_solve", "sba_ba_solve_problem",
     "sba_eular2rot", "sba_crop_rotated_lut", "sba_crop_rotated_image", "sba_spherical_crops", "sba_rotate_pixels", "sba_rotate_pixels_mat", "sba_rotate_keypoints",
     "sba_pair_rotation_begin", "sba_pair_rotation_end", "sba_eight_point_null", "sba_essential_to_candidates", "sba_initial_guess",
-    "sba_ctx_set_remap_kernel", "sba_remap_plan_info", "sba_remap_plan_sorted_info", "sba_ctx_set_matcher_ctas",
+    "sba_ctx_set_remap_kernel", "sba_remap_plan_info", "sba_remap_plan_sorted_info", "sba_ctx_set_matcher_ctas", "sba_ctx_set_dependent_launch",
     "sba_descriptors_create", "sba_descriptors_destroy", "sba_descriptors_count", "sba_knn2_ratio_prepared",
 ]
 
@@ -112,6 +112,7 @@ def load():
     lib.sba_descriptors_count.argtypes = [vp]
     lib.sba_knn2_ratio_prepared.argtypes = [vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, i32, i32]
     lib.sba_ctx_set_remap_kernel.argtypes = [vp, i32]
+    lib.sba_ctx_set_dependent_launch.argtypes = [vp, i32]
     lib.sba_ctx_set_matcher_ctas.argtypes = [vp, i32]
     lib.sba_remap_plan_info.argtypes = [vp, i32, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(f32 * 4)]
     lib.sba_remap_plan_sorted_info.argtypes = [vp, i32, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(f32 * 2)]

@@ -121,6 +121,11 @@ class Context:
         """Persistent CTAs of the tensor-core matcher (0 = one per SM)."""
         check(self._lib.sba_ctx_set_matcher_ctas(self._h, int(n_ctas)))
 
+    def set_dependent_launch(self, enable: bool):
+        """Programmatic dependent launch along the kernel chain of a match / a pair: lower one-pair latency, ~3 % less throughput with
+        several pairs in flight (default off)."""
+        check(self._lib.sba_ctx_set_dependent_launch(self._h, int(bool(enable))))
+
     def set_remap_kernel(self, mode: int):
         """0 = per-plan choice from the timed trial, 1 = direct gather, 2 = tiled / 3 = source-ordered gather wherever possible."""
         check(self._lib.sba_ctx_set_remap_kernel(self._h, int(mode)))

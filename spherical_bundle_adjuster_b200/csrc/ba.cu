@@ -812,6 +812,12 @@ struct PairSolveArgs {
     float4* b1;
     float4* b2;
     SolveConsts k;
+    // starting point and fresh solver state travel as kernel arguments, the result goes straight into the problem's pinned host
+    // mailboxes: no copy nodes on the stream in front of or behind the launch
+    double r0[3];
+    LMState init;
+    LMState* h_state;
+    double* h_x;
 };
 
 // Damped 3x3 solve for the one-thread decision of the fused pair kernel.  Same Cholesky as solve3_spd, but every
@@ -952,6 +958,7 @@ __global__ void __launch_bounds__(PAIR_SOLVE_THREADS) ba_pair_solve_kernel(PairS
     __shared__ double s_R[9];
     __shared__ int s_done;
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    pdl_wait();   // launched as a programmatic dependent of knn2_finalize_kernel: the match list and its count are complete from here
     const int n = min(P.cap, *P.d_n);
     const int stride = nblk * PAIR_SOLVE_THREADS;
     const double d1 = P.k.d1, d2 = P.k.d2, huber = P.k.huber, hub2 = huber * huber;
@@ -962,14 +969,19 @@ __global__ void __launch_bounds__(PAIR_SOLVE_THREADS) ba_pair_solve_kernel(PairS
     // of CTA 0 writes the derivative tables the first contraction needs -- nothing is broadcast and nobody waits for a single
     // thread's serial fp64 code here; the bearings below hide it.
     if (tid == 0) {
-        double r[3] = {A.xc[0], A.xc[1], A.xc[2]}, R[9], dR[3][9];
+        double r[3] = {P.r0[0], P.r0[1], P.r0[2]}, R[9], dR[3][9];
+        if (rank == 0) {   // the solver's device-side state starts here (the decision below is this same thread)
+#pragma unroll
+            for (int a = 0; a < 3; a++) { A.x[a] = r[a]; A.xc[a] = r[a]; }
+            *A.st = P.init;
+        }
         rot_and_derivs(r, R, dR);
 #pragma unroll
         for (int a = 0; a < 9; a++) s_R[a] = d1 * R[a];
         s_done = 0;
     }
     if (rank == 0 && tid == 32) {
-        double r[3] = {A.xc[0], A.xc[1], A.xc[2]};
+        double r[3] = {P.r0[0], P.r0[1], P.r0[2]};
         write_cam_params(r, d1, A.params);
     }
     // 1. bearings of this thread's matches
@@ -1057,6 +1069,14 @@ __global__ void __launch_bounds__(PAIR_SOLVE_THREADS) ba_pair_solve_kernel(PairS
         PS_TRACE(6 + 4 * gen_);
         gen_++;
         if (s_done) break;
+    }
+    if (rank == 0 && tid == 0) {   // result -> pinned host mailboxes (read by ba_solve_finish after its synchronise)
+        static_assert(sizeof(LMState) % 8 == 0, "LMState is copied as 64-bit words");
+#pragma unroll
+        for (int a = 0; a < (int)(sizeof(LMState) / 8); a++) ((unsigned long long*)P.h_state)[a] = ((volatile unsigned long long*)A.st)[a];
+#pragma unroll
+        for (int a = 0; a < 3; a++) P.h_x[a] = ((volatile double*)A.x)[a];
+        __threadfence_system();
     }
 }
 
@@ -1619,10 +1639,11 @@ int ba_pair_solve_enqueue(sba_ba_problem* p, const float* key_l, const float* ke
 {
     sba_ctx* c = p->ctx;
     cudaStream_t st = c->stream;
-    SBA_CUDA(cudaMemcpyAsync(p->x, p->h_x, 3 * sizeof(double), cudaMemcpyHostToDevice, st));
-    SBA_CUDA(cudaMemcpyAsync(p->xc, p->x, 3 * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    SBA_CUDA(cudaMemcpyAsync(p->state, p->h_state, sizeof(LMState), cudaMemcpyHostToDevice, st));
     PairSolveArgs P;
+    for (int k = 0; k < 3; k++) P.r0[k] = p->h_x[k];    // ba_solve_prepare_host put the starting point and the fresh state there
+    P.init = *p->h_state;
+    P.h_state = p->h_state; P.h_x = p->h_x;
+    p->h_state->done = 0;
     P.key_l = (const float2*)key_l; P.key_r = (const float2*)key_r; P.qi = qi; P.ti = ti; P.d_n = d_n;
     P.cap = cap; P.cs = cs; P.w = w; P.h = h; P.b1 = p->b1; P.b2 = p->b2;
     P.k.t[0] = t[0]; P.k.t[1] = t[1]; P.k.t[2] = t[2]; P.k.d1 = d1; P.k.d2 = d2; P.k.huber = huber;
@@ -1645,17 +1666,17 @@ int ba_pair_solve_enqueue(sba_ba_problem* p, const float* key_l, const float* ke
     }
     const int grid = std::max(1, std::min(cluster_size, (cap + PAIR_SOLVE_THREADS - 1) / PAIR_SOLVE_THREADS));   // small pairs: a smaller cluster
     cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)grid; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(PAIR_SOLVE_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(PAIR_SOLVE_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = c->pdl ? 2 : 1;
     prof_begin(c, SBA_KERNEL_BA_EVAL);
     SBA_CUDA(cudaLaunchKernelEx(&cfg, ba_pair_solve_kernel, P, A));
     prof_end(c, SBA_KERNEL_BA_EVAL);
     SBA_LAUNCHED(c);
     SBA_CUDA(cudaGetLastError());
-    SBA_CUDA(cudaMemcpyAsync(p->h_state, p->state, sizeof(LMState), cudaMemcpyDeviceToHost, st));
-    SBA_CUDA(cudaMemcpyAsync(p->h_x, p->x, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
     *launched = max_iter + 1;   // the kernel runs the solve to completion: ba_solve_finish has nothing to add
     return SBA_OK;
 }

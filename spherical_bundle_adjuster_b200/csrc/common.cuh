@@ -4,6 +4,8 @@
 #include <stdint.h>
 
 #include <cstdio>
+#include <cstdlib>
+#include <utility>
 #include <cstring>
 #include <map>
 #include <string>
@@ -187,6 +189,7 @@ struct sba_ctx {
     const int* fb_count = nullptr;
     int fb_grid = 0;
     int matcher_ctas = 0;       // persistent CTAs of the tensor-core matcher; 0 = one per SM (sba_ctx_set_matcher_ctas)
+    bool pdl = false;           // programmatic dependent launch along the pair chain (sba_ctx_set_dependent_launch)
     int remap_kernel = 0;       // 0 = per-plan choice from the timed trial, 1 = direct gather, 2 = tiled, 3 = source-ordered (sba_ctx_set_remap_kernel)
     bool pair_pending = false;  // a sba_pair_rotation_begin whose _end has not run yet (pipeline.cu)
     int* pinned_i32 = nullptr;  // small pinned host mailbox (64 ints) for scalar read-backs
@@ -239,6 +242,33 @@ inline int finish(sba_ctx* c, int mem)
 }
 
 #define SBA_LAUNCHED(ctx) ((ctx)->launches++)
+
+// ---- programmatic dependent launch (the kernels of one pair are a chain on one stream) ----------------------------------
+// A kernel launched with launch_pdl may be scheduled while its predecessor in the stream is still draining (its CTAs take
+// SMs as the predecessor's retire, so the ~4 us between two dependent launches disappears).  Such a kernel calls pdl_wait()
+// before it reads or writes ANY global memory: the call returns when the predecessor grid has completed and its writes are
+// visible -- and since every kernel of the chain waits like that, when all earlier ones have.  pdl_trigger() at the top of a
+// kernel lets the NEXT launch start being scheduled; without the launch attribute both calls are no-ops.
+// Measured on B200 (C2 pair): one pair at a time 254 -> 240 us, but with six pairs in flight 7 706 -> 7 506 pairs/s -- CTAs
+// that sit on an SM waiting for their own chain keep other pairs' kernels off it -- so it is a per-context latency knob
+// (sba_ctx_set_dependent_launch, default off).
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(bool enable, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args)
+{
+    const bool off = !enable;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.attrs = at; cfg.numAttrs = off ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+#endif
 
 // Bracket the dominant kernel of a stage with events when profiling is on.
 inline void prof_begin(sba_ctx* c, int id)

@@ -57,6 +57,7 @@ int sba_ctx_create(int device, void* stream, sba_ctx** out)
         }
         c->own_stream = true;
     }
+    c->pdl = getenv("SBA_PDL") != nullptr;
     e = cudaMallocHost((void**)&c->pinned_i32, 64 * sizeof(int));
     if (e != cudaSuccess) {
         if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -102,6 +103,13 @@ int sba_ctx_set_matcher_ctas(sba_ctx* c, int n_ctas)
 {
     SBA_CHECK_ARG(c && n_ctas >= 0);
     c->matcher_ctas = n_ctas;
+    return SBA_OK;
+}
+
+int sba_ctx_set_dependent_launch(sba_ctx* c, int enable)
+{
+    SBA_CHECK_ARG(c != nullptr);
+    c->pdl = enable != 0;
     return SBA_OK;
 }
 

@@ -166,11 +166,13 @@ __global__ void __launch_bounds__(FIN_THREADS)
 knn2_finalize_kernel(const Top2* __restrict__ top, int nq, float ratio, int32_t* __restrict__ knn_idx, float* __restrict__ knn_dist,
                      int32_t* __restrict__ query_idx, int32_t* __restrict__ train_idx, float* __restrict__ dist, int32_t* __restrict__ n_matches,
                      unsigned int* __restrict__ counts /* [-1] = arrival ticket */, unsigned int epoch, const Top2* __restrict__ fb_parts, const int* __restrict__ fb_count,
-                     int fb_grid)
+                     int fb_grid, int32_t* __restrict__ mail /* the context's pinned host mailbox, written directly: [0] = count, [8..10] = tensor-path counters */)
 {
     __shared__ int warp_off[32];
     __shared__ int s_base, s_blk;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_trigger();
+    pdl_wait();
     // Logical block number = arrival order (a ticket in the slot BEFORE the counts): a block only ever waits for blocks that are
     // already running, whatever order the hardware starts them in.  The last ticket resets the counter for the next call.
     if (tid == 0) {
@@ -231,7 +233,11 @@ knn2_finalize_kernel(const Top2* __restrict__ top, int nq, float ratio, int32_t*
         for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
         if (lane == 0) {
             s_base = before;
-            if (blk == (int)gridDim.x - 1) *n_matches = before + total;
+            if (blk == (int)gridDim.x - 1) {
+                *n_matches = before + total;
+                mail[0] = before + total;      // the host reads the mailbox after its synchronise: no copy node on the stream
+                if (fb_count) { mail[8] = fb_count[0]; mail[9] = fb_count[1]; mail[10] = fb_count[2]; }
+            }
         }
     }
     __syncthreads();
@@ -255,8 +261,9 @@ int launch_knn_finish(sba_ctx* c, const Top2* d_top2, int nq, float ratio, int32
         SBA_CUDA(cudaMemsetAsync(c->scratch[SCR_FIN_COUNTS].p, 0, c->scratch[SCR_FIN_COUNTS].cap, c->stream));
         if (c->fin_epoch == 0) c->fin_epoch = 1;
     }
-    knn2_finalize_kernel<<<nblocks, FIN_THREADS, 0, c->stream>>>(d_top2, nq, ratio, d_knn_idx, d_knn_dist, d_query_idx, d_train_idx, d_dist, d_n_matches,
-                                                                c->scratch[SCR_FIN_COUNTS].as<unsigned int>() + 1, c->fin_epoch, d_fb_parts, d_fb_count, fb_grid);
+    SBA_CUDA(launch_pdl(c->pdl, knn2_finalize_kernel, dim3(nblocks), dim3(FIN_THREADS), 0, c->stream, d_top2, nq, ratio, d_knn_idx, d_knn_dist, d_query_idx, d_train_idx,
+                        d_dist, d_n_matches, c->scratch[SCR_FIN_COUNTS].as<unsigned int>() + 1, c->fin_epoch, d_fb_parts, d_fb_count, fb_grid,
+                        (int32_t*)c->pinned_i32));
     SBA_LAUNCHED(c);
     SBA_CUDA(cudaGetLastError());
     return SBA_OK;
@@ -390,9 +397,8 @@ static int knn2_ratio_impl(sba_ctx* c, const float* q, int nq, const float* t, i
     c->match_stats.algo_used = use;
     SBA_TRY(launch_knn_finish(c, d_top, nq, ratio, d_qi, d_ti, d_d, d_n, d_ki, d_kd, (const Top2*)c->fb_parts, c->fb_count, c->fb_grid));
     if (mem == SBA_MEM_HOST) {
-        SBA_CUDA(cudaMemcpyAsync(c->pinned_i32, d_n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         SBA_CUDA(cudaStreamSynchronize(st));
-        const int n = c->pinned_i32[0];
+        const int n = c->pinned_i32[0];     // written by knn2_finalize_kernel
         *n_matches = n;
         SBA_TRY(copy_out(c, query_idx, d_qi, (size_t)n, mem));
         SBA_TRY(copy_out(c, train_idx, d_ti, (size_t)n, mem));
@@ -474,7 +480,7 @@ int sba_match_last_stats(sba_ctx* c, sba_match_stats* out)
 {
     SBA_CHECK_ARG(c && out);
     if (c->match_stats.n_fallback_rows < 0) {
-        // tensor path: the counters were copied to the pinned mailbox on the stream
+        // tensor path: knn2_finalize_kernel copied the counters into the pinned mailbox
         SBA_CUDA(cudaStreamSynchronize(c->stream));
         c->match_stats.n_fallback_rows = c->pinned_i32[8];
         memcpy(&c->match_stats.max_rel_err, c->pinned_i32 + 10, sizeof(float));

@@ -263,6 +263,7 @@ __global__ void tc_prep_kernel(const float* __restrict__ q, int nq, int nq_pad, 
                                float* __restrict__ nb_max /* running maximum of the finite train norms */, float* __restrict__ na_max,
                                __half* __restrict__ out16A, __half* __restrict__ out16B)
 {
+    pdl_trigger();   // the distance kernel may be scheduled while this one drains (it waits before touching memory)
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     const int row = gid / (D / 4), part = gid % (D / 4);   // D/4 threads per row, 4 floats each; a row never straddles two warps or the two sets
     if (row < nq_pad) prep_row<D>(q, nq, row, part, outA, na, 0.f, na_max, out16A);
@@ -405,6 +406,7 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     uint32_t* tmem_slot = (uint32_t*)(bars + 12 + 2 * STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_trigger();
     if (threadIdx.x == 0) TC_TRACE(0);   // CTA start
     // this CTA's span of tiles, walked with 32-bit incremental (query block, train tile) indices
     const int t_begin = (int)part.start(blockIdx.x), n_tiles = (int)part.start(blockIdx.x + 1) - t_begin;
@@ -428,6 +430,7 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();   // barriers and TMEM are set up; the operands (tc_prep_kernel's output) are touched only from here on
     if (threadIdx.x == 0) TC_TRACE(1);   // set-up done
 
     if (warp == 0) {
@@ -740,6 +743,8 @@ tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ 
     const bool active = row < nq;
     const int r = active ? row : nq - 1;
     const float INF = __int_as_float(0x7f800000);
+    pdl_trigger();
+    pdl_wait();
 #ifdef SBA_TC_TRACE
     if (threadIdx.x == 0) atomicMin(&g_tc_edge[1], gtime_early());
 #endif
@@ -914,6 +919,8 @@ tc_fallback_kernel(const float* __restrict__ q, const float* __restrict__ t, int
     constexpr int DIM = D;
     __shared__ float qs[FB_ROWS][DIM];
     __shared__ float ts[FB_CHUNK][FB_PITCH];
+    pdl_trigger();
+    pdl_wait();
     const int n = *fb_count;
     if (n == 0) return;
     const int S = fb_splits(n, gridDim.x);
@@ -1109,13 +1116,13 @@ int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, 
     prof_begin(c, SBA_KERNEL_MATCH);
     if (mode == 1) {
         SBA_CUDA(cudaFuncSetAttribute(tc_knn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Scheme<1>::SMEM_BYTES));
-        tc_knn_kernel<1><<<part.n_ctas, THREADS, Scheme<1>::SMEM_BYTES, st>>>(map_a, map_b, d_nb, part, d_cv, d_ci, slots);
+        SBA_CUDA(launch_pdl(c->pdl, tc_knn_kernel<1>, dim3(part.n_ctas), dim3(THREADS), Scheme<1>::SMEM_BYTES, st, map_a, map_b, d_nb, part, d_cv, d_ci, slots));
     } else if (mode == 2) {
         SBA_CUDA(cudaFuncSetAttribute(tc_knn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Scheme<2>::SMEM_BYTES));
-        tc_knn_kernel<2><<<part.n_ctas, THREADS, Scheme<2>::SMEM_BYTES, st>>>(map_a, map_b, d_nb, part, d_cv, d_ci, slots);
+        SBA_CUDA(launch_pdl(c->pdl, tc_knn_kernel<2>, dim3(part.n_ctas), dim3(THREADS), Scheme<2>::SMEM_BYTES, st, map_a, map_b, d_nb, part, d_cv, d_ci, slots));
     } else {
         SBA_CUDA(cudaFuncSetAttribute(tc_knn_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Scheme<3>::SMEM_BYTES));
-        tc_knn_kernel<3><<<part.n_ctas, THREADS, Scheme<3>::SMEM_BYTES, st>>>(map_a, map_b, d_nb, part, d_cv, d_ci, slots);
+        SBA_CUDA(launch_pdl(c->pdl, tc_knn_kernel<3>, dim3(part.n_ctas), dim3(THREADS), Scheme<3>::SMEM_BYTES, st, map_a, map_b, d_nb, part, d_cv, d_ci, slots));
     }
     prof_end(c, SBA_KERNEL_MATCH);
     SBA_LAUNCHED(c);
@@ -1124,21 +1131,21 @@ int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, 
     const float dcoef = f16 ? DELTA_COEF_FP16 : DELTA_COEF;
     const float* namax = f16 ? d_namax : nullptr;
     if (dim == 64) {
-        tc_rerank_kernel<64><<<(nq + RR<64>::ROWS - 1) / RR<64>::ROWS, RR<64>::THREADS, 0, st>>>(d_q, nq, d_t, nt, d_na, d_nbmax, part, d_cv, d_ci, slots, d_top, d_fl,
-                                                                                               d_fb_count, d_dbg, dcoef, namax);
+        SBA_CUDA(launch_pdl(c->pdl, tc_rerank_kernel<64>, dim3((nq + RR<64>::ROWS - 1) / RR<64>::ROWS), dim3(RR<64>::THREADS), 0, st, d_q, nq, d_t, nt, d_na, d_nbmax, part,
+                            d_cv, d_ci, slots, d_top, d_fl, d_fb_count, d_dbg, dcoef, namax));
         SBA_LAUNCHED(c);
-        tc_fallback_kernel<64><<<fb_grid, FB_THREADS, 0, st>>>(d_q, d_t, nt, d_fl, d_fb_count, d_fparts);
+        SBA_CUDA(launch_pdl(c->pdl, tc_fallback_kernel<64>, dim3(fb_grid), dim3(FB_THREADS), 0, st, d_q, d_t, nt, d_fl, d_fb_count, d_fparts));
     } else {
-        tc_rerank_kernel<128><<<(nq + RR<128>::ROWS - 1) / RR<128>::ROWS, RR<128>::THREADS, 0, st>>>(d_q, nq, d_t, nt, d_na, d_nbmax, part, d_cv, d_ci, slots, d_top,
-                                                                                                   d_fl, d_fb_count, d_dbg, dcoef, namax);
+        SBA_CUDA(launch_pdl(c->pdl, tc_rerank_kernel<128>, dim3((nq + RR<128>::ROWS - 1) / RR<128>::ROWS), dim3(RR<128>::THREADS), 0, st, d_q, nq, d_t, nt, d_na, d_nbmax,
+                            part, d_cv, d_ci, slots, d_top, d_fl, d_fb_count, d_dbg, dcoef, namax));
         SBA_LAUNCHED(c);
-        tc_fallback_kernel<128><<<fb_grid, FB_THREADS, 0, st>>>(d_q, d_t, nt, d_fl, d_fb_count, d_fparts);
+        SBA_CUDA(launch_pdl(c->pdl, tc_fallback_kernel<128>, dim3(fb_grid), dim3(FB_THREADS), 0, st, d_q, d_t, nt, d_fl, d_fb_count, d_fparts));
     }
     SBA_LAUNCHED(c);
     c->fb_parts = d_fparts; c->fb_count = d_fb_count; c->fb_grid = fb_grid;   // merged per row by knn2_finalize_kernel
     SBA_CUDA(cudaGetLastError());
-    // diagnostics land in the pinned mailbox; read by sba_match_last_stats after a synchronise
-    SBA_CUDA(cudaMemcpyAsync(c->pinned_i32 + 8, d_fb_count, 12, cudaMemcpyDeviceToHost, st));
+    // diagnostics (the three words at d_fb_count) reach the pinned mailbox through knn2_finalize_kernel; sba_match_last_stats reads
+    // them after a synchronise
     c->match_stats.n_tiles = (int)part.T;
     c->match_stats.n_ctas = part.n_ctas;
     c->match_stats.n_fallback_rows = -1;  // resolved lazily from the mailbox

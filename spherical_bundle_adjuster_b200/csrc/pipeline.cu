@@ -125,7 +125,7 @@ static int enqueue_pair(sba_ctx* c, const PairKey& a, const double r0[3], sba_ba
     ps->d_dist = (ps->dev_lists && a.dist) ? (float*)a.dist : s_dist;
     SBA_TRY(sba_knn2_ratio(c, d_desc0, n_left, d_desc1, n_right, dim, a.ratio, ps->d_qi, ps->d_ti, ps->d_dist, d_n, nullptr, nullptr, D,
                            SBA_MATCH_AUTO));
-    SBA_CUDA(cudaMemcpyAsync(c->pinned_i32, d_n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));   // read after the final synchronise
+    // the count also lands in the context's pinned mailbox (written by knn2_finalize_kernel), read after the final synchronise
 
     ps->have_solve = (n_left > 0 && n_right > 0);
     *launched = 0;

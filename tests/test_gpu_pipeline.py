@@ -134,36 +134,37 @@ def test_pair_rotation_no_matches_and_no_images(ctx):
     assert np.allclose(res.rotation, (0.1, 0.2, 0.3))                            # initial value returned untouched
 
 
-def test_pair_rotation_graph_replay_matches_eager():
-    """Opt-in CUDA-graph replay (SBA_PAIR_GRAPHS=1): third and later calls with the same buffers replay a
-    captured graph; results must equal the eager path bit for bit, also when the start rotation changes."""
-    import os, subprocess, sys
-    code = r"""
-import numpy as np, torch
-from spherical_bundle_adjuster_b200 import Context, synth
-ctx = Context(0)
-w, h, cs, n = 1024, 512, 256, 3000
-pair = synth.make_pair(n, n, cs=cs, seed=5, rotvec=(0.1, -0.2, 0.3))
-im1, im2 = synth.make_erp_image(w, h, seed=2), synth.make_erp_image(w, h, seed=3)
-args = [torch.from_numpy(a).cuda() for a in (im1, im2, pair['desc1'], pair['desc2'], pair['key1_xy'], pair['key2_xy'])]
-out = []
-for k in range(5):
-    res, (qi, ti, dd), _ = ctx.pair_rotation(*args, cs, r0=(0.01 * (k % 2), 0.0, 0.0), want_matches=True)
-    out.append((tuple(res.rotation), res.n_matches, res.lm_iterations, int(qi.sum().item())))
-print(out)
-"""
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+def test_pair_rotation_dependent_launch_gives_identical_results():
+    """sba_ctx_set_dependent_launch: the pair's kernel chain launched programmatically dependent (each kernel scheduled while
+    its predecessor drains, waiting on the device before it touches memory) -- same match list, same distance bits, same
+    rotation bits as the plain stream-ordered launches, call after call, on device tensors and on host buffers; the match
+    entry point alone as well."""
+    import torch
+    from spherical_bundle_adjuster_b200 import Context
+    c = Context(0)
+    w, h, cs, n = 1024, 512, 256, 3000
+    pair = synth.make_pair(n, n, cs=cs, seed=5, rotvec=(0.1, -0.2, 0.3))
+    im1, im2 = synth.make_erp_image(w, h, seed=2), synth.make_erp_image(w, h, seed=3)
+    host = [im1, im2, pair["desc1"], pair["desc2"], pair["key1_xy"], pair["key2_xy"]]
+    dev = [torch.from_numpy(a).cuda() for a in host]
     runs = {}
-    for flag in ("0", "1"):
-        env = dict(os.environ, PYTHONPATH=root)
-        env.pop("SBA_PAIR_GRAPHS", None)
-        if flag == "1":
-            env["SBA_PAIR_GRAPHS"] = "1"
-        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
-        assert r.returncode == 0, r.stderr[-2000:]
-        runs[flag] = eval(r.stdout.strip().splitlines()[-1])
-    assert runs["0"] == runs["1"]
-    assert runs["0"][0][1] > 1000 and runs["0"][0] == runs["0"][2] and runs["0"][1] == runs["0"][3]
+    for flag in (False, True, False, True):
+        c.set_dependent_launch(flag)
+        out = []
+        for k in range(6):
+            args = dev if k % 2 == 0 else host
+            res, (qi, ti, dd), _ = c.pair_rotation(*args, cs, r0=(0.01 * (k % 3), 0.0, 0.0), want_matches=True)
+            if k % 2 == 0:
+                torch.cuda.synchronize()
+                qi, ti, dd = qi.cpu().numpy(), ti.cpu().numpy(), dd.cpu().numpy()
+            out.append((tuple(res.rotation), res.n_matches, res.lm_iterations, res.lm_termination, qi.tobytes(), ti.tobytes(), dd.tobytes()))
+        m = c.match_two_image(dev[2], dev[3], 0.3)
+        torch.cuda.synchronize()
+        out.append(tuple(x.cpu().numpy().tobytes() for x in (m.query_idx, m.train_idx, m.distance)))
+        runs.setdefault(flag, []).append(out)
+    c.set_dependent_launch(False)
+    assert runs[False][0] == runs[False][1] == runs[True][0] == runs[True][1]
+    assert runs[False][0][0][1] > 1000
 
 
 @pytest.mark.parametrize("kind", ["host", "device"])
