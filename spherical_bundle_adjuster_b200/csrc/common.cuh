@@ -183,6 +183,7 @@ struct sba_ctx {
     std::map<std::tuple<int, int, uint32_t>, sba::CropPlan> crop_plans;   // keyed by (w, h, bits of the pitch)
     std::map<std::pair<int, int>, int32_t*> band_plans;                  // the four bands of spherical_surf::do_all in one table
     std::map<std::pair<int, int>, sba::TiledPlan> band_tiled;             // ... and its tiled form
+    std::map<std::tuple<int, int, int, int>, std::pair<std::vector<int>, int*>> tc_spans;   // tensor matcher: per-geometry query-block -> CTA span tables (matcher_tc.cu)
     sba_match_stats match_stats{};
     unsigned int fin_epoch = 0;   // call counter of knn2_finalize_kernel (tags its count slots)
     const void* fb_parts = nullptr;   // tensor matcher -> finalize: partial top-2 lists of the exact fallback (Top2*), queue length, scan grid

@@ -85,6 +85,7 @@ int sba_ctx_destroy(sba_ctx* c)
         if (kv.second.lut) cudaFree(kv.second.lut);
     for (auto& kv : c->band_plans)
         if (kv.second) cudaFree(kv.second);
+    for (auto& kv : c->tc_spans) cudaFree(kv.second.second);
     if (c->pinned_i32) cudaFreeHost(c->pinned_i32);
     for (int k = 0; k < 3; k++) {
         if (c->prof_e0[k]) cudaEventDestroy(c->prof_e0[k]);

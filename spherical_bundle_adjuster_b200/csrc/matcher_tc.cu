@@ -731,7 +731,7 @@ __global__ void __launch_bounds__(RR<D>::THREADS, D == 64 ? 6 : 4)   // 37 KB of
 tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, int nt, const float* __restrict__ na,
                  const float* __restrict__ nb_max, Partition part, const float4* __restrict__ cand_v, const int4* __restrict__ cand_id,
                  int slots, Top2* __restrict__ top, int* __restrict__ fb_list, int* __restrict__ fb_count, float* __restrict__ dbg_max_err,
-                 float delta_coef, const float* __restrict__ na_max)
+                 float delta_coef, const float* __restrict__ na_max, const int2* __restrict__ qb_span)
 {
     constexpr int RR_ROWS = RR<D>::ROWS, V4 = D / 64;   // V4: float4 pieces of a row per thread of the 16-thread group
     __shared__ __align__(16) float qs[RR_ROWS][D];
@@ -757,7 +757,10 @@ tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ 
 
     // a) merge candidate lists
     const int qb = r / BM;
-    const int c_first = part.cta_of((long long)qb * part.ntb), c_last = part.cta_of((long long)(qb + 1) * part.ntb - 1);
+    // first and last CTA that hold lists of this query block: a per-geometry table built on the host (inverting the partition
+    // here -- two searches over 64-bit divisions per thread -- was a third of this kernel's instructions)
+    const int2 sp = __ldg(qb_span + qb);
+    const int c_first = sp.x, c_last = sp.y;
     const int n_ent = (c_last - c_first + 1) * SUBSLOTS * NCAND;   // entries are (slot, k) pairs, contiguous in memory
     const float* ev = reinterpret_cast<const float*>(cand_v + (size_t)r * slots);
     const int* ei = reinterpret_cast<const int*>(cand_id + (size_t)r * slots);
@@ -1039,6 +1042,33 @@ int knn2_prepare_set(sba_ctx* c, const float* d_raw, int n, int n_pad, __nv_bflo
     return SBA_OK;
 }
 
+// Per query block the first and last CTA whose span holds tiles of it (the re-rank merges exactly those CTAs' lists).  The table
+// depends on the partition only, so it is built on the host once per geometry and cached in the context.
+static int span_table(sba_ctx* c, const tc::Partition& part, const int2** out)
+{
+    const auto key = std::make_tuple(part.nqb, part.ntb, part.n_ctas, part.bcost);
+    auto it = c->tc_spans.find(key);
+    if (it == c->tc_spans.end()) {
+        if (c->tc_spans.size() >= 256) {   // a sweep over many sizes: start over rather than grow without bound
+            SBA_CUDA(cudaStreamSynchronize(c->stream));
+            for (auto& kv : c->tc_spans) cudaFree(kv.second.second);
+            c->tc_spans.clear();
+        }
+        std::vector<int> host((size_t)2 * part.nqb);
+        for (int qb = 0; qb < part.nqb; qb++) {
+            host[2 * qb] = part.cta_of((long long)qb * part.ntb);
+            host[2 * qb + 1] = part.cta_of((long long)(qb + 1) * part.ntb - 1);
+        }
+        int* dev = nullptr;
+        SBA_CUDA(cudaMalloc(&dev, host.size() * sizeof(int)));
+        it = c->tc_spans.emplace(key, std::make_pair(std::move(host), dev)).first;
+        // the host copy lives in the cache entry, so the asynchronous copy may read it whenever it runs
+        SBA_CUDA(cudaMemcpyAsync(dev, it->second.first.data(), it->second.first.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    }
+    *out = reinterpret_cast<const int2*>(it->second.second);
+    return SBA_OK;
+}
+
 // pq / pt: optional prepared forms of the query / train set (64-d only; then that side is not converted again).
 // products: 3 = bf16 split filter, 1 = fp16 filter (see tc::Scheme); 128-d descriptors always take the fp16 filter (mode 2).
 int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, int dim, Top2* d_top, const PreparedSet* pq, const PreparedSet* pt,
@@ -1091,6 +1121,8 @@ int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, 
     int* d_fl = (int*)(ws + o_fl);
     Top2* d_fparts = (Top2*)(ws + o_fp);
     int* d_fb_count = (int*)(ws + o_misc);
+    const int2* d_span = nullptr;
+    SBA_TRY(span_table(c, part, &d_span));
     const float* d_nbmax = pt ? pt->max_norm : (const float*)(ws + o_misc + 4);
     float* d_dbg = (float*)(ws + o_misc + 8);
     const float* d_namax = pq ? pq->max_norm : (const float*)(ws + o_misc + 12);
@@ -1132,12 +1164,12 @@ int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, 
     const float* namax = f16 ? d_namax : nullptr;
     if (dim == 64) {
         SBA_CUDA(launch_pdl(c->pdl, tc_rerank_kernel<64>, dim3((nq + RR<64>::ROWS - 1) / RR<64>::ROWS), dim3(RR<64>::THREADS), 0, st, d_q, nq, d_t, nt, d_na, d_nbmax, part,
-                            d_cv, d_ci, slots, d_top, d_fl, d_fb_count, d_dbg, dcoef, namax));
+                            d_cv, d_ci, slots, d_top, d_fl, d_fb_count, d_dbg, dcoef, namax, d_span));
         SBA_LAUNCHED(c);
         SBA_CUDA(launch_pdl(c->pdl, tc_fallback_kernel<64>, dim3(fb_grid), dim3(FB_THREADS), 0, st, d_q, d_t, nt, d_fl, d_fb_count, d_fparts));
     } else {
         SBA_CUDA(launch_pdl(c->pdl, tc_rerank_kernel<128>, dim3((nq + RR<128>::ROWS - 1) / RR<128>::ROWS), dim3(RR<128>::THREADS), 0, st, d_q, nq, d_t, nt, d_na, d_nbmax,
-                            part, d_cv, d_ci, slots, d_top, d_fl, d_fb_count, d_dbg, dcoef, namax));
+                            part, d_cv, d_ci, slots, d_top, d_fl, d_fb_count, d_dbg, dcoef, namax, d_span));
         SBA_LAUNCHED(c);
         SBA_CUDA(launch_pdl(c->pdl, tc_fallback_kernel<128>, dim3(fb_grid), dim3(FB_THREADS), 0, st, d_q, d_t, nt, d_fl, d_fb_count, d_fparts));
     }
