@@ -210,8 +210,8 @@ struct Partition {
 // ---- 1. prepare ------------------------------------------------------------------------------------------
 // D/4 threads per row, 4 floats each.  Rows >= n are padding: zeros, norm = PAD_NORM (train) so they never win.
 template <int D>
-__device__ __forceinline__ void prep_row(const float* __restrict__ x, int n, int row, int part, __nv_bfloat16* __restrict__ out, float* __restrict__ norm,
-                                         float pad_norm, float* __restrict__ max_norm, __half* __restrict__ out16)
+__device__ __forceinline__ float prep_row(const float* __restrict__ x, int n, int row, int part, __nv_bfloat16* __restrict__ out, float* __restrict__ norm,
+                                          float pad_norm, __half* __restrict__ out16)
 {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (row < n) v = __ldg(reinterpret_cast<const float4*>(x + (size_t)row * D) + part);
@@ -238,10 +238,8 @@ __device__ __forceinline__ void prep_row(const float* __restrict__ x, int n, int
         for (int k = 0; k < 4; k++) h[k] = __float2half_rn(f[k]);
         *reinterpret_cast<uint2*>(out16 + (size_t)row * D + part * 4) = *reinterpret_cast<const uint2*>(h);
     }
-    if (part == 0) {
-        norm[row] = row < n ? s : pad_norm;
-        if (max_norm && row < n) atomicMax((int*)max_norm, __float_as_int(s));   // non-negative floats order like ints
-    }
+    if (part == 0) norm[row] = row < n ? s : pad_norm;
+    return row < n ? s : 0.f;   // for the caller's running maximum (padding rows do not count)
 }
 
 #ifdef SBA_TC_TRACE
@@ -264,10 +262,26 @@ __global__ void tc_prep_kernel(const float* __restrict__ q, int nq, int nq_pad, 
                                __half* __restrict__ out16A, __half* __restrict__ out16B)
 {
     pdl_trigger();   // the distance kernel may be scheduled while this one drains (it waits before touching memory)
+    __shared__ float s_max[2][8];
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     const int row = gid / (D / 4), part = gid % (D / 4);   // D/4 threads per row, 4 floats each; a row never straddles two warps or the two sets
-    if (row < nq_pad) prep_row<D>(q, nq, row, part, outA, na, 0.f, na_max, out16A);
-    else if (row < nq_pad + nt_pad) prep_row<D>(t, nt, row - nq_pad, part, outB, nb, PAD_NORM, nb_max, out16B);
+    float mq = 0.f, mt = 0.f;   // squared norms are non-negative: 0 is the neutral element
+    if (row < nq_pad) mq = prep_row<D>(q, nq, row, part, outA, na, 0.f, out16A);
+    else if (row < nq_pad + nt_pad) mt = prep_row<D>(t, nt, row - nq_pad, part, outB, nb, PAD_NORM, out16B);
+    // running maxima of the norms: one atomic per CTA and set instead of one per row (32 768 same-address atomics serialise in L2)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mq = fmaxf(mq, __shfl_xor_sync(0xffffffffu, mq, o));
+        mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_max[0][threadIdx.x >> 5] = mq; s_max[1][threadIdx.x >> 5] = mt; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        float m = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) m = fmaxf(m, s_max[threadIdx.x][w]);
+        float* dst = threadIdx.x == 0 ? na_max : nb_max;
+        if (dst && m > 0.f) atomicMax((int*)dst, __float_as_int(m));   // non-negative floats order like ints
+    }
 #ifdef SBA_TC_TRACE
     if (threadIdx.x == 0) atomicMax(&g_tc_edge[0], gtime_early());
 #endif
@@ -749,33 +763,36 @@ tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ 
     if (threadIdx.x == 0) atomicMin(&g_tc_edge[1], gtime_early());
 #endif
 
-    // query rows of this CTA -> shared (coalesced 128-bit loads: 8 rows x 16 float4)
-#pragma unroll
-    for (int v = 0; v < V4; v++) reinterpret_cast<float4*>(&qs[grp][0])[e + 16 * v] = __ldg(reinterpret_cast<const float4*>(q + (size_t)r * D) + e + 16 * v);
-    if (e < NCAND) { win_v[grp][e] = INF; win_id[grp][e] = -1; }
-    __syncthreads();
-
-    // a) merge candidate lists
+    // a) merge candidate lists.  Everything this row needs from global memory before the exact phase is requested up front: the
+    //    span of CTAs that hold lists of its query block (a per-geometry table built on the host; inverting the partition here --
+    //    two searches over 64-bit divisions per thread -- was a third of this kernel's instructions), the list entries this thread
+    //    owns, and its piece of the query row.
     const int qb = r / BM;
-    // first and last CTA that hold lists of this query block: a per-geometry table built on the host (inverting the partition
-    // here -- two searches over 64-bit divisions per thread -- was a third of this kernel's instructions)
     const int2 sp = __ldg(qb_span + qb);
     const int c_first = sp.x, c_last = sp.y;
     const int n_ent = (c_last - c_first + 1) * SUBSLOTS * NCAND;   // entries are (slot, k) pairs, contiguous in memory
     const float* ev = reinterpret_cast<const float*>(cand_v + (size_t)r * slots);
     const int* ei = reinterpret_cast<const int*>(cand_id + (size_t)r * slots);
+    float v[RR_PER_THREAD];
+    int id[RR_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < RR_PER_THREAD; k++) {
+        const int pos = e + 16 * k;
+        const bool in = pos < n_ent && n_ent <= 16 * RR_PER_THREAD;
+        v[k] = in ? __ldg(ev + pos) : INF;
+        id[k] = in ? __ldg(ei + pos) : -1;
+    }
+    // query rows of this CTA -> shared (coalesced 128-bit loads: 8 rows x 16 float4); a row is written and read by its own
+    // 16-thread group only, so a warp-level barrier orders it
+#pragma unroll
+    for (int vv = 0; vv < V4; vv++) reinterpret_cast<float4*>(&qs[grp][0])[e + 16 * vv] = __ldg(reinterpret_cast<const float4*>(q + (size_t)r * D) + e + 16 * vv);
+    if (e < NCAND) { win_v[grp][e] = INF; win_id[grp][e] = -1; }
+    __syncwarp();
+
     if (n_ent <= 16 * RR_PER_THREAD) {
         // Four selection rounds: every thread offers the best of the (<= 4) entries it holds, a width-16 xor butterfly finds the
         // smallest (value, then position -- the same order the lists' slots have in memory), its owner retires it.
         // ~150 instructions per thread; counting ranks over all pairs of entries cost ~800.
-        float v[RR_PER_THREAD];
-        int id[RR_PER_THREAD];
-#pragma unroll
-        for (int k = 0; k < RR_PER_THREAD; k++) {
-            const int pos = e + 16 * k;
-            v[k] = pos < n_ent ? ev[pos] : INF;
-            id[k] = pos < n_ent ? ei[pos] : -1;
-        }
 #pragma unroll
         for (int round = 0; round < NCAND; round++) {
             float bv = v[0];
