@@ -1159,18 +1159,28 @@ int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, 
         SBA_LAUNCHED(c);
     }
 
+    static bool smem_attr_done[4][64] = {};
     CUtensorMap map_a, map_b;
     SBA_TRY(make_map(&map_a, (void*)dA, nq_pad, BM, row_bytes / 2));
     SBA_TRY(make_map(&map_b, (void*)dB, nt_pad, BN, row_bytes / 2));
     prof_begin(c, SBA_KERNEL_MATCH);
     if (mode == 1) {
-        SBA_CUDA(cudaFuncSetAttribute(tc_knn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Scheme<1>::SMEM_BYTES));
+        if (!smem_attr_done[1][c->device & 63]) {   // once per device: function attributes are per device
+            SBA_CUDA(cudaFuncSetAttribute(tc_knn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Scheme<1>::SMEM_BYTES));
+            smem_attr_done[1][c->device & 63] = true;
+        }
         SBA_CUDA(launch_pdl(c->pdl, tc_knn_kernel<1>, dim3(part.n_ctas), dim3(THREADS), Scheme<1>::SMEM_BYTES, st, map_a, map_b, d_nb, part, d_cv, d_ci, slots));
     } else if (mode == 2) {
-        SBA_CUDA(cudaFuncSetAttribute(tc_knn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Scheme<2>::SMEM_BYTES));
+        if (!smem_attr_done[2][c->device & 63]) {   // once per device: function attributes are per device
+            SBA_CUDA(cudaFuncSetAttribute(tc_knn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Scheme<2>::SMEM_BYTES));
+            smem_attr_done[2][c->device & 63] = true;
+        }
         SBA_CUDA(launch_pdl(c->pdl, tc_knn_kernel<2>, dim3(part.n_ctas), dim3(THREADS), Scheme<2>::SMEM_BYTES, st, map_a, map_b, d_nb, part, d_cv, d_ci, slots));
     } else {
-        SBA_CUDA(cudaFuncSetAttribute(tc_knn_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Scheme<3>::SMEM_BYTES));
+        if (!smem_attr_done[3][c->device & 63]) {   // once per device: function attributes are per device
+            SBA_CUDA(cudaFuncSetAttribute(tc_knn_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Scheme<3>::SMEM_BYTES));
+            smem_attr_done[3][c->device & 63] = true;
+        }
         SBA_CUDA(launch_pdl(c->pdl, tc_knn_kernel<3>, dim3(part.n_ctas), dim3(THREADS), Scheme<3>::SMEM_BYTES, st, map_a, map_b, d_nb, part, d_cv, d_ci, slots));
     }
     prof_end(c, SBA_KERNEL_MATCH);
