@@ -548,7 +548,8 @@ int build_tiled_plan(sba_ctx* c, const int32_t* lut, int rows, int cols, int w, 
             if ((variant == 1 && !tp.tiles) || (variant == 2 && !tp.sorted)) { tp.trial_ms[cls][variant] = 0.f; continue; }
             c->remap_kernel = variant + 1;
             float best = 1e30f;
-            for (int rep = 0; rep < 4 && rc == SBA_OK; rep++) {
+            const int reps = cls == 0 ? 9 : 4;   // the 2-frame launches are ~35 us each: more of them, the minimum is what counts
+            for (int rep = 0; rep < reps && rc == SBA_OK; rep++) {
                 cudaEventRecord(e0, c->stream);
                 rc = launch_lut_gather(c, c->scratch[SCR_WORK3].as<uint8_t>(), (int64_t)src_bytes, lut, rows, cols, c->scratch[SCR_WORK4].as<uint8_t>(),
                                        frames, masked, &tp, w);
@@ -560,9 +561,9 @@ int build_tiled_plan(sba_ctx* c, const int32_t* lut, int rows, int cols, int w, 
             }
             tp.trial_ms[cls][variant] = best;
         }
-        // a challenger has to win by 5 % to displace the direct gather
+        // a challenger has to win by 3 % to displace the direct gather
         tp.best[cls] = 1;
-        float best_ms = 0.95f * tp.trial_ms[cls][0];
+        float best_ms = 0.97f * tp.trial_ms[cls][0];
         for (int variant = 1; variant < 3; variant++)
             if (tp.trial_ms[cls][variant] > 0.f && tp.trial_ms[cls][variant] < best_ms) { best_ms = tp.trial_ms[cls][variant]; tp.best[cls] = variant + 1; }
         tp.preferred[cls] = tp.best[cls] == 2;
