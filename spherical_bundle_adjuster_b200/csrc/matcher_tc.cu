@@ -134,6 +134,46 @@ __device__ __forceinline__ void tcgen05_commit(uint64_t* bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants: two CTAs of one cluster (one TPC) run every MMA together -- M = 256, each CTA's tensor
+// core works on its own 128 rows of A, the B operand is split in halves of 64 columns, one half in each CTA's shared memory,
+// and read ONCE for both tensor cores.  Barriers that gate the MMA issue live in the even CTA (the leader, the only one that
+// issues); an address of the executing CTA with the peer bit cleared names the leader's copy of the same object.
+constexpr uint32_t PEER_BIT = 0x01000000u;
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_leader(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(smem_u32(bar) & ~PEER_BIT), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & ~PEER_BIT) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_peer(uint64_t* bar)   // called by the leader: the odd CTA's copy
+{
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) | PEER_BIT) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"((uint64_t)map), "r"(smem_u32(bar) & ~PEER_BIT), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_pair(uint64_t* bar)   // arrives on the barrier at this offset in BOTH CTAs
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -144,6 +184,17 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// The same issued for a CTA pair: M256 (128 rows in each CTA) x N128 (64 columns from each CTA's shared memory) x K16.
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
@@ -165,6 +216,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr)
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 // the same with fp16 operands (A / B format fields 0)
 constexpr uint32_t IDESC_F16 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// CTA pair: M = 256
+constexpr uint32_t IDESC_PAIR = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+constexpr uint32_t IDESC_F16_PAIR = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
 #define TMEM_LD_X32(r, taddr)                                                                                                  \
     asm volatile(                                                                                                              \
@@ -394,7 +448,11 @@ __device__ __forceinline__ unsigned long long gtime()
 #define TC_TRACE(slot) do { } while (0)
 #endif
 
-template <int P>
+// PAIR: the CTAs 2p and 2p+1 form a cluster and walk ONE span of (query super-block, train tile) together: CTA rank r owns query
+// block 2 * super-block + r (its own A operand, accumulators, epilogue and candidate lists, exactly as in the single-CTA kernel)
+// and loads rows 64r .. 64r+63 of every train tile; the leader (rank 0) issues cta_group::2 MMAs for both.  The partition,
+// the list slots and the re-rank's span table are then in units of pairs and super-blocks (`part` arrives in those units).
+template <int P, bool PAIR = false>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const float* __restrict__ nb,
               Partition part, float4* __restrict__ cand_v, int4* __restrict__ cand_id, int slots)
@@ -422,26 +480,37 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     pdl_trigger();
     if (threadIdx.x == 0) TC_TRACE(0);   // CTA start
+    const int rank = PAIR ? (int)cluster_ctarank() : 0;             // CTA inside its pair
+    const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // what the partition counts: pairs or CTAs
+    const int qmul = PAIR ? 2 : 1;                                   // query blocks per partition block
     // this CTA's span of tiles, walked with 32-bit incremental (query block, train tile) indices
-    const int t_begin = (int)part.start(blockIdx.x), n_tiles = (int)part.start(blockIdx.x + 1) - t_begin;
+    const int t_begin = (int)part.start(unit), n_tiles = (int)part.start(unit + 1) - t_begin;
     const int ntb = part.ntb;
     const int qb0 = t_begin / ntb, tb0 = t_begin - qb0 * ntb;
 
     if (threadIdx.x == 0) {
-        mbar_init(a_full, 1);
+        // pair mode: the leader's "full" barriers collect one arrival (+ its bytes) from each CTA's producer, its accumulator
+        // "empty" barriers one from every epilogue warp of both CTAs; "empty" / "ready" signals go out to both CTAs at once
+        mbar_init(a_full, PAIR ? 2 : 1);
         mbar_init(a_empty, 2);   // one arrival per MMA issuer warp
-        for (int s = 0; s < STAGES; s++) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
-        for (int s = 0; s < 4; s++) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, EPI_WARPS / 2); }
+        for (int s = 0; s < STAGES; s++) { mbar_init(b_full + s, PAIR ? 2 : 1); mbar_init(b_empty + s, 1); }
+        for (int s = 0; s < 4; s++) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, PAIR ? EPI_WARPS : EPI_WARPS / 2); }
         mbar_init(turn + 0, 1);
         mbar_init(turn + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();   // the peer's barriers exist before anything arrives on them
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();   // barriers and TMEM are set up; the operands (tc_prep_kernel's output) are touched only from here on
@@ -456,9 +525,16 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             for (int n = 0; n < n_tiles; n++) {
                 if (new_seg) {
                     mbar_wait(a_empty, (seg & 1) ^ 1);
-                    mbar_expect_tx(a_full, SMEM_A);
-                    tma_load_2d(sA, &map_a, a_full, 0, qb * BM);
-                    if (P != 1) tma_load_2d(sA + A_KBLOCK_BYTES, &map_a, a_full, 64, qb * BM);
+                    const int arow = (qb * qmul + rank) * BM;   // this CTA's own query block
+                    if (PAIR) {
+                        mbar_expect_tx_leader(a_full, SMEM_A);
+                        tma_load_2d_pair(sA, &map_a, a_full, 0, arow);
+                        if (P != 1) tma_load_2d_pair(sA + A_KBLOCK_BYTES, &map_a, a_full, 64, arow);
+                    } else {
+                        mbar_expect_tx(a_full, SMEM_A);
+                        tma_load_2d(sA, &map_a, a_full, 0, arow);
+                        if (P != 1) tma_load_2d(sA + A_KBLOCK_BYTES, &map_a, a_full, 64, arow);
+                    }
                     seg++;
                 }
                 mbar_wait(b_empty + s, ring_phase ^ 1);
@@ -466,10 +542,16 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 if (n >= STAGES) { mbar_arrive(b_full + s); } else
 #endif
                 {
-                mbar_expect_tx(b_full + s, B_STAGE_BYTES);
                 uint8_t* dst = sB + s * B_STAGE_BYTES;
-                tma_load_2d(dst, &map_b, b_full + s, 0, tb * BN);
-                if (P != 1) tma_load_2d(dst + B_KBLOCK_BYTES, &map_b, b_full + s, 64, tb * BN);
+                if (PAIR) {   // this CTA's half of the tile (map_b is the 64-row box here): rows 0..63 of each k-block's region
+                    mbar_expect_tx_leader(b_full + s, B_STAGE_BYTES / 2);
+                    tma_load_2d_pair(dst, &map_b, b_full + s, 0, tb * BN + rank * (BN / 2));
+                    if (P != 1) tma_load_2d_pair(dst + B_KBLOCK_BYTES, &map_b, b_full + s, 64, tb * BN + rank * (BN / 2));
+                } else {
+                    mbar_expect_tx(b_full + s, B_STAGE_BYTES);
+                    tma_load_2d(dst, &map_b, b_full + s, 0, tb * BN);
+                    if (P != 1) tma_load_2d(dst + B_KBLOCK_BYTES, &map_b, b_full + s, 64, tb * BN);
+                }
                 }
                 if (++s == STAGES) { s = 0; ring_phase ^= 1; }
                 new_seg = (++tb == ntb);
@@ -477,14 +559,23 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             }
         }
         __syncwarp();
-    } else if (warp == 1 || warp == 2) {
-        // ===== MMA issuers: warp 1 takes the even tiles of the span (accumulator stage 0), warp 2 the odd ones =====
+    } else if ((warp == 1 || warp == 2) && rank == 0) {
+        // ===== MMA issuers (pair mode: in the leader CTA only): warp 1 takes the even tiles of the span (accumulator stage 0), warp 2 the odd ones =====
         // The tensor pipe's queue is shallow: measured with the probe builds (Makefile `trace EXP=...`), a single
         // issuing warp costs 0.27 us of idle pipe per tile -- its barrier waits, fences and commits -- on top of
         // 35 ns per MMA.  Two issuers hide each other's per-tile overhead; tiles are independent (own accumulator
         // stage, own B stage), so no ordering between the two warps is needed.
         // Each warp walks the tile loop in lock-step (waits included) so every descriptor is warp-uniform and
         // lives in uniform registers; only the tcgen05 instructions themselves are issued by one elected lane.
+        constexpr uint32_t ID_BF = PAIR ? IDESC_PAIR : IDESC, ID_F16 = PAIR ? IDESC_F16_PAIR : IDESC_F16;
+        auto UMMA = [](uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+            if (PAIR) umma_bf16_pair(d, da, db, idesc, accumulate);
+            else umma_bf16(d, da, db, idesc, accumulate);
+        };
+        auto COMMIT = [](uint64_t* bar) {
+            if (PAIR) tcgen05_commit_pair(bar);
+            else tcgen05_commit(bar);
+        };
         uint32_t is_leader;
         asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(is_leader));
         const int my_parity = warp - 1;
@@ -518,39 +609,39 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 if (is_leader) {
                     // hi.hi + hi.lo + lo.hi ; each 64-wide k-block is four K=16 steps, 32 B apart
 #pragma unroll
-                    for (int k = 0; k < 4; k++) umma_bf16(d0, dA_hi0 + 2 * k, dB_hi + 2 * k, P == 3 ? IDESC : IDESC_F16, k > 0);
+                    for (int k = 0; k < 4; k++) UMMA(d0, dA_hi0 + 2 * k, dB_hi + 2 * k, P == 3 ? ID_BF : ID_F16, k > 0);
 #ifndef SBA_TC_EXP_1PROD   // experiment (trace builds): one product only -- WRONG results, timing probe
                     if (P == 3) {
 #pragma unroll
-                        for (int k = 0; k < 4; k++) umma_bf16(d0, dA_hi0 + 2 * k, dB_lo + 2 * k, IDESC, 1);
+                        for (int k = 0; k < 4; k++) UMMA(d0, dA_hi0 + 2 * k, dB_lo + 2 * k, ID_BF, 1);
 #pragma unroll
-                        for (int k = 0; k < 4; k++) umma_bf16(d0, dA_lo0 + 2 * k, dB_hi + 2 * k, IDESC, 1);
+                        for (int k = 0; k < 4; k++) UMMA(d0, dA_lo0 + 2 * k, dB_hi + 2 * k, ID_BF, 1);
                     } else if (P == 2) {   // second half of the 128-long rows
 #pragma unroll
-                        for (int k = 0; k < 4; k++) umma_bf16(d0, dA_lo0 + 2 * k, dB_lo + 2 * k, IDESC_F16, 1);
+                        for (int k = 0; k < 4; k++) UMMA(d0, dA_lo0 + 2 * k, dB_lo + 2 * k, ID_F16, 1);
                     }
 #endif
-                    tcgen05_commit(acc_full + 2 * acc);      // row-half 0 ready for its epilogue warps
+                    COMMIT(acc_full + 2 * acc);      // row-half 0 ready for its epilogue warps
                 }
                 mbar_wait(acc_empty + 2 * acc + 1, (uint32_t)(((n >> 1) & 1) ^ 1));
                 tcgen05_fence_after();
                 if (is_leader) {
 #pragma unroll
-                    for (int k = 0; k < 4; k++) umma_bf16(d1, dA_hi1 + 2 * k, dB_hi + 2 * k, P == 3 ? IDESC : IDESC_F16, k > 0);
+                    for (int k = 0; k < 4; k++) UMMA(d1, dA_hi1 + 2 * k, dB_hi + 2 * k, P == 3 ? ID_BF : ID_F16, k > 0);
 #ifndef SBA_TC_EXP_1PROD
                     if (P == 3) {
 #pragma unroll
-                        for (int k = 0; k < 4; k++) umma_bf16(d1, dA_hi1 + 2 * k, dB_lo + 2 * k, IDESC, 1);
+                        for (int k = 0; k < 4; k++) UMMA(d1, dA_hi1 + 2 * k, dB_lo + 2 * k, ID_BF, 1);
 #pragma unroll
-                        for (int k = 0; k < 4; k++) umma_bf16(d1, dA_lo1 + 2 * k, dB_hi + 2 * k, IDESC, 1);
+                        for (int k = 0; k < 4; k++) UMMA(d1, dA_lo1 + 2 * k, dB_hi + 2 * k, ID_BF, 1);
                     } else if (P == 2) {
 #pragma unroll
-                        for (int k = 0; k < 4; k++) umma_bf16(d1, dA_lo1 + 2 * k, dB_lo + 2 * k, IDESC_F16, 1);
+                        for (int k = 0; k < 4; k++) UMMA(d1, dA_lo1 + 2 * k, dB_lo + 2 * k, ID_F16, 1);
                     }
 #endif
                     mbar_arrive(turn + (my_parity ^ 1));     // the other issuer may queue the next tile
-                    tcgen05_commit(b_empty + s);             // B stage free once these MMAs have read it
-                    tcgen05_commit(acc_full + 2 * acc + 1);  // row-half 1 ready
+                    COMMIT(b_empty + s);             // B stage free once these MMAs have read it
+                    COMMIT(acc_full + 2 * acc + 1);  // row-half 1 ready
                 }
                 issued_in_block = true;
             }
@@ -560,8 +651,11 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             if (new_seg || n + 1 == n_tiles) {   // last tile of this query block in the span: A may be overwritten once BOTH
                                                  // warps' MMAs on it are complete (a_empty counts two arrivals)
                 if (is_leader) {
-                    if (issued_in_block) tcgen05_commit(a_empty);
-                    else mbar_arrive(a_empty);   // this warp had no tile in the block
+                    if (issued_in_block) COMMIT(a_empty);
+                    else {                       // this warp had no tile in the block
+                        mbar_arrive(a_empty);
+                        if (PAIR) mbar_arrive_peer(a_empty);
+                    }
                 }
                 issued_in_block = false;
             }
@@ -615,7 +709,10 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             // release the accumulator stage as soon as its values sit in registers
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty + 2 * acc + half);
+            if (lane == 0) {
+                if (PAIR) mbar_arrive_leader(acc_empty + 2 * acc + half);
+                else mbar_arrive(acc_empty + 2 * acc + half);
+            }
 #ifdef SBA_TC_EXP_NOEPI   // experiment (trace builds): accumulators are read and dropped -- WRONG results, timing probe
             if (buf[0] == 0x12345678u && buf[63] == 0x9abcdef0u) key[0] = 0.f;
 #else
@@ -676,8 +773,8 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 chunk_base = tb_next * (BN / CHUNK) + csub * 8;
             }
             if (block_end) {   // publish
-                const int slot = ((int)blockIdx.x - part.cta_of((long long)qb * ntb)) * SUBSLOTS + csub;
-                const size_t o = ((size_t)qb * BM + row) * slots + slot;
+                const int slot = (unit - part.cta_of((long long)qb * ntb)) * SUBSLOTS + csub;
+                const size_t o = ((size_t)(qb * qmul + rank) * BM + row) * slots + slot;
                 float pv[NCAND];
 #pragma unroll
                 for (int i = 0; i < NCAND; i++)
@@ -698,9 +795,11 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 #ifdef SBA_TC_TRACE
     if (threadIdx.x == 0) g_tc_trace[(blockIdx.x % 148) * 16 + 8] = (unsigned long long)n_tiles;
 #endif
+    if (PAIR) cluster_sync_all();   // neither CTA leaves (or frees TMEM) while the pair's MMAs and signals may still touch it
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -1061,9 +1160,10 @@ int knn2_prepare_set(sba_ctx* c, const float* d_raw, int n, int n_pad, __nv_bflo
 
 // Per query block the first and last CTA whose span holds tiles of it (the re-rank merges exactly those CTAs' lists).  The table
 // depends on the partition only, so it is built on the host once per geometry and cached in the context.
-static int span_table(sba_ctx* c, const tc::Partition& part, const int2** out)
+// pair mode: the partition counts CTA pairs and super-blocks of two query blocks; the table still has one entry per query block.
+static int span_table(sba_ctx* c, const tc::Partition& part, int n_query_blocks, bool pair, const int2** out)
 {
-    const auto key = std::make_tuple(part.nqb, part.ntb, part.n_ctas, part.bcost);
+    const auto key = std::make_tuple(pair ? -n_query_blocks : n_query_blocks, part.ntb, part.n_ctas, part.bcost);
     auto it = c->tc_spans.find(key);
     if (it == c->tc_spans.end()) {
         if (c->tc_spans.size() >= 256) {   // a sweep over many sizes: start over rather than grow without bound
@@ -1071,10 +1171,11 @@ static int span_table(sba_ctx* c, const tc::Partition& part, const int2** out)
             for (auto& kv : c->tc_spans) cudaFree(kv.second.second);
             c->tc_spans.clear();
         }
-        std::vector<int> host((size_t)2 * part.nqb);
-        for (int qb = 0; qb < part.nqb; qb++) {
-            host[2 * qb] = part.cta_of((long long)qb * part.ntb);
-            host[2 * qb + 1] = part.cta_of((long long)(qb + 1) * part.ntb - 1);
+        std::vector<int> host((size_t)2 * n_query_blocks);
+        for (int qb = 0; qb < n_query_blocks; qb++) {
+            const int pb = pair ? qb / 2 : qb;   // the partition's block this query block belongs to
+            host[2 * qb] = part.cta_of((long long)pb * part.ntb);
+            host[2 * qb + 1] = part.cta_of((long long)(pb + 1) * part.ntb - 1);
         }
         int* dev = nullptr;
         SBA_CUDA(cudaMalloc(&dev, host.size() * sizeof(int)));
@@ -1083,6 +1184,34 @@ static int span_table(sba_ctx* c, const tc::Partition& part, const int2** out)
         SBA_CUDA(cudaMemcpyAsync(dev, it->second.first.data(), it->second.first.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     }
     *out = reinterpret_cast<const int2*>(it->second.second);
+    return SBA_OK;
+}
+
+// One launch of the distance kernel: single CTAs, or clusters of two (pair mode; `part` then counts pairs).
+template <int P>
+static int launch_knn(sba_ctx* c, bool pair, const tc::Partition& part, cudaStream_t st, const CUtensorMap& map_a, const CUtensorMap& map_b, const float* d_nb,
+                      float4* d_cv, int4* d_ci, int slots)
+{
+    using namespace tc;
+    static bool attr_done[2][64] = {};   // function attributes are per device
+    if (!attr_done[pair ? 1 : 0][c->device & 63]) {
+        if (pair) SBA_CUDA(cudaFuncSetAttribute(tc_knn_kernel<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Scheme<P>::SMEM_BYTES));
+        else SBA_CUDA(cudaFuncSetAttribute(tc_knn_kernel<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Scheme<P>::SMEM_BYTES));
+        attr_done[pair ? 1 : 0][c->device & 63] = true;
+    }
+    if (!pair) {
+        SBA_CUDA(launch_pdl(c->pdl, tc_knn_kernel<P, false>, dim3(part.n_ctas), dim3(THREADS), Scheme<P>::SMEM_BYTES, st, map_a, map_b, d_nb, part, d_cv, d_ci, slots));
+        return SBA_OK;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.gridDim = dim3(2 * part.n_ctas); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = Scheme<P>::SMEM_BYTES; cfg.stream = st;
+    cfg.attrs = at; cfg.numAttrs = c->pdl ? 2 : 1;
+    SBA_CUDA(cudaLaunchKernelEx(&cfg, tc_knn_kernel<P, true>, map_a, map_b, d_nb, part, d_cv, d_ci, slots));
     return SBA_OK;
 }
 
@@ -1102,9 +1231,15 @@ int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, 
     cudaStream_t st = c->stream;
     const int nqb = (nq + BM - 1) / BM, ntb = (nt + BN - 1) / BN;
     const int nq_pad = pq ? pq->n_pad : nqb * BM, nt_pad = pt ? pt->n_pad : ntb * BN;
+    // CTA-pair mode (cta_group::2 MMAs: each B half is read from shared memory once for both SMs' tensor cores -- the kernel is
+    // bound by shared-memory bandwidth): the partition then counts pairs and super-blocks of two query blocks
+    static const int pair_env = std::getenv("SBA_TC_PAIR") ? atoi(std::getenv("SBA_TC_PAIR")) : 1;   // SBA_TC_PAIR=0: single-CTA kernel everywhere
+    const int ctas_avail = c->matcher_ctas > 0 ? std::min(c->matcher_ctas, c->sm_count) : c->sm_count;
+    const bool pair = pair_env != 0 && ctas_avail >= 2 && ctas_avail % 2 == 0 && nqb >= 2;   // an odd CTA budget is honoured exactly by single CTAs
+    const int npb = pair ? (nqb + 1) / 2 : nqb;   // blocks the partition counts
     Partition part;
-    part.nqb = nqb; part.ntb = ntb; part.T = (long long)nqb * ntb;
-    part.n_ctas = (int)std::min<long long>(c->matcher_ctas > 0 ? std::min(c->matcher_ctas, c->sm_count) : c->sm_count, part.T);
+    part.nqb = npb; part.ntb = ntb; part.T = (long long)npb * ntb;
+    part.n_ctas = (int)std::min<long long>(pair ? ctas_avail / 2 : ctas_avail, part.T);
     // measured with the trace build at 16k x 16k: spans that cross into a new query block finish ~8 us (5-6 tiles) late;
     // capped so that no span can come out empty
     static const int bcost_max = std::getenv("SBA_TC_BCOST") ? std::max(0, atoi(std::getenv("SBA_TC_BCOST"))) : 5;   // tuning knob (tiles)
@@ -1119,8 +1254,9 @@ int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, 
     const size_t o_b = off; off = align_up(off + (size_t)nt_pad * row_bytes);
     const size_t o_na = off; off = align_up(off + (size_t)nq_pad * 4);
     const size_t o_nb = off; off = align_up(off + (size_t)nt_pad * 4);
-    const size_t o_cv = off; off = align_up(off + (size_t)nq_pad * slots * 16);
-    const size_t o_ci = off; off = align_up(off + (size_t)nq_pad * slots * 16);
+    const size_t cand_rows = std::max<size_t>((size_t)nq_pad, (size_t)npb * (pair ? 2 : 1) * BM);   // pair mode: an odd last block still has a (padding) partner
+    const size_t o_cv = off; off = align_up(off + cand_rows * slots * 16);
+    const size_t o_ci = off; off = align_up(off + cand_rows * slots * 16);
     const size_t o_fl = off; off = align_up(off + (size_t)nq * 4);
     const int fb_grid = 2 * c->sm_count;
     // >= n_rows * fb_splits(n_rows, fb_grid) for every n_rows <= nq: FB_MAX_SPLIT lists per row while the queue is short, then ~fb_grid * FB_ROWS + n_rows
@@ -1139,7 +1275,7 @@ int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, 
     Top2* d_fparts = (Top2*)(ws + o_fp);
     int* d_fb_count = (int*)(ws + o_misc);
     const int2* d_span = nullptr;
-    SBA_TRY(span_table(c, part, &d_span));
+    SBA_TRY(span_table(c, part, nqb, pair, &d_span));
     const float* d_nbmax = pt ? pt->max_norm : (const float*)(ws + o_misc + 4);
     float* d_dbg = (float*)(ws + o_misc + 8);
     const float* d_namax = pq ? pq->max_norm : (const float*)(ws + o_misc + 12);
@@ -1159,30 +1295,13 @@ int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, 
         SBA_LAUNCHED(c);
     }
 
-    static bool smem_attr_done[4][64] = {};
     CUtensorMap map_a, map_b;
     SBA_TRY(make_map(&map_a, (void*)dA, nq_pad, BM, row_bytes / 2));
-    SBA_TRY(make_map(&map_b, (void*)dB, nt_pad, BN, row_bytes / 2));
+    SBA_TRY(make_map(&map_b, (void*)dB, nt_pad, pair ? BN / 2 : BN, row_bytes / 2));   // pair mode: each CTA loads half a tile
     prof_begin(c, SBA_KERNEL_MATCH);
-    if (mode == 1) {
-        if (!smem_attr_done[1][c->device & 63]) {   // once per device: function attributes are per device
-            SBA_CUDA(cudaFuncSetAttribute(tc_knn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Scheme<1>::SMEM_BYTES));
-            smem_attr_done[1][c->device & 63] = true;
-        }
-        SBA_CUDA(launch_pdl(c->pdl, tc_knn_kernel<1>, dim3(part.n_ctas), dim3(THREADS), Scheme<1>::SMEM_BYTES, st, map_a, map_b, d_nb, part, d_cv, d_ci, slots));
-    } else if (mode == 2) {
-        if (!smem_attr_done[2][c->device & 63]) {   // once per device: function attributes are per device
-            SBA_CUDA(cudaFuncSetAttribute(tc_knn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Scheme<2>::SMEM_BYTES));
-            smem_attr_done[2][c->device & 63] = true;
-        }
-        SBA_CUDA(launch_pdl(c->pdl, tc_knn_kernel<2>, dim3(part.n_ctas), dim3(THREADS), Scheme<2>::SMEM_BYTES, st, map_a, map_b, d_nb, part, d_cv, d_ci, slots));
-    } else {
-        if (!smem_attr_done[3][c->device & 63]) {   // once per device: function attributes are per device
-            SBA_CUDA(cudaFuncSetAttribute(tc_knn_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Scheme<3>::SMEM_BYTES));
-            smem_attr_done[3][c->device & 63] = true;
-        }
-        SBA_CUDA(launch_pdl(c->pdl, tc_knn_kernel<3>, dim3(part.n_ctas), dim3(THREADS), Scheme<3>::SMEM_BYTES, st, map_a, map_b, d_nb, part, d_cv, d_ci, slots));
-    }
+    if (mode == 1) SBA_TRY(launch_knn<1>(c, pair, part, st, map_a, map_b, d_nb, d_cv, d_ci, slots));
+    else if (mode == 2) SBA_TRY(launch_knn<2>(c, pair, part, st, map_a, map_b, d_nb, d_cv, d_ci, slots));
+    else SBA_TRY(launch_knn<3>(c, pair, part, st, map_a, map_b, d_nb, d_cv, d_ci, slots));
     prof_end(c, SBA_KERNEL_MATCH);
     SBA_LAUNCHED(c);
     SBA_CUDA(cudaGetLastError());
@@ -1205,8 +1324,8 @@ int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, 
     SBA_CUDA(cudaGetLastError());
     // diagnostics (the three words at d_fb_count) reach the pinned mailbox through knn2_finalize_kernel; sba_match_last_stats reads
     // them after a synchronise
-    c->match_stats.n_tiles = (int)part.T;
-    c->match_stats.n_ctas = part.n_ctas;
+    c->match_stats.n_tiles = (int)((long long)nqb * ntb);                 // 256 x 128 tiles, whatever the partition counts
+    c->match_stats.n_ctas = pair ? 2 * part.n_ctas : part.n_ctas;
     c->match_stats.n_fallback_rows = -1;  // resolved lazily from the mailbox
     return SBA_OK;
 }

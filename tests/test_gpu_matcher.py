@@ -43,7 +43,7 @@ def test_matcher_matches_cv2_golden(ctx, golden_dir, name, algo):
 
 
 @pytest.mark.parametrize("algo", ALGOS)
-@pytest.mark.parametrize("nq,nt,dim", [(1000, 1000, 64), (777, 1301, 64), (130, 4097, 64), (2048, 300, 128), (5000, 3000, 64), (3000, 4100, 128)])
+@pytest.mark.parametrize("nq,nt,dim", [(1000, 1000, 64), (777, 1301, 64), (130, 4097, 64), (2048, 300, 128), (5000, 3000, 64), (3000, 4100, 128), (700, 2000, 64), (1290, 900, 128)])
 def test_matcher_matches_oracle(ctx, nq, nt, dim, algo):
     A, B, _ = synth.make_descriptors(nq, nt, dim, seed=nq + nt)
     _check(_match(ctx, A, B, 0.3, algo, want_knn=True), A, B)
