@@ -98,7 +98,8 @@ int sba_equi2cube_face(sba_ctx* ctx, const uint8_t* erp, int w, int h, int cube_
  * sba_remap_plan_info reports what the trials of a cube plan found: tiled_preferred bit 0 = small batches, bit 1 = large;
  * trial_ms = {small direct, small tiled, large direct, large tiled}. */
 int sba_ctx_set_remap_kernel(sba_ctx* ctx, int mode);
-/* Persistent CTAs of the tensor-core matcher (one per SM by default; 0 restores that).  With several pairs in flight on
+/* Persistent CTAs of the tensor-core matcher (one per SM by default; 0 restores that).  An even budget runs the distance kernel
+ * as CTA pairs (cta_group::2 MMAs, two SMs share every train tile), an odd one as single CTAs; env SBA_TC_PAIR=0 forces single CTAs.  With several pairs in flight on
  * one GPU, half the SMs per match lets two matches run side by side on longer spans. */
 int sba_ctx_set_matcher_ctas(sba_ctx* ctx, int n_ctas);
 /* Programmatic dependent launch along the kernel chain of a match / a pair (prep -> distance kernel -> re-rank -> fallback ->
