@@ -52,7 +52,7 @@ constexpr int STAGES = 4;          // B smem ring
 constexpr int EPI_WARPS = 16;      // 4 TMEM lane quarters x 4 column slices
 constexpr int SUBSLOTS = 2;        // candidate lists per query row per CTA span (2 column slices per row-half)
 constexpr int EPI_WARP0 = 3;      // first epilogue warp
-constexpr int THREADS = (EPI_WARP0 + EPI_WARPS) * 32;   // warp0 TMA, warps 1-2 MMA issuers (even / odd tiles), warps 3-18 epilogue: 608 threads -> 104 registers each
+constexpr int THREADS = (EPI_WARP0 + EPI_WARPS) * 32;   // warp0 TMA, warps 1-2 MMA issuers (even / odd tiles), warps 3-18 epilogue: 608 threads -> a budget of 104 registers each (95-96 used)
 constexpr int A_KBLOCK_BYTES = BM * 128;   // one 64-wide 16-bit k-block of A: 32 KB
 constexpr int B_KBLOCK_BYTES = BN * 128;   // 16 KB
 // Two filter schemes, template parameter P = tensor products per result:
