@@ -940,28 +940,27 @@ tc_rerank_kernel(const float* __restrict__ q, int nq, const float* __restrict__ 
         const bool need = !final_row;
         if (phase == 1 && !__any_sync(0xffffffffu, need)) break;   // the common case: every row of the warp was settled by phase 0
         // b) the 16 candidate rows of this phase (chunks 2*phase, 2*phase + 1), fetched COOPERATIVELY -- for each row the 16
-        //    threads of the group read its 256 contiguous bytes as one float4 each, so a load instruction touches 4 lines per
-        //    warp instead of 32 -- parked in shared memory (row stride 68 floats: the float4 reads below are conflict free).
-        {
-            float4 stage[8][V4];
+        //    threads of the group copy its 256 contiguous bytes as one 16-byte piece each, so a request touches 4 lines per
+        //    warp instead of 32 -- straight into shared memory with cp.async (row stride 68 floats: the float4 reads below are
+        //    conflict free): all 16 rows are in flight together and no register holds them on the way (staging them through
+        //    registers, eight rows at a time, cost two dependent round trips and 32 registers).
 #pragma unroll
-            for (int half = 0; half < 2; half++) {
-                const int cid = win_id[grp][2 * phase + half];
+        for (int half = 0; half < 2; half++) {
+            const int cid = win_id[grp][2 * phase + half];
 #pragma unroll
-                for (int cc = 0; cc < 8; cc++) {
-                    const int cj = cid * CHUNK + cc;
-                    const bool ok = need && cid >= 0 && cj < nt;
+            for (int cc = 0; cc < 8; cc++) {
+                const int cj = cid * CHUNK + cc;
+                const bool ok = need && cid >= 0 && cj < nt;
 #pragma unroll
-                    for (int v = 0; v < V4; v++)
-                        stage[cc][v] = ok ? __ldg(reinterpret_cast<const float4*>(t + (size_t)cj * D) + e + 16 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int v = 0; v < V4; v++) {
+                    const float* src = ok ? t + (size_t)cj * D + 4 * (e + 16 * v) : t;   // nothing is read when ok is false (zero fill)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(&ts[grp][half * 8 + cc][4 * (e + 16 * v)])), "l"(src),
+                                 "r"(ok ? 16 : 0)
+                                 : "memory");
                 }
-                __syncwarp();
-#pragma unroll
-                for (int cc = 0; cc < 8; cc++)
-#pragma unroll
-                    for (int v = 0; v < V4; v++) *reinterpret_cast<float4*>(&ts[grp][half * 8 + cc][4 * (e + 16 * v)]) = stage[cc][v];
             }
         }
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
         __syncwarp();
         const int chunk = win_id[grp][2 * phase + (e >> 3)];
         const float chunk_v = win_v[grp][2 * phase + (e >> 3)];
