@@ -149,12 +149,15 @@ __global__ void knn2_merge_splits_kernel(const Top2* __restrict__ parts, int nq,
 }
 
 // Ratio test (feature_matcher.cpp:47-56) + ordered compaction of the survivors in ONE launch (knn2_finalize_kernel):
-// 1024 queries per CTA.  Every CTA publishes its survivor count tagged with the call's epoch, then sums the counts of
+// FIN_THREADS queries per CTA.  Every CTA publishes its survivor count tagged with the call's epoch, then sums the counts of
 // the CTAs before it (spinning only on counts that are not there yet -- all of them are written within a microsecond of
 // the launch, so this is one hop, not a chain), scans its own flags and scatters: survivors stay in ascending query
 // order.  Rows the tensor path queued for the exact fallback arrive as a marker in `top` (i0 == KNN_FALLBACK, i1 =
 // position in the queue) and their partial top-2 lists (one per scanned range) are merged here in range order.
-constexpr int FIN_THREADS = 1024;
+#ifndef SBA_FIN_THREADS
+#define SBA_FIN_THREADS 1024
+#endif
+constexpr int FIN_THREADS = SBA_FIN_THREADS;   // queries per CTA (measured: 1024 -> 6.4 us for 16 384 rows under ncu, 256 -> 8.4 us)
 constexpr int FIN_EPOCH_SHIFT = 11;   // counts are <= 1024
 
 __device__ inline int keep_flag(const Top2& r, float ratio)
@@ -209,7 +212,7 @@ knn2_finalize_kernel(const Top2* __restrict__ top, int nq, float ratio, int32_t*
     __syncthreads();
     int total = 0;
     if (warp == 0) {
-        const int v = warp_off[lane];
+        const int v = lane < FIN_THREADS / 32 ? warp_off[lane] : 0;
         int incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
