@@ -106,7 +106,8 @@ int sba_ctx_set_matcher_ctas(sba_ctx* ctx, int n_ctas);
  * finalize -> pair solve): each kernel is scheduled while its predecessor drains and waits on the device before touching
  * memory.  A latency knob: one C2 pair at a time 254 -> 240 us on B200, but several pairs in flight on one GPU lose ~3 % of
  * their throughput (waiting CTAs keep other pairs' kernels off their SMs), so it is off by default (env SBA_PDL=1 turns it
- * on for every new context).  Results are identical either way. */
+ * on for every new context).  Results are identical either way.  The three small kernels at the end of the chain (fallback,
+ * finalize, pair solve) are always launched dependent: their early CTAs occupy next to nothing. */
 int sba_ctx_set_dependent_launch(sba_ctx* ctx, int enable);
 int sba_remap_plan_info(sba_ctx* ctx, int w, int h, int cube_size, int* tiled_available, int* tiled_preferred, int* n_tiles,
                         int* n_fallback_tiles, float trial_ms[4]);

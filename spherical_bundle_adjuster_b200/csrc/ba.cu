@@ -1671,7 +1671,7 @@ int ba_pair_solve_enqueue(sba_ba_problem* p, const float* key_l, const float* ke
     attr[0].val.clusterDim.x = (unsigned)grid; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(PAIR_SOLVE_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = c->pdl ? 2 : 1;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(PAIR_SOLVE_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = (c->pdl || c->pdl_small) ? 2 : 1;
     prof_begin(c, SBA_KERNEL_BA_EVAL);
     SBA_CUDA(cudaLaunchKernelEx(&cfg, ba_pair_solve_kernel, P, A));
     prof_end(c, SBA_KERNEL_BA_EVAL);

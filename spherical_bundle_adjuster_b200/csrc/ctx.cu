@@ -58,6 +58,7 @@ int sba_ctx_create(int device, void* stream, sba_ctx** out)
         c->own_stream = true;
     }
     c->pdl = getenv("SBA_PDL") != nullptr;
+    c->pdl_small = getenv("SBA_NO_PDL_SMALL") == nullptr;   // measurement switch
     e = cudaMallocHost((void**)&c->pinned_i32, 64 * sizeof(int));
     if (e != cudaSuccess) {
         if (c->own_stream) cudaStreamDestroy(c->stream);

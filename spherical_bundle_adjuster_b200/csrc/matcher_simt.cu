@@ -264,7 +264,7 @@ int launch_knn_finish(sba_ctx* c, const Top2* d_top2, int nq, float ratio, int32
         SBA_CUDA(cudaMemsetAsync(c->scratch[SCR_FIN_COUNTS].p, 0, c->scratch[SCR_FIN_COUNTS].cap, c->stream));
         if (c->fin_epoch == 0) c->fin_epoch = 1;
     }
-    SBA_CUDA(launch_pdl(c->pdl, knn2_finalize_kernel, dim3(nblocks), dim3(FIN_THREADS), 0, c->stream, d_top2, nq, ratio, d_knn_idx, d_knn_dist, d_query_idx, d_train_idx,
+    SBA_CUDA(launch_pdl(c->pdl || c->pdl_small, knn2_finalize_kernel, dim3(nblocks), dim3(FIN_THREADS), 0, c->stream, d_top2, nq, ratio, d_knn_idx, d_knn_dist, d_query_idx, d_train_idx,
                         d_dist, d_n_matches, c->scratch[SCR_FIN_COUNTS].as<unsigned int>() + 1, c->fin_epoch, d_fb_parts, d_fb_count, fb_grid,
                         (int32_t*)c->pinned_i32));
     SBA_LAUNCHED(c);

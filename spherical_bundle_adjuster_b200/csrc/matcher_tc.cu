@@ -1311,12 +1311,12 @@ int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, 
         SBA_CUDA(launch_pdl(c->pdl, tc_rerank_kernel<64>, dim3((nq + RR<64>::ROWS - 1) / RR<64>::ROWS), dim3(RR<64>::THREADS), 0, st, d_q, nq, d_t, nt, d_na, d_nbmax, part,
                             d_cv, d_ci, slots, d_top, d_fl, d_fb_count, d_dbg, dcoef, namax, d_span));
         SBA_LAUNCHED(c);
-        SBA_CUDA(launch_pdl(c->pdl, tc_fallback_kernel<64>, dim3(fb_grid), dim3(FB_THREADS), 0, st, d_q, d_t, nt, d_fl, d_fb_count, d_fparts));
+        SBA_CUDA(launch_pdl(c->pdl || c->pdl_small, tc_fallback_kernel<64>, dim3(fb_grid), dim3(FB_THREADS), 0, st, d_q, d_t, nt, d_fl, d_fb_count, d_fparts));
     } else {
         SBA_CUDA(launch_pdl(c->pdl, tc_rerank_kernel<128>, dim3((nq + RR<128>::ROWS - 1) / RR<128>::ROWS), dim3(RR<128>::THREADS), 0, st, d_q, nq, d_t, nt, d_na, d_nbmax,
                             part, d_cv, d_ci, slots, d_top, d_fl, d_fb_count, d_dbg, dcoef, namax, d_span));
         SBA_LAUNCHED(c);
-        SBA_CUDA(launch_pdl(c->pdl, tc_fallback_kernel<128>, dim3(fb_grid), dim3(FB_THREADS), 0, st, d_q, d_t, nt, d_fl, d_fb_count, d_fparts));
+        SBA_CUDA(launch_pdl(c->pdl || c->pdl_small, tc_fallback_kernel<128>, dim3(fb_grid), dim3(FB_THREADS), 0, st, d_q, d_t, nt, d_fl, d_fb_count, d_fparts));
     }
     SBA_LAUNCHED(c);
     c->fb_parts = d_fparts; c->fb_count = d_fb_count; c->fb_grid = fb_grid;   // merged per row by knn2_finalize_kernel
