@@ -1214,6 +1214,40 @@ static int launch_knn(sba_ctx* c, bool pair, const tc::Partition& part, cudaStre
     return SBA_OK;
 }
 
+// Can this device co-schedule a cluster of two of these CTAs (a whole SM each)?  Asked once per device and scheme; a part (or a
+// partition of one) that cannot simply keeps the single-CTA kernel.
+static bool pair_launchable(int device, int mode)
+{
+    using namespace tc;
+    static int known[4][64] = {};   // 0 = not asked yet, 1 = yes, -1 = no
+    int& k = known[mode & 3][device & 63];
+    if (k == 0) {
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.gridDim = dim3(2); cfg.blockDim = dim3(THREADS); cfg.attrs = at; cfg.numAttrs = 1;
+        int n = 0;
+        cudaError_t e;
+        if (mode == 1) {
+            cfg.dynamicSmemBytes = Scheme<1>::SMEM_BYTES;
+            e = cudaFuncSetAttribute(tc_knn_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Scheme<1>::SMEM_BYTES);
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, tc_knn_kernel<1, true>, &cfg);
+        } else if (mode == 2) {
+            cfg.dynamicSmemBytes = Scheme<2>::SMEM_BYTES;
+            e = cudaFuncSetAttribute(tc_knn_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Scheme<2>::SMEM_BYTES);
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, tc_knn_kernel<2, true>, &cfg);
+        } else {
+            cfg.dynamicSmemBytes = Scheme<3>::SMEM_BYTES;
+            e = cudaFuncSetAttribute(tc_knn_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Scheme<3>::SMEM_BYTES);
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, tc_knn_kernel<3, true>, &cfg);
+        }
+        if (e != cudaSuccess) cudaGetLastError();   // not an error of the call that asked
+        k = (e == cudaSuccess && n >= 1) ? 1 : -1;
+    }
+    return k > 0;
+}
+
 // pq / pt: optional prepared forms of the query / train set (64-d only; then that side is not converted again).
 // products: 3 = bf16 split filter, 1 = fp16 filter (see tc::Scheme); 128-d descriptors always take the fp16 filter (mode 2).
 int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, int dim, Top2* d_top, const PreparedSet* pq, const PreparedSet* pt,
@@ -1234,7 +1268,8 @@ int knn2_tensor(sba_ctx* c, const float* d_q, int nq, const float* d_t, int nt, 
     // bound by shared-memory bandwidth): the partition then counts pairs and super-blocks of two query blocks
     static const int pair_env = std::getenv("SBA_TC_PAIR") ? atoi(std::getenv("SBA_TC_PAIR")) : 1;   // SBA_TC_PAIR=0: single-CTA kernel everywhere
     const int ctas_avail = c->matcher_ctas > 0 ? std::min(c->matcher_ctas, c->sm_count) : c->sm_count;
-    const bool pair = pair_env != 0 && ctas_avail >= 2 && ctas_avail % 2 == 0 && nqb >= 2;   // an odd CTA budget is honoured exactly by single CTAs
+    const bool pair = pair_env != 0 && ctas_avail >= 2 && ctas_avail % 2 == 0 && nqb >= 2 &&   // an odd CTA budget is honoured exactly by single CTAs
+                      pair_launchable(c->device, mode);
     const int npb = pair ? (nqb + 1) / 2 : nqb;   // blocks the partition counts
     Partition part;
     part.nqb = npb; part.ntb = ntb; part.T = (long long)npb * ntb;
